@@ -1,0 +1,17 @@
+"""TEST INFRASTRUCTURE ONLY -- the seeded small cases shared by golden generation and the tests."""
+from centermask2_b200.config import get_cfg, lite_overrides
+
+# name -> (cfg overrides, [(h, w), ...] image sizes, weight seed, image seed, candidates/level target)
+CASES = {
+    "v19_two_images": (["MODEL.VOVNET.CONV_BODY", "V-19-eSE"], [(96, 128), (80, 120)], 11, 21, 300),
+    "v39_one_image": ([], [(128, 160)], 12, 22, 400),
+    "v19_lite": (lite_overrides(), [(64, 96), (64, 96), (60, 90)], 13, 23, 200),
+    "v19_empty": (["MODEL.VOVNET.CONV_BODY", "V-19-eSE"], [(64, 64)], 14, 24, 0),
+    "v19_crowded": (["MODEL.VOVNET.CONV_BODY", "V-19-eSE", "MODEL.FCOS.POST_NMS_TOPK_TEST", 100],
+                    [(128, 128)], 15, 25, 3000),
+    "v99_one_image": (["MODEL.VOVNET.CONV_BODY", "V-99-eSE"], [(64, 96)], 16, 26, 300),
+}
+
+
+def case_cfg(name):
+    return get_cfg("centermask_V_39_eSE_FPN.yaml", CASES[name][0])

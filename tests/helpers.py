@@ -1,0 +1,74 @@
+"""Shared helpers for the parity tests (oracle side + comparison metrics)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle.cases import CASES, case_cfg
+from centermask2_b200.synth import synthetic_state_dict, synthetic_images
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# Tolerances stated by BASELINE.json north_star for the fp32 variant.
+BOX_TOL_PX = 1e-2
+SCORE_TOL = 1e-3
+MASK_IOU_MIN = 0.99
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+
+
+def build_case(name, gold=None):
+    """cfg, state_dict (with the golden's calibrated cls bias) and inputs of a named case."""
+    overrides, sizes, wseed, iseed, target = CASES[name]
+    cfg = case_cfg(name)
+    sd = synthetic_state_dict(cfg, seed=wseed)
+    if gold is None:
+        gold = load_golden(name)
+    key = "proposal_generator.fcos_head.cls_logits.bias"
+    sd[key] = torch.full_like(sd[key], gold["cls_bias"])
+    inputs = []
+    for i, (h, w) in enumerate(sizes):
+        inputs.extend(synthetic_images(1, h, w, seed=iseed + i))
+    return cfg, sd, inputs
+
+
+def weights_checksum(sd):
+    acc = 0.0
+    for k in sorted(sd):
+        acc += float(sd[k].double().abs().sum())
+    return acc
+
+
+def unpack_masks(post):
+    shape = post["pred_masks_shape"]
+    n = int(np.prod(shape))
+    bits = np.unpackbits(post["pred_masks_packed"].numpy())[:n]
+    return torch.from_numpy(bits.reshape(shape).astype(bool))
+
+
+def mask_iou(a, b):
+    a = a.reshape(a.shape[0], -1).bool()
+    b = b.reshape(b.shape[0], -1).bool()
+    inter = (a & b).sum(1).double()
+    union = (a | b).sum(1).double()
+    return torch.where(union > 0, inter / union.clamp(min=1), torch.ones_like(inter))
+
+
+def assert_detections_match(got, ref, box_tol=BOX_TOL_PX, score_tol=SCORE_TOL, what=""):
+    """got / ref: dicts with pred_boxes, scores, pred_classes, locations (sorted by score desc)."""
+    assert len(got["scores"]) == len(ref["scores"]), "{}: {} vs {} detections".format(
+        what, len(got["scores"]), len(ref["scores"]))
+    if len(ref["scores"]) == 0:
+        return
+    # identical kept set *and* order: class + originating location identify a candidate
+    assert torch.equal(got["pred_classes"].cpu().long(), ref["pred_classes"].long()), what + ": classes/order differ"
+    assert torch.equal(got["locations"].cpu().float(), ref["locations"].float()), what + ": locations/order differ"
+    db = (got["pred_boxes"].cpu().float() - ref["pred_boxes"].float()).abs().max().item()
+    ds = (got["scores"].cpu().float() - ref["scores"].float()).abs().max().item()
+    assert db <= box_tol, "{}: box diff {} px".format(what, db)
+    assert ds <= score_tol, "{}: score diff {}".format(what, ds)
+    if "mask_scores" in ref:
+        dm = (got["mask_scores"].cpu().float() - ref["mask_scores"].float()).abs().max().item()
+        assert dm <= score_tol, "{}: mask_score diff {}".format(what, dm)
