@@ -1,0 +1,434 @@
+// Bandwidth-bound kernels on pitched NHWC views: input normalisation, max-pool, eSE, GroupNorm, ReLU.
+// All are coalesced over the channel dimension (innermost) and vectorised 8 channels/thread.
+// Reductions are deterministic (fixed two-stage trees, no atomics).
+#include "common.cuh"
+
+namespace cm2 {
+
+// ---------------------------------------------------------------------------------------------
+// preprocess: CHW (u8 | f32) -> normalised, zero-padded HWC
+// ---------------------------------------------------------------------------------------------
+template <typename InT, typename OutT>
+__global__ void preprocess_kernel(const InT* __restrict__ img, int h, int w, float m0, float m1, float m2,
+                                  float s0, float s1, float s2, View<OutT> out, int b) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y;
+  if (x >= out.w) return;
+  OutT* q = out.at(b, y, x);
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+  if (y < h && x < w) {
+    size_t plane = (size_t)h * w;
+    size_t o = (size_t)y * w + x;
+    v0 = ((float)img[o] - m0) / s0;
+    v1 = ((float)img[plane + o] - m1) / s1;
+    v2 = ((float)img[2 * plane + o] - m2) / s2;
+  }
+  q[0] = from_f32<OutT>(v0);
+  q[1] = from_f32<OutT>(v1);
+  q[2] = from_f32<OutT>(v2);
+  for (int c = 3; c < out.c; ++c) q[c] = from_f32<OutT>(0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxPool 3x3 stride 2, ceil_mode, no padding (windows clipped at the bottom/right edge)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool3s2_kernel(View<const T> in, View<T> out) {
+  const int c8 = in.c >> 3;
+  int64_t total = (int64_t)out.n * out.h * out.w * c8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % c8);
+    int64_t pix = i / c8;
+    int ox = (int)(pix % out.w);
+    int64_t t = pix / out.w;
+    int oy = (int)(t % out.h);
+    int b = (int)(t / out.h);
+    float best[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) best[k] = -INFINITY;
+    int y0 = oy * 2, x0 = ox * 2;
+    for (int dy = 0; dy < 3; ++dy) {
+      int y = y0 + dy;
+      if (y >= in.h) break;
+      for (int dx = 0; dx < 3; ++dx) {
+        int x = x0 + dx;
+        if (x >= in.w) break;
+        float v[8];
+        Vec8<T>::load(in.at(b, y, x) + cv * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) best[k] = fmaxf(best[k], v[k]);
+      }
+    }
+    Vec8<T>::store(out.at(b, oy, ox) + cv * 8, best);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// eSE
+// ---------------------------------------------------------------------------------------------
+constexpr int ESE_PIX_PER_CHUNK = 256;
+
+// stage 1: grid (chunks, n); each thread owns 8 channels and walks the chunk's pixels.
+template <typename T>
+__global__ void ese_pool_partial_kernel(View<const T> x, int chunks, float* __restrict__ ws) {
+  int chunk = blockIdx.x, b = blockIdx.y;
+  int c8 = x.c >> 3;
+  int hw = x.h * x.w;
+  int p0 = chunk * ESE_PIX_PER_CHUNK;
+  int p1 = min(p0 + ESE_PIX_PER_CHUNK, hw);
+  for (int cv = threadIdx.x; cv < c8; cv += blockDim.x) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int y = p0 / x.w, xx = p0 - y * x.w;
+    for (int p = p0; p < p1; ++p) {
+      float v[8];
+      Vec8<T>::load(x.at(b, y, xx) + cv * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v[k];
+      if (++xx == x.w) { xx = 0; ++y; }
+    }
+    float* o = ws + ((size_t)b * chunks + chunk) * x.c + cv * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = acc[k];
+  }
+}
+
+__global__ void ese_pool_final_kernel(const float* __restrict__ ws, int chunks, int c, float inv_hw,
+                                      float* __restrict__ pooled) {
+  int b = blockIdx.y;
+  int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  float acc = 0.f;
+  for (int k = 0; k < chunks; ++k) acc += ws[((size_t)b * chunks + k) * c + ch];
+  pooled[(size_t)b * c + ch] = acc * inv_hw;
+}
+
+// gate[b, o] = relu6(sum_i W[o,i]*pooled[b,i]*inv + bias[o] + 3) / 6 ; one warp per output channel.
+__global__ void ese_gate_kernel(const float* __restrict__ pooled, float inv_count, const float* __restrict__ w,
+                                const float* __restrict__ bias, float* __restrict__ gate, int c) {
+  int b = blockIdx.y;
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= c) return;
+  const float* wr = w + (size_t)warp * c;
+  const float* pv = pooled + (size_t)b * c;
+  float acc = 0.f;
+  for (int i = lane; i < c; i += 32) acc = fmaf(__ldg(wr + i), pv[i] * inv_count, acc);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float v = acc + bias[warp] + 3.0f;
+    v = fminf(fmaxf(v, 0.f), 6.f) / 6.0f;
+    gate[(size_t)b * c + warp] = v;
+  }
+}
+
+template <typename T>
+__global__ void ese_apply_kernel(View<const T> x, const float* __restrict__ gate, View<const T> idn, View<T> out) {
+  int c8 = x.c >> 3;
+  int64_t total8 = (int64_t)x.n * x.h * x.w * c8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % c8);
+    int64_t pix = i / c8;
+    int xx = (int)(pix % x.w);
+    int64_t t = pix / x.w;
+    int y = (int)(t % x.h);
+    int b = (int)(t / x.h);
+    float v[8];
+    Vec8<T>::load(x.at(b, y, xx) + cv * 8, v);
+    const float* g = gate + (size_t)b * x.c + cv * 8;
+    if (idn.p) {
+      float r[8];
+      Vec8<T>::load(idn.at(b, y, xx) + cv * 8, r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = v[k] * g[k] + r[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = v[k] * g[k];
+    }
+    Vec8<T>::store(out.at(b, y, xx) + cv * 8, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm (+ReLU), in place.  stage 1: per (chunk, sample) per-channel partial sum / sum of squares,
+// stage 2: double-precision combine per (group, sample) -> mean, rstd; stage 3: normalise.
+// ---------------------------------------------------------------------------------------------
+constexpr int GN_PIX_PER_CHUNK = 128;
+
+template <typename T>
+__global__ void gn_partial_kernel(View<const T> x, int chunks, float* __restrict__ ws) {
+  // grid (chunks, n), 256 threads.  Thread t owns the 8-channel column cv = t % c8 on pixel lane
+  // pl = t / c8; lanes are combined through shared memory in a fixed order.
+  __shared__ float sm[2048 * 2];          // [lanes][c][2], lanes * c == 2048 at most
+  int chunk = blockIdx.x, b = blockIdx.y;
+  int c = x.c, c8 = c >> 3;
+  int hw = x.h * x.w;
+  int lanes = blockDim.x / c8;
+  int cv = threadIdx.x % c8, pl = threadIdx.x / c8;
+  int p0 = chunk * GN_PIX_PER_CHUNK, p1 = min(p0 + GN_PIX_PER_CHUNK, hw);
+  if (pl < lanes) {
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      int y = p / x.w, xx = p - y * x.w;
+      float v[8];
+      Vec8<T>::load(x.at(b, y, xx) + cv * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s[k] += v[k]; q[k] = fmaf(v[k], v[k], q[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sm[((size_t)pl * c + cv * 8 + k) * 2 + 0] = s[k];
+      sm[((size_t)pl * c + cv * 8 + k) * 2 + 1] = q[k];
+    }
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int l = 0; l < lanes; ++l) { s += sm[((size_t)l * c + ch) * 2]; q += sm[((size_t)l * c + ch) * 2 + 1]; }
+    ws[(((size_t)b * chunks + chunk) * c + ch) * 2 + 0] = s;
+    ws[(((size_t)b * chunks + chunk) * c + ch) * 2 + 1] = q;
+  }
+}
+
+// one warp per (group, sample): combines the per-chunk per-channel partials in double precision.
+__global__ void gn_final_kernel(const float* __restrict__ ws, int hw, int c, int groups, int chunks, float eps,
+                                float* __restrict__ stats) {
+  int b = blockIdx.y, g = blockIdx.x;
+  int cpg = c / groups;
+  int lane = threadIdx.x;
+  double sum = 0.0, sq = 0.0;
+  int total = chunks * cpg;
+  for (int i = lane; i < total; i += 32) {
+    int chunk = i / cpg, ch = g * cpg + (i - chunk * cpg);
+    const float* q = ws + (((size_t)b * chunks + chunk) * c + ch) * 2;
+    sum += (double)q[0];
+    sq += (double)q[1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  if (lane == 0) {
+    double cnt = (double)hw * cpg;
+    double mean = sum / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0) var = 0;
+    stats[((size_t)b * groups + g) * 2 + 0] = (float)mean;
+    stats[((size_t)b * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+template <typename T>
+__global__ void gn_apply_kernel(View<T> x, int groups, const float* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int relu) {
+  int c8 = x.c >> 3, cpg = x.c / groups;
+  int64_t total8 = (int64_t)x.n * x.h * x.w * c8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % c8);
+    int64_t pix = i / c8;
+    int xx = (int)(pix % x.w);
+    int64_t t = pix / x.w;
+    int y = (int)(t % x.h);
+    int b = (int)(t / x.h);
+    float v[8];
+    T* ptr = x.at(b, y, xx) + cv * 8;
+    Vec8<T>::load(ptr, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int g = (cv * 8 + k) / cpg;
+      float mean = stats[((size_t)b * groups + g) * 2], rstd = stats[((size_t)b * groups + g) * 2 + 1];
+      float yv = (v[k] - mean) * rstd * __ldg(gamma + cv * 8 + k) + __ldg(beta + cv * 8 + k);
+      v[k] = relu ? fmaxf(yv, 0.f) : yv;
+    }
+    Vec8<T>::store(ptr, v);
+  }
+}
+
+template <typename T>
+__global__ void relu_kernel(View<const T> in, View<T> out) {
+  int c8 = in.c >> 3;
+  int64_t total8 = (int64_t)in.n * in.h * in.w * c8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % c8);
+    int64_t pix = i / c8;
+    int xx = (int)(pix % in.w);
+    int64_t t = pix / in.w;
+    int y = (int)(t % in.h);
+    int b = (int)(t / in.h);
+    float v[8];
+    Vec8<T>::load(in.at(b, y, xx) + cv * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+    Vec8<T>::store(out.at(b, y, xx) + cv * 8, v);
+  }
+}
+
+int grid_for(int64_t work, int block) {
+  int64_t g = ceil_div64(work, block);
+  int64_t cap = 148 * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace cm2
+
+using namespace cm2;
+
+#define CM2_CHECK_DTYPE(dtype, name) \
+  CM2_CHECK_ARG((dtype) == CM2_F32 || (dtype) == CM2_BF16, name ": dtype %d not supported", (int)(dtype))
+
+extern "C" int cm2_preprocess_image(const void* img, int32_t in_dtype, int32_t h, int32_t w, const float* mean3,
+                                    const float* std3, const cm2_act* out, int32_t out_dtype, int32_t out_index,
+                                    void* stream) {
+  CM2_CHECK_ARG(img && out && out->data && mean3 && std3, "preprocess: null pointer");
+  CM2_CHECK_ARG(h > 0 && w > 0 && out->h >= h && out->w >= w && out->c >= 3 && out_index >= 0 && out_index < out->n,
+                "preprocess: bad extents %dx%d -> %dx%d (image %d of %d)", h, w, out->h, out->w, out_index, out->n);
+  dim3 grid(ceil_div(out->w, 256), out->h);
+  cudaStream_t s = (cudaStream_t)stream;
+#define CM2_PRE(IN, OUT)                                                                                   \
+  preprocess_kernel<IN, OUT><<<grid, 256, 0, s>>>((const IN*)img, h, w, mean3[0], mean3[1], mean3[2], std3[0], \
+                                                  std3[1], std3[2], make_view<OUT>(*out), out_index)
+  if (in_dtype == CM2_F32 && out_dtype == CM2_F32) CM2_PRE(float, float);
+  else if (in_dtype == CM2_F32 && out_dtype == CM2_BF16) CM2_PRE(float, __nv_bfloat16);
+  else if (in_dtype == CM2_U8 && out_dtype == CM2_F32) CM2_PRE(uint8_t, float);
+  else if (in_dtype == CM2_U8 && out_dtype == CM2_BF16) CM2_PRE(uint8_t, __nv_bfloat16);
+  else { set_error("preprocess: unsupported dtypes %d -> %d", in_dtype, out_dtype); return CM2_ERR_UNSUPPORTED; }
+#undef CM2_PRE
+  CM2_CHECK_LAUNCH("preprocess");
+  return CM2_OK;
+}
+
+extern "C" int cm2_maxpool3x3s2_ceil(const cm2_act* in, const cm2_act* out, int32_t dtype, void* stream) {
+  CM2_CHECK_ARG(in && out && in->data && out->data, "maxpool: null pointer");
+  CM2_CHECK_DTYPE(dtype, "maxpool");
+  CM2_CHECK_ARG(vec8_ok(*in, elem_bytes(dtype)) && vec8_ok(*out, elem_bytes(dtype)),
+                "maxpool: channels/strides must be multiples of 8 (c=%d)", in->c);
+  int h = in->h, w = in->w;
+  int eh = (h - 3 + 1) / 2 + 1, ew = (w - 3 + 1) / 2 + 1;   // ceil((h-3)/2)+1
+  if ((eh - 1) * 2 >= h) --eh;                               // last window must start inside the input
+  if ((ew - 1) * 2 >= w) --ew;
+  CM2_CHECK_ARG(out->h == eh && out->w == ew && out->n == in->n && out->c == in->c,
+                "maxpool: out [%d,%d,%d,%d] != expected [%d,%d,%d,%d]", out->n, out->h, out->w, out->c, in->n, eh, ew,
+                in->c);
+  int64_t total = (int64_t)out->n * out->h * out->w * (in->c / 8);
+  if (total == 0) return CM2_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == CM2_F32)
+    maxpool3s2_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(make_view<const float>(*in), make_view<float>(*out));
+  else
+    maxpool3s2_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(make_view<const __nv_bfloat16>(*in),
+                                                                        make_view<__nv_bfloat16>(*out));
+  CM2_CHECK_LAUNCH("maxpool3x3s2");
+  return CM2_OK;
+}
+
+extern "C" int32_t cm2_ese_pool_chunks(int32_t hw) { return ceil_div(hw, ESE_PIX_PER_CHUNK); }
+
+extern "C" int cm2_ese_pool(const cm2_act* x, int32_t dtype, float* workspace, float* pooled, void* stream) {
+  CM2_CHECK_ARG(x && x->data && workspace && pooled, "ese_pool: null pointer");
+  CM2_CHECK_DTYPE(dtype, "ese_pool");
+  CM2_CHECK_ARG(vec8_ok(*x, elem_bytes(dtype)) && x->h > 0 && x->w > 0, "ese_pool: bad shape %dx%d c=%d", x->h, x->w,
+                x->c);
+  if (x->n == 0) return CM2_OK;
+  int hw = x->h * x->w;
+  int chunks = cm2_ese_pool_chunks(hw);
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 g1(chunks, x->n);
+  if (dtype == CM2_F32)
+    ese_pool_partial_kernel<float><<<g1, 128, 0, s>>>(make_view<const float>(*x), chunks, workspace);
+  else
+    ese_pool_partial_kernel<__nv_bfloat16><<<g1, 128, 0, s>>>(make_view<const __nv_bfloat16>(*x), chunks, workspace);
+  CM2_CHECK_LAUNCH("ese_pool_partial");
+  dim3 g2(ceil_div(x->c, 128), x->n);
+  ese_pool_final_kernel<<<g2, 128, 0, s>>>(workspace, chunks, x->c, 1.0f / (float)hw, pooled);
+  CM2_CHECK_LAUNCH("ese_pool_final");
+  return CM2_OK;
+}
+
+extern "C" int cm2_ese_gate(const float* pooled, float inv_count, const float* fc_w, const float* fc_b, float* gate,
+                            int32_t n, int32_t c, void* stream) {
+  CM2_CHECK_ARG(pooled && fc_w && fc_b && gate, "ese_gate: null pointer");
+  if (n == 0) return CM2_OK;
+  dim3 grid(ceil_div(c * 32, 256), n);
+  ese_gate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pooled, inv_count, fc_w, fc_b, gate, c);
+  CM2_CHECK_LAUNCH("ese_gate");
+  return CM2_OK;
+}
+
+extern "C" int cm2_ese_apply(const cm2_act* x, const float* gate, const cm2_act* identity, const cm2_act* out,
+                             int32_t dtype, void* stream) {
+  CM2_CHECK_ARG(x && x->data && gate && out && out->data, "ese_apply: null pointer");
+  CM2_CHECK_DTYPE(dtype, "ese_apply");
+  int eb = elem_bytes(dtype);
+  CM2_CHECK_ARG(vec8_ok(*x, eb) && vec8_ok(*out, eb) && same_extent(*x, *out), "ese_apply: bad views (c=%d)", x->c);
+  cm2_act idn;
+  memset(&idn, 0, sizeof(idn));
+  if (identity && identity->data) {
+    CM2_CHECK_ARG(vec8_ok(*identity, eb) && same_extent(*x, *identity), "ese_apply: identity view mismatch");
+    idn = *identity;
+  }
+  int64_t total8 = (int64_t)x->n * x->h * x->w * (x->c / 8);
+  if (total8 == 0) return CM2_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == CM2_F32)
+    ese_apply_kernel<float><<<grid_for(total8, 256), 256, 0, s>>>(make_view<const float>(*x), gate,
+                                                                 make_view<const float>(idn), make_view<float>(*out));
+  else
+    ese_apply_kernel<__nv_bfloat16><<<grid_for(total8, 256), 256, 0, s>>>(
+        make_view<const __nv_bfloat16>(*x), gate, make_view<const __nv_bfloat16>(idn), make_view<__nv_bfloat16>(*out));
+  CM2_CHECK_LAUNCH("ese_apply");
+  return CM2_OK;
+}
+
+extern "C" int64_t cm2_gn_workspace_floats(int32_t n, int32_t hw, int32_t c, int32_t groups) {
+  int chunks = ceil_div(hw, GN_PIX_PER_CHUNK);
+  return (int64_t)2 * n * chunks * c + (int64_t)2 * n * groups;
+}
+
+extern "C" int cm2_groupnorm_relu(const cm2_act* x, int32_t dtype, int32_t groups, const float* gamma,
+                                  const float* beta, float eps, int32_t relu, float* workspace, void* stream) {
+  CM2_CHECK_ARG(x && x->data && gamma && beta && workspace, "groupnorm: null pointer");
+  CM2_CHECK_DTYPE(dtype, "groupnorm");
+  int c = x->c, n = x->n, hw = x->h * x->w;
+  CM2_CHECK_ARG(groups > 0 && c % groups == 0 && vec8_ok(*x, elem_bytes(dtype)) && c / 8 <= 256 && 256 % (c / 8) == 0,
+                "groupnorm: unsupported c=%d groups=%d (need c %% 8 == 0, c/8 a divisor of 256)", c, groups);
+  if (n == 0 || hw == 0) return CM2_OK;
+  const int nthreads = 256;
+  int chunks = ceil_div(hw, GN_PIX_PER_CHUNK);
+  cudaStream_t s = (cudaStream_t)stream;
+  float* partial = workspace;
+  float* stats = workspace + (size_t)2 * n * chunks * c;
+  dim3 g1(chunks, n);
+  if (dtype == CM2_F32)
+    gn_partial_kernel<float><<<g1, nthreads, 0, s>>>(make_view<const float>(*x), chunks, partial);
+  else
+    gn_partial_kernel<__nv_bfloat16><<<g1, nthreads, 0, s>>>(make_view<const __nv_bfloat16>(*x), chunks, partial);
+  CM2_CHECK_LAUNCH("gn_partial");
+  dim3 g2(groups, n);
+  gn_final_kernel<<<g2, 32, 0, s>>>(partial, hw, c, groups, chunks, eps, stats);
+  CM2_CHECK_LAUNCH("gn_final");
+  int64_t total8 = (int64_t)n * hw * (c / 8);
+  if (dtype == CM2_F32)
+    gn_apply_kernel<float><<<grid_for(total8, 256), 256, 0, s>>>(make_view<float>(*x), groups, stats, gamma, beta, relu);
+  else
+    gn_apply_kernel<__nv_bfloat16><<<grid_for(total8, 256), 256, 0, s>>>(make_view<__nv_bfloat16>(*x), groups, stats,
+                                                                        gamma, beta, relu);
+  CM2_CHECK_LAUNCH("gn_apply");
+  return CM2_OK;
+}
+
+extern "C" int cm2_relu(const cm2_act* in, const cm2_act* out, int32_t dtype, void* stream) {
+  CM2_CHECK_ARG(in && out && in->data && out->data, "relu: null pointer");
+  CM2_CHECK_DTYPE(dtype, "relu");
+  int eb = elem_bytes(dtype);
+  CM2_CHECK_ARG(vec8_ok(*in, eb) && vec8_ok(*out, eb) && same_extent(*in, *out), "relu: bad views");
+  int64_t total8 = (int64_t)in->n * in->h * in->w * (in->c / 8);
+  if (total8 == 0) return CM2_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == CM2_F32)
+    relu_kernel<float><<<grid_for(total8, 256), 256, 0, s>>>(make_view<const float>(*in), make_view<float>(*out));
+  else
+    relu_kernel<__nv_bfloat16><<<grid_for(total8, 256), 256, 0, s>>>(make_view<const __nv_bfloat16>(*in),
+                                                                    make_view<__nv_bfloat16>(*out));
+  CM2_CHECK_LAUNCH("relu");
+  return CM2_OK;
+}

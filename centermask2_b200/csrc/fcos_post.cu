@@ -1,0 +1,319 @@
+// FCOS post-process: decode + threshold + compaction, per-level top-k, class-aware NMS, post top-k.
+//
+// Reference: modeling/fcos/fcos_outputs.py:372-495 and layers/ml_nms.py:93-96.  The reference loops
+// over images and levels in Python and calls nonzero / index / torchvision NMS; here the whole
+// post-process of a batch is three launches per batch (plus one decode launch per level).
+//
+// Determinism: candidates are appended with atomics (unordered), then every (image, level) segment
+// is sorted by (raw score desc, flat index asc), which makes all later stages order-independent.
+#include "common.cuh"
+
+namespace cm2 {
+
+// ---------------------------------------------------------------------------------------------
+// decode: one warp per location; lanes stride over classes so the logits row is read coalesced.
+// ---------------------------------------------------------------------------------------------
+__global__ void fcos_decode_kernel(View<const float> logits, View<const float> regctr, int stride, float thresh,
+                                   int thresh_with_ctr, int level, int num_levels, int cap, cm2_cand_buffers cand) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int h = logits.h, w = logits.w, ncls = logits.c;
+  const int hw = h * w;
+  const int64_t total = (int64_t)logits.n * hw;
+  for (int64_t loc = warp; loc < total; loc += nwarps) {
+    const int img = (int)(loc / hw);
+    const int pos = (int)(loc - (int64_t)img * hw);
+    const int py_ = pos / w, px_ = pos - py_ * w;
+    const float* lrow = logits.at(img, py_, px_);
+    const float* rrow = regctr.at(img, py_, px_);
+    const float ctr = sigmoid_f32(__ldg(rrow + 4));
+    const int seg = img * num_levels + level;
+    for (int c0 = 0; c0 < ncls; c0 += 32) {
+      int c = c0 + lane;
+      bool is_cand = false;
+      float s = 0.f;
+      if (c < ncls) {
+        float p = sigmoid_f32(__ldg(lrow + c));
+        s = p * ctr;
+        is_cand = thresh_with_ctr ? (s > thresh) : (p > thresh);
+      }
+      unsigned m = __ballot_sync(0xffffffffu, is_cand);
+      if (m == 0) continue;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(cand.count + seg, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (is_cand) {
+        int slot = base + __popc(m & ((1u << lane) - 1));
+        if (slot < cap) {
+          float l = fmaxf(__ldg(rrow + 0), 0.f) * (float)stride;
+          float t = fmaxf(__ldg(rrow + 1), 0.f) * (float)stride;
+          float r = fmaxf(__ldg(rrow + 2), 0.f) * (float)stride;
+          float b = fmaxf(__ldg(rrow + 3), 0.f) * (float)stride;
+          float px = (float)(px_ * stride + stride / 2);
+          float py = (float)(py_ * stride + stride / 2);
+          size_t o = (size_t)seg * cap + slot;
+          reinterpret_cast<float4*>(cand.boxes)[o] = make_float4(px - l, py - t, px + r, py + b);
+          cand.score[o] = s;
+          cand.cls[o] = c;
+          cand.flat[o] = pos * ncls + c;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// in-CTA bitonic sort of 64-bit keys, descending.  `n` must be a power of two.
+// ---------------------------------------------------------------------------------------------
+__device__ void bitonic_sort_desc(unsigned long long* keys, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long a = keys[i], b = keys[ixj];
+          bool up = (i & k) == 0;          // descending in the "up" half
+          if (up ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct SelectWs {
+  float* boxes;        // [n][levels][pre][4]   per-level sorted + truncated candidates
+  float* score;        // [n][levels][pre]
+  int* cls;            // [n][levels][pre]
+  int* flat;           // [n][levels][pre]
+  int* kept;           // [n][levels]
+};
+
+// grid (levels, n).  Sort one (image, level) segment by (raw score desc, flat asc), keep pre_topk.
+__global__ void fcos_select_level_kernel(cm2_cand_buffers cand, int num_levels, int cap, int pre_topk, int sort_n,
+                                         SelectWs ws) {
+  extern __shared__ unsigned long long keys[];
+  const int level = blockIdx.x, img = blockIdx.y;
+  const int seg = img * num_levels + level;
+  int cnt = min(cand.count[seg], cap);
+  for (int i = threadIdx.x; i < sort_n; i += blockDim.x) {
+    unsigned long long k = 0ull;
+    if (i < cnt) {
+      size_t o = (size_t)seg * cap + i;
+      // primary: raw score bits (positive floats order as unsigned ints); secondary: lower flat first.
+      // The slot index rides in a side array because 64 bits are used up.
+      k = ((unsigned long long)__float_as_uint(cand.score[o]) << 32) | (unsigned)(0xffffffffu - (unsigned)cand.flat[o]);
+    }
+    keys[i] = k;
+  }
+  __syncthreads();
+  bitonic_sort_desc(keys, sort_n);
+  int keep = min(cnt, pre_topk);
+  if (threadIdx.x == 0) ws.kept[seg] = keep;
+  // map sorted keys back to slots: flat is unique within a segment, so search it.  To stay O(n log n)
+  // we sort a second time on (flat) would be wasteful; instead build an index: every thread scans for
+  // its key's slot through a shared flat->slot pass below.
+  // Pass: each candidate slot finds its rank by binary search over the sorted keys.
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    size_t o = (size_t)seg * cap + i;
+    unsigned long long k =
+        ((unsigned long long)__float_as_uint(cand.score[o]) << 32) | (unsigned)(0xffffffffu - (unsigned)cand.flat[o]);
+    int lo = 0, hi = cnt - 1;             // keys[0..cnt) descending, all distinct
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (keys[mid] > k) lo = mid + 1; else hi = mid;
+    }
+    int rank = lo;
+    if (rank < keep) {
+      size_t d = (size_t)seg * pre_topk + rank;
+      reinterpret_cast<float4*>(ws.boxes)[d] = reinterpret_cast<const float4*>(cand.boxes)[o];
+      ws.score[d] = cand.score[o];
+      ws.cls[d] = cand.cls[o];
+      ws.flat[d] = cand.flat[o];
+    }
+  }
+}
+
+__device__ __forceinline__ bool iou_gt(const float4& a, float area_a, const float4& b, float area_b, float thr) {
+  // torchvision nms_kernel (CPU): inter / (area_a + area_b - inter) > thr
+  float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+  float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
+  float inter = w * h;
+  float ovr = inter / (area_a + area_b - inter);
+  return ovr > thr;
+}
+
+// grid (n); 1024 threads sort, warp 0 runs the greedy sweep with early exit at post_topk survivors.
+__global__ void fcos_nms_image_kernel(SelectWs ws, int num_levels, int pre_topk, int sort_n, const int* level_w,
+                                      const int* level_stride, int ncls, float nms_thresh, int post_topk,
+                                      cm2_det_buffers det) {
+  extern __shared__ unsigned long long keys[];
+  __shared__ float4 kept_box[256];
+  __shared__ float kept_area[256];
+  __shared__ int kept_cls[256];
+  __shared__ int kept_idx[256];
+  const int img = blockIdx.x;
+  const int total_slots = num_levels * pre_topk;
+  for (int i = threadIdx.x; i < sort_n; i += blockDim.x) {
+    unsigned long long k = 0ull;
+    if (i < total_slots) {
+      int level = i / pre_topk, r = i - level * pre_topk;
+      if (r < ws.kept[img * num_levels + level]) {
+        size_t o = (size_t)(img * num_levels + level) * pre_topk + r;
+        float sc = sqrtf(ws.score[o]);                       // fcos_outputs.py:460
+        // secondary key: earlier (level, rank) first -- deterministic because segments are sorted
+        k = ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned)(0xffffffffu - (unsigned)i);
+        if (k == 0ull) k = 1ull;
+      }
+    }
+    keys[i] = k;
+  }
+  __syncthreads();
+  bitonic_sort_desc(keys, sort_n);
+
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int nkept = 0;
+    for (int base = 0; base < total_slots && nkept < post_topk; base += 32) {
+      unsigned long long k = (base + lane < sort_n) ? keys[base + lane] : 0ull;
+      bool alive = k != 0ull;
+      float4 bx = make_float4(0, 0, 0, 0);
+      float area = 0.f;
+      int cls = -1, slot = 0;
+      if (alive) {
+        slot = (int)(0xffffffffu - (unsigned)(k & 0xffffffffull));
+        int level = slot / pre_topk, r = slot - level * pre_topk;
+        size_t o = (size_t)(img * num_levels + level) * pre_topk + r;
+        bx = reinterpret_cast<const float4*>(ws.boxes)[o];
+        area = (bx.z - bx.x) * (bx.w - bx.y);
+        cls = ws.cls[o];
+        for (int j = 0; j < nkept; ++j)
+          if (kept_cls[j] == cls && iou_gt(kept_box[j], kept_area[j], bx, area, nms_thresh)) { alive = false; break; }
+      }
+      unsigned m = __ballot_sync(0xffffffffu, alive);
+      if (__ballot_sync(0xffffffffu, k != 0ull) == 0u) break;      // ran out of candidates
+      while (m != 0u && nkept < post_topk) {
+        int leader = __ffs(m) - 1;
+        float4 lb;
+        lb.x = __shfl_sync(0xffffffffu, bx.x, leader);
+        lb.y = __shfl_sync(0xffffffffu, bx.y, leader);
+        lb.z = __shfl_sync(0xffffffffu, bx.z, leader);
+        lb.w = __shfl_sync(0xffffffffu, bx.w, leader);
+        float la = __shfl_sync(0xffffffffu, area, leader);
+        int lc = __shfl_sync(0xffffffffu, cls, leader);
+        int ls = __shfl_sync(0xffffffffu, slot, leader);
+        if (lane == 0) { kept_box[nkept] = lb; kept_area[nkept] = la; kept_cls[nkept] = lc; kept_idx[nkept] = ls; }
+        ++nkept;
+        if (alive && lane > leader && cls == lc && iou_gt(lb, la, bx, area, nms_thresh)) alive = false;
+        if (lane == leader) alive = false;
+        m = __ballot_sync(0xffffffffu, alive);
+      }
+      __syncwarp();
+    }
+    __syncwarp();
+    // write-out: survivors are already in descending score order
+    for (int j = lane; j < post_topk; j += 32) {
+      size_t d = (size_t)img * post_topk + j;
+      if (j < nkept) {
+        int slot = kept_idx[j];
+        int level = slot / pre_topk, r = slot - level * pre_topk;
+        size_t o = (size_t)(img * num_levels + level) * pre_topk + r;
+        reinterpret_cast<float4*>(det.boxes)[d] = kept_box[j];
+        det.scores[d] = sqrtf(ws.score[o]);
+        det.classes[d] = (int64_t)kept_cls[j];
+        int pos = ws.flat[o] / ncls;
+        int w = level_w[level], st = level_stride[level];
+        int y = pos / w, x = pos - y * w;
+        det.locations[2 * d] = (float)(x * st + st / 2);
+        det.locations[2 * d + 1] = (float)(y * st + st / 2);
+      } else {
+        reinterpret_cast<float4*>(det.boxes)[d] = make_float4(0, 0, 0, 0);
+        det.scores[d] = 0.f;
+        det.classes[d] = 0;
+        det.locations[2 * d] = 0.f;
+        det.locations[2 * d + 1] = 0.f;
+      }
+    }
+    if (lane == 0) det.count[img] = nkept;
+  }
+}
+
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static SelectWs carve_ws(void* workspace, int n, int num_levels, int pre) {
+  SelectWs ws;
+  char* p = reinterpret_cast<char*>(workspace);
+  size_t slots = (size_t)n * num_levels * pre;
+  ws.boxes = reinterpret_cast<float*>(p); p += slots * 16;
+  ws.score = reinterpret_cast<float*>(p); p += slots * 4;
+  ws.cls = reinterpret_cast<int*>(p); p += slots * 4;
+  ws.flat = reinterpret_cast<int*>(p); p += slots * 4;
+  ws.kept = reinterpret_cast<int*>(p);
+  return ws;
+}
+
+}  // namespace cm2
+
+using namespace cm2;
+
+extern "C" int cm2_fcos_decode(const cm2_act* logits, const cm2_act* regctr, int32_t stride, float thresh,
+                               int32_t thresh_with_ctr, int32_t level, int32_t num_levels, int32_t cap,
+                               const cm2_cand_buffers* cand, void* stream) {
+  CM2_CHECK_ARG(logits && regctr && logits->data && regctr->data && cand && cand->boxes && cand->score && cand->cls &&
+                cand->flat && cand->count, "fcos_decode: null pointer");
+  CM2_CHECK_ARG(regctr->c >= 5 && logits->c > 0 && cap > 0 && level >= 0 && level < num_levels,
+                "fcos_decode: bad arguments");
+  CM2_CHECK_ARG(regctr->n == logits->n && regctr->h == logits->h && regctr->w == logits->w,
+                "fcos_decode: logits / regctr extents differ");
+  CM2_CHECK_ARG((int64_t)logits->h * logits->w * logits->c < (1ll << 31), "fcos_decode: level too large");
+  int64_t total = (int64_t)logits->n * logits->h * logits->w;
+  if (total == 0) return CM2_OK;
+  int64_t blocks = ceil_div64(total * 32, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  fcos_decode_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(make_view<const float>(*logits),
+                                                                   make_view<const float>(*regctr), stride, thresh,
+                                                                   thresh_with_ctr, level, num_levels, cap, *cand);
+  CM2_CHECK_LAUNCH("fcos_decode");
+  return CM2_OK;
+}
+
+extern "C" int64_t cm2_fcos_select_workspace(int32_t n, int32_t num_levels, int32_t cap) {
+  // sized for pre_topk <= cap
+  size_t slots = (size_t)n * num_levels * cap;
+  return (int64_t)(slots * 28 + (size_t)n * num_levels * 4 + 256);
+}
+
+extern "C" int cm2_fcos_select(const cm2_cand_buffers* cand, int32_t n, int32_t num_levels, int32_t cap,
+                               const int32_t* level_w, const int32_t* level_stride, int32_t ncls, int32_t pre_topk,
+                               float nms_thresh, int32_t post_topk, const cm2_det_buffers* det, void* workspace,
+                               void* stream) {
+  CM2_CHECK_ARG(cand && det && workspace && level_w && level_stride, "fcos_select: null pointer");
+  CM2_CHECK_ARG(pre_topk > 0 && pre_topk <= cap, "fcos_select: pre_topk %d must be in (0, cap=%d]", pre_topk, cap);
+  CM2_CHECK_ARG(post_topk > 0 && post_topk <= 256, "fcos_select: post_topk %d must be in (0, 256]", post_topk);
+  int sort_a = next_pow2(cap);
+  int sort_b = next_pow2(num_levels * pre_topk);
+  CM2_CHECK_ARG(sort_a <= 16384 && sort_b <= 16384, "fcos_select: cap %d / levels*pre_topk %d exceed the in-CTA sort (16384)",
+                cap, num_levels * pre_topk);
+  if (n == 0) return CM2_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  SelectWs ws = carve_ws(workspace, n, num_levels, pre_topk);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(fcos_select_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    cudaFuncSetAttribute(fcos_nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    attr_done = true;
+  }
+  dim3 g1(num_levels, n);
+  fcos_select_level_kernel<<<g1, 1024, (size_t)sort_a * 8, s>>>(*cand, num_levels, cap, pre_topk, sort_a, ws);
+  CM2_CHECK_LAUNCH("fcos_select_level");
+  fcos_nms_image_kernel<<<n, 1024, (size_t)sort_b * 8, s>>>(ws, num_levels, pre_topk, sort_b, level_w, level_stride, ncls,
+                                                          nms_thresh, post_topk, *det);
+  CM2_CHECK_LAUNCH("fcos_nms_image");
+  return CM2_OK;
+}

@@ -1,0 +1,410 @@
+"""Launch plans of the CenterMask2 inference path on ``libcm2.so``.
+
+This module is the host side of the hot path: it owns the activation buffers (NHWC with a one-pixel
+zero halo, see ``include/cm2.h``), turns the static layer tables of ``arch.py`` plus packed weights
+(``packing.py``) into sequences of C-ABI calls, and never touches torch compute ops -- torch is used
+for device memory, streams and (at the API boundary only) indexing of the fixed-size result buffers.
+
+Reference call sequence being replaced: ``GeneralizedRCNN.inference`` [d2] as mirrored in-tree at
+``/root/reference/tester.py:24-75``: backbone (``vovnet.py:471-481`` + FPN [d2] + ``fpn.py:32-35``)
+-> ``FCOS.forward`` (``fcos/fcos.py:61-118``) -> ``CenterROIHeads.forward`` (``center_heads.py:384-444``)
+-> ``detector_postprocess`` [d2].
+"""
+import math
+
+import torch
+
+from . import lib, packing
+from .arch import vovnet_blocks
+
+
+class FMap(object):
+    """A feature map stored NHWC inside a buffer with ``halo`` zero pixels on every side."""
+
+    __slots__ = ("buf", "halo")
+
+    def __init__(self, buf, halo):
+        self.buf, self.halo = buf, halo
+
+    @property
+    def view(self):
+        h = self.halo
+        return self.buf[:, h:self.buf.shape[1] - h, h:self.buf.shape[2] - h, :] if h else self.buf
+
+    @property
+    def n(self):
+        return self.buf.shape[0]
+
+    @property
+    def h(self):
+        return self.buf.shape[1] - 2 * self.halo
+
+    @property
+    def w(self):
+        return self.buf.shape[2] - 2 * self.halo
+
+    @property
+    def c(self):
+        return self.buf.shape[3]
+
+    def nchw(self):
+        """Zero-copy [N, C, H, W]-shaped (channels_last-strided) tensor for the registry-level API."""
+        t = self.view.permute(0, 3, 1, 2)
+        t._cm2_fmap = self
+        return t
+
+
+def as_fmap(t, dtype, device):
+    """Accept what a detectron2 caller hands over: one of our own tensors (zero copy) or any NCHW
+    tensor (copied once into a halo buffer)."""
+    fm = getattr(t, "_cm2_fmap", None)
+    if fm is not None and fm.buf.dtype == dtype:
+        return fm
+    n, c, h, w = t.shape
+    buf = torch.zeros((n, h + 2, w + 2, c), dtype=dtype, device=device)
+    buf[:, 1:-1, 1:-1, :] = t.permute(0, 2, 3, 1).to(device=device, dtype=dtype)
+    return FMap(buf, 1)
+
+
+class Engine(object):
+    """Buffer cache + layer launchers for one (cfg, precision, device)."""
+
+    def __init__(self, cfg, precision="fp32", device="cuda"):
+        assert precision in ("fp32", "bf16"), precision
+        self.cfg = cfg
+        self.precision = precision
+        self.dtype = torch.float32 if precision == "fp32" else torch.bfloat16
+        self.tc = precision == "bf16"
+        self.device = torch.device(device)
+        self._bufs = {}
+        lib.load()
+
+    # -- buffers ---------------------------------------------------------------------------------
+    def buffer(self, name, shape, dtype, zero=True):
+        key = (name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def fmap(self, name, n, h, w, c, dtype=None, halo=1):
+        return FMap(self.buffer(name, (n, h + 2 * halo, w + 2 * halo, c), dtype or self.dtype), halo)
+
+    def release(self):
+        self._bufs.clear()
+
+    # -- one convolution -------------------------------------------------------------------------
+    def conv(self, name, srcs, w, out_dtype=None, residual=None, res_mode=0, out_mode=0, in_relu=False,
+             out_halo=1, chan_sum=None, out=None):
+        x0 = srcs[0]
+        ho = (x0.h + 2 * w.pad - w.k) // w.stride + 1
+        wo = (x0.w + 2 * w.pad - w.k) // w.stride + 1
+        if out is None:
+            if out_mode == 0:
+                out = self.fmap(name, x0.n, ho, wo, w.cout, out_dtype, out_halo)
+            else:
+                out = self.fmap(name, x0.n, 2 * ho, 2 * wo, w.cout // 4, out_dtype, out_halo)
+        views = [s.view for s in srcs]
+        for v, c in zip(views, w.src_c):
+            assert v.shape[3] == c, (name, v.shape, w.src_c)
+        kw = dict(scale=w.scale, shift=w.shift, relu=w.relu, in_relu=in_relu,
+                  residual=None if residual is None else residual.view, res_mode=res_mode, out_mode=out_mode)
+        if self.tc and w.w_tc is not None and lib.conv2d(views, w.w_tc, out.view, w.cout, w.k, w.stride, w.pad,
+                                                          engine=lib.ENGINE_TC, chan_sum=chan_sum, probe=True, **kw):
+            return out
+        assert chan_sum is None, "chan_sum requires the tensor-core engine"
+        lib.conv2d(views, w.w_simt, out.view, w.cout, w.k, w.stride, w.pad, engine=lib.ENGINE_SIMT, **kw)
+        return out
+
+    # =============================================================================================
+    # backbone: VoVNetV2-eSE + FPN + P6/P7
+    # =============================================================================================
+    def pack_backbone(self, sd, prefix=""):
+        """``sd`` keys relative to the backbone module (``bottom_up.*``, ``fpn_*``, ``top_block.*``)."""
+        cfg, dt, dev, tc = self.cfg, self.dtype, self.device, self.tc
+        stem, blocks = vovnet_blocks(cfg.MODEL.VOVNET.CONV_BODY)
+        P = {"stem": [], "blocks": []}
+        cin = 3
+        for i, (c, s) in enumerate(zip(stem, (2, 1, 2))):
+            P["stem"].append(packing.conv_bn_relu(sd, prefix + "bottom_up.stem.stem_{}".format(i + 1), [cin], s, 1, dt, dev, tc))
+            cin = c
+        for b in blocks:
+            convs = []
+            c = b.in_ch
+            for i in range(b.n_conv):
+                convs.append(packing.conv_bn_relu(sd, prefix + "bottom_up." + b.key(i), [c], 1, 1, dt, dev, tc))
+                c = b.mid_ch
+            cat = packing.conv_bn_relu(sd, prefix + "bottom_up." + b.key("concat"), [b.in_ch] + [b.mid_ch] * b.n_conv, 1, 0, dt, dev, tc)
+            ek = prefix + "bottom_up." + b.ese_key()
+            ese_w = sd[ek + ".weight"].detach().reshape(b.out_ch, b.out_ch).to(device=dev, dtype=torch.float32).contiguous()
+            ese_b = sd[ek + ".bias"].detach().to(device=dev, dtype=torch.float32).contiguous()
+            P["blocks"].append((b, convs, cat, ese_w, ese_b))
+        out_ch = {"stage{}".format(b.stage): b.out_ch for b in blocks}
+        fc = cfg.MODEL.FPN.OUT_CHANNELS
+        P["fpn"] = {}
+        for f in cfg.MODEL.FPN.IN_FEATURES:
+            lvl = int(f[-1])
+            lat = packing.conv_bias(sd, prefix + "fpn_lateral{}".format(lvl), [out_ch[f]], 1, 0, False, dt, dev, tc)
+            outc = packing.conv_bias(sd, prefix + "fpn_output{}".format(lvl), [fc], 1, 1, False, dt, dev, tc)
+            P["fpn"][f] = (lvl, lat, outc)
+        P["top"] = [packing.conv_bias(sd, prefix + "top_block.p{}".format(6 + i), [fc], 2, 1, False, dt, dev, tc)
+                    for i in range(cfg.MODEL.FCOS.TOP_LEVELS)]
+        return P
+
+    def run_backbone(self, x, P):
+        """x: FMap [N, Hp, Wp, 3] (normalised, padded to /32).  Returns {"p3": FMap, ...}."""
+        cfg = self.cfg
+        for i, w in enumerate(P["stem"]):
+            x = self.conv("stem{}".format(i + 1), [x], w)
+        stage = 2
+        stage_out = {}
+        for b, convs, cat, ese_w, ese_b in P["blocks"]:
+            if b.stage != stage:
+                # MaxPool2d(3, 2, ceil_mode=True), vovnet.py:349-350
+                ho, wo = -(-(x.h - 3) // 2) + 1, -(-(x.w - 3) // 2) + 1
+                if (ho - 1) * 2 >= x.h:
+                    ho -= 1
+                if (wo - 1) * 2 >= x.w:
+                    wo -= 1
+                pooled = self.fmap("pool{}".format(b.stage), x.n, ho, wo, x.c)
+                lib.maxpool3x3s2_ceil(x.view, pooled.view)
+                x = pooled
+                stage = b.stage
+            identity = x
+            feats = [x]
+            y = x
+            for i, w in enumerate(convs):
+                y = self.conv("{}_{}".format(b.name, i), [y], w)
+                feats.append(y)
+            agg = self.conv(b.name + "_cat", feats, cat)                       # virtual concat, vovnet.py:324-325
+            # eSE, vovnet.py:247-260 / :327-330
+            n, hw, c = agg.n, agg.h * agg.w, agg.c
+            wsp = self.buffer(b.name + "_esews", (n * lib.ese_pool_chunks(hw) * c,), torch.float32, zero=False)
+            pooled = self.buffer(b.name + "_pool", (n, c), torch.float32, zero=False)
+            gate = self.buffer(b.name + "_gate", (n, c), torch.float32, zero=False)
+            lib.ese_pool(agg.view, wsp, pooled)
+            lib.ese_gate(pooled, 1.0, ese_w, ese_b, gate, n, c)
+            out = self.fmap(b.name + "_out", n, agg.h, agg.w, c)
+            lib.ese_apply(agg.view, gate, identity.view if b.identity else None, out.view)
+            x = out
+            stage_out["stage{}".format(b.stage)] = x
+        # FPN top-down [d2] (constructed at vovnet.py:547-554)
+        res = {}
+        prev = None
+        for f in reversed(list(cfg.MODEL.FPN.IN_FEATURES)):
+            lvl, lat, outc = P["fpn"][f]
+            prev = self.conv("fpn_inner{}".format(lvl), [stage_out[f]], lat, residual=prev, res_mode=2 if prev is not None else 0)
+            res["p{}".format(lvl)] = self.conv("p{}".format(lvl), [prev], outc)
+        # LastLevelP6P7, fpn.py:32-35 (P7 = conv(relu(P6)))
+        top = res["p5"]
+        for i, w in enumerate(P["top"]):
+            top = self.conv("p{}".format(6 + i), [top], w, in_relu=(i == 1))
+            res["p{}".format(6 + i)] = top
+        return {k: res[k] for k in sorted(res)}
+
+    # =============================================================================================
+    # FCOS head + post-process
+    # =============================================================================================
+    def pack_fcos(self, sd, prefix=""):
+        cfg, dt, dev, tc = self.cfg, self.dtype, self.device, self.tc
+        fc = sd[prefix + "fcos_head.cls_logits.weight"].shape[1]
+        use_gn = cfg.MODEL.FCOS.NORM == "GN"
+        per = 3 if use_gn else 2
+        P = {"towers": {}, "use_gn": use_gn}
+        for name, n in (("share", cfg.MODEL.FCOS.NUM_SHARE_CONVS), ("cls", cfg.MODEL.FCOS.NUM_CLS_CONVS),
+                        ("bbox", cfg.MODEL.FCOS.NUM_BOX_CONVS)):
+            units = []
+            for i in range(n):
+                p = prefix + "fcos_head.{}_tower.{}".format(name, per * i)
+                conv = packing.conv_bias(sd, p, [fc], 1, 1, not use_gn, dt, dev, tc)
+                gn = None
+                if use_gn:
+                    q = prefix + "fcos_head.{}_tower.{}".format(name, per * i + 1)
+                    gn = (sd[q + ".weight"].detach().to(device=dev, dtype=torch.float32).contiguous(),
+                          sd[q + ".bias"].detach().to(device=dev, dtype=torch.float32).contiguous())
+                units.append((conv, gn))
+            P["towers"][name] = units
+        P["cls"] = packing.conv_bias(sd, prefix + "fcos_head.cls_logits", [fc], 1, 1, False, dt, dev, tc)
+        # bbox_pred (4) and ctrness (1) merged into one 5-column conv; the per-level Scale (fcos.py:19-25,
+        # :233-238) is folded into per-level epilogue vectors, ReLU is applied by the decode kernel.
+        wb = sd[prefix + "fcos_head.bbox_pred.weight"].detach().float()
+        wc = sd[prefix + "fcos_head.ctrness.weight"].detach().float()
+        bb = sd[prefix + "fcos_head.bbox_pred.bias"].detach().float()
+        bc = sd[prefix + "fcos_head.ctrness.bias"].detach().float()
+        P["regctr"] = []
+        for l in range(len(cfg.MODEL.FCOS.FPN_STRIDES)):
+            s = sd[prefix + "fcos_head.scales.{}.scale".format(l)].detach().float().reshape(()) if cfg.MODEL.FCOS.USE_SCALE \
+                else torch.tensor(1.0)
+            scale = torch.cat([s.expand(4), torch.ones(1)])
+            shift = torch.cat([bb * s, bc])
+            P["regctr"].append(packing.ConvW(torch.cat([wb, wc], 0), [fc], 1, 1, scale, shift, False, dt, dev, tc))
+        return P
+
+    def run_fcos_head(self, feats, P):
+        """feats: list of FMap (p3..p7).  Returns per level (logits f32 FMap [N,H,W,ncls], regctr f32 FMap [N,H,W,5])."""
+        out = []
+        for l, f in enumerate(feats):
+            def tower(x, units, tag):
+                for i, (conv, gn) in enumerate(units):
+                    x = self.conv("fcos_{}{}_l{}".format(tag, i, l), [x], conv)
+                    if gn is not None:
+                        wsp = self.buffer("fcos_gnws_l{}".format(l), (lib.gn_workspace_floats(x.n, x.h * x.w, x.c, 32),),
+                                          torch.float32, zero=False)
+                        lib.groupnorm_relu(x.view, 32, gn[0], gn[1], 1e-5, True, wsp)
+                return x
+            x = tower(f, P["towers"]["share"], "share")
+            ct = tower(x, P["towers"]["cls"], "cls")
+            bt = tower(x, P["towers"]["bbox"], "bbox")
+            logits = self.conv("fcos_logits_l{}".format(l), [ct], P["cls"], out_dtype=torch.float32, out_halo=0)
+            regctr = self.conv("fcos_regctr_l{}".format(l), [bt], P["regctr"][l], out_dtype=torch.float32, out_halo=0)
+            out.append((logits, regctr))
+        return out
+
+    def run_fcos_post(self, head_out, cand_cap=None):
+        """fcos_outputs.py:372-495 on device.  Returns fixed-size detection buffers (dict of tensors):
+        boxes [N,R,4], scores [N,R], classes [N,R] (int64), locations [N,R,2], count [N] (int32),
+        cand_count [N,L] (int32; > cand_cap means overflow)."""
+        cfg = self.cfg
+        n = head_out[0][0].n
+        L = len(head_out)
+        ncls = head_out[0][0].c
+        pre = cfg.MODEL.FCOS.PRE_NMS_TOPK_TEST
+        post = cfg.MODEL.FCOS.POST_NMS_TOPK_TEST
+        cap = cand_cap or max(2048, 2 * pre)
+        B = self.buffer
+        cb = dict(boxes=B("cand_boxes", (n, L, cap, 4), torch.float32, False), score=B("cand_score", (n, L, cap), torch.float32, False),
+                  cls=B("cand_cls", (n, L, cap), torch.int32, False), flat=B("cand_flat", (n, L, cap), torch.int32, False),
+                  count=B("cand_count", (n, L), torch.int32))
+        cb["count"].zero_()
+        cand = lib.cand_buffers(cb["boxes"], cb["score"], cb["cls"], cb["flat"], cb["count"])
+        strides = list(cfg.MODEL.FCOS.FPN_STRIDES)
+        for l, (logits, regctr) in enumerate(head_out):
+            lib.fcos_decode(logits.view, regctr.view, strides[l], float(cfg.MODEL.FCOS.INFERENCE_TH_TEST),
+                            bool(cfg.MODEL.FCOS.THRESH_WITH_CTR), l, L, cap, cand)
+        det = dict(boxes=B("det_boxes", (n, post, 4), torch.float32, False), scores=B("det_scores", (n, post), torch.float32, False),
+                   classes=B("det_classes", (n, post), torch.int64, False), locations=B("det_locs", (n, post, 2), torch.float32, False),
+                   count=B("det_count", (n,), torch.int32, False))
+        lw_key = ("level_w", tuple(h[0].w for h in head_out))
+        if lw_key not in self._bufs:
+            self._bufs[lw_key] = (torch.tensor([h[0].w for h in head_out], dtype=torch.int32, device=self.device),
+                                  torch.tensor(strides[:L], dtype=torch.int32, device=self.device))
+        level_w, level_s = self._bufs[lw_key]
+        wsp = B("select_ws", (lib.fcos_select_workspace(n, L, cap),), torch.uint8, False)
+        lib.fcos_select(cand, n, L, cap, level_w, level_s, ncls, min(pre, cap), float(cfg.MODEL.FCOS.NMS_TH), post,
+                        lib.det_buffers(det["boxes"], det["scores"], det["classes"], det["locations"], det["count"]), wsp)
+        det["cand_count"] = cb["count"]
+        det["cand_cap"] = cap
+        return det
+
+    # =============================================================================================
+    # ROI heads: SAG-Mask + MaskIoU
+    # =============================================================================================
+    def pack_roi_heads(self, sd, prefix=""):
+        cfg, dt, dev, tc = self.cfg, self.dtype, self.device, self.tc
+        P = {}
+        mh = cfg.MODEL.ROI_MASK_HEAD
+        c = sd[prefix + "mask_head.mask_fcn1.weight"].shape[1] if mh.NUM_CONV > 0 else sd[prefix + "mask_head.deconv.weight"].shape[0]
+        P["in_ch"] = c
+        P["mask_fcn"] = []
+        for k in range(mh.NUM_CONV):
+            P["mask_fcn"].append(packing.conv_bias(sd, prefix + "mask_head.mask_fcn{}".format(k + 1), [c], 1, 1, True, dt, dev, tc))
+            c = mh.CONV_DIM
+        P["sam_w"] = sd[prefix + "mask_head.spatialAtt.conv.weight"].detach().reshape(18).to(device=dev, dtype=torch.float32).contiguous()
+        P["deconv"] = packing.deconv2x2(sd, prefix + "mask_head.deconv", dt, dev, tc)
+        pw = sd[prefix + "mask_head.predictor.weight"].detach()
+        P["pred_w"] = pw.reshape(pw.shape[0], pw.shape[1]).to(device=dev, dtype=torch.float32).contiguous()
+        P["pred_b"] = sd[prefix + "mask_head.predictor.bias"].detach().to(device=dev, dtype=torch.float32).contiguous()
+        if cfg.MODEL.MASKIOU_ON:
+            mi = cfg.MODEL.ROI_MASKIOU_HEAD
+            P["iou_fcn"] = []
+            src = [P["in_ch"], 1]
+            for k in range(mi.NUM_CONV):
+                stride = 2 if k + 1 == mi.NUM_CONV else 1
+                wk = prefix + "maskiou_head.maskiou_fcn{}".format(k + 1)
+                if k == 0:
+                    # input = cat(roi feature, pooled mask) (maskiou_head.py:109-112); the single mask channel
+                    # lives in a 16-channel zero-padded buffer so that the TC engine can read it
+                    w = sd[wk + ".weight"].detach().float()
+                    wpad = torch.zeros((w.shape[0], P["in_ch"] + 16, 3, 3))
+                    wpad[:, :P["in_ch"] + 1] = w
+                    P["iou_fcn"].append(packing.ConvW(wpad, [P["in_ch"], 16], stride, 1, None, sd[wk + ".bias"], True, dt, dev, tc))
+                else:
+                    P["iou_fcn"].append(packing.conv_bias(sd, wk, [mi.CONV_DIM], stride, 1, True, dt, dev, tc))
+            r = mh.POOLER_RESOLUTION // 2
+            P["iou_fc1"] = packing.linear(sd, prefix + "maskiou_head.maskiou_fc1", True, dt, dev, tc, chw=(mi.CONV_DIM, r, r))
+            P["iou_fc2"] = packing.linear(sd, prefix + "maskiou_head.maskiou_fc2", True, dt, dev, tc)
+            P["iou_out"] = packing.linear(sd, prefix + "maskiou_head.maskiou", False, dt, dev, tc)
+        return P
+
+    def run_roi_heads(self, feats, strides, det, image_sizes, P):
+        """center_heads.py:413-444 on fixed-size ROI slots [N*R].  feats: list of FMap (p3..p5).
+        Returns (mask probs f32 [N*R, 1, 2*res, 2*res], mask_scores f32 [N*R] or None)."""
+        cfg = self.cfg
+        mh = cfg.MODEL.ROI_MASK_HEAD
+        n, r_cap = det["boxes"].shape[0], det["boxes"].shape[1]
+        R = n * r_cap
+        res = mh.POOLER_RESOLUTION
+        key = ("img_area", tuple(image_sizes))
+        if key not in self._bufs:
+            self._bufs[key] = torch.tensor([float(h * w) for h, w in image_sizes], dtype=torch.float32, device=self.device)
+        area = self._bufs[key]
+        roi = self.fmap("roi_feat", R, res, res, P["in_ch"])
+        crit = 0 if mh.ASSIGN_CRITERION == "ratio" else 1
+        lib.roialign_fpn([f.view for f in feats], strides, det["boxes"], det["count"], n, r_cap, area, crit,
+                         int(mh.POOLER_SAMPLING_RATIO), roi.view)
+        x = roi
+        for k, w in enumerate(P["mask_fcn"]):
+            x = self.conv("mask_fcn{}".format(k + 1), [x], w)
+        att = self.fmap("mask_att", R, res, res, x.c)
+        lib.spatial_attention(x.view, att.view, P["sam_w"])
+        up = self.conv("mask_deconv", [att], P["deconv"], out_mode=1, out_halo=0)
+        probs = self.buffer("mask_probs", (R, 1, 2 * res, 2 * res), torch.float32, False)
+        ncls = P["pred_w"].shape[0]
+        classes = det["classes"].reshape(-1)
+        lib.mask_predict(up.view, P["pred_w"], P["pred_b"], classes, ncls, probs)
+        mask_scores = None
+        if cfg.MODEL.MASKIOU_ON:
+            pm = self.fmap("iou_mask", R, res, res, 16)
+            lib.maskiou_prep(probs, pm.view)
+            y = None
+            for k, w in enumerate(P["iou_fcn"]):
+                last = k + 1 == len(P["iou_fcn"])
+                srcs = [roi, pm] if k == 0 else [y]
+                y = self.conv("iou_fcn{}".format(k + 1), srcs, w, out_halo=0 if last else 1)
+            flat = FMap(y.buf.reshape(R, 1, 1, -1), 0)
+            y = self.conv("iou_fc1", [flat], P["iou_fc1"], out_halo=0)
+            y = self.conv("iou_fc2", [y], P["iou_fc2"], out_halo=0)
+            y = self.conv("iou_out", [y], P["iou_out"], out_dtype=torch.float32, out_halo=0)
+            mask_scores = self.buffer("mask_scores", (R,), torch.float32, False)
+            lib.maskiou_score(y.buf, R, y.c, classes, det["scores"].reshape(-1), mask_scores)
+        return probs, mask_scores
+
+    # =============================================================================================
+    # input / output side
+    # =============================================================================================
+    def preprocess(self, images, size_divisibility=32):
+        """GeneralizedRCNN.preprocess_image [d2] (deploy_utils.py:76-98): normalise + pad to /32.
+        ``images``: list of CHW device tensors (float32 or uint8, BGR)."""
+        cfg = self.cfg
+        sizes = [(int(im.shape[-2]), int(im.shape[-1])) for im in images]
+        hp = max(s[0] for s in sizes)
+        wp = max(s[1] for s in sizes)
+        hp = (hp + size_divisibility - 1) // size_divisibility * size_divisibility
+        wp = (wp + size_divisibility - 1) // size_divisibility * size_divisibility
+        x = self.fmap("input", len(images), hp, wp, 3)
+        for i, im in enumerate(images):
+            lib.preprocess_image(im.contiguous(), cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD, x.view, i)
+        return x, sizes
+
+    def paste(self, probs, boxes, out_h, out_w, image_size, threshold=0.5):
+        """detector_postprocess [d2] for the slots of one image: returns (boxes', valid u8, masks u8 [R,H,W])."""
+        r = boxes.shape[0]
+        sx, sy = out_w / image_size[1], out_h / image_size[0]
+        b2 = torch.empty_like(boxes)
+        valid = torch.empty((r,), dtype=torch.uint8, device=self.device)
+        lib.scale_clip_boxes(boxes, b2, valid, r, sx, sy, float(out_w), float(out_h))
+        masks = torch.empty((r, out_h, out_w), dtype=torch.uint8, device=self.device)
+        m = probs.shape[-1]
+        lib.paste_masks(probs, b2, valid, masks, r, m, out_h, out_w, threshold)
+        return b2, valid, masks

@@ -1,0 +1,295 @@
+"""ctypes binding of ``libcm2.so`` (``include/cm2.h``).
+
+There is no CPU fallback and no torch-op fallback: if the library is missing, or a call fails, a
+``RuntimeError`` is raised.  All functions enqueue on ``torch.cuda.current_stream()``.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcm2.so")
+
+F32, BF16, U8 = 0, 1, 2
+ENGINE_SIMT, ENGINE_TC = 0, 1
+MAX_SRC = 8
+
+_DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.uint8: U8}
+
+
+class Act(C.Structure):
+    """cm2_act: pitched NHWC view."""
+    _fields_ = [("data", C.c_void_p), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+                ("sn", C.c_int64), ("sh", C.c_int64), ("sw", C.c_int64)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("out_dtype", C.c_int32), ("engine", C.c_int32), ("num_src", C.c_int32),
+                ("src", Act * MAX_SRC),
+                ("cout", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+                ("weight", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("relu", C.c_int32), ("in_relu", C.c_int32),
+                ("residual", Act), ("res_mode", C.c_int32), ("out_mode", C.c_int32),
+                ("out", Act), ("chan_sum", C.c_void_p)]
+
+
+class CandBuffers(C.Structure):
+    _fields_ = [("boxes", C.c_void_p), ("score", C.c_void_p), ("cls", C.c_void_p), ("flat", C.c_void_p),
+                ("count", C.c_void_p)]
+
+
+class DetBuffers(C.Structure):
+    _fields_ = [("boxes", C.c_void_p), ("scores", C.c_void_p), ("classes", C.c_void_p), ("locations", C.c_void_p),
+                ("count", C.c_void_p)]
+
+
+# every symbol include/cm2.h declares: name -> (restype, argtypes)
+_P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+_AP = C.POINTER(Act)
+SYMBOLS = {
+    "cm2_version": (_I, []),
+    "cm2_last_error": (C.c_char_p, []),
+    "cm2_device_info": (_I, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "cm2_conv2d": (_I, [C.POINTER(ConvDesc), _P]),
+    "cm2_conv_tc_klen": (_L, [_I, _I, _I, C.POINTER(_I)]),
+    "cm2_conv_tc_supported": (_I, [C.POINTER(ConvDesc)]),
+    "cm2_preprocess_image": (_I, [_P, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _AP, _I, _I, _P]),
+    "cm2_maxpool3x3s2_ceil": (_I, [_AP, _AP, _I, _P]),
+    "cm2_ese_pool_chunks": (_I, [_I]),
+    "cm2_ese_pool": (_I, [_AP, _I, _P, _P, _P]),
+    "cm2_ese_gate": (_I, [_P, _F, _P, _P, _P, _I, _I, _P]),
+    "cm2_ese_apply": (_I, [_AP, _P, _AP, _AP, _I, _P]),
+    "cm2_gn_workspace_floats": (_L, [_I, _I, _I, _I]),
+    "cm2_groupnorm_relu": (_I, [_AP, _I, _I, _P, _P, _F, _I, _P, _P]),
+    "cm2_relu": (_I, [_AP, _AP, _I, _P]),
+    "cm2_fcos_decode": (_I, [_AP, _AP, _I, _F, _I, _I, _I, _I, C.POINTER(CandBuffers), _P]),
+    "cm2_fcos_select_workspace": (_L, [_I, _I, _I]),
+    "cm2_fcos_select": (_I, [C.POINTER(CandBuffers), _I, _I, _I, C.POINTER(_I), C.POINTER(_I), _I, _I, _F, _I,
+                             C.POINTER(DetBuffers), _P, _P]),
+    "cm2_roialign_fpn": (_I, [_AP, C.POINTER(_I), _I, _I, _P, _P, _I, _I, _P, _I, _I, _AP, _P, _P]),
+    "cm2_spatial_attention": (_I, [_AP, _AP, _I, _P, _P]),
+    "cm2_mask_predict": (_I, [_AP, _I, _P, _P, _P, _I, _P, _P]),
+    "cm2_maskiou_prep": (_I, [_P, _AP, _I, _P]),
+    "cm2_maskiou_score": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
+    "cm2_scale_clip_boxes": (_I, [_P, _P, _P, _I, _F, _F, _F, _F, _P]),
+    "cm2_paste_masks": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
+}
+
+_lib = None
+launch_count = 0          # incremented by every kernel-launching call (bench.py reports it)
+
+
+def load():
+    """Load ``libcm2.so`` and bind every symbol of ``include/cm2.h``; raise if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("{} not found: run `python -m centermask2_b200.build` (there is no fallback path)".format(LIB_PATH))
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            raise RuntimeError("libcm2.so does not export {}".format(name))
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().cm2_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("{} failed ({}): {}".format(what, rc, last_error()))
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dtype_code(t):
+    return _DTYPES[t.dtype if isinstance(t, torch.Tensor) else t]
+
+
+def act(t):
+    """``cm2_act`` of a 4-D NHWC tensor/view [n, h, w, c] whose channel stride is 1."""
+    if t is None:
+        return Act()
+    assert t.dim() == 4 and (t.stride(3) == 1 or t.shape[3] == 1), (t.shape, t.stride())
+    return Act(t.data_ptr(), t.shape[0], t.shape[1], t.shape[2], t.shape[3], t.stride(0), t.stride(1), t.stride(2))
+
+
+def ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _count(k=1):
+    global launch_count
+    launch_count += k
+
+
+# ------------------------------------------------------------------------------------------------
+# thin wrappers (one per entry point)
+# ------------------------------------------------------------------------------------------------
+def conv2d(srcs, weight, out, cout, k, stride, pad, scale=None, shift=None, relu=False, in_relu=False,
+           residual=None, res_mode=0, out_mode=0, engine=ENGINE_SIMT, chan_sum=None, probe=False):
+    """Enqueue one convolution.  With ``probe=True`` (TC engine) the descriptor is first checked with
+    ``cm2_conv_tc_supported``; returns False without launching if the engine does not take it."""
+    d = ConvDesc()
+    d.dtype = dtype_code(srcs[0])
+    d.out_dtype = dtype_code(out)
+    d.engine = engine
+    d.num_src = len(srcs)
+    for i, s in enumerate(srcs):
+        d.src[i] = act(s)
+    d.cout, d.kh, d.kw, d.stride, d.pad = cout, k, k, stride, pad
+    d.weight = weight.data_ptr()
+    d.scale = 0 if scale is None else scale.data_ptr()
+    d.shift = 0 if shift is None else shift.data_ptr()
+    d.relu, d.in_relu = int(relu), int(in_relu)
+    d.residual = act(residual)
+    d.res_mode = res_mode if residual is not None else 0
+    d.out_mode = out_mode
+    d.out = act(out)
+    d.chan_sum = 0 if chan_sum is None else chan_sum.data_ptr()
+    if probe and not load().cm2_conv_tc_supported(C.byref(d)):
+        return False
+    check(load().cm2_conv2d(C.byref(d), stream()), "cm2_conv2d")
+    _count()
+    return True
+
+
+def conv_tc_klen(k, src_c):
+    arr = (C.c_int32 * len(src_c))(*src_c)
+    return int(load().cm2_conv_tc_klen(k, k, len(src_c), arr))
+
+
+def preprocess_image(img, mean, std, out, index):
+    m = (C.c_float * 3)(*mean)
+    s = (C.c_float * 3)(*std)
+    a = act(out)
+    check(load().cm2_preprocess_image(ptr(img), dtype_code(img), img.shape[1], img.shape[2], m, s, C.byref(a),
+                                      dtype_code(out), index, stream()), "cm2_preprocess_image")
+    _count()
+
+
+def maxpool3x3s2_ceil(x, out):
+    a, b = act(x), act(out)
+    check(load().cm2_maxpool3x3s2_ceil(C.byref(a), C.byref(b), dtype_code(x), stream()), "cm2_maxpool3x3s2_ceil")
+    _count()
+
+
+def ese_pool_chunks(hw):
+    return int(load().cm2_ese_pool_chunks(hw))
+
+
+def ese_pool(x, workspace, pooled):
+    a = act(x)
+    check(load().cm2_ese_pool(C.byref(a), dtype_code(x), ptr(workspace), ptr(pooled), stream()), "cm2_ese_pool")
+    _count(2)
+
+
+def ese_gate(pooled, inv_count, fc_w, fc_b, gate, n, c):
+    check(load().cm2_ese_gate(ptr(pooled), inv_count, ptr(fc_w), ptr(fc_b), ptr(gate), n, c, stream()), "cm2_ese_gate")
+    _count()
+
+
+def ese_apply(x, gate, identity, out):
+    a, i, o = act(x), act(identity), act(out)
+    check(load().cm2_ese_apply(C.byref(a), ptr(gate), C.byref(i), C.byref(o), dtype_code(x), stream()), "cm2_ese_apply")
+    _count()
+
+
+def gn_workspace_floats(n, hw, c, groups):
+    return int(load().cm2_gn_workspace_floats(n, hw, c, groups))
+
+
+def groupnorm_relu(x, groups, gamma, beta, eps, relu, workspace):
+    a = act(x)
+    check(load().cm2_groupnorm_relu(C.byref(a), dtype_code(x), groups, ptr(gamma), ptr(beta), eps, int(relu),
+                                    ptr(workspace), stream()), "cm2_groupnorm_relu")
+    _count(3)
+
+
+def relu(x, out):
+    a, o = act(x), act(out)
+    check(load().cm2_relu(C.byref(a), C.byref(o), dtype_code(x), stream()), "cm2_relu")
+    _count()
+
+
+def cand_buffers(boxes, score, cls, flat, count):
+    return CandBuffers(boxes.data_ptr(), score.data_ptr(), cls.data_ptr(), flat.data_ptr(), count.data_ptr())
+
+
+def det_buffers(boxes, scores, classes, locations, count):
+    return DetBuffers(boxes.data_ptr(), scores.data_ptr(), classes.data_ptr(), locations.data_ptr(), count.data_ptr())
+
+
+def fcos_decode(logits, regctr, stride, thresh, thresh_with_ctr, level, num_levels, cap, cand):
+    a, b = act(logits), act(regctr)
+    check(load().cm2_fcos_decode(C.byref(a), C.byref(b), stride, thresh, int(thresh_with_ctr), level, num_levels, cap,
+                                 C.byref(cand), stream()), "cm2_fcos_decode")
+    _count()
+
+
+def fcos_select_workspace(n, num_levels, cap):
+    return int(load().cm2_fcos_select_workspace(n, num_levels, cap))
+
+
+def fcos_select(cand, n, num_levels, cap, level_w, level_stride, ncls, pre_topk, nms_thresh, post_topk, det, workspace):
+    check(load().cm2_fcos_select(C.byref(cand), n, num_levels, cap, C.cast(ptr(level_w), C.POINTER(C.c_int32)),
+                                 C.cast(ptr(level_stride), C.POINTER(C.c_int32)), ncls, pre_topk, nms_thresh, post_topk,
+                                 C.byref(det), ptr(workspace), stream()), "cm2_fcos_select")
+    _count(2)
+
+
+def roialign_fpn(feats, strides, boxes, det_count, n, r_cap, image_area, crit, sampling_ratio, out, level_out=None):
+    arr = (Act * len(feats))(*[act(f) for f in feats])
+    st = (C.c_int32 * len(strides))(*strides)
+    o = act(out)
+    check(load().cm2_roialign_fpn(arr, st, len(feats), dtype_code(feats[0]), ptr(boxes), ptr(det_count), n, r_cap,
+                                  ptr(image_area), crit, sampling_ratio, C.byref(o), ptr(level_out), stream()),
+          "cm2_roialign_fpn")
+    _count()
+
+
+def spatial_attention(x, out, w18):
+    a, o = act(x), act(out)
+    check(load().cm2_spatial_attention(C.byref(a), C.byref(o), dtype_code(x), ptr(w18), stream()), "cm2_spatial_attention")
+    _count()
+
+
+def mask_predict(x, wp, bp, classes, ncls, probs):
+    a = act(x)
+    check(load().cm2_mask_predict(C.byref(a), dtype_code(x), ptr(wp), ptr(bp), ptr(classes), ncls, ptr(probs), stream()),
+          "cm2_mask_predict")
+    _count()
+
+
+def maskiou_prep(probs, out):
+    o = act(out)
+    check(load().cm2_maskiou_prep(ptr(probs), C.byref(o), dtype_code(out), stream()), "cm2_maskiou_prep")
+    _count()
+
+
+def maskiou_score(iou, r, ncls, classes, scores, mask_scores):
+    check(load().cm2_maskiou_score(ptr(iou), dtype_code(iou), r, ncls, ptr(classes), ptr(scores), ptr(mask_scores),
+                                   stream()), "cm2_maskiou_score")
+    _count()
+
+
+def scale_clip_boxes(boxes_in, boxes_out, valid, r, sx, sy, out_w, out_h):
+    check(load().cm2_scale_clip_boxes(ptr(boxes_in), ptr(boxes_out), ptr(valid), r, sx, sy, out_w, out_h, stream()),
+          "cm2_scale_clip_boxes")
+    _count()
+
+
+def paste_masks(probs, boxes, valid, out, r, m, out_h, out_w, threshold):
+    check(load().cm2_paste_masks(ptr(probs), ptr(boxes), ptr(valid), ptr(out), r, m, out_h, out_w, threshold, stream()),
+          "cm2_paste_masks")
+    _count()

@@ -1,0 +1,65 @@
+"""Parameter trees with the reference's ``state_dict`` key names.
+
+The reference's modules are deep trees of tiny ``nn.Module``s (one per conv / norm / relu, some with
+"/" in their names, e.g. ``stem.stem_1/conv``).  The B200 plug-ins keep the *names* -- so that a
+checkpoint written by the reference loads with ``load_state_dict`` -- but the leaves are plain
+parameters/buffers hung on empty container modules; all compute happens in ``libcm2.so`` on packed
+copies (``packing.py``).
+"""
+import torch
+from torch import nn
+
+_BUFFER_KINDS = ("bn_weight", "bn_bias", "bn_mean", "bn_var")        # FrozenBatchNorm2d holds buffers [d2]
+
+
+def _default(kind, shape):
+    """Identity-like defaults (real values come from ``load_state_dict``)."""
+    if kind in ("bn_weight", "gn_weight", "scale"):
+        return torch.ones(shape)
+    if kind == "bn_var":
+        return torch.ones(shape) - 1e-5                              # FrozenBatchNorm2d init [d2]
+    if len(shape) >= 2:
+        fan_in = 1
+        for d in shape[1:]:
+            fan_in *= d
+        return torch.randn(shape) * (1.0 / fan_in) ** 0.5
+    return torch.zeros(shape)
+
+
+def attach_params(root, spec):
+    """Create ``root.<a>.<b>.<leaf>`` for every key ``a.b.leaf`` of ``spec`` ({key: (shape, kind)})."""
+    for key, (shape, kind) in spec.items():
+        parts = key.split(".")
+        mod = root
+        for p in parts[:-1]:
+            if p not in mod._modules:
+                mod.add_module(p, nn.Module())
+            mod = mod._modules[p]
+        value = _default(kind, tuple(shape))
+        if kind in _BUFFER_KINDS:
+            mod.register_buffer(parts[-1], value)
+        else:
+            mod.register_parameter(parts[-1], nn.Parameter(value, requires_grad=False))
+
+
+class PackedModule(nn.Module):
+    """Base of the plug-ins: owns reference-named parameters and a lazily built packed copy."""
+
+    def __init__(self):
+        super().__init__()
+        self.training = False
+        self._packed = None
+        self._engine = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+
+    def _invalidate(self):
+        self._packed = None
+
+    def _apply(self, fn, *a, **k):
+        self._invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def train(self, mode=True):
+        if mode:
+            raise NotImplementedError("centermask2_b200 implements the inference path only (training is out of scope)")
+        return super().train(False)

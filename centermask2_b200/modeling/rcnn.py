@@ -1,0 +1,127 @@
+"""``GeneralizedRCNN`` (inference) over the B200 plug-ins.
+
+Call sequence of detectron2's ``GeneralizedRCNN.inference`` [d2] as mirrored in-tree by the reference
+at ``/root/reference/tester.py:24-75``; the tensor-in / tuple-out variant follows
+``/root/reference/modified_class.py:27-40`` and ``deploy_utils.py:117-126``.
+"""
+import torch
+from torch import nn
+
+from .. import runtime
+from .compat import (BACKBONE_REGISTRY, META_ARCH_REGISTRY, PROPOSAL_GENERATOR_REGISTRY, ROI_HEADS_REGISTRY, Boxes,
+                     ImageList, Instances, ShapeSpec)
+from .fcos import instances_from_det
+
+
+class _Sizes(object):
+    """What FCOS / ROI heads read from an ImageList: ``len()`` and ``.image_sizes``."""
+
+    def __init__(self, image_sizes):
+        self.image_sizes = [tuple(s) for s in image_sizes]
+
+    def __len__(self):
+        return len(self.image_sizes)
+
+
+class GeneralizedRCNN(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.backbone = BACKBONE_REGISTRY.get(cfg.MODEL.BACKBONE.NAME)(cfg, ShapeSpec(channels=len(cfg.MODEL.PIXEL_MEAN)))
+        shape = self.backbone.output_shape()
+        self.proposal_generator = PROPOSAL_GENERATOR_REGISTRY.get(cfg.MODEL.PROPOSAL_GENERATOR.NAME)(cfg, shape)
+        self.roi_heads = ROI_HEADS_REGISTRY.get(cfg.MODEL.ROI_HEADS.NAME)(cfg, shape)
+        self.register_buffer("pixel_mean", torch.tensor(cfg.MODEL.PIXEL_MEAN).view(-1, 1, 1), False)
+        self.register_buffer("pixel_std", torch.tensor(cfg.MODEL.PIXEL_STD).view(-1, 1, 1), False)
+        self.train(False)
+
+    def train(self, mode=True):
+        if mode:
+            raise NotImplementedError("inference only")
+        return super().train(False)
+
+    @property
+    def device(self):
+        return runtime.engine_for(self.cfg).device
+
+    # -- the reference-facing call -------------------------------------------------------------
+    def forward(self, batched_inputs):
+        return self.inference(batched_inputs)
+
+    @torch.no_grad()
+    def inference(self, batched_inputs, detected_instances=None, do_postprocess=True):
+        """list[{"image": [3,H,W] BGR (float or uint8), "height", "width"}] -> list[{"instances": Instances}]."""
+        eng = runtime.engine_for(self.cfg)
+        images = [b["image"].to(eng.device, non_blocking=True) for b in batched_inputs]
+        x, sizes = eng.preprocess(images, self.backbone.size_divisibility)
+        feats = self.backbone.forward_fmap(x)
+        if detected_instances is None:
+            det = self.proposal_generator.detect([feats[f] for f in self.proposal_generator.in_features])
+            results = instances_from_det(det, sizes)
+        else:
+            results = [i.to(eng.device) for i in detected_instances]
+        results = self.roi_heads.forward_with_given_boxes({k: v.nchw() for k, v in feats.items()}, results)
+        if not do_postprocess:
+            return results
+        out = []
+        for inst, b, size in zip(results, batched_inputs, sizes):
+            out.append({"instances": self.detector_postprocess(inst, b.get("height", size[0]), b.get("width", size[1]))})
+        return out
+
+    def preprocess_image(self, batched_inputs):
+        """[d2] API parity: returns an ``ImageList`` whose tensor is the normalised padded batch [N,3,H,W]."""
+        eng = runtime.engine_for(self.cfg)
+        images = [b["image"].to(eng.device) for b in batched_inputs]
+        x, sizes = eng.preprocess(images, self.backbone.size_divisibility)
+        return ImageList(x.nchw(), sizes)
+
+    def detector_postprocess(self, results, output_height, output_width, mask_threshold=0.5):
+        """detector_postprocess + paste_masks_in_image [d2] (fork restatement: deploy_utils.py:129-158)."""
+        eng = runtime.engine_for(self.cfg)
+        out = Instances((output_height, output_width))
+        r = len(results)
+        boxes = results.pred_boxes.tensor.contiguous()
+        if results.has("pred_masks") and r > 0:
+            b2, valid, masks = eng.paste(results.pred_masks.contiguous(), boxes, output_height, output_width,
+                                         results.image_size, mask_threshold)
+        else:
+            b2 = boxes.clone()
+            b2[:, 0::2] = (b2[:, 0::2] * (output_width / results.image_size[1])).clamp(0, output_width)
+            b2[:, 1::2] = (b2[:, 1::2] * (output_height / results.image_size[0])).clamp(0, output_height)
+            valid = ((b2[:, 2] - b2[:, 0]) > 0) & ((b2[:, 3] - b2[:, 1]) > 0)
+            masks = None
+        keep = valid.bool()
+        out.pred_boxes = Boxes(b2[keep])
+        for k, v in results.get_fields().items():
+            if k in ("pred_boxes", "pred_masks"):
+                continue
+            out.set(k, v[keep])
+        if masks is not None:
+            out.pred_masks = masks[keep].bool()
+        elif results.has("pred_masks"):
+            out.pred_masks = torch.zeros((0, output_height, output_width), dtype=torch.bool, device=boxes.device)
+        return out
+
+    # -- the fork's export-friendly variant ------------------------------------------------------
+    @torch.no_grad()
+    def forward_tensor(self, img):
+        """``modified_class.py:27-40``: already normalised + padded ``img[1,3,H,W]`` -> 6-tuple
+        (locations, mask_scores, pred_boxes, pred_classes, pred_masks, scores) of batch element 0."""
+        features = self.backbone(img)
+        sizes = _Sizes([(img.shape[-2], img.shape[-1])] * img.shape[0])
+        proposals, _ = self.proposal_generator(sizes, features, None)
+        results, _ = self.roi_heads(sizes, features, proposals, None)
+        r = results[0]
+        ms = r.mask_scores if r.has("mask_scores") else r.scores.new_zeros((0,))
+        pm = r.pred_masks if r.has("pred_masks") else r.scores.new_zeros((0, 1, 28, 28))
+        return r.locations, ms, r.pred_boxes.tensor, r.pred_classes, pm, r.scores
+
+
+def _register():
+    m = getattr(META_ARCH_REGISTRY, "_obj_map", getattr(META_ARCH_REGISTRY, "_map", None))
+    if m is not None and "GeneralizedRCNN" in m:
+        m.pop("GeneralizedRCNN")            # same move as the reference: convert_model_into_onnx.py:30-31
+    META_ARCH_REGISTRY.register(GeneralizedRCNN)
+
+
+_register()

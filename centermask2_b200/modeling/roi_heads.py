@@ -1,0 +1,109 @@
+"""``CenterROIHeads`` with the SAG-Mask head and the MaskIoU head on libcm2.
+
+Replaces ``centermask/modeling/centermask/center_heads.py:295-553`` (inference branches),
+``pooler.py:192-366`` (ROIPooler eager path), ``sam.py:12-97`` (SpatialAttention(MaskHead)),
+``mask_head.py:174-216`` (mask_rcnn_inference) and ``maskiou_head.py:50-120``.
+"""
+import torch
+
+from .. import runtime
+from ..arch import roi_heads_param_spec
+from ..engine import as_fmap
+from .compat import ROI_HEADS_REGISTRY, Registry
+from .params import PackedModule, attach_params
+
+# The reference registers its heads in two more registries (mask_head.py:17, maskiou_head.py:10);
+# the names are kept so that cfg.MODEL.ROI_MASK_HEAD.NAME / ROI_MASKIOU_HEAD.NAME resolve.
+ROI_MASK_HEAD_REGISTRY = Registry("ROI_MASK_HEAD")
+ROI_MASKIOU_HEAD_REGISTRY = Registry("ROI_MASKIOU_HEAD")
+
+
+@ROI_MASK_HEAD_REGISTRY.register()
+class SpatialAttentionMaskHead(object):
+    """Marker for ``cfg.MODEL.ROI_MASK_HEAD.NAME`` (sam.py:31); its parameters live under
+    ``CenterROIHeads.mask_head.*`` and its compute is part of the fused ROI plan."""
+
+
+@ROI_MASKIOU_HEAD_REGISTRY.register()
+class MaskIoUHead(object):
+    """Marker for ``cfg.MODEL.ROI_MASKIOU_HEAD.NAME`` (maskiou_head.py:63)."""
+
+
+@ROI_HEADS_REGISTRY.register()
+class CenterROIHeads(PackedModule):
+    def __init__(self, cfg, input_shape):
+        super().__init__()
+        self.cfg = cfg
+        self.in_features = list(cfg.MODEL.ROI_HEADS.IN_FEATURES)                 # center_heads.py:121
+        self.mask_on = bool(cfg.MODEL.MASK_ON)
+        self.maskiou_on = bool(cfg.MODEL.MASKIOU_ON)
+        if cfg.MODEL.KEYPOINT_ON:
+            raise NotImplementedError("KEYPOINT_ON is out of scope (false in every reference config)")
+        ROI_MASK_HEAD_REGISTRY.get(cfg.MODEL.ROI_MASK_HEAD.NAME)
+        if self.maskiou_on:
+            ROI_MASKIOU_HEAD_REGISTRY.get(cfg.MODEL.ROI_MASKIOU_HEAD.NAME)
+        chans = {input_shape[f].channels for f in self.in_features}
+        assert len(chans) == 1, chans                                            # center_heads.py:327
+        self.strides = [input_shape[f].stride for f in self.in_features]
+        attach_params(self, roi_heads_param_spec(cfg, chans.pop()))
+
+    def _pack(self):
+        eng = runtime.engine_for(self.cfg)
+        if self._packed is None or self._engine is not eng:
+            self._packed = eng.pack_roi_heads(self.state_dict())
+            self._engine = eng
+        return eng, self._packed
+
+    def run(self, feats, det, image_sizes):
+        """Device-only: feats list of FMaps, det fixed-size buffers -> (probs [N*R,1,m,m], mask_scores [N*R])."""
+        eng, P = self._pack()
+        return eng.run_roi_heads(feats, self.strides, det, image_sizes, P)
+
+    def forward(self, images, features, proposals, targets=None):
+        """center_heads.py:384-411 (inference): returns ``(list[Instances], {})``."""
+        assert targets is None and not self.training, "inference only"
+        return self.forward_with_given_boxes(features, proposals), {}
+
+    def forward_with_given_boxes(self, features, instances):
+        """center_heads.py:413-444: adds ``pred_masks`` [R,1,28,28] and, when the batch has at least one
+        detection, ``mask_scores`` [R] to the *same* Instances objects and returns them."""
+        assert instances[0].has("pred_boxes") and instances[0].has("pred_classes")
+        if not self.mask_on:
+            return instances
+        eng, _ = self._pack()
+        feats = [as_fmap(features[f], eng.dtype, eng.device) for f in self.in_features]
+        det = _det_from_instances(instances, eng)
+        sizes = [tuple(i.image_size) for i in instances]
+        probs, mask_scores = self.run(feats, det, sizes)
+        r_cap = det["boxes"].shape[1]
+        total = sum(len(i) for i in instances)
+        for k, inst in enumerate(instances):
+            m = len(inst)
+            inst.pred_masks = probs[k * r_cap:k * r_cap + m].clone()              # mask_head.py:215-216
+            if self.maskiou_on and total > 0:                                     # center_heads.py:511-517
+                inst.mask_scores = mask_scores[k * r_cap:k * r_cap + m].clone()   # maskiou_head.py:59-60
+        return instances
+
+
+def _det_from_instances(instances, eng):
+    """Fixed-size ROI slot buffers for a list of Instances: reuse FCOS's device buffers when the
+    Instances came from our own proposal generator, else pack the given boxes."""
+    tags = [getattr(i, "_cm2_det", None) for i in instances]
+    if all(t is not None for t in tags) and all(t[0] is tags[0][0] and t[1] == k for k, t in enumerate(tags)) \
+            and tags[0][0]["boxes"].shape[0] == len(instances):
+        return tags[0][0]
+    n = len(instances)
+    r_cap = max(1, max(len(i) for i in instances))
+    dev = eng.device
+    det = dict(boxes=torch.zeros((n, r_cap, 4), dtype=torch.float32, device=dev),
+               scores=torch.zeros((n, r_cap), dtype=torch.float32, device=dev),
+               classes=torch.zeros((n, r_cap), dtype=torch.int64, device=dev),
+               count=torch.tensor([len(i) for i in instances], dtype=torch.int32, device=dev))
+    for k, inst in enumerate(instances):
+        m = len(inst)
+        if m:
+            det["boxes"][k, :m] = inst.pred_boxes.tensor.to(dev)
+            det["classes"][k, :m] = inst.pred_classes.to(dev)
+            if inst.has("scores"):
+                det["scores"][k, :m] = inst.scores.to(dev)
+    return det

@@ -1,0 +1,82 @@
+"""One-time repacking of reference ``state_dict`` tensors into the layouts ``libcm2.so`` consumes.
+
+Packed buffers are derived data: they are rebuilt from the modules' parameters whenever those
+change and are never serialised (SURVEY.md 8b "Weights").
+"""
+import torch
+
+from . import lib
+
+BN_EPS = 1e-5          # detectron2 FrozenBatchNorm2d eps [d2]
+
+
+class ConvW(object):
+    """Packed weights of one convolution / linear layer.
+
+    ``w_simt``: [kh*kw*cin_total, cout] in the activation dtype (CM2_ENGINE_SIMT layout).
+    ``w_tc``  : [cout_pad16, k_tc] bf16, K-major with every source's channels padded to 64
+                (CM2_ENGINE_TC layout) -- only built for bf16 models.
+    ``scale`` / ``shift``: fp32 [cout] epilogue vectors (folded FrozenBN, or bias)."""
+
+    def __init__(self, weight, src_c, stride, pad, scale, shift, relu, dtype, device, build_tc):
+        cout, cin, kh, kw = weight.shape
+        assert cin == sum(src_c), (cin, src_c)
+        self.k, self.stride, self.pad, self.cout, self.src_c, self.relu = kh, stride, pad, cout, list(src_c), relu
+        w = weight.detach().to(torch.float32)
+        self.w_simt = w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous().to(device=device, dtype=dtype)
+        self.w_tc = None
+        if build_tc:
+            cout_pad = (cout + 15) // 16 * 16
+            parts = []
+            off = 0
+            for c in src_c:
+                cp = (c + 63) // 64 * 64
+                blk = torch.zeros((cout_pad, kh * kw, cp), dtype=torch.float32)
+                blk[:cout, :, :c] = w[:, off:off + c].permute(0, 2, 3, 1).reshape(cout, kh * kw, c)
+                parts.append(blk)
+                off += c
+            # k = (tap, source, channel): concatenate sources inside each tap
+            wt = torch.cat(parts, dim=2).reshape(cout_pad, -1)
+            assert wt.shape[1] == lib.conv_tc_klen(kh, src_c)
+            self.w_tc = wt.contiguous().to(device=device, dtype=torch.bfloat16)
+        self.scale = None if scale is None else scale.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.shift = None if shift is None else shift.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def fold_frozen_bn(weight, bias, mean, var, eps=BN_EPS):
+    """FrozenBatchNorm2d [d2]: y = (x - mean) * rsqrt(var + eps) * weight + bias  ->  scale, shift."""
+    scale = weight.to(torch.float32) * torch.rsqrt(var.to(torch.float32) + eps)
+    shift = bias.to(torch.float32) - mean.to(torch.float32) * scale
+    return scale, shift
+
+
+def conv_bn_relu(sd, prefix, src_c, stride, pad, dtype, device, tc):
+    """conv (no bias) -> FrozenBN -> ReLU unit, vovnet.py:205-236."""
+    scale, shift = fold_frozen_bn(sd[prefix + "/norm.weight"], sd[prefix + "/norm.bias"],
+                                  sd[prefix + "/norm.running_mean"], sd[prefix + "/norm.running_var"])
+    return ConvW(sd[prefix + "/conv.weight"], src_c, stride, pad, scale, shift, True, dtype, device, tc)
+
+
+def conv_bias(sd, prefix, src_c, stride, pad, relu, dtype, device, tc):
+    """conv with bias (no norm), optional ReLU."""
+    return ConvW(sd[prefix + ".weight"], src_c, stride, pad, None, sd[prefix + ".bias"], relu, dtype, device, tc)
+
+
+def deconv2x2(sd, prefix, dtype, device, tc):
+    """ConvTranspose2d(k=2, s=2) + bias + ReLU (sam.py:74-80) as a 1x1 convolution to 4*cout columns:
+    column j = (dy*2 + dx)*cout + co, scattered by the conv epilogue (out_mode 1)."""
+    w = sd[prefix + ".weight"]                      # [cin, cout, 2, 2]
+    cin, cout = w.shape[0], w.shape[1]
+    w4 = w.permute(2, 3, 1, 0).reshape(4 * cout, cin, 1, 1)
+    bias = sd[prefix + ".bias"].repeat(4)
+    return ConvW(w4, [cin], 1, 0, None, bias, True, dtype, device, tc)
+
+
+def linear(sd, prefix, relu, dtype, device, tc, chw=None):
+    """nn.Linear as a 1x1 convolution over a [r, 1, 1, k] view.  ``chw`` = (c, h, w) re-orders the
+    input features from the reference's flatten(C, H, W) order (maskiou_head.py:115) to NHWC."""
+    w = sd[prefix + ".weight"]
+    if chw is not None:
+        c, h, ww = chw
+        w = w.reshape(w.shape[0], c, h, ww).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+    return ConvW(w[:, :, None, None], [w.shape[1]], 1, 0, None, sd[prefix + ".bias"], relu, dtype, device, tc)

@@ -1,0 +1,244 @@
+/*
+ * cm2.h -- C ABI of libcm2.so: hand-written sm_100a kernels for the CenterMask2 inference path.
+ *
+ * The reference (Zeng-Yan/centermask2) is pure Python behind detectron2's registry; it has no FFI
+ * of its own.  The drop-in boundary is therefore the registry surface; this
+ * header is the layer *below* it: one entry point per kernel family, each replacing the torch /
+ * torchvision / detectron2 call the reference makes at the cited place.  Paths are relative to
+ * /root/reference/centermask2/centermask/ ; "[d2]" marks un-vendored detectron2 v0.5 code whose
+ * semantics are described in SURVEY.md Appendix A.
+ *
+ * Conventions
+ *   - Every function returns 0 (CM2_OK) or a negative CM2_ERR_* code; cm2_last_error() gives a
+ *     thread-local message.  Nothing throws or aborts.
+ *   - All pointers documented as device pointers are caller-allocated device memory; the library
+ *     never allocates, frees or retains device memory.
+ *   - `stream` is a cudaStream_t passed as void*.  All work is enqueued asynchronously on it; there
+ *     are no hidden synchronisations, so every call is CUDA-graph capturable.
+ *   - Activations are *pitched NHWC views* (cm2_act): channels are innermost and dense, the pixel,
+ *     row and image strides are explicit (in elements).  This lets the caller keep every feature
+ *     map inside a buffer with a one-pixel zero halo ([n, h+2, w+2, c], view = interior), which
+ *     is what the tensor-core convolution engine requires.
+ *   - There is no CPU fallback: on a device that is not sm_100 the tensor-core entry points return
+ *     CM2_ERR_UNSUPPORTED.
+ */
+#ifndef CM2_H_
+#define CM2_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CM2_VERSION 101
+
+#define CM2_OK 0
+#define CM2_ERR_BAD_SHAPE (-1)
+#define CM2_ERR_UNSUPPORTED (-2)
+#define CM2_ERR_CUDA (-3)
+
+#define CM2_F32 0
+#define CM2_BF16 1
+#define CM2_U8 2
+
+#define CM2_ENGINE_SIMT 0 /* fp32-accumulate CUDA-core implicit GEMM; any shape; f32 or bf16 I/O   */
+#define CM2_ENGINE_TC 1   /* tcgen05/TMEM implicit GEMM with TMA-staged tiles; bf16 in             */
+
+#define CM2_MAX_SRC 8
+
+/* Pitched NHWC view.  `data` addresses element (n=0, y=0, x=0, c=0); channel stride is 1. */
+typedef struct cm2_act {
+  void* data;
+  int32_t n, h, w, c;
+  int64_t sn, sh, sw; /* element strides of image, row, pixel */
+} cm2_act;
+
+int cm2_version(void);
+const char* cm2_last_error(void);
+/* Number of SMs / compute capability of the current device (0 if no device). */
+int cm2_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolution (the dense contractions).  Replaces every F.conv2d / conv_transpose2d / F.linear on
+ * the path: modeling/backbone/vovnet.py:205-236 (conv-FrozenBN-ReLU), :324-325 (torch.cat + 1x1,
+ * here a *virtual* concat over `src[]`), [d2] FPN lateral/output convs incl. the top-down
+ * nearest-2x upsample-add (res_mode 2), modeling/backbone/fpn.py:32-35, modeling/fcos/fcos.py:
+ * 169-200, modeling/centermask/sam.py:58-83 (deconv: out_mode 1), maskiou_head.py:78-94.
+ *
+ *   out[p, co] = act( scale[co] * sum_{tap, s, c} src_s[p*stride + tap - pad][c] * W[co, tap, s, c]
+ *                     + shift[co] + residual[p, co] )
+ *
+ * Weight layouts (built once by the caller; see centermask2_b200/packing.py):
+ *   SIMT : [kh*kw*cin_total][cout]          row k = (ky*kw + kx)*cin_total + c,  dtype = `dtype`
+ *   TC   : [cout_pad][k_tc] bf16, K-major; k = (tap, source, channel padded to 64 per source);
+ *          k_tc = kh*kw * sum_s roundup(src_c[s], 64)  (cm2_conv_tc_klen); cout_pad =
+ *          roundup(cout, 16); padding entries are zero.
+ *
+ * TC engine constraints (cm2_conv_tc_supported): bf16 sources, stride 1, kernel 1x1 (pad 0) or 3x3
+ * (pad 1); all sources and the output are interior views of one-pixel-halo buffers of identical
+ * geometry (sw == c, sh == (w+2)*sw, sn == (h+2)*sh), or, for 1x1 only, fully dense views
+ * (sh == w*sw, sn == h*sh).  With halo buffers the engine also (re)writes the halo of the output
+ * with zeros, so a chain of convolutions keeps the invariant "halo == 0".
+ * ------------------------------------------------------------------------------------------- */
+typedef struct cm2_conv_desc {
+  int32_t dtype;     /* CM2_F32 | CM2_BF16: sources, weights, residual                            */
+  int32_t out_dtype; /* CM2_F32 | CM2_BF16: output                                                */
+  int32_t engine;    /* CM2_ENGINE_*                                                              */
+  int32_t num_src;
+  cm2_act src[CM2_MAX_SRC]; /* same n, h, w for all sources                                       */
+  int32_t cout, kh, kw, stride, pad;
+  const void* weight;
+  const float* scale; /* device [cout] or NULL (1)                                                */
+  const float* shift; /* device [cout] or NULL (0)                                                */
+  int32_t relu;       /* ReLU after scale/shift/residual                                          */
+  int32_t in_relu;    /* ReLU on the input while loading (fpn.py:34, P7 = conv(relu(P6))); SIMT   */
+  cm2_act residual;   /* data == NULL: none.  dtype `dtype`                                       */
+  int32_t res_mode;   /* 1: same extent as out   2: [n,ho/2,wo/2,cout] read with nearest-2x
+                         upsample ([d2] FPN top-down path)                                        */
+  int32_t out_mode;   /* 0: out is [n,ho,wo,cout]
+                         1: 2x2/stride-2 transposed-conv scatter: GEMM column j = (dy*2+dx)*(cout/4)
+                            + co goes to out[n, 2y+dy, 2x+dx, co]  (out is [n,2ho,2wo,cout/4])     */
+  cm2_act out;
+  /* optional per-(image, channel) sum of the stored (post-activation) outputs, float [n][cout],
+   * accumulated with atomics (caller zeroes); used for the eSE global pool.  NULL: off.  TC only. */
+  float* chan_sum;
+} cm2_conv_desc;
+
+int cm2_conv2d(const cm2_conv_desc* d, void* stream);
+/* K extent of the TC weight layout for this source list. */
+int64_t cm2_conv_tc_klen(int32_t kh, int32_t kw, int32_t num_src, const int32_t* src_c);
+/* 1 if the TC engine accepts this descriptor, 0 otherwise (message via cm2_last_error). */
+int cm2_conv_tc_supported(const cm2_conv_desc* d);
+
+/* ---------------------------------------------------------------------------------------------
+ * Input side.  GeneralizedRCNN.preprocess_image [d2], restated in-tree at
+ * /root/reference/deploy_utils.py:76-98: (x - mean) / std, zero pad right/bottom.
+ * img: device CHW [3,h,w] (CM2_F32 or CM2_U8); out: view of image `out_index` is written for the
+ * whole padded extent out.h x out.w (pixels beyond h, w are zero).
+ * ------------------------------------------------------------------------------------------- */
+int cm2_preprocess_image(const void* img, int32_t in_dtype, int32_t h, int32_t w, const float* mean3,
+                         const float* std3, const cm2_act* out, int32_t out_dtype, int32_t out_index,
+                         void* stream);
+
+/* MaxPool2d(3, stride 2, ceil_mode=True), vovnet.py:349-350. */
+int cm2_maxpool3x3s2_ceil(const cm2_act* in, const cm2_act* out, int32_t dtype, void* stream);
+
+/* eSE (vovnet.py:238-260, applied at :327-330):
+ *   pooled[n,c] = mean_hw x ;  gate = relu6(W.pooled + b + 3) / 6 ;  out = x*gate (+ identity).
+ * cm2_ese_pool needs a float workspace of n*chunks*c floats, chunks = cm2_ese_pool_chunks(h*w).
+ * cm2_ese_gate: `pooled` holds means when inv_count == 1, or raw sums with inv_count = 1/(h*w). */
+int32_t cm2_ese_pool_chunks(int32_t hw);
+int cm2_ese_pool(const cm2_act* x, int32_t dtype, float* workspace, float* pooled, void* stream);
+int cm2_ese_gate(const float* pooled, float inv_count, const float* fc_w, const float* fc_b, float* gate,
+                 int32_t n, int32_t c, void* stream);
+int cm2_ese_apply(const cm2_act* x, const float* gate, const cm2_act* identity, const cm2_act* out,
+                  int32_t dtype, void* stream);
+
+/* GroupNorm(groups, c) + optional ReLU in place; fcos.py:182-185 (eps 1e-5, biased variance over
+ * (c/groups)*h*w per sample).  workspace: cm2_gn_workspace_floats(n, h*w, c, groups) floats. */
+int64_t cm2_gn_workspace_floats(int32_t n, int32_t hw, int32_t c, int32_t groups);
+int cm2_groupnorm_relu(const cm2_act* x, int32_t dtype, int32_t groups, const float* gamma,
+                       const float* beta, float eps, int32_t relu, float* workspace, void* stream);
+
+/* Elementwise ReLU copy (P7 input when the conv engine cannot apply in_relu). */
+int cm2_relu(const cm2_act* in, const cm2_act* out, int32_t dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * FCOS post-process.  fcos/fcos_outputs.py:372-495.
+ *
+ * cm2_fcos_decode (forward_for_single_feature_map :396-466, one FPN level, all images):
+ *   p = sigmoid(logit); c = sigmoid(ctr); candidate iff p > thresh (p*c > thresh when
+ *   thresh_with_ctr); raw score = p*c; box = (x-l, y-t, x+r, y+b) with (l,t,r,b) = reg*stride,
+ *   (x,y) = (col*stride + stride/2, row*stride + stride/2)  (fcos.py:132-144).
+ *   logits: f32 view [n,h,w,ncls];  regctr: f32 view [n,h,w,>=5] with channels (l,t,r,b,ctr,...)
+ *   where l..b already include Scale and ReLU (fcos.py:233-238).
+ *   Candidates are appended (unordered) to segment (image, level) of the candidate arrays, each
+ *   of capacity `cap`; cand_count[image*num_levels+level] counts *all* candidates, so a value > cap
+ *   signals overflow to the caller.  cand_count must be zeroed by the caller.
+ *
+ * cm2_fcos_select (:444-449 upstream top-k, select_over_all_levels :468-495, ml_nms layers/ml_nms.py:
+ *   93-96): per (image, level) keep the `pre_topk` best raw scores, then per image class-aware greedy
+ *   NMS in descending sqrt(score) order (suppress when IoU > nms_thresh, torchvision arithmetic) and
+ *   keep the first `post_topk` survivors.  Outputs are fixed-size [n][post_topk] with det_count[n].
+ *   workspace bytes: cm2_fcos_select_workspace(n, num_levels, cap).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct cm2_cand_buffers {
+  float* boxes;    /* [n][levels][cap][4] */
+  float* score;    /* [n][levels][cap]   raw p*c */
+  int32_t* cls;    /* [n][levels][cap] */
+  int32_t* flat;   /* [n][levels][cap]   loc*ncls + cls */
+  int32_t* count;  /* [n][levels] */
+} cm2_cand_buffers;
+
+int cm2_fcos_decode(const cm2_act* logits, const cm2_act* regctr, int32_t stride, float thresh,
+                    int32_t thresh_with_ctr, int32_t level, int32_t num_levels, int32_t cap,
+                    const cm2_cand_buffers* cand, void* stream);
+
+int64_t cm2_fcos_select_workspace(int32_t n, int32_t num_levels, int32_t cap);
+
+typedef struct cm2_det_buffers {
+  float* boxes;      /* [n][post_topk][4] */
+  float* scores;     /* [n][post_topk]  sqrt(p*c) */
+  int64_t* classes;  /* [n][post_topk] */
+  float* locations;  /* [n][post_topk][2] */
+  int32_t* count;    /* [n] */
+} cm2_det_buffers;
+
+int cm2_fcos_select(const cm2_cand_buffers* cand, int32_t n, int32_t num_levels, int32_t cap,
+                    const int32_t* level_w, const int32_t* level_stride, int32_t ncls,
+                    int32_t pre_topk, float nms_thresh, int32_t post_topk,
+                    const cm2_det_buffers* det, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ROI stage.
+ *
+ * cm2_roialign_fpn: centermask/pooler.py:320-366 with assign_boxes_to_levels_by_ratio (:80-118,
+ *   crit 0) or assign_boxes_to_levels (:121-152, crit 1) fused into [d2] ROIAlign (= torchvision
+ *   roi_align, aligned=True, sampling_ratio as given; 0 = adaptive).  ROI slots are [n][r_cap] with
+ *   det_count[n] valid ones per image; out is a view [n*r_cap, res, res, c] (invalid slots are
+ *   written with zeros).  image_area: device float [n] = h*w of the unpadded image (pooler.py:70-77).
+ *   level_out: device int32 [n*r_cap] (may be NULL).
+ * ------------------------------------------------------------------------------------------- */
+int cm2_roialign_fpn(const cm2_act* feats, const int32_t* feat_stride, int32_t num_levels, int32_t dtype,
+                     const float* boxes, const int32_t* det_count, int32_t n, int32_t r_cap,
+                     const float* image_area, int32_t crit, int32_t sampling_ratio,
+                     const cm2_act* out, int32_t* level_out, void* stream);
+
+/* SpatialAttention, centermask/sam.py:23-28: x * sigmoid(conv3x3([mean_c x, max_c x])); views
+ * [r,s,s,c]; w18 = conv weight [1][2][3][3] flattened (device). */
+int cm2_spatial_attention(const cm2_act* x, const cm2_act* out, int32_t dtype, const float* w18,
+                          void* stream);
+
+/* predictor (sam.py:83,97) restricted to the predicted class + mask_rcnn_inference
+ * (mask_head.py:196-216): probs[r, y, x] = sigmoid(x[r,y,x,:] . wp[cls_r,:] + bp[cls_r]).
+ * x view [r, m, m, c]; wp f32 [ncls][c]; classes int64 [r]; probs f32 dense [r][m][m]. */
+int cm2_mask_predict(const cm2_act* x, int32_t dtype, const float* wp, const float* bp,
+                     const int64_t* classes, int32_t ncls, float* probs, void* stream);
+
+/* MaskIoU input (maskiou_head.py:108-112): 2x2 max-pool of probs [r,2s,2s] written to channel 0 of
+ * out view [r,s,s,cpad]; remaining channels zero. */
+int cm2_maskiou_prep(const float* probs, const cm2_act* out, int32_t dtype, void* stream);
+
+/* mask_iou_inference (maskiou_head.py:50-60): mask_scores[r] = scores[r] * iou[r, cls_r];
+ * iou dense [r][ncls] of `dtype`. */
+int cm2_maskiou_score(const void* iou, int32_t dtype, int32_t r, int32_t ncls, const int64_t* classes,
+                      const float* scores, float* mask_scores, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Output side.  detector_postprocess + paste_masks_in_image [d2] (the fork's
+ * restatement is /root/reference/deploy_utils.py:129-158).
+ * cm2_scale_clip_boxes: boxes *= (sx, sy); clip to [0,out_w]x[0,out_h]; valid = w>0 && h>0.
+ * cm2_paste_masks: bilinear grid_sample (zero padding, align_corners=False) of probs [r,m,m] at the
+ *   pixel centres of out [r,out_h,out_w] (uint8 0/1), `>= threshold`, restricted to the window
+ *   [floor(x0)-1, ceil(x1)+1) x [floor(y0)-1, ceil(y1)+1); rows of invalid ROIs are zero.
+ * ------------------------------------------------------------------------------------------- */
+int cm2_scale_clip_boxes(const float* boxes_in, float* boxes_out, uint8_t* valid, int32_t r, float sx,
+                         float sy, float out_w, float out_h, void* stream);
+int cm2_paste_masks(const float* probs, const float* boxes, const uint8_t* valid, uint8_t* out,
+                    int32_t r, int32_t m, int32_t out_h, int32_t out_w, float threshold, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CM2_H_ */
