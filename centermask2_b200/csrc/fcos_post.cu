@@ -97,6 +97,12 @@ __global__ void fcos_select_level_kernel(cm2_cand_buffers cand, int num_levels, 
   const int level = blockIdx.x, img = blockIdx.y;
   const int seg = img * num_levels + level;
   int cnt = min(cand.count[seg], cap);
+  // sort only as many keys as there are candidates (power of two, <= the launch-time bound)
+  {
+    int sn = 32;
+    while (sn < cnt) sn <<= 1;
+    sort_n = min(sort_n, sn);
+  }
   for (int i = threadIdx.x; i < sort_n; i += blockDim.x) {
     unsigned long long k = 0ull;
     if (i < cnt) {

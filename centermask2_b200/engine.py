@@ -271,7 +271,7 @@ class Engine(object):
         ncls = head_out[0][0].c
         pre = cfg.MODEL.FCOS.PRE_NMS_TOPK_TEST
         post = cfg.MODEL.FCOS.POST_NMS_TOPK_TEST
-        cap = cand_cap or max(2048, 2 * pre)
+        cap = cand_cap or max(8192, 2 * pre)
         B = self.buffer
         cb = dict(boxes=B("cand_boxes", (n, L, cap, 4), torch.float32, False), score=B("cand_score", (n, L, cap), torch.float32, False),
                   cls=B("cand_cls", (n, L, cap), torch.int32, False), flat=B("cand_flat", (n, L, cap), torch.int32, False),
