@@ -1,14 +1,533 @@
-// placeholder until the tcgen05 engine lands (replaced in the next commit)
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM,
+// operands staged by TMA into 128B-swizzled shared memory) -- sm_100a only.
+//
+// GEMM view.  Activations live in NHWC buffers with a one-pixel zero halo, [n, h+2, w+2, c], which this
+// kernel treats as a *flat* 2-D matrix  A[rows = n*(h+2)*(w+2)][c].  For a stride-1 3x3 convolution the
+// operand of tap (ky, kx) is the same matrix shifted by (ky-1)*(w+2) + (kx-1) rows, so every K-block is
+// ONE plain 2-D TMA box load [128 rows x 64 channels] at row coordinate m0 + shift (out-of-range rows
+// are zero-filled by TMA).  Outputs are produced for every padded position; the epilogue writes zeros
+// to the halo rows, which keeps the invariant "halo == 0" for the next layer.  1x1 convolutions and
+// linear layers use the same path with a single tap; a channel concat (OSA aggregation, vovnet.py:324)
+// is a K loop over several source matrices (one tensor map each) and is never materialised.
+//
+//   D[128 x BN] (fp32, TMEM)  +=  A_tile[128 x 64] (bf16, smem, K-major SW128)  x  W_tile[BN x 64]^T
+//
+// Warp roles (192 threads, one CTA per SM, persistent over output tiles):
+//   warp 0     TMA producer (one elected lane): A + W boxes per K-block into a STAGES-deep ring
+//   warp 1     TMEM allocation + MMA issue (one elected lane): 4 x tcgen05.mma (K=16) per K-block,
+//              tcgen05.commit releases the smem slot / publishes the accumulator
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 16 columns), scale/shift (folded FrozenBN or bias),
+//              residual / nearest-2x upsample add, ReLU, halo masking, bf16/f32 store, deconv scatter.
+// Two accumulator stages (2 x 256 TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "common.cuh"
+#include <cuda.h>
+
 namespace cm2 {
-int conv_tc_launch(const cm2_conv_desc* d, cudaStream_t stream) {
-  set_error("conv2d: tensor-core engine not built");
-  return CM2_ERR_UNSUPPORTED;
+
+constexpr int TC_BM = 128;          // rows per tile (UMMA M)
+constexpr int TC_BK = 64;           // bf16 channels per K-block = 128 bytes = one swizzle row
+constexpr int TC_THREADS = 192;
+constexpr int TC_ACC_COLS = 256;    // TMEM columns per accumulator stage
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;
+
+struct alignas(64) TcParams {
+  CUtensorMap a_map[CM2_MAX_SRC];
+  CUtensorMap b_map;
+  int num_src;
+  int src_c[CM2_MAX_SRC];
+  int taps;                 // 1 or 9
+  int pitch;                // w + 2 (rows per padded image line); 0 in dense mode
+  int plane;                // (h + 2) * (w + 2); h*w in dense mode
+  int h, w, halo;           // halo: 1 = padded geometry, 0 = dense rows
+  int rows;                 // total GEMM rows
+  int m_tiles, n_tiles, bn, cout;
+  int stages;
+  const float* scale;
+  const float* shift;
+  int relu;
+  // output
+  void* out;
+  long long out_sn, out_sh, out_sw;
+  int out_f32, out_halo, out_mode, out_vec;
+  // residual
+  const __nv_bfloat16* res;
+  long long res_sn, res_sh, res_sw;
+  int res_mode;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((++spins & 1023u) == 0) {          // a protocol bug must fail loudly, not hang the GPU box
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) {  // ~2 s
+        printf("conv_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile (rows of 128 bytes, 8-row groups 1024 bytes apart):
+//   start address >> 4 | LBO (ignored for swizzled K-major) = 1 | SBO = 1024 >> 4 | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 2;
+  const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
+  const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;
+  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base address
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&p.a_map[s]);
+    tma_prefetch_desc(&p.b_map);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m0 = (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.bn;
+        int kb = 0;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int shift = p.taps == 9 ? (tap / 3 - 1) * p.pitch + (tap % 3 - 1) : 0;
+          for (int s = 0; s < p.num_src; ++s) {
+            const int nblk = (p.src_c[s] + TC_BK - 1) / TC_BK;
+            for (int cb = 0; cb < nblk; ++cb, ++kb) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+              mbar_expect_tx(full_bar(stage), TC_A_BYTES + b_bytes);
+              tma_load_2d(sa, &p.a_map[s], full_bar(stage), cb * TC_BK, m0 + shift);
+              tma_load_2d(sa + TC_A_BYTES, &p.b_map, full_bar(stage), kb * TC_BK, n0);
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = bn, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_ACC_COLS);
+        uint32_t accumulate = 0;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          for (int s = 0; s < p.num_src; ++s) {
+            const int c = p.src_c[s];
+            const int nblk = (c + TC_BK - 1) / TC_BK;
+            for (int cb = 0; cb < nblk; ++cb) {
+              const int nk = (min(TC_BK, c - cb * TC_BK) + 15) >> 4;        // 16-channel MMAs in this block
+              mbar_wait(full_bar(stage), phase);
+              tc_fence_after();
+              const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+              const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + TC_A_BYTES);
+              for (int k = 0; k < nk; ++k) {
+                // +32 bytes per K=16 step inside the 128B swizzle row (start-address field is in 16B units)
+                tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate);
+                accumulate = 1;
+              }
+              tc_commit(empty_bar(stage));          // frees the smem slot when these MMAs have read it
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+        tc_commit(tfull_bar(acc));                  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m0 = (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.bn;
+      const int m = m0 + q * 32 + lane;
+      // decode the GEMM row into (image, y, x) of the *unpadded* feature map
+      bool in_range = m < p.rows, interior = false;
+      int img = 0, y = 0, x = 0;
+      if (in_range) {
+        img = m / p.plane;
+        int r = m - img * p.plane;
+        if (p.halo) {
+          int yy = r / p.pitch, xx = r - yy * p.pitch;
+          y = yy - 1; x = xx - 1;
+          interior = y >= 0 && y < p.h && x >= 0 && x < p.w;
+        } else {
+          y = r / p.w; x = r - y * p.w;
+          interior = true;
+        }
+      }
+      // rows that get written: interior rows always; halo rows (as zeros) only when the output keeps the halo
+      const bool do_store = in_range && (interior || (p.out_halo && p.out_mode == 0));
+      const long long out_off = (long long)img * p.out_sn + (long long)(p.out_mode ? 2 * y : y) * p.out_sh +
+                                (long long)(p.out_mode ? 2 * x : x) * p.out_sw;
+      const __nv_bfloat16* res_row = nullptr;
+      if (p.res_mode && interior)
+        res_row = p.res + (long long)img * p.res_sn + (long long)(p.res_mode == 2 ? (y >> 1) : y) * p.res_sh +
+                  (long long)(p.res_mode == 2 ? (x >> 1) : x) * p.res_sw;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * TC_ACC_COLS) + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+        uint32_t raw[16];
+        __syncwarp();                                       // tcgen05.ld is warp-collective (.sync.aligned)
+        tc_ld16(taddr + (uint32_t)c0, raw);
+        tc_ld_wait();
+        const int co0 = n0 + c0;
+        if (!do_store || co0 >= p.cout) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int co = co0 + j;
+          float a = __uint_as_float(raw[j]);
+          if (co < p.cout) {
+            if (p.scale) a *= __ldg(p.scale + co);
+            if (p.shift) a += __ldg(p.shift + co);
+          }
+          v[j] = a;
+        }
+        if (res_row) {
+          if (p.out_vec) {
+            float r0[8], r1[8];
+            Vec8<__nv_bfloat16>::load(res_row + co0, r0);
+            Vec8<__nv_bfloat16>::load(res_row + co0 + 8, r1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[j] += r0[j]; v[8 + j] += r1[j]; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (co0 + j < p.cout) v[j] += __bfloat162float(res_row[co0 + j]);
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (!interior) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
+        long long off = out_off;
+        int cc = co0;
+        if (p.out_mode) {                                   // 2x2 transposed-conv scatter (sam.py:74-80)
+          const int cq = p.cout >> 2;
+          const int quad = co0 / cq;
+          cc = co0 - quad * cq;
+          off += (long long)(quad >> 1) * p.out_sh + (long long)(quad & 1) * p.out_sw;
+        }
+        if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.out) + off + cc;
+          if (p.out_vec) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (co0 + j < p.cout) o[j] = v[j];
+          }
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + cc;
+          if (p.out_vec) {
+            float lo[8], hi[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+            Vec8<__nv_bfloat16>::store(o, lo);
+            Vec8<__nv_bfloat16>::store(o + 8, hi);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (co0 + j < p.cout) o[j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// bf16 matrix [rows][cols] (cols contiguous, row pitch = cols) ; box = [box_rows][64 cols], 128B swizzle
+static bool encode_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static bool is_halo_view(const cm2_act& a) {
+  return a.sw == a.c && a.sh == (long long)(a.w + 2) * a.sw && a.sn == (long long)(a.h + 2) * a.sh;
+}
+static bool is_dense_view(const cm2_act& a) {
+  return a.sw == a.c && a.sh == (long long)a.w * a.sw && a.sn == (long long)a.h * a.sh;
+}
+
+static int device_is_sm100() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    cached = major == 10 ? 1 : 0;
+  }
+  return cached;
+}
+
+static int pick_bn(int cout_pad, int m_tiles, int sms) {
+  int bn = cout_pad;
+  if (bn > 256) {
+    bn = 256;
+    while (cout_pad % bn) bn -= 16;
+  }
+  // small problems: narrower tiles give more CTAs (weights are streamed once per N tile either way)
+  while (bn >= 64 && bn % 32 == 0 && m_tiles * (cout_pad / bn) < sms) bn >>= 1;
+  return bn;
+}
+
+// Validates the descriptor for the TC engine; on success fills `p` (without tensor maps when maps == false).
+static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
+  const cm2_act& s0 = d->src[0];
+  if (!device_is_sm100()) { set_error("conv_tc: device is not sm_100"); return CM2_ERR_UNSUPPORTED; }
+#define TC_REQUIRE(cond, ...) do { if (!(cond)) { set_error(__VA_ARGS__); return CM2_ERR_UNSUPPORTED; } } while (0)
+  TC_REQUIRE(d->dtype == CM2_BF16 && (d->out_dtype == CM2_BF16 || d->out_dtype == CM2_F32), "conv_tc: needs bf16 sources");
+  TC_REQUIRE(d->stride == 1 && d->kh == d->kw && ((d->kh == 1 && d->pad == 0) || (d->kh == 3 && d->pad == 1)),
+             "conv_tc: only stride-1 1x1/p0 and 3x3/p1 (got k%d s%d p%d)", d->kh, d->stride, d->pad);
+  TC_REQUIRE(!d->in_relu && !d->chan_sum, "conv_tc: in_relu / chan_sum not supported");
+  const bool halo = is_halo_view(s0);
+  TC_REQUIRE(halo || (d->kh == 1 && is_dense_view(s0)), "conv_tc: source 0 is neither a halo-1 view nor (for 1x1) dense");
+  for (int i = 0; i < d->num_src; ++i) {
+    const cm2_act& s = d->src[i];
+    TC_REQUIRE(s.c % 16 == 0 && (reinterpret_cast<uintptr_t>(s.data) & 15) == 0, "conv_tc: source %d channels %d / alignment", i, s.c);
+    TC_REQUIRE(halo ? is_halo_view(s) : is_dense_view(s), "conv_tc: source %d geometry differs from source 0", i);
+  }
+  memset(p, 0, sizeof(*p));
+  p->num_src = d->num_src;
+  for (int i = 0; i < d->num_src; ++i) p->src_c[i] = d->src[i].c;
+  p->taps = d->kh * d->kw;
+  p->halo = halo ? 1 : 0;
+  p->h = s0.h; p->w = s0.w;
+  p->pitch = halo ? s0.w + 2 : 0;
+  p->plane = halo ? (s0.h + 2) * (s0.w + 2) : s0.h * s0.w;
+  long long rows = (long long)s0.n * p->plane;
+  TC_REQUIRE(rows > 0 && rows < (1ll << 31) - 4096, "conv_tc: %lld rows out of range", rows);
+  p->rows = (int)rows;
+  p->m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
+  p->cout = d->cout;
+  const int cout_pad = (d->cout + 15) / 16 * 16;
+  int sms = 148;
+  p->bn = pick_bn(cout_pad, p->m_tiles, sms);
+  if (d->out_mode == 1) {
+    TC_REQUIRE((d->cout / 4) % 16 == 0, "conv_tc: deconv scatter needs cout/4 %% 16 == 0");
+  }
+  p->n_tiles = (cout_pad + p->bn - 1) / p->bn;
+  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p->bn * TC_BK * 2;
+  int stages = (int)((220u * 1024u) / stage_bytes);
+  p->stages = stages > 8 ? 8 : stages;
+  p->scale = d->scale; p->shift = d->shift; p->relu = d->relu;
+  p->out = d->out.data;
+  p->out_sn = d->out.sn; p->out_sh = d->out.sh; p->out_sw = d->out.sw;
+  p->out_f32 = d->out_dtype == CM2_F32;
+  p->out_mode = d->out_mode;
+  p->out_halo = (halo && d->out_mode == 0 && is_halo_view(d->out) && d->out.h == s0.h && d->out.w == s0.w) ? 1 : 0;
+  const int oc = d->out_mode ? d->cout / 4 : d->cout;
+  const int oeb = p->out_f32 ? 4 : 2;
+  p->out_vec = (oc % 16 == 0 && d->out.sn % 8 == 0 && d->out.sh % 8 == 0 && d->out.sw % 8 == 0 &&
+                (reinterpret_cast<uintptr_t>(d->out.data) % (size_t)(8 * oeb)) == 0) ? 1 : 0;
+  if (d->residual.data) {
+    p->res = reinterpret_cast<const __nv_bfloat16*>(d->residual.data);
+    p->res_sn = d->residual.sn; p->res_sh = d->residual.sh; p->res_sw = d->residual.sw;
+    p->res_mode = d->res_mode;
+    if (p->out_vec && !(d->residual.sn % 8 == 0 && d->residual.sh % 8 == 0 && d->residual.sw % 8 == 0 &&
+                        (reinterpret_cast<uintptr_t>(d->residual.data) & 15) == 0))
+      p->out_vec = 0;
+  }
+#undef TC_REQUIRE
+  if (!maps) return CM2_OK;
+  for (int i = 0; i < d->num_src; ++i) {
+    // base of the flat matrix = address of padded pixel (0,0) of image 0
+    const char* basep = reinterpret_cast<const char*>(d->src[i].data);
+    if (halo) basep -= (size_t)(d->src[i].sh + d->src[i].sw) * 2;
+    if (!encode_2d(&p->a_map[i], basep, (uint64_t)rows, (uint64_t)d->src[i].c, TC_BM)) {
+      set_error("conv_tc: cuTensorMapEncodeTiled failed for source %d", i);
+      return CM2_ERR_CUDA;
+    }
+  }
+  const int64_t ktc = cm2_conv_tc_klen(d->kh, d->kw, d->num_src, p->src_c);
+  if (!encode_2d(&p->b_map, d->weight, (uint64_t)cout_pad, (uint64_t)ktc, (uint32_t)p->bn)) {
+    set_error("conv_tc: cuTensorMapEncodeTiled failed for the weights");
+    return CM2_ERR_CUDA;
+  }
+  return CM2_OK;
+}
+
+int conv_tc_launch(const cm2_conv_desc* d, cudaStream_t stream) {
+  TcParams p;
+  int rc = tc_plan(d, &p, true);
+  if (rc != CM2_OK) return rc;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }
+  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.bn * TC_BK * 2;
+  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + 8 * (2 * p.stages + 4) + 16;
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < sms ? tiles : sms;
+  conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
+  CM2_CHECK_LAUNCH("conv_tc");
+  return CM2_OK;
+}
+
 }  // namespace cm2
+
 extern "C" int64_t cm2_conv_tc_klen(int32_t kh, int32_t kw, int32_t num_src, const int32_t* src_c) {
   int64_t k = 0;
   for (int i = 0; i < num_src; ++i) k += (src_c[i] + 63) / 64 * 64;
   return k * kh * kw;
 }
-extern "C" int cm2_conv_tc_supported(const cm2_conv_desc* d) { return 0; }
+
+extern "C" int cm2_conv_tc_supported(const cm2_conv_desc* d) {
+  if (!d || d->num_src < 1 || d->num_src > CM2_MAX_SRC) return 0;
+  cm2::TcParams p;
+  return cm2::tc_plan(d, &p, false) == CM2_OK ? 1 : 0;
+}

@@ -1,0 +1,159 @@
+"""GPU: the tcgen05 implicit-GEMM convolution (CM2_ENGINE_TC) against torch.conv2d on the same
+bf16-rounded operands (fp32 accumulation on both sides).  Tolerance: one bf16 rounding of the output
+(rtol 2^-8) plus fp32 accumulation-order noise; f32 outputs are compared at 1e-3."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from centermask2_b200 import lib, packing              # noqa: E402
+from centermask2_b200.engine import FMap               # noqa: E402
+
+DEV = "cuda"
+BF = torch.bfloat16
+
+
+def halo(t_nchw, dtype=BF):
+    n, c, h, w = t_nchw.shape
+    buf = torch.zeros((n, h + 2, w + 2, c), dtype=dtype, device=DEV)
+    buf[:, 1:-1, 1:-1] = t_nchw.permute(0, 2, 3, 1).to(DEV, dtype)
+    return FMap(buf, 1)
+
+
+def nchw(view):
+    return view.permute(0, 3, 1, 2).float().cpu()
+
+
+def rb(t):
+    return t.to(BF).float()
+
+
+def close(got, ref, out_bf16=True):
+    tol = 1.0 / 128 if out_bf16 else 1e-3
+    err = (got - ref).abs()
+    bound = tol * ref.abs() + tol * ref.abs().mean() + 1e-3
+    assert (err <= bound).all(), "max err {} at ref {}".format(err.max().item(), ref.flatten()[err.argmax()].item())
+
+
+@pytest.mark.parametrize("srcs,cout,k,h,w,n", [
+    ([64], 64, 3, 20, 24, 1),            # stem_2 shape class
+    ([128], 128, 3, 17, 23, 2),          # OSA2 3x3, two images (tiles straddle image boundary)
+    ([160], 160, 3, 13, 21, 1),          # K tail: 160 = 2.5 k-blocks, N = 160
+    ([224], 224, 3, 9, 11, 1),           # K tail 224, N = 224
+    ([256], 256, 3, 25, 42, 1),          # FCOS tower / FPN output
+    ([256], 80, 3, 13, 21, 2),           # cls_logits (N = 80)
+    ([256], 5, 3, 7, 11, 1),             # bbox_pred + ctrness merged (N padded to 16, scalar stores)
+    ([128, 128, 128, 128, 128, 128], 256, 1, 12, 16, 1),   # OSA2 aggregation: virtual concat of 6
+    ([256, 160, 160, 160, 160, 160], 512, 1, 10, 12, 2),   # OSA3 aggregation: two N tiles, K tails
+    ([1024], 256, 1, 25, 42, 1),         # FPN lateral 5
+    ([256, 16], 256, 3, 14, 14, 5),      # MaskIoU fcn1: roi feature + 16-channel padded mask plane
+])
+def test_conv_tc_halo(srcs, cout, k, h, w, n):
+    g = torch.Generator().manual_seed(sum(srcs) + cout + k)
+    cin = sum(srcs)
+    xs = [rb(torch.randn(n, c, h, w, generator=g)) for c in srcs]
+    wt = rb(torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k))
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g) * 0.1
+    ref = F.relu(F.conv2d(torch.cat(xs, 1), wt, None, 1, k // 2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    cw = packing.ConvW(wt, srcs, 1, k // 2, scale, shift, True, BF, DEV, True)
+    out = halo(torch.full((n, cout, h, w), 7.0))
+    out.buf.fill_(7.0)                                          # the engine must rewrite the halo with zeros
+    ok = lib.conv2d([halo(x).view for x in xs], cw.w_tc, out.view, cout, k, 1, k // 2, scale=cw.scale, shift=cw.shift,
+                    relu=True, engine=lib.ENGINE_TC, probe=True)
+    assert ok, lib.last_error()
+    torch.cuda.synchronize()
+    close(nchw(out.view), ref)
+    b = out.buf.float()
+    assert b[:, 0].abs().max() == 0 and b[:, -1].abs().max() == 0 and b[:, :, 0].abs().max() == 0 and b[:, :, -1].abs().max() == 0
+
+
+def test_conv_tc_f32_dense_output_and_no_relu():
+    g = torch.Generator().manual_seed(1)
+    x = rb(torch.randn(2, 256, 13, 21, generator=g))
+    wt = rb(torch.randn(80, 256, 3, 3, generator=g) / 48)
+    bias = torch.randn(80, generator=g)
+    ref = F.conv2d(x, wt, bias, 1, 1)
+    cw = packing.ConvW(wt, [256], 1, 1, None, bias, False, BF, DEV, True)
+    out = torch.full((2, 13, 21, 80), 3.0, device=DEV)
+    assert lib.conv2d([halo(x).view], cw.w_tc, out, 80, 3, 1, 1, shift=cw.shift, engine=lib.ENGINE_TC, probe=True)
+    torch.cuda.synchronize()
+    close(nchw(out), ref, out_bf16=False)
+    # 5-channel f32 output (scalar store path)
+    wt5 = rb(torch.randn(5, 256, 3, 3, generator=g) / 48)
+    sc5, sh5 = torch.rand(5, generator=g) + 0.5, torch.randn(5, generator=g)
+    ref5 = F.conv2d(x, wt5, None, 1, 1) * sc5.view(1, -1, 1, 1) + sh5.view(1, -1, 1, 1)
+    cw5 = packing.ConvW(wt5, [256], 1, 1, sc5, sh5, False, BF, DEV, True)
+    out5 = torch.zeros((2, 13, 21, 5), device=DEV)
+    assert lib.conv2d([halo(x).view], cw5.w_tc, out5, 5, 3, 1, 1, scale=cw5.scale, shift=cw5.shift, engine=lib.ENGINE_TC, probe=True)
+    torch.cuda.synchronize()
+    close(nchw(out5), ref5, out_bf16=False)
+
+
+def test_conv_tc_fpn_lateral_with_upsample_add():
+    g = torch.Generator().manual_seed(2)
+    x = rb(torch.randn(2, 512, 12, 20, generator=g))
+    low = rb(torch.randn(2, 256, 6, 10, generator=g))
+    wt = rb(torch.randn(256, 512, 1, 1, generator=g) / 22)
+    bias = torch.randn(256, generator=g) * 0.1
+    ref = F.conv2d(x, wt, bias) + F.interpolate(low, scale_factor=2.0, mode="nearest")
+    cw = packing.ConvW(wt, [512], 1, 0, None, bias, False, BF, DEV, True)
+    out = halo(torch.zeros(2, 256, 12, 20))
+    assert lib.conv2d([halo(x).view], cw.w_tc, out.view, 256, 1, 1, 0, shift=cw.shift, residual=halo(low).view,
+                      res_mode=2, engine=lib.ENGINE_TC, probe=True)
+    torch.cuda.synchronize()
+    close(nchw(out.view), ref)
+
+
+def test_conv_tc_deconv_scatter():
+    g = torch.Generator().manual_seed(3)
+    x = rb(torch.randn(6, 256, 14, 14, generator=g))
+    wd = rb(torch.randn(256, 256, 2, 2, generator=g) / 16)
+    bd = torch.randn(256, generator=g) * 0.1
+    ref = F.relu(F.conv_transpose2d(x, wd, bd, stride=2))
+    cw = packing.deconv2x2({"d.weight": wd, "d.bias": bd}, "d", BF, DEV, True)
+    out = torch.zeros((6, 28, 28, 256), dtype=BF, device=DEV)
+    assert lib.conv2d([halo(x).view], cw.w_tc, out, 1024, 1, 1, 0, shift=cw.shift, relu=True, out_mode=1,
+                      engine=lib.ENGINE_TC, probe=True)
+    torch.cuda.synchronize()
+    close(nchw(out), ref)
+
+
+def test_conv_tc_linear_dense_rows():
+    g = torch.Generator().manual_seed(4)
+    r, kdim, cout = 150, 12544, 1024
+    x = rb(torch.randn(r, kdim, generator=g))
+    wt = rb(torch.randn(cout, kdim, generator=g) / math.sqrt(kdim))
+    bias = torch.randn(cout, generator=g) * 0.1
+    ref = F.relu(F.linear(x, wt, bias))
+    cw = packing.linear({"l.weight": wt, "l.bias": bias}, "l", True, BF, DEV, True)
+    xin = x.to(DEV, BF).reshape(r, 1, 1, kdim)
+    out = torch.zeros((r, 1, 1, cout), dtype=BF, device=DEV)
+    assert lib.conv2d([xin], cw.w_tc, out, cout, 1, 1, 0, shift=cw.shift, relu=True, engine=lib.ENGINE_TC, probe=True)
+    torch.cuda.synchronize()
+    close(out.reshape(r, cout).float().cpu(), ref)
+
+
+def test_conv_tc_large_multi_wave():
+    """More tiles than SMs (persistent loop, both accumulator stages, ring wrap-around)."""
+    g = torch.Generator().manual_seed(5)
+    x = rb(torch.randn(2, 128, 100, 168, generator=g))
+    wt = rb(torch.randn(128, 128, 3, 3, generator=g) / 34)
+    ref = F.relu(F.conv2d(x, wt, None, 1, 1))
+    cw = packing.ConvW(wt, [128], 1, 1, None, None, True, BF, DEV, True)
+    out = halo(torch.zeros(2, 128, 100, 168))
+    assert lib.conv2d([halo(x).view], cw.w_tc, out.view, 128, 3, 1, 1, relu=True, engine=lib.ENGINE_TC, probe=True)
+    torch.cuda.synchronize()
+    close(nchw(out.view), ref)
+
+
+def test_unsupported_shapes_are_refused_not_miscomputed():
+    x = halo(torch.zeros(1, 64, 8, 8))
+    w = torch.zeros((64, 64 * 9), dtype=BF, device=DEV)
+    out = halo(torch.zeros(1, 64, 4, 4))
+    assert lib.conv2d([x.view], w, out.view, 64, 3, 2, 1, engine=lib.ENGINE_TC, probe=True) is False
+    with pytest.raises(RuntimeError):
+        lib.conv2d([x.view], w, out.view, 64, 3, 2, 1, engine=lib.ENGINE_TC)
