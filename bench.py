@@ -165,19 +165,24 @@ def device_step(model, cfg, dev_images, sizes_out):
     return det, mask_scores
 
 
-def conv_time_per_step(model, cfg, dev_images, steps):
+def conv_time_per_step(model, cfg, dev_images, steps, layers=None):
     """Sum of the device time of every convolution launch in one step (CUDA events around each launch)."""
     from centermask2_b200 import runtime
     eng = runtime.engine_for(cfg)
     events = []
     orig = eng.conv
 
-    def timed(*a, **k):
+    def timed(name, srcs, w, *a, **k):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        r = orig(*a, **k)
+        r = orig(name, srcs, w, *a, **k)
         e1.record()
         events.append((e0, e1))
+        if layers is not None:
+            x = srcs[0]
+            ho = (x.h + 2 * w.pad - w.k) // w.stride + 1
+            wo = (x.w + 2 * w.pad - w.k) // w.stride + 1
+            layers.append((name, 2.0 * x.n * ho * wo * sum(w.src_c) * w.k * w.k * w.cout / 1e9, (e0, e1)))
         return r
     eng.conv = timed
     try:
@@ -227,6 +232,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("CM2_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", default=None, help="write a per-conv-layer timing table (one step) to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -319,6 +325,14 @@ def main():
 
     # ---- roofline of the dominant kernel family (convolutions)
     conv_ms, conv_launches = conv_time_per_step(model, cfg, dev_images, max(2, min(args.steps, 5)))
+    if args.layers and rank == 0:
+        rows = []
+        conv_time_per_step(model, cfg, dev_images, 1, layers=rows)
+        with open(args.layers, "w") as f:
+            f.write("# batch {} precision {}\n# name gflop ms tflops\n".format(args.batch, args.precision))
+            for nme, gf, (a, b) in rows:
+                ms_l = a.elapsed_time(b)
+                f.write("{:24s} {:10.3f} {:9.4f} {:9.1f}\n".format(nme, gf, ms_l, gf / ms_l if ms_l > 0 else 0.0))
     gflop_img = conv_gflop_per_image(cfg, 800, 1344, r_cap)          # algorithmic FLOPs, R = slots computed
     hbm, tf_burst, tf_sus, src = peaks()
     achieved = gflop_img * args.batch / conv_ms                       # GFLOP / ms = TFLOP/s

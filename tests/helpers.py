@@ -70,5 +70,8 @@ def assert_detections_match(got, ref, box_tol=BOX_TOL_PX, score_tol=SCORE_TOL, w
     assert db <= box_tol, "{}: box diff {} px".format(what, db)
     assert ds <= score_tol, "{}: score diff {}".format(what, ds)
     if "mask_scores" in ref:
+        # mask_scores = score * maskiou; with random-init weights the MaskIoU output is not confined to [0, 1]
+        # (hundreds for the deep V-99 body), so the absolute tolerance is scaled by the reference magnitude.
         dm = (got["mask_scores"].cpu().float() - ref["mask_scores"].float()).abs().max().item()
-        assert dm <= score_tol, "{}: mask_score diff {}".format(what, dm)
+        bound = score_tol * max(1.0, ref["mask_scores"].abs().max().item())
+        assert dm <= bound, "{}: mask_score diff {} > {}".format(what, dm, bound)
