@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const SimtConvParams p) {
 }
 
 void conv_out_extent(const cm2_conv_desc* d, int* ho, int* wo) {
+  if (d->src_phase) { *ho = d->src[0].h; *wo = d->src[0].w; return; }   // plane extent == output extent
   *ho = (d->src[0].h + 2 * d->pad - d->kh) / d->stride + 1;
   *wo = (d->src[0].w + 2 * d->pad - d->kw) / d->stride + 1;
 }
@@ -257,12 +258,16 @@ extern "C" int cm2_conv2d(const cm2_conv_desc* d, void* stream) {
   int ho, wo;
   conv_out_extent(d, &ho, &wo);
   CM2_CHECK_ARG(ho > 0 && wo > 0, "conv2d: empty output");
-  CM2_CHECK_ARG(d->out_mode == 0 || (d->out_mode == 1 && d->cout % 4 == 0), "conv2d: bad out_mode");
+  CM2_CHECK_ARG(d->out_mode == 0 || (d->out_mode == 1 && d->cout % 4 == 0) || d->out_mode == 2, "conv2d: bad out_mode");
   CM2_CHECK_ARG(d->weight != nullptr && d->out.data != nullptr, "conv2d: null weight/out");
   if (d->out_mode == 0)
     CM2_CHECK_ARG(d->out.n == s0.n && d->out.h == ho && d->out.w == wo && d->out.c == d->cout,
                   "conv2d: out view [%d,%d,%d,%d] != expected [%d,%d,%d,%d]", d->out.n, d->out.h, d->out.w, d->out.c,
                   s0.n, ho, wo, d->cout);
+  else if (d->out_mode == 2)
+    CM2_CHECK_ARG(d->out.n == s0.n && d->out.h == (ho + 1) / 2 && d->out.w == (wo + 1) / 2 && d->out.c == d->cout,
+                  "conv2d: phase-split out view [%d,%d,%d,%d] != expected [%d,%d,%d,%d]", d->out.n, d->out.h, d->out.w,
+                  d->out.c, s0.n, (ho + 1) / 2, (wo + 1) / 2, d->cout);
   else
     CM2_CHECK_ARG(d->out.n == s0.n && d->out.h == 2 * ho && d->out.w == 2 * wo && d->out.c == d->cout / 4,
                   "conv2d: deconv out view [%d,%d,%d,%d] != expected [%d,%d,%d,%d]", d->out.n, d->out.h, d->out.w,
@@ -277,6 +282,10 @@ extern "C" int cm2_conv2d(const cm2_conv_desc* d, void* stream) {
   }
   if (d->engine == CM2_ENGINE_SIMT) {
     CM2_CHECK_ARG(d->chan_sum == nullptr, "conv2d: chan_sum needs the TC engine");
+    if (d->src_phase || d->out_mode == 2) {
+      set_error("conv2d: phase-split layouts need the TC engine");
+      return CM2_ERR_UNSUPPORTED;
+    }
     return conv_simt_launch(d, (cudaStream_t)stream);
   }
   if (d->engine == CM2_ENGINE_TC) return conv_tc_launch(d, (cudaStream_t)stream);

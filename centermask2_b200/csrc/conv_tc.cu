@@ -36,6 +36,7 @@ struct alignas(64) TcParams {
   int num_src;
   int src_c[CM2_MAX_SRC];
   int taps;                 // 1 or 9
+  int tap_shift[9];         // row shift of every tap in the flat source matrix
   int pitch;                // w + 2 (rows per padded image line); 0 in dense mode
   int plane;                // (h + 2) * (w + 2); h*w in dense mode
   int h, w, halo;           // halo: 1 = padded geometry, 0 = dense rows
@@ -48,6 +49,7 @@ struct alignas(64) TcParams {
   // output
   void* out;
   long long out_sn, out_sh, out_sw;
+  long long out_plane;      // out_mode 2: element stride between the four phase planes
   int out_f32, out_halo, out_mode, out_vec;
   // residual
   const __nv_bfloat16* res;
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int m0 = (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.bn;
         int kb = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
-          const int shift = p.taps == 9 ? (tap / 3 - 1) * p.pitch + (tap % 3 - 1) : 0;
+          const int shift = p.tap_shift[tap];
           for (int s = 0; s < p.num_src; ++s) {
             const int nblk = (p.src_c[s] + TC_BK - 1) / TC_BK;
             for (int cb = 0; cb < nblk; ++cb, ++kb) {
@@ -256,8 +258,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
       // rows that get written: interior rows always; halo rows (as zeros) only when the output keeps the halo
       const bool do_store = in_range && (interior || (p.out_halo && p.out_mode == 0));
-      const long long out_off = (long long)img * p.out_sn + (long long)(p.out_mode ? 2 * y : y) * p.out_sh +
-                                (long long)(p.out_mode ? 2 * x : x) * p.out_sw;
+      long long out_off;
+      if (p.out_mode == 0)
+        out_off = (long long)img * p.out_sn + (long long)y * p.out_sh + (long long)x * p.out_sw;
+      else if (p.out_mode == 1)       // 2x2 transposed-conv scatter: quadrant offset added per column chunk
+        out_off = (long long)img * p.out_sn + (long long)(2 * y) * p.out_sh + (long long)(2 * x) * p.out_sw;
+      else                            // phase-split store for a following stride-2 convolution
+        out_off = (long long)((y & 1) * 2 + (x & 1)) * p.out_plane + (long long)img * p.out_sn +
+                  (long long)(y >> 1) * p.out_sh + (long long)(x >> 1) * p.out_sw;
       const __nv_bfloat16* res_row = nullptr;
       if (p.res_mode && interior)
         res_row = p.res + (long long)img * p.res_sn + (long long)(p.res_mode == 2 ? (y >> 1) : y) * p.res_sh +
@@ -307,7 +315,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         long long off = out_off;
         int cc = co0;
-        if (p.out_mode) {                                   // 2x2 transposed-conv scatter (sam.py:74-80)
+        if (p.out_mode == 1) {                              // 2x2 transposed-conv scatter (sam.py:74-80)
           const int cq = p.cout >> 2;
           const int quad = co0 / cq;
           cc = co0 - quad * cq;
@@ -428,8 +436,13 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   if (!device_is_sm100()) { set_error("conv_tc: device is not sm_100"); return CM2_ERR_UNSUPPORTED; }
 #define TC_REQUIRE(cond, ...) do { if (!(cond)) { set_error(__VA_ARGS__); return CM2_ERR_UNSUPPORTED; } } while (0)
   TC_REQUIRE(d->dtype == CM2_BF16 && (d->out_dtype == CM2_BF16 || d->out_dtype == CM2_F32), "conv_tc: needs bf16 sources");
-  TC_REQUIRE(d->stride == 1 && d->kh == d->kw && ((d->kh == 1 && d->pad == 0) || (d->kh == 3 && d->pad == 1)),
-             "conv_tc: only stride-1 1x1/p0 and 3x3/p1 (got k%d s%d p%d)", d->kh, d->stride, d->pad);
+  const bool phase = d->src_phase != 0;
+  if (phase)
+    TC_REQUIRE(d->stride == 2 && d->kh == 3 && d->kw == 3 && d->pad == 1, "conv_tc: phase-split sources need a 3x3/s2/p1 conv");
+  else
+    TC_REQUIRE(d->stride == 1 && d->kh == d->kw && ((d->kh == 1 && d->pad == 0) || (d->kh == 3 && d->pad == 1)),
+               "conv_tc: only stride-1 1x1/p0 and 3x3/p1, or 3x3/s2/p1 on phase-split sources (got k%d s%d p%d)", d->kh,
+               d->stride, d->pad);
   TC_REQUIRE(!d->in_relu && !d->chan_sum, "conv_tc: in_relu / chan_sum not supported");
   const bool halo = is_halo_view(s0);
   TC_REQUIRE(halo || (d->kh == 1 && is_dense_view(s0)), "conv_tc: source 0 is neither a halo-1 view nor (for 1x1) dense");
@@ -448,6 +461,18 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   p->plane = halo ? (s0.h + 2) * (s0.w + 2) : s0.h * s0.w;
   long long rows = (long long)s0.n * p->plane;
   TC_REQUIRE(rows > 0 && rows < (1ll << 31) - 4096, "conv_tc: %lld rows out of range", rows);
+  TC_REQUIRE(!phase || halo, "conv_tc: phase-split sources must be halo views");
+  TC_REQUIRE(!phase || rows * 4 < (1ll << 31) - 4096, "conv_tc: phase-split source too large");
+  for (int tap = 0; tap < p->taps; ++tap) {
+    const int ky = tap / 3, kx = tap % 3;
+    if (p->taps == 1) p->tap_shift[tap] = 0;
+    else if (!phase) p->tap_shift[tap] = (ky - 1) * p->pitch + (kx - 1);
+    else {
+      // input row 2*oy + ky - 1: ky = 0 -> odd plane, one line up; ky = 1 -> even plane; ky = 2 -> odd plane, same line
+      const int py = ky == 1 ? 0 : 1, px = kx == 1 ? 0 : 1, dy = ky == 0 ? -1 : 0, dx = kx == 0 ? -1 : 0;
+      p->tap_shift[tap] = (int)((py * 2 + px) * rows) + dy * p->pitch + dx;
+    }
+  }
   p->rows = (int)rows;
   p->m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
   p->cout = d->cout;
@@ -466,8 +491,9 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   p->out_sn = d->out.sn; p->out_sh = d->out.sh; p->out_sw = d->out.sw;
   p->out_f32 = d->out_dtype == CM2_F32;
   p->out_mode = d->out_mode;
+  p->out_plane = (long long)d->out.n * d->out.sn;
   p->out_halo = (halo && d->out_mode == 0 && is_halo_view(d->out) && d->out.h == s0.h && d->out.w == s0.w) ? 1 : 0;
-  const int oc = d->out_mode ? d->cout / 4 : d->cout;
+  const int oc = d->out_mode == 1 ? d->cout / 4 : d->cout;
   const int oeb = p->out_f32 ? 4 : 2;
   p->out_vec = (oc % 16 == 0 && d->out.sn % 8 == 0 && d->out.sh % 8 == 0 && d->out.sw % 8 == 0 &&
                 (reinterpret_cast<uintptr_t>(d->out.data) % (size_t)(8 * oeb)) == 0) ? 1 : 0;
@@ -485,7 +511,7 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     // base of the flat matrix = address of padded pixel (0,0) of image 0
     const char* basep = reinterpret_cast<const char*>(d->src[i].data);
     if (halo) basep -= (size_t)(d->src[i].sh + d->src[i].sw) * 2;
-    if (!encode_2d(&p->a_map[i], basep, (uint64_t)rows, (uint64_t)d->src[i].c, TC_BM)) {
+    if (!encode_2d(&p->a_map[i], basep, (uint64_t)rows * (phase ? 4 : 1), (uint64_t)d->src[i].c, TC_BM)) {
       set_error("conv_tc: cuTensorMapEncodeTiled failed for source %d", i);
       return CM2_ERR_CUDA;
     }

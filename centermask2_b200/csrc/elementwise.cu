@@ -263,6 +263,63 @@ __global__ void relu_kernel(View<const T> in, View<T> out) {
   }
 }
 
+// phase-split copy: pixel (y, x) -> plane (y&1)*2 + (x&1) at (y>>1, x>>1), optional ReLU
+template <typename T>
+__global__ void phase_split_kernel(View<const T> in, View<T> out, long long plane_stride, int relu) {
+  int c8 = in.c >> 3;
+  int64_t total8 = (int64_t)in.n * in.h * in.w * c8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % c8);
+    int64_t pix = i / c8;
+    int xx = (int)(pix % in.w);
+    int64_t t = pix / in.w;
+    int y = (int)(t % in.h);
+    int b = (int)(t / in.h);
+    float v[8];
+    Vec8<T>::load(in.at(b, y, xx) + cv * 8, v);
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+    Vec8<T>::store(out.at(b, y >> 1, xx >> 1) + ((y & 1) * 2 + (xx & 1)) * plane_stride + cv * 8, v);
+  }
+}
+
+// fused normalise + pad + im2col (3x3, stride 2, pad 1, Cin 3) -> 32 bf16 channels per output pixel
+template <typename InT>
+__global__ void preprocess_im2col_kernel(const InT* __restrict__ img, int h, int w, int ho, int wo, float m0, float m1,
+                                         float m2, float r0, float r1, float r2, View<__nv_bfloat16> out, int b) {
+  int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  int oy = blockIdx.y;
+  if (ox >= wo) return;
+  const size_t plane = (size_t)h * w;
+  const float mean[3] = {m0, m1, m2}, rstd[3] = {r0, r1, r2};
+  float v[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    int iy = 2 * oy + ky - 1;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      int ix = 2 * ox + kx - 1;
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
+        size_t o = (size_t)iy * w + ix;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[(ky * 3 + kx) * 3 + c] = ((float)img[c * plane + o] - mean[c]) / rstd[c];
+      }
+    }
+  }
+  __nv_bfloat16* q = out.at(b, oy, ox);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float t8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t8[k] = v[j * 8 + k];
+    Vec8<__nv_bfloat16>::store(q + j * 8, t8);
+  }
+}
+
 int grid_for(int64_t work, int block) {
   int64_t g = ceil_div64(work, block);
   int64_t cap = 148 * 16;
@@ -294,6 +351,52 @@ extern "C" int cm2_preprocess_image(const void* img, int32_t in_dtype, int32_t h
   else { set_error("preprocess: unsupported dtypes %d -> %d", in_dtype, out_dtype); return CM2_ERR_UNSUPPORTED; }
 #undef CM2_PRE
   CM2_CHECK_LAUNCH("preprocess");
+  return CM2_OK;
+}
+
+extern "C" int cm2_preprocess_im2col(const void* img, int32_t in_dtype, int32_t h, int32_t w, int32_t hp, int32_t wp,
+                                     const float* mean3, const float* std3, const cm2_act* out, int32_t out_index,
+                                     void* stream) {
+  CM2_CHECK_ARG(img && out && out->data && mean3 && std3, "preprocess_im2col: null pointer");
+  CM2_CHECK_ARG(h > 0 && w > 0 && hp >= h && wp >= w && hp % 2 == 0 && wp % 2 == 0, "preprocess_im2col: bad extents");
+  CM2_CHECK_ARG(out->h == hp / 2 && out->w == wp / 2 && out->c == 32 && out_index >= 0 && out_index < out->n &&
+                vec8_ok(*out, 2), "preprocess_im2col: out view [%d,%d,%d,%d] != [n,%d,%d,32]", out->n, out->h, out->w,
+                out->c, hp / 2, wp / 2);
+  dim3 grid(ceil_div(out->w, 128), out->h);
+  cudaStream_t s = (cudaStream_t)stream;
+  // (x - mean) / std is computed with a true division, exactly as cm2_preprocess_image does
+  if (in_dtype == CM2_F32)
+    preprocess_im2col_kernel<float><<<grid, 128, 0, s>>>((const float*)img, h, w, out->h, out->w, mean3[0], mean3[1],
+                                                         mean3[2], std3[0], std3[1], std3[2],
+                                                         make_view<__nv_bfloat16>(*out), out_index);
+  else if (in_dtype == CM2_U8)
+    preprocess_im2col_kernel<uint8_t><<<grid, 128, 0, s>>>((const uint8_t*)img, h, w, out->h, out->w, mean3[0], mean3[1],
+                                                           mean3[2], std3[0], std3[1], std3[2],
+                                                           make_view<__nv_bfloat16>(*out), out_index);
+  else { set_error("preprocess_im2col: unsupported input dtype %d", in_dtype); return CM2_ERR_UNSUPPORTED; }
+  CM2_CHECK_LAUNCH("preprocess_im2col");
+  return CM2_OK;
+}
+
+extern "C" int cm2_phase_split(const cm2_act* in, const cm2_act* out_plane0, int32_t dtype, int32_t relu, void* stream) {
+  CM2_CHECK_ARG(in && out_plane0 && in->data && out_plane0->data, "phase_split: null pointer");
+  CM2_CHECK_DTYPE(dtype, "phase_split");
+  int eb = elem_bytes(dtype);
+  CM2_CHECK_ARG(vec8_ok(*in, eb) && vec8_ok(*out_plane0, eb), "phase_split: channels/strides must be multiples of 8");
+  CM2_CHECK_ARG(out_plane0->n == in->n && out_plane0->c == in->c && out_plane0->h == (in->h + 1) / 2 &&
+                out_plane0->w == (in->w + 1) / 2, "phase_split: plane view [%d,%d,%d,%d] does not match input [%d,%d,%d,%d]",
+                out_plane0->n, out_plane0->h, out_plane0->w, out_plane0->c, in->n, in->h, in->w, in->c);
+  int64_t total8 = (int64_t)in->n * in->h * in->w * (in->c / 8);
+  if (total8 == 0) return CM2_OK;
+  long long ps = (long long)out_plane0->n * out_plane0->sn;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == CM2_F32)
+    phase_split_kernel<float><<<grid_for(total8, 256), 256, 0, s>>>(make_view<const float>(*in),
+                                                                   make_view<float>(*out_plane0), ps, relu);
+  else
+    phase_split_kernel<__nv_bfloat16><<<grid_for(total8, 256), 256, 0, s>>>(make_view<const __nv_bfloat16>(*in),
+                                                                          make_view<__nv_bfloat16>(*out_plane0), ps, relu);
+  CM2_CHECK_LAUNCH("phase_split");
   return CM2_OK;
 }
 

@@ -54,6 +54,38 @@ class FMap(object):
         return t
 
 
+class PhaseMap(object):
+    """A feature map stored as four stride-2 phase planes, ``buf[q, n, ceil(H/2)+2, ceil(W/2)+2, c]`` with
+    q = (y&1)*2 + (x&1): the layout the tensor-core engine reads for 3x3 / stride-2 convolutions
+    (``include/cm2.h``: ``src_phase`` / ``out_mode`` 2).  ``view`` is the interior of plane 0."""
+
+    __slots__ = ("buf",)
+    halo = 1
+
+    def __init__(self, buf):
+        self.buf = buf
+
+    @property
+    def view(self):
+        return self.buf[0, :, 1:-1, 1:-1, :]
+
+    @property
+    def n(self):
+        return self.buf.shape[1]
+
+    @property
+    def h(self):
+        return self.buf.shape[2] - 2
+
+    @property
+    def w(self):
+        return self.buf.shape[3] - 2
+
+    @property
+    def c(self):
+        return self.buf.shape[4]
+
+
 def as_fmap(t, dtype, device):
     """Accept what a detectron2 caller hands over: one of our own tensors (zero copy) or any NCHW
     tensor (copied once into a halo buffer)."""
@@ -91,24 +123,41 @@ class Engine(object):
     def fmap(self, name, n, h, w, c, dtype=None, halo=1):
         return FMap(self.buffer(name, (n, h + 2 * halo, w + 2 * halo, c), dtype or self.dtype), halo)
 
+    def phasemap(self, name, n, h, w, c):
+        """Phase planes for a full-resolution [n, h, w, c] map."""
+        return PhaseMap(self.buffer(name, (4, n, (h + 1) // 2 + 2, (w + 1) // 2 + 2, c), self.dtype))
+
+    def phase_split(self, name, x, relu=False):
+        out = self.phasemap(name, x.n, x.h, x.w, x.c)
+        lib.phase_split(x.view, out.view, relu)
+        return out
+
     def release(self):
         self._bufs.clear()
 
     # -- one convolution -------------------------------------------------------------------------
     def conv(self, name, srcs, w, out_dtype=None, residual=None, res_mode=0, out_mode=0, in_relu=False,
              out_halo=1, chan_sum=None, out=None):
+        """One convolution.  ``srcs`` are FMaps (virtual concat) or, for a stride-2 conv on the TC engine,
+        PhaseMaps.  ``out_mode`` 1 = deconv scatter, 2 = write the result as a PhaseMap."""
         x0 = srcs[0]
-        ho = (x0.h + 2 * w.pad - w.k) // w.stride + 1
-        wo = (x0.w + 2 * w.pad - w.k) // w.stride + 1
+        src_phase = isinstance(x0, PhaseMap)
+        if src_phase:
+            ho, wo = x0.h, x0.w
+        else:
+            ho = (x0.h + 2 * w.pad - w.k) // w.stride + 1
+            wo = (x0.w + 2 * w.pad - w.k) // w.stride + 1
         if out is None:
             if out_mode == 0:
                 out = self.fmap(name, x0.n, ho, wo, w.cout, out_dtype, out_halo)
-            else:
+            elif out_mode == 1:
                 out = self.fmap(name, x0.n, 2 * ho, 2 * wo, w.cout // 4, out_dtype, out_halo)
+            else:
+                out = self.phasemap(name, x0.n, ho, wo, w.cout)
         views = [s.view for s in srcs]
         for v, c in zip(views, w.src_c):
             assert v.shape[3] == c, (name, v.shape, w.src_c)
-        kw = dict(scale=w.scale, shift=w.shift, relu=w.relu, in_relu=in_relu,
+        kw = dict(scale=w.scale, shift=w.shift, relu=w.relu, in_relu=in_relu, src_phase=src_phase,
                   residual=None if residual is None else residual.view, res_mode=res_mode, out_mode=out_mode)
         if self.tc and w.w_tc is not None and lib.conv2d(views, w.w_tc, out.view, w.cout, w.k, w.stride, w.pad,
                                                           engine=lib.ENGINE_TC, chan_sum=chan_sum, probe=True, **kw):
@@ -129,6 +178,15 @@ class Engine(object):
         for i, (c, s) in enumerate(zip(stem, (2, 1, 2))):
             P["stem"].append(packing.conv_bn_relu(sd, prefix + "bottom_up.stem.stem_{}".format(i + 1), [cin], s, 1, dt, dev, tc))
             cin = c
+        if tc:
+            # stem_1 as a 1x1 conv over the fused normalise+im2col input (cm2_preprocess_im2col): K = 27 -> 32
+            k1 = prefix + "bottom_up.stem.stem_1"
+            w1 = sd[k1 + "/conv.weight"].detach().float()
+            w32 = torch.zeros((w1.shape[0], 32, 1, 1))
+            w32[:, :27, 0, 0] = w1.permute(0, 2, 3, 1).reshape(w1.shape[0], 27)
+            sc, sh = packing.fold_frozen_bn(sd[k1 + "/norm.weight"], sd[k1 + "/norm.bias"], sd[k1 + "/norm.running_mean"],
+                                            sd[k1 + "/norm.running_var"])
+            P["stem1_im2col"] = packing.ConvW(w32, [32], 1, 0, sc, sh, True, dt, dev, tc)
         for b in blocks:
             convs = []
             c = b.in_ch
@@ -155,8 +213,17 @@ class Engine(object):
     def run_backbone(self, x, P):
         """x: FMap [N, Hp, Wp, 3] (normalised, padded to /32).  Returns {"p3": FMap, ...}."""
         cfg = self.cfg
-        for i, w in enumerate(P["stem"]):
-            x = self.conv("stem{}".format(i + 1), [x], w)
+        if self.tc:
+            # tensor-core path: stem_1 = 1x1 over the im2col'd input, stem_2 writes phase planes, stem_3 (stride 2) reads them
+            if x.c == 32:
+                x = self.conv("stem1", [x], P["stem1_im2col"])
+            else:
+                x = self.conv("stem1", [x], P["stem"][0])
+            x = self.conv("stem2", [x], P["stem"][1], out_mode=2)
+            x = self.conv("stem3", [x], P["stem"][2])
+        else:
+            for i, w in enumerate(P["stem"]):
+                x = self.conv("stem{}".format(i + 1), [x], w)
         stage = 2
         stage_out = {}
         for b, convs, cat, ese_w, ese_b in P["blocks"]:
@@ -199,7 +266,11 @@ class Engine(object):
         # LastLevelP6P7, fpn.py:32-35 (P7 = conv(relu(P6)))
         top = res["p5"]
         for i, w in enumerate(P["top"]):
-            top = self.conv("p{}".format(6 + i), [top], w, in_relu=(i == 1))
+            if self.tc:
+                src = self.phase_split("p{}_phase".format(5 + i), top, relu=(i == 1))
+                top = self.conv("p{}".format(6 + i), [src], w)
+            else:
+                top = self.conv("p{}".format(6 + i), [top], w, in_relu=(i == 1))
             res["p{}".format(6 + i)] = top
         return {k: res[k] for k in sorted(res)}
 
@@ -368,10 +439,13 @@ class Engine(object):
             pm = self.fmap("iou_mask", R, res, res, 16)
             lib.maskiou_prep(probs, pm.view)
             y = None
+            nconv = len(P["iou_fcn"])
             for k, w in enumerate(P["iou_fcn"]):
-                last = k + 1 == len(P["iou_fcn"])
+                last = k + 1 == nconv
                 srcs = [roi, pm] if k == 0 else [y]
-                y = self.conv("iou_fcn{}".format(k + 1), srcs, w, out_halo=0 if last else 1)
+                # the last conv is stride 2: on the TC engine its producer stores phase planes
+                to_phase = self.tc and k + 2 == nconv and k > 0
+                y = self.conv("iou_fcn{}".format(k + 1), srcs, w, out_halo=0 if last else 1, out_mode=2 if to_phase else 0)
             flat = FMap(y.buf.reshape(R, 1, 1, -1), 0)
             y = self.conv("iou_fc1", [flat], P["iou_fc1"], out_halo=0)
             y = self.conv("iou_fc2", [y], P["iou_fc2"], out_halo=0)
@@ -383,7 +457,7 @@ class Engine(object):
     # =============================================================================================
     # input / output side
     # =============================================================================================
-    def preprocess(self, images, size_divisibility=32):
+    def preprocess(self, images, size_divisibility=32, fused_stem=True):
         """GeneralizedRCNN.preprocess_image [d2] (deploy_utils.py:76-98): normalise + pad to /32.
         ``images``: list of CHW device tensors (float32 or uint8, BGR)."""
         cfg = self.cfg
@@ -392,6 +466,12 @@ class Engine(object):
         wp = max(s[1] for s in sizes)
         hp = (hp + size_divisibility - 1) // size_divisibility * size_divisibility
         wp = (wp + size_divisibility - 1) // size_divisibility * size_divisibility
+        if self.tc and fused_stem and len(cfg.MODEL.PIXEL_MEAN) == 3:
+            # normalise + pad + im2col of stem_1 in one pass (the TC engine then runs stem_1 as a 1x1 conv)
+            x = self.fmap("input_im2col", len(images), hp // 2, wp // 2, 32)
+            for i, im in enumerate(images):
+                lib.preprocess_im2col(im.contiguous(), cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD, hp, wp, x.view, i)
+            return x, sizes
         x = self.fmap("input", len(images), hp, wp, 3)
         for i, im in enumerate(images):
             lib.preprocess_image(im.contiguous(), cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD, x.view, i)

@@ -31,7 +31,7 @@ class ConvDesc(C.Structure):
                 ("weight", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("relu", C.c_int32), ("in_relu", C.c_int32),
                 ("residual", Act), ("res_mode", C.c_int32), ("out_mode", C.c_int32),
-                ("out", Act), ("chan_sum", C.c_void_p)]
+                ("out", Act), ("chan_sum", C.c_void_p), ("src_phase", C.c_int32)]
 
 
 class CandBuffers(C.Structure):
@@ -55,6 +55,8 @@ SYMBOLS = {
     "cm2_conv_tc_klen": (_L, [_I, _I, _I, C.POINTER(_I)]),
     "cm2_conv_tc_supported": (_I, [C.POINTER(ConvDesc)]),
     "cm2_preprocess_image": (_I, [_P, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _AP, _I, _I, _P]),
+    "cm2_preprocess_im2col": (_I, [_P, _I, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _AP, _I, _P]),
+    "cm2_phase_split": (_I, [_AP, _AP, _I, _I, _P]),
     "cm2_maxpool3x3s2_ceil": (_I, [_AP, _AP, _I, _P]),
     "cm2_ese_pool_chunks": (_I, [_I]),
     "cm2_ese_pool": (_I, [_AP, _I, _P, _P, _P]),
@@ -137,7 +139,7 @@ def _count(k=1):
 # thin wrappers (one per entry point)
 # ------------------------------------------------------------------------------------------------
 def conv2d(srcs, weight, out, cout, k, stride, pad, scale=None, shift=None, relu=False, in_relu=False,
-           residual=None, res_mode=0, out_mode=0, engine=ENGINE_SIMT, chan_sum=None, probe=False):
+           residual=None, res_mode=0, out_mode=0, engine=ENGINE_SIMT, chan_sum=None, probe=False, src_phase=False):
     """Enqueue one convolution.  With ``probe=True`` (TC engine) the descriptor is first checked with
     ``cm2_conv_tc_supported``; returns False without launching if the engine does not take it."""
     d = ConvDesc()
@@ -157,6 +159,7 @@ def conv2d(srcs, weight, out, cout, k, stride, pad, scale=None, shift=None, relu
     d.out_mode = out_mode
     d.out = act(out)
     d.chan_sum = 0 if chan_sum is None else chan_sum.data_ptr()
+    d.src_phase = int(src_phase)
     if probe and not load().cm2_conv_tc_supported(C.byref(d)):
         return False
     check(load().cm2_conv2d(C.byref(d), stream()), "cm2_conv2d")
@@ -175,6 +178,21 @@ def preprocess_image(img, mean, std, out, index):
     a = act(out)
     check(load().cm2_preprocess_image(ptr(img), dtype_code(img), img.shape[1], img.shape[2], m, s, C.byref(a),
                                       dtype_code(out), index, stream()), "cm2_preprocess_image")
+    _count()
+
+
+def preprocess_im2col(img, mean, std, hp, wp, out, index):
+    m = (C.c_float * 3)(*mean)
+    s = (C.c_float * 3)(*std)
+    a = act(out)
+    check(load().cm2_preprocess_im2col(ptr(img), dtype_code(img), img.shape[1], img.shape[2], hp, wp, m, s, C.byref(a),
+                                       index, stream()), "cm2_preprocess_im2col")
+    _count()
+
+
+def phase_split(x, out_plane0, relu=False):
+    a, o = act(x), act(out_plane0)
+    check(load().cm2_phase_split(C.byref(a), C.byref(o), dtype_code(x), int(relu), stream()), "cm2_phase_split")
     _count()
 
 

@@ -72,7 +72,7 @@ class GeneralizedRCNN(nn.Module):
         """[d2] API parity: returns an ``ImageList`` whose tensor is the normalised padded batch [N,3,H,W]."""
         eng = runtime.engine_for(self.cfg)
         images = [b["image"].to(eng.device) for b in batched_inputs]
-        x, sizes = eng.preprocess(images, self.backbone.size_divisibility)
+        x, sizes = eng.preprocess(images, self.backbone.size_divisibility, fused_stem=False)
         return ImageList(x.nchw(), sizes)
 
     def detector_postprocess(self, results, output_height, output_width, mask_threshold=0.5):

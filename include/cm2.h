@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CM2_VERSION 101
+#define CM2_VERSION 102
 
 #define CM2_OK 0
 #define CM2_ERR_BAD_SHAPE (-1)
@@ -98,11 +98,18 @@ typedef struct cm2_conv_desc {
                          upsample ([d2] FPN top-down path)                                        */
   int32_t out_mode;   /* 0: out is [n,ho,wo,cout]
                          1: 2x2/stride-2 transposed-conv scatter: GEMM column j = (dy*2+dx)*(cout/4)
-                            + co goes to out[n, 2y+dy, 2x+dx, co]  (out is [n,2ho,2wo,cout/4])     */
+                            + co goes to out[n, 2y+dy, 2x+dx, co]  (out is [n,2ho,2wo,cout/4])
+                         2: phase-split store (TC engine): out is plane 0 of four phase planes,
+                            [n, ceil(ho/2), ceil(wo/2), cout]; pixel (y,x) goes to plane
+                            (y&1)*2+(x&1) at (y>>1, x>>1)                                          */
   cm2_act out;
   /* optional per-(image, channel) sum of the stored (post-activation) outputs, float [n][cout],
    * accumulated with atomics (caller zeroes); used for the eSE global pool.  NULL: off.  TC only. */
   float* chan_sum;
+  /* 1: every source is stored as four stride-2 *phase planes* (see cm2_phase_split): src[i] is the
+   * halo-1 interior view of plane 0, [n, ceil(H/2), ceil(W/2), c], plane q = (y&1)*2 + (x&1) starts
+   * n*sn elements after plane q-1.  Requires a 3x3 / stride 2 / pad 1 convolution; TC engine only. */
+  int32_t src_phase;
 } cm2_conv_desc;
 
 int cm2_conv2d(const cm2_conv_desc* d, void* stream);
@@ -120,6 +127,14 @@ int cm2_conv_tc_supported(const cm2_conv_desc* d);
 int cm2_preprocess_image(const void* img, int32_t in_dtype, int32_t h, int32_t w, const float* mean3,
                          const float* std3, const cm2_act* out, int32_t out_dtype, int32_t out_index,
                          void* stream);
+
+/* Fused input side for the tensor-core path: normalise + zero-pad (as above) + im2col of the first
+ * stem convolution (vovnet.py:409: 3x3, stride 2, pad 1, Cin 3).  out: view [n, hp/2, wp/2, 32] bf16,
+ * channel k = (ky*3 + kx)*3 + c for k < 27, zero for k >= 27; image `out_index` is written.  stem_1
+ * then is a 1x1 convolution with K = 32 on the TC engine. */
+int cm2_preprocess_im2col(const void* img, int32_t in_dtype, int32_t h, int32_t w, int32_t hp, int32_t wp,
+                          const float* mean3, const float* std3, const cm2_act* out, int32_t out_index,
+                          void* stream);
 
 /* MaxPool2d(3, stride 2, ceil_mode=True), vovnet.py:349-350. */
 int cm2_maxpool3x3s2_ceil(const cm2_act* in, const cm2_act* out, int32_t dtype, void* stream);
@@ -140,6 +155,11 @@ int cm2_ese_apply(const cm2_act* x, const float* gate, const cm2_act* identity, 
 int64_t cm2_gn_workspace_floats(int32_t n, int32_t hw, int32_t c, int32_t groups);
 int cm2_groupnorm_relu(const cm2_act* x, int32_t dtype, int32_t groups, const float* gamma,
                        const float* beta, float eps, int32_t relu, float* workspace, void* stream);
+
+/* Phase-split copy (optionally with ReLU, fpn.py:34): in [n,h,w,c] -> four planes, out = plane 0 view
+ * [n, ceil(h/2), ceil(w/2), c] (planes n*sn elements apart); pixel (y,x) -> plane (y&1)*2+(x&1) at
+ * (y>>1, x>>1).  Positions of a plane that no input pixel maps to are left untouched (zero). */
+int cm2_phase_split(const cm2_act* in, const cm2_act* out_plane0, int32_t dtype, int32_t relu, void* stream);
 
 /* Elementwise ReLU copy (P7 input when the conv engine cannot apply in_relu). */
 int cm2_relu(const cm2_act* in, const cm2_act* out, int32_t dtype, void* stream);

@@ -157,3 +157,79 @@ def test_unsupported_shapes_are_refused_not_miscomputed():
     assert lib.conv2d([x.view], w, out.view, 64, 3, 2, 1, engine=lib.ENGINE_TC, probe=True) is False
     with pytest.raises(RuntimeError):
         lib.conv2d([x.view], w, out.view, 64, 3, 2, 1, engine=lib.ENGINE_TC)
+
+
+@pytest.mark.parametrize("cin,cout,h,w,n", [(64, 128, 24, 32, 2), (256, 256, 25, 42, 1), (256, 256, 13, 21, 2),
+                                            (256, 256, 14, 14, 7)])
+def test_conv_tc_stride2_on_phase_planes(cin, cout, h, w, n):
+    """3x3 / stride 2 / pad 1 (stem_3, P6, P7, maskiou_fcn4) through cm2_phase_split + src_phase."""
+    g = torch.Generator().manual_seed(cin + h)
+    x = rb(torch.randn(n, cin, h, w, generator=g))
+    wt = rb(torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9))
+    bias = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv2d(F.relu(x), wt, bias, 2, 1)
+    ho, wo = ref.shape[2], ref.shape[3]
+    planes = torch.zeros((4, n, ho + 2, wo + 2, cin), dtype=BF, device=DEV)
+    lib.phase_split(halo(x).view, planes[0, :, 1:-1, 1:-1, :], relu=True)
+    torch.cuda.synchronize()
+    # the four planes hold the (relu'd) input pixels by parity
+    xr = F.relu(x)
+    for q in range(4):
+        py, px = q >> 1, q & 1
+        sub = xr[:, :, py::2, px::2]
+        got = planes[q, :, 1:1 + sub.shape[2], 1:1 + sub.shape[3], :].permute(0, 3, 1, 2).float().cpu()
+        assert torch.equal(got, sub)
+    cw = packing.ConvW(wt, [cin], 2, 1, None, bias, False, BF, DEV, True)
+    out = torch.zeros((n, ho, wo, cout), dtype=BF, device=DEV)
+    assert lib.conv2d([planes[0, :, 1:-1, 1:-1, :]], cw.w_tc, out, cout, 3, 2, 1, shift=cw.shift, engine=lib.ENGINE_TC,
+                      probe=True, src_phase=True), lib.last_error()
+    torch.cuda.synchronize()
+    close(nchw(out), ref)
+
+
+def test_conv_tc_phase_split_store_feeds_stride2_conv():
+    """stem_2 -> stem_3 chain: out_mode 2 (phase-split store) then a stride-2 conv on the planes."""
+    g = torch.Generator().manual_seed(11)
+    n, h, w = 2, 20, 28
+    x = rb(torch.randn(n, 64, h, w, generator=g))
+    w2 = rb(torch.randn(64, 64, 3, 3, generator=g) / 24)
+    w3 = rb(torch.randn(128, 64, 3, 3, generator=g) / 24)
+    mid = rb(F.relu(F.conv2d(x, w2, None, 1, 1)))
+    ref = F.relu(F.conv2d(mid, w3, None, 2, 1))
+    c2 = packing.ConvW(w2, [64], 1, 1, None, None, True, BF, DEV, True)
+    c3 = packing.ConvW(w3, [64], 2, 1, None, None, True, BF, DEV, True)
+    planes = torch.zeros((4, n, h // 2 + 2, w // 2 + 2, 64), dtype=BF, device=DEV)
+    p0 = planes[0, :, 1:-1, 1:-1, :]
+    assert lib.conv2d([halo(x).view], c2.w_tc, p0, 64, 3, 1, 1, relu=True, out_mode=2, engine=lib.ENGINE_TC, probe=True)
+    out = halo(torch.zeros(n, 128, h // 2, w // 2))
+    assert lib.conv2d([p0], c3.w_tc, out.view, 128, 3, 2, 1, relu=True, engine=lib.ENGINE_TC, probe=True, src_phase=True)
+    torch.cuda.synchronize()
+    for q in range(4):
+        py, px = q >> 1, q & 1
+        got = planes[q, :, 1:-1, 1:-1, :].permute(0, 3, 1, 2).float().cpu()
+        close(got, mid[:, :, py::2, px::2])
+        assert planes[q, :, 0].abs().max() == 0 and planes[q, :, :, 0].abs().max() == 0      # plane halos stay zero
+    close(nchw(out.view), ref)
+
+
+def test_fused_preprocess_im2col_stem1():
+    """cm2_preprocess_im2col + 1x1 TC conv == normalise/pad + 3x3 s2 conv (vovnet.py:409)."""
+    g = torch.Generator().manual_seed(12)
+    h, w, hp, wp = 45, 61, 64, 64
+    img = (torch.rand(3, h, w, generator=g) * 255).floor()
+    mean, std = [103.53, 116.28, 123.675], [1.0, 1.0, 1.0]
+    xn = torch.zeros(1, 3, hp, wp)
+    xn[0, :, :h, :w] = rb(img - torch.tensor(mean).view(3, 1, 1))
+    w1 = rb(torch.randn(64, 3, 3, 3, generator=g) / 5)
+    ref = F.conv2d(xn, w1, None, 2, 1)
+    w32 = torch.zeros(64, 32, 1, 1)
+    w32[:, :27, 0, 0] = w1.permute(0, 2, 3, 1).reshape(64, 27)
+    cw = packing.ConvW(w32, [32], 1, 0, None, None, False, BF, DEV, True)
+    for src in (img, img.to(torch.uint8)):
+        cols = halo(torch.zeros(2, 32, hp // 2, wp // 2))
+        lib.preprocess_im2col(src.to(DEV), mean, std, hp, wp, cols.view, 1)
+        out = halo(torch.zeros(2, 64, hp // 2, wp // 2))
+        assert lib.conv2d([cols.view], cw.w_tc, out.view, 64, 1, 1, 0, engine=lib.ENGINE_TC, probe=True)
+        torch.cuda.synchronize()
+        close(nchw(out.view)[1:], ref)
+        assert nchw(out.view)[0].abs().max() == 0

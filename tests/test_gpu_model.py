@@ -123,3 +123,34 @@ def test_layerwise_against_oracle_trace():
         assert (reg - tr["regs"][l]).abs().max().item() <= 2e-3 * max(1.0, tr["regs"][l].abs().max().item()), l
         ctr = rc.view[..., 4:5].permute(0, 3, 1, 2).cpu()
         assert (ctr - tr["ctrs"][l]).abs().max().item() <= 2e-3, l
+
+
+def test_bf16_tensor_core_model_tracks_the_fp32_oracle():
+    """bf16 variant (tcgen05 engine): ~60 bf16 layers cannot meet the fp32 tolerances bit for bit, so this
+    checks the *raw deviation* against the fp32 oracle: feature maps within 3% relative L2, and the
+    detections it keeps overlap the oracle's (same class + same originating location) by >= 70%."""
+    runtime.reset()
+    runtime.set_precision("bf16")
+    try:
+        name = "v39_one_image"
+        gold = load_golden(name)
+        cfg, sd, inputs = build_case(name, gold)
+        model = cm.build_model(cfg)
+        model.load_state_dict(sd)
+        eng = runtime.engine_for(cfg)
+        x, sizes = eng.preprocess([b["image"].cuda() for b in inputs])
+        feats = model.backbone.forward_fmap(x)
+        for k, v in gold["features"].items():
+            got = feats[k].view.permute(0, 3, 1, 2).float().cpu()
+            rel = (got - v).norm() / v.norm()
+            assert rel <= 0.03, (k, rel.item())
+        out = model.inference(inputs, do_postprocess=False)
+        ref = gold["raw"]
+        for o, r in zip(out, ref):
+            g = fields(o)
+            keys_ref = {(int(c), float(l[0]), float(l[1])) for c, l in zip(r["pred_classes"], r["locations"])}
+            keys_got = {(int(c), float(l[0]), float(l[1])) for c, l in zip(g["pred_classes"], g["locations"])}
+            assert len(keys_ref & keys_got) >= 0.7 * len(keys_ref), (len(keys_ref & keys_got), len(keys_ref))
+    finally:
+        runtime.reset()
+        runtime.set_precision("fp32")
