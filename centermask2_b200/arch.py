@@ -77,6 +77,11 @@ def backbone_param_spec(cfg):
             _conv_bn(spec, "bottom_up." + b.key(i), b.mid_ch, c, 3)
             c = b.mid_ch
         _conv_bn(spec, "bottom_up." + b.key("concat"), b.out_ch, b.cat_ch, 1)
+        if b.identity:
+            # synthetic-weight hint only: residual blocks get a damped aggregation conv so that deep bodies
+            # (V-99: 9 residual blocks in stage 4) keep O(1..100) activations instead of growing geometrically
+            k = "bottom_up." + b.key("concat") + "/conv.weight"
+            spec[k] = (spec[k][0], "conv_relu_residual")
         spec["bottom_up." + b.ese_key() + ".weight"] = ((b.out_ch, b.out_ch, 1, 1), "ese_weight")
         spec["bottom_up." + b.ese_key() + ".bias"] = ((b.out_ch,), "ese_bias")
     out_ch = {"stage{}".format(b.stage): b.out_ch for b in blocks}

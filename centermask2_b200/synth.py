@@ -35,6 +35,8 @@ def _draw(kind, shape, g, key):
         fan_in *= d
     if kind == "conv_relu" or kind == "fc_relu":
         return normal(math.sqrt(2.0 / fan_in))
+    if kind == "conv_relu_residual":
+        return normal(0.35 * math.sqrt(2.0 / fan_in))
     if kind == "conv_linear":
         return normal(math.sqrt(1.0 / fan_in))
     if kind == "deconv":          # (Cin, Cout, 2, 2), stride 2: one tap per output pixel

@@ -25,16 +25,43 @@ from centermask2_b200.arch import vovnet_blocks          # static layer tables o
 
 BN_EPS = 1e-5
 
+# ----------------------------------------------------------------------------------------------
+# bf16 simulation.  The tensor-core engine keeps activations and weights in bf16 (fp32 accumulation,
+# fp32 epilogue, one rounding when a layer's output is stored).  With ``bf16_sim(True)`` this
+# restatement rounds at the same places -- conv / linear weights, and every tensor the engine stores as
+# bf16 -- so that the CUDA bf16 path can be checked against a reference that differs only by
+# accumulation order.  Head outputs (logits, reg, ctr, mask probabilities, MaskIoU) stay fp32 there.
+# ----------------------------------------------------------------------------------------------
+_BF16 = False
+
+
+class bf16_sim(object):
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        global _BF16
+        self.prev, _BF16 = _BF16, self.on
+
+    def __exit__(self, *a):
+        global _BF16
+        _BF16 = self.prev
+
+
+def _q(x):
+    """Round to bf16 (and back to fp32) when simulating the tensor-core engine."""
+    return x.to(torch.bfloat16).to(torch.float32) if _BF16 else x
+
 
 # ----------------------------------------------------------------------------------------------
 # backbone
 # ----------------------------------------------------------------------------------------------
 def _conv_bn_relu(x, sd, prefix, stride, pad):
     """conv (no bias) -> FrozenBN -> ReLU.  modeling/backbone/vovnet.py:205-236; FrozenBN [d2]."""
-    x = F.conv2d(x, sd[prefix + "/conv.weight"], None, stride, pad)
+    x = F.conv2d(x, _q(sd[prefix + "/conv.weight"]), None, stride, pad)
     x = F.batch_norm(x, sd[prefix + "/norm.running_mean"], sd[prefix + "/norm.running_var"],
                      sd[prefix + "/norm.weight"], sd[prefix + "/norm.bias"], False, 0.0, BN_EPS)
-    return F.relu(x)
+    return _q(F.relu(x))
 
 
 def _ese(x, sd, prefix):
@@ -42,7 +69,7 @@ def _ese(x, sd, prefix):
     g = F.adaptive_avg_pool2d(x, 1)
     g = F.conv2d(g, sd[prefix + ".weight"], sd[prefix + ".bias"])
     g = F.relu6(g + 3.0) / 6.0
-    return x * g
+    return x * g          # rounded by the caller (after the optional identity add)
 
 
 def vovnet_forward(x, sd, cfg, prefix="backbone.bottom_up.", trace=None):
@@ -71,7 +98,7 @@ def vovnet_forward(x, sd, cfg, prefix="backbone.bottom_up.", trace=None):
         y = _ese(y, sd, prefix + b.ese_key())                           # :327 (unconditional)
         if b.identity:
             y = y + identity                                           # :329-330
-        x = y
+        x = _q(y)
         outs["stage{}".format(b.stage)] = x
         if trace is not None:
             trace[b.name] = x
@@ -85,21 +112,21 @@ def fpn_forward(feats, sd, cfg, prefix="backbone."):
     prev = None
     for f in reversed(in_features):
         lvl = int(f[-1])
-        lat = F.conv2d(feats[f], sd[prefix + "fpn_lateral{}.weight".format(lvl)],
+        lat = F.conv2d(feats[f], _q(sd[prefix + "fpn_lateral{}.weight".format(lvl)]),
                        sd[prefix + "fpn_lateral{}.bias".format(lvl)])
         if prev is not None:
             lat = lat + F.interpolate(prev, scale_factor=2.0, mode="nearest")
-        prev = lat
-        results["p{}".format(lvl)] = F.conv2d(prev, sd[prefix + "fpn_output{}.weight".format(lvl)],
-                                              sd[prefix + "fpn_output{}.bias".format(lvl)], 1, 1)
+        prev = _q(lat)
+        results["p{}".format(lvl)] = _q(F.conv2d(prev, _q(sd[prefix + "fpn_output{}.weight".format(lvl)]),
+                                                 sd[prefix + "fpn_output{}.bias".format(lvl)], 1, 1))
     top = cfg.MODEL.FCOS.TOP_LEVELS
     if top >= 1:
-        p6 = F.conv2d(results["p5"], sd[prefix + "top_block.p6.weight"], sd[prefix + "top_block.p6.bias"], 2, 1)
+        p6 = _q(F.conv2d(results["p5"], _q(sd[prefix + "top_block.p6.weight"]), sd[prefix + "top_block.p6.bias"], 2, 1))
         results["p6"] = p6
         if top == 2:
             # P7 consumes relu(P6); P6 itself is returned without the ReLU (fpn.py:33-35)
-            results["p7"] = F.conv2d(F.relu(p6), sd[prefix + "top_block.p7.weight"],
-                                     sd[prefix + "top_block.p7.bias"], 2, 1)
+            results["p7"] = _q(F.conv2d(F.relu(p6), _q(sd[prefix + "top_block.p7.weight"]),
+                                        sd[prefix + "top_block.p7.bias"], 2, 1))
     return {k: results[k] for k in sorted(results)}
 
 
@@ -122,11 +149,11 @@ def fcos_head_forward(features, sd, cfg, prefix="proposal_generator.fcos_head.")
     def tower(x, name, n):
         for i in range(n):
             p = prefix + "{}_tower.{}".format(name, per_unit * i)
-            x = F.conv2d(x, sd[p + ".weight"], sd[p + ".bias"], 1, 1)
+            x = _q(F.conv2d(x, _q(sd[p + ".weight"]), sd[p + ".bias"], 1, 1))   # engine stores the conv output, then GN in place
             if use_gn:
                 q = prefix + "{}_tower.{}".format(name, per_unit * i + 1)
                 x = F.group_norm(x, 32, sd[q + ".weight"], sd[q + ".bias"], 1e-5)
-            x = F.relu(x)
+            x = _q(F.relu(x))
         return x
 
     logits, regs, ctrs = [], [], []
@@ -134,9 +161,9 @@ def fcos_head_forward(features, sd, cfg, prefix="proposal_generator.fcos_head.")
         x = tower(features[f], "share", cfg.MODEL.FCOS.NUM_SHARE_CONVS)
         ct = tower(x, "cls", cfg.MODEL.FCOS.NUM_CLS_CONVS)
         bt = tower(x, "bbox", cfg.MODEL.FCOS.NUM_BOX_CONVS)
-        logits.append(F.conv2d(ct, sd[prefix + "cls_logits.weight"], sd[prefix + "cls_logits.bias"], 1, 1))
-        ctrs.append(F.conv2d(bt, sd[prefix + "ctrness.weight"], sd[prefix + "ctrness.bias"], 1, 1))
-        reg = F.conv2d(bt, sd[prefix + "bbox_pred.weight"], sd[prefix + "bbox_pred.bias"], 1, 1)
+        logits.append(F.conv2d(ct, _q(sd[prefix + "cls_logits.weight"]), sd[prefix + "cls_logits.bias"], 1, 1))
+        ctrs.append(F.conv2d(bt, _q(sd[prefix + "ctrness.weight"]), sd[prefix + "ctrness.bias"], 1, 1))
+        reg = F.conv2d(bt, _q(sd[prefix + "bbox_pred.weight"]), sd[prefix + "bbox_pred.bias"], 1, 1)
         if cfg.MODEL.FCOS.USE_SCALE:
             reg = reg * sd[prefix + "scales.{}.scale".format(l)]
         regs.append(F.relu(reg))
@@ -258,34 +285,34 @@ def roi_pool(features, dets, cfg):
         if len(names) == 1:
             inds = torch.arange(rois.shape[0])
         out[inds] = torchvision.ops.roi_align(features[n], rois[inds], res, 1.0 / s, ratio, True)
-    return out, lvls
+    return _q(out), lvls
 
 
 def mask_head_forward(x, sd, cfg, prefix="roi_heads.mask_head."):
     """SpatialAttentionMaskHead.forward (centermask/sam.py:92-97) with SpatialAttention (:23-28)."""
     for k in range(cfg.MODEL.ROI_MASK_HEAD.NUM_CONV):
         p = prefix + "mask_fcn{}".format(k + 1)
-        x = F.relu(F.conv2d(x, sd[p + ".weight"], sd[p + ".bias"], 1, 1))
+        x = _q(F.relu(F.conv2d(x, _q(sd[p + ".weight"]), sd[p + ".bias"], 1, 1)))
     avg = torch.mean(x, dim=1, keepdim=True)
     mx = torch.max(x, dim=1, keepdim=True)[0] if x.numel() else x.new_empty((x.shape[0], 1) + x.shape[2:])
     att = F.conv2d(torch.cat([avg, mx], dim=1), sd[prefix + "spatialAtt.conv.weight"], None, 1, 1)
-    x = x * torch.sigmoid(att)
+    x = _q(x * torch.sigmoid(att))
     feat = x
-    x = F.relu(F.conv_transpose2d(x, sd[prefix + "deconv.weight"], sd[prefix + "deconv.bias"], stride=2))
-    return F.conv2d(x, sd[prefix + "predictor.weight"], sd[prefix + "predictor.bias"]), feat
+    x = _q(F.relu(F.conv_transpose2d(x, _q(sd[prefix + "deconv.weight"]), sd[prefix + "deconv.bias"], stride=2)))
+    return F.conv2d(x, sd[prefix + "predictor.weight"], sd[prefix + "predictor.bias"]), feat      # fp32 predictor weights
 
 
 def maskiou_head_forward(roi_feat, mask, sd, cfg, prefix="roi_heads.maskiou_head."):
     """MaskIoUHead.forward (centermask/maskiou_head.py:107-120)."""
-    x = torch.cat((roi_feat, F.max_pool2d(mask, kernel_size=2, stride=2)), 1)
+    x = torch.cat((roi_feat, _q(F.max_pool2d(mask, kernel_size=2, stride=2))), 1)
     n_conv = cfg.MODEL.ROI_MASKIOU_HEAD.NUM_CONV
     for k in range(n_conv):
         p = prefix + "maskiou_fcn{}".format(k + 1)
-        x = F.relu(F.conv2d(x, sd[p + ".weight"], sd[p + ".bias"], 2 if k + 1 == n_conv else 1, 1))
+        x = _q(F.relu(F.conv2d(x, _q(sd[p + ".weight"]), sd[p + ".bias"], 2 if k + 1 == n_conv else 1, 1)))
     x = torch.flatten(x, 1)
-    x = F.relu(F.linear(x, sd[prefix + "maskiou_fc1.weight"], sd[prefix + "maskiou_fc1.bias"]))
-    x = F.relu(F.linear(x, sd[prefix + "maskiou_fc2.weight"], sd[prefix + "maskiou_fc2.bias"]))
-    return F.linear(x, sd[prefix + "maskiou.weight"], sd[prefix + "maskiou.bias"])
+    x = _q(F.relu(F.linear(x, _q(sd[prefix + "maskiou_fc1.weight"]), sd[prefix + "maskiou_fc1.bias"])))
+    x = _q(F.relu(F.linear(x, _q(sd[prefix + "maskiou_fc2.weight"]), sd[prefix + "maskiou_fc2.bias"])))
+    return F.linear(x, _q(sd[prefix + "maskiou.weight"]), sd[prefix + "maskiou.bias"])
 
 
 def roi_heads_forward(features, dets, sd, cfg, trace=None):
@@ -333,7 +360,7 @@ def preprocess(batched_inputs, cfg, size_divisibility=32):
     mw = (mw + size_divisibility - 1) // size_divisibility * size_divisibility
     out = torch.zeros((len(imgs), imgs[0].shape[0], mh, mw), dtype=torch.float32)
     for i, im in enumerate(imgs):
-        out[i, :, : im.shape[-2], : im.shape[-1]] = im
+        out[i, :, : im.shape[-2], : im.shape[-1]] = _q(im)
     return out, sizes
 
 

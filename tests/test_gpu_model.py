@@ -125,32 +125,48 @@ def test_layerwise_against_oracle_trace():
         assert (ctr - tr["ctrs"][l]).abs().max().item() <= 2e-3, l
 
 
-def test_bf16_tensor_core_model_tracks_the_fp32_oracle():
-    """bf16 variant (tcgen05 engine): ~60 bf16 layers cannot meet the fp32 tolerances bit for bit, so this
-    checks the *raw deviation* against the fp32 oracle: feature maps within 3% relative L2, and the
-    detections it keeps overlap the oracle's (same class + same originating location) by >= 70%."""
+def test_bf16_tensor_core_model_matches_bf16_rounding_oracle():
+    """bf16 variant (tcgen05 engine).  bf16 through ~60 layers of a random-init network deviates from pure fp32
+    by several percent (the same is true of the oracle when it rounds at the same places), so the reference
+    here is ``restate.bf16_sim()``: the fp32 restatement with weights and stored activations rounded to bf16
+    exactly where the engine rounds.  What remains is accumulation order plus the rare rounding flip.
+    Gates: feature maps within 1% relative L2 of the bf16-rounding oracle; head outputs within 2% of their
+    range; >= 90% of the oracle's kept detections (class + originating location) are kept.  The raw deviation
+    against the pure-fp32 oracle is printed for the record."""
     runtime.reset()
     runtime.set_precision("bf16")
     try:
         name = "v39_one_image"
         gold = load_golden(name)
         cfg, sd, inputs = build_case(name, gold)
+        tr = {}
+        with restate.bf16_sim():
+            ref = restate.run_model(inputs, sd, cfg, postprocess=False, trace=tr)
         model = cm.build_model(cfg)
         model.load_state_dict(sd)
         eng = runtime.engine_for(cfg)
         x, sizes = eng.preprocess([b["image"].cuda() for b in inputs])
         feats = model.backbone.forward_fmap(x)
-        for k, v in gold["features"].items():
+        for k, v in tr["features"].items():
             got = feats[k].view.permute(0, 3, 1, 2).float().cpu()
-            rel = (got - v).norm() / v.norm()
-            assert rel <= 0.03, (k, rel.item())
+            rel = ((got - v).norm() / v.norm()).item()
+            raw = ((got - gold["features"][k]).norm() / gold["features"][k].norm()).item()
+            print("bf16 {}: rel L2 vs bf16-rounding oracle {:.4f}, vs fp32 reference {:.4f}".format(k, rel, raw))
+            assert rel <= 0.01, (k, rel)
+        fcos = model.proposal_generator
+        e2, P = fcos._pack()
+        head = e2.run_fcos_head([feats[f] for f in fcos.in_features], P)
+        for l, (lg, rc) in enumerate(head):
+            got = lg.view.permute(0, 3, 1, 2).cpu()
+            span = (tr["logits"][l].max() - tr["logits"][l].min()).item()
+            assert (got - tr["logits"][l]).abs().max().item() <= 0.02 * span, l
         out = model.inference(inputs, do_postprocess=False)
-        ref = gold["raw"]
         for o, r in zip(out, ref):
             g = fields(o)
             keys_ref = {(int(c), float(l[0]), float(l[1])) for c, l in zip(r["pred_classes"], r["locations"])}
             keys_got = {(int(c), float(l[0]), float(l[1])) for c, l in zip(g["pred_classes"], g["locations"])}
-            assert len(keys_ref & keys_got) >= 0.7 * len(keys_ref), (len(keys_ref & keys_got), len(keys_ref))
+            print("bf16 detections kept in common: {}/{}".format(len(keys_ref & keys_got), len(keys_ref)))
+            assert len(keys_ref & keys_got) >= 0.9 * len(keys_ref)
     finally:
         runtime.reset()
         runtime.set_precision("fp32")
