@@ -21,6 +21,7 @@
 // Two accumulator stages (2 x 256 TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace cm2 {
 
@@ -55,6 +56,15 @@ struct alignas(64) TcParams {
   const __nv_bfloat16* res;
   long long res_sn, res_sh, res_sw;
   int res_mode;
+  // ---- v2 kernel (256-row tiles, separate A / B rings, optional kx-merged A slabs)
+  int kx_merge;             // 1: one A slab per (ky, source, k-block) serves the three kx taps
+  int a_box_rows;           // rows per A TMA box: 128, or 136 with kx_merge (two boxes per slab)
+  int sa_stages, sb_stages; // ring depths
+  int acc_stages;           // 2 when bn <= 128 (2 x 2 x 128 TMEM columns), else 1
+  int nblk_total;           // sum over sources of ceil(c / 64)
+  int desc_mode;            // 0: base_offset field 0;  1: base_offset = (start >> 7) & 7 for unaligned starts
+  int variant;              // host only: 1 = conv_tc_kernel (128-row tiles), 2 = conv_tc2_kernel
+  unsigned smem_bytes;      // host only: dynamic shared memory of the launch
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -135,6 +145,116 @@ __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sy
 //   start address >> 4 | LBO (ignored for swizzled K-major) = 1 | SBO = 1024 >> 4 | version 1 | SWIZZLE_128B
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue of one accumulator (128 rows x bn columns): the calling warp owns TMEM lanes [32q, 32q+32),
+// i.e. GEMM rows m = tile_row0 + 32q + lane.  `taddr` = TMEM address of (lane 32q, column 0 of the tile).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_epilogue_rows(const TcParams& p, uint32_t taddr, int m, int n0) {
+      // decode the GEMM row into (image, y, x) of the *unpadded* feature map
+  bool in_range = m < p.rows, interior = false;
+  int img = 0, y = 0, x = 0;
+  if (in_range) {
+    img = m / p.plane;
+    int r = m - img * p.plane;
+    if (p.halo) {
+      int yy = r / p.pitch, xx = r - yy * p.pitch;
+      y = yy - 1; x = xx - 1;
+      interior = y >= 0 && y < p.h && x >= 0 && x < p.w;
+    } else {
+      y = r / p.w; x = r - y * p.w;
+      interior = true;
+    }
+  }
+  // rows that get written: interior rows always; halo rows (as zeros) only when the output keeps the halo
+  const bool do_store = in_range && (interior || (p.out_halo && p.out_mode == 0));
+  long long out_off;
+  if (p.out_mode == 0)
+    out_off = (long long)img * p.out_sn + (long long)y * p.out_sh + (long long)x * p.out_sw;
+  else if (p.out_mode == 1)       // 2x2 transposed-conv scatter: quadrant offset added per column chunk
+    out_off = (long long)img * p.out_sn + (long long)(2 * y) * p.out_sh + (long long)(2 * x) * p.out_sw;
+  else                            // phase-split store for a following stride-2 convolution
+    out_off = (long long)((y & 1) * 2 + (x & 1)) * p.out_plane + (long long)img * p.out_sn +
+              (long long)(y >> 1) * p.out_sh + (long long)(x >> 1) * p.out_sw;
+  const __nv_bfloat16* res_row = nullptr;
+  if (p.res_mode && interior)
+    res_row = p.res + (long long)img * p.res_sn + (long long)(p.res_mode == 2 ? (y >> 1) : y) * p.res_sh +
+              (long long)(p.res_mode == 2 ? (x >> 1) : x) * p.res_sw;
+
+  for (int c0 = 0; c0 < p.bn; c0 += 16) {
+    uint32_t raw[16];
+    __syncwarp();                                       // tcgen05.ld is warp-collective (.sync.aligned)
+    tc_ld16(taddr + (uint32_t)c0, raw);
+    tc_ld_wait();
+    const int co0 = n0 + c0;
+    if (!do_store || co0 >= p.cout) continue;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int co = co0 + j;
+      float a = __uint_as_float(raw[j]);
+      if (co < p.cout) {
+        if (p.scale) a *= __ldg(p.scale + co);
+        if (p.shift) a += __ldg(p.shift + co);
+      }
+      v[j] = a;
+    }
+    if (res_row) {
+      if (p.out_vec) {
+        float r0[8], r1[8];
+        Vec8<__nv_bfloat16>::load(res_row + co0, r0);
+        Vec8<__nv_bfloat16>::load(res_row + co0 + 8, r1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[j] += r0[j]; v[8 + j] += r1[j]; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (co0 + j < p.cout) v[j] += __bfloat162float(res_row[co0 + j]);
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (!interior) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    }
+    long long off = out_off;
+    int cc = co0;
+    if (p.out_mode == 1) {                              // 2x2 transposed-conv scatter (sam.py:74-80)
+      const int cq = p.cout >> 2;
+      const int quad = co0 / cq;
+      cc = co0 - quad * cq;
+      off += (long long)(quad >> 1) * p.out_sh + (long long)(quad & 1) * p.out_sw;
+    }
+    if (p.out_f32) {
+      float* o = reinterpret_cast<float*>(p.out) + off + cc;
+      if (p.out_vec) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (co0 + j < p.cout) o[j] = v[j];
+      }
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + cc;
+      if (p.out_vec) {
+        float lo[8], hi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+        Vec8<__nv_bfloat16>::store(o, lo);
+        Vec8<__nv_bfloat16>::store(o + 8, hi);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (co0 + j < p.cout) o[j] = __float2bfloat16_rn(v[j]);
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -240,117 +360,174 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int m0 = (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.bn;
-      const int m = m0 + q * 32 + lane;
-      // decode the GEMM row into (image, y, x) of the *unpadded* feature map
-      bool in_range = m < p.rows, interior = false;
-      int img = 0, y = 0, x = 0;
-      if (in_range) {
-        img = m / p.plane;
-        int r = m - img * p.plane;
-        if (p.halo) {
-          int yy = r / p.pitch, xx = r - yy * p.pitch;
-          y = yy - 1; x = xx - 1;
-          interior = y >= 0 && y < p.h && x >= 0 && x < p.w;
-        } else {
-          y = r / p.w; x = r - y * p.w;
-          interior = true;
-        }
-      }
-      // rows that get written: interior rows always; halo rows (as zeros) only when the output keeps the halo
-      const bool do_store = in_range && (interior || (p.out_halo && p.out_mode == 0));
-      long long out_off;
-      if (p.out_mode == 0)
-        out_off = (long long)img * p.out_sn + (long long)y * p.out_sh + (long long)x * p.out_sw;
-      else if (p.out_mode == 1)       // 2x2 transposed-conv scatter: quadrant offset added per column chunk
-        out_off = (long long)img * p.out_sn + (long long)(2 * y) * p.out_sh + (long long)(2 * x) * p.out_sw;
-      else                            // phase-split store for a following stride-2 convolution
-        out_off = (long long)((y & 1) * 2 + (x & 1)) * p.out_plane + (long long)img * p.out_sn +
-                  (long long)(y >> 1) * p.out_sh + (long long)(x >> 1) * p.out_sw;
-      const __nv_bfloat16* res_row = nullptr;
-      if (p.res_mode && interior)
-        res_row = p.res + (long long)img * p.res_sn + (long long)(p.res_mode == 2 ? (y >> 1) : y) * p.res_sh +
-                  (long long)(p.res_mode == 2 ? (x >> 1) : x) * p.res_sw;
-
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(acc * TC_ACC_COLS) + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < p.bn; c0 += 16) {
-        uint32_t raw[16];
-        __syncwarp();                                       // tcgen05.ld is warp-collective (.sync.aligned)
-        tc_ld16(taddr + (uint32_t)c0, raw);
-        tc_ld_wait();
-        const int co0 = n0 + c0;
-        if (!do_store || co0 >= p.cout) continue;
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int co = co0 + j;
-          float a = __uint_as_float(raw[j]);
-          if (co < p.cout) {
-            if (p.scale) a *= __ldg(p.scale + co);
-            if (p.shift) a += __ldg(p.shift + co);
-          }
-          v[j] = a;
-        }
-        if (res_row) {
-          if (p.out_vec) {
-            float r0[8], r1[8];
-            Vec8<__nv_bfloat16>::load(res_row + co0, r0);
-            Vec8<__nv_bfloat16>::load(res_row + co0 + 8, r1);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { v[j] += r0[j]; v[8 + j] += r1[j]; }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (co0 + j < p.cout) v[j] += __bfloat162float(res_row[co0 + j]);
-          }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (!interior) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.f;
-        }
-        long long off = out_off;
-        int cc = co0;
-        if (p.out_mode == 1) {                              // 2x2 transposed-conv scatter (sam.py:74-80)
-          const int cq = p.cout >> 2;
-          const int quad = co0 / cq;
-          cc = co0 - quad * cq;
-          off += (long long)(quad >> 1) * p.out_sh + (long long)(quad & 1) * p.out_sw;
-        }
-        if (p.out_f32) {
-          float* o = reinterpret_cast<float*>(p.out) + off + cc;
-          if (p.out_vec) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (co0 + j < p.cout) o[j] = v[j];
-          }
-        } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + cc;
-          if (p.out_vec) {
-            float lo[8], hi[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
-            Vec8<__nv_bfloat16>::store(o, lo);
-            Vec8<__nv_bfloat16>::store(o + 8, hi);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (co0 + j < p.cout) o[j] = __float2bfloat16_rn(v[j]);
-          }
-        }
-      }
+      tc_epilogue_rows(p, tmem_base + (uint32_t)(acc * TC_ACC_COLS) + ((uint32_t)(q * 32) << 16), m0 + q * 32 + lane, n0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// v2: 256 GEMM rows per tile (two 128-row accumulators that share every weight tile), separate smem
+// rings for A slabs and W tiles, 8 epilogue warps.  The conv kernels are bound by L2 -> smem traffic
+// (ncu: tensor pipe 30-55 %, L2 ~7 TB/s), so this variant cuts bytes per MAC:
+//   * W tile traffic per row halves (one W box feeds 256 rows);
+//   * kx-merge (stride-1 3x3): the three taps (ky, 0..2) of a k-block read the SAME rows shifted by
+//     -1/0/+1, so ONE slab of 272 rows (two TMA boxes of 136) is loaded per (ky, source, k-block) and the
+//     MMA A-descriptor simply starts 0, 1 or 2 rows (128 B each) into it -- A traffic drops 3x.
+// Warps: 0 = TMA producer, 1 = TMEM alloc + MMA issue, 2..9 = epilogue (warps 2-5: rows 0-127, 6-9: 128-255).
+// ------------------------------------------------------------------------------------------------
+constexpr int TC2_THREADS = 320;
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_at(uint32_t smem_addr, int desc_mode) {
+  uint64_t d = umma_desc_sw128(smem_addr);
+  if (desc_mode == 1) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;      // matrix base offset
+  return d;
+}
+
+__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_half_bytes = (uint32_t)p.a_box_rows * 128u;
+  const uint32_t a_slab_bytes = 2u * a_half_bytes;
+  const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 2;
+  const uint32_t b_base = base + (uint32_t)p.sa_stages * a_slab_bytes;
+  const uint32_t bar_base = b_base + (uint32_t)p.sb_stages * b_bytes;
+  auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (p.sa_stages + s); };
+  auto bfull_bar = [&](int s) { return bar_base + 8u * (2 * p.sa_stages + s); };
+  auto bempty_bar = [&](int s) { return bar_base + 8u * (2 * p.sa_stages + p.sb_stages + s); };
+  const uint32_t tbar = bar_base + 8u * (2 * p.sa_stages + 2 * p.sb_stages);
+  auto tfull_bar = [&](int a) { return tbar + 8u * a; };
+  auto tempty_bar = [&](int a) { return tbar + 8u * (2 + a); };
+  const uint32_t tmem_slot = tbar + 8u * 4;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int groups_per_tap_row = p.kx_merge ? 3 : 1;          // W tiles consumed per A slab
+  const int ngroup_outer = p.kx_merge ? 3 : p.taps;            // ky (merged) or tap
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&p.a_map[s]);
+    tma_prefetch_desc(&p.b_map);
+    for (int s = 0; s < p.sa_stages; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
+    for (int s = 0; s < p.sb_stages; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  const int half_cols = p.acc_stages == 2 ? 128 : 256;        // TMEM columns per 128-row accumulator
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m0 = (t / p.n_tiles) * 256, n0 = (t % p.n_tiles) * p.bn;
+        for (int g = 0; g < ngroup_outer; ++g) {
+          // first row of the slab in the flat source matrix
+          const int row0 = m0 + (p.kx_merge ? p.tap_shift[g * 3 + 1] - 1 : p.tap_shift[g]);
+          int blk = 0;
+          for (int s = 0; s < p.num_src; ++s) {
+            const int nblk = (p.src_c[s] + TC_BK - 1) / TC_BK;
+            for (int cb = 0; cb < nblk; ++cb, ++blk) {
+              mbar_wait(aempty_bar(sa), pa ^ 1u);
+              const uint32_t slab = base + (uint32_t)sa * a_slab_bytes;
+              mbar_expect_tx(afull_bar(sa), a_slab_bytes);
+              tma_load_2d(slab, &p.a_map[s], afull_bar(sa), cb * TC_BK, row0);
+              tma_load_2d(slab + a_half_bytes, &p.a_map[s], afull_bar(sa), cb * TC_BK, row0 + p.a_box_rows);
+              if (++sa == p.sa_stages) { sa = 0; pa ^= 1u; }
+              for (int j = 0; j < groups_per_tap_row; ++j) {
+                const int tap = p.kx_merge ? g * 3 + j : g;
+                mbar_wait(bempty_bar(sb), pb ^ 1u);
+                mbar_expect_tx(bfull_bar(sb), b_bytes);
+                tma_load_2d(b_base + (uint32_t)sb * b_bytes, &p.b_map, bfull_bar(sb), (tap * p.nblk_total + blk) * TC_BK, n0);
+                if (++sb == p.sb_stages) { sb = 0; pb ^= 1u; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int sa = 0, sb = 0, acc = 0;
+      uint32_t pa = 0, pb = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * half_cols);
+        uint32_t accumulate = 0;
+        for (int g = 0; g < ngroup_outer; ++g) {
+          for (int s = 0; s < p.num_src; ++s) {
+            const int c = p.src_c[s];
+            const int nblk = (c + TC_BK - 1) / TC_BK;
+            for (int cb = 0; cb < nblk; ++cb) {
+              const int nk = (min(TC_BK, c - cb * TC_BK) + 15) >> 4;
+              mbar_wait(afull_bar(sa), pa);
+              const uint32_t slab = base + (uint32_t)sa * a_slab_bytes;
+              for (int j = 0; j < groups_per_tap_row; ++j) {
+                mbar_wait(bfull_bar(sb), pb);
+                tc_fence_after();
+                const uint32_t sbm = b_base + (uint32_t)sb * b_bytes;
+                const uint64_t bdesc = umma_desc_sw128(sbm);
+                // tap kx = j reads the slab j rows (128 B each) further down; rows 128.. feed the second accumulator
+                const uint32_t a0 = slab + (uint32_t)(p.kx_merge ? j : 0) * 128u;
+                const uint32_t a1 = a0 + 128u * 128u;
+                const uint64_t adesc0 = umma_desc_sw128_at(a0, p.desc_mode), adesc1 = umma_desc_sw128_at(a1, p.desc_mode);
+                for (int k = 0; k < nk; ++k) tc_mma_bf16(d0, adesc0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
+                for (int k = 0; k < nk; ++k) tc_mma_bf16(d0 + (uint32_t)half_cols, adesc1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
+                accumulate = 1;
+                tc_commit(bempty_bar(sb));
+                if (++sb == p.sb_stages) { sb = 0; pb ^= 1u; }
+              }
+              tc_commit(aempty_bar(sa));
+              if (++sa == p.sa_stages) { sa = 0; pa ^= 1u; }
+            }
+          }
+        }
+        tc_commit(tfull_bar(acc));
+        if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int q = warp & 3;
+    const int half = warp >= 6 ? 1 : 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m0 = (t / p.n_tiles) * 256, n0 = (t % p.n_tiles) * p.bn;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      tc_epilogue_rows(p, tmem_base + (uint32_t)(acc * 2 * half_cols + half * half_cols) + ((uint32_t)(q * 32) << 16),
+                       m0 + half * 128 + q * 32 + lane, n0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
@@ -474,18 +651,54 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     }
   }
   p->rows = (int)rows;
-  p->m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
   p->cout = d->cout;
   const int cout_pad = (d->cout + 15) / 16 * 16;
-  int sms = 148;
-  p->bn = pick_bn(cout_pad, p->m_tiles, sms);
+  const int sms = 148;
   if (d->out_mode == 1) {
     TC_REQUIRE((d->cout / 4) % 16 == 0, "conv_tc: deconv scatter needs cout/4 %% 16 == 0");
   }
-  p->n_tiles = (cout_pad + p->bn - 1) / p->bn;
-  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p->bn * TC_BK * 2;
-  int stages = (int)((220u * 1024u) / stage_bytes);
-  p->stages = stages > 8 ? 8 : stages;
+  p->nblk_total = 0;
+  for (int i = 0; i < d->num_src; ++i) p->nblk_total += (d->src[i].c + TC_BK - 1) / TC_BK;
+  // ---- kernel variant: 256-row tiles (v2) whenever that still fills the machine, else 128-row tiles (v1)
+  static const int env_variant = getenv("CM2_TC_VARIANT") ? atoi(getenv("CM2_TC_VARIANT")) : 0;
+  static const int env_desc = getenv("CM2_TC_DESC_MODE") ? atoi(getenv("CM2_TC_DESC_MODE")) : 0;
+  const int m_tiles256 = (int)((rows + 255) / 256);
+  const int bn2 = pick_bn(cout_pad, m_tiles256, sms);
+  bool use_v2 = m_tiles256 * (cout_pad / bn2) >= sms;
+  if (env_variant == 1) use_v2 = false;
+  if (env_variant >= 2) use_v2 = true;
+  const size_t budget = 225u * 1024u;
+  if (use_v2) {
+    p->variant = 2;
+    p->bn = bn2;
+    p->m_tiles = m_tiles256;
+    p->n_tiles = (cout_pad + p->bn - 1) / p->bn;
+    p->kx_merge = (p->taps == 9 && !phase && env_variant != 2) ? 1 : 0;
+    p->a_box_rows = p->kx_merge ? 136 : 128;
+    p->acc_stages = p->bn <= 128 ? 2 : 1;
+    p->desc_mode = env_desc;
+    const size_t a_slab = 2u * (size_t)p->a_box_rows * 128u, b_bytes = (size_t)p->bn * TC_BK * 2;
+    if (p->kx_merge) {
+      p->sa_stages = 3;
+      size_t sb = (budget - p->sa_stages * a_slab) / b_bytes;
+      p->sb_stages = (int)(sb > 9 ? 9 : sb);
+    } else {
+      size_t st = budget / (a_slab + b_bytes);
+      p->sa_stages = p->sb_stages = (int)(st > 6 ? 6 : st);
+    }
+    p->smem_bytes = (unsigned)(1024 + p->sa_stages * a_slab + p->sb_stages * b_bytes +
+                               8 * (2 * p->sa_stages + 2 * p->sb_stages + 4) + 16);
+  } else {
+    p->variant = 1;
+    p->m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
+    p->bn = pick_bn(cout_pad, p->m_tiles, sms);
+    p->n_tiles = (cout_pad + p->bn - 1) / p->bn;
+    p->a_box_rows = TC_BM;
+    const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p->bn * TC_BK * 2;
+    int stages = (int)(budget / stage_bytes);
+    p->stages = stages > 8 ? 8 : stages;
+    p->smem_bytes = (unsigned)(1024 + (size_t)p->stages * stage_bytes + 8 * (2 * p->stages + 4) + 16);
+  }
   p->scale = d->scale; p->shift = d->shift; p->relu = d->relu;
   p->out = d->out.data;
   p->out_sn = d->out.sn; p->out_sh = d->out.sh; p->out_sw = d->out.sw;
@@ -511,7 +724,7 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     // base of the flat matrix = address of padded pixel (0,0) of image 0
     const char* basep = reinterpret_cast<const char*>(d->src[i].data);
     if (halo) basep -= (size_t)(d->src[i].sh + d->src[i].sw) * 2;
-    if (!encode_2d(&p->a_map[i], basep, (uint64_t)rows * (phase ? 4 : 1), (uint64_t)d->src[i].c, TC_BM)) {
+    if (!encode_2d(&p->a_map[i], basep, (uint64_t)rows * (phase ? 4 : 1), (uint64_t)d->src[i].c, (uint32_t)p->a_box_rows)) {
       set_error("conv_tc: cuTensorMapEncodeTiled failed for source %d", i);
       return CM2_ERR_CUDA;
     }
@@ -534,12 +747,14 @@ int conv_tc_launch(const cm2_conv_desc* d, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   }
-  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.bn * TC_BK * 2;
-  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + 8 * (2 * p.stages + 4) + 16;
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sms ? tiles : sms;
-  conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
+  if (p.variant == 2)
+    conv_tc2_kernel<<<grid, TC2_THREADS, p.smem_bytes, stream>>>(p);
+  else
+    conv_tc_kernel<<<grid, TC_THREADS, p.smem_bytes, stream>>>(p);
   CM2_CHECK_LAUNCH("conv_tc");
   return CM2_OK;
 }
