@@ -63,6 +63,8 @@ struct alignas(64) TcParams {
   int acc_stages;           // 2 when bn <= 128 (2 x 2 x 128 TMEM columns), else 1
   int nblk_total;           // sum over sources of ceil(c / 64)
   int desc_mode;            // 0: base_offset field 0;  1: base_offset = (start >> 7) & 7 for unaligned starts
+  int fast_store;           // 1: epilogue transposes through shared memory and writes 64-byte row segments
+  int dbg;                  // tuning experiments (CM2_TC_DEBUG): 1 no epilogue stores, 2 no TMA loads, 4 no MMAs
   int variant;              // host only: 1 = conv_tc_kernel (128-row tiles), 2 = conv_tc2_kernel
   unsigned smem_bytes;      // host only: dynamic shared memory of the launch
 };
@@ -147,11 +149,34 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// Per-tile epilogue vectors in shared memory: the epilogue warps cooperatively copy scale/shift of the tile's
+// bn columns (1 / 0 where absent or beyond cout) and meet on a named barrier; per-element __ldg in the
+// epilogue loop showed up as the top stall (long scoreboard on every FMUL) in ncu.
+__device__ __forceinline__ void tc_stage_scale_shift(const TcParams& p, uint32_t ss_smem, int n0, int tid_e, int n_epi) {
+  for (int i = tid_e; i < p.bn; i += n_epi) {
+    const int co = n0 + i;
+    float sc = 1.f, sh = 0.f;
+    if (co < p.cout) {
+      if (p.scale) sc = __ldg(p.scale + co);
+      if (p.shift) sh = __ldg(p.shift + co);
+    }
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(ss_smem + 4u * i), "f"(sc) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(ss_smem + 1024u + 4u * i), "f"(sh) : "memory");
+  }
+  asm volatile("bar.sync 1, %0;" ::"r"(n_epi) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+constexpr uint32_t EPI_SS_BYTES = 2 * 2048;         // two tile parities x (scale[256] + shift[256])
+
 // ------------------------------------------------------------------------------------------------
 // epilogue of one accumulator (128 rows x bn columns): the calling warp owns TMEM lanes [32q, 32q+32),
 // i.e. GEMM rows m = tile_row0 + 32q + lane.  `taddr` = TMEM address of (lane 32q, column 0 of the tile).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tc_epilogue_rows(const TcParams& p, uint32_t taddr, int m, int n0) {
+__device__ __forceinline__ void tc_epilogue_rows(const TcParams& p, uint32_t taddr, int m, int n0, uint32_t ss_smem) {
       // decode the GEMM row into (image, y, x) of the *unpadded* feature map
   bool in_range = m < p.rows, interior = false;
   int img = 0, y = 0, x = 0;
@@ -168,7 +193,7 @@ __device__ __forceinline__ void tc_epilogue_rows(const TcParams& p, uint32_t tad
     }
   }
   // rows that get written: interior rows always; halo rows (as zeros) only when the output keeps the halo
-  const bool do_store = in_range && (interior || (p.out_halo && p.out_mode == 0));
+  const bool do_store = in_range && (interior || (p.out_halo && p.out_mode == 0)) && !(p.dbg & 1);
   long long out_off;
   if (p.out_mode == 0)
     out_off = (long long)img * p.out_sn + (long long)y * p.out_sh + (long long)x * p.out_sw;
@@ -191,14 +216,12 @@ __device__ __forceinline__ void tc_epilogue_rows(const TcParams& p, uint32_t tad
     if (!do_store || co0 >= p.cout) continue;
     float v[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int co = co0 + j;
-      float a = __uint_as_float(raw[j]);
-      if (co < p.cout) {
-        if (p.scale) a *= __ldg(p.scale + co);
-        if (p.shift) a += __ldg(p.shift + co);
-      }
-      v[j] = a;
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const float4 sc = lds_f4(ss_smem + 4u * (uint32_t)(c0 + 4 * j4)), sh = lds_f4(ss_smem + 1024u + 4u * (uint32_t)(c0 + 4 * j4));
+      v[4 * j4 + 0] = fmaf(__uint_as_float(raw[4 * j4 + 0]), sc.x, sh.x);
+      v[4 * j4 + 1] = fmaf(__uint_as_float(raw[4 * j4 + 1]), sc.y, sh.y);
+      v[4 * j4 + 2] = fmaf(__uint_as_float(raw[4 * j4 + 2]), sc.z, sh.z);
+      v[4 * j4 + 3] = fmaf(__uint_as_float(raw[4 * j4 + 3]), sc.w, sh.w);
     }
     if (res_row) {
       if (p.out_vec) {
@@ -258,6 +281,126 @@ __device__ __forceinline__ void tc_epilogue_rows(const TcParams& p, uint32_t tad
 }
 
 // ------------------------------------------------------------------------------------------------
+// Coalescing epilogue.  In the TMEM register layout a thread owns one output ROW, so direct stores make
+// every warp instruction touch 32 different rows 16 bytes at a time (measured: the stores alone cost as
+// much as all MMAs of a 3x3 256->256 layer).  Here each pass moves a [32 rows x 64 bytes] block through
+// a per-warp staging buffer (row pitch 80 B: conflict-free 16-byte st.shared) and writes it back as
+// 8 rows x 64 contiguous bytes per instruction.  Used when the output is vectorisable and there is no
+// residual; everything else takes tc_epilogue_rows.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t EPI_PITCH = 80;                  // bytes per staged row (64 payload + 16 pad)
+constexpr uint32_t EPI_WARP_BYTES = 32 * EPI_PITCH;
+
+__device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, uint32_t taddr, int m, int n0,
+                                                        uint32_t stage_smem, int lane, uint32_t ss_smem) {
+  bool in_range = m < p.rows, interior = false;
+  int img = 0, y = 0, x = 0;
+  if (in_range) {
+    img = m / p.plane;
+    int r = m - img * p.plane;
+    if (p.halo) {
+      int yy = r / p.pitch, xx = r - yy * p.pitch;
+      y = yy - 1; x = xx - 1;
+      interior = y >= 0 && y < p.h && x >= 0 && x < p.w;
+    } else {
+      y = r / p.w; x = r - y * p.w;
+      interior = true;
+    }
+  }
+  const bool do_store = in_range && (interior || (p.out_halo && p.out_mode == 0)) && !(p.dbg & 1);
+  long long out_off;
+  if (p.out_mode == 0)
+    out_off = (long long)img * p.out_sn + (long long)y * p.out_sh + (long long)x * p.out_sw;
+  else if (p.out_mode == 1)
+    out_off = (long long)img * p.out_sn + (long long)(2 * y) * p.out_sh + (long long)(2 * x) * p.out_sw;
+  else
+    out_off = (long long)((y & 1) * 2 + (x & 1)) * p.out_plane + (long long)img * p.out_sn +
+              (long long)(y >> 1) * p.out_sh + (long long)(x >> 1) * p.out_sw;
+  const unsigned store_mask = __ballot_sync(0xffffffffu, do_store);      // rows of this warp that get written
+  const int cpp = p.out_f32 ? 16 : 32;               // channels per pass = 64 bytes per row
+  const uint32_t my_row = stage_smem + (uint32_t)lane * EPI_PITCH;
+  for (int c0 = 0; c0 < p.bn; c0 += cpp) {
+    const int co0 = n0 + c0;
+    float v[32];
+    {
+      uint32_t raw[16];
+      __syncwarp();
+      tc_ld16(taddr + (uint32_t)c0, raw);
+      if (!p.out_f32 && c0 + 16 < p.bn) {
+        uint32_t raw2[16];
+        tc_ld16(taddr + (uint32_t)(c0 + 16), raw2);
+        tc_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[16 + j] = __uint_as_float(raw2[j]);
+      } else {
+        tc_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[16 + j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+    }
+    if (co0 >= p.cout) continue;                     // warp-uniform
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      if (4 * j4 < cpp && c0 + 4 * j4 < p.bn) {
+        const float4 sc = lds_f4(ss_smem + 4u * (uint32_t)(c0 + 4 * j4)), sh = lds_f4(ss_smem + 1024u + 4u * (uint32_t)(c0 + 4 * j4));
+        float a0 = fmaf(v[4 * j4 + 0], sc.x, sh.x), a1 = fmaf(v[4 * j4 + 1], sc.y, sh.y);
+        float a2 = fmaf(v[4 * j4 + 2], sc.z, sh.z), a3 = fmaf(v[4 * j4 + 3], sc.w, sh.w);
+        if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+        v[4 * j4 + 0] = interior ? a0 : 0.f; v[4 * j4 + 1] = interior ? a1 : 0.f;
+        v[4 * j4 + 2] = interior ? a2 : 0.f; v[4 * j4 + 3] = interior ? a3 : 0.f;
+      }
+    }
+    // ---- stage this thread's 64 bytes
+    if (p.out_f32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + 16u * j), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                     "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+          w[i] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + 16u * j), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                     "r"(w[3]) : "memory");
+      }
+    }
+    __syncwarp();
+    // ---- write back: 4 instructions x (8 rows x 64 bytes)
+    long long extra = 0;
+    int cc = co0;
+    if (p.out_mode == 1) {
+      const int cq = p.cout >> 2;
+      const int quad = co0 / cq;
+      cc = co0 - quad * cq;
+      extra = (long long)(quad >> 1) * p.out_sh + (long long)(quad & 1) * p.out_sw;
+    }
+    const int elems16 = p.out_f32 ? 4 : 8;           // elements per 16-byte piece
+    // 16-byte pieces of this pass that belong to this tile (bn need not be a multiple of the pass width) and to cout
+    const int valid_pieces = min(4, (min(p.bn - c0, p.cout - co0) + elems16 - 1) / elems16);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int row = it * 8 + (lane >> 2), piece = lane & 3;
+      const long long roff = __shfl_sync(0xffffffffu, out_off, row);
+      uint4 val;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                   : "r"(stage_smem + (uint32_t)row * EPI_PITCH + 16u * piece) : "memory");
+      if (((store_mask >> row) & 1u) && piece < valid_pieces) {
+        char* dst = reinterpret_cast<char*>(p.out) + ((roff + extra + cc) * (p.out_f32 ? 4 : 2)) + 16 * piece;
+        *reinterpret_cast<uint4*>(dst) = val;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
@@ -272,6 +415,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+  const uint32_t epi_base = (tmem_slot + 16u + 15u) & ~15u;       // 4 x EPI_WARP_BYTES of staging
+  const uint32_t ss_base = epi_base + 4u * EPI_WARP_BYTES;         // EPI_SS_BYTES of scale/shift
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -308,9 +453,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int cb = 0; cb < nblk; ++cb, ++kb) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
               const uint32_t sa = base + (uint32_t)stage * stage_bytes;
-              mbar_expect_tx(full_bar(stage), TC_A_BYTES + b_bytes);
-              tma_load_2d(sa, &p.a_map[s], full_bar(stage), cb * TC_BK, m0 + shift);
-              tma_load_2d(sa + TC_A_BYTES, &p.b_map, full_bar(stage), kb * TC_BK, n0);
+              if (p.dbg & 2) {
+                mbar_arrive(full_bar(stage));
+              } else {
+                mbar_expect_tx(full_bar(stage), TC_A_BYTES + b_bytes);
+                tma_load_2d(sa, &p.a_map[s], full_bar(stage), cb * TC_BK, m0 + shift);
+                tma_load_2d(sa + TC_A_BYTES, &p.b_map, full_bar(stage), kb * TC_BK, n0);
+              }
               if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
           }
@@ -339,7 +488,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               tc_fence_after();
               const uint32_t sa = base + (uint32_t)stage * stage_bytes;
               const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + TC_A_BYTES);
-              for (int k = 0; k < nk; ++k) {
+              for (int k = 0; k < nk && !(p.dbg & 4); ++k) {
                 // +32 bytes per K=16 step inside the 128B swizzle row (start-address field is in 16B units)
                 tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate);
                 accumulate = 1;
@@ -358,11 +507,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    uint32_t parity = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, parity ^= 1u) {
       const int m0 = (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.bn;
+      const uint32_t ss = ss_base + parity * 2048u;
+      tc_stage_scale_shift(p, ss, n0, (int)threadIdx.x - 64, 128);      // overlaps the MMAs of this tile
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      tc_epilogue_rows(p, tmem_base + (uint32_t)(acc * TC_ACC_COLS) + ((uint32_t)(q * 32) << 16), m0 + q * 32 + lane, n0);
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * TC_ACC_COLS) + ((uint32_t)(q * 32) << 16);
+      if (p.fast_store)
+        tc_epilogue_rows_staged(p, taddr, m0 + q * 32 + lane, n0, epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES, lane, ss);
+      else
+        tc_epilogue_rows(p, taddr, m0 + q * 32 + lane, n0, ss);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -412,6 +568,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
   auto tfull_bar = [&](int a) { return tbar + 8u * a; };
   auto tempty_bar = [&](int a) { return tbar + 8u * (2 + a); };
   const uint32_t tmem_slot = tbar + 8u * 4;
+  const uint32_t epi_base = (tmem_slot + 16u + 15u) & ~15u;       // 8 x EPI_WARP_BYTES of staging
+  const uint32_t ss_base = epi_base + 8u * EPI_WARP_BYTES;         // EPI_SS_BYTES of scale/shift
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -453,15 +611,23 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
             for (int cb = 0; cb < nblk; ++cb, ++blk) {
               mbar_wait(aempty_bar(sa), pa ^ 1u);
               const uint32_t slab = base + (uint32_t)sa * a_slab_bytes;
-              mbar_expect_tx(afull_bar(sa), a_slab_bytes);
-              tma_load_2d(slab, &p.a_map[s], afull_bar(sa), cb * TC_BK, row0);
-              tma_load_2d(slab + a_half_bytes, &p.a_map[s], afull_bar(sa), cb * TC_BK, row0 + p.a_box_rows);
+              if (p.dbg & 2) {
+                mbar_arrive(afull_bar(sa));
+              } else {
+                mbar_expect_tx(afull_bar(sa), a_slab_bytes);
+                tma_load_2d(slab, &p.a_map[s], afull_bar(sa), cb * TC_BK, row0);
+                tma_load_2d(slab + a_half_bytes, &p.a_map[s], afull_bar(sa), cb * TC_BK, row0 + p.a_box_rows);
+              }
               if (++sa == p.sa_stages) { sa = 0; pa ^= 1u; }
               for (int j = 0; j < groups_per_tap_row; ++j) {
                 const int tap = p.kx_merge ? g * 3 + j : g;
                 mbar_wait(bempty_bar(sb), pb ^ 1u);
-                mbar_expect_tx(bfull_bar(sb), b_bytes);
-                tma_load_2d(b_base + (uint32_t)sb * b_bytes, &p.b_map, bfull_bar(sb), (tap * p.nblk_total + blk) * TC_BK, n0);
+                if (p.dbg & 2) {
+                  mbar_arrive(bfull_bar(sb));
+                } else {
+                  mbar_expect_tx(bfull_bar(sb), b_bytes);
+                  tma_load_2d(b_base + (uint32_t)sb * b_bytes, &p.b_map, bfull_bar(sb), (tap * p.nblk_total + blk) * TC_BK, n0);
+                }
                 if (++sb == p.sb_stages) { sb = 0; pb ^= 1u; }
               }
             }
@@ -497,8 +663,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                 const uint32_t a0 = slab + (uint32_t)(p.kx_merge ? j : 0) * 128u;
                 const uint32_t a1 = a0 + 128u * 128u;
                 const uint64_t adesc0 = umma_desc_sw128_at(a0, p.desc_mode), adesc1 = umma_desc_sw128_at(a1, p.desc_mode);
-                for (int k = 0; k < nk; ++k) tc_mma_bf16(d0, adesc0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
-                for (int k = 0; k < nk; ++k) tc_mma_bf16(d0 + (uint32_t)half_cols, adesc1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
+                if (!(p.dbg & 4)) {
+                  for (int k = 0; k < nk; ++k) tc_mma_bf16(d0, adesc0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
+                  for (int k = 0; k < nk; ++k) tc_mma_bf16(d0 + (uint32_t)half_cols, adesc1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
+                }
                 accumulate = 1;
                 tc_commit(bempty_bar(sb));
                 if (++sb == p.sb_stages) { sb = 0; pb ^= 1u; }
@@ -518,12 +686,18 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
     const int half = warp >= 6 ? 1 : 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    uint32_t parity = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, parity ^= 1u) {
       const int m0 = (t / p.n_tiles) * 256, n0 = (t % p.n_tiles) * p.bn;
+      const uint32_t ss = ss_base + parity * 2048u;
+      tc_stage_scale_shift(p, ss, n0, (int)threadIdx.x - 64, 256);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      tc_epilogue_rows(p, tmem_base + (uint32_t)(acc * 2 * half_cols + half * half_cols) + ((uint32_t)(q * 32) << 16),
-                       m0 + half * 128 + q * 32 + lane, n0);
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * 2 * half_cols + half * half_cols) + ((uint32_t)(q * 32) << 16);
+      if (p.fast_store)
+        tc_epilogue_rows_staged(p, taddr, m0 + half * 128 + q * 32 + lane, n0, epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES, lane, ss);
+      else
+        tc_epilogue_rows(p, taddr, m0 + half * 128 + q * 32 + lane, n0, ss);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -662,12 +836,22 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   // ---- kernel variant: 256-row tiles (v2) whenever that still fills the machine, else 128-row tiles (v1)
   static const int env_variant = getenv("CM2_TC_VARIANT") ? atoi(getenv("CM2_TC_VARIANT")) : 0;
   static const int env_desc = getenv("CM2_TC_DESC_MODE") ? atoi(getenv("CM2_TC_DESC_MODE")) : 0;
+  static const int env_dbg = getenv("CM2_TC_DEBUG") ? atoi(getenv("CM2_TC_DEBUG")) : 0;
+  p->dbg = env_dbg;
   const int m_tiles256 = (int)((rows + 255) / 256);
   const int bn2 = pick_bn(cout_pad, m_tiles256, sms);
-  bool use_v2 = m_tiles256 * (cout_pad / bn2) >= sms;
+  // Measured (tools/conv_bench.py, B200): 256-row tiles win when the kx-merged slab applies and both accumulators
+  // stay double-buffered (bn <= 128), and for short-K 1x1 layers whose epilogue dominates (8 epilogue warps);
+  // with bn > 128 the single accumulator stage exposes the epilogue and 128-row tiles are as fast or faster.
+  const bool merge_ok = p->taps == 9 && !phase;
+  int k_total = 0;
+  for (int i = 0; i < d->num_src; ++i) k_total += d->src[i].c;
+  bool use_v2 = m_tiles256 * (cout_pad / bn2) >= sms && ((merge_ok && bn2 <= 128) || (p->taps == 1 && k_total <= 512));
   if (env_variant == 1) use_v2 = false;
   if (env_variant >= 2) use_v2 = true;
-  const size_t budget = 225u * 1024u;
+  const size_t tail_v1 = 8 * (2 * 8 + 4) + 48 + 4 * EPI_WARP_BYTES + EPI_SS_BYTES;
+  const size_t tail_v2 = 8 * (2 * 6 + 2 * 9 + 4) + 48 + 8 * EPI_WARP_BYTES + EPI_SS_BYTES;
+  const size_t smem_max = 227u * 1024u - 1024u;          // minus the 1 KB alignment slack
   if (use_v2) {
     p->variant = 2;
     p->bn = bn2;
@@ -680,14 +864,13 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     const size_t a_slab = 2u * (size_t)p->a_box_rows * 128u, b_bytes = (size_t)p->bn * TC_BK * 2;
     if (p->kx_merge) {
       p->sa_stages = 3;
-      size_t sb = (budget - p->sa_stages * a_slab) / b_bytes;
+      size_t sb = (smem_max - tail_v2 - p->sa_stages * a_slab) / b_bytes;
       p->sb_stages = (int)(sb > 9 ? 9 : sb);
     } else {
-      size_t st = budget / (a_slab + b_bytes);
+      size_t st = (smem_max - tail_v2) / (a_slab + b_bytes);
       p->sa_stages = p->sb_stages = (int)(st > 6 ? 6 : st);
     }
-    p->smem_bytes = (unsigned)(1024 + p->sa_stages * a_slab + p->sb_stages * b_bytes +
-                               8 * (2 * p->sa_stages + 2 * p->sb_stages + 4) + 16);
+    p->smem_bytes = (unsigned)(1024 + p->sa_stages * a_slab + p->sb_stages * b_bytes + tail_v2);
   } else {
     p->variant = 1;
     p->m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
@@ -695,9 +878,9 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     p->n_tiles = (cout_pad + p->bn - 1) / p->bn;
     p->a_box_rows = TC_BM;
     const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p->bn * TC_BK * 2;
-    int stages = (int)(budget / stage_bytes);
+    int stages = (int)((smem_max - tail_v1) / stage_bytes);
     p->stages = stages > 8 ? 8 : stages;
-    p->smem_bytes = (unsigned)(1024 + (size_t)p->stages * stage_bytes + 8 * (2 * p->stages + 4) + 16);
+    p->smem_bytes = (unsigned)(1024 + (size_t)p->stages * stage_bytes + tail_v1);
   }
   p->scale = d->scale; p->shift = d->shift; p->relu = d->relu;
   p->out = d->out.data;
@@ -718,6 +901,8 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
                         (reinterpret_cast<uintptr_t>(d->residual.data) & 15) == 0))
       p->out_vec = 0;
   }
+  static const int env_store = getenv("CM2_TC_FAST_STORE") ? atoi(getenv("CM2_TC_FAST_STORE")) : 1;
+  p->fast_store = (env_store && p->out_vec && !p->res_mode && (d->out_mode != 1 || (d->cout / 4) % 32 == 0)) ? 1 : 0;
 #undef TC_REQUIRE
   if (!maps) return CM2_OK;
   for (int i = 0; i < d->num_src; ++i) {
