@@ -134,20 +134,9 @@ def calibrate_on_gpu(model, cfg, inputs):
 
 
 def compact_results(results, r_cap):
-    """Fixed-size result record per image (SURVEY 5 'Distributed communication backend')."""
-    rec = []
-    for r in results:
-        inst = r["instances"]
-        k = len(inst)
-        t = torch.zeros((r_cap, 8), dtype=torch.float32, device=inst.scores.device)
-        t[:k, :4] = inst.pred_boxes.tensor
-        t[:k, 4] = inst.scores
-        t[:k, 5] = inst.pred_classes.float()
-        if inst.has("mask_scores"):
-            t[:k, 6] = inst.mask_scores
-        t[:, 7] = float(k)
-        rec.append(t)
-    return torch.stack(rec)
+    """Fixed-size result record per image (centermask2_b200/parallel.py; SURVEY 5 'Distributed communication backend')."""
+    from centermask2_b200 import parallel
+    return parallel.pack_records([r["instances"] for r in results], r_cap)
 
 
 def device_step(model, cfg, dev_images, sizes_out):
@@ -319,9 +308,9 @@ def main():
     d2h = rec.numel() * rec.element_size()
 
     # ---- final result gather (the only collective; not on the hot path)
-    if world > 1:
-        allrec = [torch.empty_like(rec, device="cuda") for _ in range(world)]
-        dist.all_gather(allrec, rec.cuda())
+    from centermask2_b200 import parallel
+    allrec = parallel.gather_records(rec.cuda(), args.batch * world)       # [batch*world, r_cap, 8] on every rank
+    assert allrec.shape[0] == args.batch * world
 
     # ---- roofline of the dominant kernel family (convolutions)
     conv_ms, conv_launches = conv_time_per_step(model, cfg, dev_images, max(2, min(args.steps, 5)))
