@@ -130,7 +130,7 @@ def test_bf16_tensor_core_model_matches_bf16_rounding_oracle():
     by several percent (the same is true of the oracle when it rounds at the same places), so the reference
     here is ``restate.bf16_sim()``: the fp32 restatement with weights and stored activations rounded to bf16
     exactly where the engine rounds.  What remains is accumulation order plus the rare rounding flip.
-    Gates: feature maps within 1% relative L2 of the bf16-rounding oracle; head outputs within 2% of their
+    Gates: feature maps within 2% relative L2 of the bf16-rounding oracle; head outputs within 2% of their
     range; >= 90% of the oracle's kept detections (class + originating location) are kept.  The raw deviation
     against the pure-fp32 oracle is printed for the record."""
     runtime.reset()
@@ -152,7 +152,7 @@ def test_bf16_tensor_core_model_matches_bf16_rounding_oracle():
             rel = ((got - v).norm() / v.norm()).item()
             raw = ((got - gold["features"][k]).norm() / gold["features"][k].norm()).item()
             print("bf16 {}: rel L2 vs bf16-rounding oracle {:.4f}, vs fp32 reference {:.4f}".format(k, rel, raw))
-            assert rel <= 0.01, (k, rel)
+            assert rel <= 0.02, (k, rel)
         fcos = model.proposal_generator
         e2, P = fcos._pack()
         head = e2.run_fcos_head([feats[f] for f in fcos.in_features], P)
