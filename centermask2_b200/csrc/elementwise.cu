@@ -68,27 +68,37 @@ __global__ void maxpool3s2_kernel(View<const T> in, View<T> out) {
 // ---------------------------------------------------------------------------------------------
 constexpr int ESE_PIX_PER_CHUNK = 256;
 
-// stage 1: grid (chunks, n); each thread owns 8 channels and walks the chunk's pixels.
+// stage 1: grid (chunks, n), 256 threads.  Thread t owns the 8-channel column cv = t % c8 on pixel lane
+// pl = t / c8 (lanes = 256 / c8); the lanes are combined through shared memory in a fixed order, so the
+// result is deterministic.  (The first version walked 256 pixels serially per thread and ran at ~1/6 of HBM.)
 template <typename T>
-__global__ void ese_pool_partial_kernel(View<const T> x, int chunks, float* __restrict__ ws) {
+__global__ void __launch_bounds__(256) ese_pool_partial_kernel(View<const T> x, int chunks, float* __restrict__ ws) {
+  __shared__ float sm[8 * 1024];                      // [lanes][c], lanes * c <= 8192 (c <= 1024)
   int chunk = blockIdx.x, b = blockIdx.y;
-  int c8 = x.c >> 3;
+  int c = x.c, c8 = c >> 3;
   int hw = x.h * x.w;
+  int lanes = blockDim.x / c8;
+  if (lanes > 8) lanes = 8;
+  int cv = threadIdx.x % c8, pl = threadIdx.x / c8;
   int p0 = chunk * ESE_PIX_PER_CHUNK;
   int p1 = min(p0 + ESE_PIX_PER_CHUNK, hw);
-  for (int cv = threadIdx.x; cv < c8; cv += blockDim.x) {
+  if (pl < lanes) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int y = p0 / x.w, xx = p0 - y * x.w;
-    for (int p = p0; p < p1; ++p) {
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      int y = p / x.w, xx = p - y * x.w;
       float v[8];
       Vec8<T>::load(x.at(b, y, xx) + cv * 8, v);
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] += v[k];
-      if (++xx == x.w) { xx = 0; ++y; }
     }
-    float* o = ws + ((size_t)b * chunks + chunk) * x.c + cv * 8;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = acc[k];
+    for (int k = 0; k < 8; ++k) sm[pl * c + cv * 8 + k] = acc[k];
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += sm[l * c + ch];
+    ws[((size_t)b * chunks + chunk) * c + ch] = s;
   }
 }
 
@@ -429,17 +439,17 @@ extern "C" int32_t cm2_ese_pool_chunks(int32_t hw) { return ceil_div(hw, ESE_PIX
 extern "C" int cm2_ese_pool(const cm2_act* x, int32_t dtype, float* workspace, float* pooled, void* stream) {
   CM2_CHECK_ARG(x && x->data && workspace && pooled, "ese_pool: null pointer");
   CM2_CHECK_DTYPE(dtype, "ese_pool");
-  CM2_CHECK_ARG(vec8_ok(*x, elem_bytes(dtype)) && x->h > 0 && x->w > 0, "ese_pool: bad shape %dx%d c=%d", x->h, x->w,
-                x->c);
+  CM2_CHECK_ARG(vec8_ok(*x, elem_bytes(dtype)) && x->h > 0 && x->w > 0 && x->c <= 1024 && x->c / 8 <= 256,
+                "ese_pool: bad shape %dx%d c=%d (need c %% 8 == 0, c <= 1024)", x->h, x->w, x->c);
   if (x->n == 0) return CM2_OK;
   int hw = x->h * x->w;
   int chunks = cm2_ese_pool_chunks(hw);
   cudaStream_t s = (cudaStream_t)stream;
   dim3 g1(chunks, x->n);
   if (dtype == CM2_F32)
-    ese_pool_partial_kernel<float><<<g1, 128, 0, s>>>(make_view<const float>(*x), chunks, workspace);
+    ese_pool_partial_kernel<float><<<g1, 256, 0, s>>>(make_view<const float>(*x), chunks, workspace);
   else
-    ese_pool_partial_kernel<__nv_bfloat16><<<g1, 128, 0, s>>>(make_view<const __nv_bfloat16>(*x), chunks, workspace);
+    ese_pool_partial_kernel<__nv_bfloat16><<<g1, 256, 0, s>>>(make_view<const __nv_bfloat16>(*x), chunks, workspace);
   CM2_CHECK_LAUNCH("ese_pool_partial");
   dim3 g2(ceil_div(x->c, 128), x->n);
   ese_pool_final_kernel<<<g2, 128, 0, s>>>(workspace, chunks, x->c, 1.0f / (float)hw, pooled);

@@ -50,22 +50,72 @@ class GeneralizedRCNN(nn.Module):
 
     @torch.no_grad()
     def inference(self, batched_inputs, detected_instances=None, do_postprocess=True):
-        """list[{"image": [3,H,W] BGR (float or uint8), "height", "width"}] -> list[{"instances": Instances}]."""
+        """list[{"image": [3,H,W] BGR (float or uint8), "height", "width"}] -> list[{"instances": Instances}].
+
+        The whole batch runs on fixed-size device buffers (no host sync) up to and including the mask
+        paste-back; one D2H copy of the detection counts / box validity then cuts out the per-image
+        ``Instances`` (slices, no per-field gathers unless a box became empty after clipping)."""
         eng = runtime.engine_for(self.cfg)
         images = [b["image"].to(eng.device, non_blocking=True) for b in batched_inputs]
         x, sizes = eng.preprocess(images, self.backbone.size_divisibility)
         feats = self.backbone.forward_fmap(x)
-        if detected_instances is None:
-            det = self.proposal_generator.detect([feats[f] for f in self.proposal_generator.in_features])
-            results = instances_from_det(det, sizes)
-        else:
+        roi = self.roi_heads
+        if detected_instances is not None:
             results = [i.to(eng.device) for i in detected_instances]
-        results = self.roi_heads.forward_with_given_boxes({k: v.nchw() for k, v in feats.items()}, results)
-        if not do_postprocess:
-            return results
+            results = roi.forward_with_given_boxes({k: v.nchw() for k, v in feats.items()}, results)
+            if not do_postprocess:
+                return results
+            return [{"instances": self.detector_postprocess(inst, b.get("height", sz[0]), b.get("width", sz[1]))}
+                    for inst, b, sz in zip(results, batched_inputs, sizes)]
+        fcos = self.proposal_generator
+        det = fcos.detect([feats[f] for f in fcos.in_features])
+        n, r_cap = det["boxes"].shape[0], det["boxes"].shape[1]
+        probs = mask_scores = None
+        if roi.mask_on:
+            probs, mask_scores = roi.run([feats[f] for f in roi.in_features], det, sizes)
+        # one snapshot of the small per-detection tensors (the engine reuses its buffers on the next call)
+        scores, classes, locs = det["scores"].clone(), det["classes"].clone(), det["locations"].clone()
+        mscores = mask_scores.reshape(n, r_cap).clone() if mask_scores is not None else None
+        from .. import lib
+        if do_postprocess:
+            out_sizes = [(b.get("height", sz[0]), b.get("width", sz[1])) for b, sz in zip(batched_inputs, sizes)]
+            boxes = torch.empty_like(det["boxes"])
+            valid = torch.empty((n, r_cap), dtype=torch.uint8, device=eng.device)
+            masks = []
+            for i, ((oh, ow), sz) in enumerate(zip(out_sizes, sizes)):
+                lib.scale_clip_boxes(det["boxes"][i], boxes[i], valid[i], r_cap, ow / sz[1], oh / sz[0], float(ow), float(oh))
+                if probs is not None:
+                    m = torch.empty((r_cap, oh, ow), dtype=torch.bool, device=eng.device)      # kernel writes 0/1 bytes
+                    lib.paste_masks(probs[i * r_cap:(i + 1) * r_cap], boxes[i], valid[i], m, r_cap, probs.shape[-1], oh, ow, 0.5)
+                    masks.append(m)
+            valid_h = valid.cpu()
+        else:
+            boxes = det["boxes"].clone()
+            pm = probs.clone() if probs is not None else None
+        counts = det["count"].tolist()
+        over = bool((det["cand_count"] > det["cand_cap"]).any().item())
+        if over:
+            raise RuntimeError("FCOS candidate buffer overflow (> {} candidates above threshold in one level)".format(det["cand_cap"]))
+        total = sum(counts)
         out = []
-        for inst, b, size in zip(results, batched_inputs, sizes):
-            out.append({"instances": self.detector_postprocess(inst, b.get("height", size[0]), b.get("width", size[1]))})
+        for i, k in enumerate(counts):
+            sel = slice(0, k)
+            if do_postprocess:
+                v = valid_h[i, :k]
+                if not bool(v.all()):
+                    sel = torch.nonzero(v).squeeze(1).to(eng.device)
+                inst = Instances(tuple(out_sizes[i]))
+            else:
+                inst = Instances(tuple(sizes[i]))
+            inst.pred_boxes = Boxes(boxes[i, sel])
+            inst.scores = scores[i, sel]
+            inst.pred_classes = classes[i, sel]
+            inst.locations = locs[i, sel]
+            if probs is not None:
+                inst.pred_masks = masks[i][sel] if do_postprocess else pm[i * r_cap:(i + 1) * r_cap][sel]
+                if mscores is not None and total > 0:                    # center_heads.py:511-517
+                    inst.mask_scores = mscores[i, sel]
+            out.append({"instances": inst} if do_postprocess else inst)
         return out
 
     def preprocess_image(self, batched_inputs):
