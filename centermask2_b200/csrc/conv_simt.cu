@@ -248,6 +248,11 @@ extern "C" int cm2_conv2d(const cm2_conv_desc* d, void* stream) {
   CM2_CHECK_ARG(d != nullptr, "conv2d: null descriptor");
   CM2_CHECK_ARG(d->num_src >= 1 && d->num_src <= CM2_MAX_SRC, "conv2d: num_src %d out of range", d->num_src);
   CM2_CHECK_ARG(d->kh > 0 && d->kw > 0 && d->stride > 0 && d->pad >= 0 && d->cout > 0, "conv2d: bad kernel geometry");
+  if (d->num_seg > 0) {                      // segmented tensors: validated and run by the TC engine only
+    CM2_CHECK_ARG(d->num_seg <= CM2_MAX_SEG && d->engine == CM2_ENGINE_TC && d->out_mode == 0 && !d->residual.data &&
+                  !d->src_phase && d->weight && d->out.data, "conv2d: bad segmented descriptor");
+    return conv_tc_launch(d, (cudaStream_t)stream);
+  }
   const cm2_act& s0 = d->src[0];
   CM2_CHECK_ARG(s0.n >= 0 && s0.h > 0 && s0.w > 0, "conv2d: bad extents");
   for (int i = 0; i < d->num_src; ++i) {

@@ -63,6 +63,10 @@ struct alignas(64) TcParams {
   int acc_stages;           // 2 when bn <= 128 (2 x 2 x 128 TMEM columns), else 1
   int nblk_total;           // sum over sources of ceil(c / 64)
   int desc_mode;            // 0: base_offset field 0;  1: base_offset = (start >> 7) & 7 for unaligned starts
+  int phase;                // 1: sources are stride-2 phase planes (tap_shift holds plane + line offsets)
+  int num_seg;              // > 0: segmented halo tensor (several maps of different extent in one flat buffer)
+  int seg_row0[CM2_MAX_SEG], seg_rows[CM2_MAX_SEG], seg_pitch[CM2_MAX_SEG], seg_plane[CM2_MAX_SEG];
+  int seg_h[CM2_MAX_SEG], seg_w[CM2_MAX_SEG];
   int fast_store;           // 1: epilogue transposes through shared memory and writes 64-byte row segments
   int dbg;                  // tuning experiments (CM2_TC_DEBUG): 1 no epilogue stores, 2 no TMA loads, 4 no MMAs
   int variant;              // host only: 1 = conv_tc_kernel (128-row tiles), 2 = conv_tc2_kernel
@@ -149,6 +153,28 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// Geometry of the map a tile belongs to (segments start at multiples of 256 rows, so a tile never straddles two).
+struct TileGeom { int row0, rows, pitch, plane, h, w; };
+__device__ __forceinline__ TileGeom tc_geom(const TcParams& p, int m0) {
+  TileGeom g;
+  if (p.num_seg == 0) {
+    g.row0 = 0; g.rows = p.rows; g.pitch = p.pitch; g.plane = p.plane; g.h = p.h; g.w = p.w;
+  } else {
+    int s = 0;
+#pragma unroll
+    for (int i = 1; i < CM2_MAX_SEG; ++i)
+      if (i < p.num_seg && m0 >= p.seg_row0[i]) s = i;
+    g.row0 = p.seg_row0[s]; g.rows = p.seg_rows[s]; g.pitch = p.seg_pitch[s]; g.plane = p.seg_plane[s];
+    g.h = p.seg_h[s]; g.w = p.seg_w[s];
+  }
+  return g;
+}
+__device__ __forceinline__ int tc_tap_shift(const TcParams& p, int tap, int pitch) {
+  if (p.taps == 1) return 0;
+  if (p.phase) return p.tap_shift[tap];
+  return (tap / 3 - 1) * pitch + (tap % 3 - 1);
+}
+
 // Per-tile epilogue vectors in shared memory: the epilogue warps cooperatively copy scale/shift of the tile's
 // bn columns (1 / 0 where absent or beyond cout) and meet on a named barrier; per-element __ldg in the
 // epilogue loop showed up as the top stall (long scoreboard on every FMUL) in ncu.
@@ -176,26 +202,30 @@ constexpr uint32_t EPI_SS_BYTES = 2 * 2048;         // two tile parities x (scal
 // epilogue of one accumulator (128 rows x bn columns): the calling warp owns TMEM lanes [32q, 32q+32),
 // i.e. GEMM rows m = tile_row0 + 32q + lane.  `taddr` = TMEM address of (lane 32q, column 0 of the tile).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tc_epilogue_rows(const TcParams& p, uint32_t taddr, int m, int n0, uint32_t ss_smem) {
+__device__ __forceinline__ void tc_epilogue_rows(const TcParams& p, const TileGeom& g, uint32_t taddr, int m, int n0,
+                                                 uint32_t ss_smem) {
       // decode the GEMM row into (image, y, x) of the *unpadded* feature map
-  bool in_range = m < p.rows, interior = false;
+  const int mr = m - g.row0;
+  bool in_range = mr >= 0 && mr < g.rows, interior = false;
   int img = 0, y = 0, x = 0;
   if (in_range) {
-    img = m / p.plane;
-    int r = m - img * p.plane;
+    img = mr / g.plane;
+    int r = mr - img * g.plane;
     if (p.halo) {
-      int yy = r / p.pitch, xx = r - yy * p.pitch;
+      int yy = r / g.pitch, xx = r - yy * g.pitch;
       y = yy - 1; x = xx - 1;
-      interior = y >= 0 && y < p.h && x >= 0 && x < p.w;
+      interior = y >= 0 && y < g.h && x >= 0 && x < g.w;
     } else {
-      y = r / p.w; x = r - y * p.w;
+      y = r / g.w; x = r - y * g.w;
       interior = true;
     }
   }
   // rows that get written: interior rows always; halo rows (as zeros) only when the output keeps the halo
   const bool do_store = in_range && (interior || (p.out_halo && p.out_mode == 0)) && !(p.dbg & 1);
   long long out_off;
-  if (p.out_mode == 0)
+  if (p.num_seg)
+    out_off = (long long)m * p.out_sw;                 // segmented output: same flat row, pitch = cout
+  else if (p.out_mode == 0)
     out_off = (long long)img * p.out_sn + (long long)y * p.out_sh + (long long)x * p.out_sw;
   else if (p.out_mode == 1)       // 2x2 transposed-conv scatter: quadrant offset added per column chunk
     out_off = (long long)img * p.out_sn + (long long)(2 * y) * p.out_sh + (long long)(2 * x) * p.out_sw;
@@ -291,25 +321,28 @@ __device__ __forceinline__ void tc_epilogue_rows(const TcParams& p, uint32_t tad
 constexpr uint32_t EPI_PITCH = 80;                  // bytes per staged row (64 payload + 16 pad)
 constexpr uint32_t EPI_WARP_BYTES = 32 * EPI_PITCH;
 
-__device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, uint32_t taddr, int m, int n0,
+__device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const TileGeom& g, uint32_t taddr, int m, int n0,
                                                         uint32_t stage_smem, int lane, uint32_t ss_smem) {
-  bool in_range = m < p.rows, interior = false;
+  const int mr = m - g.row0;
+  bool in_range = mr >= 0 && mr < g.rows, interior = false;
   int img = 0, y = 0, x = 0;
   if (in_range) {
-    img = m / p.plane;
-    int r = m - img * p.plane;
+    img = mr / g.plane;
+    int r = mr - img * g.plane;
     if (p.halo) {
-      int yy = r / p.pitch, xx = r - yy * p.pitch;
+      int yy = r / g.pitch, xx = r - yy * g.pitch;
       y = yy - 1; x = xx - 1;
-      interior = y >= 0 && y < p.h && x >= 0 && x < p.w;
+      interior = y >= 0 && y < g.h && x >= 0 && x < g.w;
     } else {
-      y = r / p.w; x = r - y * p.w;
+      y = r / g.w; x = r - y * g.w;
       interior = true;
     }
   }
   const bool do_store = in_range && (interior || (p.out_halo && p.out_mode == 0)) && !(p.dbg & 1);
   long long out_off;
-  if (p.out_mode == 0)
+  if (p.num_seg)
+    out_off = (long long)m * p.out_sw;                 // segmented output: same flat row, pitch = cout
+  else if (p.out_mode == 0)
     out_off = (long long)img * p.out_sn + (long long)y * p.out_sh + (long long)x * p.out_sw;
   else if (p.out_mode == 1)
     out_off = (long long)img * p.out_sn + (long long)(2 * y) * p.out_sh + (long long)(2 * x) * p.out_sw;
@@ -447,7 +480,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int m0 = (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.bn;
         int kb = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
-          const int shift = p.tap_shift[tap];
+          const int shift = tc_tap_shift(p, tap, p.num_seg ? tc_geom(p, m0).pitch : p.pitch);
           for (int s = 0; s < p.num_src; ++s) {
             const int nblk = (p.src_c[s] + TC_BK - 1) / TC_BK;
             for (int cb = 0; cb < nblk; ++cb, ++kb) {
@@ -515,10 +548,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * TC_ACC_COLS) + ((uint32_t)(q * 32) << 16);
+      const TileGeom g = tc_geom(p, m0);
       if (p.fast_store)
-        tc_epilogue_rows_staged(p, taddr, m0 + q * 32 + lane, n0, epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES, lane, ss);
+        tc_epilogue_rows_staged(p, g, taddr, m0 + q * 32 + lane, n0, epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES, lane, ss);
       else
-        tc_epilogue_rows(p, taddr, m0 + q * 32 + lane, n0, ss);
+        tc_epilogue_rows(p, g, taddr, m0 + q * 32 + lane, n0, ss);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -604,7 +638,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
         const int m0 = (t / p.n_tiles) * 256, n0 = (t % p.n_tiles) * p.bn;
         for (int g = 0; g < ngroup_outer; ++g) {
           // first row of the slab in the flat source matrix
-          const int row0 = m0 + (p.kx_merge ? p.tap_shift[g * 3 + 1] - 1 : p.tap_shift[g]);
+          const int pitch = p.num_seg ? tc_geom(p, m0).pitch : p.pitch;
+          const int row0 = m0 + (p.kx_merge ? tc_tap_shift(p, g * 3 + 1, pitch) - 1 : tc_tap_shift(p, g, pitch));
           int blk = 0;
           for (int s = 0; s < p.num_src; ++s) {
             const int nblk = (p.src_c[s] + TC_BK - 1) / TC_BK;
@@ -694,10 +729,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * 2 * half_cols + half * half_cols) + ((uint32_t)(q * 32) << 16);
+      const TileGeom tg = tc_geom(p, m0);
       if (p.fast_store)
-        tc_epilogue_rows_staged(p, taddr, m0 + half * 128 + q * 32 + lane, n0, epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES, lane, ss);
+        tc_epilogue_rows_staged(p, tg, taddr, m0 + half * 128 + q * 32 + lane, n0, epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES, lane, ss);
       else
-        tc_epilogue_rows(p, taddr, m0 + half * 128 + q * 32 + lane, n0, ss);
+        tc_epilogue_rows(p, tg, taddr, m0 + half * 128 + q * 32 + lane, n0, ss);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -795,22 +831,41 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
                "conv_tc: only stride-1 1x1/p0 and 3x3/p1, or 3x3/s2/p1 on phase-split sources (got k%d s%d p%d)", d->kh,
                d->stride, d->pad);
   TC_REQUIRE(!d->in_relu && !d->chan_sum, "conv_tc: in_relu / chan_sum not supported");
-  const bool halo = is_halo_view(s0);
+  const bool seg = d->num_seg > 0;
+  if (seg)
+    TC_REQUIRE(d->num_seg <= CM2_MAX_SEG && !phase && d->out_mode == 0 && !d->residual.data,
+               "conv_tc: segmented tensors need stride 1, out_mode 0, no residual");
+  const bool halo = seg || is_halo_view(s0);
   TC_REQUIRE(halo || (d->kh == 1 && is_dense_view(s0)), "conv_tc: source 0 is neither a halo-1 view nor (for 1x1) dense");
   for (int i = 0; i < d->num_src; ++i) {
     const cm2_act& s = d->src[i];
     TC_REQUIRE(s.c % 16 == 0 && (reinterpret_cast<uintptr_t>(s.data) & 15) == 0, "conv_tc: source %d channels %d / alignment", i, s.c);
-    TC_REQUIRE(halo ? is_halo_view(s) : is_dense_view(s), "conv_tc: source %d geometry differs from source 0", i);
+    if (!seg) TC_REQUIRE(halo ? is_halo_view(s) : is_dense_view(s), "conv_tc: source %d geometry differs from source 0", i);
   }
   memset(p, 0, sizeof(*p));
   p->num_src = d->num_src;
   for (int i = 0; i < d->num_src; ++i) p->src_c[i] = d->src[i].c;
   p->taps = d->kh * d->kw;
   p->halo = halo ? 1 : 0;
+  p->phase = phase ? 1 : 0;
   p->h = s0.h; p->w = s0.w;
   p->pitch = halo ? s0.w + 2 : 0;
   p->plane = halo ? (s0.h + 2) * (s0.w + 2) : s0.h * s0.w;
   long long rows = (long long)s0.n * p->plane;
+  if (seg) {
+    p->num_seg = d->num_seg;
+    rows = 0;
+    for (int i = 0; i < d->num_seg; ++i) {
+      const cm2_seg& g = d->seg[i];
+      TC_REQUIRE(g.row0 % 256 == 0 && g.row0 >= rows && g.n > 0 && g.h > 0 && g.w > 0, "conv_tc: segment %d badly placed", i);
+      const long long srows = (long long)g.n * (g.h + 2) * (g.w + 2);
+      TC_REQUIRE(g.row0 + srows < (1ll << 31) - 4096, "conv_tc: segment %d out of range", i);
+      p->seg_row0[i] = (int)g.row0; p->seg_rows[i] = (int)srows; p->seg_pitch[i] = g.w + 2;
+      p->seg_plane[i] = (g.h + 2) * (g.w + 2); p->seg_h[i] = g.h; p->seg_w[i] = g.w;
+      rows = g.row0 + srows;
+    }
+    p->h = p->w = p->pitch = p->plane = 0;
+  }
   TC_REQUIRE(rows > 0 && rows < (1ll << 31) - 4096, "conv_tc: %lld rows out of range", rows);
   TC_REQUIRE(!phase || halo, "conv_tc: phase-split sources must be halo views");
   TC_REQUIRE(!phase || rows * 4 < (1ll << 31) - 4096, "conv_tc: phase-split source too large");
@@ -893,6 +948,13 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   const int oeb = p->out_f32 ? 4 : 2;
   p->out_vec = (oc % 16 == 0 && d->out.sn % 8 == 0 && d->out.sh % 8 == 0 && d->out.sw % 8 == 0 &&
                 (reinterpret_cast<uintptr_t>(d->out.data) % (size_t)(8 * oeb)) == 0) ? 1 : 0;
+  if (seg) {
+    TC_REQUIRE(d->out.c == d->cout && d->cout % 16 == 0 && (reinterpret_cast<uintptr_t>(d->out.data) % (size_t)(8 * oeb)) == 0,
+               "conv_tc: segmented output needs out.c == cout, cout %% 16 == 0");
+    p->out_sw = d->cout; p->out_sn = p->out_sh = 0;
+    p->out_halo = 1;
+    p->out_vec = 1;
+  }
   if (d->residual.data) {
     p->res = reinterpret_cast<const __nv_bfloat16*>(d->residual.data);
     p->res_sn = d->residual.sn; p->res_sh = d->residual.sh; p->res_sw = d->residual.sw;
@@ -908,7 +970,7 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   for (int i = 0; i < d->num_src; ++i) {
     // base of the flat matrix = address of padded pixel (0,0) of image 0
     const char* basep = reinterpret_cast<const char*>(d->src[i].data);
-    if (halo) basep -= (size_t)(d->src[i].sh + d->src[i].sw) * 2;
+    if (halo && !seg) basep -= (size_t)(d->src[i].sh + d->src[i].sw) * 2;
     if (!encode_2d(&p->a_map[i], basep, (uint64_t)rows * (phase ? 4 : 1), (uint64_t)d->src[i].c, (uint32_t)p->a_box_rows)) {
       set_error("conv_tc: cuTensorMapEncodeTiled failed for source %d", i);
       return CM2_ERR_CUDA;

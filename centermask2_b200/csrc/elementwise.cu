@@ -330,6 +330,144 @@ __global__ void preprocess_im2col_kernel(const InT* __restrict__ img, int h, int
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// GroupNorm on a segmented halo tensor (all FPN levels of an FCOS tower in one launch set).
+// ---------------------------------------------------------------------------------------------
+struct GnSegs {
+  int num;
+  long long row0[CM2_MAX_SEG];
+  int n[CM2_MAX_SEG], h[CM2_MAX_SEG], w[CM2_MAX_SEG];
+  int chunk_prefix[CM2_MAX_SEG + 1];      // chunks (GN_PIX_PER_CHUNK interior pixels of one image) before segment s
+  int img_prefix[CM2_MAX_SEG + 1];        // images before segment s
+  long long vec_prefix[CM2_MAX_SEG + 1];  // 8-channel vectors of interior pixels before segment s
+};
+
+template <typename T>
+__device__ __forceinline__ T* gn_seg_pixel(T* base, const GnSegs& g, int s, int b, int y, int x, int c) {
+  long long row = g.row0[s] + (long long)b * (g.h[s] + 2) * (g.w[s] + 2) + (long long)(y + 1) * (g.w[s] + 2) + (x + 1);
+  return base + row * c;
+}
+
+template <typename T>
+__global__ void gn_seg_partial_kernel(const T* __restrict__ x, int c, GnSegs g, float* __restrict__ ws) {
+  __shared__ float sm[2048 * 2];
+  int s = 0;
+  for (int i = 1; i < g.num; ++i)
+    if ((int)blockIdx.x >= g.chunk_prefix[i]) s = i;
+  const int hw = g.h[s] * g.w[s], w = g.w[s];
+  const int cpi = (hw + GN_PIX_PER_CHUNK - 1) / GN_PIX_PER_CHUNK;
+  const int local = blockIdx.x - g.chunk_prefix[s];
+  const int b = local / cpi, chunk = local - b * cpi;
+  const int c8 = c >> 3;
+  const int lanes = blockDim.x / c8;
+  const int cv = threadIdx.x % c8, pl = threadIdx.x / c8;
+  const int p0 = chunk * GN_PIX_PER_CHUNK, p1 = min(p0 + GN_PIX_PER_CHUNK, hw);
+  if (pl < lanes) {
+    float sa[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      int y = p / w, xx = p - y * w;
+      float v[8];
+      Vec8<T>::load(gn_seg_pixel(x, g, s, b, y, xx, c) + cv * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { sa[k] += v[k]; q[k] = fmaf(v[k], v[k], q[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sm[((size_t)pl * c + cv * 8 + k) * 2 + 0] = sa[k];
+      sm[((size_t)pl * c + cv * 8 + k) * 2 + 1] = q[k];
+    }
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float a = 0.f, q = 0.f;
+    for (int l = 0; l < lanes; ++l) { a += sm[((size_t)l * c + ch) * 2]; q += sm[((size_t)l * c + ch) * 2 + 1]; }
+    ws[((size_t)blockIdx.x * c + ch) * 2 + 0] = a;
+    ws[((size_t)blockIdx.x * c + ch) * 2 + 1] = q;
+  }
+}
+
+// grid (groups, total images): one warp combines the chunk partials of one (segment, image, group)
+__global__ void gn_seg_final_kernel(const float* __restrict__ ws, int c, int groups, GnSegs g, float eps,
+                                    float* __restrict__ stats) {
+  const int gi = blockIdx.y, grp = blockIdx.x;
+  int s = 0;
+  for (int i = 1; i < g.num; ++i)
+    if (gi >= g.img_prefix[i]) s = i;
+  const int b = gi - g.img_prefix[s];
+  const int hw = g.h[s] * g.w[s];
+  const int cpi = (hw + GN_PIX_PER_CHUNK - 1) / GN_PIX_PER_CHUNK;
+  const int chunk0 = g.chunk_prefix[s] + b * cpi;
+  const int cpg = c / groups;
+  const int lane = threadIdx.x;
+  double sum = 0.0, sq = 0.0;
+  const int total = cpi * cpg;
+  for (int i = lane; i < total; i += 32) {
+    int chunk = i / cpg, ch = grp * cpg + (i - chunk * cpg);
+    const float* q = ws + ((size_t)(chunk0 + chunk) * c + ch) * 2;
+    sum += (double)q[0];
+    sq += (double)q[1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  if (lane == 0) {
+    double cnt = (double)hw * cpg;
+    double mean = sum / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0) var = 0;
+    stats[((size_t)gi * groups + grp) * 2 + 0] = (float)mean;
+    stats[((size_t)gi * groups + grp) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+template <typename T>
+__global__ void gn_seg_apply_kernel(T* __restrict__ x, int c, int groups, GnSegs g, const float* __restrict__ stats,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, int relu) {
+  const int c8 = c >> 3, cpg = c / groups;
+  const long long total8 = g.vec_prefix[g.num];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    int s = 0;
+    for (int k = 1; k < g.num; ++k)
+      if (i >= g.vec_prefix[k]) s = k;
+    long long li = i - g.vec_prefix[s];
+    int cv = (int)(li % c8);
+    long long pix = li / c8;
+    int xx = (int)(pix % g.w[s]);
+    long long t = pix / g.w[s];
+    int y = (int)(t % g.h[s]);
+    int b = (int)(t / g.h[s]);
+    const int gi = g.img_prefix[s] + b;
+    float v[8];
+    T* ptr = gn_seg_pixel(x, g, s, b, y, xx, c) + cv * 8;
+    Vec8<T>::load(ptr, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int grp = (cv * 8 + k) / cpg;
+      float mean = stats[((size_t)gi * groups + grp) * 2], rstd = stats[((size_t)gi * groups + grp) * 2 + 1];
+      float yv = (v[k] - mean) * rstd * __ldg(gamma + cv * 8 + k) + __ldg(beta + cv * 8 + k);
+      v[k] = relu ? fmaxf(yv, 0.f) : yv;
+    }
+    Vec8<T>::store(ptr, v);
+  }
+}
+
+static bool gn_make_segs(int32_t num_seg, const cm2_seg* seg, int c, GnSegs* g) {
+  if (num_seg < 1 || num_seg > CM2_MAX_SEG) return false;
+  g->num = num_seg;
+  g->chunk_prefix[0] = 0; g->img_prefix[0] = 0; g->vec_prefix[0] = 0;
+  for (int i = 0; i < num_seg; ++i) {
+    if (seg[i].n <= 0 || seg[i].h <= 0 || seg[i].w <= 0) return false;
+    g->row0[i] = seg[i].row0; g->n[i] = seg[i].n; g->h[i] = seg[i].h; g->w[i] = seg[i].w;
+    int cpi = ceil_div(seg[i].h * seg[i].w, GN_PIX_PER_CHUNK);
+    g->chunk_prefix[i + 1] = g->chunk_prefix[i] + cpi * seg[i].n;
+    g->img_prefix[i + 1] = g->img_prefix[i] + seg[i].n;
+    g->vec_prefix[i + 1] = g->vec_prefix[i] + (long long)seg[i].n * seg[i].h * seg[i].w * (c / 8);
+  }
+  return true;
+}
+
 int grid_for(int64_t work, int block) {
   int64_t g = ceil_div64(work, block);
   int64_t cap = 148 * 16;
@@ -526,6 +664,43 @@ extern "C" int cm2_groupnorm_relu(const cm2_act* x, int32_t dtype, int32_t group
     gn_apply_kernel<__nv_bfloat16><<<grid_for(total8, 256), 256, 0, s>>>(make_view<__nv_bfloat16>(*x), groups, stats,
                                                                         gamma, beta, relu);
   CM2_CHECK_LAUNCH("gn_apply");
+  return CM2_OK;
+}
+
+extern "C" int64_t cm2_gn_seg_workspace_floats(int32_t num_seg, const cm2_seg* seg, int32_t c, int32_t groups) {
+  GnSegs g;
+  if (!seg || !gn_make_segs(num_seg, seg, c, &g)) return 0;
+  return (int64_t)2 * g.chunk_prefix[num_seg] * c + (int64_t)2 * g.img_prefix[num_seg] * groups;
+}
+
+extern "C" int cm2_groupnorm_relu_seg(void* x, int32_t dtype, int32_t c, int32_t num_seg, const cm2_seg* seg,
+                                      int32_t groups, const float* gamma, const float* beta, float eps, int32_t relu,
+                                      float* workspace, void* stream) {
+  CM2_CHECK_ARG(x && seg && gamma && beta && workspace, "groupnorm_seg: null pointer");
+  CM2_CHECK_DTYPE(dtype, "groupnorm_seg");
+  CM2_CHECK_ARG(groups > 0 && c % groups == 0 && c % 8 == 0 && c / 8 <= 256 && 256 % (c / 8) == 0 &&
+                (reinterpret_cast<uintptr_t>(x) % (size_t)(8 * elem_bytes(dtype))) == 0,
+                "groupnorm_seg: unsupported c=%d groups=%d", c, groups);
+  GnSegs g;
+  CM2_CHECK_ARG(gn_make_segs(num_seg, seg, c, &g), "groupnorm_seg: bad segment table");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* partial = workspace;
+  float* stats = workspace + (size_t)2 * g.chunk_prefix[num_seg] * c;
+  const int chunks = g.chunk_prefix[num_seg], imgs = g.img_prefix[num_seg];
+  if (dtype == CM2_F32)
+    gn_seg_partial_kernel<float><<<chunks, 256, 0, s>>>((const float*)x, c, g, partial);
+  else
+    gn_seg_partial_kernel<__nv_bfloat16><<<chunks, 256, 0, s>>>((const __nv_bfloat16*)x, c, g, partial);
+  CM2_CHECK_LAUNCH("gn_seg_partial");
+  gn_seg_final_kernel<<<dim3(groups, imgs), 32, 0, s>>>(partial, c, groups, g, eps, stats);
+  CM2_CHECK_LAUNCH("gn_seg_final");
+  const long long total8 = g.vec_prefix[num_seg];
+  if (dtype == CM2_F32)
+    gn_seg_apply_kernel<float><<<grid_for(total8, 256), 256, 0, s>>>((float*)x, c, groups, g, stats, gamma, beta, relu);
+  else
+    gn_seg_apply_kernel<__nv_bfloat16><<<grid_for(total8, 256), 256, 0, s>>>((__nv_bfloat16*)x, c, groups, g, stats, gamma,
+                                                                          beta, relu);
+  CM2_CHECK_LAUNCH("gn_seg_apply");
   return CM2_OK;
 }
 

@@ -13,7 +13,7 @@ namespace cm2 {
 // ---------------------------------------------------------------------------------------------
 // decode: one warp per location; lanes stride over classes so the logits row is read coalesced.
 // ---------------------------------------------------------------------------------------------
-__global__ void fcos_decode_kernel(View<const float> logits, View<const float> regctr, int stride, float thresh,
+__global__ void fcos_decode_kernel(View<const float> logits, View<const float> regctr, int stride, float reg_scale, float thresh,
                                    int thresh_with_ctr, int level, int num_levels, int cap, cm2_cand_buffers cand) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -46,10 +46,10 @@ __global__ void fcos_decode_kernel(View<const float> logits, View<const float> r
       if (is_cand) {
         int slot = base + __popc(m & ((1u << lane) - 1));
         if (slot < cap) {
-          float l = fmaxf(__ldg(rrow + 0), 0.f) * (float)stride;
-          float t = fmaxf(__ldg(rrow + 1), 0.f) * (float)stride;
-          float r = fmaxf(__ldg(rrow + 2), 0.f) * (float)stride;
-          float b = fmaxf(__ldg(rrow + 3), 0.f) * (float)stride;
+          float l = fmaxf(__ldg(rrow + 0) * reg_scale, 0.f) * (float)stride;
+          float t = fmaxf(__ldg(rrow + 1) * reg_scale, 0.f) * (float)stride;
+          float r = fmaxf(__ldg(rrow + 2) * reg_scale, 0.f) * (float)stride;
+          float b = fmaxf(__ldg(rrow + 3) * reg_scale, 0.f) * (float)stride;
           float px = (float)(px_ * stride + stride / 2);
           float py = (float)(py_ * stride + stride / 2);
           size_t o = (size_t)seg * cap + slot;
@@ -268,7 +268,7 @@ static SelectWs carve_ws(void* workspace, int n, int num_levels, int pre) {
 
 using namespace cm2;
 
-extern "C" int cm2_fcos_decode(const cm2_act* logits, const cm2_act* regctr, int32_t stride, float thresh,
+extern "C" int cm2_fcos_decode(const cm2_act* logits, const cm2_act* regctr, int32_t stride, float reg_scale, float thresh,
                                int32_t thresh_with_ctr, int32_t level, int32_t num_levels, int32_t cap,
                                const cm2_cand_buffers* cand, void* stream) {
   CM2_CHECK_ARG(logits && regctr && logits->data && regctr->data && cand && cand->boxes && cand->score && cand->cls &&
@@ -283,7 +283,7 @@ extern "C" int cm2_fcos_decode(const cm2_act* logits, const cm2_act* regctr, int
   int64_t blocks = ceil_div64(total * 32, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   fcos_decode_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(make_view<const float>(*logits),
-                                                                   make_view<const float>(*regctr), stride, thresh,
+                                                                   make_view<const float>(*regctr), stride, reg_scale, thresh,
                                                                    thresh_with_ctr, level, num_levels, cap, *cand);
   CM2_CHECK_LAUNCH("fcos_decode");
   return CM2_OK;

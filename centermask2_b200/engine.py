@@ -86,6 +86,34 @@ class PhaseMap(object):
         return self.buf.shape[4]
 
 
+class SegMap(object):
+    """Several halo feature maps of different extent stored back to back in one flat ``[rows, c]`` buffer
+    (``include/cm2.h``: ``cm2_seg``).  Used for the FPN levels the shared-weight FCOS towers run on, so that one
+    convolution / GroupNorm launch covers all levels.  Every level is also reachable as an ordinary ``FMap``."""
+
+    ALIGN = 256
+
+    def __init__(self, shapes, c, dtype, device, alloc=None):
+        """shapes: list of (n, h, w)."""
+        self.segs, row = [], 0
+        for n, h, w in shapes:
+            self.segs.append((row, n, h, w))
+            row += n * (h + 2) * (w + 2)
+            row = (row + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.rows, self.c = max(row, self.ALIGN), c
+        self.flat = (alloc or (lambda shape: torch.zeros(shape, dtype=dtype, device=device)))((self.rows, c))
+
+    def level(self, i):
+        row0, n, h, w = self.segs[i]
+        return FMap(self.flat[row0:row0 + n * (h + 2) * (w + 2)].view(n, h + 2, w + 2, self.c), 1)
+
+    def like(self, c, dtype, alloc):
+        out = SegMap.__new__(SegMap)
+        out.segs, out.rows, out.c = self.segs, self.rows, c
+        out.flat = alloc((self.rows, c))
+        return out
+
+
 def as_fmap(t, dtype, device):
     """Accept what a detectron2 caller hands over: one of our own tensors (zero copy) or any NCHW
     tensor (copied once into a halo buffer)."""
@@ -164,6 +192,20 @@ class Engine(object):
             return out
         assert chan_sum is None, "chan_sum requires the tensor-core engine"
         lib.conv2d(views, w.w_simt, out.view, w.cout, w.k, w.stride, w.pad, engine=lib.ENGINE_SIMT, **kw)
+        return out
+
+    def segmap(self, name, shapes, c, dtype=None):
+        dt = dtype or self.dtype
+        return SegMap(shapes, c, dt, self.device, alloc=lambda shape: self.buffer(name, shape, dt))
+
+    def conv_seg(self, name, x, w, out_dtype=None):
+        """One stride-1 convolution over all maps of a SegMap (TC engine); returns a SegMap of the same geometry."""
+        dt = out_dtype or self.dtype
+        cout_pad = (w.cout + 15) // 16 * 16
+        assert cout_pad == w.cout, "segmented conv needs cout % 16 == 0"
+        out = x.like(w.cout, dt, lambda shape: self.buffer(name, shape, dt))
+        lib.conv2d([x.flat], w.w_tc, out.flat, w.cout, w.k, w.stride, w.pad, scale=w.scale, shift=w.shift, relu=w.relu,
+                   engine=lib.ENGINE_TC, segs=x.segs)
         return out
 
     # =============================================================================================
@@ -259,20 +301,38 @@ class Engine(object):
         # FPN top-down [d2] (constructed at vovnet.py:547-554)
         res = {}
         prev = None
-        for f in reversed(list(cfg.MODEL.FPN.IN_FEATURES)):
+        in_feats = list(cfg.MODEL.FPN.IN_FEATURES)
+        names = ["p{}".format(P["fpn"][f][0]) for f in in_feats] + ["p{}".format(P["fpn"][in_feats[-1]][0] + 1 + i)
+                                                                    for i in range(len(P["top"]))]
+        pyramid = None
+        if self.tc:
+            # all pyramid levels live in one segmented buffer so that the FCOS towers run as single launches
+            shapes = [(stage_out[f].n, stage_out[f].h, stage_out[f].w) for f in in_feats]
+            hh, ww = shapes[-1][1], shapes[-1][2]
+            for _ in P["top"]:
+                hh, ww = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
+                shapes.append((shapes[0][0], hh, ww))
+            pyramid = self.segmap("pyramid", shapes, cfg.MODEL.FPN.OUT_CHANNELS)
+        slot = {nme: i for i, nme in enumerate(names)}
+        for f in reversed(in_feats):
             lvl, lat, outc = P["fpn"][f]
             prev = self.conv("fpn_inner{}".format(lvl), [stage_out[f]], lat, residual=prev, res_mode=2 if prev is not None else 0)
-            res["p{}".format(lvl)] = self.conv("p{}".format(lvl), [prev], outc)
+            nme = "p{}".format(lvl)
+            res[nme] = self.conv(nme, [prev], outc, out=pyramid.level(slot[nme]) if pyramid is not None else None)
         # LastLevelP6P7, fpn.py:32-35 (P7 = conv(relu(P6)))
-        top = res["p5"]
+        top = res[names[len(in_feats) - 1]]
         for i, w in enumerate(P["top"]):
+            nme = names[len(in_feats) + i]
             if self.tc:
-                src = self.phase_split("p{}_phase".format(5 + i), top, relu=(i == 1))
-                top = self.conv("p{}".format(6 + i), [src], w)
+                src = self.phase_split(nme + "_src_phase", top, relu=(i == 1))
+                top = self.conv(nme, [src], w, out=pyramid.level(slot[nme]))
             else:
-                top = self.conv("p{}".format(6 + i), [top], w, in_relu=(i == 1))
-            res["p{}".format(6 + i)] = top
-        return {k: res[k] for k in sorted(res)}
+                top = self.conv(nme, [top], w, in_relu=(i == 1))
+            res[nme] = top
+        out = {k: res[k] for k in sorted(res)}
+        if pyramid is not None:
+            self._pyramid = (pyramid, [out[k] for k in names])
+        return out
 
     # =============================================================================================
     # FCOS head + post-process
@@ -303,17 +363,22 @@ class Engine(object):
         wc = sd[prefix + "fcos_head.ctrness.weight"].detach().float()
         bb = sd[prefix + "fcos_head.bbox_pred.bias"].detach().float()
         bc = sd[prefix + "fcos_head.ctrness.bias"].detach().float()
-        P["regctr"] = []
-        for l in range(len(cfg.MODEL.FCOS.FPN_STRIDES)):
-            s = sd[prefix + "fcos_head.scales.{}.scale".format(l)].detach().float().reshape(()) if cfg.MODEL.FCOS.USE_SCALE \
-                else torch.tensor(1.0)
-            scale = torch.cat([s.expand(4), torch.ones(1)])
-            shift = torch.cat([bb * s, bc])
-            P["regctr"].append(packing.ConvW(torch.cat([wb, wc], 0), [fc], 1, 1, scale, shift, False, dt, dev, tc))
+        # 16 output columns: (l, t, r, b, ctr, 11 x zero) -- keeps the vectorised epilogue / segmented path
+        w16 = torch.zeros((16,) + tuple(wb.shape[1:]))
+        w16[:4], w16[4:5] = wb, wc
+        b16 = torch.zeros(16)
+        b16[:4], b16[4:5] = bb, bc
+        P["regctr"] = packing.ConvW(w16, [fc], 1, 1, None, b16, False, dt, dev, tc)
+        P["reg_scale"] = [float(sd[prefix + "fcos_head.scales.{}.scale".format(l)].detach().float().reshape(()))
+                          if cfg.MODEL.FCOS.USE_SCALE else 1.0 for l in range(len(cfg.MODEL.FCOS.FPN_STRIDES))]
         return P
 
     def run_fcos_head(self, feats, P):
         """feats: list of FMap (p3..p7).  Returns per level (logits f32 FMap [N,H,W,ncls], regctr f32 FMap [N,H,W,5])."""
+        pyr = getattr(self, "_pyramid", None)
+        if self.tc and pyr is not None and len(pyr[1]) == len(feats) and all(a is b for a, b in zip(pyr[1], feats)) \
+                and P["cls"].cout % 16 == 0:
+            return self._run_fcos_head_seg(pyr[0], P)
         out = []
         for l, f in enumerate(feats):
             def tower(x, units, tag):
@@ -328,11 +393,27 @@ class Engine(object):
             ct = tower(x, P["towers"]["cls"], "cls")
             bt = tower(x, P["towers"]["bbox"], "bbox")
             logits = self.conv("fcos_logits_l{}".format(l), [ct], P["cls"], out_dtype=torch.float32, out_halo=0)
-            regctr = self.conv("fcos_regctr_l{}".format(l), [bt], P["regctr"][l], out_dtype=torch.float32, out_halo=0)
+            regctr = self.conv("fcos_regctr_l{}".format(l), [bt], P["regctr"], out_dtype=torch.float32, out_halo=0)
             out.append((logits, regctr))
         return out
 
-    def run_fcos_post(self, head_out, cand_cap=None):
+    def _run_fcos_head_seg(self, pyramid, P):
+        """All pyramid levels per launch: the towers' weights are shared across levels (fcos.py:227-238)."""
+        def tower(x, units, tag):
+            for i, (conv, gn) in enumerate(units):
+                x = self.conv_seg("fcos_{}{}_seg".format(tag, i), x, conv)
+                if gn is not None:
+                    wsp = self.buffer("fcos_gnws_seg", (lib.gn_seg_workspace_floats(x.segs, x.c, 32),), torch.float32, zero=False)
+                    lib.groupnorm_relu_seg(x.flat, x.segs, 32, gn[0], gn[1], 1e-5, True, wsp)
+            return x
+        x = tower(pyramid, P["towers"]["share"], "share")
+        ct = tower(x, P["towers"]["cls"], "cls")
+        bt = tower(x, P["towers"]["bbox"], "bbox")
+        logits = self.conv_seg("fcos_logits_seg", ct, P["cls"], out_dtype=torch.float32)
+        regctr = self.conv_seg("fcos_regctr_seg", bt, P["regctr"], out_dtype=torch.float32)
+        return [(logits.level(l), regctr.level(l)) for l in range(len(pyramid.segs))]
+
+    def run_fcos_post(self, head_out, cand_cap=None, reg_scale=None):
         """fcos_outputs.py:372-495 on device.  Returns fixed-size detection buffers (dict of tensors):
         boxes [N,R,4], scores [N,R], classes [N,R] (int64), locations [N,R,2], count [N] (int32),
         cand_count [N,L] (int32; > cand_cap means overflow)."""
@@ -351,7 +432,8 @@ class Engine(object):
         cand = lib.cand_buffers(cb["boxes"], cb["score"], cb["cls"], cb["flat"], cb["count"])
         strides = list(cfg.MODEL.FCOS.FPN_STRIDES)
         for l, (logits, regctr) in enumerate(head_out):
-            lib.fcos_decode(logits.view, regctr.view, strides[l], float(cfg.MODEL.FCOS.INFERENCE_TH_TEST),
+            lib.fcos_decode(logits.view, regctr.view, strides[l], 1.0 if reg_scale is None else float(reg_scale[l]),
+                            float(cfg.MODEL.FCOS.INFERENCE_TH_TEST),
                             bool(cfg.MODEL.FCOS.THRESH_WITH_CTR), l, L, cap, cand)
         det = dict(boxes=B("det_boxes", (n, post, 4), torch.float32, False), scores=B("det_scores", (n, post), torch.float32, False),
                    classes=B("det_classes", (n, post), torch.int64, False), locations=B("det_locs", (n, post, 2), torch.float32, False),

@@ -24,6 +24,14 @@ class Act(C.Structure):
                 ("sn", C.c_int64), ("sh", C.c_int64), ("sw", C.c_int64)]
 
 
+MAX_SEG = 8
+
+
+class Seg(C.Structure):
+    """cm2_seg: one map of a segmented halo tensor."""
+    _fields_ = [("row0", C.c_int64), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("reserved", C.c_int32)]
+
+
 class ConvDesc(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("out_dtype", C.c_int32), ("engine", C.c_int32), ("num_src", C.c_int32),
                 ("src", Act * MAX_SRC),
@@ -31,7 +39,8 @@ class ConvDesc(C.Structure):
                 ("weight", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("relu", C.c_int32), ("in_relu", C.c_int32),
                 ("residual", Act), ("res_mode", C.c_int32), ("out_mode", C.c_int32),
-                ("out", Act), ("chan_sum", C.c_void_p), ("src_phase", C.c_int32)]
+                ("out", Act), ("chan_sum", C.c_void_p), ("src_phase", C.c_int32), ("num_seg", C.c_int32),
+                ("seg", Seg * MAX_SEG)]
 
 
 class CandBuffers(C.Structure):
@@ -64,8 +73,10 @@ SYMBOLS = {
     "cm2_ese_apply": (_I, [_AP, _P, _AP, _AP, _I, _P]),
     "cm2_gn_workspace_floats": (_L, [_I, _I, _I, _I]),
     "cm2_groupnorm_relu": (_I, [_AP, _I, _I, _P, _P, _F, _I, _P, _P]),
+    "cm2_gn_seg_workspace_floats": (_L, [_I, C.POINTER(Seg), _I, _I]),
+    "cm2_groupnorm_relu_seg": (_I, [_P, _I, _I, _I, C.POINTER(Seg), _I, _P, _P, _F, _I, _P, _P]),
     "cm2_relu": (_I, [_AP, _AP, _I, _P]),
-    "cm2_fcos_decode": (_I, [_AP, _AP, _I, _F, _I, _I, _I, _I, C.POINTER(CandBuffers), _P]),
+    "cm2_fcos_decode": (_I, [_AP, _AP, _I, _F, _F, _I, _I, _I, _I, C.POINTER(CandBuffers), _P]),
     "cm2_fcos_select_workspace": (_L, [_I, _I, _I]),
     "cm2_fcos_select": (_I, [C.POINTER(CandBuffers), _I, _I, _I, C.POINTER(_I), C.POINTER(_I), _I, _I, _F, _I,
                              C.POINTER(DetBuffers), _P, _P]),
@@ -126,6 +137,16 @@ def act(t):
     return Act(t.data_ptr(), t.shape[0], t.shape[1], t.shape[2], t.shape[3], t.stride(0), t.stride(1), t.stride(2))
 
 
+def flat_act(t):
+    """``cm2_act`` of a flat [rows, c] buffer (segmented tensors: only data and c are read)."""
+    assert t.dim() == 2 and t.stride(1) == 1 and t.stride(0) == t.shape[1], (t.shape, t.stride())
+    return Act(t.data_ptr(), 1, 1, t.shape[0], t.shape[1], t.shape[0] * t.shape[1], t.shape[0] * t.shape[1], t.shape[1])
+
+
+def seg_array(segs):
+    return (Seg * len(segs))(*[Seg(r, n, h, w, 0) for r, n, h, w in segs])
+
+
 def ptr(t):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
@@ -139,7 +160,8 @@ def _count(k=1):
 # thin wrappers (one per entry point)
 # ------------------------------------------------------------------------------------------------
 def conv2d(srcs, weight, out, cout, k, stride, pad, scale=None, shift=None, relu=False, in_relu=False,
-           residual=None, res_mode=0, out_mode=0, engine=ENGINE_SIMT, chan_sum=None, probe=False, src_phase=False):
+           residual=None, res_mode=0, out_mode=0, engine=ENGINE_SIMT, chan_sum=None, probe=False, src_phase=False,
+           segs=None):
     """Enqueue one convolution.  With ``probe=True`` (TC engine) the descriptor is first checked with
     ``cm2_conv_tc_supported``; returns False without launching if the engine does not take it."""
     d = ConvDesc()
@@ -147,8 +169,16 @@ def conv2d(srcs, weight, out, cout, k, stride, pad, scale=None, shift=None, relu
     d.out_dtype = dtype_code(out)
     d.engine = engine
     d.num_src = len(srcs)
-    for i, s in enumerate(srcs):
-        d.src[i] = act(s)
+    if segs is not None:
+        # segmented halo tensors: srcs / out are flat [rows, c] buffers sharing the segment table
+        d.num_seg = len(segs)
+        for i, (row0, n, h, w) in enumerate(segs):
+            d.seg[i] = Seg(row0, n, h, w, 0)
+        for i, s in enumerate(srcs):
+            d.src[i] = flat_act(s)
+    else:
+        for i, s in enumerate(srcs):
+            d.src[i] = act(s)
     d.cout, d.kh, d.kw, d.stride, d.pad = cout, k, k, stride, pad
     d.weight = weight.data_ptr()
     d.scale = 0 if scale is None else scale.data_ptr()
@@ -157,7 +187,7 @@ def conv2d(srcs, weight, out, cout, k, stride, pad, scale=None, shift=None, relu
     d.residual = act(residual)
     d.res_mode = res_mode if residual is not None else 0
     d.out_mode = out_mode
-    d.out = act(out)
+    d.out = flat_act(out) if segs is not None else act(out)
     d.chan_sum = 0 if chan_sum is None else chan_sum.data_ptr()
     d.src_phase = int(src_phase)
     if probe and not load().cm2_conv_tc_supported(C.byref(d)):
@@ -234,6 +264,17 @@ def groupnorm_relu(x, groups, gamma, beta, eps, relu, workspace):
     _count(3)
 
 
+def gn_seg_workspace_floats(segs, c, groups):
+    return int(load().cm2_gn_seg_workspace_floats(len(segs), seg_array(segs), c, groups))
+
+
+def groupnorm_relu_seg(flat, segs, groups, gamma, beta, eps, relu, workspace):
+    check(load().cm2_groupnorm_relu_seg(ptr(flat), dtype_code(flat), flat.shape[1], len(segs), seg_array(segs), groups,
+                                        ptr(gamma), ptr(beta), eps, int(relu), ptr(workspace), stream()),
+          "cm2_groupnorm_relu_seg")
+    _count(3)
+
+
 def relu(x, out):
     a, o = act(x), act(out)
     check(load().cm2_relu(C.byref(a), C.byref(o), dtype_code(x), stream()), "cm2_relu")
@@ -248,9 +289,9 @@ def det_buffers(boxes, scores, classes, locations, count):
     return DetBuffers(boxes.data_ptr(), scores.data_ptr(), classes.data_ptr(), locations.data_ptr(), count.data_ptr())
 
 
-def fcos_decode(logits, regctr, stride, thresh, thresh_with_ctr, level, num_levels, cap, cand):
+def fcos_decode(logits, regctr, stride, reg_scale, thresh, thresh_with_ctr, level, num_levels, cap, cand):
     a, b = act(logits), act(regctr)
-    check(load().cm2_fcos_decode(C.byref(a), C.byref(b), stride, thresh, int(thresh_with_ctr), level, num_levels, cap,
+    check(load().cm2_fcos_decode(C.byref(a), C.byref(b), stride, reg_scale, thresh, int(thresh_with_ctr), level, num_levels, cap,
                                  C.byref(cand), stream()), "cm2_fcos_decode")
     _count()
 

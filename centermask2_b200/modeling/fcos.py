@@ -50,7 +50,7 @@ class FCOS(PackedModule):
         """feats: list of engine FMaps.  Device-only: returns the fixed-size detection buffers."""
         eng, P = self._pack()
         head = eng.run_fcos_head(feats, P)
-        return eng.run_fcos_post(head)
+        return eng.run_fcos_post(head, reg_scale=P["reg_scale"])
 
     def forward(self, images, features, gt_instances=None):
         """``fcos.py:61-118``: returns ``(list[Instances], {})`` with fields pred_boxes, scores,

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CM2_VERSION 102
+#define CM2_VERSION 103
 
 #define CM2_OK 0
 #define CM2_ERR_BAD_SHAPE (-1)
@@ -46,6 +46,7 @@ extern "C" {
 #define CM2_ENGINE_TC 1   /* tcgen05/TMEM implicit GEMM with TMA-staged tiles; bf16 in             */
 
 #define CM2_MAX_SRC 8
+#define CM2_MAX_SEG 8
 
 /* Pitched NHWC view.  `data` addresses element (n=0, y=0, x=0, c=0); channel stride is 1. */
 typedef struct cm2_act {
@@ -53,6 +54,16 @@ typedef struct cm2_act {
   int32_t n, h, w, c;
   int64_t sn, sh, sw; /* element strides of image, row, pixel */
 } cm2_act;
+
+/* One segment of a *segmented* halo tensor: several feature maps of different extent (the FPN levels the
+ * shared-weight FCOS towers run on, fcos.py:227-238) stored back to back in one flat [rows, c] buffer.
+ * Segment s occupies rows [row0, row0 + n*(h+2)*(w+2)) as a halo-1 block [n, h+2, w+2, c]; row0 must be a
+ * multiple of 256; rows between segments are padding (ignored on input, untouched on output). */
+typedef struct cm2_seg {
+  int64_t row0;
+  int32_t n, h, w;
+  int32_t reserved;
+} cm2_seg;
 
 int cm2_version(void);
 const char* cm2_last_error(void);
@@ -110,6 +121,11 @@ typedef struct cm2_conv_desc {
    * halo-1 interior view of plane 0, [n, ceil(H/2), ceil(W/2), c], plane q = (y&1)*2 + (x&1) starts
    * n*sn elements after plane q-1.  Requires a 3x3 / stride 2 / pad 1 convolution; TC engine only. */
   int32_t src_phase;
+  /* > 0: sources and output are segmented halo tensors sharing the segment table `seg` (TC engine, stride 1,
+   * out_mode 0, no residual): src[i].data / out.data address flat row 0, src[i].c / out.c are the channel counts
+   * (= row pitch in elements); the other cm2_act fields are ignored.  One launch then covers all segments. */
+  int32_t num_seg;
+  cm2_seg seg[CM2_MAX_SEG];
 } cm2_conv_desc;
 
 int cm2_conv2d(const cm2_conv_desc* d, void* stream);
@@ -161,6 +177,13 @@ int cm2_groupnorm_relu(const cm2_act* x, int32_t dtype, int32_t groups, const fl
  * (y>>1, x>>1).  Positions of a plane that no input pixel maps to are left untouched (zero). */
 int cm2_phase_split(const cm2_act* in, const cm2_act* out_plane0, int32_t dtype, int32_t relu, void* stream);
 
+/* The same on a segmented halo tensor (see cm2_seg): one launch set for all segments; statistics are per
+ * (segment, image, group).  x: flat [rows, c].  workspace: cm2_gn_seg_workspace_floats floats. */
+int64_t cm2_gn_seg_workspace_floats(int32_t num_seg, const cm2_seg* seg, int32_t c, int32_t groups);
+int cm2_groupnorm_relu_seg(void* x, int32_t dtype, int32_t c, int32_t num_seg, const cm2_seg* seg, int32_t groups,
+                           const float* gamma, const float* beta, float eps, int32_t relu, float* workspace,
+                           void* stream);
+
 /* Elementwise ReLU copy (P7 input when the conv engine cannot apply in_relu). */
 int cm2_relu(const cm2_act* in, const cm2_act* out, int32_t dtype, void* stream);
 
@@ -171,8 +194,9 @@ int cm2_relu(const cm2_act* in, const cm2_act* out, int32_t dtype, void* stream)
  *   p = sigmoid(logit); c = sigmoid(ctr); candidate iff p > thresh (p*c > thresh when
  *   thresh_with_ctr); raw score = p*c; box = (x-l, y-t, x+r, y+b) with (l,t,r,b) = reg*stride,
  *   (x,y) = (col*stride + stride/2, row*stride + stride/2)  (fcos.py:132-144).
- *   logits: f32 view [n,h,w,ncls];  regctr: f32 view [n,h,w,>=5] with channels (l,t,r,b,ctr,...)
- *   where l..b already include Scale and ReLU (fcos.py:233-238).
+ *   logits: f32 view [n,h,w,ncls];  regctr: f32 view [n,h,w,>=5] with channels (l,t,r,b,ctr,...) where
+ *   l..b are the raw bbox_pred outputs: the per-level Scale and the ReLU (fcos.py:233-238) are applied here,
+ *   (l,t,r,b) = relu(reg * reg_scale) * stride.
  *   Candidates are appended (unordered) to segment (image, level) of the candidate arrays, each
  *   of capacity `cap`; cand_count[image*num_levels+level] counts *all* candidates, so a value > cap
  *   signals overflow to the caller.  cand_count must be zeroed by the caller.
@@ -191,7 +215,7 @@ typedef struct cm2_cand_buffers {
   int32_t* count;  /* [n][levels] */
 } cm2_cand_buffers;
 
-int cm2_fcos_decode(const cm2_act* logits, const cm2_act* regctr, int32_t stride, float thresh,
+int cm2_fcos_decode(const cm2_act* logits, const cm2_act* regctr, int32_t stride, float reg_scale, float thresh,
                     int32_t thresh_with_ctr, int32_t level, int32_t num_levels, int32_t cap,
                     const cm2_cand_buffers* cand, void* stream);
 

@@ -233,3 +233,49 @@ def test_fused_preprocess_im2col_stem1():
         torch.cuda.synchronize()
         close(nchw(out.view)[1:], ref)
         assert nchw(out.view)[0].abs().max() == 0
+
+
+def test_segmented_conv_and_groupnorm_match_per_level_results():
+    """All FPN levels of an FCOS tower in one launch (cm2_seg): conv3x3 + bias, then GroupNorm(32)+ReLU in place."""
+    from centermask2_b200.engine import SegMap
+    g = torch.Generator().manual_seed(21)
+    n, c = 2, 256
+    shapes = [(n, 25, 42), (n, 13, 21), (n, 7, 11), (n, 4, 6), (n, 2, 3)]
+    xs = [rb(torch.randn(n, c, h, w, generator=g)) for _, h, w in shapes]
+    wt = rb(torch.randn(c, c, 3, 3, generator=g) / 48)
+    bias = torch.randn(c, generator=g) * 0.1
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.2
+    seg = SegMap(shapes, c, BF, DEV)
+    for i, x in enumerate(xs):
+        seg.level(i).view.copy_(x.permute(0, 2, 3, 1).to(DEV, BF))
+    cw = packing.ConvW(wt, [c], 1, 1, None, bias, False, BF, DEV, True)
+    out = seg.like(c, BF, lambda shape: torch.full(shape, 5.0, dtype=BF, device=DEV))
+    lib.conv2d([seg.flat], cw.w_tc, out.flat, c, 3, 1, 1, shift=cw.shift, engine=lib.ENGINE_TC, segs=seg.segs)
+    torch.cuda.synchronize()
+    conv_ref = [rb(F.conv2d(x, wt, bias, 1, 1)) for x in xs]
+    for i, ref in enumerate(conv_ref):
+        lv = out.level(i)
+        close(nchw(lv.view), ref)
+        b = lv.buf.float()
+        assert b[:, 0].abs().max() == 0 and b[:, :, 0].abs().max() == 0 and b[:, -1].abs().max() == 0       # halo zeroed
+    ws = torch.empty(lib.gn_seg_workspace_floats(out.segs, c, 32), device=DEV)
+    lib.groupnorm_relu_seg(out.flat, out.segs, 32, gamma.to(DEV), beta.to(DEV), 1e-5, True, ws)
+    torch.cuda.synchronize()
+    for i in range(len(shapes)):
+        lv = out.level(i)
+        got_conv = conv_ref[i]
+        # reference GN on what the engine actually stored (bf16-rounded conv output)
+        ref = F.relu(F.group_norm(got_conv, 32, gamma, beta, 1e-5))
+        close(nchw(lv.view), ref)
+        assert lv.buf.float()[:, 0].abs().max() == 0
+    # f32 head output with 16 columns (bbox_pred + ctrness padded)
+    w16 = torch.zeros(16, c, 3, 3)
+    w16[:5] = rb(torch.randn(5, c, 3, 3, generator=g) / 48)
+    b16 = torch.zeros(16)
+    b16[:5] = torch.randn(5, generator=g)
+    cw16 = packing.ConvW(w16, [c], 1, 1, None, b16, False, BF, DEV, True)
+    o16 = seg.like(16, torch.float32, lambda shape: torch.zeros(shape, dtype=torch.float32, device=DEV))
+    lib.conv2d([seg.flat], cw16.w_tc, o16.flat, 16, 3, 1, 1, shift=cw16.shift, engine=lib.ENGINE_TC, segs=seg.segs)
+    torch.cuda.synchronize()
+    for i, x in enumerate(xs):
+        close(nchw(o16.level(i).view), F.conv2d(x, w16, b16, 1, 1), out_bf16=False)

@@ -119,7 +119,7 @@ def test_layerwise_against_oracle_trace():
     for l, (lg, rc) in enumerate(head):
         got = lg.view.permute(0, 3, 1, 2).cpu()
         assert (got - tr["logits"][l]).abs().max().item() <= 2e-3, l
-        reg = torch.relu(rc.view[..., :4]).permute(0, 3, 1, 2).cpu()
+        reg = torch.relu(rc.view[..., :4] * P["reg_scale"][l]).permute(0, 3, 1, 2).cpu()      # Scale + ReLU live in the decode kernel
         assert (reg - tr["regs"][l]).abs().max().item() <= 2e-3 * max(1.0, tr["regs"][l].abs().max().item()), l
         ctr = rc.view[..., 4:5].permute(0, 3, 1, 2).cpu()
         assert (ctr - tr["ctrs"][l]).abs().max().item() <= 2e-3, l
