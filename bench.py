@@ -173,13 +173,27 @@ def conv_time_per_step(model, cfg, dev_images, steps, layers=None):
             wo = (x.w + 2 * w.pad - w.k) // w.stride + 1
             layers.append((name, 2.0 * x.n * ho * wo * sum(w.src_c) * w.k * w.k * w.cout / 1e9, (e0, e1)))
         return r
+    orig_seg = eng.conv_seg
+
+    def timed_seg(name, x, w, *a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_seg(name, x, w, *a, **k)
+        e1.record()
+        events.append((e0, e1))
+        if layers is not None:
+            px = sum(n * h * ww for _, n, h, ww in x.segs)
+            layers.append((name, 2.0 * px * sum(w.src_c) * w.k * w.k * w.cout / 1e9, (e0, e1)))
+        return r
     eng.conv = timed
+    eng.conv_seg = timed_seg
     try:
         for _ in range(steps):
             device_step(model, cfg, dev_images, (H, W))
         torch.cuda.synchronize()
     finally:
         eng.conv = orig
+        eng.conv_seg = orig_seg
     total = sum(a.elapsed_time(b) for a, b in events)
     return total / steps, len(events) // steps
 

@@ -13,7 +13,7 @@ from centermask2_b200 import runtime                                            
 from oracle import restate                                                       # noqa: E402
 from oracle.cases import CASES                                                   # noqa: E402
 from tests.helpers import (load_golden, build_case, unpack_masks, mask_iou,     # noqa: E402
-                           assert_detections_match, MASK_IOU_MIN)
+                           assert_detections_match, assert_masks_match, MASK_IOU_MIN)
 
 
 def fields(inst):
@@ -76,7 +76,7 @@ def test_postprocessed_match_reference(case):
         if len(r["scores"]):
             ref_masks = unpack_masks(r)
             assert g["pred_masks"].dtype == torch.bool and g["pred_masks"].shape == ref_masks.shape
-            assert mask_iou(g["pred_masks"], ref_masks).min().item() >= MASK_IOU_MIN
+            assert_masks_match(g["pred_masks"], ref_masks, what="{}[{}]".format(name, i))
 
 
 def test_registry_level_modules_compose_like_the_reference(case):
