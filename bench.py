@@ -44,28 +44,33 @@ def peaks():
 # clocks
 # --------------------------------------------------------------------------------------------------
 class ClockSampler(object):
+    """`nvidia-smi -lms` running for the whole process (its start-up takes longer than a short timed region);
+    only samples whose arrival time falls inside a `window()` -- the timed regions -- are summarised."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
-
-    def __enter__(self):
+        self.index, self.rows, self.proc, self.windows = index, [], None, []
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
-        return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def __exit__(self, *a):
+    @contextlib.contextmanager
+    def window(self):
+        t0 = time.perf_counter()
+        yield
+        self.windows.append((t0, time.perf_counter()))
+
+    def close(self):
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -76,7 +81,9 @@ class ClockSampler(object):
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if not any(a <= t <= b + 0.02 for a, b in self.windows):
+                continue
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -139,19 +146,35 @@ def compact_results(results, r_cap):
     return parallel.pack_records([r["instances"] for r in results], r_cap)
 
 
-def device_step(model, cfg, dev_images, sizes_out):
-    """Hot path with inputs resident in HBM; results stay on the device in fixed-size buffers (no host sync)."""
+def make_device_step(model, cfg, dev_images, sizes_out, graph=True):
+    """Hot path with inputs resident in HBM; results stay on the device in fixed-size buffers (no host sync).
+    Returns a callable running one step: the launch plan replayed as a CUDA graph (``graph=True``, the product
+    path of ``GeneralizedRCNN.inference``) or launched eagerly through the C ABI."""
     from centermask2_b200 import runtime
     eng = runtime.engine_for(cfg)
-    x, sizes = eng.preprocess(dev_images, 32)
-    feats = model.backbone.forward_fmap(x)
     fcos, roi = model.proposal_generator, model.roi_heads
-    det = fcos.detect([feats[f] for f in fcos.in_features])
-    probs, mask_scores = roi.run([feats[f] for f in roi.in_features], det, sizes)
-    r_cap = det["boxes"].shape[1]
-    for i in range(len(dev_images)):
-        eng.paste(probs[i * r_cap:(i + 1) * r_cap], det["boxes"][i], sizes_out[0], sizes_out[1], sizes[i])
-    return det, mask_scores
+    n = len(dev_images)
+    out_sizes = [tuple(sizes_out)] * n
+
+    def plan():
+        x, sizes = eng.preprocess(dev_images, 32)
+        feats = model.backbone.forward_fmap(x)
+        det = fcos.detect([feats[f] for f in fcos.in_features])
+        probs, mask_scores = roi.run([feats[f] for f in roi.in_features], det, sizes)
+        boxes, valid = eng.rescale_boxes(det["boxes"], sizes, out_sizes)
+        r_cap = det["boxes"].shape[1]
+        masks = eng.buffer("bench_masks", (n, r_cap, sizes_out[0], sizes_out[1]), torch.uint8, zero=False)
+        eng.paste_batch(probs, boxes, valid, out_sizes, masks=masks)
+        return det, mask_scores
+
+    if graph and eng.use_graphs:
+        return lambda: eng.graphed(("bench_step", n, tuple(sizes_out)), plan)
+    return plan
+
+
+def device_step(model, cfg, dev_images, sizes_out):
+    """One eager step (used by the instrumented per-launch timing pass)."""
+    return make_device_step(model, cfg, dev_images, sizes_out, graph=False)()
 
 
 def conv_time_per_step(model, cfg, dev_images, steps, layers=None):
@@ -229,12 +252,13 @@ def cpu_baseline(steps, warmup, images_per_step=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--precision", default=os.environ.get("CM2_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying its CUDA graph")
     ap.add_argument("--layers", default=None, help="write a per-conv-layer timing table (one step) to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -264,6 +288,7 @@ def main():
     from centermask2_b200.arch import conv_gflop_per_image
     from centermask2_b200.synth import synthetic_state_dict
 
+    clk = ClockSampler(local)
     cfg = make_cfg(args.precision)
     model = cm.build_model(cfg)
     model.load_state_dict(synthetic_state_dict(cfg, seed=WEIGHT_SEED))
@@ -271,6 +296,8 @@ def main():
     bias = calibrate_on_gpu(model, cfg, host_inputs)
     dev_images = [b["image"].cuda() for b in host_inputs]
     eng = runtime.engine_for(cfg)
+    if args.no_graph:
+        eng.use_graphs = False
     r_cap = cfg.MODEL.FCOS.POST_NMS_TOPK_TEST
 
     def barrier():
@@ -280,17 +307,18 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value")
+    step = make_device_step(model, cfg, dev_images, (H, W), graph=not args.no_graph)
     for _ in range(warmup):
-        det, _ms = device_step(model, cfg, dev_images, (H, W))
+        det, _ms = step()
     barrier()
     dets_per_image = det["count"].float().mean().item()
     cand = det["cand_count"].float().mean().item()
     l0 = lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    with clk.window():
         e0.record()
         for _ in range(args.steps):
-            device_step(model, cfg, dev_images, (H, W))
+            step()
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1)
@@ -309,11 +337,12 @@ def main():
     for _ in range(2):
         e2e_step()
     barrier()
-    e0.record()
-    for _ in range(args.steps):
-        rec = e2e_step()
-    e1.record()
-    barrier()
+    with clk.window():
+        e0.record()
+        for _ in range(args.steps):
+            rec = e2e_step()
+        e1.record()
+        barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -337,6 +366,7 @@ def main():
                 ms_l = a.elapsed_time(b)
                 f.write("{:24s} {:10.3f} {:9.4f} {:9.1f}\n".format(nme, gf, ms_l, gf / ms_l if ms_l > 0 else 0.0))
     gflop_img = conv_gflop_per_image(cfg, 800, 1344, r_cap)          # algorithmic FLOPs, R = slots computed
+    clk.close()
     hbm, tf_burst, tf_sus, src = peaks()
     achieved = gflop_img * args.batch / conv_ms                       # GFLOP / ms = TFLOP/s
     peak = tf_sus
@@ -349,7 +379,7 @@ def main():
                    "images_per_gpu": args.batch, "precision": args.precision, "cls_bias": bias,
                    "detections_per_image": dets_per_image, "candidates_per_level": cand,
                    "l2": "activations per step ({} images) far exceed the 126 MB L2; no explicit flush".format(args.batch),
-                   "parallelism": "dp{}".format(world)},
+                   "cuda_graph": bool(eng.use_graphs and not args.no_graph), "parallelism": "dp{}".format(world)},
         "clocks": clk.summary(),
         "e2e": {"value": args.batch * world / (e2e_ms / 1e3), "unit": "img/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,

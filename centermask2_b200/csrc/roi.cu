@@ -233,60 +233,101 @@ __global__ void scale_clip_boxes_kernel(const float* __restrict__ in, float* __r
   valid[i] = ((b.z - b.x) > 0.f && (b.w - b.y) > 0.f) ? 1 : 0;
 }
 
-// grid (x-chunks, y-chunks, r).  Each thread produces 4 consecutive output bytes (one 32-bit store).
+// Batched variant: params[img] = (sx, sy, out_w, out_h) in device memory, r_cap slots per image.
+__global__ void scale_clip_boxes_batch_kernel(const float* __restrict__ in, float* __restrict__ out, uint8_t* __restrict__ valid,
+                                              int total, int r_cap, const float* __restrict__ params) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float4 q = __ldg(reinterpret_cast<const float4*>(params) + i / r_cap);
+  float4 b = reinterpret_cast<const float4*>(in)[i];
+  b.x = fminf(fmaxf(b.x * q.x, 0.f), q.z);
+  b.z = fminf(fmaxf(b.z * q.x, 0.f), q.z);
+  b.y = fminf(fmaxf(b.y * q.y, 0.f), q.w);
+  b.w = fminf(fmaxf(b.w * q.y, 0.f), q.w);
+  reinterpret_cast<float4*>(out)[i] = b;
+  valid[i] = ((b.z - b.x) > 0.f && (b.w - b.y) > 0.f) ? 1 : 0;
+}
+
+// Mask paste-back.  The output of one ROI is treated as a flat byte string of out_h*out_w bytes (rows of an
+// 800x1333 mask are not 4-byte aligned, so a per-row vector store is impossible); it is cut into absolute
+// 16-byte-aligned pieces, one 128-bit store each.  grid (spans, r): a block covers PASTE_SPAN consecutive bytes
+// of ROI r and loads the 28x28 probabilities only if its rows intersect the (dilated) box -- most blocks are
+// pure zero fill at store bandwidth.
 // grid_sample(bilinear, zeros, align_corners=False): ix = ((gx + 1) * m - 1) / 2.
-constexpr int PASTE_ROWS = 8;
+constexpr int PASTE_ITERS = 4;
+constexpr int PASTE_SPAN = 256 * 16 * PASTE_ITERS;
 __global__ void __launch_bounds__(256) paste_masks_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
                                                           const uint8_t* __restrict__ valid, uint8_t* __restrict__ out,
                                                           int m, int out_h, int out_w, float threshold) {
   extern __shared__ float s_mask[];
-  const int r = blockIdx.z;
-  for (int i = threadIdx.x; i < m * m; i += blockDim.x) s_mask[i] = probs[(size_t)r * m * m + i];
-  __syncthreads();
+  const int r = blockIdx.y;
+  const long long hw = (long long)out_h * out_w;
+  uint8_t* obase = out + (size_t)r * hw;
+  const long long lead = (long long)(reinterpret_cast<uintptr_t>(obase) & 15);     // bytes before obase in its first 16B piece
+  const long long f_lo = (long long)blockIdx.x * PASTE_SPAN - lead;               // flat range of this block
+  if (f_lo >= hw) return;
+  const long long f_hi = min(f_lo + PASTE_SPAN, hw);
   const float4 b = reinterpret_cast<const float4*>(boxes)[r];
-  const bool ok = valid[r] != 0;
   const int xa = max((int)floorf(b.x) - 1, 0), ya = max((int)floorf(b.y) - 1, 0);
   const int xb = min((int)ceilf(b.z) + 1, out_w), yb = min((int)ceilf(b.w) + 1, out_h);
   const float bw = b.z - b.x, bh = b.w - b.y;
-  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (x0 >= out_w) return;
-  uint8_t* obase = out + (size_t)r * out_h * out_w;
-  const bool vec = (out_w % 4) == 0;
-  for (int dy = 0; dy < PASTE_ROWS; ++dy) {
-    int y = blockIdx.y * PASTE_ROWS + dy;
-    if (y >= out_h) break;
-    uint32_t packed = 0;
-    if (ok && y >= ya && y < yb && x0 + 3 >= xa && x0 < xb) {
-      float gy = ((float)y + 0.5f - b.y) / bh * 2.f - 1.f;
-      float iy = ((gy + 1.f) * (float)m - 1.f) * 0.5f;
-      float fy = floorf(iy);
-      int y0 = (int)fy, y1 = y0 + 1;
-      float wy1 = iy - fy, wy0 = (fy + 1.f) - iy;      // ATen: (iy_se - iy), (iy - iy_nw)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        int x = x0 + k;
-        if (x < xa || x >= xb || x >= out_w) continue;
-        float gx = ((float)x + 0.5f - b.x) / bw * 2.f - 1.f;
-        float ix = ((gx + 1.f) * (float)m - 1.f) * 0.5f;
-        float fx = floorf(ix);
-        int xl = (int)fx, xh = xl + 1;
-        float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
-        float v = 0.f;
-        bool yl_in = y0 >= 0 && y0 < m, yh_in = y1 >= 0 && y1 < m;
-        bool xl_in = xl >= 0 && xl < m, xh_in = xh >= 0 && xh < m;
-        // same accumulation order as ATen's grid_sampler_2d (nw, ne, sw, se)
-        if (yl_in && xl_in) v += s_mask[y0 * m + xl] * (wx0 * wy0);
-        if (yl_in && xh_in) v += s_mask[y0 * m + xh] * (wx1 * wy0);
-        if (yh_in && xl_in) v += s_mask[y1 * m + xl] * (wx0 * wy1);
-        if (yh_in && xh_in) v += s_mask[y1 * m + xh] * (wx1 * wy1);
-        if (v >= threshold) packed |= 1u << (8 * k);
+  const int row_lo = (int)(max(f_lo, 0ll) / out_w), row_hi = (int)((f_hi - 1) / out_w);
+  const bool touch = valid[r] != 0 && row_hi >= ya && row_lo < yb && xa < xb;      // block-uniform
+  if (touch) {
+    for (int i = threadIdx.x; i < m * m; i += blockDim.x) s_mask[i] = probs[(size_t)r * m * m + i];
+    __syncthreads();
+  }
+  const float fm = (float)m;
+#pragma unroll 1
+  for (int it = 0; it < PASTE_ITERS; ++it) {
+    const long long f = f_lo + (long long)(it * 256 + threadIdx.x) * 16;
+    if (f >= hw) break;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (touch) {
+      const long long fs = max(f, 0ll), fe = min(f + 16, hw);
+      int y = (int)(fs / out_w), x = (int)(fs - (long long)y * out_w);
+      const int y_last = (int)((fe - 1) / out_w);
+      if (y_last >= ya && y < yb) {
+        int cur_y = -1;
+        float wy0 = 0.f, wy1 = 0.f;
+        int y0 = 0, y1 = 0;
+        for (long long ff = fs; ff < fe; ++ff) {
+          if (y >= ya && y < yb && x >= xa && x < xb) {
+            if (cur_y != y) {
+              cur_y = y;
+              float gy = ((float)y + 0.5f - b.y) / bh * 2.f - 1.f;
+              float iy = ((gy + 1.f) * fm - 1.f) * 0.5f;
+              float fy = floorf(iy);
+              y0 = (int)fy; y1 = y0 + 1;
+              wy1 = iy - fy; wy0 = (fy + 1.f) - iy;      // ATen: (iy_se - iy), (iy - iy_nw)
+            }
+            float gx = ((float)x + 0.5f - b.x) / bw * 2.f - 1.f;
+            float ix = ((gx + 1.f) * fm - 1.f) * 0.5f;
+            float fx = floorf(ix);
+            int xl = (int)fx, xh = xl + 1;
+            float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
+            float v = 0.f;
+            bool yl_in = y0 >= 0 && y0 < m, yh_in = y1 >= 0 && y1 < m;
+            bool xl_in = xl >= 0 && xl < m, xh_in = xh >= 0 && xh < m;
+            // same accumulation order as ATen's grid_sampler_2d (nw, ne, sw, se)
+            if (yl_in && xl_in) v += s_mask[y0 * m + xl] * (wx0 * wy0);
+            if (yl_in && xh_in) v += s_mask[y0 * m + xh] * (wx1 * wy0);
+            if (yh_in && xl_in) v += s_mask[y1 * m + xl] * (wx0 * wy1);
+            if (yh_in && xh_in) v += s_mask[y1 * m + xh] * (wx1 * wy1);
+            if (v >= threshold) {
+              const int k = (int)(ff - f);
+              w[k >> 2] |= 1u << (8 * (k & 3));
+            }
+          }
+          if (++x == out_w) { x = 0; ++y; }
+        }
       }
     }
-    uint8_t* o = obase + (size_t)y * out_w + x0;
-    if (vec) {
-      *reinterpret_cast<uint32_t*>(o) = packed;
+    if (f >= 0 && f + 16 <= hw) {
+      *reinterpret_cast<uint4*>(obase + f) = make_uint4(w[0], w[1], w[2], w[3]);
     } else {
-      for (int k = 0; k < 4 && x0 + k < out_w; ++k) o[k] = (uint8_t)((packed >> (8 * k)) & 0xff);
+      for (int k = 0; k < 16; ++k)
+        if (f + k >= 0 && f + k < hw) obase[f + k] = (uint8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xff);
     }
   }
 }
@@ -427,13 +468,25 @@ extern "C" int cm2_scale_clip_boxes(const float* boxes_in, float* boxes_out, uin
   return CM2_OK;
 }
 
+extern "C" int cm2_scale_clip_boxes_batch(const float* boxes_in, float* boxes_out, uint8_t* valid, int32_t n, int32_t r_cap,
+                                          const float* params, void* stream) {
+  CM2_CHECK_ARG(boxes_in && boxes_out && valid && params, "scale_clip_boxes_batch: null pointer");
+  CM2_CHECK_ARG(n >= 0 && r_cap > 0, "scale_clip_boxes_batch: bad extents n=%d r_cap=%d", n, r_cap);
+  if (n == 0) return CM2_OK;
+  scale_clip_boxes_batch_kernel<<<ceil_div(n * r_cap, 128), 128, 0, (cudaStream_t)stream>>>(boxes_in, boxes_out, valid, n * r_cap,
+                                                                                           r_cap, params);
+  CM2_CHECK_LAUNCH("scale_clip_boxes_batch");
+  return CM2_OK;
+}
+
 extern "C" int cm2_paste_masks(const float* probs, const float* boxes, const uint8_t* valid, uint8_t* out, int32_t r,
                                int32_t m, int32_t out_h, int32_t out_w, float threshold, void* stream) {
   CM2_CHECK_ARG(probs && boxes && valid && out, "paste_masks: null pointer");
   CM2_CHECK_ARG(m > 0 && m <= 64 && out_h > 0 && out_w > 0, "paste_masks: bad extents m=%d out=%dx%d", m, out_h, out_w);
   if (r == 0) return CM2_OK;
   CM2_CHECK_ARG(r <= 65535, "paste_masks: too many ROIs in one call (%d)", r);
-  dim3 grid(ceil_div(ceil_div(out_w, 4), 256), ceil_div(out_h, PASTE_ROWS), r);
+  const long long hw = (long long)out_h * out_w;
+  dim3 grid((unsigned)((hw + 15 + PASTE_SPAN - 1) / PASTE_SPAN), r);
   paste_masks_kernel<<<grid, 256, (size_t)m * m * sizeof(float), (cudaStream_t)stream>>>(probs, boxes, valid, out, m,
                                                                                           out_h, out_w, threshold);
   CM2_CHECK_LAUNCH("paste_masks");

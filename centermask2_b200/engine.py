@@ -11,6 +11,7 @@ Reference call sequence being replaced: ``GeneralizedRCNN.inference`` [d2] as mi
 -> ``detector_postprocess`` [d2].
 """
 import math
+import os
 
 import torch
 
@@ -137,6 +138,8 @@ class Engine(object):
         self.tc = precision == "bf16"
         self.device = torch.device(device)
         self._bufs = {}
+        self._graphs = {}
+        self.use_graphs = os.environ.get("CM2_GRAPH", "1") != "0"
         lib.load()
 
     # -- buffers ---------------------------------------------------------------------------------
@@ -145,6 +148,15 @@ class Engine(object):
         t = self._bufs.get(key)
         if t is None:
             t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def pinned(self, name, shape, dtype):
+        """Page-locked host staging buffer (async D2H of the small result-size tensors)."""
+        key = ("pinned", name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
             self._bufs[key] = t
         return t
 
@@ -161,6 +173,7 @@ class Engine(object):
         return out
 
     def release(self):
+        self._graphs.clear()
         self._bufs.clear()
 
     # -- one convolution -------------------------------------------------------------------------
@@ -570,3 +583,60 @@ class Engine(object):
         m = probs.shape[-1]
         lib.paste_masks(probs, b2, valid, masks, r, m, out_h, out_w, threshold)
         return b2, valid, masks
+
+    def rescale_boxes(self, det_boxes, sizes, out_sizes):
+        """Box half of detector_postprocess for the whole batch (one launch): det_boxes [n, r_cap, 4] ->
+        (boxes' [n, r_cap, 4], valid u8 [n, r_cap]) in engine-owned buffers."""
+        n, r_cap = det_boxes.shape[0], det_boxes.shape[1]
+        key = ("pp_params", tuple(sizes), tuple(out_sizes))
+        if key not in self._bufs:
+            self._bufs[key] = torch.tensor([[ow / sz[1], oh / sz[0], float(ow), float(oh)] for (oh, ow), sz in zip(out_sizes, sizes)],
+                                           dtype=torch.float32, device=self.device)
+        boxes = self.buffer("pp_boxes", (n, r_cap, 4), torch.float32, False)
+        valid = self.buffer("pp_valid", (n, r_cap), torch.uint8, False)
+        lib.scale_clip_boxes_batch(det_boxes, boxes, valid, n, r_cap, self._bufs[key])
+        return boxes, valid
+
+    def paste_batch(self, probs, boxes, valid, out_sizes, masks=None, threshold=0.5, dtype=torch.uint8):
+        """Mask half of detector_postprocess: probs [n*r_cap, 1, m, m] -> list of [r_cap, oh, ow] 0/1 byte masks
+        (one launch when every image has the same output size).  ``masks``: optional preallocated
+        [n, r_cap, oh, ow] buffer (uniform sizes only)."""
+        n, r_cap = boxes.shape[0], boxes.shape[1]
+        m = probs.shape[-1]
+        if len(set(out_sizes)) == 1 and n * r_cap <= 65535:
+            oh, ow = out_sizes[0]
+            if masks is None:
+                masks = torch.empty((n, r_cap, oh, ow), dtype=dtype, device=self.device)
+            lib.paste_masks(probs, boxes, valid, masks, n * r_cap, m, oh, ow, threshold)
+            return [masks[i] for i in range(n)]
+        out = []
+        for i, (oh, ow) in enumerate(out_sizes):
+            mk = torch.empty((r_cap, oh, ow), dtype=dtype, device=self.device)
+            lib.paste_masks(probs[i * r_cap:(i + 1) * r_cap], boxes[i], valid[i], mk, r_cap, m, oh, ow, threshold)
+            out.append(mk)
+        return out
+
+    # =============================================================================================
+    # CUDA-graph replay of a launch plan
+    # =============================================================================================
+    def graphed(self, key, fn):
+        """Run ``fn`` (a sequence of C-ABI launches on engine-owned buffers, no host sync) through a CUDA graph:
+        the first call with a given ``key`` runs it eagerly once (allocates every buffer), captures it, and every
+        call replays the capture -- the ~170 launches of a step cost one graph launch on the host.  Returns whatever
+        ``fn`` returned at capture time (the same engine-owned buffers every call).  ``CM2_GRAPH=0`` disables."""
+        if not self.use_graphs:
+            return fn()
+        ent = self._graphs.get(key)
+        if ent is None:
+            fn()                                        # warm-up: buffer allocation, lazily cached constants
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            c0 = lib.launch_count
+            with torch.cuda.graph(g):
+                out = fn()
+            ent = (g, out, lib.launch_count - c0)
+            self._graphs[key] = ent
+        g, out, launches = ent
+        g.replay()
+        lib._count(launches)
+        return out

@@ -86,6 +86,7 @@ SYMBOLS = {
     "cm2_maskiou_prep": (_I, [_P, _AP, _I, _P]),
     "cm2_maskiou_score": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "cm2_scale_clip_boxes": (_I, [_P, _P, _P, _I, _F, _F, _F, _F, _P]),
+    "cm2_scale_clip_boxes_batch": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "cm2_paste_masks": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
 }
 
@@ -345,6 +346,12 @@ def maskiou_score(iou, r, ncls, classes, scores, mask_scores):
 def scale_clip_boxes(boxes_in, boxes_out, valid, r, sx, sy, out_w, out_h):
     check(load().cm2_scale_clip_boxes(ptr(boxes_in), ptr(boxes_out), ptr(valid), r, sx, sy, out_w, out_h, stream()),
           "cm2_scale_clip_boxes")
+    _count()
+
+
+def scale_clip_boxes_batch(boxes_in, boxes_out, valid, n, r_cap, params):
+    check(load().cm2_scale_clip_boxes_batch(ptr(boxes_in), ptr(boxes_out), ptr(valid), n, r_cap, ptr(params), stream()),
+          "cm2_scale_clip_boxes_batch")
     _count()
 
 

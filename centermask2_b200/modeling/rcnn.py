@@ -56,52 +56,65 @@ class GeneralizedRCNN(nn.Module):
         paste-back; one D2H copy of the detection counts / box validity then cuts out the per-image
         ``Instances`` (slices, no per-field gathers unless a box became empty after clipping)."""
         eng = runtime.engine_for(self.cfg)
-        images = [b["image"].to(eng.device, non_blocking=True) for b in batched_inputs]
-        x, sizes = eng.preprocess(images, self.backbone.size_divisibility)
-        feats = self.backbone.forward_fmap(x)
+        n = len(batched_inputs)
+        sizes = [(int(b["image"].shape[-2]), int(b["image"].shape[-1])) for b in batched_inputs]
         roi = self.roi_heads
         if detected_instances is not None:
+            images = [b["image"].to(eng.device, non_blocking=True) for b in batched_inputs]
+            x, _ = eng.preprocess(images, self.backbone.size_divisibility)
+            feats = self.backbone.forward_fmap(x)
             results = [i.to(eng.device) for i in detected_instances]
             results = roi.forward_with_given_boxes({k: v.nchw() for k, v in feats.items()}, results)
             if not do_postprocess:
                 return results
             return [{"instances": self.detector_postprocess(inst, b.get("height", sz[0]), b.get("width", sz[1]))}
                     for inst, b, sz in zip(results, batched_inputs, sizes)]
+        out_sizes = [(int(b.get("height", sz[0])), int(b.get("width", sz[1]))) for b, sz in zip(batched_inputs, sizes)]
+        # inputs land in engine-owned buffers (static addresses: the launch plan below is replayed as a CUDA graph)
+        sig = tuple((tuple(b["image"].shape), b["image"].dtype) for b in batched_inputs)
+        images = [eng.buffer("input_image{}".format(i), shp, dt, zero=False) for i, (shp, dt) in enumerate(sig)]
+        for dst, b in zip(images, batched_inputs):
+            dst.copy_(b["image"], non_blocking=True)
         fcos = self.proposal_generator
-        det = fcos.detect([feats[f] for f in fcos.in_features])
-        n, r_cap = det["boxes"].shape[0], det["boxes"].shape[1]
-        probs = mask_scores = None
-        if roi.mask_on:
-            probs, mask_scores = roi.run([feats[f] for f in roi.in_features], det, sizes)
+
+        def plan():
+            x, _ = eng.preprocess(images, self.backbone.size_divisibility)
+            feats = self.backbone.forward_fmap(x)
+            det = fcos.detect([feats[f] for f in fcos.in_features])
+            probs = mask_scores = boxes = valid = None
+            if roi.mask_on:
+                probs, mask_scores = roi.run([feats[f] for f in roi.in_features], det, sizes)
+            if do_postprocess:
+                boxes, valid = eng.rescale_boxes(det["boxes"], sizes, out_sizes)
+            return det, probs, mask_scores, boxes, valid
+
+        det, probs, mask_scores, boxes, valid = eng.graphed(("inference", sig, tuple(out_sizes), bool(do_postprocess)), plan)
+        r_cap = det["boxes"].shape[1]
         # one snapshot of the small per-detection tensors (the engine reuses its buffers on the next call)
         scores, classes, locs = det["scores"].clone(), det["classes"].clone(), det["locations"].clone()
         mscores = mask_scores.reshape(n, r_cap).clone() if mask_scores is not None else None
-        from .. import lib
+        h_count = eng.pinned("h_count", (n,), torch.int32)
+        h_cand = eng.pinned("h_cand", tuple(det["cand_count"].shape), torch.int32)
+        h_count.copy_(det["count"], non_blocking=True)
+        h_cand.copy_(det["cand_count"], non_blocking=True)
         if do_postprocess:
-            out_sizes = [(b.get("height", sz[0]), b.get("width", sz[1])) for b, sz in zip(batched_inputs, sizes)]
-            boxes = torch.empty_like(det["boxes"])
-            valid = torch.empty((n, r_cap), dtype=torch.uint8, device=eng.device)
-            masks = []
-            for i, ((oh, ow), sz) in enumerate(zip(out_sizes, sizes)):
-                lib.scale_clip_boxes(det["boxes"][i], boxes[i], valid[i], r_cap, ow / sz[1], oh / sz[0], float(ow), float(oh))
-                if probs is not None:
-                    m = torch.empty((r_cap, oh, ow), dtype=torch.bool, device=eng.device)      # kernel writes 0/1 bytes
-                    lib.paste_masks(probs[i * r_cap:(i + 1) * r_cap], boxes[i], valid[i], m, r_cap, probs.shape[-1], oh, ow, 0.5)
-                    masks.append(m)
-            valid_h = valid.cpu()
+            boxes = boxes.clone()
+            h_valid = eng.pinned("h_valid", (n, r_cap), torch.uint8)
+            h_valid.copy_(valid, non_blocking=True)
+            masks = eng.paste_batch(probs, boxes, valid, out_sizes, dtype=torch.bool) if probs is not None else None
         else:
             boxes = det["boxes"].clone()
             pm = probs.clone() if probs is not None else None
-        counts = det["count"].tolist()
-        over = bool((det["cand_count"] > det["cand_cap"]).any().item())
-        if over:
+        torch.cuda.current_stream(eng.device).synchronize()
+        counts = h_count.tolist()
+        if bool((h_cand > det["cand_cap"]).any()):
             raise RuntimeError("FCOS candidate buffer overflow (> {} candidates above threshold in one level)".format(det["cand_cap"]))
         total = sum(counts)
         out = []
         for i, k in enumerate(counts):
             sel = slice(0, k)
             if do_postprocess:
-                v = valid_h[i, :k]
+                v = h_valid[i, :k]
                 if not bool(v.all()):
                     sel = torch.nonzero(v).squeeze(1).to(eng.device)
                 inst = Instances(tuple(out_sizes[i]))

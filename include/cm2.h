@@ -279,6 +279,9 @@ int cm2_maskiou_score(const void* iou, int32_t dtype, int32_t r, int32_t ncls, c
  * ------------------------------------------------------------------------------------------- */
 int cm2_scale_clip_boxes(const float* boxes_in, float* boxes_out, uint8_t* valid, int32_t r, float sx,
                          float sy, float out_w, float out_h, void* stream);
+/* Whole batch in one launch: boxes [n][r_cap][4]; params [n][4] = (sx, sy, out_w, out_h) in DEVICE memory. */
+int cm2_scale_clip_boxes_batch(const float* boxes_in, float* boxes_out, uint8_t* valid, int32_t n, int32_t r_cap,
+                               const float* params, void* stream);
 int cm2_paste_masks(const float* probs, const float* boxes, const uint8_t* valid, uint8_t* out,
                     int32_t r, int32_t m, int32_t out_h, int32_t out_w, float threshold, void* stream);
 

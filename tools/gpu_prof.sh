@@ -6,6 +6,6 @@ timeout 600 python bench.py --precision bf16 --batch $B --steps 3 --warmup 3 --n
 tail -1 gpurun_out/bench_prof.log | cut -c1-400
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_b$B.csv python bench.py --precision bf16 --batch $B --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 30 -c 4 -o gpurun_out/prof_conv_tc -f python bench.py --precision bf16 --batch $B --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 300 -c 3 -o gpurun_out/prof_conv_tc -f python bench.py --precision bf16 --batch $B --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit $?"
 ls -la gpurun_out
