@@ -286,7 +286,7 @@ extern "C" int cm2_conv2d(const cm2_conv_desc* d, void* stream) {
                   ho, wo);
   }
   if (d->engine == CM2_ENGINE_SIMT) {
-    CM2_CHECK_ARG(d->chan_sum == nullptr, "conv2d: chan_sum needs the TC engine");
+    CM2_CHECK_ARG(d->stats == nullptr, "conv2d: fused statistics need the TC engine");
     if (d->src_phase || d->out_mode == 2) {
       set_error("conv2d: phase-split layouts need the TC engine");
       return CM2_ERR_UNSUPPORTED;

@@ -27,7 +27,7 @@ namespace cm2 {
 
 constexpr int TC_BM = 128;          // rows per tile (UMMA M)
 constexpr int TC_BK = 64;           // bf16 channels per K-block = 128 bytes = one swizzle row
-constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_THREADS = 320;   // 2 control warps + 8 epilogue warps
 constexpr int TC_ACC_COLS = 256;    // TMEM columns per accumulator stage
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;
 
@@ -67,6 +67,11 @@ struct alignas(64) TcParams {
   int num_seg;              // > 0: segmented halo tensor (several maps of different extent in one flat buffer)
   int seg_row0[CM2_MAX_SEG], seg_rows[CM2_MAX_SEG], seg_pitch[CM2_MAX_SEG], seg_plane[CM2_MAX_SEG];
   int seg_h[CM2_MAX_SEG], seg_w[CM2_MAX_SEG];
+  double* stats;            // fused output statistics (see cm2_conv_desc.stats_mode); nullptr: off
+  int stats_mode;           // 1: per (image, channel) sum;  2: per (image, 8-channel chunk) sum and sum of squares
+  int stats_stride;         // doubles per image
+  int seg_img0[CM2_MAX_SEG];// global image index of the first image of every segment
+  int epi_sets;             // column sets of epilogue warps per 128-row accumulator (1, 2 or 4)
   int fast_store;           // 1: epilogue transposes through shared memory and writes 64-byte row segments
   int dbg;                  // tuning experiments (CM2_TC_DEBUG): 1 no epilogue stores, 2 no TMA loads, 4 no MMAs
   int variant;              // host only: 1 = conv_tc_kernel (128-row tiles), 2 = conv_tc2_kernel
@@ -154,18 +159,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 
 // Geometry of the map a tile belongs to (segments start at multiples of 256 rows, so a tile never straddles two).
-struct TileGeom { int row0, rows, pitch, plane, h, w; };
+struct TileGeom { int row0, rows, pitch, plane, h, w, img0; };
 __device__ __forceinline__ TileGeom tc_geom(const TcParams& p, int m0) {
   TileGeom g;
   if (p.num_seg == 0) {
-    g.row0 = 0; g.rows = p.rows; g.pitch = p.pitch; g.plane = p.plane; g.h = p.h; g.w = p.w;
+    g.row0 = 0; g.rows = p.rows; g.pitch = p.pitch; g.plane = p.plane; g.h = p.h; g.w = p.w; g.img0 = 0;
   } else {
     int s = 0;
 #pragma unroll
     for (int i = 1; i < CM2_MAX_SEG; ++i)
       if (i < p.num_seg && m0 >= p.seg_row0[i]) s = i;
     g.row0 = p.seg_row0[s]; g.rows = p.seg_rows[s]; g.pitch = p.seg_pitch[s]; g.plane = p.seg_plane[s];
-    g.h = p.seg_h[s]; g.w = p.seg_w[s];
+    g.h = p.seg_h[s]; g.w = p.seg_w[s]; g.img0 = p.seg_img0[s];
   }
   return g;
 }
@@ -311,6 +316,93 @@ __device__ __forceinline__ void tc_epilogue_rows(const TcParams& p, const TileGe
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused output statistics (staged epilogue only).  v[0..31] = this row's 32 stored values of the pass (zeros for
+// halo / out-of-range rows).  Rows of a warp usually belong to one image; the loop handles tiles that straddle
+// images.  Values are reduced across the warp with a halving butterfly (each exchange halves the number of live
+// values), then added to the fp64 accumulators -- fp64 keeps the result independent of the atomic order to ~1e-16,
+// i.e. bit-identical after the consumer's conversion to fp32.
+//   mode 1 (eSE pool, vovnet.py:254): stats[img][c]         += sum over pixels
+//   mode 2 (GroupNorm, fcos.py:182):  stats[img][c/8][2]    += (sum, sum of squares) over pixels x 8 channels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_epilogue_stats(const TcParams& p, const float (&v)[32], unsigned rows, bool interior,
+                                                  int img_g, int co0, int ncol, int lane) {
+  while (rows) {                                     // warp-uniform
+    const int leader = __ffs(rows) - 1;
+    const int li = __shfl_sync(0xffffffffu, img_g, leader);
+    const bool mine = interior && img_g == li;
+    rows &= ~__ballot_sync(0xffffffffu, mine);
+    if (p.stats_mode == 2) {
+      float r[8];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        float sa = 0.f, sq = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float x = mine ? v[8 * ch + k] : 0.f; sa += x; sq = fmaf(x, x, sq); }
+        r[2 * ch] = sa; r[2 * ch + 1] = sq;
+      }
+      // 8 -> 4 -> 2 -> 1 live values over lane bits 4, 3, 2; then a plain sum over bits 1, 0
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool up = lane & 16;
+        const float keep = up ? r[i + 4] : r[i], send = up ? r[i] : r[i + 4];
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const bool up = lane & 8;
+        const float keep = up ? r[i + 2] : r[i], send = up ? r[i] : r[i + 2];
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      {
+        const bool up = lane & 4;
+        const float keep = up ? r[1] : r[0], send = up ? r[0] : r[1];
+        r[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      r[0] += __shfl_xor_sync(0xffffffffu, r[0], 2);
+      r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
+      const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);    // value index = chunk * 2 + {sum, sq}
+      if ((lane & 3) == 0 && (k >> 1) * 8 < ncol)
+        atomicAdd(p.stats + (size_t)li * p.stats_stride + (size_t)((co0 >> 3) + (k >> 1)) * 2 + (k & 1), (double)r[0]);
+    } else {
+      float r[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) r[k] = mine ? v[k] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const bool up = lane & 16;
+        const float keep = up ? r[i + 16] : r[i], send = up ? r[i] : r[i + 16];
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool up = lane & 8;
+        const float keep = up ? r[i + 8] : r[i], send = up ? r[i] : r[i + 8];
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool up = lane & 4;
+        const float keep = up ? r[i + 4] : r[i], send = up ? r[i] : r[i + 4];
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const bool up = lane & 2;
+        const float keep = up ? r[i + 2] : r[i], send = up ? r[i] : r[i + 2];
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      {
+        const bool up = lane & 1;
+        const float keep = up ? r[1] : r[0], send = up ? r[0] : r[1];
+        r[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+      // lane now holds the column sum of channel index (bit4,bit3,bit2,bit1,bit0) = lane
+      if (lane < ncol) atomicAdd(p.stats + (size_t)li * p.stats_stride + (size_t)(co0 + lane), (double)r[0]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Coalescing epilogue.  In the TMEM register layout a thread owns one output ROW, so direct stores make
 // every warp instruction touch 32 different rows 16 bytes at a time (measured: the stores alone cost as
 // much as all MMAs of a 3x3 256->256 layer).  Here each pass moves a [32 rows x 64 bytes] block through
@@ -321,8 +413,18 @@ __device__ __forceinline__ void tc_epilogue_rows(const TcParams& p, const TileGe
 constexpr uint32_t EPI_PITCH = 80;                  // bytes per staged row (64 payload + 16 pad)
 constexpr uint32_t EPI_WARP_BYTES = 32 * EPI_PITCH;
 
+// two fp32 FMAs in one instruction (FFMA2)
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+
+// The epilogue warps of one 128-row accumulator are organised in `ncset` column sets (one warp per TMEM lane quarter
+// and set); set `cset` handles every ncset-th 64-byte column pass.  Several warps per scheduler hide the
+// tcgen05.ld -> FMA -> st.shared -> ld.shared -> st.global dependency chain, which is what bounds short-K layers.
 __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const TileGeom& g, uint32_t taddr, int m, int n0,
-                                                        uint32_t stage_smem, int lane, uint32_t ss_smem) {
+                                                        uint32_t stage_smem, int lane, uint32_t ss_smem, int cset, int ncset) {
   const int mr = m - g.row0;
   bool in_range = mr >= 0 && mr < g.rows, interior = false;
   int img = 0, y = 0, x = 0;
@@ -349,12 +451,41 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
   else
     out_off = (long long)((y & 1) * 2 + (x & 1)) * p.out_plane + (long long)img * p.out_sn +
               (long long)(y >> 1) * p.out_sh + (long long)(x >> 1) * p.out_sw;
+  const __nv_bfloat16* res_row = nullptr;
+  if (p.res_mode && interior)
+    res_row = p.res + (long long)img * p.res_sn + (long long)(p.res_mode == 2 ? (y >> 1) : y) * p.res_sh +
+              (long long)(p.res_mode == 2 ? (x >> 1) : x) * p.res_sw;
   const unsigned store_mask = __ballot_sync(0xffffffffu, do_store);      // rows of this warp that get written
+  const unsigned int_mask = __ballot_sync(0xffffffffu, interior);
+  const bool all_int = int_mask == 0xffffffffu;
+  const unsigned stat_rows = p.stats_mode ? int_mask : 0u;
+  const int img_g = img + g.img0;                    // image index across segments (statistics slot)
+  const int esize = p.out_f32 ? 4 : 2;
   const int cpp = p.out_f32 ? 16 : 32;               // channels per pass = 64 bytes per row
   const uint32_t my_row = stage_smem + (uint32_t)lane * EPI_PITCH;
-  for (int c0 = 0; c0 < p.bn; c0 += cpp) {
+  // write-back role of this lane: rows it*8 + lane/4, 16-byte piece lane%4 -- row addresses are fixed for the tile
+  char* wptr[4];
+  bool wok[4];
+  uint32_t wsm[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 8 + (lane >> 2);
+    const long long roff = __shfl_sync(0xffffffffu, out_off, row);
+    wptr[it] = reinterpret_cast<char*>(p.out) + roff * esize + 16 * (lane & 3);
+    wok[it] = (store_mask >> row) & 1u;
+    wsm[it] = stage_smem + (uint32_t)row * EPI_PITCH + 16u * (uint32_t)(lane & 3);
+  }
+  for (int c0 = cset * cpp; c0 < p.bn; c0 += ncset * cpp) {
     const int co0 = n0 + c0;
     float v[32];
+    uint4 rres[4];
+    const bool has_res = res_row != nullptr && co0 < p.cout;
+    if (has_res) {                                     // issue the residual loads before waiting on TMEM
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (8 * j < cpp && co0 + 8 * j < p.cout) rres[j] = __ldg(reinterpret_cast<const uint4*>(res_row + co0 + 8 * j));
+        else rres[j] = make_uint4(0u, 0u, 0u, 0u);
+    }
     {
       uint32_t raw[16];
       __syncwarp();
@@ -378,32 +509,55 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
     for (int j4 = 0; j4 < 8; ++j4) {
       if (4 * j4 < cpp && c0 + 4 * j4 < p.bn) {
         const float4 sc = lds_f4(ss_smem + 4u * (uint32_t)(c0 + 4 * j4)), sh = lds_f4(ss_smem + 1024u + 4u * (uint32_t)(c0 + 4 * j4));
-        float a0 = fmaf(v[4 * j4 + 0], sc.x, sh.x), a1 = fmaf(v[4 * j4 + 1], sc.y, sh.y);
-        float a2 = fmaf(v[4 * j4 + 2], sc.z, sh.z), a3 = fmaf(v[4 * j4 + 3], sc.w, sh.w);
-        if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
-        v[4 * j4 + 0] = interior ? a0 : 0.f; v[4 * j4 + 1] = interior ? a1 : 0.f;
-        v[4 * j4 + 2] = interior ? a2 : 0.f; v[4 * j4 + 3] = interior ? a3 : 0.f;
+        ffma2(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 0], v[4 * j4 + 1], sc.x, sc.y, sh.x, sh.y);
+        ffma2(v[4 * j4 + 2], v[4 * j4 + 3], v[4 * j4 + 2], v[4 * j4 + 3], sc.z, sc.w, sh.z, sh.w);
+      }
+    }
+    if (has_res) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (8 * j < cpp) {
+          const uint32_t w[4] = {rres[j].x, rres[j].y, rres[j].z, rres[j].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[8 * j + 2 * i] += __uint_as_float(w[i] << 16);
+            v[8 * j + 2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+          }
+        }
       }
     }
     // ---- stage this thread's 64 bytes
     if (p.out_f32) {
 #pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (p.relu) v[j] = fmaxf(v[j], 0.f);
+        if (!all_int) v[j] = interior ? v[j] : 0.f;
+      }
+#pragma unroll
       for (int j = 0; j < 4; ++j)
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + 16u * j), "f"(v[4 * j]), "f"(v[4 * j + 1]),
                      "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
     } else {
+      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+          if (p.relu) h2 = __hmax2(h2, zero2);         // max(round(x), 0) == round(max(x, 0))
           w[i] = *reinterpret_cast<uint32_t*>(&h2);
+          if (!all_int) w[i] = interior ? w[i] : 0u;
+          if (p.stats_mode) {                        // statistics of the values as stored (bf16-rounded)
+            v[8 * j + 2 * i] = __uint_as_float(w[i] << 16);
+            v[8 * j + 2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+          }
         }
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + 16u * j), "r"(w[0]), "r"(w[1]), "r"(w[2]),
                      "r"(w[3]) : "memory");
       }
     }
+    if (p.stats_mode) tc_epilogue_stats(p, v, stat_rows, interior, img_g, co0, min(p.bn - c0, p.cout - co0), lane);
     __syncwarp();
     // ---- write back: 4 instructions x (8 rows x 64 bytes)
     long long extra = 0;
@@ -414,20 +568,17 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
       cc = co0 - quad * cq;
       extra = (long long)(quad >> 1) * p.out_sh + (long long)(quad & 1) * p.out_sw;
     }
+    const long long col_bytes = (extra + cc) * esize;
     const int elems16 = p.out_f32 ? 4 : 8;           // elements per 16-byte piece
     // 16-byte pieces of this pass that belong to this tile (bn need not be a multiple of the pass width) and to cout
     const int valid_pieces = min(4, (min(p.bn - c0, p.cout - co0) + elems16 - 1) / elems16);
+    const bool piece_ok = (lane & 3) < valid_pieces;
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
-      const int row = it * 8 + (lane >> 2), piece = lane & 3;
-      const long long roff = __shfl_sync(0xffffffffu, out_off, row);
       uint4 val;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
-                   : "r"(stage_smem + (uint32_t)row * EPI_PITCH + 16u * piece) : "memory");
-      if (((store_mask >> row) & 1u) && piece < valid_pieces) {
-        char* dst = reinterpret_cast<char*>(p.out) + ((roff + extra + cc) * (p.out_f32 ? 4 : 2)) + 16 * piece;
-        *reinterpret_cast<uint4*>(dst) = val;
-      }
+                   : "r"(wsm[it]) : "memory");
+      if (wok[it] && piece_ok) *reinterpret_cast<uint4*>(wptr[it] + col_bytes) = val;
     }
   }
   __syncwarp();
@@ -436,7 +587,7 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 2;
@@ -448,8 +599,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
-  const uint32_t epi_base = (tmem_slot + 16u + 15u) & ~15u;       // 4 x EPI_WARP_BYTES of staging
-  const uint32_t ss_base = epi_base + 4u * EPI_WARP_BYTES;         // EPI_SS_BYTES of scale/shift
+  const int n_epi_warps = 4 * p.epi_sets;
+  const uint32_t epi_base = (tmem_slot + 16u + 15u) & ~15u;       // n_epi_warps x EPI_WARP_BYTES of staging
+  const uint32_t ss_base = epi_base + (uint32_t)n_epi_warps * EPI_WARP_BYTES;         // EPI_SS_BYTES of scale/shift
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -458,7 +610,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&p.a_map[s]);
     tma_prefetch_desc(&p.b_map);
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (uint32_t)n_epi_warps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -543,15 +695,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint32_t parity = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, parity ^= 1u) {
       const int m0 = (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.bn;
-      const uint32_t ss = ss_base + parity * 2048u;
-      tc_stage_scale_shift(p, ss, n0, (int)threadIdx.x - 64, 128);      // overlaps the MMAs of this tile
+      // scale / shift of the tile's columns: staged once when there is a single N tile, else per tile (double buffered)
+      const uint32_t ss = ss_base + (p.n_tiles == 1 ? 0u : parity * 2048u);
+      if (p.n_tiles > 1 || t == (int)blockIdx.x)
+        tc_stage_scale_shift(p, ss, n0, (int)threadIdx.x - 64, 32 * n_epi_warps);      // overlaps the MMAs of this tile
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * TC_ACC_COLS) + ((uint32_t)(q * 32) << 16);
       const TileGeom g = tc_geom(p, m0);
+      const int cset = (warp - 2) >> 2;
       if (p.fast_store)
-        tc_epilogue_rows_staged(p, g, taddr, m0 + q * 32 + lane, n0, epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES, lane, ss);
-      else
+        tc_epilogue_rows_staged(p, g, taddr, m0 + q * 32 + lane, n0, epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES, lane, ss,
+                                cset, p.epi_sets);
+      else if (cset == 0)
         tc_epilogue_rows(p, g, taddr, m0 + q * 32 + lane, n0, ss);
       tc_fence_before();
       __syncwarp();
@@ -578,7 +734,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 //     MMA A-descriptor simply starts 0, 1 or 2 rows (128 B each) into it -- A traffic drops 3x.
 // Warps: 0 = TMA producer, 1 = TMEM alloc + MMA issue, 2..9 = epilogue (warps 2-5: rows 0-127, 6-9: 128-255).
 // ------------------------------------------------------------------------------------------------
-constexpr int TC2_THREADS = 320;
 
 __device__ __forceinline__ uint64_t umma_desc_sw128_at(uint32_t smem_addr, int desc_mode) {
   uint64_t d = umma_desc_sw128(smem_addr);
@@ -586,7 +741,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_at(uint32_t smem_addr, int d
   return d;
 }
 
-__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc2_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_half_bytes = (uint32_t)p.a_box_rows * 128u;
@@ -602,8 +757,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
   auto tfull_bar = [&](int a) { return tbar + 8u * a; };
   auto tempty_bar = [&](int a) { return tbar + 8u * (2 + a); };
   const uint32_t tmem_slot = tbar + 8u * 4;
-  const uint32_t epi_base = (tmem_slot + 16u + 15u) & ~15u;       // 8 x EPI_WARP_BYTES of staging
-  const uint32_t ss_base = epi_base + 8u * EPI_WARP_BYTES;         // EPI_SS_BYTES of scale/shift
+  const int n_epi_warps = 8 * p.epi_sets;
+  const uint32_t epi_base = (tmem_slot + 16u + 15u) & ~15u;       // n_epi_warps x EPI_WARP_BYTES of staging
+  const uint32_t ss_base = epi_base + (uint32_t)n_epi_warps * EPI_WARP_BYTES;         // EPI_SS_BYTES of scale/shift
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -615,7 +771,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
     tma_prefetch_desc(&p.b_map);
     for (int s = 0; s < p.sa_stages; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
     for (int s = 0; s < p.sb_stages; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (uint32_t)n_epi_warps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -718,21 +874,24 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
   } else {
     // ===================================== epilogue =========================================
     const int q = warp & 3;
-    const int half = warp >= 6 ? 1 : 0;
+    const int half = ((warp - 2) >> 2) & 1;            // warps 2-5 / 10-13: rows 0-127, warps 6-9 / 14-17: rows 128-255
+    const int cset = (warp - 2) >> 3;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t parity = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, parity ^= 1u) {
       const int m0 = (t / p.n_tiles) * 256, n0 = (t % p.n_tiles) * p.bn;
-      const uint32_t ss = ss_base + parity * 2048u;
-      tc_stage_scale_shift(p, ss, n0, (int)threadIdx.x - 64, 256);
+      const uint32_t ss = ss_base + (p.n_tiles == 1 ? 0u : parity * 2048u);
+      if (p.n_tiles > 1 || t == (int)blockIdx.x)
+        tc_stage_scale_shift(p, ss, n0, (int)threadIdx.x - 64, 32 * n_epi_warps);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * 2 * half_cols + half * half_cols) + ((uint32_t)(q * 32) << 16);
       const TileGeom tg = tc_geom(p, m0);
       if (p.fast_store)
-        tc_epilogue_rows_staged(p, tg, taddr, m0 + half * 128 + q * 32 + lane, n0, epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES, lane, ss);
-      else
+        tc_epilogue_rows_staged(p, tg, taddr, m0 + half * 128 + q * 32 + lane, n0, epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES, lane, ss,
+                                cset, p.epi_sets);
+      else if (cset == 0)
         tc_epilogue_rows(p, tg, taddr, m0 + half * 128 + q * 32 + lane, n0, ss);
       tc_fence_before();
       __syncwarp();
@@ -830,7 +989,8 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     TC_REQUIRE(d->stride == 1 && d->kh == d->kw && ((d->kh == 1 && d->pad == 0) || (d->kh == 3 && d->pad == 1)),
                "conv_tc: only stride-1 1x1/p0 and 3x3/p1, or 3x3/s2/p1 on phase-split sources (got k%d s%d p%d)", d->kh,
                d->stride, d->pad);
-  TC_REQUIRE(!d->in_relu && !d->chan_sum, "conv_tc: in_relu / chan_sum not supported");
+  TC_REQUIRE(!d->in_relu, "conv_tc: in_relu not supported");
+  TC_REQUIRE(!d->stats || d->stats_mode == 1 || d->stats_mode == 2, "conv_tc: stats_mode must be 1 or 2");
   const bool seg = d->num_seg > 0;
   if (seg)
     TC_REQUIRE(d->num_seg <= CM2_MAX_SEG && !phase && d->out_mode == 0 && !d->residual.data,
@@ -862,6 +1022,7 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
       TC_REQUIRE(g.row0 + srows < (1ll << 31) - 4096, "conv_tc: segment %d out of range", i);
       p->seg_row0[i] = (int)g.row0; p->seg_rows[i] = (int)srows; p->seg_pitch[i] = g.w + 2;
       p->seg_plane[i] = (g.h + 2) * (g.w + 2); p->seg_h[i] = g.h; p->seg_w[i] = g.w;
+      p->seg_img0[i] = i ? p->seg_img0[i - 1] + d->seg[i - 1].n : 0;
       rows = g.row0 + srows;
     }
     p->h = p->w = p->pitch = p->plane = 0;
@@ -904,11 +1065,17 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   bool use_v2 = m_tiles256 * (cout_pad / bn2) >= sms && ((merge_ok && bn2 <= 128) || (p->taps == 1 && k_total <= 512));
   if (env_variant == 1) use_v2 = false;
   if (env_variant >= 2) use_v2 = true;
-  const size_t tail_v1 = 8 * (2 * 8 + 4) + 48 + 4 * EPI_WARP_BYTES + EPI_SS_BYTES;
-  const size_t tail_v2 = 8 * (2 * 6 + 2 * 9 + 4) + 48 + 8 * EPI_WARP_BYTES + EPI_SS_BYTES;
+  static const int env_sets1 = getenv("CM2_TC_EPI_SETS_V1") ? atoi(getenv("CM2_TC_EPI_SETS_V1")) : 2;
+  static const int env_sets2 = getenv("CM2_TC_EPI_SETS_V2") ? atoi(getenv("CM2_TC_EPI_SETS_V2")) : 1;
+  const int sets1 = env_sets1 == 1 ? 1 : 2;            // 64 + 128 * sets1 <= TC_MAX_THREADS
+  const int sets2 = 1;                                 // 64 + 256 * sets2 <= TC_MAX_THREADS
+  (void)env_sets2;
+  const size_t tail_v1 = 8 * (2 * 8 + 4) + 48 + 4 * sets1 * EPI_WARP_BYTES + EPI_SS_BYTES;
+  const size_t tail_v2 = 8 * (2 * 6 + 2 * 9 + 4) + 48 + 8 * sets2 * EPI_WARP_BYTES + EPI_SS_BYTES;
   const size_t smem_max = 227u * 1024u - 1024u;          // minus the 1 KB alignment slack
   if (use_v2) {
     p->variant = 2;
+    p->epi_sets = sets2;
     p->bn = bn2;
     p->m_tiles = m_tiles256;
     p->n_tiles = (cout_pad + p->bn - 1) / p->bn;
@@ -928,6 +1095,7 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     p->smem_bytes = (unsigned)(1024 + p->sa_stages * a_slab + p->sb_stages * b_bytes + tail_v2);
   } else {
     p->variant = 1;
+    p->epi_sets = sets1;
     p->m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
     p->bn = pick_bn(cout_pad, p->m_tiles, sms);
     p->n_tiles = (cout_pad + p->bn - 1) / p->bn;
@@ -964,7 +1132,14 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
       p->out_vec = 0;
   }
   static const int env_store = getenv("CM2_TC_FAST_STORE") ? atoi(getenv("CM2_TC_FAST_STORE")) : 1;
-  p->fast_store = (env_store && p->out_vec && !p->res_mode && (d->out_mode != 1 || (d->cout / 4) % 32 == 0)) ? 1 : 0;
+  p->fast_store = (env_store && p->out_vec && (d->out_mode != 1 || (d->cout / 4) % 32 == 0)) ? 1 : 0;
+  if (d->stats) {
+    TC_REQUIRE(p->fast_store && !p->out_f32 && d->out_mode == 0 && d->cout % 8 == 0,
+               "conv_tc: fused statistics need a bf16 out_mode-0 output without residual, cout %% 8 == 0");
+    p->stats = reinterpret_cast<double*>(d->stats);
+    p->stats_mode = d->stats_mode;
+    p->stats_stride = d->stats_mode == 1 ? d->cout : (d->cout / 8) * 2;
+  }
 #undef TC_REQUIRE
   if (!maps) return CM2_OK;
   for (int i = 0; i < d->num_src; ++i) {
@@ -996,12 +1171,23 @@ int conv_tc_launch(const cm2_conv_desc* d, cudaStream_t stream) {
     cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   }
+  if (p.stats) {
+    long long imgs = d->src[0].n;
+    if (d->num_seg > 0) {
+      imgs = 0;
+      for (int i = 0; i < d->num_seg; ++i) imgs += d->seg[i].n;
+    }
+    if (cudaMemsetAsync(p.stats, 0, (size_t)imgs * p.stats_stride * sizeof(double), stream) != cudaSuccess) {
+      set_error("conv_tc: cudaMemsetAsync(stats) failed");
+      return CM2_ERR_CUDA;
+    }
+  }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sms ? tiles : sms;
   if (p.variant == 2)
-    conv_tc2_kernel<<<grid, TC2_THREADS, p.smem_bytes, stream>>>(p);
+    conv_tc2_kernel<<<grid, 64 + 256 * p.epi_sets, p.smem_bytes, stream>>>(p);
   else
-    conv_tc_kernel<<<grid, TC_THREADS, p.smem_bytes, stream>>>(p);
+    conv_tc_kernel<<<grid, 64 + 128 * p.epi_sets, p.smem_bytes, stream>>>(p);
   CM2_CHECK_LAUNCH("conv_tc");
   return CM2_OK;
 }

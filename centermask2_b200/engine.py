@@ -178,7 +178,7 @@ class Engine(object):
 
     # -- one convolution -------------------------------------------------------------------------
     def conv(self, name, srcs, w, out_dtype=None, residual=None, res_mode=0, out_mode=0, in_relu=False,
-             out_halo=1, chan_sum=None, out=None):
+             out_halo=1, stats=None, stats_mode=0, out=None):
         """One convolution.  ``srcs`` are FMaps (virtual concat) or, for a stride-2 conv on the TC engine,
         PhaseMaps.  ``out_mode`` 1 = deconv scatter, 2 = write the result as a PhaseMap."""
         x0 = srcs[0]
@@ -201,9 +201,9 @@ class Engine(object):
         kw = dict(scale=w.scale, shift=w.shift, relu=w.relu, in_relu=in_relu, src_phase=src_phase,
                   residual=None if residual is None else residual.view, res_mode=res_mode, out_mode=out_mode)
         if self.tc and w.w_tc is not None and lib.conv2d(views, w.w_tc, out.view, w.cout, w.k, w.stride, w.pad,
-                                                          engine=lib.ENGINE_TC, chan_sum=chan_sum, probe=True, **kw):
+                                                          engine=lib.ENGINE_TC, stats=stats, stats_mode=stats_mode, probe=True, **kw):
             return out
-        assert chan_sum is None, "chan_sum requires the tensor-core engine"
+        assert stats is None, "fused statistics require the tensor-core engine: " + lib.last_error()
         lib.conv2d(views, w.w_simt, out.view, w.cout, w.k, w.stride, w.pad, engine=lib.ENGINE_SIMT, **kw)
         return out
 
@@ -211,14 +211,14 @@ class Engine(object):
         dt = dtype or self.dtype
         return SegMap(shapes, c, dt, self.device, alloc=lambda shape: self.buffer(name, shape, dt))
 
-    def conv_seg(self, name, x, w, out_dtype=None):
+    def conv_seg(self, name, x, w, out_dtype=None, stats=None, stats_mode=0):
         """One stride-1 convolution over all maps of a SegMap (TC engine); returns a SegMap of the same geometry."""
         dt = out_dtype or self.dtype
         cout_pad = (w.cout + 15) // 16 * 16
         assert cout_pad == w.cout, "segmented conv needs cout % 16 == 0"
         out = x.like(w.cout, dt, lambda shape: self.buffer(name, shape, dt))
         lib.conv2d([x.flat], w.w_tc, out.flat, w.cout, w.k, w.stride, w.pad, scale=w.scale, shift=w.shift, relu=w.relu,
-                   engine=lib.ENGINE_TC, segs=x.segs)
+                   engine=lib.ENGINE_TC, segs=x.segs, stats=stats, stats_mode=stats_mode)
         return out
 
     # =============================================================================================
@@ -265,6 +265,16 @@ class Engine(object):
                     for i in range(cfg.MODEL.FCOS.TOP_LEVELS)]
         return P
 
+    @staticmethod
+    def _pool_extent(h, w):
+        """Output extent of MaxPool2d(3, 2, ceil_mode=True) (vovnet.py:349-350)."""
+        ho, wo = -(-(h - 3) // 2) + 1, -(-(w - 3) // 2) + 1
+        if (ho - 1) * 2 >= h:
+            ho -= 1
+        if (wo - 1) * 2 >= w:
+            wo -= 1
+        return ho, wo
+
     def run_backbone(self, x, P):
         """x: FMap [N, Hp, Wp, 3] (normalised, padded to /32).  Returns {"p3": FMap, ...}."""
         cfg = self.cfg
@@ -281,17 +291,19 @@ class Engine(object):
                 x = self.conv("stem{}".format(i + 1), [x], w)
         stage = 2
         stage_out = {}
-        for b, convs, cat, ese_w, ese_b in P["blocks"]:
+        blocks = P["blocks"]
+        fpn_in = set(cfg.MODEL.FPN.IN_FEATURES)
+        pooled_next = None                                   # next stage's input when the eSE pass already pooled it
+        for bi, (b, convs, cat, ese_w, ese_b) in enumerate(blocks):
             if b.stage != stage:
-                # MaxPool2d(3, 2, ceil_mode=True), vovnet.py:349-350
-                ho, wo = -(-(x.h - 3) // 2) + 1, -(-(x.w - 3) // 2) + 1
-                if (ho - 1) * 2 >= x.h:
-                    ho -= 1
-                if (wo - 1) * 2 >= x.w:
-                    wo -= 1
-                pooled = self.fmap("pool{}".format(b.stage), x.n, ho, wo, x.c)
-                lib.maxpool3x3s2_ceil(x.view, pooled.view)
-                x = pooled
+                if pooled_next is not None:
+                    x, pooled_next = pooled_next, None
+                else:
+                    # MaxPool2d(3, 2, ceil_mode=True), vovnet.py:349-350
+                    ho, wo = self._pool_extent(x.h, x.w)
+                    pooled = self.fmap("pool{}".format(b.stage), x.n, ho, wo, x.c)
+                    lib.maxpool3x3s2_ceil(x.view, pooled.view)
+                    x = pooled
                 stage = b.stage
             identity = x
             feats = [x]
@@ -299,18 +311,35 @@ class Engine(object):
             for i, w in enumerate(convs):
                 y = self.conv("{}_{}".format(b.name, i), [y], w)
                 feats.append(y)
-            agg = self.conv(b.name + "_cat", feats, cat)                       # virtual concat, vovnet.py:324-325
-            # eSE, vovnet.py:247-260 / :327-330
-            n, hw, c = agg.n, agg.h * agg.w, agg.c
-            wsp = self.buffer(b.name + "_esews", (n * lib.ese_pool_chunks(hw) * c,), torch.float32, zero=False)
-            pooled = self.buffer(b.name + "_pool", (n, c), torch.float32, zero=False)
+            n, c = x.n, cat.cout
             gate = self.buffer(b.name + "_gate", (n, c), torch.float32, zero=False)
-            lib.ese_pool(agg.view, wsp, pooled)
-            lib.ese_gate(pooled, 1.0, ese_w, ese_b, gate, n, c)
-            out = self.fmap(b.name + "_out", n, agg.h, agg.w, c)
-            lib.ese_apply(agg.view, gate, identity.view if b.identity else None, out.view)
+            last_of_stage = bi + 1 == len(blocks) or blocks[bi + 1][0].stage != b.stage
+            if self.tc and cat.w_tc is not None:
+                # eSE (vovnet.py:247-260 / :327-330): channel sums from the conv epilogue, gate, then x * gate (+ identity)
+                # fused with the max-pool that opens the next stage
+                sums = self.buffer(b.name + "_sums", (n, c), torch.float64, zero=False)
+                agg = self.conv(b.name + "_cat", feats, cat, stats=sums, stats_mode=1)      # virtual concat, vovnet.py:324-325
+                lib.ese_gate_f64(sums, 1.0 / (agg.h * agg.w), ese_w, ese_b, gate, n, c)
+                want_pool = last_of_stage and bi + 1 < len(blocks) and agg.h >= 3 and agg.w >= 3
+                want_full = not last_of_stage or "stage{}".format(b.stage) in fpn_in or not want_pool
+                out = self.fmap(b.name + "_out", n, agg.h, agg.w, c) if want_full else None
+                if want_pool:
+                    ho, wo = self._pool_extent(agg.h, agg.w)
+                    pooled_next = self.fmap("pool{}".format(b.stage + 1), n, ho, wo, c)
+                lib.ese_apply_pool(agg.view, gate, identity.view if b.identity else None,
+                                   out.view if out is not None else None, pooled_next.view if want_pool else None)
+            else:
+                agg = self.conv(b.name + "_cat", feats, cat)
+                hw = agg.h * agg.w
+                wsp = self.buffer(b.name + "_esews", (n * lib.ese_pool_chunks(hw) * c,), torch.float32, zero=False)
+                pooled = self.buffer(b.name + "_pool", (n, c), torch.float32, zero=False)
+                lib.ese_pool(agg.view, wsp, pooled)
+                lib.ese_gate(pooled, 1.0, ese_w, ese_b, gate, n, c)
+                out = self.fmap(b.name + "_out", n, agg.h, agg.w, c)
+                lib.ese_apply(agg.view, gate, identity.view if b.identity else None, out.view)
             x = out
-            stage_out["stage{}".format(b.stage)] = x
+            if out is not None:
+                stage_out["stage{}".format(b.stage)] = x
         # FPN top-down [d2] (constructed at vovnet.py:547-554)
         res = {}
         prev = None
@@ -412,8 +441,16 @@ class Engine(object):
 
     def _run_fcos_head_seg(self, pyramid, P):
         """All pyramid levels per launch: the towers' weights are shared across levels (fcos.py:227-238)."""
+        n_img = sum(n for _, n, _, _ in pyramid.segs)
+
         def tower(x, units, tag):
             for i, (conv, gn) in enumerate(units):
+                if gn is not None and conv.cout % 256 == 0:
+                    # GroupNorm statistics come out of the conv epilogue (fp64 sums per image and 8-channel chunk)
+                    st = self.buffer("fcos_gnstats_seg", (n_img, conv.cout // 8, 2), torch.float64, zero=False)
+                    x = self.conv_seg("fcos_{}{}_seg".format(tag, i), x, conv, stats=st, stats_mode=2)
+                    lib.groupnorm_apply_seg(x.flat, x.segs, 32, gn[0], gn[1], 1e-5, True, st)
+                    continue
                 x = self.conv_seg("fcos_{}{}_seg".format(tag, i), x, conv)
                 if gn is not None:
                     wsp = self.buffer("fcos_gnws_seg", (lib.gn_seg_workspace_floats(x.segs, x.c, 32),), torch.float32, zero=False)

@@ -39,8 +39,8 @@ class ConvDesc(C.Structure):
                 ("weight", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("relu", C.c_int32), ("in_relu", C.c_int32),
                 ("residual", Act), ("res_mode", C.c_int32), ("out_mode", C.c_int32),
-                ("out", Act), ("chan_sum", C.c_void_p), ("src_phase", C.c_int32), ("num_seg", C.c_int32),
-                ("seg", Seg * MAX_SEG)]
+                ("out", Act), ("stats", C.c_void_p), ("src_phase", C.c_int32), ("num_seg", C.c_int32),
+                ("seg", Seg * MAX_SEG), ("stats_mode", C.c_int32), ("reserved", C.c_int32)]
 
 
 class CandBuffers(C.Structure):
@@ -75,6 +75,9 @@ SYMBOLS = {
     "cm2_groupnorm_relu": (_I, [_AP, _I, _I, _P, _P, _F, _I, _P, _P]),
     "cm2_gn_seg_workspace_floats": (_L, [_I, C.POINTER(Seg), _I, _I]),
     "cm2_groupnorm_relu_seg": (_I, [_P, _I, _I, _I, C.POINTER(Seg), _I, _P, _P, _F, _I, _P, _P]),
+    "cm2_groupnorm_apply_seg": (_I, [_P, _I, _I, _I, C.POINTER(Seg), _I, _P, _P, _F, _I, _P, _P]),
+    "cm2_ese_gate_f64": (_I, [_P, C.c_double, _P, _P, _P, _I, _I, _P]),
+    "cm2_ese_apply_pool": (_I, [_AP, _P, _AP, _AP, _AP, _I, _P]),
     "cm2_relu": (_I, [_AP, _AP, _I, _P]),
     "cm2_fcos_decode": (_I, [_AP, _AP, _I, _F, _F, _I, _I, _I, _I, C.POINTER(CandBuffers), _P]),
     "cm2_fcos_select_workspace": (_L, [_I, _I, _I]),
@@ -161,7 +164,7 @@ def _count(k=1):
 # thin wrappers (one per entry point)
 # ------------------------------------------------------------------------------------------------
 def conv2d(srcs, weight, out, cout, k, stride, pad, scale=None, shift=None, relu=False, in_relu=False,
-           residual=None, res_mode=0, out_mode=0, engine=ENGINE_SIMT, chan_sum=None, probe=False, src_phase=False,
+           residual=None, res_mode=0, out_mode=0, engine=ENGINE_SIMT, stats=None, stats_mode=0, probe=False, src_phase=False,
            segs=None):
     """Enqueue one convolution.  With ``probe=True`` (TC engine) the descriptor is first checked with
     ``cm2_conv_tc_supported``; returns False without launching if the engine does not take it."""
@@ -189,7 +192,8 @@ def conv2d(srcs, weight, out, cout, k, stride, pad, scale=None, shift=None, relu
     d.res_mode = res_mode if residual is not None else 0
     d.out_mode = out_mode
     d.out = flat_act(out) if segs is not None else act(out)
-    d.chan_sum = 0 if chan_sum is None else chan_sum.data_ptr()
+    d.stats = 0 if stats is None else stats.data_ptr()
+    d.stats_mode = stats_mode if stats is not None else 0
     d.src_phase = int(src_phase)
     if probe and not load().cm2_conv_tc_supported(C.byref(d)):
         return False
@@ -274,6 +278,25 @@ def groupnorm_relu_seg(flat, segs, groups, gamma, beta, eps, relu, workspace):
                                         ptr(gamma), ptr(beta), eps, int(relu), ptr(workspace), stream()),
           "cm2_groupnorm_relu_seg")
     _count(3)
+
+
+def groupnorm_apply_seg(flat, segs, groups, gamma, beta, eps, relu, stats):
+    check(load().cm2_groupnorm_apply_seg(ptr(flat), dtype_code(flat), flat.shape[1], len(segs), seg_array(segs), groups,
+                                         ptr(gamma), ptr(beta), eps, int(relu), ptr(stats), stream()),
+          "cm2_groupnorm_apply_seg")
+    _count()
+
+
+def ese_gate_f64(sums, inv_count, fc_w, fc_b, gate, n, c):
+    check(load().cm2_ese_gate_f64(ptr(sums), inv_count, ptr(fc_w), ptr(fc_b), ptr(gate), n, c, stream()), "cm2_ese_gate_f64")
+    _count()
+
+
+def ese_apply_pool(x, gate, identity, full, pool):
+    a, i, f, p = act(x), act(identity), act(full), act(pool)
+    check(load().cm2_ese_apply_pool(C.byref(a), ptr(gate), C.byref(i), C.byref(f), C.byref(p), dtype_code(x), stream()),
+          "cm2_ese_apply_pool")
+    _count()
 
 
 def relu(x, out):

@@ -114,9 +114,10 @@ typedef struct cm2_conv_desc {
                             [n, ceil(ho/2), ceil(wo/2), cout]; pixel (y,x) goes to plane
                             (y&1)*2+(x&1) at (y>>1, x>>1)                                          */
   cm2_act out;
-  /* optional per-(image, channel) sum of the stored (post-activation) outputs, float [n][cout],
-   * accumulated with atomics (caller zeroes); used for the eSE global pool.  NULL: off.  TC only. */
-  float* chan_sum;
+  /* optional fused statistics of the stored (post-activation, bf16-rounded) interior outputs, fp64, zeroed by
+   * the call and accumulated by the epilogue (see stats_mode below).  NULL: off.  TC engine only, bf16 output,
+   * out_mode 0, no residual.  Image index runs over all images of all segments for segmented tensors. */
+  void* stats;
   /* 1: every source is stored as four stride-2 *phase planes* (see cm2_phase_split): src[i] is the
    * halo-1 interior view of plane 0, [n, ceil(H/2), ceil(W/2), c], plane q = (y&1)*2 + (x&1) starts
    * n*sn elements after plane q-1.  Requires a 3x3 / stride 2 / pad 1 convolution; TC engine only. */
@@ -126,6 +127,11 @@ typedef struct cm2_conv_desc {
    * (= row pitch in elements); the other cm2_act fields are ignored.  One launch then covers all segments. */
   int32_t num_seg;
   cm2_seg seg[CM2_MAX_SEG];
+  /* 1: stats = double [images][cout]          per-channel sums (eSE global pool, vovnet.py:254)
+   * 2: stats = double [images][cout/8][2]     (sum, sum of squares) per 8-channel chunk (GroupNorm, fcos.py:182;
+   *                                           consumed by cm2_groupnorm_apply_seg)                           */
+  int32_t stats_mode;
+  int32_t reserved;
 } cm2_conv_desc;
 
 int cm2_conv2d(const cm2_conv_desc* d, void* stream);
@@ -165,6 +171,17 @@ int cm2_ese_gate(const float* pooled, float inv_count, const float* fc_w, const 
                  int32_t n, int32_t c, void* stream);
 int cm2_ese_apply(const cm2_act* x, const float* gate, const cm2_act* identity, const cm2_act* out,
                   int32_t dtype, void* stream);
+/* Fused variants used with the tensor-core engine.
+ * cm2_ese_gate_f64: as cm2_ese_gate, from the fp64 channel sums the producing convolution accumulated in its
+ *   epilogue (cm2_conv_desc.stats, stats_mode 1); inv_count = 1/(h*w).
+ * cm2_ese_apply_pool: y = x * gate (+ identity), stored to `full` (optional) and reduced by the
+ *   MaxPool2d(3, 2, ceil_mode=True) that opens the next stage (vovnet.py:349-350) into `pool` (optional,
+ *   [n, ho, wo, c]) in the same pass -- max over the values as stored.  Without `pool`, x / identity / full
+ *   must be interior views of identically shaped one-pixel-halo buffers (flat streaming pass). */
+int cm2_ese_gate_f64(const double* sums, double inv_count, const float* fc_w, const float* fc_b, float* gate,
+                     int32_t n, int32_t c, void* stream);
+int cm2_ese_apply_pool(const cm2_act* x, const float* gate, const cm2_act* identity, const cm2_act* full,
+                       const cm2_act* pool, int32_t dtype, void* stream);
 
 /* GroupNorm(groups, c) + optional ReLU in place; fcos.py:182-185 (eps 1e-5, biased variance over
  * (c/groups)*h*w per sample).  workspace: cm2_gn_workspace_floats(n, h*w, c, groups) floats. */
@@ -183,6 +200,11 @@ int64_t cm2_gn_seg_workspace_floats(int32_t num_seg, const cm2_seg* seg, int32_t
 int cm2_groupnorm_relu_seg(void* x, int32_t dtype, int32_t c, int32_t num_seg, const cm2_seg* seg, int32_t groups,
                            const float* gamma, const float* beta, float eps, int32_t relu, float* workspace,
                            void* stream);
+/* Normalise (+ReLU) in place from the statistics the producing convolution accumulated in its epilogue
+ * (cm2_conv_desc.stats, stats_mode 2: double [images][c/8][2]); needs (c / groups) % 8 == 0.  One pass. */
+int cm2_groupnorm_apply_seg(void* x, int32_t dtype, int32_t c, int32_t num_seg, const cm2_seg* seg, int32_t groups,
+                            const float* gamma, const float* beta, float eps, int32_t relu, const double* stats,
+                            void* stream);
 
 /* Elementwise ReLU copy (P7 input when the conv engine cannot apply in_relu). */
 int cm2_relu(const cm2_act* in, const cm2_act* out, int32_t dtype, void* stream);

@@ -63,12 +63,13 @@ def test_struct_layout_matches_header():
     """ctypes mirror of cm2_conv_desc must have the C layout (checked against sizeof from a tiny C program)."""
     from centermask2_b200 import lib
     import ctypes as C
-    src = '#include <stdio.h>\n#include <stddef.h>\n#include "cm2.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu",' \
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "cm2.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu",' \
           'sizeof(cm2_act),sizeof(cm2_conv_desc),offsetof(cm2_conv_desc,weight),offsetof(cm2_conv_desc,out),' \
-          'offsetof(cm2_conv_desc,chan_sum),offsetof(cm2_conv_desc,src_phase),offsetof(cm2_conv_desc,seg),' \
-          'sizeof(cm2_seg));return 0;}'
+          'offsetof(cm2_conv_desc,stats),offsetof(cm2_conv_desc,src_phase),offsetof(cm2_conv_desc,seg),' \
+          'sizeof(cm2_seg),offsetof(cm2_conv_desc,stats_mode));return 0;}'
     exe = "/tmp/cm2_layout_check"
     subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src, text=True, check=True)
     vals = [int(v) for v in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
     assert vals == [C.sizeof(lib.Act), C.sizeof(lib.ConvDesc), lib.ConvDesc.weight.offset, lib.ConvDesc.out.offset,
-                    lib.ConvDesc.chan_sum.offset, lib.ConvDesc.src_phase.offset, lib.ConvDesc.seg.offset, C.sizeof(lib.Seg)]
+                    lib.ConvDesc.stats.offset, lib.ConvDesc.src_phase.offset, lib.ConvDesc.seg.offset, C.sizeof(lib.Seg),
+                    lib.ConvDesc.stats_mode.offset]

@@ -279,3 +279,114 @@ def test_segmented_conv_and_groupnorm_match_per_level_results():
     torch.cuda.synchronize()
     for i, x in enumerate(xs):
         close(nchw(o16.level(i).view), F.conv2d(x, w16, b16, 1, 1), out_bf16=False)
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused output statistics (cm2_conv_desc.stats) and their consumers
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("srcs,cout,k,h,w,n,variant", [
+    ([128, 128, 128], 256, 1, 12, 16, 3, 0),      # OSA aggregation, tiles straddle images
+    ([256, 160], 512, 1, 9, 11, 2, 0),            # two N tiles
+    ([64, 64], 768, 1, 7, 9, 5, 0),               # three N tiles, many images per tile
+    ([128], 128, 3, 17, 23, 2, 0),
+])
+def test_conv_tc_channel_sums(srcs, cout, k, h, w, n, variant):
+    """stats_mode 1: per (image, channel) sums of the stored outputs (eSE global pool, vovnet.py:254)."""
+    g = torch.Generator().manual_seed(cout + h)
+    cin = sum(srcs)
+    xs = [rb(torch.randn(n, c, h, w, generator=g)) for c in srcs]
+    wt = rb(torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k))
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    cw = packing.ConvW(wt, srcs, 1, k // 2, scale, shift, True, BF, DEV, True)
+    out = halo(torch.zeros(n, cout, h, w))
+    sums = torch.full((n, cout), 123.0, dtype=torch.float64, device=DEV)        # the call zeroes it
+    assert lib.conv2d([halo(x).view for x in xs], cw.w_tc, out.view, cout, k, 1, k // 2, scale=cw.scale, shift=cw.shift,
+                      relu=True, engine=lib.ENGINE_TC, probe=True, stats=sums, stats_mode=1), lib.last_error()
+    torch.cuda.synchronize()
+    ref = out.view.double().sum(dim=(1, 2))                                     # of the values as stored
+    assert torch.allclose(sums, ref, rtol=1e-5, atol=1e-3), (sums - ref).abs().max()
+
+
+def test_conv_tc_seg_groupnorm_fused():
+    """stats_mode 2 + cm2_groupnorm_apply_seg == conv -> GroupNorm(32) -> ReLU per level (fcos.py:176-186)."""
+    from centermask2_b200.engine import SegMap
+    g = torch.Generator().manual_seed(5)
+    shapes = [(2, 13, 21), (2, 7, 11), (2, 4, 6), (2, 2, 3)]
+    c = 256
+    seg = SegMap(shapes, c, BF, DEV)
+    xs = []
+    for i, (n, h, w) in enumerate(shapes):
+        x = rb(torch.randn(n, c, h, w, generator=g))
+        xs.append(x)
+        seg.level(i).view.copy_(x.permute(0, 2, 3, 1).to(DEV, BF))
+    wt = rb(torch.randn(c, c, 3, 3, generator=g) / 48)
+    bias = torch.randn(c, generator=g) * 0.1
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    cw = packing.ConvW(wt, [c], 1, 1, None, bias, False, BF, DEV, True)
+    out = seg.like(c, BF, lambda shape: torch.zeros(shape, dtype=BF, device=DEV))
+    n_img = sum(s[0] for s in shapes)
+    st = torch.zeros((n_img, c // 8, 2), dtype=torch.float64, device=DEV)
+    assert lib.conv2d([seg.flat], cw.w_tc, out.flat, c, 3, 1, 1, shift=cw.shift, engine=lib.ENGINE_TC, segs=seg.segs,
+                      stats=st, stats_mode=2)
+    torch.cuda.synchronize()
+    img = 0
+    convs = []
+    for i, (n, h, w) in enumerate(shapes):
+        y = out.level(i).view.double()                                          # stored conv outputs [n, h, w, c]
+        convs.append(y.clone())
+        ref_s = y.reshape(n, h * w, c // 8, 8).sum(dim=(1, 3))
+        ref_q = (y * y).reshape(n, h * w, c // 8, 8).sum(dim=(1, 3))
+        assert torch.allclose(st[img:img + n, :, 0], ref_s, rtol=1e-6, atol=1e-4)
+        assert torch.allclose(st[img:img + n, :, 1], ref_q, rtol=1e-6, atol=1e-4)
+        img += n
+    lib.groupnorm_apply_seg(out.flat, out.segs, 32, gamma.to(DEV), beta.to(DEV), 1e-5, True, st)
+    torch.cuda.synchronize()
+    for i, (n, h, w) in enumerate(shapes):
+        ref = F.relu(F.group_norm(convs[i].float().permute(0, 3, 1, 2), 32, gamma.to(DEV), beta.to(DEV), 1e-5))
+        got = out.level(i).view.permute(0, 3, 1, 2).float()
+        close(got.cpu(), ref.cpu())
+        b = out.level(i).buf.float()
+        assert b[:, 0].abs().max() == 0 and b[:, -1].abs().max() == 0 and b[:, :, 0].abs().max() == 0 and b[:, :, -1].abs().max() == 0
+
+
+@pytest.mark.parametrize("h,w,c,identity,full", [(20, 33, 256, False, False), (25, 42, 512, True, True), (7, 8, 64, False, True),
+                                                 (50, 84, 768, True, True)])
+def test_ese_apply_pool(h, w, c, identity, full):
+    """x * gate (+ identity) fused with MaxPool2d(3, 2, ceil_mode=True) (vovnet.py:258-260, :349-350)."""
+    g = torch.Generator().manual_seed(h * w + c)
+    n = 2
+    x = rb(torch.randn(n, c, h, w, generator=g))
+    idn = rb(torch.randn(n, c, h, w, generator=g)) if identity else None
+    gate = torch.rand(n, c, generator=g)
+    y = x * gate.view(n, c, 1, 1)
+    if idn is not None:
+        y = y + idn
+    y = rb(y)
+    ref_pool = F.max_pool2d(y, 3, 2, ceil_mode=True)
+    ho, wo = ref_pool.shape[-2:]
+    fx, fi = halo(x), (halo(idn) if idn is not None else None)
+    out_full = halo(torch.zeros(n, c, h, w)) if full else None
+    out_pool = halo(torch.zeros(n, c, ho, wo))
+    lib.ese_apply_pool(fx.view, gate.to(DEV), fi.view if fi is not None else None, out_full.view if full else None, out_pool.view)
+    torch.cuda.synchronize()
+    assert torch.equal(nchw(out_pool.view), ref_pool)
+    if full:
+        assert torch.equal(nchw(out_full.view), y)
+    # flat variant (no pooling)
+    out2 = halo(torch.zeros(n, c, h, w))
+    lib.ese_apply_pool(fx.view, gate.to(DEV), fi.view if fi is not None else None, out2.view, None)
+    torch.cuda.synchronize()
+    assert torch.equal(nchw(out2.view), y)
+    assert out2.buf[:, 0].abs().max() == 0 and out2.buf[:, :, -1].abs().max() == 0
+
+
+def test_ese_gate_f64_matches_reference():
+    g = torch.Generator().manual_seed(9)
+    n, c, hw = 3, 256, 1234
+    sums = torch.randn(n, c, generator=g, dtype=torch.float64) * hw
+    w, b = torch.randn(c, c, generator=g) / 16, torch.randn(c, generator=g)
+    gate = torch.zeros(n, c, device=DEV)
+    lib.ese_gate_f64(sums.to(DEV), 1.0 / hw, w.to(DEV), b.to(DEV), gate, n, c)
+    torch.cuda.synchronize()
+    ref = F.relu6((sums / hw).float() @ w.t() + b + 3.0) / 6.0
+    assert torch.allclose(gate.cpu(), ref, atol=2e-5)

@@ -29,6 +29,7 @@ def main():
     r = 50 * n
     shapes = [
         # name, images, h, w, sources, cout, k, out_mode
+        ("stem1_1x1_32_64", n, 400, 672, [32], 64, 1, 0),
         ("stem2_3x3_64", n, 400, 672, [64], 64, 3, 0),
         ("osa2_3x3_128", n, 200, 336, [128], 128, 3, 0),
         ("osa2_cat_768_256", n, 200, 336, [128] * 6, 256, 1, 0),
@@ -40,6 +41,8 @@ def main():
         ("fcos_tower_p3", n, 100, 168, [256], 256, 3, 0),
         ("fcos_tower_p4", n, 50, 84, [256], 256, 3, 0),
         ("fcos_logits_p3", n, 100, 168, [256], 80, 3, 0),
+        ("fcos_regctr_p3", n, 100, 168, [256], 16, 3, 0),
+        ("iou_fc1_12544_1024", 1, 1, r, [12544], 1024, 1, 0),
         ("mask_fcn", r, 14, 14, [256], 256, 3, 0),
         ("mask_deconv", r, 14, 14, [256], 1024, 1, 1),
     ]
