@@ -71,6 +71,9 @@ struct alignas(64) TcParams {
   int stats_mode;           // 1: per (image, channel) sum;  2: per (image, 8-channel chunk) sum and sum of squares
   int stats_stride;         // doubles per image
   int seg_img0[CM2_MAX_SEG];// global image index of the first image of every segment
+  double rcp_plane, rcp_pitch;                       // 1 / plane, 1 / pitch (1 / w in dense mode): exact fast division
+  double seg_rcp_plane[CM2_MAX_SEG], seg_rcp_pitch[CM2_MAX_SEG];
+  int epi_kind;             // staged-epilogue variant (see tc_epilogue_dispatch)
   int epi_sets;             // column sets of epilogue warps per 128-row accumulator (1, 2 or 4)
   int fast_store;           // 1: epilogue transposes through shared memory and writes 64-byte row segments
   int dbg;                  // tuning experiments (CM2_TC_DEBUG): 1 no epilogue stores, 2 no TMA loads, 4 no MMAs
@@ -159,11 +162,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 
 // Geometry of the map a tile belongs to (segments start at multiples of 256 rows, so a tile never straddles two).
-struct TileGeom { int row0, rows, pitch, plane, h, w, img0; };
+struct TileGeom { int row0, rows, pitch, plane, h, w, img0; double rcp_plane, rcp_pitch; };
 __device__ __forceinline__ TileGeom tc_geom(const TcParams& p, int m0) {
   TileGeom g;
   if (p.num_seg == 0) {
     g.row0 = 0; g.rows = p.rows; g.pitch = p.pitch; g.plane = p.plane; g.h = p.h; g.w = p.w; g.img0 = 0;
+    g.rcp_plane = p.rcp_plane; g.rcp_pitch = p.rcp_pitch;
   } else {
     int s = 0;
 #pragma unroll
@@ -171,6 +175,7 @@ __device__ __forceinline__ TileGeom tc_geom(const TcParams& p, int m0) {
       if (i < p.num_seg && m0 >= p.seg_row0[i]) s = i;
     g.row0 = p.seg_row0[s]; g.rows = p.seg_rows[s]; g.pitch = p.seg_pitch[s]; g.plane = p.seg_plane[s];
     g.h = p.seg_h[s]; g.w = p.seg_w[s]; g.img0 = p.seg_img0[s];
+    g.rcp_plane = p.seg_rcp_plane[s]; g.rcp_pitch = p.seg_rcp_pitch[s];
   }
   return g;
 }
@@ -324,6 +329,7 @@ __device__ __forceinline__ void tc_epilogue_rows(const TcParams& p, const TileGe
 //   mode 1 (eSE pool, vovnet.py:254): stats[img][c]         += sum over pixels
 //   mode 2 (GroupNorm, fcos.py:182):  stats[img][c/8][2]    += (sum, sum of squares) over pixels x 8 channels
 // ------------------------------------------------------------------------------------------------
+template <int STATS>
 __device__ __forceinline__ void tc_epilogue_stats(const TcParams& p, const float (&v)[32], unsigned rows, bool interior,
                                                   int img_g, int co0, int ncol, int lane) {
   while (rows) {                                     // warp-uniform
@@ -331,7 +337,7 @@ __device__ __forceinline__ void tc_epilogue_stats(const TcParams& p, const float
     const int li = __shfl_sync(0xffffffffu, img_g, leader);
     const bool mine = interior && img_g == li;
     rows &= ~__ballot_sync(0xffffffffu, mine);
-    if (p.stats_mode == 2) {
+    if (STATS == 2) {
       float r[8];
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
@@ -423,20 +429,32 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
 // The epilogue warps of one 128-row accumulator are organised in `ncset` column sets (one warp per TMEM lane quarter
 // and set); set `cset` handles every ncset-th 64-byte column pass.  Several warps per scheduler hide the
 // tcgen05.ld -> FMA -> st.shared -> ld.shared -> st.global dependency chain, which is what bounds short-K layers.
+// Compile-time variants (runtime flags in the pass loop cost ~150 of its 250 SASS instructions -- measured with ncu on
+// the K = 32 stem layer, whose epilogue is the whole kernel): F32 output, residual add, fused statistics (0 / 1 / 2),
+// deconv scatter.
+__device__ __forceinline__ int tc_fast_div(int n, int d, double rcp) {          // n >= 0, d > 0; exact
+  int q = __double2int_rz((double)n * rcp);
+  const int r = n - q * d;
+  if (r < 0) --q;
+  else if (r >= d) ++q;
+  return q;
+}
+
+template <bool F32, bool RES, int STATS, bool DECONV>
 __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const TileGeom& g, uint32_t taddr, int m, int n0,
                                                         uint32_t stage_smem, int lane, uint32_t ss_smem, int cset, int ncset) {
   const int mr = m - g.row0;
   bool in_range = mr >= 0 && mr < g.rows, interior = false;
   int img = 0, y = 0, x = 0;
   if (in_range) {
-    img = mr / g.plane;
+    img = tc_fast_div(mr, g.plane, g.rcp_plane);
     int r = mr - img * g.plane;
     if (p.halo) {
-      int yy = r / g.pitch, xx = r - yy * g.pitch;
+      int yy = tc_fast_div(r, g.pitch, g.rcp_pitch), xx = r - yy * g.pitch;
       y = yy - 1; x = xx - 1;
       interior = y >= 0 && y < g.h && x >= 0 && x < g.w;
     } else {
-      y = r / g.w; x = r - y * g.w;
+      y = tc_fast_div(r, g.w, g.rcp_pitch); x = r - y * g.w;
       interior = true;
     }
   }
@@ -444,24 +462,25 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
   long long out_off;
   if (p.num_seg)
     out_off = (long long)m * p.out_sw;                 // segmented output: same flat row, pitch = cout
+  else if (DECONV)
+    out_off = (long long)img * p.out_sn + (long long)(2 * y) * p.out_sh + (long long)(2 * x) * p.out_sw;
   else if (p.out_mode == 0)
     out_off = (long long)img * p.out_sn + (long long)y * p.out_sh + (long long)x * p.out_sw;
-  else if (p.out_mode == 1)
-    out_off = (long long)img * p.out_sn + (long long)(2 * y) * p.out_sh + (long long)(2 * x) * p.out_sw;
   else
     out_off = (long long)((y & 1) * 2 + (x & 1)) * p.out_plane + (long long)img * p.out_sn +
               (long long)(y >> 1) * p.out_sh + (long long)(x >> 1) * p.out_sw;
   const __nv_bfloat16* res_row = nullptr;
-  if (p.res_mode && interior)
+  if (RES && interior)
     res_row = p.res + (long long)img * p.res_sn + (long long)(p.res_mode == 2 ? (y >> 1) : y) * p.res_sh +
               (long long)(p.res_mode == 2 ? (x >> 1) : x) * p.res_sw;
   const unsigned store_mask = __ballot_sync(0xffffffffu, do_store);      // rows of this warp that get written
   const unsigned int_mask = __ballot_sync(0xffffffffu, interior);
   const bool all_int = int_mask == 0xffffffffu;
-  const unsigned stat_rows = p.stats_mode ? int_mask : 0u;
+  const unsigned stat_rows = STATS ? int_mask : 0u;
   const int img_g = img + g.img0;                    // image index across segments (statistics slot)
-  const int esize = p.out_f32 ? 4 : 2;
-  const int cpp = p.out_f32 ? 16 : 32;               // channels per pass = 64 bytes per row
+  constexpr int esize = F32 ? 4 : 2;
+  constexpr int cpp = F32 ? 16 : 32;                 // channels per pass = 64 bytes per row
+  const float relu_floor = p.relu ? 0.f : -INFINITY;
   const uint32_t my_row = stage_smem + (uint32_t)lane * EPI_PITCH;
   // write-back role of this lane: rows it*8 + lane/4, 16-byte piece lane%4 -- row addresses are fixed for the tile
   char* wptr[4];
@@ -479,8 +498,8 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
     const int co0 = n0 + c0;
     float v[32];
     uint4 rres[4];
-    const bool has_res = res_row != nullptr && co0 < p.cout;
-    if (has_res) {                                     // issue the residual loads before waiting on TMEM
+    const bool has_res = RES && res_row != nullptr && co0 < p.cout;
+    if (RES && has_res) {                                     // issue the residual loads before waiting on TMEM
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (8 * j < cpp && co0 + 8 * j < p.cout) rres[j] = __ldg(reinterpret_cast<const uint4*>(res_row + co0 + 8 * j));
@@ -490,7 +509,7 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
       uint32_t raw[16];
       __syncwarp();
       tc_ld16(taddr + (uint32_t)c0, raw);
-      if (!p.out_f32 && c0 + 16 < p.bn) {
+      if (!F32 && c0 + 16 < p.bn) {
         uint32_t raw2[16];
         tc_ld16(taddr + (uint32_t)(c0 + 16), raw2);
         tc_ld_wait();
@@ -513,7 +532,7 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
         ffma2(v[4 * j4 + 2], v[4 * j4 + 3], v[4 * j4 + 2], v[4 * j4 + 3], sc.z, sc.w, sh.z, sh.w);
       }
     }
-    if (has_res) {
+    if (RES && has_res) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (8 * j < cpp) {
@@ -527,49 +546,55 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
       }
     }
     // ---- stage this thread's 64 bytes
-    if (p.out_f32) {
+    if (F32) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (p.relu) v[j] = fmaxf(v[j], 0.f);
-        if (!all_int) v[j] = interior ? v[j] : 0.f;
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], relu_floor);
+      if (!all_int) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = interior ? v[j] : 0.f;
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + 16u * j), "f"(v[4 * j]), "f"(v[4 * j + 1]),
                      "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
     } else {
-      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+      const __nv_bfloat162 floor2 = __floats2bfloat162_rn(relu_floor, relu_floor);
+      uint32_t w[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
-          if (p.relu) h2 = __hmax2(h2, zero2);         // max(round(x), 0) == round(max(x, 0))
-          w[i] = *reinterpret_cast<uint32_t*>(&h2);
-          if (!all_int) w[i] = interior ? w[i] : 0u;
-          if (p.stats_mode) {                        // statistics of the values as stored (bf16-rounded)
-            v[8 * j + 2 * i] = __uint_as_float(w[i] << 16);
-            v[8 * j + 2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-          }
-        }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + 16u * j), "r"(w[0]), "r"(w[1]), "r"(w[2]),
-                     "r"(w[3]) : "memory");
+      for (int i = 0; i < 16; ++i) {
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        h2 = __hmax2(h2, floor2);                    // max(round(x), 0) == round(max(x, 0))
+        w[i] = *reinterpret_cast<uint32_t*>(&h2);
       }
+      if (!all_int) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = interior ? w[i] : 0u;
+      }
+      if (STATS) {                                   // statistics of the values as stored (bf16-rounded)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          v[2 * i] = __uint_as_float(w[i] << 16);
+          v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + 16u * j), "r"(w[4 * j]), "r"(w[4 * j + 1]),
+                     "r"(w[4 * j + 2]), "r"(w[4 * j + 3]) : "memory");
     }
-    if (p.stats_mode) tc_epilogue_stats(p, v, stat_rows, interior, img_g, co0, min(p.bn - c0, p.cout - co0), lane);
+    if (STATS) tc_epilogue_stats<STATS>(p, v, stat_rows, interior, img_g, co0, min(p.bn - c0, p.cout - co0), lane);
     __syncwarp();
     // ---- write back: 4 instructions x (8 rows x 64 bytes)
     long long extra = 0;
     int cc = co0;
-    if (p.out_mode == 1) {
+    if (DECONV) {
       const int cq = p.cout >> 2;
       const int quad = co0 / cq;
       cc = co0 - quad * cq;
       extra = (long long)(quad >> 1) * p.out_sh + (long long)(quad & 1) * p.out_sw;
     }
     const long long col_bytes = (extra + cc) * esize;
-    const int elems16 = p.out_f32 ? 4 : 8;           // elements per 16-byte piece
+    constexpr int elems16 = F32 ? 4 : 8;             // elements per 16-byte piece
     // 16-byte pieces of this pass that belong to this tile (bn need not be a multiple of the pass width) and to cout
     const int valid_pieces = min(4, (min(p.bn - c0, p.cout - co0) + elems16 - 1) / elems16);
     const bool piece_ok = (lane & 3) < valid_pieces;
@@ -582,6 +607,19 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
     }
   }
   __syncwarp();
+}
+
+// kind: 0 plain bf16, 1 bf16 + channel sums, 2 bf16 + GroupNorm sums, 3 bf16 + residual, 4 f32, 5 bf16 deconv scatter
+__device__ __forceinline__ void tc_epilogue_dispatch(const TcParams& p, const TileGeom& g, uint32_t taddr, int m, int n0,
+                                                     uint32_t stage_smem, int lane, uint32_t ss_smem, int cset, int ncset) {
+  switch (p.epi_kind) {
+    case 0: tc_epilogue_rows_staged<false, false, 0, false>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
+    case 1: tc_epilogue_rows_staged<false, false, 1, false>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
+    case 2: tc_epilogue_rows_staged<false, false, 2, false>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
+    case 3: tc_epilogue_rows_staged<false, true, 0, false>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
+    case 4: tc_epilogue_rows_staged<true, false, 0, false>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
+    default: tc_epilogue_rows_staged<false, false, 0, true>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -705,8 +743,8 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc_kernel(const __grid
       const TileGeom g = tc_geom(p, m0);
       const int cset = (warp - 2) >> 2;
       if (p.fast_store)
-        tc_epilogue_rows_staged(p, g, taddr, m0 + q * 32 + lane, n0, epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES, lane, ss,
-                                cset, p.epi_sets);
+        tc_epilogue_dispatch(p, g, taddr, m0 + q * 32 + lane, n0, epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES, lane, ss,
+                             cset, p.epi_sets);
       else if (cset == 0)
         tc_epilogue_rows(p, g, taddr, m0 + q * 32 + lane, n0, ss);
       tc_fence_before();
@@ -889,8 +927,8 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc2_kernel(const __gri
       const uint32_t taddr = tmem_base + (uint32_t)(acc * 2 * half_cols + half * half_cols) + ((uint32_t)(q * 32) << 16);
       const TileGeom tg = tc_geom(p, m0);
       if (p.fast_store)
-        tc_epilogue_rows_staged(p, tg, taddr, m0 + half * 128 + q * 32 + lane, n0, epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES, lane, ss,
-                                cset, p.epi_sets);
+        tc_epilogue_dispatch(p, tg, taddr, m0 + half * 128 + q * 32 + lane, n0, epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES, lane, ss,
+                             cset, p.epi_sets);
       else if (cset == 0)
         tc_epilogue_rows(p, tg, taddr, m0 + half * 128 + q * 32 + lane, n0, ss);
       tc_fence_before();
@@ -1028,6 +1066,15 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     p->h = p->w = p->pitch = p->plane = 0;
   }
   TC_REQUIRE(rows > 0 && rows < (1ll << 31) - 4096, "conv_tc: %lld rows out of range", rows);
+  if (seg) {
+    for (int i = 0; i < d->num_seg; ++i) {
+      p->seg_rcp_plane[i] = 1.0 / (double)p->seg_plane[i];
+      p->seg_rcp_pitch[i] = 1.0 / (double)p->seg_pitch[i];
+    }
+  } else {
+    p->rcp_plane = 1.0 / (double)p->plane;
+    p->rcp_pitch = 1.0 / (double)(halo ? p->pitch : s0.w);
+  }
   TC_REQUIRE(!phase || halo, "conv_tc: phase-split sources must be halo views");
   TC_REQUIRE(!phase || rows * 4 < (1ll << 31) - 4096, "conv_tc: phase-split source too large");
   for (int tap = 0; tap < p->taps; ++tap) {
@@ -1133,11 +1180,15 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   }
   static const int env_store = getenv("CM2_TC_FAST_STORE") ? atoi(getenv("CM2_TC_FAST_STORE")) : 1;
   p->fast_store = (env_store && p->out_vec && (d->out_mode != 1 || (d->cout / 4) % 32 == 0)) ? 1 : 0;
+  p->epi_kind = p->out_f32 ? 4 : (p->res_mode ? 3 : (d->out_mode == 1 ? 5 : 0));
+  if (p->fast_store) TC_REQUIRE(!(p->out_f32 && (p->res_mode || d->out_mode == 1)) && !(p->res_mode && d->out_mode == 1),
+                                "conv_tc: unsupported epilogue combination (f32 / residual / deconv)");
   if (d->stats) {
-    TC_REQUIRE(p->fast_store && !p->out_f32 && d->out_mode == 0 && d->cout % 8 == 0,
+    TC_REQUIRE(p->fast_store && !p->res_mode && !p->out_f32 && d->out_mode == 0 && d->cout % 8 == 0,
                "conv_tc: fused statistics need a bf16 out_mode-0 output without residual, cout %% 8 == 0");
     p->stats = reinterpret_cast<double*>(d->stats);
     p->stats_mode = d->stats_mode;
+    p->epi_kind = d->stats_mode;
     p->stats_stride = d->stats_mode == 1 ? d->cout : (d->cout / 8) * 2;
   }
 #undef TC_REQUIRE

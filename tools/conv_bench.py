@@ -31,6 +31,8 @@ def main():
         # name, images, h, w, sources, cout, k, out_mode
         ("stem1_1x1_32_64", n, 400, 672, [32], 64, 1, 0),
         ("stem2_3x3_64", n, 400, 672, [64], 64, 3, 0),
+        ("stem2_phase_out", n, 400, 672, [64], 64, 3, 2),
+        ("stem3_s2_64_128", n, 400, 672, [64], 128, 3, 3),
         ("osa2_3x3_128", n, 200, 336, [128], 128, 3, 0),
         ("osa2_cat_768_256", n, 200, 336, [128] * 6, 256, 1, 0),
         ("osa3_3x3_160", n, 100, 168, [160], 160, 3, 0),
@@ -53,20 +55,36 @@ def main():
             continue
         g = torch.Generator().manual_seed(1)
         cin = sum(srcs)
-        bufs = [torch.zeros((nn, h + 2, w + 2, c), dtype=BF, device=dev) for c in srcs]
-        for b in bufs:
-            b[:, 1:-1, 1:-1].normal_()
+        stride, src_phase = 1, False
+        if out_mode == 3:                                   # 3x3 / stride 2 reading phase planes (stem_3, P6, P7)
+            stride, src_phase = 2, True
+            bufs = [torch.zeros((4, nn, h // 2 + 2, w // 2 + 2, c), dtype=BF, device=dev) for c in srcs]
+            for b in bufs:
+                b[:, :, 1:-1, 1:-1].normal_()
+        else:
+            bufs = [torch.zeros((nn, h + 2, w + 2, c), dtype=BF, device=dev) for c in srcs]
+            for b in bufs:
+                b[:, 1:-1, 1:-1].normal_()
         wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
-        cw = packing.ConvW(wt, srcs, 1, k // 2, torch.ones(cout), torch.zeros(cout), True, BF, dev, True)
+        cw = packing.ConvW(wt, srcs, stride, k // 2, torch.ones(cout), torch.zeros(cout), True, BF, dev, True)
+        om = out_mode
         if out_mode == 0:
             out = torch.zeros((nn, h + 2, w + 2, cout), dtype=BF, device=dev)[:, 1:-1, 1:-1]
-        else:
+            views = [b[:, 1:-1, 1:-1] for b in bufs]
+        elif out_mode == 1:
             out = torch.zeros((nn, 2 * h, 2 * w, cout // 4), dtype=BF, device=dev)
-        views = [b[:, 1:-1, 1:-1] for b in bufs]
+            views = [b[:, 1:-1, 1:-1] for b in bufs]
+        elif out_mode == 2:
+            out = torch.zeros((4, nn, h // 2 + 2, w // 2 + 2, cout), dtype=BF, device=dev)[0, :, 1:-1, 1:-1]
+            views = [b[:, 1:-1, 1:-1] for b in bufs]
+        else:
+            om = 0
+            out = torch.zeros((nn, h // 2 + 2, w // 2 + 2, cout), dtype=BF, device=dev)[:, 1:-1, 1:-1]
+            views = [b[0, :, 1:-1, 1:-1] for b in bufs]
 
         def run():
-            ok = lib.conv2d(views, cw.w_tc, out, cout, k, 1, k // 2, scale=cw.scale, shift=cw.shift, relu=True,
-                            out_mode=out_mode, engine=lib.ENGINE_TC, probe=True)
+            ok = lib.conv2d(views, cw.w_tc, out, cout, k, stride, k // 2, scale=cw.scale, shift=cw.shift, relu=True,
+                            out_mode=om, engine=lib.ENGINE_TC, probe=True, src_phase=src_phase)
             assert ok, lib.last_error()
         for _ in range(2):
             run()
@@ -78,7 +96,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.reps
-        gflop = 2.0 * nn * h * w * cin * k * k * cout / 1e9
+        gflop = 2.0 * nn * (h // stride) * (w // stride) * cin * k * k * cout / 1e9
         print("{:22s} {:9.1f} GFLOP {:8.4f} ms {:8.1f} TFLOP/s".format(name, gflop, ms, gflop / ms))
 
 
