@@ -120,6 +120,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// One lane of a fully converged warp.  The control warps run their loops warp-uniformly and predicate only the
+// TMA / MMA / commit instructions with this: their operands then live in uniform registers and each UTCHMMA /
+// UTMALDG is a single instruction.  (Wrapping the loops in `if (lane == 0)` made ptxas emit an ELECT / BRA.U.ANY
+// uniformisation loop plus R2UR moves around every one of them -- ~170 cycles per MMA in the ncu source view.)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, %1;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -663,7 +680,7 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc_kernel(const __grid
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -676,13 +693,16 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc_kernel(const __grid
             for (int cb = 0; cb < nblk; ++cb, ++kb) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
               const uint32_t sa = base + (uint32_t)stage * stage_bytes;
-              if (p.dbg & 2) {
-                mbar_arrive(full_bar(stage));
-              } else {
-                mbar_expect_tx(full_bar(stage), TC_A_BYTES + b_bytes);
-                tma_load_2d(sa, &p.a_map[s], full_bar(stage), cb * TC_BK, m0 + shift);
-                tma_load_2d(sa + TC_A_BYTES, &p.b_map, full_bar(stage), kb * TC_BK, n0);
+              if (elect_one_sync()) {
+                if (p.dbg & 2) {
+                  mbar_arrive(full_bar(stage));
+                } else {
+                  mbar_expect_tx(full_bar(stage), TC_A_BYTES + b_bytes);
+                  tma_load_2d(sa, &p.a_map[s], full_bar(stage), cb * TC_BK, m0 + shift);
+                  tma_load_2d(sa + TC_A_BYTES, &p.b_map, full_bar(stage), kb * TC_BK, n0);
+                }
               }
+              __syncwarp();
               if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
           }
@@ -691,7 +711,7 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc_kernel(const __grid
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N = bn, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0, acc = 0;
@@ -711,17 +731,24 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc_kernel(const __grid
               tc_fence_after();
               const uint32_t sa = base + (uint32_t)stage * stage_bytes;
               const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + TC_A_BYTES);
-              for (int k = 0; k < nk && !(p.dbg & 4); ++k) {
-                // +32 bytes per K=16 step inside the 128B swizzle row (start-address field is in 16B units)
-                tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate);
-                accumulate = 1;
+              if (elect_one_sync()) {
+                if (!(p.dbg & 4)) {
+                  // +32 bytes per K=16 step inside the 128B swizzle row (start-address field is in 16B units)
+                  tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+                  if (nk > 1) tc_mma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                  if (nk > 2) tc_mma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                  if (nk > 3) tc_mma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                }
+                tc_commit(empty_bar(stage));          // frees the smem slot when these MMAs have read it
               }
-              tc_commit(empty_bar(stage));          // frees the smem slot when these MMAs have read it
+              __syncwarp();
+              accumulate = 1;
               if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
           }
         }
-        tc_commit(tfull_bar(acc));                  // accumulator complete -> epilogue
+        if (elect_one_sync()) tc_commit(tfull_bar(acc));                  // accumulator complete -> epilogue
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -825,7 +852,7 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc2_kernel(const __gri
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -840,23 +867,29 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc2_kernel(const __gri
             for (int cb = 0; cb < nblk; ++cb, ++blk) {
               mbar_wait(aempty_bar(sa), pa ^ 1u);
               const uint32_t slab = base + (uint32_t)sa * a_slab_bytes;
-              if (p.dbg & 2) {
-                mbar_arrive(afull_bar(sa));
-              } else {
-                mbar_expect_tx(afull_bar(sa), a_slab_bytes);
-                tma_load_2d(slab, &p.a_map[s], afull_bar(sa), cb * TC_BK, row0);
-                tma_load_2d(slab + a_half_bytes, &p.a_map[s], afull_bar(sa), cb * TC_BK, row0 + p.a_box_rows);
+              if (elect_one_sync()) {
+                if (p.dbg & 2) {
+                  mbar_arrive(afull_bar(sa));
+                } else {
+                  mbar_expect_tx(afull_bar(sa), a_slab_bytes);
+                  tma_load_2d(slab, &p.a_map[s], afull_bar(sa), cb * TC_BK, row0);
+                  tma_load_2d(slab + a_half_bytes, &p.a_map[s], afull_bar(sa), cb * TC_BK, row0 + p.a_box_rows);
+                }
               }
+              __syncwarp();
               if (++sa == p.sa_stages) { sa = 0; pa ^= 1u; }
               for (int j = 0; j < groups_per_tap_row; ++j) {
                 const int tap = p.kx_merge ? g * 3 + j : g;
                 mbar_wait(bempty_bar(sb), pb ^ 1u);
-                if (p.dbg & 2) {
-                  mbar_arrive(bfull_bar(sb));
-                } else {
-                  mbar_expect_tx(bfull_bar(sb), b_bytes);
-                  tma_load_2d(b_base + (uint32_t)sb * b_bytes, &p.b_map, bfull_bar(sb), (tap * p.nblk_total + blk) * TC_BK, n0);
+                if (elect_one_sync()) {
+                  if (p.dbg & 2) {
+                    mbar_arrive(bfull_bar(sb));
+                  } else {
+                    mbar_expect_tx(bfull_bar(sb), b_bytes);
+                    tma_load_2d(b_base + (uint32_t)sb * b_bytes, &p.b_map, bfull_bar(sb), (tap * p.nblk_total + blk) * TC_BK, n0);
+                  }
                 }
+                __syncwarp();
                 if (++sb == p.sb_stages) { sb = 0; pb ^= 1u; }
               }
             }
@@ -866,7 +899,7 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc2_kernel(const __gri
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int sa = 0, sb = 0, acc = 0;
       uint32_t pa = 0, pb = 0, acc_phase = 0;
@@ -874,6 +907,7 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc2_kernel(const __gri
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * half_cols);
+        const uint32_t d1 = d0 + (uint32_t)half_cols;
         uint32_t accumulate = 0;
         for (int g = 0; g < ngroup_outer; ++g) {
           for (int s = 0; s < p.num_src; ++s) {
@@ -892,20 +926,31 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc2_kernel(const __gri
                 const uint32_t a0 = slab + (uint32_t)(p.kx_merge ? j : 0) * 128u;
                 const uint32_t a1 = a0 + 128u * 128u;
                 const uint64_t adesc0 = umma_desc_sw128_at(a0, p.desc_mode), adesc1 = umma_desc_sw128_at(a1, p.desc_mode);
-                if (!(p.dbg & 4)) {
-                  for (int k = 0; k < nk; ++k) tc_mma_bf16(d0, adesc0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
-                  for (int k = 0; k < nk; ++k) tc_mma_bf16(d0 + (uint32_t)half_cols, adesc1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
+                if (elect_one_sync()) {
+                  if (!(p.dbg & 4)) {
+                    tc_mma_bf16(d0, adesc0, bdesc, idesc, accumulate);
+                    if (nk > 1) tc_mma_bf16(d0, adesc0 + 2, bdesc + 2, idesc, 1u);
+                    if (nk > 2) tc_mma_bf16(d0, adesc0 + 4, bdesc + 4, idesc, 1u);
+                    if (nk > 3) tc_mma_bf16(d0, adesc0 + 6, bdesc + 6, idesc, 1u);
+                    tc_mma_bf16(d1, adesc1, bdesc, idesc, accumulate);
+                    if (nk > 1) tc_mma_bf16(d1, adesc1 + 2, bdesc + 2, idesc, 1u);
+                    if (nk > 2) tc_mma_bf16(d1, adesc1 + 4, bdesc + 4, idesc, 1u);
+                    if (nk > 3) tc_mma_bf16(d1, adesc1 + 6, bdesc + 6, idesc, 1u);
+                  }
+                  tc_commit(bempty_bar(sb));
                 }
+                __syncwarp();
                 accumulate = 1;
-                tc_commit(bempty_bar(sb));
                 if (++sb == p.sb_stages) { sb = 0; pb ^= 1u; }
               }
-              tc_commit(aempty_bar(sa));
+              if (elect_one_sync()) tc_commit(aempty_bar(sa));
+              __syncwarp();
               if (++sa == p.sa_stages) { sa = 0; pa ^= 1u; }
             }
           }
         }
-        tc_commit(tfull_bar(acc));
+        if (elect_one_sync()) tc_commit(tfull_bar(acc));
+        __syncwarp();
         if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
       }
     }
