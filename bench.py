@@ -259,6 +259,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying its CUDA graph")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="warm up, then run exactly one eager step between cudaProfilerStart/Stop and exit (for "
+                         "`ncu --profile-from-start off`); prints nothing that counts as a bench value")
     ap.add_argument("--layers", default=None, help="write a per-conv-layer timing table (one step) to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -305,6 +308,18 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.profile_step:
+        eager = make_device_step(model, cfg, dev_images, (H, W), graph=False)
+        for _ in range(warmup):
+            eager()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        eager()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        clk.close()
+        return 0
 
     # ---- device-resident throughput ("value")
     step = make_device_step(model, cfg, dev_images, (H, W), graph=not args.no_graph)
@@ -366,6 +381,12 @@ def main():
                 ms_l = a.elapsed_time(b)
                 f.write("{:24s} {:10.3f} {:9.4f} {:9.1f}\n".format(nme, gf, ms_l, gf / ms_l if ms_l > 0 else 0.0))
     gflop_img = conv_gflop_per_image(cfg, 800, 1344, r_cap)          # algorithmic FLOPs, R = slots computed
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")      # written by tools/ncu_step_summary.py from an ncu capture
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("images_per_gpu") == args.batch and tj.get("precision") == args.precision:
+            traffic = tj.get("conv_dram_bytes_per_step")
     clk.close()
     hbm, tf_burst, tf_sus, src = peaks()
     achieved = gflop_img * args.batch / conv_ms                       # GFLOP / ms = TFLOP/s
@@ -387,7 +408,7 @@ def main():
                         "(on device) -> compact result record copied to host"},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "conv (all launches of one step)", "launches_per_step": conv_launches,
+                     "traffic": traffic, "kernel": "conv (all launches of one step)", "launches_per_step": conv_launches,
                      "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / ms_step,
                      "gflop_per_image": gflop_img, "peak_source": src + " (bf16 sustained cuBLAS)",
                      "frac_of_burst": achieved / tf_burst},

@@ -1148,13 +1148,18 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   p->dbg = env_dbg;
   const int m_tiles256 = (int)((rows + 255) / 256);
   const int bn2 = pick_bn(cout_pad, m_tiles256, sms);
-  // Measured (tools/conv_bench.py, B200): 256-row tiles win when the kx-merged slab applies and both accumulators
-  // stay double-buffered (bn <= 128), and for short-K 1x1 layers whose epilogue dominates (8 epilogue warps);
-  // with bn > 128 the single accumulator stage exposes the epilogue and 128-row tiles are as fast or faster.
+  // Measured (tools/conv_bench.py, B200, batch 16; profiles/r1_convbench_variants_b16.txt): 256-row tiles win
+  //   * with the kx-merged slab while both accumulators stay double-buffered (bn <= 128) and the problem has at least
+  //     two waves of tiles (small maps, e.g. OSA5 25x42, are faster on 128-row tiles);
+  //   * for stride-2 convolutions on phase planes (stem_3: 760 vs 650 TFLOP/s);
+  //   * for very short K 1x1 layers whose epilogue is the whole kernel (stem_1, K = 32).
+  // Everything else (N = 256 towers, 1x1 aggregations / laterals with K >= 512) is as fast or faster on 128-row tiles.
   const bool merge_ok = p->taps == 9 && !phase;
   int k_total = 0;
   for (int i = 0; i < d->num_src; ++i) k_total += d->src[i].c;
-  bool use_v2 = m_tiles256 * (cout_pad / bn2) >= sms && ((merge_ok && bn2 <= 128) || (p->taps == 1 && k_total <= 512));
+  const int tiles256 = m_tiles256 * (cout_pad / bn2);
+  bool use_v2 = (merge_ok && bn2 <= 128 && tiles256 >= 2 * sms) || (phase && bn2 <= 128 && tiles256 >= sms) ||
+                (p->taps == 1 && k_total <= 128 && tiles256 >= sms);
   if (env_variant == 1) use_v2 = false;
   if (env_variant >= 2) use_v2 = true;
   static const int env_sets1 = getenv("CM2_TC_EPI_SETS_V1") ? atoi(getenv("CM2_TC_EPI_SETS_V1")) : 2;

@@ -2,6 +2,8 @@
 // All are coalesced over the channel dimension (innermost) and vectorised 8 channels/thread.
 // Reductions are deterministic (fixed two-stage trees, no atomics).
 #include "common.cuh"
+#include <algorithm>
+#include <string.h>
 
 namespace cm2 {
 
@@ -330,6 +332,44 @@ __global__ void preprocess_im2col_kernel(const InT* __restrict__ img, int h, int
   }
 }
 
+// The same for a whole batch in one launch: grid (pixel-chunks, 1, image).  One thread per (output pixel, 8-channel
+// chunk): 8 byte loads and ONE 16-byte store, consecutive threads write consecutive 16-byte pieces (a warp stores
+// 512 contiguous bytes).  UNIT_STD skips the division when std == 1 (x / 1.0f is exact, so the result is unchanged).
+struct Im2colBatch {
+  const void* img[CM2_MAX_BATCH_PTRS];
+  int h[CM2_MAX_BATCH_PTRS], w[CM2_MAX_BATCH_PTRS];
+};
+
+template <typename InT, bool UNIT_STD>
+__global__ void __launch_bounds__(256) preprocess_im2col_batch_kernel(Im2colBatch bt, int ho, int wo, float m0, float m1, float m2,
+                                                                      float r0, float r1, float r2, View<__nv_bfloat16> out, int b0) {
+  const int b = blockIdx.z;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned pix = idx >> 2;
+  const int chunk = idx & 3;
+  if (pix >= (unsigned)(ho * wo)) return;
+  const int oy = pix / (unsigned)wo, ox = pix - oy * wo;
+  const InT* __restrict__ img = reinterpret_cast<const InT*>(bt.img[b]);
+  const int h = bt.h[b], w = bt.w[b];
+  const size_t plane = (size_t)h * w;
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int e = chunk * 8 + k;                       // element (ky, kx, c) of the 27 (+5 zero) im2col channels
+    const int tap = e / 3, c = e - tap * 3;
+    const int ky = tap / 3, kx = tap - ky * 3;
+    const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
+    float val = 0.f;
+    if (e < 27 && iy >= 0 && iy < h && ix >= 0 && ix < w) {
+      const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+      val = (float)img[c * plane + (size_t)iy * w + ix] - mean;
+      if (!UNIT_STD) val = val / (c == 0 ? r0 : (c == 1 ? r1 : r2));
+    }
+    v[k] = val;
+  }
+  Vec8<__nv_bfloat16>::store(out.at(b0 + b, oy, ox) + chunk * 8, v);
+}
+
 // ---------------------------------------------------------------------------------------------
 // GroupNorm on a segmented halo tensor (all FPN levels of an FCOS tower in one launch set).
 // ---------------------------------------------------------------------------------------------
@@ -523,6 +563,38 @@ extern "C" int cm2_preprocess_im2col(const void* img, int32_t in_dtype, int32_t 
                                                            make_view<__nv_bfloat16>(*out), out_index);
   else { set_error("preprocess_im2col: unsupported input dtype %d", in_dtype); return CM2_ERR_UNSUPPORTED; }
   CM2_CHECK_LAUNCH("preprocess_im2col");
+  return CM2_OK;
+}
+
+extern "C" int cm2_preprocess_im2col_batch(const void* const* imgs, const int32_t* hs, const int32_t* ws, int32_t n, int32_t in_dtype,
+                                           int32_t hp, int32_t wp, const float* mean3, const float* std3, const cm2_act* out,
+                                           int32_t out_index0, void* stream) {
+  CM2_CHECK_ARG(imgs && hs && ws && out && out->data && mean3 && std3, "preprocess_im2col_batch: null pointer");
+  CM2_CHECK_ARG(n >= 0 && hp > 0 && wp > 0 && hp % 2 == 0 && wp % 2 == 0, "preprocess_im2col_batch: bad extents");
+  CM2_CHECK_ARG(out->h == hp / 2 && out->w == wp / 2 && out->c == 32 && out_index0 >= 0 && out_index0 + n <= out->n &&
+                vec8_ok(*out, 2), "preprocess_im2col_batch: out view [%d,%d,%d,%d] != [>=%d,%d,%d,32]", out->n, out->h, out->w,
+                out->c, out_index0 + n, hp / 2, wp / 2);
+  CM2_CHECK_ARG(in_dtype == CM2_F32 || in_dtype == CM2_U8, "preprocess_im2col_batch: unsupported input dtype %d", in_dtype);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool unit = std3[0] == 1.f && std3[1] == 1.f && std3[2] == 1.f;
+  for (int i0 = 0; i0 < n; i0 += CM2_MAX_BATCH_PTRS) {
+    const int nb = std::min(n - i0, (int)CM2_MAX_BATCH_PTRS);
+    Im2colBatch bt;
+    memset(&bt, 0, sizeof(bt));
+    for (int i = 0; i < nb; ++i) {
+      CM2_CHECK_ARG(imgs[i0 + i] && hs[i0 + i] > 0 && ws[i0 + i] > 0 && hs[i0 + i] <= hp && ws[i0 + i] <= wp,
+                    "preprocess_im2col_batch: image %d is %dx%d, padded extent %dx%d", i0 + i, hs[i0 + i], ws[i0 + i], hp, wp);
+      bt.img[i] = imgs[i0 + i]; bt.h[i] = hs[i0 + i]; bt.w[i] = ws[i0 + i];
+    }
+    dim3 grid(ceil_div(out->h * out->w * 4, 256), 1, nb);
+    View<__nv_bfloat16> ov = make_view<__nv_bfloat16>(*out);
+#define CM2_IM2COL(T, U) preprocess_im2col_batch_kernel<T, U><<<grid, 256, 0, s>>>(bt, out->h, out->w, mean3[0], mean3[1], mean3[2], \
+                                                                                   std3[0], std3[1], std3[2], ov, out_index0 + i0)
+    if (in_dtype == CM2_F32) { if (unit) CM2_IM2COL(float, true); else CM2_IM2COL(float, false); }
+    else { if (unit) CM2_IM2COL(uint8_t, true); else CM2_IM2COL(uint8_t, false); }
+#undef CM2_IM2COL
+    CM2_CHECK_LAUNCH("preprocess_im2col_batch");
+  }
   return CM2_OK;
 }
 

@@ -287,10 +287,13 @@ __global__ void __launch_bounds__(256) paste_masks_kernel(const float* __restric
       const long long fs = max(f, 0ll), fe = min(f + 16, hw);
       int y = (int)(fs / out_w), x = (int)(fs - (long long)y * out_w);
       const int y_last = (int)((fe - 1) / out_w);
-      if (y_last >= ya && y < yb) {
+      // quick reject: the piece lies in one row and entirely left / right of the box window
+      const bool miss_x = y == y_last && (x + (int)(fe - fs) <= xa || x >= xb);
+      if (y_last >= ya && y < yb && !miss_x) {
         int cur_y = -1;
         float wy0 = 0.f, wy1 = 0.f;
         int y0 = 0, y1 = 0;
+        bool y_in = false;
         for (long long ff = fs; ff < fe; ++ff) {
           if (y >= ya && y < yb && x >= xa && x < xb) {
             if (cur_y != y) {
@@ -300,6 +303,7 @@ __global__ void __launch_bounds__(256) paste_masks_kernel(const float* __restric
               float fy = floorf(iy);
               y0 = (int)fy; y1 = y0 + 1;
               wy1 = iy - fy; wy0 = (fy + 1.f) - iy;      // ATen: (iy_se - iy), (iy - iy_nw)
+              y_in = y0 >= 0 && y1 < m;
             }
             float gx = ((float)x + 0.5f - b.x) / bw * 2.f - 1.f;
             float ix = ((gx + 1.f) * fm - 1.f) * 0.5f;
@@ -307,13 +311,21 @@ __global__ void __launch_bounds__(256) paste_masks_kernel(const float* __restric
             int xl = (int)fx, xh = xl + 1;
             float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
             float v = 0.f;
-            bool yl_in = y0 >= 0 && y0 < m, yh_in = y1 >= 0 && y1 < m;
-            bool xl_in = xl >= 0 && xl < m, xh_in = xh >= 0 && xh < m;
             // same accumulation order as ATen's grid_sampler_2d (nw, ne, sw, se)
-            if (yl_in && xl_in) v += s_mask[y0 * m + xl] * (wx0 * wy0);
-            if (yl_in && xh_in) v += s_mask[y0 * m + xh] * (wx1 * wy0);
-            if (yh_in && xl_in) v += s_mask[y1 * m + xl] * (wx0 * wy1);
-            if (yh_in && xh_in) v += s_mask[y1 * m + xh] * (wx1 * wy1);
+            if (y_in && xl >= 0 && xh < m) {             // all four taps inside the mask: no bounds tests
+              const float* r0 = s_mask + y0 * m + xl;
+              v += r0[0] * (wx0 * wy0);
+              v += r0[1] * (wx1 * wy0);
+              v += r0[m] * (wx0 * wy1);
+              v += r0[m + 1] * (wx1 * wy1);
+            } else {
+              bool yl_in = y0 >= 0 && y0 < m, yh_in = y1 >= 0 && y1 < m;
+              bool xl_in = xl >= 0 && xl < m, xh_in = xh >= 0 && xh < m;
+              if (yl_in && xl_in) v += s_mask[y0 * m + xl] * (wx0 * wy0);
+              if (yl_in && xh_in) v += s_mask[y0 * m + xh] * (wx1 * wy0);
+              if (yh_in && xl_in) v += s_mask[y1 * m + xl] * (wx0 * wy1);
+              if (yh_in && xh_in) v += s_mask[y1 * m + xh] * (wx1 * wy1);
+            }
             if (v >= threshold) {
               const int k = (int)(ff - f);
               w[k >> 2] |= 1u << (8 * (k & 3));

@@ -601,8 +601,11 @@ class Engine(object):
         if self.tc and fused_stem and len(cfg.MODEL.PIXEL_MEAN) == 3:
             # normalise + pad + im2col of stem_1 in one pass (the TC engine then runs stem_1 as a 1x1 conv)
             x = self.fmap("input_im2col", len(images), hp // 2, wp // 2, 32)
-            for i, im in enumerate(images):
-                lib.preprocess_im2col(im.contiguous(), cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD, hp, wp, x.view, i)
+            if len({im.dtype for im in images}) == 1:
+                lib.preprocess_im2col_batch([im.contiguous() for im in images], cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD, hp, wp, x.view)
+            else:
+                for i, im in enumerate(images):
+                    lib.preprocess_im2col(im.contiguous(), cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD, hp, wp, x.view, i)
             return x, sizes
         x = self.fmap("input", len(images), hp, wp, 3)
         for i, im in enumerate(images):

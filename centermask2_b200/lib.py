@@ -65,6 +65,8 @@ SYMBOLS = {
     "cm2_conv_tc_supported": (_I, [C.POINTER(ConvDesc)]),
     "cm2_preprocess_image": (_I, [_P, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _AP, _I, _I, _P]),
     "cm2_preprocess_im2col": (_I, [_P, _I, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _AP, _I, _P]),
+    "cm2_preprocess_im2col_batch": (_I, [C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _AP,
+                                         _I, _P]),
     "cm2_phase_split": (_I, [_AP, _AP, _I, _I, _P]),
     "cm2_maxpool3x3s2_ceil": (_I, [_AP, _AP, _I, _P]),
     "cm2_ese_pool_chunks": (_I, [_I]),
@@ -223,6 +225,20 @@ def preprocess_im2col(img, mean, std, hp, wp, out, index):
     check(load().cm2_preprocess_im2col(ptr(img), dtype_code(img), img.shape[1], img.shape[2], hp, wp, m, s, C.byref(a),
                                        index, stream()), "cm2_preprocess_im2col")
     _count()
+
+
+def preprocess_im2col_batch(imgs, mean, std, hp, wp, out, index0=0):
+    """All images (same dtype; [3, h, w] planar, contiguous) in one launch."""
+    n = len(imgs)
+    ptrs = (_P * n)(*[im.data_ptr() for im in imgs])
+    hs = (_I * n)(*[im.shape[1] for im in imgs])
+    ws = (_I * n)(*[im.shape[2] for im in imgs])
+    m = (C.c_float * 3)(*mean)
+    s = (C.c_float * 3)(*std)
+    a = act(out)
+    check(load().cm2_preprocess_im2col_batch(ptrs, hs, ws, n, dtype_code(imgs[0]), hp, wp, m, s, C.byref(a), index0, stream()),
+          "cm2_preprocess_im2col_batch")
+    _count((n + 31) // 32)
 
 
 def phase_split(x, out_plane0, relu=False):

@@ -157,6 +157,12 @@ int cm2_preprocess_image(const void* img, int32_t in_dtype, int32_t h, int32_t w
 int cm2_preprocess_im2col(const void* img, int32_t in_dtype, int32_t h, int32_t w, int32_t hp, int32_t wp,
                           const float* mean3, const float* std3, const cm2_act* out, int32_t out_index,
                           void* stream);
+/* Whole batch in one launch (n <= CM2_MAX_BATCH_PTRS per launch; more are chunked): imgs / hs / ws are HOST arrays
+ * of n device pointers ([3, hs[i], ws[i]] planar images) and extents; image i goes to out[out_index0 + i]. */
+#define CM2_MAX_BATCH_PTRS 32
+int cm2_preprocess_im2col_batch(const void* const* imgs, const int32_t* hs, const int32_t* ws, int32_t n, int32_t in_dtype,
+                                int32_t hp, int32_t wp, const float* mean3, const float* std3, const cm2_act* out,
+                                int32_t out_index0, void* stream);
 
 /* MaxPool2d(3, stride 2, ceil_mode=True), vovnet.py:349-350. */
 int cm2_maxpool3x3s2_ceil(const cm2_act* in, const cm2_act* out, int32_t dtype, void* stream);

@@ -235,6 +235,26 @@ def test_fused_preprocess_im2col_stem1():
         assert nchw(out.view)[0].abs().max() == 0
 
 
+@pytest.mark.parametrize("std", [[1.0, 1.0, 1.0], [57.375, 57.12, 58.395]])
+def test_preprocess_im2col_batch_equals_per_image(std):
+    """One launch for the whole batch (images of different extents) == the per-image entry point, bit for bit."""
+    g = torch.Generator().manual_seed(13)
+    hp, wp = 64, 96
+    mean = [103.53, 116.28, 123.675]
+    imgs = [(torch.rand(3, h, w, generator=g) * 255).floor().to(torch.uint8).to(DEV) for h, w in ((45, 61), (64, 96), (33, 90))]
+    a, b = halo(torch.zeros(4, 32, hp // 2, wp // 2)), halo(torch.zeros(4, 32, hp // 2, wp // 2))
+    a.view.fill_(9.0)
+    b.view.fill_(9.0)
+    for i, im in enumerate(imgs):
+        lib.preprocess_im2col(im, mean, std, hp, wp, a.view, 1 + i)
+    lib.preprocess_im2col_batch(imgs, mean, std, hp, wp, b.view, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(a.buf, b.buf)
+    lib.preprocess_im2col_batch([im.float() for im in imgs], mean, std, hp, wp, b.view, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(a.buf, b.buf)
+
+
 def test_segmented_conv_and_groupnorm_match_per_level_results():
     """All FPN levels of an FCOS tower in one launch (cm2_seg): conv3x3 + bias, then GroupNorm(32)+ReLU in place."""
     from centermask2_b200.engine import SegMap
