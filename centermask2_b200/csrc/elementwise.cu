@@ -340,22 +340,17 @@ struct Im2colBatch {
   int h[CM2_MAX_BATCH_PTRS], w[CM2_MAX_BATCH_PTRS];
 };
 
-template <typename InT, bool UNIT_STD>
-__global__ void __launch_bounds__(256) preprocess_im2col_batch_kernel(Im2colBatch bt, int ho, int wo, float m0, float m1, float m2,
-                                                                      float r0, float r1, float r2, View<__nv_bfloat16> out, int b0) {
-  const int b = blockIdx.z;
-  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned pix = idx >> 2;
-  const int chunk = idx & 3;
-  if (pix >= (unsigned)(ho * wo)) return;
-  const int oy = pix / (unsigned)wo, ox = pix - oy * wo;
-  const InT* __restrict__ img = reinterpret_cast<const InT*>(bt.img[b]);
-  const int h = bt.h[b], w = bt.w[b];
-  const size_t plane = (size_t)h * w;
+constexpr int IM2COL_PIX_PER_BLOCK = 1024;
+
+template <typename InT, bool UNIT_STD, int CHUNK>
+__device__ __forceinline__ void im2col_chunk(const InT* __restrict__ img, int h, int w, size_t plane, int oy, int ox, float m0,
+                                             float m1, float m2, float r0, float r1, float r2, __nv_bfloat16* dst) {
   float v[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const int e = chunk * 8 + k;                       // element (ky, kx, c) of the 27 (+5 zero) im2col channels
+    constexpr int dummy = 0;
+    (void)dummy;
+    const int e = CHUNK * 8 + k;                       // compile-time: element (ky, kx, c) of the 27 (+5 zero) channels
     const int tap = e / 3, c = e - tap * 3;
     const int ky = tap / 3, kx = tap - ky * 3;
     const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
@@ -367,7 +362,31 @@ __global__ void __launch_bounds__(256) preprocess_im2col_batch_kernel(Im2colBatc
     }
     v[k] = val;
   }
-  Vec8<__nv_bfloat16>::store(out.at(b0 + b, oy, ox) + chunk * 8, v);
+  Vec8<__nv_bfloat16>::store(dst + CHUNK * 8, v);
+}
+
+template <typename InT, bool UNIT_STD>
+__global__ void __launch_bounds__(256) preprocess_im2col_batch_kernel(Im2colBatch bt, int ho, int wo, float m0, float m1, float m2,
+                                                                      float r0, float r1, float r2, View<__nv_bfloat16> out, int b0) {
+  const int b = blockIdx.z;
+  const InT* __restrict__ img = reinterpret_cast<const InT*>(bt.img[b]);
+  const int h = bt.h[b], w = bt.w[b];
+  const size_t plane = (size_t)h * w;
+  // a block covers IM2COL_PIX_PER_BLOCK consecutive output pixels, 64 per pass (67 200 tiny blocks per image batch were
+  // block-scheduling bound)
+#pragma unroll 1
+  for (int k = 0; k < IM2COL_PIX_PER_BLOCK / 64; ++k) {
+    const unsigned pix = blockIdx.x * IM2COL_PIX_PER_BLOCK + k * 64 + (threadIdx.x >> 2);
+    if (pix >= (unsigned)(ho * wo)) return;
+    const int oy = pix / (unsigned)wo, ox = pix - oy * wo;
+    __nv_bfloat16* dst = out.at(b0 + b, oy, ox);
+    switch (threadIdx.x & 3) {                          // the chunk index is a template argument: all tap / channel arithmetic folds
+      case 0: im2col_chunk<InT, UNIT_STD, 0>(img, h, w, plane, oy, ox, m0, m1, m2, r0, r1, r2, dst); break;
+      case 1: im2col_chunk<InT, UNIT_STD, 1>(img, h, w, plane, oy, ox, m0, m1, m2, r0, r1, r2, dst); break;
+      case 2: im2col_chunk<InT, UNIT_STD, 2>(img, h, w, plane, oy, ox, m0, m1, m2, r0, r1, r2, dst); break;
+      default: im2col_chunk<InT, UNIT_STD, 3>(img, h, w, plane, oy, ox, m0, m1, m2, r0, r1, r2, dst); break;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -586,7 +605,7 @@ extern "C" int cm2_preprocess_im2col_batch(const void* const* imgs, const int32_
                     "preprocess_im2col_batch: image %d is %dx%d, padded extent %dx%d", i0 + i, hs[i0 + i], ws[i0 + i], hp, wp);
       bt.img[i] = imgs[i0 + i]; bt.h[i] = hs[i0 + i]; bt.w[i] = ws[i0 + i];
     }
-    dim3 grid(ceil_div(out->h * out->w * 4, 256), 1, nb);
+    dim3 grid(ceil_div(out->h * out->w, IM2COL_PIX_PER_BLOCK), 1, nb);
     View<__nv_bfloat16> ov = make_view<__nv_bfloat16>(*out);
 #define CM2_IM2COL(T, U) preprocess_im2col_batch_kernel<T, U><<<grid, 256, 0, s>>>(bt, out->h, out->w, mean3[0], mean3[1], mean3[2], \
                                                                                    std3[0], std3[1], std3[2], ov, out_index0 + i0)

@@ -13,8 +13,11 @@ namespace cm2 {
 // ---------------------------------------------------------------------------------------------
 // decode: one warp per location; lanes stride over classes so the logits row is read coalesced.
 // ---------------------------------------------------------------------------------------------
+// `logit_floor` = logit(thresh) - 1e-3: logits below it cannot pass `sigmoid(x) > thresh` (nor `sigmoid(x) * ctr > thresh`,
+// ctr <= 1), so the exact ATen-arithmetic sigmoid is evaluated only for the ~0.1% of logits near or above the threshold.
 __global__ void fcos_decode_kernel(View<const float> logits, View<const float> regctr, int stride, float reg_scale, float thresh,
-                                   int thresh_with_ctr, int level, int num_levels, int cap, cm2_cand_buffers cand) {
+                                   float logit_floor, int thresh_with_ctr, int level, int num_levels, int cap,
+                                   cm2_cand_buffers cand) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -27,14 +30,17 @@ __global__ void fcos_decode_kernel(View<const float> logits, View<const float> r
     const int py_ = pos / w, px_ = pos - py_ * w;
     const float* lrow = logits.at(img, py_, px_);
     const float* rrow = regctr.at(img, py_, px_);
-    const float ctr = sigmoid_f32(__ldg(rrow + 4));
     const int seg = img * num_levels + level;
     for (int c0 = 0; c0 < ncls; c0 += 32) {
       int c = c0 + lane;
+      const float xl = c < ncls ? __ldg(lrow + c) : 0.f;
+      const bool near = c < ncls && xl >= logit_floor;
+      if (__ballot_sync(0xffffffffu, near) == 0) continue;                 // the common case: nothing near the threshold
       bool is_cand = false;
       float s = 0.f;
-      if (c < ncls) {
-        float p = sigmoid_f32(__ldg(lrow + c));
+      if (near) {
+        const float ctr = sigmoid_f32(__ldg(rrow + 4));
+        float p = sigmoid_f32(xl);
         s = p * ctr;
         is_cand = thresh_with_ctr ? (s > thresh) : (p > thresh);
       }
@@ -282,9 +288,11 @@ extern "C" int cm2_fcos_decode(const cm2_act* logits, const cm2_act* regctr, int
   if (total == 0) return CM2_OK;
   int64_t blocks = ceil_div64(total * 32, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
+  // thresh in (0, 1): prefilter in logit space with a 1e-3 safety margin; otherwise evaluate everything
+  const float logit_floor = (thresh > 0.f && thresh < 1.f) ? (float)(log((double)thresh / (1.0 - (double)thresh)) - 1e-3) : -INFINITY;
   fcos_decode_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(make_view<const float>(*logits),
                                                                    make_view<const float>(*regctr), stride, reg_scale, thresh,
-                                                                   thresh_with_ctr, level, num_levels, cap, *cand);
+                                                                   logit_floor, thresh_with_ctr, level, num_levels, cap, *cand);
   CM2_CHECK_LAUNCH("fcos_decode");
   return CM2_OK;
 }

@@ -118,6 +118,104 @@ __global__ void __launch_bounds__(256) gn_seg_apply_stats_kernel(T* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// packed helpers (bf16 vectors of 8 channels = one uint4)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmul.rn.f32x2 rd, ra, rb;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void ffma2p(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {          // round-to-nearest-even
+  uint32_t w;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));
+  return w;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {     // max(x, 0) then round
+  uint32_t w;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));
+  return w;
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm apply, bf16, one block per interior image line (no per-pixel index arithmetic): thread = (pixel lane,
+// 8-channel vector); the per-(image, group) coefficients are computed once per thread.  ~20 instructions per
+// 16-byte vector (the generic kernel above needed ~130 and was issue-bound at half of HBM speed).
+// ---------------------------------------------------------------------------------------------
+struct GnLineSegs {
+  int num;
+  int row0[CM2_MAX_SEG], pitch[CM2_MAX_SEG], plane[CM2_MAX_SEG], h[CM2_MAX_SEG], w[CM2_MAX_SEG], img0[CM2_MAX_SEG];
+  int line_prefix[CM2_MAX_SEG + 1];
+};
+
+__global__ void __launch_bounds__(256) gn_seg_apply_lines_kernel(__nv_bfloat16* __restrict__ x, int c, int cpg, GnLineSegs g,
+                                                                 const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float eps, int relu) {
+  const int line = blockIdx.x;
+  int s = 0;
+#pragma unroll
+  for (int j = 1; j < CM2_MAX_SEG; ++j)
+    if (j < g.num && line >= g.line_prefix[j]) s = j;
+  const int l = line - g.line_prefix[s];
+  const int img = l / g.h[s], y = l - img * g.h[s];
+  const int c8 = c >> 3;
+  const int cv = threadIdx.x % c8, p0 = threadIdx.x / c8, pstep = blockDim.x / c8;
+  const int w = g.w[s];
+  // coefficients of this thread's 8 channels: y = v * a + b
+  float a[8], b[8];
+  {
+    const int gi = g.img0[s] + img;
+    const int chunks_per_group = cpg >> 3;
+    const int grp = (cv * 8) / cpg;
+    const double* q = stats + ((size_t)gi * c8 + (size_t)grp * chunks_per_group) * 2;
+    double sum = 0.0, sq = 0.0;
+    for (int j = 0; j < chunks_per_group; ++j) { sum += q[2 * j]; sq += q[2 * j + 1]; }
+    const double cnt = (double)g.h[s] * (double)w * (double)cpg;
+    const double m = sum / cnt;
+    double var = sq / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    const float mean = (float)m, rstd = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gm = __ldg(gamma + cv * 8 + j);
+      a[j] = rstd * gm;
+      b[j] = __ldg(beta + cv * 8 + j) - mean * rstd * gm;
+    }
+  }
+  uint4* base = reinterpret_cast<uint4*>(x + ((size_t)g.row0[s] + (size_t)img * g.plane[s] + (size_t)(y + 1) * g.pitch[s] + 1) * c) + cv;
+  constexpr int U = 4;                                  // independent 16-byte loads in flight per thread
+  for (int px = p0; px < w; px += U * pstep) {
+    uint4 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (px + u * pstep < w) raw[u] = base[(size_t)(px + u * pstep) * c8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (px + u * pstep >= w) break;
+      const uint32_t in[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v0, v1;
+        ffma2p(v0, v1, bf_lo(in[j]), bf_hi(in[j]), a[2 * j], a[2 * j + 1], b[2 * j], b[2 * j + 1]);
+        o[j] = relu ? pack_bf16x2_relu(v0, v1) : pack_bf16x2(v0, v1);
+      }
+      base[(size_t)(px + u * pstep) * c8] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // eSE gate from fp64 channel sums: gate[b, o] = relu6(sum_i W[o,i] * mean[b,i] + bias[o] + 3) / 6
 // ---------------------------------------------------------------------------------------------
 __global__ void ese_gate_f64_kernel(const double* __restrict__ sums, double inv_count, const float* __restrict__ w,
@@ -223,6 +321,91 @@ __global__ void __launch_bounds__(256) ese_apply_pool_kernel(View<const T> x, co
   }
 }
 
+// bf16 fast path of the above: one block per (image, pooled line), thread = (pooled-pixel lane, 8-channel vector),
+// packed bf16x2 / f32x2 arithmetic.  Without identity the max is taken on the raw bf16 inputs and multiplied once
+// (gate >= 0 and rounding is monotone, so max_k round(x_k * g) == round(max_k(x_k) * g)): ~50 instructions per
+// pooled vector instead of ~400.
+template <bool IDN, bool FULL>
+__global__ void __launch_bounds__(256) ese_apply_pool_lines_kernel(View<const __nv_bfloat16> x, const float* __restrict__ gate,
+                                                                   View<const __nv_bfloat16> idn, View<__nv_bfloat16> full,
+                                                                   View<__nv_bfloat16> pool) {
+  const int b = blockIdx.y, oy = blockIdx.x;
+  const int c8 = x.c >> 3;
+  const int cv = threadIdx.x % c8, o0 = threadIdx.x / c8, ostep = blockDim.x / c8;
+  float gt[8];
+  {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)b * x.c + cv * 8));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)b * x.c + cv * 8) + 1);
+    gt[0] = a0.x; gt[1] = a0.y; gt[2] = a0.z; gt[3] = a0.w; gt[4] = a1.x; gt[5] = a1.y; gt[6] = a1.z; gt[7] = a1.w;
+  }
+  const int own_y = (oy == pool.h - 1) ? 3 : 2;
+  const int ny = min(3, x.h - 2 * oy);                  // valid window rows / cols (>= 1)
+  for (int ox = o0; ox < pool.w; ox += ostep) {
+    const int own_x = (ox == pool.w - 1) ? 3 : 2;
+    const int nx = min(3, x.w - 2 * ox);
+    uint4 rx[9], ri[9];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx)
+        if (dy < ny && dx < nx) {
+          rx[dy * 3 + dx] = __ldg(reinterpret_cast<const uint4*>(x.at(b, 2 * oy + dy, 2 * ox + dx) + cv * 8));
+          if (IDN) ri[dy * 3 + dx] = __ldg(reinterpret_cast<const uint4*>(idn.at(b, 2 * oy + dy, 2 * ox + dx) + cv * 8));
+        }
+    uint32_t m[4];
+    if (!IDN) {
+      m[0] = rx[0].x; m[1] = rx[0].y; m[2] = rx[0].z; m[3] = rx[0].w;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+          if (dy < ny && dx < nx) {
+            const uint4 r = rx[dy * 3 + dx];
+            m[0] = max_bf16x2(m[0], r.x); m[1] = max_bf16x2(m[1], r.y); m[2] = max_bf16x2(m[2], r.z); m[3] = max_bf16x2(m[3], r.w);
+            if (FULL && dy < own_y && dx < own_x) {
+              const uint32_t in[4] = {r.x, r.y, r.z, r.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float v0, v1;
+                fmul2(v0, v1, bf_lo(in[j]), bf_hi(in[j]), gt[2 * j], gt[2 * j + 1]);
+                o[j] = pack_bf16x2(v0, v1);
+              }
+              *reinterpret_cast<uint4*>(full.at(b, 2 * oy + dy, 2 * ox + dx) + cv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v0, v1;
+        fmul2(v0, v1, bf_lo(m[j]), bf_hi(m[j]), gt[2 * j], gt[2 * j + 1]);
+        m[j] = pack_bf16x2(v0, v1);
+      }
+    } else {
+      m[0] = m[1] = m[2] = m[3] = 0xff80ff80u;             // (-inf, -inf)
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+          if (dy < ny && dx < nx) {
+            const uint4 r = rx[dy * 3 + dx], q = ri[dy * 3 + dx];
+            const uint32_t in[4] = {r.x, r.y, r.z, r.w}, id[4] = {q.x, q.y, q.z, q.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              // two roundings, as ATen (x * g, then + identity): scalar intrinsics are never contracted
+              const float v0 = __fadd_rn(__fmul_rn(bf_lo(in[j]), gt[2 * j]), bf_lo(id[j]));
+              const float v1 = __fadd_rn(__fmul_rn(bf_hi(in[j]), gt[2 * j + 1]), bf_hi(id[j]));
+              o[j] = pack_bf16x2(v0, v1);
+              m[j] = max_bf16x2(m[j], o[j]);
+            }
+            if (FULL && dy < own_y && dx < own_x)
+              *reinterpret_cast<uint4*>(full.at(b, 2 * oy + dy, 2 * ox + dx) + cv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+    }
+    *reinterpret_cast<uint4*>(pool.at(b, oy, ox) + cv * 8) = make_uint4(m[0], m[1], m[2], m[3]);
+  }
+}
+
 // eSE apply over whole halo buffers (x, identity and out are interior views of identically shaped, contiguous
 // one-pixel-halo buffers): a flat streaming pass, halo included (0 * g + 0 = 0 keeps it zero).
 template <typename T>
@@ -286,10 +469,23 @@ extern "C" int cm2_groupnorm_apply_seg(void* x, int32_t dtype, int32_t c, int32_
     img0 += seg[i].n;
     end = seg[i].row0 + rows;
   }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == CM2_BF16 && 256 % (c / 8) == 0) {
+    GnLineSegs gl;
+    memset(&gl, 0, sizeof(gl));
+    gl.num = num_seg;
+    for (int i = 0; i < num_seg; ++i) {
+      gl.row0[i] = g.row0[i]; gl.pitch[i] = g.pitch[i]; gl.plane[i] = g.plane[i]; gl.h[i] = g.h[i]; gl.w[i] = g.w[i];
+      gl.img0[i] = g.img0[i];
+      gl.line_prefix[i + 1] = gl.line_prefix[i] + seg[i].n * seg[i].h;
+    }
+    gn_seg_apply_lines_kernel<<<gl.line_prefix[num_seg], 256, 0, s>>>((__nv_bfloat16*)x, c, c / groups, gl, stats, gamma, beta, eps, relu);
+    CM2_CHECK_LAUNCH("gn_seg_apply_lines");
+    return CM2_OK;
+  }
   const int total_rows = (int)end;
   const long long nvec = (long long)ceil_div(total_rows, GN_ROWS_PER_THREAD) * (c / 8);
   CM2_CHECK_ARG(nvec < (1ll << 32) - (1ll << 24), "groupnorm_apply_seg: too many elements for 32-bit indexing");
-  cudaStream_t s = (cudaStream_t)stream;
   const int grid = (int)std::min<long long>(ceil_div64(nvec, 256), 148 * 32);
   if (dtype == CM2_F32)
     gn_seg_apply_stats_kernel<float><<<grid, 256, 0, s>>>((float*)x, c, c / groups, g, total_rows, stats, gamma, beta, eps, relu);
@@ -339,6 +535,19 @@ extern "C" int cm2_ese_apply_pool(const cm2_act* x, const float* gate, const cm2
     po = *pool;
     const long long total = (long long)po.n * po.h * po.w * (x->c / 8);
     CM2_CHECK_ARG(total < (1ll << 32) - (1ll << 24), "ese_apply_pool: too many elements for 32-bit indexing");
+    const int c8 = x->c / 8;
+    if (dtype == CM2_BF16 && c8 <= 256 && x->n <= 65535) {
+      const int threads = c8 * std::max(1, 256 / c8);
+      dim3 grid(po.h, x->n);
+      View<const __nv_bfloat16> vx = make_view<const __nv_bfloat16>(*x), vi = make_view<const __nv_bfloat16>(idn);
+      View<__nv_bfloat16> vf = make_view<__nv_bfloat16>(fu), vp = make_view<__nv_bfloat16>(po);
+      if (idn.data && has_full) ese_apply_pool_lines_kernel<true, true><<<grid, threads, 0, s>>>(vx, gate, vi, vf, vp);
+      else if (idn.data) ese_apply_pool_lines_kernel<true, false><<<grid, threads, 0, s>>>(vx, gate, vi, vf, vp);
+      else if (has_full) ese_apply_pool_lines_kernel<false, true><<<grid, threads, 0, s>>>(vx, gate, vi, vf, vp);
+      else ese_apply_pool_lines_kernel<false, false><<<grid, threads, 0, s>>>(vx, gate, vi, vf, vp);
+      CM2_CHECK_LAUNCH("ese_apply_pool_lines");
+      return CM2_OK;
+    }
     const int grid = (int)std::min<long long>(ceil_div64(total, 256), 148 * 32);
     if (dtype == CM2_F32)
       ese_apply_pool_kernel<float><<<grid, 256, 0, s>>>(make_view<const float>(*x), gate, make_view<const float>(idn),
