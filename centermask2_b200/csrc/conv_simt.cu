@@ -263,7 +263,8 @@ extern "C" int cm2_conv2d(const cm2_conv_desc* d, void* stream) {
   int ho, wo;
   conv_out_extent(d, &ho, &wo);
   CM2_CHECK_ARG(ho > 0 && wo > 0, "conv2d: empty output");
-  CM2_CHECK_ARG(d->out_mode == 0 || (d->out_mode == 1 && d->cout % 4 == 0) || d->out_mode == 2, "conv2d: bad out_mode");
+  CM2_CHECK_ARG(d->out_mode == 0 || ((d->out_mode == 1 || d->out_mode == 3) && d->cout % 4 == 0) || d->out_mode == 2,
+                "conv2d: bad out_mode");
   CM2_CHECK_ARG(d->weight != nullptr && d->out.data != nullptr, "conv2d: null weight/out");
   if (d->out_mode == 0)
     CM2_CHECK_ARG(d->out.n == s0.n && d->out.h == ho && d->out.w == wo && d->out.c == d->cout,
@@ -273,6 +274,9 @@ extern "C" int cm2_conv2d(const cm2_conv_desc* d, void* stream) {
     CM2_CHECK_ARG(d->out.n == s0.n && d->out.h == (ho + 1) / 2 && d->out.w == (wo + 1) / 2 && d->out.c == d->cout,
                   "conv2d: phase-split out view [%d,%d,%d,%d] != expected [%d,%d,%d,%d]", d->out.n, d->out.h, d->out.w,
                   d->out.c, s0.n, (ho + 1) / 2, (wo + 1) / 2, d->cout);
+  else if (d->out_mode == 3)
+    CM2_CHECK_ARG(d->out.n == s0.n && d->out.h == 2 * ho && d->out.w == 2 * wo && d->out.c == 1 && d->engine == CM2_ENGINE_TC,
+                  "conv2d: fused deconv + predictor (TC engine) writes [%d,%d,%d,1]", s0.n, 2 * ho, 2 * wo);
   else
     CM2_CHECK_ARG(d->out.n == s0.n && d->out.h == 2 * ho && d->out.w == 2 * wo && d->out.c == d->cout / 4,
                   "conv2d: deconv out view [%d,%d,%d,%d] != expected [%d,%d,%d,%d]", d->out.n, d->out.h, d->out.w,

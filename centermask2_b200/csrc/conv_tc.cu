@@ -73,6 +73,8 @@ struct alignas(64) TcParams {
   int seg_img0[CM2_MAX_SEG];// global image index of the first image of every segment
   double rcp_plane, rcp_pitch;                       // 1 / plane, 1 / pitch (1 / w in dense mode): exact fast division
   double seg_rcp_plane[CM2_MAX_SEG], seg_rcp_pitch[CM2_MAX_SEG];
+  // out_mode 3: class-gathered mask predictor fused behind the 2x2 transposed conv
+  const float* pred_w; const float* pred_b; const long long* pred_cls; int pred_ncls;
   int epi_kind;             // staged-epilogue variant (see tc_epilogue_dispatch)
   int epi_sets;             // column sets of epilogue warps per 128-row accumulator (1, 2 or 4)
   int fast_store;           // 1: epilogue transposes through shared memory and writes 64-byte row segments
@@ -205,13 +207,21 @@ __device__ __forceinline__ int tc_tap_shift(const TcParams& p, int tap, int pitc
 // Per-tile epilogue vectors in shared memory: the epilogue warps cooperatively copy scale/shift of the tile's
 // bn columns (1 / 0 where absent or beyond cout) and meet on a named barrier; per-element __ldg in the
 // epilogue loop showed up as the top stall (long scoreboard on every FMUL) in ncu.
-__device__ __forceinline__ void tc_stage_scale_shift(const TcParams& p, uint32_t ss_smem, int n0, int tid_e, int n_epi) {
+__device__ __forceinline__ void tc_stage_scale_shift(const TcParams& p, uint32_t ss_smem, int n0, int tid_e, int n_epi, int m0) {
+  const float* pred_row = nullptr;
+  if (p.out_mode == 3) {                             // rows of a tile belong to one ROI (plane rows per ROI, plane % 128 == 0)
+    const int roi = m0 / p.plane;
+    int cls = p.pred_ncls == 1 ? 0 : (int)p.pred_cls[roi];
+    cls = min(max(cls, 0), p.pred_ncls - 1);
+    pred_row = p.pred_w + (size_t)cls * (p.cout >> 2);
+  }
   for (int i = tid_e; i < p.bn; i += n_epi) {
     const int co = n0 + i;
     float sc = 1.f, sh = 0.f;
     if (co < p.cout) {
       if (p.scale) sc = __ldg(p.scale + co);
       if (p.shift) sh = __ldg(p.shift + co);
+      if (pred_row) sc = __ldg(pred_row + (co % (p.cout >> 2)));
     }
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(ss_smem + 4u * i), "f"(sc) : "memory");
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(ss_smem + 1024u + 4u * i), "f"(sh) : "memory");
@@ -626,9 +636,64 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
   __syncwarp();
 }
 
+// out_mode 3 (sam.py:74-83, :96-97 + mask_head.py:196-216): the GEMM is the 2x2 transposed conv (column = quadrant *
+// cq + channel, one N tile per quadrant); each thread owns an input pixel, applies bias + ReLU + bf16 rounding (the
+// value the unfused pipeline stores), dots it with the predictor row of the ROI's class (staged in the "scale" slot)
+// and writes sigmoid(dot + b[cls]) to probs[roi, 2y + dy, 2x + dx].  The [R, 28, 28, 256] tensor is never materialised.
+__device__ __forceinline__ void tc_epilogue_deconv_predict(const TcParams& p, const TileGeom& g, uint32_t taddr, int m, int n0,
+                                                           uint32_t ss_smem) {
+  const int mr = m - g.row0;
+  const bool in_range = mr >= 0 && mr < g.rows;
+  int img = 0, y = 0, x = 0;
+  bool interior = false;
+  if (in_range) {
+    img = tc_fast_div(mr, g.plane, g.rcp_plane);
+    const int r = mr - img * g.plane;
+    const int yy = tc_fast_div(r, g.pitch, g.rcp_pitch), xx = r - yy * g.pitch;
+    y = yy - 1; x = xx - 1;
+    interior = y >= 0 && y < g.h && x >= 0 && x < g.w;
+  }
+  float dot0 = 0.f, dot1 = 0.f;
+  for (int c0 = 0; c0 < p.bn; c0 += 32) {
+    float v[32];
+    {
+      uint32_t raw[16], raw2[16];
+      __syncwarp();
+      tc_ld16(taddr + (uint32_t)c0, raw);
+      tc_ld16(taddr + (uint32_t)(c0 + 16), raw2);
+      tc_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(raw[j]); v[16 + j] = __uint_as_float(raw2[j]); }
+    }
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 wv = lds_f4(ss_smem + 4u * (uint32_t)(c0 + 4 * j4)), sh = lds_f4(ss_smem + 1024u + 4u * (uint32_t)(c0 + 4 * j4));
+      // relu(acc + bias) rounded to bf16, as stored by the unfused deconv
+      __nv_bfloat162 a = __floats2bfloat162_rn(fmaxf(v[4 * j4 + 0] + sh.x, 0.f), fmaxf(v[4 * j4 + 1] + sh.y, 0.f));
+      __nv_bfloat162 b = __floats2bfloat162_rn(fmaxf(v[4 * j4 + 2] + sh.z, 0.f), fmaxf(v[4 * j4 + 3] + sh.w, 0.f));
+      const uint32_t ua = *reinterpret_cast<uint32_t*>(&a), ub = *reinterpret_cast<uint32_t*>(&b);
+      ffma2(dot0, dot1, __uint_as_float(ua << 16), __uint_as_float(ua & 0xffff0000u), wv.x, wv.y, dot0, dot1);
+      ffma2(dot0, dot1, __uint_as_float(ub << 16), __uint_as_float(ub & 0xffff0000u), wv.z, wv.w, dot0, dot1);
+    }
+  }
+  if (interior && !(p.dbg & 1)) {
+    int cls = p.pred_ncls == 1 ? 0 : (int)p.pred_cls[img];
+    cls = min(max(cls, 0), p.pred_ncls - 1);
+    const int quad = n0 / (p.cout >> 2);
+    const float logit = (dot0 + dot1) + __ldg(p.pred_b + cls);
+    float* o = reinterpret_cast<float*>(p.out) + (long long)img * p.out_sn + (long long)(2 * y + (quad >> 1)) * p.out_sh +
+               (long long)(2 * x + (quad & 1)) * p.out_sw;
+    *o = 1.0f / (1.0f + expf(-logit));
+  }
+}
+
 // kind: 0 plain bf16, 1 bf16 + channel sums, 2 bf16 + GroupNorm sums, 3 bf16 + residual, 4 f32, 5 bf16 deconv scatter
 __device__ __forceinline__ void tc_epilogue_dispatch(const TcParams& p, const TileGeom& g, uint32_t taddr, int m, int n0,
                                                      uint32_t stage_smem, int lane, uint32_t ss_smem, int cset, int ncset) {
+  if (p.epi_kind == 6) {
+    if (cset == 0) tc_epilogue_deconv_predict(p, g, taddr, m, n0, ss_smem);
+    return;
+  }
   switch (p.epi_kind) {
     case 0: tc_epilogue_rows_staged<false, false, 0, false>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
     case 1: tc_epilogue_rows_staged<false, false, 1, false>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
@@ -763,7 +828,7 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc_kernel(const __grid
       // scale / shift of the tile's columns: staged once when there is a single N tile, else per tile (double buffered)
       const uint32_t ss = ss_base + (p.n_tiles == 1 ? 0u : parity * 2048u);
       if (p.n_tiles > 1 || t == (int)blockIdx.x)
-        tc_stage_scale_shift(p, ss, n0, (int)threadIdx.x - 64, 32 * n_epi_warps);      // overlaps the MMAs of this tile
+        tc_stage_scale_shift(p, ss, n0, (int)threadIdx.x - 64, 32 * n_epi_warps, m0);      // overlaps the MMAs of this tile
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * TC_ACC_COLS) + ((uint32_t)(q * 32) << 16);
@@ -966,7 +1031,7 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc2_kernel(const __gri
       const int m0 = (t / p.n_tiles) * 256, n0 = (t % p.n_tiles) * p.bn;
       const uint32_t ss = ss_base + (p.n_tiles == 1 ? 0u : parity * 2048u);
       if (p.n_tiles > 1 || t == (int)blockIdx.x)
-        tc_stage_scale_shift(p, ss, n0, (int)threadIdx.x - 64, 32 * n_epi_warps);
+        tc_stage_scale_shift(p, ss, n0, (int)threadIdx.x - 64, 32 * n_epi_warps, m0);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * 2 * half_cols + half * half_cols) + ((uint32_t)(q * 32) << 16);
@@ -1139,6 +1204,16 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   if (d->out_mode == 1) {
     TC_REQUIRE((d->cout / 4) % 16 == 0, "conv_tc: deconv scatter needs cout/4 %% 16 == 0");
   }
+  const bool pred = d->out_mode == 3;
+  if (pred) {
+    TC_REQUIRE(halo && !seg && !phase && p->taps == 1 && d->cout % 4 == 0 && (d->cout / 4) % 32 == 0 && d->cout / 4 <= 256,
+               "conv_tc: fused deconv + predictor needs a 1x1 GEMM over halo buffers with cout/4 a multiple of 32, <= 256");
+    TC_REQUIRE(p->plane % TC_BM == 0, "conv_tc: fused deconv + predictor needs (h+2)*(w+2) %% 128 == 0 (one ROI per tile)");
+    TC_REQUIRE(d->pred_w && d->pred_b && d->pred_cls && d->pred_ncls > 0 && d->out_dtype == CM2_F32 && !d->residual.data &&
+               !d->scale && !d->stats && d->relu, "conv_tc: fused deconv + predictor: missing predictor / unsupported epilogue flags");
+    TC_REQUIRE(d->out.c == 1 && d->out.h == 2 * s0.h && d->out.w == 2 * s0.w && d->out.n == s0.n,
+               "conv_tc: fused deconv + predictor writes probabilities [n, 2h, 2w, 1]");
+  }
   p->nblk_total = 0;
   for (int i = 0; i < d->num_src; ++i) p->nblk_total += (d->src[i].c + TC_BK - 1) / TC_BK;
   // ---- kernel variant: 256-row tiles (v2) whenever that still fills the machine, else 128-row tiles (v1)
@@ -1158,10 +1233,10 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   int k_total = 0;
   for (int i = 0; i < d->num_src; ++i) k_total += d->src[i].c;
   const int tiles256 = m_tiles256 * (cout_pad / bn2);
-  bool use_v2 = (merge_ok && bn2 <= 128 && tiles256 >= 2 * sms) || (phase && bn2 <= 128 && tiles256 >= sms) ||
+  bool use_v2 = !pred && (merge_ok && bn2 <= 128 && tiles256 >= 2 * sms) || (phase && bn2 <= 128 && tiles256 >= sms) ||
                 (p->taps == 1 && k_total <= 128 && tiles256 >= sms);
   if (env_variant == 1) use_v2 = false;
-  if (env_variant >= 2) use_v2 = true;
+  if (env_variant >= 2 && !pred) use_v2 = true;
   static const int env_sets1 = getenv("CM2_TC_EPI_SETS_V1") ? atoi(getenv("CM2_TC_EPI_SETS_V1")) : 2;
   static const int env_sets2 = getenv("CM2_TC_EPI_SETS_V2") ? atoi(getenv("CM2_TC_EPI_SETS_V2")) : 1;
   const int sets1 = env_sets1 == 1 ? 1 : 2;            // 64 + 128 * sets1 <= TC_MAX_THREADS
@@ -1194,7 +1269,7 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     p->variant = 1;
     p->epi_sets = sets1;
     p->m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
-    p->bn = pick_bn(cout_pad, p->m_tiles, sms);
+    p->bn = pred ? d->cout / 4 : pick_bn(cout_pad, p->m_tiles, sms);     // fused predictor: one N tile per quadrant
     p->n_tiles = (cout_pad + p->bn - 1) / p->bn;
     p->a_box_rows = TC_BM;
     const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p->bn * TC_BK * 2;
@@ -1231,6 +1306,12 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   static const int env_store = getenv("CM2_TC_FAST_STORE") ? atoi(getenv("CM2_TC_FAST_STORE")) : 1;
   p->fast_store = (env_store && p->out_vec && (d->out_mode != 1 || (d->cout / 4) % 32 == 0)) ? 1 : 0;
   p->epi_kind = p->out_f32 ? 4 : (p->res_mode ? 3 : (d->out_mode == 1 ? 5 : 0));
+  if (pred) {
+    p->fast_store = 1;                                 // dispatcher path; nothing is staged
+    p->epi_kind = 6;
+    p->pred_w = d->pred_w; p->pred_b = d->pred_b; p->pred_cls = reinterpret_cast<const long long*>(d->pred_cls);
+    p->pred_ncls = d->pred_ncls;
+  }
   if (p->fast_store) TC_REQUIRE(!(p->out_f32 && (p->res_mode || d->out_mode == 1)) && !(p->res_mode && d->out_mode == 1),
                                 "conv_tc: unsupported epilogue combination (f32 / residual / deconv)");
   if (d->stats) {

@@ -178,7 +178,7 @@ class Engine(object):
 
     # -- one convolution -------------------------------------------------------------------------
     def conv(self, name, srcs, w, out_dtype=None, residual=None, res_mode=0, out_mode=0, in_relu=False,
-             out_halo=1, stats=None, stats_mode=0, out=None):
+             out_halo=1, stats=None, stats_mode=0, out=None, pred=None):
         """One convolution.  ``srcs`` are FMaps (virtual concat) or, for a stride-2 conv on the TC engine,
         PhaseMaps.  ``out_mode`` 1 = deconv scatter, 2 = write the result as a PhaseMap."""
         x0 = srcs[0]
@@ -201,9 +201,9 @@ class Engine(object):
         kw = dict(scale=w.scale, shift=w.shift, relu=w.relu, in_relu=in_relu, src_phase=src_phase,
                   residual=None if residual is None else residual.view, res_mode=res_mode, out_mode=out_mode)
         if self.tc and w.w_tc is not None and lib.conv2d(views, w.w_tc, out.view, w.cout, w.k, w.stride, w.pad,
-                                                          engine=lib.ENGINE_TC, stats=stats, stats_mode=stats_mode, probe=True, **kw):
+                                                          engine=lib.ENGINE_TC, stats=stats, stats_mode=stats_mode, probe=True, pred=pred, **kw):
             return out
-        assert stats is None, "fused statistics require the tensor-core engine: " + lib.last_error()
+        assert stats is None and pred is None, "fused epilogues require the tensor-core engine: " + lib.last_error()
         lib.conv2d(views, w.w_simt, out.view, w.cout, w.k, w.stride, w.pad, engine=lib.ENGINE_SIMT, **kw)
         return out
 
@@ -561,11 +561,17 @@ class Engine(object):
             x = self.conv("mask_fcn{}".format(k + 1), [x], w)
         att = self.fmap("mask_att", R, res, res, x.c)
         lib.spatial_attention(x.view, att.view, P["sam_w"])
-        up = self.conv("mask_deconv", [att], P["deconv"], out_mode=1, out_halo=0)
         probs = self.buffer("mask_probs", (R, 1, 2 * res, 2 * res), torch.float32, False)
         ncls = P["pred_w"].shape[0]
         classes = det["classes"].reshape(-1)
-        lib.mask_predict(up.view, P["pred_w"], P["pred_b"], classes, ncls, probs)
+        dw = P["deconv"]
+        if self.tc and dw.w_tc is not None and ((res + 2) * (res + 2)) % 128 == 0 and (dw.cout // 4) % 32 == 0 and dw.cout // 4 <= 256:
+            # deconv + ReLU + class-gathered predictor + sigmoid in one launch (the [R, 28, 28, C] tensor is never stored)
+            self.conv("mask_deconv_predict", [att], dw, out_mode=3, out=FMap(probs.view(R, 2 * res, 2 * res, 1), 0),
+                      pred=(P["pred_w"], P["pred_b"], classes, ncls))
+        else:
+            up = self.conv("mask_deconv", [att], dw, out_mode=1, out_halo=0)
+            lib.mask_predict(up.view, P["pred_w"], P["pred_b"], classes, ncls, probs)
         mask_scores = None
         if cfg.MODEL.MASKIOU_ON:
             pm = self.fmap("iou_mask", R, res, res, 16)

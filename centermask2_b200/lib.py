@@ -40,7 +40,8 @@ class ConvDesc(C.Structure):
                 ("relu", C.c_int32), ("in_relu", C.c_int32),
                 ("residual", Act), ("res_mode", C.c_int32), ("out_mode", C.c_int32),
                 ("out", Act), ("stats", C.c_void_p), ("src_phase", C.c_int32), ("num_seg", C.c_int32),
-                ("seg", Seg * MAX_SEG), ("stats_mode", C.c_int32), ("reserved", C.c_int32)]
+                ("seg", Seg * MAX_SEG), ("stats_mode", C.c_int32), ("pred_ncls", C.c_int32),
+                ("pred_w", C.c_void_p), ("pred_b", C.c_void_p), ("pred_cls", C.c_void_p)]
 
 
 class CandBuffers(C.Structure):
@@ -167,8 +168,8 @@ def _count(k=1):
 # ------------------------------------------------------------------------------------------------
 def conv2d(srcs, weight, out, cout, k, stride, pad, scale=None, shift=None, relu=False, in_relu=False,
            residual=None, res_mode=0, out_mode=0, engine=ENGINE_SIMT, stats=None, stats_mode=0, probe=False, src_phase=False,
-           segs=None):
-    """Enqueue one convolution.  With ``probe=True`` (TC engine) the descriptor is first checked with
+           segs=None, pred=None):
+    """Enqueue one convolution.  ``pred`` = (pred_w, pred_b, classes, ncls) for out_mode 3.  With ``probe=True`` (TC engine) the descriptor is first checked with
     ``cm2_conv_tc_supported``; returns False without launching if the engine does not take it."""
     d = ConvDesc()
     d.dtype = dtype_code(srcs[0])
@@ -197,6 +198,8 @@ def conv2d(srcs, weight, out, cout, k, stride, pad, scale=None, shift=None, relu
     d.stats = 0 if stats is None else stats.data_ptr()
     d.stats_mode = stats_mode if stats is not None else 0
     d.src_phase = int(src_phase)
+    if pred is not None:
+        d.pred_w, d.pred_b, d.pred_cls, d.pred_ncls = pred[0].data_ptr(), pred[1].data_ptr(), pred[2].data_ptr(), int(pred[3])
     if probe and not load().cm2_conv_tc_supported(C.byref(d)):
         return False
     check(load().cm2_conv2d(C.byref(d), stream()), "cm2_conv2d")

@@ -112,7 +112,11 @@ typedef struct cm2_conv_desc {
                             + co goes to out[n, 2y+dy, 2x+dx, co]  (out is [n,2ho,2wo,cout/4])
                          2: phase-split store (TC engine): out is plane 0 of four phase planes,
                             [n, ceil(ho/2), ceil(wo/2), cout]; pixel (y,x) goes to plane
-                            (y&1)*2+(x&1) at (y>>1, x>>1)                                          */
+                            (y&1)*2+(x&1) at (y>>1, x>>1)
+                         3: (TC engine) out_mode 1 fused with the class-gathered mask predictor
+                            (sam.py:74-83, 96-97; mask_head.py:196-216): out is f32 [n, 2ho, 2wo, 1] =
+                            sigmoid(pred_w[cls_n] . relu(deconv)[n, y, x, :] + pred_b[cls_n]); the deconv
+                            output is rounded to bf16 in registers and never stored                       */
   cm2_act out;
   /* optional fused statistics of the stored (post-activation, bf16-rounded) interior outputs, fp64, zeroed by
    * the call and accumulated by the epilogue (see stats_mode below).  NULL: off.  TC engine only, bf16 output,
@@ -131,7 +135,10 @@ typedef struct cm2_conv_desc {
    * 2: stats = double [images][cout/8][2]     (sum, sum of squares) per 8-channel chunk (GroupNorm, fcos.py:182;
    *                                           consumed by cm2_groupnorm_apply_seg)                           */
   int32_t stats_mode;
-  int32_t reserved;
+  int32_t pred_ncls;        /* out_mode 3: number of predictor classes                                   */
+  const float* pred_w;      /* out_mode 3: device [pred_ncls][cout/4]                                    */
+  const float* pred_b;      /* out_mode 3: device [pred_ncls]                                            */
+  const int64_t* pred_cls;  /* out_mode 3: device [n] class per image (ROI); clamped to [0, pred_ncls)   */
 } cm2_conv_desc;
 
 int cm2_conv2d(const cm2_conv_desc* d, void* stream);

@@ -410,3 +410,33 @@ def test_ese_gate_f64_matches_reference():
     torch.cuda.synchronize()
     ref = F.relu6((sums / hw).float() @ w.t() + b + 3.0) / 6.0
     assert torch.allclose(gate.cpu(), ref, atol=2e-5)
+
+
+def test_conv_tc_deconv_with_fused_mask_predictor():
+    """out_mode 3: ConvTranspose2d(2, 2) + ReLU + class-gathered 1x1 predictor + sigmoid in one launch
+    (sam.py:74-83, :96-97; mask_head.py:196-216) == the unfused deconv (bf16 store) followed by cm2_mask_predict."""
+    g = torch.Generator().manual_seed(31)
+    r, c, s, ncls = 7, 256, 14, 80
+    x = rb(torch.randn(r, c, s, s, generator=g))
+    wd = rb(torch.randn(c, c, 2, 2, generator=g) / 16)
+    bd = torch.randn(c, generator=g) * 0.1
+    wp = torch.randn(ncls, c, generator=g) / 16
+    bp = torch.randn(ncls, generator=g) * 0.1
+    classes = torch.randint(0, ncls, (r,), generator=g)
+    cw = packing.deconv2x2({"d.weight": wd, "d.bias": bd}, "d", BF, DEV, True)
+    probs = torch.full((r, 2 * s, 2 * s, 1), -1.0, device=DEV)
+    assert lib.conv2d([halo(x).view], cw.w_tc, probs, 4 * c, 1, 1, 0, shift=cw.shift, relu=True, out_mode=3, engine=lib.ENGINE_TC,
+                      probe=True, pred=(wp.to(DEV), bp.to(DEV), classes.to(DEV), ncls)), lib.last_error()
+    torch.cuda.synchronize()
+    up = rb(F.relu(F.conv_transpose2d(x, wd, bd, stride=2)))                       # what the unfused deconv stores
+    logits = torch.einsum("rchw,rc->rhw", up, wp[classes]) + bp[classes].view(r, 1, 1)
+    ref = torch.sigmoid(logits)
+    got = probs[..., 0].cpu()
+    assert (got - ref).abs().max().item() <= 2e-3, (got - ref).abs().max().item()
+    # and against the unfused kernels of the library itself
+    up_dev = torch.zeros((r, 2 * s, 2 * s, c), dtype=BF, device=DEV)
+    assert lib.conv2d([halo(x).view], cw.w_tc, up_dev, 4 * c, 1, 1, 0, shift=cw.shift, relu=True, out_mode=1, engine=lib.ENGINE_TC, probe=True)
+    p2 = torch.zeros((r, 1, 2 * s, 2 * s), device=DEV)
+    lib.mask_predict(up_dev, wp.to(DEV), bp.to(DEV), classes.to(DEV), ncls, p2)
+    torch.cuda.synchronize()
+    assert (probs[..., 0] - p2[:, 0]).abs().max().item() <= 1e-5
