@@ -101,11 +101,17 @@ class GeneralizedRCNN(nn.Module):
             boxes = boxes.clone()
             h_valid = eng.pinned("h_valid", (n, r_cap), torch.uint8)
             h_valid.copy_(valid, non_blocking=True)
-            masks = eng.paste_batch(probs, boxes, valid, out_sizes, dtype=torch.bool) if probs is not None else None
         else:
             boxes = det["boxes"].clone()
             pm = probs.clone() if probs is not None else None
-        torch.cuda.current_stream(eng.device).synchronize()
+        # the host needs only the counts / validity flags: wait for those, and let the paste-back kernel (the last ~3% of
+        # the device work) run while the Instances are assembled -- everything returned is stream-ordered device memory
+        ready = torch.cuda.Event()
+        ready.record()
+        masks = None
+        if do_postprocess and probs is not None:
+            masks = eng.paste_batch(probs, boxes, valid, out_sizes, dtype=torch.bool)
+        ready.synchronize()
         counts = h_count.tolist()
         if bool((h_cand > det["cand_cap"]).any()):
             raise RuntimeError("FCOS candidate buffer overflow (> {} candidates above threshold in one level)".format(det["cand_cap"]))

@@ -18,23 +18,33 @@ def shard_range(n_items, rank, world):
 
 
 def pack_records(instances_list, r_cap, device=None):
-    """list[Instances] -> float32 [len, r_cap, RECORD_FIELDS] (zero padded; field 7 = number of detections)."""
-    rec = []
-    for inst in instances_list:
-        k = len(inst)
-        dev = device if device is not None else inst.scores.device
-        t = torch.zeros((r_cap, RECORD_FIELDS), dtype=torch.float32, device=dev)
-        if k:
-            t[:k, :4] = inst.pred_boxes.tensor
-            t[:k, 4] = inst.scores
-            t[:k, 5] = inst.pred_classes.to(torch.float32)
-            if inst.has("mask_scores"):
-                t[:k, 6] = inst.mask_scores
-        t[:, 7] = float(k)
-        rec.append(t)
-    if not rec:
+    """list[Instances] -> float32 [len, r_cap, RECORD_FIELDS] (zero padded; field 7 = number of detections).
+    A handful of batched ops for the whole list (one cat per field, one scatter), not a loop of small kernels."""
+    n = len(instances_list)
+    if n == 0:
         return torch.zeros((0, r_cap, RECORD_FIELDS), dtype=torch.float32, device=device)
-    return torch.stack(rec)
+    dev = device if device is not None else instances_list[0].scores.device
+    counts = [min(len(inst), r_cap) for inst in instances_list]
+    rec = torch.zeros((n, r_cap, RECORD_FIELDS), dtype=torch.float32, device=dev)
+    rec[:, :, 7] = torch.tensor(counts, dtype=torch.float32).to(dev, non_blocking=True).view(n, 1)
+    total = sum(counts)
+    if total:
+        rows = torch.cat([torch.arange(k, dtype=torch.int64) + i * r_cap for i, k in enumerate(counts) if k]).to(dev, non_blocking=True)
+        live = [(inst, k) for inst, k in zip(instances_list, counts) if k]
+        vals = torch.zeros((total, 7), dtype=torch.float32, device=dev)
+        vals[:, :4] = torch.cat([inst.pred_boxes.tensor[:k] for inst, k in live]).to(dev)
+        vals[:, 4] = torch.cat([inst.scores[:k] for inst, k in live]).to(dev)
+        vals[:, 5] = torch.cat([inst.pred_classes[:k] for inst, k in live]).to(dev, torch.float32)
+        if all(inst.has("mask_scores") for inst, _ in live):
+            vals[:, 6] = torch.cat([inst.mask_scores[:k] for inst, k in live]).to(dev)
+        else:
+            off = 0
+            for inst, k in live:
+                if inst.has("mask_scores"):
+                    vals[off:off + k, 6] = inst.mask_scores[:k].to(dev)
+                off += k
+        rec.view(n * r_cap, RECORD_FIELDS)[rows, :7] = vals
+    return rec
 
 
 def gather_records(local, n_items, group=None):
