@@ -423,13 +423,24 @@ __global__ void __launch_bounds__(256) preprocess_im2col_u8_tiled_kernel(Im2colB
   const int h = bt.h[b], w = bt.w[b];
   const size_t plane = (size_t)h * w;
   constexpr int COLS = 2 * IM2COL_TILE + 1;
-  for (int i = threadIdx.x; i < 9 * COLS; i += blockDim.x) {
+  constexpr int ITERS = (9 * COLS + 255) / 256;
+  // all loads of a thread are issued before the first shared-memory store (a load -> store loop pays one L2 latency per
+  // iteration: 19 x ~700 cycles per block)
+  uint8_t stage[ITERS];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int i = it * 256 + threadIdx.x;
     const int pr = i / COLS, col = i - pr * COLS;
     const int c = pr / 3, ky = pr - c * 3;
     const int iy = 2 * oy + ky - 1, ix = 2 * ox0 - 1 + col;
-    uint8_t val = 0;
-    if (iy >= 0 && iy < h && ix >= 0 && ix < w) val = img[c * plane + (size_t)iy * w + ix];
-    tile[pr][col] = val;
+    stage[it] = 0;
+    if (i < 9 * COLS && iy >= 0 && iy < h && ix >= 0 && ix < w) stage[it] = __ldg(img + c * plane + (size_t)iy * w + ix);
+  }
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int i = it * 256 + threadIdx.x;
+    const int pr = i / COLS, col = i - pr * COLS;
+    if (i < 9 * COLS) tile[pr][col] = stage[it];
   }
   __syncthreads();
 #pragma unroll 1
