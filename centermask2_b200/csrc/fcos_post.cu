@@ -7,6 +7,7 @@
 // Determinism: candidates are appended with atomics (unordered), then every (image, level) segment
 // is sorted by (raw score desc, flat index asc), which makes all later stages order-independent.
 #include "common.cuh"
+#include <algorithm>
 
 namespace cm2 {
 
@@ -15,6 +16,65 @@ namespace cm2 {
 // ---------------------------------------------------------------------------------------------
 // `logit_floor` = logit(thresh) - 1e-3: logits below it cannot pass `sigmoid(x) > thresh` (nor `sigmoid(x) * ctr > thresh`,
 // ctr <= 1), so the exact ATen-arithmetic sigmoid is evaluated only for the ~0.1% of logits near or above the threshold.
+__device__ __forceinline__ void fcos_emit_candidate(const View<const float>& regctr, int img, int py_, int px_, int c, int ncls,
+                                                    float xl, int stride, float reg_scale, float thresh, int thresh_with_ctr,
+                                                    int level, int num_levels, int cap, const cm2_cand_buffers& cand) {
+  const float* rrow = regctr.at(img, py_, px_);
+  const float ctr = sigmoid_f32(__ldg(rrow + 4));
+  const float p = sigmoid_f32(xl);
+  const float s = p * ctr;
+  if (!(thresh_with_ctr ? (s > thresh) : (p > thresh))) return;
+  const int seg = img * num_levels + level;
+  const int slot = atomicAdd(cand.count + seg, 1);
+  if (slot >= cap) return;
+  float l = fmaxf(__ldg(rrow + 0) * reg_scale, 0.f) * (float)stride;
+  float t = fmaxf(__ldg(rrow + 1) * reg_scale, 0.f) * (float)stride;
+  float r = fmaxf(__ldg(rrow + 2) * reg_scale, 0.f) * (float)stride;
+  float b = fmaxf(__ldg(rrow + 3) * reg_scale, 0.f) * (float)stride;
+  float px = (float)(px_ * stride + stride / 2);
+  float py = (float)(py_ * stride + stride / 2);
+  size_t o = (size_t)seg * cap + slot;
+  reinterpret_cast<float4*>(cand.boxes)[o] = make_float4(px - l, py - t, px + r, py + b);
+  cand.score[o] = s;
+  cand.cls[o] = c;
+  cand.flat[o] = (py_ * regctr.w + px_) * ncls + c;
+}
+
+// Streaming variant (needs ncls % 4 == 0, pixel stride == ncls and 16-byte aligned rows): grid (row-chunks, h, n); an
+// image row of the level is w * ncls contiguous floats, read as float4 with four loads in flight per thread -- the
+// common case costs one 128-bit load and four compares per four logits.
+__global__ void __launch_bounds__(256) fcos_decode_rows_kernel(View<const float> logits, View<const float> regctr, int stride,
+                                                               float reg_scale, float thresh, float logit_floor, int thresh_with_ctr,
+                                                               int level, int num_levels, int cap, cm2_cand_buffers cand) {
+  const int img = blockIdx.z, py_ = blockIdx.y;
+  const int ncls = logits.c;
+  const int n4 = (logits.w * ncls) >> 2;
+  const float4* row = reinterpret_cast<const float4*>(logits.at(img, py_, 0));
+  constexpr int U = 4;
+  for (int i0 = blockIdx.x * blockDim.x * U + threadIdx.x; i0 < n4; i0 += gridDim.x * blockDim.x * U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i0 + u * (int)blockDim.x < n4) v[u] = __ldg(row + i0 + u * blockDim.x);
+      else v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float m4 = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
+      if (i0 + u * (int)blockDim.x < n4 && m4 >= logit_floor) {      // rare
+        const int e = (i0 + u * (int)blockDim.x) * 4;
+        const int px_ = e / ncls, c = e - px_ * ncls;
+        const float vals[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (vals[k] >= logit_floor)
+            fcos_emit_candidate(regctr, img, py_, px_, c + k, ncls, vals[k], stride, reg_scale, thresh, thresh_with_ctr, level,
+                                num_levels, cap, cand);
+      }
+    }
+  }
+}
+
+// Generic variant: one warp per location; lanes stride over classes.
 __global__ void fcos_decode_kernel(View<const float> logits, View<const float> regctr, int stride, float reg_scale, float thresh,
                                    float logit_floor, int thresh_with_ctr, int level, int num_levels, int cap,
                                    cm2_cand_buffers cand) {
@@ -29,42 +89,12 @@ __global__ void fcos_decode_kernel(View<const float> logits, View<const float> r
     const int pos = (int)(loc - (int64_t)img * hw);
     const int py_ = pos / w, px_ = pos - py_ * w;
     const float* lrow = logits.at(img, py_, px_);
-    const float* rrow = regctr.at(img, py_, px_);
-    const int seg = img * num_levels + level;
     for (int c0 = 0; c0 < ncls; c0 += 32) {
-      int c = c0 + lane;
+      const int c = c0 + lane;
       const float xl = c < ncls ? __ldg(lrow + c) : 0.f;
-      const bool near = c < ncls && xl >= logit_floor;
-      if (__ballot_sync(0xffffffffu, near) == 0) continue;                 // the common case: nothing near the threshold
-      bool is_cand = false;
-      float s = 0.f;
-      if (near) {
-        const float ctr = sigmoid_f32(__ldg(rrow + 4));
-        float p = sigmoid_f32(xl);
-        s = p * ctr;
-        is_cand = thresh_with_ctr ? (s > thresh) : (p > thresh);
-      }
-      unsigned m = __ballot_sync(0xffffffffu, is_cand);
-      if (m == 0) continue;
-      int base = 0;
-      if (lane == 0) base = atomicAdd(cand.count + seg, __popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (is_cand) {
-        int slot = base + __popc(m & ((1u << lane) - 1));
-        if (slot < cap) {
-          float l = fmaxf(__ldg(rrow + 0) * reg_scale, 0.f) * (float)stride;
-          float t = fmaxf(__ldg(rrow + 1) * reg_scale, 0.f) * (float)stride;
-          float r = fmaxf(__ldg(rrow + 2) * reg_scale, 0.f) * (float)stride;
-          float b = fmaxf(__ldg(rrow + 3) * reg_scale, 0.f) * (float)stride;
-          float px = (float)(px_ * stride + stride / 2);
-          float py = (float)(py_ * stride + stride / 2);
-          size_t o = (size_t)seg * cap + slot;
-          reinterpret_cast<float4*>(cand.boxes)[o] = make_float4(px - l, py - t, px + r, py + b);
-          cand.score[o] = s;
-          cand.cls[o] = c;
-          cand.flat[o] = pos * ncls + c;
-        }
-      }
+      if (c < ncls && xl >= logit_floor)
+        fcos_emit_candidate(regctr, img, py_, px_, c, ncls, xl, stride, reg_scale, thresh, thresh_with_ctr, level, num_levels, cap,
+                            cand);
     }
   }
 }
@@ -290,6 +320,16 @@ extern "C" int cm2_fcos_decode(const cm2_act* logits, const cm2_act* regctr, int
   if (blocks > 148 * 8) blocks = 148 * 8;
   // thresh in (0, 1): prefilter in logit space with a 1e-3 safety margin; otherwise evaluate everything
   const float logit_floor = (thresh > 0.f && thresh < 1.f) ? (float)(log((double)thresh / (1.0 - (double)thresh)) - 1e-3) : -INFINITY;
+  if (logits->c % 4 == 0 && logits->sw == logits->c && logits->sh % 4 == 0 && logits->sn % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(logits->data) & 15) == 0 && logits->h <= 65535 && logits->n <= 65535) {
+    const int n4 = logits->w * logits->c / 4;
+    dim3 grid(std::max(1, std::min(8, ceil_div(n4, 256 * 4))), logits->h, logits->n);
+    fcos_decode_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(make_view<const float>(*logits), make_view<const float>(*regctr),
+                                                                    stride, reg_scale, thresh, logit_floor, thresh_with_ctr, level,
+                                                                    num_levels, cap, *cand);
+    CM2_CHECK_LAUNCH("fcos_decode_rows");
+    return CM2_OK;
+  }
   fcos_decode_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(make_view<const float>(*logits),
                                                                    make_view<const float>(*regctr), stride, reg_scale, thresh,
                                                                    logit_floor, thresh_with_ctr, level, num_levels, cap, *cand);

@@ -159,6 +159,69 @@ __global__ void __launch_bounds__(256) spatial_attention_kernel(View<const T> x,
   }
 }
 
+// bf16 variant that keeps the ROI's [S, S, C] tile in shared memory between the pooling and the scaling phase
+// (100 KB for 14x14x256): the tensor is read once and written once instead of read twice.
+__global__ void __launch_bounds__(512) spatial_attention_smem_kernel(View<const __nv_bfloat16> x, View<__nv_bfloat16> out,
+                                                                     const float* __restrict__ w18) {
+  extern __shared__ uint4 s_x[];                        // [S*S][c8]
+  __shared__ float s_avg[SAM_MAX_S * SAM_MAX_S], s_max[SAM_MAX_S * SAM_MAX_S], s_att[SAM_MAX_S * SAM_MAX_S];
+  __shared__ float s_w[18];
+  const int r = blockIdx.x;
+  const int S = x.h, C = x.c, c8 = C >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (threadIdx.x < 18) s_w[threadIdx.x] = w18[threadIdx.x];
+  for (int pix = warp; pix < S * S; pix += nwarps) {
+    const int y = pix / S, xx = pix - y * S;
+    const uint4* row = reinterpret_cast<const uint4*>(x.at(r, y, xx));
+    float sum = 0.f, mx = -INFINITY;
+    for (int cv = lane; cv < c8; cv += 32) {
+      const uint4 q = __ldg(row + cv);
+      s_x[pix * c8 + cv] = q;
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float lo = __uint_as_float(w[k] << 16), hi = __uint_as_float(w[k] & 0xffff0000u);
+        sum += lo; sum += hi;
+        mx = fmaxf(mx, fmaxf(lo, hi));
+      }
+    }
+    sum = warp_sum(sum);
+    mx = warp_max(mx);
+    if (lane == 0) { s_avg[pix] = sum / (float)C; s_max[pix] = mx; }
+  }
+  __syncthreads();
+  for (int pix = threadIdx.x; pix < S * S; pix += blockDim.x) {
+    const int y = pix / S, xx = pix - y * S;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int iy = y + ky - 1, ix = xx + kx - 1;
+        if (iy >= 0 && iy < S && ix >= 0 && ix < S) {
+          acc = fmaf(s_w[ky * 3 + kx], s_avg[iy * S + ix], acc);
+          acc = fmaf(s_w[9 + ky * 3 + kx], s_max[iy * S + ix], acc);
+        }
+      }
+    s_att[pix] = sigmoid_f32(acc);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < S * S * c8; i += blockDim.x) {
+    const int pix = i / c8, cv = i - pix * c8;
+    const int y = pix / S, xx = pix - y * S;
+    const uint4 q = s_x[i];
+    const float a = s_att[pix];
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(w[k] << 16) * a, __uint_as_float(w[k] & 0xffff0000u) * a);
+      o[k] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(out.at(r, y, xx) + cv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // predictor restricted to the predicted class + sigmoid (sam.py:97, mask_head.py:196-216).
 // warp per output pixel; lanes stride over channels.
@@ -248,98 +311,158 @@ __global__ void scale_clip_boxes_batch_kernel(const float* __restrict__ in, floa
   valid[i] = ((b.z - b.x) > 0.f && (b.w - b.y) > 0.f) ? 1 : 0;
 }
 
-// Mask paste-back.  The output of one ROI is treated as a flat byte string of out_h*out_w bytes (rows of an
-// 800x1333 mask are not 4-byte aligned, so a per-row vector store is impossible); it is cut into absolute
-// 16-byte-aligned pieces, one 128-bit store each.  grid (spans, r): a block covers PASTE_SPAN consecutive bytes
-// of ROI r and loads the 28x28 probabilities only if its rows intersect the (dilated) box -- most blocks are
-// pure zero fill at store bandwidth.
+// Mask paste-back in two steps: (1) the whole [r, out_h, out_w] buffer is cleared with one memset at store bandwidth
+// (most bytes lie outside their box); (2) paste_window_kernel visits only the dilated box window
+// [floor(x0)-1, ceil(x1)+1) x [floor(y0)-1, ceil(y1)+1) of every valid ROI.  grid (PASTE_CTAS_PER_ROI, r): a CTA keeps
+// the 28x28 probabilities in shared memory with a zero border (index clamping replaces the four bounds tests of
+// grid_sample's zero padding) and walks the window in tiles of 8 rows x 256 columns; a thread owns one column of the
+// tile, so the x interpolation coefficients are computed once per 8 pixels.  Rows of an 800x1333 mask are not even
+// 2-byte aligned, so the window is written with byte stores (32 consecutive bytes per warp instruction).
 // grid_sample(bilinear, zeros, align_corners=False): ix = ((gx + 1) * m - 1) / 2.
-constexpr int PASTE_ITERS = 4;
-constexpr int PASTE_SPAN = 256 * 16 * PASTE_ITERS;
-__global__ void __launch_bounds__(256) paste_masks_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
-                                                          const uint8_t* __restrict__ valid, uint8_t* __restrict__ out,
-                                                          int m, int out_h, int out_w, float threshold) {
-  extern __shared__ float s_mask[];
+constexpr int PASTE_CTAS_PER_ROI = 8;
+constexpr int PASTE_MAX_W = 4096;                      // widest output the column table supports (else byte kernel)
+
+// Word variant (out_h * out_w % 4 == 0 and a 4-byte aligned buffer, so every ROI plane starts on a word): a warp takes
+// one window row at a time and its lanes own consecutive aligned 32-bit words of the flat plane, i.e. 128 pixels per
+// warp instruction and full-sector stores (byte stores into lines that are not L2-resident cost a DRAM fill each).
+// Bytes of a boundary word that fall outside the window are zeros by definition, so whole words can be written.  The
+// x interpolation (tap columns + weights) is tabulated once per CTA in shared memory.
+struct __align__(16) PasteCol { float wx0, wx1; int cl, ch; };
+
+__global__ void __launch_bounds__(256) paste_window_words_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
+                                                                 const uint8_t* __restrict__ valid, uint8_t* __restrict__ out,
+                                                                 int m, int out_h, int out_w, float threshold) {
+  extern __shared__ float s_dyn[];                     // (m + 2)^2 mask with zero border, then the column table
   const int r = blockIdx.y;
-  const long long hw = (long long)out_h * out_w;
-  uint8_t* obase = out + (size_t)r * hw;
-  const long long lead = (long long)(reinterpret_cast<uintptr_t>(obase) & 15);     // bytes before obase in its first 16B piece
-  const long long f_lo = (long long)blockIdx.x * PASTE_SPAN - lead;               // flat range of this block
-  if (f_lo >= hw) return;
-  const long long f_hi = min(f_lo + PASTE_SPAN, hw);
+  if (valid[r] == 0) return;
   const float4 b = reinterpret_cast<const float4*>(boxes)[r];
   const int xa = max((int)floorf(b.x) - 1, 0), ya = max((int)floorf(b.y) - 1, 0);
   const int xb = min((int)ceilf(b.z) + 1, out_w), yb = min((int)ceilf(b.w) + 1, out_h);
-  const float bw = b.z - b.x, bh = b.w - b.y;
-  const int row_lo = (int)(max(f_lo, 0ll) / out_w), row_hi = (int)((f_hi - 1) / out_w);
-  const bool touch = valid[r] != 0 && row_hi >= ya && row_lo < yb && xa < xb;      // block-uniform
-  if (touch) {
-    for (int i = threadIdx.x; i < m * m; i += blockDim.x) s_mask[i] = probs[(size_t)r * m * m + i];
-    __syncthreads();
+  if (xa >= xb || ya >= yb) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  if ((int)blockIdx.x * nwarps >= yb - ya) return;
+  const int mp = m + 2;
+  float* s_mask = s_dyn;
+  PasteCol* s_col = reinterpret_cast<PasteCol*>(s_dyn + ((mp * mp + 3) & ~3));
+  for (int i = threadIdx.x; i < mp * mp; i += blockDim.x) {
+    const int yy = i / mp - 1, xx = i - (yy + 1) * mp - 1;
+    s_mask[i] = (yy >= 0 && yy < m && xx >= 0 && xx < m) ? probs[(size_t)r * m * m + yy * m + xx] : 0.f;
   }
-  const float fm = (float)m;
-#pragma unroll 1
-  for (int it = 0; it < PASTE_ITERS; ++it) {
-    const long long f = f_lo + (long long)(it * 256 + threadIdx.x) * 16;
-    if (f >= hw) break;
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-    if (touch) {
-      const long long fs = max(f, 0ll), fe = min(f + 16, hw);
-      int y = (int)(fs / out_w), x = (int)(fs - (long long)y * out_w);
-      const int y_last = (int)((fe - 1) / out_w);
-      // quick reject: the piece lies in one row and entirely left / right of the box window
-      const bool miss_x = y == y_last && (x + (int)(fe - fs) <= xa || x >= xb);
-      if (y_last >= ya && y < yb && !miss_x) {
-        int cur_y = -1;
-        float wy0 = 0.f, wy1 = 0.f;
-        int y0 = 0, y1 = 0;
-        bool y_in = false;
-        for (long long ff = fs; ff < fe; ++ff) {
-          if (y >= ya && y < yb && x >= xa && x < xb) {
-            if (cur_y != y) {
-              cur_y = y;
-              float gy = ((float)y + 0.5f - b.y) / bh * 2.f - 1.f;
-              float iy = ((gy + 1.f) * fm - 1.f) * 0.5f;
-              float fy = floorf(iy);
-              y0 = (int)fy; y1 = y0 + 1;
-              wy1 = iy - fy; wy0 = (fy + 1.f) - iy;      // ATen: (iy_se - iy), (iy - iy_nw)
-              y_in = y0 >= 0 && y1 < m;
-            }
-            float gx = ((float)x + 0.5f - b.x) / bw * 2.f - 1.f;
-            float ix = ((gx + 1.f) * fm - 1.f) * 0.5f;
-            float fx = floorf(ix);
-            int xl = (int)fx, xh = xl + 1;
-            float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
-            float v = 0.f;
-            // same accumulation order as ATen's grid_sampler_2d (nw, ne, sw, se)
-            if (y_in && xl >= 0 && xh < m) {             // all four taps inside the mask: no bounds tests
-              const float* r0 = s_mask + y0 * m + xl;
-              v += r0[0] * (wx0 * wy0);
-              v += r0[1] * (wx1 * wy0);
-              v += r0[m] * (wx0 * wy1);
-              v += r0[m + 1] * (wx1 * wy1);
-            } else {
-              bool yl_in = y0 >= 0 && y0 < m, yh_in = y1 >= 0 && y1 < m;
-              bool xl_in = xl >= 0 && xl < m, xh_in = xh >= 0 && xh < m;
-              if (yl_in && xl_in) v += s_mask[y0 * m + xl] * (wx0 * wy0);
-              if (yl_in && xh_in) v += s_mask[y0 * m + xh] * (wx1 * wy0);
-              if (yh_in && xl_in) v += s_mask[y1 * m + xl] * (wx0 * wy1);
-              if (yh_in && xh_in) v += s_mask[y1 * m + xh] * (wx1 * wy1);
-            }
-            if (v >= threshold) {
-              const int k = (int)(ff - f);
-              w[k >> 2] |= 1u << (8 * (k & 3));
-            }
+  const float bw = b.z - b.x, bh = b.w - b.y, fm = (float)m;
+  for (int x = xa + threadIdx.x; x < xb; x += blockDim.x) {
+    const float gx = ((float)x + 0.5f - b.x) / bw * 2.f - 1.f;
+    const float ix = ((gx + 1.f) * fm - 1.f) * 0.5f;
+    const float fx = floorf(ix);
+    // float -> int of an out-of-range value is clamped first; both taps of a far-outside column land on the zero border
+    const int xl = (int)fminf(fmaxf(fx, -2.f), fm + 1.f);
+    PasteCol c;
+    c.wx1 = ix - fx; c.wx0 = (fx + 1.f) - ix;
+    c.cl = min(max(xl + 1, 0), m + 1); c.ch = min(max(xl + 2, 0), m + 1);
+    s_col[x - xa] = c;
+  }
+  __syncthreads();
+  uint32_t* obase = reinterpret_cast<uint32_t*>(out + (size_t)r * out_h * out_w);
+  for (int y = ya + blockIdx.x * nwarps + warp; y < yb; y += gridDim.x * nwarps) {
+    const float gy = ((float)y + 0.5f - b.y) / bh * 2.f - 1.f;
+    const float iy = ((gy + 1.f) * fm - 1.f) * 0.5f;
+    const float fy = floorf(iy);
+    const float wy1 = iy - fy, wy0 = (fy + 1.f) - iy;        // ATen: (iy_se - iy), (iy - iy_nw)
+    const int yl = (int)fminf(fmaxf(fy, -2.f), fm + 1.f);
+    const float* r0 = s_mask + min(max(yl + 1, 0), m + 1) * mp;
+    const float* r1 = s_mask + min(max(yl + 2, 0), m + 1) * mp;
+    const long long row0 = (long long)y * out_w;
+    const long long w_first = (row0 + xa) >> 2, w_last = (row0 + xb - 1) >> 2;
+    // 32 words = 128 consecutive pixels per warp pass: in step k lane l evaluates pixel 32k + l (consecutive lanes read
+    // consecutive 16-byte table entries: conflict-free), a ballot collects the 32 decisions, and lane l finally stores
+    // word l assembled from ballot l / 8 -- one coalesced 128-byte store per pass.
+    for (long long w0 = w_first; w0 <= w_last; w0 += 32) {
+      uint32_t bits[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int x = (int)(w0 * 4 + 32 * k + lane - row0), yy = y;
+        // a boundary word can reach into the neighbouring row (out_w is not a multiple of 4); its bytes there are
+        // evaluated with that row's coefficients so that both rows write identical words
+        if (x < 0) { x += out_w; yy = y - 1; } else if (x >= out_w) { x -= out_w; yy = y + 1; }
+        bool on = false;
+        if (x >= xa && x < xb && yy >= ya && yy < yb) {
+          const PasteCol c = s_col[x - xa];
+          float a0 = wy0, a1 = wy1;
+          const float* q0 = r0;
+          const float* q1 = r1;
+          if (yy != y) {                                    // rare
+            const float gy2 = ((float)yy + 0.5f - b.y) / bh * 2.f - 1.f;
+            const float iy2 = ((gy2 + 1.f) * fm - 1.f) * 0.5f;
+            const float fy2 = floorf(iy2);
+            a1 = iy2 - fy2; a0 = (fy2 + 1.f) - iy2;
+            const int yl2 = (int)fminf(fmaxf(fy2, -2.f), fm + 1.f);
+            q0 = s_mask + min(max(yl2 + 1, 0), m + 1) * mp;
+            q1 = s_mask + min(max(yl2 + 2, 0), m + 1) * mp;
           }
-          if (++x == out_w) { x = 0; ++y; }
+          // same accumulation order as ATen's grid_sampler_2d (nw, ne, sw, se); border cells contribute exact zeros
+          float v = 0.f;
+          v += q0[c.cl] * (c.wx0 * a0);
+          v += q0[c.ch] * (c.wx1 * a0);
+          v += q1[c.cl] * (c.wx0 * a1);
+          v += q1[c.ch] * (c.wx1 * a1);
+          on = v >= threshold;
         }
+        bits[k] = __ballot_sync(0xffffffffu, on);
       }
+      const uint32_t sel = lane < 8 ? bits[0] : (lane < 16 ? bits[1] : (lane < 24 ? bits[2] : bits[3]));
+      const uint32_t nib = (sel >> (4 * (lane & 7))) & 0xfu;
+      const uint32_t word = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+      if (w0 + lane <= w_last) obase[w0 + lane] = word;
     }
-    if (f >= 0 && f + 16 <= hw) {
-      *reinterpret_cast<uint4*>(obase + f) = make_uint4(w[0], w[1], w[2], w[3]);
-    } else {
-      for (int k = 0; k < 16; ++k)
-        if (f + k >= 0 && f + k < hw) obase[f + k] = (uint8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xff);
+  }
+}
+
+// Byte-store variant for buffers whose ROI planes are not word aligned: a thread owns one column of an 8-row tile.
+constexpr int PASTE_TILE_ROWS = 8;
+__global__ void __launch_bounds__(256) paste_window_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
+                                                           const uint8_t* __restrict__ valid, uint8_t* __restrict__ out,
+                                                           int m, int out_h, int out_w, float threshold) {
+  extern __shared__ float s_mask[];                    // (m + 2) x (m + 2), zero border
+  const int r = blockIdx.y;
+  if (valid[r] == 0) return;
+  const float4 b = reinterpret_cast<const float4*>(boxes)[r];
+  const int xa = max((int)floorf(b.x) - 1, 0), ya = max((int)floorf(b.y) - 1, 0);
+  const int xb = min((int)ceilf(b.z) + 1, out_w), yb = min((int)ceilf(b.w) + 1, out_h);
+  if (xa >= xb || ya >= yb) return;
+  const int ntx = (xb - xa + 255) >> 8, nty = (yb - ya + PASTE_TILE_ROWS - 1) / PASTE_TILE_ROWS;
+  if ((int)blockIdx.x >= ntx * nty) return;
+  const int mp = m + 2;
+  for (int i = threadIdx.x; i < mp * mp; i += blockDim.x) {
+    const int yy = i / mp - 1, xx = i - (yy + 1) * mp - 1;
+    s_mask[i] = (yy >= 0 && yy < m && xx >= 0 && xx < m) ? probs[(size_t)r * m * m + yy * m + xx] : 0.f;
+  }
+  __syncthreads();
+  const float bw = b.z - b.x, bh = b.w - b.y, fm = (float)m;
+  uint8_t* obase = out + (size_t)r * out_h * out_w;
+  for (int t = blockIdx.x; t < ntx * nty; t += gridDim.x) {
+    const int ty = t / ntx, tx = t - ty * ntx;
+    const int x = xa + tx * 256 + threadIdx.x;
+    if (x >= xb) continue;
+    const float gx = ((float)x + 0.5f - b.x) / bw * 2.f - 1.f;
+    const float ix = ((gx + 1.f) * fm - 1.f) * 0.5f;
+    const float fx = floorf(ix);
+    const float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
+    const int xl = (int)fminf(fmaxf(fx, -2.f), fm + 1.f);
+    const int cl = min(max(xl + 1, 0), m + 1), ch = min(max(xl + 2, 0), m + 1);
+    const int y_end = min(ya + (ty + 1) * PASTE_TILE_ROWS, yb);
+    for (int y = ya + ty * PASTE_TILE_ROWS; y < y_end; ++y) {
+      const float gy = ((float)y + 0.5f - b.y) / bh * 2.f - 1.f;
+      const float iy = ((gy + 1.f) * fm - 1.f) * 0.5f;
+      const float fy = floorf(iy);
+      const float wy1 = iy - fy, wy0 = (fy + 1.f) - iy;      // ATen: (iy_se - iy), (iy - iy_nw)
+      const int yl = (int)fminf(fmaxf(fy, -2.f), fm + 1.f);
+      const float* r0 = s_mask + min(max(yl + 1, 0), m + 1) * mp;
+      const float* r1 = s_mask + min(max(yl + 2, 0), m + 1) * mp;
+      float v = 0.f;
+      v += r0[cl] * (wx0 * wy0);
+      v += r0[ch] * (wx1 * wy0);
+      v += r1[cl] * (wx0 * wy1);
+      v += r1[ch] * (wx1 * wy1);
+      obase[(size_t)y * out_w + x] = v >= threshold ? 1 : 0;
     }
   }
 }
@@ -413,6 +536,17 @@ extern "C" int cm2_spatial_attention(const cm2_act* x, const cm2_act* out, int32
                 "spatial_attention: bad views [%d,%d,%d,%d]", x->n, x->h, x->w, x->c);
   if (x->n == 0) return CM2_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  const size_t tile_bytes = (size_t)x->h * x->w * x->c * 2;
+  if (dtype == CM2_BF16 && tile_bytes <= 110 * 1024) {     // two CTAs per SM
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(spatial_attention_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+      attr_done = true;
+    }
+    spatial_attention_smem_kernel<<<x->n, 512, tile_bytes, s>>>(make_view<const __nv_bfloat16>(*x), make_view<__nv_bfloat16>(*out), w18);
+    CM2_CHECK_LAUNCH("spatial_attention_smem");
+    return CM2_OK;
+  }
   if (dtype == CM2_F32)
     spatial_attention_kernel<float><<<x->n, 256, 0, s>>>(make_view<const float>(*x), make_view<float>(*out), w18);
   else
@@ -497,10 +631,26 @@ extern "C" int cm2_paste_masks(const float* probs, const float* boxes, const uin
   CM2_CHECK_ARG(m > 0 && m <= 64 && out_h > 0 && out_w > 0, "paste_masks: bad extents m=%d out=%dx%d", m, out_h, out_w);
   if (r == 0) return CM2_OK;
   CM2_CHECK_ARG(r <= 65535, "paste_masks: too many ROIs in one call (%d)", r);
-  const long long hw = (long long)out_h * out_w;
-  dim3 grid((unsigned)((hw + 15 + PASTE_SPAN - 1) / PASTE_SPAN), r);
-  paste_masks_kernel<<<grid, 256, (size_t)m * m * sizeof(float), (cudaStream_t)stream>>>(probs, boxes, valid, out, m,
-                                                                                          out_h, out_w, threshold);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(out, 0, (size_t)r * out_h * out_w, s) != cudaSuccess) {
+    set_error("paste_masks: cudaMemsetAsync failed");
+    return CM2_ERR_CUDA;
+  }
+  dim3 grid(PASTE_CTAS_PER_ROI, r);
+  const size_t mask_floats = (size_t)(((m + 2) * (m + 2) + 3) & ~3);
+  if (((long long)out_h * out_w) % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0 && out_w <= PASTE_MAX_W) {
+    const size_t smem = mask_floats * sizeof(float) + (size_t)out_w * sizeof(PasteCol);
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(paste_window_words_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(((64 + 2) * (64 + 2) + 4) * sizeof(float) + PASTE_MAX_W * sizeof(PasteCol)));
+      attr_done = true;
+    }
+    paste_window_words_kernel<<<grid, 256, smem, s>>>(probs, boxes, valid, out, m, out_h, out_w, threshold);
+    CM2_CHECK_LAUNCH("paste_masks_words");
+    return CM2_OK;
+  }
+  paste_window_kernel<<<grid, 256, (size_t)(m + 2) * (m + 2) * sizeof(float), s>>>(probs, boxes, valid, out, m, out_h, out_w, threshold);
   CM2_CHECK_LAUNCH("paste_masks");
   return CM2_OK;
 }

@@ -229,7 +229,7 @@ def test_spatial_attention_mask_predict_maskiou_glue():
     assert torch.allclose(ms.cpu(), sc * iou[torch.arange(r), cls], atol=1e-6)
 
 
-@pytest.mark.parametrize("out_h,out_w", [(96, 128), (75, 101)])
+@pytest.mark.parametrize("out_h,out_w", [(96, 128), (75, 101), (76, 101), (40, 67)])      # word path (aligned / rows straddling words), byte path
 def test_paste_masks_and_box_rescale(out_h, out_w):
     g = torch.Generator().manual_seed(9)
     r = 12

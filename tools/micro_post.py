@@ -1,0 +1,160 @@
+#!/usr/bin/env python
+"""BASELINE config 5: FCOS post-process + SAG-Mask microbenchmark (no convolutions).
+
+    python tools/micro_post.py [--batch 32] [--cand 1000] [--rois 100] [--out profiles/r1_micro_post_b32.json]
+
+5 FPN levels of the 800x1344 pyramid, head outputs drawn directly: logits N(mu_l, 1) with mu_l chosen
+so that ~`cand` entries per level and image exceed the 0.05 threshold, regression |N(0,1)|*4 (stride units),
+centerness N(0,1); ROI stage fed `rois` boxes per image with log-uniform areas so that all three levels are used;
+random bf16 P3-P5 features and 28x28 mask probabilities.  Every kernel is timed with CUDA events (3 warm-ups, 10
+launches; working sets exceed the 126 MB L2 except for top-k / NMS) and reported as achieved GB/s over its
+ALGORITHMIC bytes against the measured HBM copy peak.  One JSON object per kernel.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from centermask2_b200 import lib                                    # noqa: E402
+from centermask2_b200.config import get_cfg                        # noqa: E402
+from centermask2_b200.engine import Engine, FMap                   # noqa: E402
+
+H, W = 800, 1344
+LEVELS = [(100, 168, 8), (50, 84, 16), (25, 42, 32), (13, 21, 64), (7, 11, 128)]
+
+
+def norm_isf(p):
+    """Inverse survival function of N(0,1) (Acklam-free: bisection on erfc)."""
+    lo, hi = -10.0, 10.0
+    for _ in range(80):
+        mid = 0.5 * (lo + hi)
+        if 0.5 * math.erfc(mid / math.sqrt(2.0)) > p:
+            lo = mid
+        else:
+            hi = mid
+    return 0.5 * (lo + hi)
+
+
+def timed(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--cand", type=int, default=1000)
+    ap.add_argument("--rois", type=int, default=100)
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    n, R = args.batch, args.rois
+    dev = "cuda"
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    hbm = peaks["hbm_gbs"]
+    cfg = get_cfg("centermask_V_39_eSE_FPN.yaml", ["MODEL.FCOS.POST_NMS_TOPK_TEST", R, "MODEL.B200.PRECISION", "bf16"])
+    eng = Engine(cfg, "bf16", dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    ncls = 80
+    thr_logit = math.log(0.05 / 0.95)
+    head = []
+    for (h, w, s) in LEVELS:
+        frac = min(0.5, args.cand / float(h * w * ncls))
+        mu = thr_logit - norm_isf(frac)
+        lg = torch.randn((n, h, w, ncls), device=dev, generator=g) + mu
+        rc = torch.zeros((n, h, w, 16), device=dev)
+        rc[..., :4] = torch.randn((n, h, w, 4), device=dev, generator=g).abs() * 4.0
+        rc[..., 4] = torch.randn((n, h, w), device=dev, generator=g)
+        head.append((FMap(lg, 0), FMap(rc, 0)))
+    results = []
+
+    def report(name, ms, alg_bytes, note=""):
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        row = {"kernel": name, "ms": round(ms, 4), "algorithmic_MB": round(alg_bytes / 1e6, 1), "GBps": round(gbs, 1),
+               "frac_of_hbm_peak": round(gbs / hbm, 3), "batch": n, "note": note}
+        results.append(row)
+        print(json.dumps(row))
+
+    # ---- decode + threshold (A11): 22 400 x 85 fp32 per image
+    det = eng.run_fcos_post(head)
+    torch.cuda.synchronize()
+    cand = det["cand_count"].float().mean().item()
+    B = eng.buffer
+    L = len(LEVELS)
+    cap = det["cand_cap"]
+    cb = dict(boxes=B("cand_boxes", (n, L, cap, 4), torch.float32, False), score=B("cand_score", (n, L, cap), torch.float32, False),
+              cls=B("cand_cls", (n, L, cap), torch.int32, False), flat=B("cand_flat", (n, L, cap), torch.int32, False),
+              count=B("cand_count", (n, L), torch.int32))
+    cbuf = lib.cand_buffers(cb["boxes"], cb["score"], cb["cls"], cb["flat"], cb["count"])
+
+    def decode():
+        cb["count"].zero_()
+        for l, (lg, rc) in enumerate(head):
+            lib.fcos_decode(lg.view, rc.view, LEVELS[l][2], 1.0, 0.05, False, l, L, cap, cbuf)
+    ms = timed(decode)
+    report("fcos_decode (5 levels)", ms, n * 22400 * 85 * 4, "{:.0f} candidates / level / image".format(cand))
+
+    # ---- per-level top-k + class-aware NMS + post top-k (A12-A14): latency-bound
+    ms_all = timed(lambda: eng.run_fcos_post(head))
+    report("fcos_select + nms (per image CTA)", max(ms_all - ms, 1e-6), n * L * args.cand * 24,
+           "latency-bound: {} candidates in, {} kept / image".format(int(cand * L), int(det["count"].float().mean().item())))
+
+    # ---- ROIAlign with level assignment (A15 + A16)
+    c = 256
+    feats = [eng.fmap("mf{}".format(i), n, h, w, c) for i, (h, w, _) in enumerate(LEVELS[:3])]
+    for f in feats:
+        f.view.copy_(torch.randn(f.view.shape, device=dev, generator=g).to(torch.bfloat16))
+    area = torch.exp(torch.rand((n, R), device=dev, generator=g) * (math.log(0.9 * H * W) - math.log(32.0 * 32.0)) + math.log(32.0 * 32.0))
+    ar = torch.exp((torch.rand((n, R), device=dev, generator=g) - 0.5) * 1.4)
+    bw, bh = torch.sqrt(area * ar).clamp(max=W - 1.0), torch.sqrt(area / ar).clamp(max=H - 1.0)
+    x0 = torch.rand((n, R), device=dev, generator=g) * (W - bw)
+    y0 = torch.rand((n, R), device=dev, generator=g) * (H - bh)
+    boxes = torch.stack([x0, y0, x0 + bw, y0 + bh], dim=2).contiguous()
+    counts = torch.full((n,), R, dtype=torch.int32, device=dev)
+    img_area = torch.full((n,), float(H * W), device=dev)
+    roi = eng.fmap("mroi", n * R, 14, 14, c)
+    lvl = torch.zeros((n * R,), dtype=torch.int32, device=dev)
+    ms = timed(lambda: lib.roialign_fpn([f.view for f in feats], [8, 16, 32], boxes, counts, n, R, img_area, 0, 0, roi.view, lvl))
+    hist = torch.bincount(lvl.long(), minlength=3).tolist()
+    report("roialign_fpn (+ level assignment)", ms, n * (R * c * 196 * 2 + c * 22050 * 2), "ROIs per level {}".format(hist))
+
+    # ---- spatial attention (A18)
+    att = eng.fmap("matt", n * R, 14, 14, c)
+    w18 = torch.randn((18,), device=dev, generator=g)
+    ms = timed(lambda: lib.spatial_attention(roi.view, att.view, w18))
+    report("spatial_attention", ms, n * R * c * 196 * 2 * 2)
+
+    # ---- paste-back (A23)
+    probs = torch.rand((n * R, 1, 28, 28), device=dev, generator=g)
+    sizes = [(H, 1333)] * n
+    bx, valid = eng.rescale_boxes(boxes, sizes, sizes)
+    chunk = max(1, min(n, 600 // R))                       # <= 65535 ROIs per launch and a bounded output buffer
+    masks = torch.empty((chunk * R, H, 1333), dtype=torch.uint8, device=dev)
+
+    def paste():
+        for i0 in range(0, n, chunk):
+            k = min(chunk, n - i0)
+            lib.paste_masks(probs[i0 * R:(i0 + k) * R], bx[i0:i0 + k], valid[i0:i0 + k], masks, k * R, 28, H, 1333, 0.5)
+    ms = timed(paste, reps=3, warm=1)
+    inbox = float(((bx[..., 2] - bx[..., 0]) * (bx[..., 3] - bx[..., 1])).mean().item()) / (H * 1333)
+    report("paste_masks", ms, n * R * H * 1333 + n * R * 784 * 4, "mean box area {:.1%} of the image".format(inbox))
+    if args.out:
+        with open(args.out, "w") as f:
+            for r in results:
+                f.write(json.dumps(r) + "\n")
+
+
+if __name__ == "__main__":
+    main()
