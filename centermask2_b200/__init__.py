@@ -7,5 +7,6 @@ from .config import get_cfg, lite_overrides  # noqa: F401
 from .runtime import set_precision  # noqa: F401
 from . import modeling  # noqa: F401
 from .modeling import build_model  # noqa: F401
+from .checkpoint import DetectionCheckpointer, load_checkpoint  # noqa: F401
 
 __version__ = "0.1.0"
