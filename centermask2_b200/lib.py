@@ -68,6 +68,7 @@ SYMBOLS = {
     "cm2_preprocess_im2col": (_I, [_P, _I, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _AP, _I, _P]),
     "cm2_preprocess_im2col_batch": (_I, [C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _AP,
                                          _I, _P]),
+    "cm2_resize_pil_u8": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _I, _P]),
     "cm2_phase_split": (_I, [_AP, _AP, _I, _I, _P]),
     "cm2_maxpool3x3s2_ceil": (_I, [_AP, _AP, _I, _P]),
     "cm2_ese_pool_chunks": (_I, [_I]),
@@ -242,6 +243,12 @@ def preprocess_im2col_batch(imgs, mean, std, hp, wp, out, index0=0):
     check(load().cm2_preprocess_im2col_batch(ptrs, hs, ws, n, dtype_code(imgs[0]), hp, wp, m, s, C.byref(a), index0, stream()),
           "cm2_preprocess_im2col_batch")
     _count((n + 31) // 32)
+
+
+def resize_pil_u8(src, tmp, dst, h, w, c, oh, ow, bounds_x, kk_x, bounds_y, kk_y, chw):
+    check(load().cm2_resize_pil_u8(ptr(src), ptr(tmp), ptr(dst), h, w, c, oh, ow, ptr(bounds_x), ptr(kk_x), kk_x.shape[1],
+                                   ptr(bounds_y), ptr(kk_y), kk_y.shape[1], int(chw), stream()), "cm2_resize_pil_u8")
+    _count(2)
 
 
 def phase_split(x, out_plane0, relu=False):

@@ -305,6 +305,18 @@ int cm2_maskiou_score(const void* iou, int32_t dtype, int32_t r, int32_t ncls, c
                       const float* scores, float* mask_scores, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Input side, upstream of preprocess: detectron2's ResizeShortestEdge / ResizeTransform for
+ * uint8 HWC images (/root/reference/deploy_utils.py:60-73), i.e. PIL.Image.resize(BILINEAR): Pillow's two-pass
+ * fixed-point resampler.  bounds_* [out][2] = (first input index, tap count), kk_* [out][ksize_*] = 22-bit
+ * fixed-point taps, both built by centermask2_b200/transforms.py::pil_bilinear_coeffs (device memory).
+ * src [h][w][c] -> tmp [h][ow][c] (horizontal pass) -> dst [oh][ow][c] (chw == 0) or [c][oh][ow] (chw == 1).
+ * Bit-identical to Pillow 12.2.0.
+ * ------------------------------------------------------------------------------------------- */
+int cm2_resize_pil_u8(const uint8_t* src, uint8_t* tmp, uint8_t* dst, int32_t h, int32_t w, int32_t c, int32_t oh,
+                      int32_t ow, const int32_t* bounds_x, const int32_t* kk_x, int32_t ksize_x,
+                      const int32_t* bounds_y, const int32_t* kk_y, int32_t ksize_y, int32_t chw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Output side.  detector_postprocess + paste_masks_in_image [d2] (the fork's
  * restatement is /root/reference/deploy_utils.py:129-158).
  * cm2_scale_clip_boxes: boxes *= (sx, sy); clip to [0,out_w]x[0,out_h]; valid = w>0 && h>0.
