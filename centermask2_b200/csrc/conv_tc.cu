@@ -60,6 +60,8 @@ struct alignas(64) TcParams {
   int kx_merge;             // 1: one A slab per (ky, source, k-block) serves the three kx taps
   int a_box_rows;           // rows per A TMA box: 128, or 136 with kx_merge (two boxes per slab)
   int sa_stages, sb_stages; // ring depths
+  int spin;                 // control warps poll their barriers with test_wait instead of the suspending try_wait
+  int b_resident;           // v2: all weight tiles of the (single) N tile stay in shared memory for the whole kernel
   int acc_stages;           // 2 when bn <= 128 (2 x 2 x 128 TMEM columns), else 1
   int nblk_total;           // sum over sources of ceil(c / 64)
   int desc_mode;            // 0: base_offset field 0;  1: base_offset = (start >> 7) & 7 for unaligned starts
@@ -78,7 +80,7 @@ struct alignas(64) TcParams {
   int epi_kind;             // staged-epilogue variant (see tc_epilogue_dispatch)
   int epi_sets;             // column sets of epilogue warps per 128-row accumulator (1, 2 or 4)
   int fast_store;           // 1: epilogue transposes through shared memory and writes 64-byte row segments
-  int dbg;                  // tuning experiments (CM2_TC_DEBUG): 1 no epilogue stores, 2 no TMA loads, 4 no MMAs
+  int dbg;                  // tuning experiments (CM2_TC_DEBUG): 1 no epilogue stores, 2 no TMA loads, 4 no MMAs, 8 no epilogue body
   int variant;              // host only: 1 = conv_tc_kernel (128-row tiles), 2 = conv_tc2_kernel
   unsigned smem_bytes;      // host only: dynamic shared memory of the launch
 };
@@ -138,6 +140,37 @@ __device__ __forceinline__ bool elect_one_sync() {
       : "+r"(pred)
       : "r"(0xffffffffu));
   return pred != 0;
+}
+// Polling wait (mbarrier.test_wait never suspends the thread): used by the two control warps, whose hand-off latency
+// bounds short pipeline stages.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((++spins & 0xfffffu) == 0) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) {
+        printf("conv_tc: mbarrier spin wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_ctl(int spin, uint32_t bar, uint32_t parity) {
+  if (spin) mbar_wait_spin(bar, parity);
+  else mbar_wait(bar, parity);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -756,7 +789,7 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc_kernel(const __grid
           for (int s = 0; s < p.num_src; ++s) {
             const int nblk = (p.src_c[s] + TC_BK - 1) / TC_BK;
             for (int cb = 0; cb < nblk; ++cb, ++kb) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
+              mbar_wait_ctl(p.spin, empty_bar(stage), phase ^ 1u);
               const uint32_t sa = base + (uint32_t)stage * stage_bytes;
               if (elect_one_sync()) {
                 if (p.dbg & 2) {
@@ -782,7 +815,7 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc_kernel(const __grid
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait_ctl(p.spin, tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_ACC_COLS);
         uint32_t accumulate = 0;
@@ -792,7 +825,7 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc_kernel(const __grid
             const int nblk = (c + TC_BK - 1) / TC_BK;
             for (int cb = 0; cb < nblk; ++cb) {
               const int nk = (min(TC_BK, c - cb * TC_BK) + 15) >> 4;        // 16-channel MMAs in this block
-              mbar_wait(full_bar(stage), phase);
+              mbar_wait_ctl(p.spin, full_bar(stage), phase);
               tc_fence_after();
               const uint32_t sa = base + (uint32_t)stage * stage_bytes;
               const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + TC_A_BYTES);
@@ -834,7 +867,8 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc_kernel(const __grid
       const uint32_t taddr = tmem_base + (uint32_t)(acc * TC_ACC_COLS) + ((uint32_t)(q * 32) << 16);
       const TileGeom g = tc_geom(p, m0);
       const int cset = (warp - 2) >> 2;
-      if (p.fast_store)
+      if (p.dbg & 8) {
+      } else if (p.fast_store)
         tc_epilogue_dispatch(p, g, taddr, m0 + q * 32 + lane, n0, epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES, lane, ss,
                              cset, p.epi_sets);
       else if (cset == 0)
@@ -920,6 +954,20 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc2_kernel(const __gri
     {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
+      if (p.b_resident) {
+        // weights of small-N layers (stem, bbox/centerness head) are loaded once per CTA: slot i = (tap, k-block) i
+        for (int i = 0; i < p.sb_stages; ++i) {
+          if (elect_one_sync()) {
+            if (p.dbg & 2) {
+              mbar_arrive(bfull_bar(i));
+            } else {
+              mbar_expect_tx(bfull_bar(i), b_bytes);
+              tma_load_2d(b_base + (uint32_t)i * b_bytes, &p.b_map, bfull_bar(i), i * TC_BK, 0);
+            }
+          }
+          __syncwarp();
+        }
+      }
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int m0 = (t / p.n_tiles) * 256, n0 = (t % p.n_tiles) * p.bn;
         for (int g = 0; g < ngroup_outer; ++g) {
@@ -930,7 +978,7 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc2_kernel(const __gri
           for (int s = 0; s < p.num_src; ++s) {
             const int nblk = (p.src_c[s] + TC_BK - 1) / TC_BK;
             for (int cb = 0; cb < nblk; ++cb, ++blk) {
-              mbar_wait(aempty_bar(sa), pa ^ 1u);
+              mbar_wait_ctl(p.spin, aempty_bar(sa), pa ^ 1u);
               const uint32_t slab = base + (uint32_t)sa * a_slab_bytes;
               if (elect_one_sync()) {
                 if (p.dbg & 2) {
@@ -943,9 +991,9 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc2_kernel(const __gri
               }
               __syncwarp();
               if (++sa == p.sa_stages) { sa = 0; pa ^= 1u; }
-              for (int j = 0; j < groups_per_tap_row; ++j) {
+              for (int j = 0; j < groups_per_tap_row && !p.b_resident; ++j) {
                 const int tap = p.kx_merge ? g * 3 + j : g;
-                mbar_wait(bempty_bar(sb), pb ^ 1u);
+                mbar_wait_ctl(p.spin, bempty_bar(sb), pb ^ 1u);
                 if (elect_one_sync()) {
                   if (p.dbg & 2) {
                     mbar_arrive(bfull_bar(sb));
@@ -968,23 +1016,33 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc2_kernel(const __gri
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int sa = 0, sb = 0, acc = 0;
       uint32_t pa = 0, pb = 0, acc_phase = 0;
+      if (p.b_resident) {
+        for (int i = 0; i < p.sb_stages; ++i) mbar_wait_ctl(p.spin, bfull_bar(i), 0u);
+        tc_fence_after();
+      }
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait_ctl(p.spin, tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * half_cols);
         const uint32_t d1 = d0 + (uint32_t)half_cols;
         uint32_t accumulate = 0;
         for (int g = 0; g < ngroup_outer; ++g) {
+          int blk = 0;
           for (int s = 0; s < p.num_src; ++s) {
             const int c = p.src_c[s];
             const int nblk = (c + TC_BK - 1) / TC_BK;
-            for (int cb = 0; cb < nblk; ++cb) {
+            for (int cb = 0; cb < nblk; ++cb, ++blk) {
               const int nk = (min(TC_BK, c - cb * TC_BK) + 15) >> 4;
-              mbar_wait(afull_bar(sa), pa);
+              mbar_wait_ctl(p.spin, afull_bar(sa), pa);
+              if (p.b_resident) tc_fence_after();
               const uint32_t slab = base + (uint32_t)sa * a_slab_bytes;
               for (int j = 0; j < groups_per_tap_row; ++j) {
-                mbar_wait(bfull_bar(sb), pb);
-                tc_fence_after();
+                if (p.b_resident) {
+                  sb = ((p.kx_merge ? g * 3 + j : g) * p.nblk_total + blk);
+                } else {
+                  mbar_wait_ctl(p.spin, bfull_bar(sb), pb);
+                  tc_fence_after();
+                }
                 const uint32_t sbm = b_base + (uint32_t)sb * b_bytes;
                 const uint64_t bdesc = umma_desc_sw128(sbm);
                 // tap kx = j reads the slab j rows (128 B each) further down; rows 128.. feed the second accumulator
@@ -1002,11 +1060,11 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc2_kernel(const __gri
                     if (nk > 2) tc_mma_bf16(d1, adesc1 + 4, bdesc + 4, idesc, 1u);
                     if (nk > 3) tc_mma_bf16(d1, adesc1 + 6, bdesc + 6, idesc, 1u);
                   }
-                  tc_commit(bempty_bar(sb));
+                  if (!p.b_resident) tc_commit(bempty_bar(sb));
                 }
                 __syncwarp();
                 accumulate = 1;
-                if (++sb == p.sb_stages) { sb = 0; pb ^= 1u; }
+                if (!p.b_resident && ++sb == p.sb_stages) { sb = 0; pb ^= 1u; }
               }
               if (elect_one_sync()) tc_commit(aempty_bar(sa));
               __syncwarp();
@@ -1036,7 +1094,8 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc2_kernel(const __gri
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * 2 * half_cols + half * half_cols) + ((uint32_t)(q * 32) << 16);
       const TileGeom tg = tc_geom(p, m0);
-      if (p.fast_store)
+      if (p.dbg & 8) {
+      } else if (p.fast_store)
         tc_epilogue_dispatch(p, tg, taddr, m0 + half * 128 + q * 32 + lane, n0, epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES, lane, ss,
                              cset, p.epi_sets);
       else if (cset == 0)
@@ -1221,6 +1280,8 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   static const int env_desc = getenv("CM2_TC_DESC_MODE") ? atoi(getenv("CM2_TC_DESC_MODE")) : 0;
   static const int env_dbg = getenv("CM2_TC_DEBUG") ? atoi(getenv("CM2_TC_DEBUG")) : 0;
   p->dbg = env_dbg;
+  static const int env_spin = getenv("CM2_TC_SPIN") ? atoi(getenv("CM2_TC_SPIN")) : 0;
+  p->spin = env_spin;
   const int m_tiles256 = (int)((rows + 255) / 256);
   const int bn2 = pick_bn(cout_pad, m_tiles256, sms);
   // Measured (tools/conv_bench.py, B200, batch 16; profiles/r1_convbench_variants_b16.txt): 256-row tiles win
@@ -1256,7 +1317,18 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     p->acc_stages = p->bn <= 128 ? 2 : 1;
     p->desc_mode = env_desc;
     const size_t a_slab = 2u * (size_t)p->a_box_rows * 128u, b_bytes = (size_t)p->bn * TC_BK * 2;
-    if (p->kx_merge) {
+    const int b_tiles = p->taps * p->nblk_total;
+    static const int env_bres = getenv("CM2_TC_B_RESIDENT") ? atoi(getenv("CM2_TC_B_RESIDENT")) : 1;
+    size_t tail2 = tail_v2;
+    if (env_bres && p->n_tiles == 1 && b_tiles <= 64 && (size_t)b_tiles * b_bytes <= 80 * 1024) {
+      // small-N layers: weights resident, only A slabs flow through the ring (3 instead of 12 stage hand-offs per tile
+      // for stem_2, and the per-tile weight re-read from L2 disappears)
+      p->b_resident = 1;
+      p->sb_stages = b_tiles;
+      tail2 += 16 * (size_t)b_tiles;
+      size_t sa = (smem_max - tail2 - (size_t)b_tiles * b_bytes) / a_slab;
+      p->sa_stages = (int)(sa > 6 ? 6 : sa);
+    } else if (p->kx_merge) {
       p->sa_stages = 3;
       size_t sb = (smem_max - tail_v2 - p->sa_stages * a_slab) / b_bytes;
       p->sb_stages = (int)(sb > 9 ? 9 : sb);
@@ -1264,7 +1336,7 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
       size_t st = (smem_max - tail_v2) / (a_slab + b_bytes);
       p->sa_stages = p->sb_stages = (int)(st > 6 ? 6 : st);
     }
-    p->smem_bytes = (unsigned)(1024 + p->sa_stages * a_slab + p->sb_stages * b_bytes + tail_v2);
+    p->smem_bytes = (unsigned)(1024 + p->sa_stages * a_slab + p->sb_stages * b_bytes + tail2);
   } else {
     p->variant = 1;
     p->epi_sets = sets1;

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q --tb=short -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu.log
+tail -12 gpurun_out/pytest_gpu.log | cut -c1-250
+timeout 300 python tools/conv_bench.py --batch 16 > gpurun_out/convbench_b16.txt 2>&1; echo "convbench exit $?"; cat gpurun_out/convbench_b16.txt
+timeout 600 python bench.py --no-cpu-baseline --layers gpurun_out/layers_b16.txt > gpurun_out/bench_b16.log 2>&1; echo "bench exit $?"; tail -1 gpurun_out/bench_b16.log | cut -c1-300
