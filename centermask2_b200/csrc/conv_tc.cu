@@ -814,34 +814,41 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc_kernel(const __grid
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
+      const int taps = p.taps, num_src = p.num_src, n_stages = p.stages, spin = p.spin;
+      const bool no_mma = (p.dbg & 4) != 0;
+      const uint64_t adesc_base = umma_desc_sw128(base), bdesc_base = umma_desc_sw128(base + TC_A_BYTES);
+      const uint64_t desc_step = (uint64_t)(stage_bytes >> 4);
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        mbar_wait_ctl(p.spin, tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait_ctl(spin, tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_ACC_COLS);
         uint32_t accumulate = 0;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          for (int s = 0; s < p.num_src; ++s) {
+        for (int tap = 0; tap < taps; ++tap) {
+          for (int s = 0; s < num_src; ++s) {
             const int c = p.src_c[s];
             const int nblk = (c + TC_BK - 1) / TC_BK;
             for (int cb = 0; cb < nblk; ++cb) {
               const int nk = (min(TC_BK, c - cb * TC_BK) + 15) >> 4;        // 16-channel MMAs in this block
-              mbar_wait_ctl(p.spin, full_bar(stage), phase);
+              mbar_wait_ctl(spin, full_bar(stage), phase);
               tc_fence_after();
-              const uint32_t sa = base + (uint32_t)stage * stage_bytes;
-              const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + TC_A_BYTES);
+              const uint64_t adesc = adesc_base + (uint64_t)stage * desc_step, bdesc = bdesc_base + (uint64_t)stage * desc_step;
               if (elect_one_sync()) {
-                if (!(p.dbg & 4)) {
+                if (!no_mma) {
                   // +32 bytes per K=16 step inside the 128B swizzle row (start-address field is in 16B units)
-                  tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
-                  if (nk > 1) tc_mma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-                  if (nk > 2) tc_mma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-                  if (nk > 3) tc_mma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                  if (nk == 4) {
+                    tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+                    tc_mma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                    tc_mma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                    tc_mma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                  } else {
+                    for (int k = 0; k < nk; ++k) tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
+                  }
                 }
                 tc_commit(empty_bar(stage));          // frees the smem slot when these MMAs have read it
               }
               __syncwarp();
               accumulate = 1;
-              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+              if (++stage == n_stages) { stage = 0; phase ^= 1u; }
             }
           }
         }
@@ -1013,68 +1020,106 @@ __global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc2_kernel(const __gri
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     {
+      // The issue loop is the critical path of short-N layers (ncu: the producer waits for THIS warp, which never waits
+      // itself): every parameter it needs is copied to a local first, descriptors are advanced incrementally, a full
+      // 64-channel block takes the branch-free 8-MMA path, and a whole slab is issued under a single elect.
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const int kx_merge = p.kx_merge, b_res = p.b_resident, nblk_total = p.nblk_total, n_acc = p.acc_stages;
+      const int n_sa = p.sa_stages, n_sb = p.sb_stages, num_src = p.num_src, spin = p.spin;
+      const bool no_mma = (p.dbg & 4) != 0;
+      const uint64_t bdesc_step = (uint64_t)(b_bytes >> 4);          // descriptor start-address units (16 B)
+      const uint64_t bdesc_base = umma_desc_sw128(b_base);
+      const uint64_t adesc_half = (uint64_t)((128u * 128u) >> 4);    // rows 128.. of the slab feed the second accumulator
       int sa = 0, sb = 0, acc = 0;
       uint32_t pa = 0, pb = 0, acc_phase = 0;
-      if (p.b_resident) {
-        for (int i = 0; i < p.sb_stages; ++i) mbar_wait_ctl(p.spin, bfull_bar(i), 0u);
+      if (b_res) {
+        for (int i = 0; i < n_sb; ++i) mbar_wait_ctl(spin, bfull_bar(i), 0u);
         tc_fence_after();
       }
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        mbar_wait_ctl(p.spin, tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait_ctl(spin, tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * half_cols);
         const uint32_t d1 = d0 + (uint32_t)half_cols;
         uint32_t accumulate = 0;
         for (int g = 0; g < ngroup_outer; ++g) {
           int blk = 0;
-          for (int s = 0; s < p.num_src; ++s) {
+          for (int s = 0; s < num_src; ++s) {
             const int c = p.src_c[s];
             const int nblk = (c + TC_BK - 1) / TC_BK;
             for (int cb = 0; cb < nblk; ++cb, ++blk) {
               const int nk = (min(TC_BK, c - cb * TC_BK) + 15) >> 4;
-              mbar_wait_ctl(p.spin, afull_bar(sa), pa);
-              if (p.b_resident) tc_fence_after();
-              const uint32_t slab = base + (uint32_t)sa * a_slab_bytes;
-              for (int j = 0; j < groups_per_tap_row; ++j) {
-                if (p.b_resident) {
-                  sb = ((p.kx_merge ? g * 3 + j : g) * p.nblk_total + blk);
-                } else {
-                  mbar_wait_ctl(p.spin, bfull_bar(sb), pb);
-                  tc_fence_after();
-                }
-                const uint32_t sbm = b_base + (uint32_t)sb * b_bytes;
-                const uint64_t bdesc = umma_desc_sw128(sbm);
-                // tap kx = j reads the slab j rows (128 B each) further down; rows 128.. feed the second accumulator
-                const uint32_t a0 = slab + (uint32_t)(p.kx_merge ? j : 0) * 128u;
-                const uint32_t a1 = a0 + 128u * 128u;
-                const uint64_t adesc0 = umma_desc_sw128_at(a0, p.desc_mode), adesc1 = umma_desc_sw128_at(a1, p.desc_mode);
+              mbar_wait_ctl(spin, afull_bar(sa), pa);
+              tc_fence_after();
+              const uint64_t adesc_slab = umma_desc_sw128(base + (uint32_t)sa * a_slab_bytes);
+              if (b_res) {
+                // weights resident: tile (tap, k-block) lives in slot tap * nblk_total + blk; one elect per slab
                 if (elect_one_sync()) {
-                  if (!(p.dbg & 4)) {
-                    tc_mma_bf16(d0, adesc0, bdesc, idesc, accumulate);
-                    if (nk > 1) tc_mma_bf16(d0, adesc0 + 2, bdesc + 2, idesc, 1u);
-                    if (nk > 2) tc_mma_bf16(d0, adesc0 + 4, bdesc + 4, idesc, 1u);
-                    if (nk > 3) tc_mma_bf16(d0, adesc0 + 6, bdesc + 6, idesc, 1u);
-                    tc_mma_bf16(d1, adesc1, bdesc, idesc, accumulate);
-                    if (nk > 1) tc_mma_bf16(d1, adesc1 + 2, bdesc + 2, idesc, 1u);
-                    if (nk > 2) tc_mma_bf16(d1, adesc1 + 4, bdesc + 4, idesc, 1u);
-                    if (nk > 3) tc_mma_bf16(d1, adesc1 + 6, bdesc + 6, idesc, 1u);
+                  for (int j = 0; j < groups_per_tap_row; ++j) {
+                    const int tap = kx_merge ? g * 3 + j : g;
+                    const uint64_t bdesc = bdesc_base + (uint64_t)(tap * nblk_total + blk) * bdesc_step;
+                    // tap kx = j reads the slab j rows (128 B = 8 descriptor units each) further down
+                    const uint64_t adesc0 = adesc_slab + (uint64_t)(kx_merge ? 8 * j : 0), adesc1 = adesc0 + adesc_half;
+                    if (!no_mma) {
+                      if (nk == 4) {
+                        tc_mma_bf16(d0, adesc0, bdesc, idesc, accumulate);
+                        tc_mma_bf16(d0, adesc0 + 2, bdesc + 2, idesc, 1u);
+                        tc_mma_bf16(d0, adesc0 + 4, bdesc + 4, idesc, 1u);
+                        tc_mma_bf16(d0, adesc0 + 6, bdesc + 6, idesc, 1u);
+                        tc_mma_bf16(d1, adesc1, bdesc, idesc, accumulate);
+                        tc_mma_bf16(d1, adesc1 + 2, bdesc + 2, idesc, 1u);
+                        tc_mma_bf16(d1, adesc1 + 4, bdesc + 4, idesc, 1u);
+                        tc_mma_bf16(d1, adesc1 + 6, bdesc + 6, idesc, 1u);
+                      } else {
+                        for (int k = 0; k < nk; ++k) tc_mma_bf16(d0, adesc0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
+                        for (int k = 0; k < nk; ++k) tc_mma_bf16(d1, adesc1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
+                      }
+                    }
+                    accumulate = 1;
                   }
-                  if (!p.b_resident) tc_commit(bempty_bar(sb));
+                  tc_commit(aempty_bar(sa));
                 }
                 __syncwarp();
                 accumulate = 1;
-                if (!p.b_resident && ++sb == p.sb_stages) { sb = 0; pb ^= 1u; }
+              } else {
+                // weights streamed through their own ring (measured: letting the elected thread wait for the weight tiles
+                // itself, to issue a whole slab from one elect region, is 5-10 % slower than these warp-level waits)
+                for (int j = 0; j < groups_per_tap_row; ++j) {
+                  mbar_wait_ctl(spin, bfull_bar(sb), pb);
+                  tc_fence_after();
+                  const uint64_t bdesc = bdesc_base + (uint64_t)sb * bdesc_step;
+                  const uint64_t adesc0 = adesc_slab + (uint64_t)(kx_merge ? 8 * j : 0), adesc1 = adesc0 + adesc_half;
+                  if (elect_one_sync()) {
+                    if (!no_mma) {
+                      if (nk == 4) {
+                        tc_mma_bf16(d0, adesc0, bdesc, idesc, accumulate);
+                        tc_mma_bf16(d0, adesc0 + 2, bdesc + 2, idesc, 1u);
+                        tc_mma_bf16(d0, adesc0 + 4, bdesc + 4, idesc, 1u);
+                        tc_mma_bf16(d0, adesc0 + 6, bdesc + 6, idesc, 1u);
+                        tc_mma_bf16(d1, adesc1, bdesc, idesc, accumulate);
+                        tc_mma_bf16(d1, adesc1 + 2, bdesc + 2, idesc, 1u);
+                        tc_mma_bf16(d1, adesc1 + 4, bdesc + 4, idesc, 1u);
+                        tc_mma_bf16(d1, adesc1 + 6, bdesc + 6, idesc, 1u);
+                      } else {
+                        for (int k = 0; k < nk; ++k) tc_mma_bf16(d0, adesc0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
+                        for (int k = 0; k < nk; ++k) tc_mma_bf16(d1, adesc1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
+                      }
+                    }
+                    tc_commit(bempty_bar(sb));
+                    if (j + 1 == groups_per_tap_row) tc_commit(aempty_bar(sa));
+                  }
+                  __syncwarp();
+                  accumulate = 1;
+                  if (++sb == n_sb) { sb = 0; pb ^= 1u; }
+                }
               }
-              if (elect_one_sync()) tc_commit(aempty_bar(sa));
-              __syncwarp();
-              if (++sa == p.sa_stages) { sa = 0; pa ^= 1u; }
+              if (++sa == n_sa) { sa = 0; pa ^= 1u; }
             }
           }
         }
         if (elect_one_sync()) tc_commit(tfull_bar(acc));
         __syncwarp();
-        if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == n_acc) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
