@@ -740,7 +740,8 @@ __device__ __forceinline__ void tc_epilogue_dispatch(const TcParams& p, const Ti
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 2;
@@ -912,7 +913,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_at(uint32_t smem_addr, int d
   return d;
 }
 
-__global__ void __launch_bounds__(TC_MAX_THREADS, 1) conv_tc2_kernel(const __grid_constant__ TcParams p) {
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) conv_tc2_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_half_bytes = (uint32_t)p.a_box_rows * 128u;
@@ -1345,8 +1347,10 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   if (env_variant >= 2 && !pred) use_v2 = true;
   static const int env_sets1 = getenv("CM2_TC_EPI_SETS_V1") ? atoi(getenv("CM2_TC_EPI_SETS_V1")) : 2;
   static const int env_sets2 = getenv("CM2_TC_EPI_SETS_V2") ? atoi(getenv("CM2_TC_EPI_SETS_V2")) : 1;
-  const int sets1 = env_sets1 == 1 ? 1 : 2;            // 64 + 128 * sets1 <= TC_MAX_THREADS
-  const int sets2 = 1;                                 // 64 + 256 * sets2 <= TC_MAX_THREADS
+  // 16 epilogue warps (576 threads, <= 96 registers per thread) were measured 3-20 % slower on every layer
+  // (profiles/r1_convbench_epilogue_sets_b16.txt), so only 4 or 8 epilogue warps are built
+  const int sets1 = env_sets1 == 1 ? 1 : 2;
+  const int sets2 = 1;
   (void)env_sets2;
   const size_t tail_v1 = 8 * (2 * 8 + 4) + 48 + 4 * sets1 * EPI_WARP_BYTES + EPI_SS_BYTES;
   const size_t tail_v2 = 8 * (2 * 6 + 2 * 9 + 4) + 48 + 8 * sets2 * EPI_WARP_BYTES + EPI_SS_BYTES;
@@ -1467,8 +1471,8 @@ int conv_tc_launch(const cm2_conv_desc* d, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc2_kernel<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   }
   if (p.stats) {
     long long imgs = d->src[0].n;
@@ -1484,9 +1488,9 @@ int conv_tc_launch(const cm2_conv_desc* d, cudaStream_t stream) {
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sms ? tiles : sms;
   if (p.variant == 2)
-    conv_tc2_kernel<<<grid, 64 + 256 * p.epi_sets, p.smem_bytes, stream>>>(p);
+    conv_tc2_kernel<320><<<grid, 64 + 256 * p.epi_sets, p.smem_bytes, stream>>>(p);
   else
-    conv_tc_kernel<<<grid, 64 + 128 * p.epi_sets, p.smem_bytes, stream>>>(p);
+    conv_tc_kernel<320><<<grid, 64 + 128 * p.epi_sets, p.smem_bytes, stream>>>(p);
   CM2_CHECK_LAUNCH("conv_tc");
   return CM2_OK;
 }

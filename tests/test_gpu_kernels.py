@@ -194,6 +194,46 @@ def test_roialign_fpn_matches_torchvision_and_reference_level_rule():
     assert got[r_cap + counts[1]:].abs().max() == 0                  # invalid slots are zeroed
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_roialign_large_rois_separable_path(dtype):
+    """Adaptive sampling grids of 2..20 samples per bin side: the separable (row / column weight) evaluation, boxes that
+    stick out of the image, and bins wider than the register span (sample-loop fallback) against torchvision."""
+    import torchvision
+    g = torch.Generator().manual_seed(17)
+    n, r_cap, c = 2, 16, 64
+    H, W = 640, 1024
+    strides = (4, 8, 16)                                      # P"3" = 160 x 256: bins up to 19 pixels wide
+    feats = [torch.randn(n, c, H // s, W // s, generator=g) for s in strides]
+    if dtype == torch.bfloat16:
+        feats = [f.to(torch.bfloat16).float() for f in feats]
+    boxes = torch.zeros(n, r_cap, 4)
+    for i in range(n):
+        cx, cy = torch.rand(r_cap, generator=g) * W, torch.rand(r_cap, generator=g) * H
+        bw, bh = torch.rand(r_cap, generator=g) * W * 0.9 + 8, torch.rand(r_cap, generator=g) * H * 0.9 + 8
+        boxes[i] = torch.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1)       # many stick out of the image
+    boxes[0, 0] = torch.tensor([0.0, 0.0, W, H])
+    boxes[0, 1] = torch.tensor([-300.0, -200.0, 90.0, 120.0])
+    boxes[1, 0] = torch.tensor([W - 60.0, H - 40.0, W + 500.0, H + 300.0])
+    counts = torch.tensor([r_cap, r_cap - 3], dtype=torch.int32)
+    area = torch.tensor([float(H * W)] * n)
+    out = halo(torch.zeros(n * r_cap, c, 14, 14), dtype)
+    lvl = torch.full((n * r_cap,), -1, dtype=torch.int32, device=DEV)
+    lib.roialign_fpn([halo(f, dtype).view for f in feats], list(strides), boxes.to(DEV), counts.to(DEV), n, r_cap, area.to(DEV), 0, 0,
+                     out.view, lvl)
+    torch.cuda.synchronize()
+    got = nchw(out.view)
+    lv = lvl.cpu()
+    for i in range(n):
+        for r in range(int(counts[i])):
+            slot = i * r_cap + r
+            li = int(lv[slot])
+            roi = torch.cat([torch.tensor([float(i)]), boxes[i, r]])[None]
+            ref = torchvision.ops.roi_align(feats[li], roi, 14, 1.0 / strides[li], 0, True)[0]
+            tol = 1e-4 if dtype == torch.float32 else 1e-2
+            assert torch.allclose(got[slot], ref, rtol=tol, atol=tol), (i, r, li, (got[slot] - ref).abs().max())
+    assert got[r_cap + int(counts[1]):].abs().max() == 0
+
+
 def test_spatial_attention_mask_predict_maskiou_glue():
     g = torch.Generator().manual_seed(8)
     r, c = 5, 64
