@@ -8,6 +8,7 @@
 // is sorted by (raw score desc, flat index asc), which makes all later stages order-independent.
 #include "common.cuh"
 #include <algorithm>
+#include <string.h>
 
 namespace cm2 {
 
@@ -69,6 +70,52 @@ __global__ void __launch_bounds__(256) fcos_decode_rows_kernel(View<const float>
           if (vals[k] >= logit_floor)
             fcos_emit_candidate(regctr, img, py_, px_, c + k, ncls, vals[k], stride, reg_scale, thresh, thresh_with_ctr, level,
                                 num_levels, cap, cand);
+      }
+    }
+  }
+}
+
+// All pyramid levels in one launch (the four small levels are a few microseconds of work each): grid
+// (row-chunks, sum of level heights, n); the block looks its level up from the row prefix.
+constexpr int FCOS_MAX_LEVELS = 8;
+struct DecodeLevels {
+  View<const float> logits[FCOS_MAX_LEVELS], regctr[FCOS_MAX_LEVELS];
+  int stride[FCOS_MAX_LEVELS], row_prefix[FCOS_MAX_LEVELS + 1];
+  float reg_scale[FCOS_MAX_LEVELS];
+  int num;
+};
+
+__global__ void __launch_bounds__(256) fcos_decode_levels_kernel(const __grid_constant__ DecodeLevels lv, float thresh, float logit_floor,
+                                                                 int thresh_with_ctr, int cap, cm2_cand_buffers cand) {
+  int level = 0;
+#pragma unroll
+  for (int l = 1; l < FCOS_MAX_LEVELS; ++l)
+    if (l < lv.num && (int)blockIdx.y >= lv.row_prefix[l]) level = l;
+  const View<const float>& logits = lv.logits[level];
+  const View<const float>& regctr = lv.regctr[level];
+  const int img = blockIdx.z, py_ = blockIdx.y - lv.row_prefix[level];
+  const int ncls = logits.c;
+  const int n4 = (logits.w * ncls) >> 2;
+  const float4* row = reinterpret_cast<const float4*>(logits.at(img, py_, 0));
+  constexpr int U = 4;
+  for (int i0 = blockIdx.x * blockDim.x * U + threadIdx.x; i0 < n4; i0 += gridDim.x * blockDim.x * U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i0 + u * (int)blockDim.x < n4) v[u] = __ldg(row + i0 + u * blockDim.x);
+      else v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float m4 = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
+      if (i0 + u * (int)blockDim.x < n4 && m4 >= logit_floor) {      // rare
+        const int e = (i0 + u * (int)blockDim.x) * 4;
+        const int px_ = e / ncls, c = e - px_ * ncls;
+        const float vals[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (vals[k] >= logit_floor)
+            fcos_emit_candidate(regctr, img, py_, px_, c + k, ncls, vals[k], lv.stride[level], lv.reg_scale[level], thresh,
+                                thresh_with_ctr, level, lv.num, cap, cand);
       }
     }
   }
@@ -334,6 +381,47 @@ extern "C" int cm2_fcos_decode(const cm2_act* logits, const cm2_act* regctr, int
                                                                    make_view<const float>(*regctr), stride, reg_scale, thresh,
                                                                    logit_floor, thresh_with_ctr, level, num_levels, cap, *cand);
   CM2_CHECK_LAUNCH("fcos_decode");
+  return CM2_OK;
+}
+
+extern "C" int cm2_fcos_decode_levels(const cm2_act* logits, const cm2_act* regctr, const int32_t* strides, const float* reg_scales,
+                                      int32_t num_levels, float thresh, int32_t thresh_with_ctr, int32_t cap,
+                                      const cm2_cand_buffers* cand, void* stream) {
+  CM2_CHECK_ARG(logits && regctr && strides && reg_scales && cand, "fcos_decode_levels: null pointer");
+  CM2_CHECK_ARG(num_levels >= 1 && num_levels <= FCOS_MAX_LEVELS && cap > 0, "fcos_decode_levels: bad level count %d / cap %d", num_levels, cap);
+  bool fast = true;
+  for (int l = 0; l < num_levels; ++l) {
+    const cm2_act& a = logits[l];
+    CM2_CHECK_ARG(a.data && regctr[l].data && a.n == logits[0].n && regctr[l].n == a.n && regctr[l].h == a.h && regctr[l].w == a.w &&
+                  regctr[l].c >= 5 && a.c == logits[0].c, "fcos_decode_levels: level %d views do not match", l);
+    CM2_CHECK_ARG((int64_t)a.h * a.w * a.c < (1ll << 31), "fcos_decode_levels: level too large");
+    fast = fast && a.c % 4 == 0 && a.sw == a.c && a.sh % 4 == 0 && a.sn % 4 == 0 && (reinterpret_cast<uintptr_t>(a.data) & 15) == 0;
+  }
+  if (logits[0].n == 0) return CM2_OK;
+  if (!fast || logits[0].n > 65535) {                      // generic per-level path
+    for (int l = 0; l < num_levels; ++l) {
+      int rc = cm2_fcos_decode(&logits[l], &regctr[l], strides[l], reg_scales[l], thresh, thresh_with_ctr, l, num_levels, cap, cand, stream);
+      if (rc != CM2_OK) return rc;
+    }
+    return CM2_OK;
+  }
+  DecodeLevels lv;
+  memset(&lv, 0, sizeof(lv));
+  lv.num = num_levels;
+  int max_n4 = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    lv.logits[l] = make_view<const float>(logits[l]);
+    lv.regctr[l] = make_view<const float>(regctr[l]);
+    lv.stride[l] = strides[l];
+    lv.reg_scale[l] = reg_scales[l];
+    lv.row_prefix[l + 1] = lv.row_prefix[l] + logits[l].h;
+    max_n4 = std::max(max_n4, logits[l].w * logits[l].c / 4);
+  }
+  CM2_CHECK_ARG(lv.row_prefix[num_levels] <= 65535, "fcos_decode_levels: too many rows");
+  const float logit_floor = (thresh > 0.f && thresh < 1.f) ? (float)(log((double)thresh / (1.0 - (double)thresh)) - 1e-3) : -INFINITY;
+  dim3 grid(std::max(1, std::min(4, ceil_div(max_n4, 256 * 4))), lv.row_prefix[num_levels], logits[0].n);
+  fcos_decode_levels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(lv, thresh, logit_floor, thresh_with_ctr, cap, *cand);
+  CM2_CHECK_LAUNCH("fcos_decode_levels");
   return CM2_OK;
 }
 

@@ -170,24 +170,46 @@ __global__ void __launch_bounds__(512) spatial_attention_smem_kernel(View<const 
   const int S = x.h, C = x.c, c8 = C >> 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   if (threadIdx.x < 18) s_w[threadIdx.x] = w18[threadIdx.x];
-  for (int pix = warp; pix < S * S; pix += nwarps) {
-    const int y = pix / S, xx = pix - y * S;
-    const uint4* row = reinterpret_cast<const uint4*>(x.at(r, y, xx));
-    float sum = 0.f, mx = -INFINITY;
+  // phase 1: a warp owns pixels warp, warp + nwarps, ...; SAM_BATCH pixel rows are requested before the first one is
+  // reduced (a load -> reduce loop pays one memory latency per pixel: 13 per warp for a 14x14 ROI)
+  constexpr int SAM_BATCH = 7;
+  for (int pix0 = warp; pix0 < S * S; pix0 += nwarps * SAM_BATCH) {
     for (int cv = lane; cv < c8; cv += 32) {
-      const uint4 q = __ldg(row + cv);
-      s_x[pix * c8 + cv] = q;
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      uint4 q[SAM_BATCH];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float lo = __uint_as_float(w[k] << 16), hi = __uint_as_float(w[k] & 0xffff0000u);
-        sum += lo; sum += hi;
-        mx = fmaxf(mx, fmaxf(lo, hi));
+      for (int b = 0; b < SAM_BATCH; ++b) {
+        const int pix = pix0 + b * nwarps;
+        if (pix < S * S) {
+          const int y = pix / S, xx = pix - y * S;
+          q[b] = __ldg(reinterpret_cast<const uint4*>(x.at(r, y, xx)) + cv);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < SAM_BATCH; ++b) {
+        const int pix = pix0 + b * nwarps;
+        if (pix < S * S) s_x[pix * c8 + cv] = q[b];
       }
     }
-    sum = warp_sum(sum);
-    mx = warp_max(mx);
-    if (lane == 0) { s_avg[pix] = sum / (float)C; s_max[pix] = mx; }
+    __syncwarp();
+#pragma unroll 1
+    for (int b = 0; b < SAM_BATCH; ++b) {
+      const int pix = pix0 + b * nwarps;
+      if (pix >= S * S) break;
+      float sum = 0.f, mx = -INFINITY;
+      for (int cv = lane; cv < c8; cv += 32) {
+        const uint4 q = s_x[pix * c8 + cv];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float lo = __uint_as_float(w[k] << 16), hi = __uint_as_float(w[k] & 0xffff0000u);
+          sum += lo; sum += hi;
+          mx = fmaxf(mx, fmaxf(lo, hi));
+        }
+      }
+      sum = warp_sum(sum);
+      mx = warp_max(mx);
+      if (lane == 0) { s_avg[pix] = sum / (float)C; s_max[pix] = mx; }
+    }
   }
   __syncthreads();
   for (int pix = threadIdx.x; pix < S * S; pix += blockDim.x) {

@@ -481,10 +481,9 @@ class Engine(object):
         cb["count"].zero_()
         cand = lib.cand_buffers(cb["boxes"], cb["score"], cb["cls"], cb["flat"], cb["count"])
         strides = list(cfg.MODEL.FCOS.FPN_STRIDES)
-        for l, (logits, regctr) in enumerate(head_out):
-            lib.fcos_decode(logits.view, regctr.view, strides[l], 1.0 if reg_scale is None else float(reg_scale[l]),
-                            float(cfg.MODEL.FCOS.INFERENCE_TH_TEST),
-                            bool(cfg.MODEL.FCOS.THRESH_WITH_CTR), l, L, cap, cand)
+        lib.fcos_decode_levels([lg.view for lg, _ in head_out], [rc.view for _, rc in head_out], strides[:L],
+                               [1.0 if reg_scale is None else float(reg_scale[l]) for l in range(L)],
+                               float(cfg.MODEL.FCOS.INFERENCE_TH_TEST), bool(cfg.MODEL.FCOS.THRESH_WITH_CTR), cap, cand)
         det = dict(boxes=B("det_boxes", (n, post, 4), torch.float32, False), scores=B("det_scores", (n, post), torch.float32, False),
                    classes=B("det_classes", (n, post), torch.int64, False), locations=B("det_locs", (n, post, 2), torch.float32, False),
                    count=B("det_count", (n,), torch.int32, False))

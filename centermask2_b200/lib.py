@@ -84,6 +84,7 @@ SYMBOLS = {
     "cm2_ese_apply_pool": (_I, [_AP, _P, _AP, _AP, _AP, _I, _P]),
     "cm2_relu": (_I, [_AP, _AP, _I, _P]),
     "cm2_fcos_decode": (_I, [_AP, _AP, _I, _F, _F, _I, _I, _I, _I, C.POINTER(CandBuffers), _P]),
+    "cm2_fcos_decode_levels": (_I, [_AP, _AP, C.POINTER(_I), C.POINTER(_F), _I, _F, _I, _I, C.POINTER(CandBuffers), _P]),
     "cm2_fcos_select_workspace": (_L, [_I, _I, _I]),
     "cm2_fcos_select": (_I, [C.POINTER(CandBuffers), _I, _I, _I, C.POINTER(_I), C.POINTER(_I), _I, _I, _F, _I,
                              C.POINTER(DetBuffers), _P, _P]),
@@ -343,6 +344,17 @@ def fcos_decode(logits, regctr, stride, reg_scale, thresh, thresh_with_ctr, leve
     a, b = act(logits), act(regctr)
     check(load().cm2_fcos_decode(C.byref(a), C.byref(b), stride, reg_scale, thresh, int(thresh_with_ctr), level, num_levels, cap,
                                  C.byref(cand), stream()), "cm2_fcos_decode")
+    _count()
+
+
+def fcos_decode_levels(logits, regctrs, strides, reg_scales, thresh, thresh_with_ctr, cap, cand):
+    L = len(logits)
+    la = (Act * L)(*[act(t) for t in logits])
+    ra = (Act * L)(*[act(t) for t in regctrs])
+    st = (C.c_int32 * L)(*strides)
+    rs = (C.c_float * L)(*reg_scales)
+    check(load().cm2_fcos_decode_levels(la, ra, st, rs, L, thresh, int(thresh_with_ctr), cap, C.byref(cand), stream()),
+          "cm2_fcos_decode_levels")
     _count()
 
 

@@ -253,6 +253,11 @@ typedef struct cm2_cand_buffers {
 int cm2_fcos_decode(const cm2_act* logits, const cm2_act* regctr, int32_t stride, float reg_scale, float thresh,
                     int32_t thresh_with_ctr, int32_t level, int32_t num_levels, int32_t cap,
                     const cm2_cand_buffers* cand, void* stream);
+/* All levels in one launch: logits / regctr / strides / reg_scales are HOST arrays of num_levels entries (<= 8);
+ * level l writes candidate segment (image, l).  Same semantics as num_levels calls of cm2_fcos_decode. */
+int cm2_fcos_decode_levels(const cm2_act* logits, const cm2_act* regctr, const int32_t* strides, const float* reg_scales,
+                           int32_t num_levels, float thresh, int32_t thresh_with_ctr, int32_t cap,
+                           const cm2_cand_buffers* cand, void* stream);
 
 int64_t cm2_fcos_select_workspace(int32_t n, int32_t num_levels, int32_t cap);
 

@@ -416,6 +416,7 @@ def run_model(batched_inputs, sd, cfg, postprocess=True, pre_topk=True, trace=No
     """GeneralizedRCNN.inference [d2] (call sequence mirrored in-tree at /root/reference/tester.py:24-75)."""
     with torch.no_grad():
         x, sizes = preprocess(batched_inputs, cfg)
+        x = _q(x)          # the tensor-core engine stores the normalised input as bf16 (fused normalise + im2col)
         stages = vovnet_forward(x, sd, cfg, trace=trace)
         feats = fpn_forward(stages, sd, cfg)
         logits, regs, ctrs = fcos_head_forward(feats, sd, cfg)

@@ -101,8 +101,8 @@ def main():
 
     def decode():
         cb["count"].zero_()
-        for l, (lg, rc) in enumerate(head):
-            lib.fcos_decode(lg.view, rc.view, LEVELS[l][2], 1.0, 0.05, False, l, L, cap, cbuf)
+        lib.fcos_decode_levels([lg.view for lg, _ in head], [rc.view for _, rc in head], [s for _, _, s in LEVELS], [1.0] * L, 0.05, False,
+                               cap, cbuf)
     ms = timed(decode)
     report("fcos_decode (5 levels)", ms, n * 22400 * 85 * 4, "{:.0f} candidates / level / image".format(cand))
 
