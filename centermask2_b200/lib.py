@@ -69,6 +69,8 @@ SYMBOLS = {
     "cm2_preprocess_im2col_batch": (_I, [C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _AP,
                                          _I, _P]),
     "cm2_resize_pil_u8": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _I, _P]),
+    "cm2_rle_count": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
+    "cm2_rle_write": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "cm2_phase_split": (_I, [_AP, _AP, _I, _I, _P]),
     "cm2_maxpool3x3s2_ceil": (_I, [_AP, _AP, _I, _P]),
     "cm2_ese_pool_chunks": (_I, [_I]),
@@ -249,6 +251,19 @@ def preprocess_im2col_batch(imgs, mean, std, hp, wp, out, index0=0):
 def resize_pil_u8(src, tmp, dst, h, w, c, oh, ow, bounds_x, kk_x, bounds_y, kk_y, chw):
     check(load().cm2_resize_pil_u8(ptr(src), ptr(tmp), ptr(dst), h, w, c, oh, ow, ptr(bounds_x), ptr(kk_x), kk_x.shape[1],
                                    ptr(bounds_y), ptr(kk_y), kk_y.shape[1], int(chw), stream()), "cm2_resize_pil_u8")
+    _count(2)
+
+
+def rle_count(masks, col_count, col_offset, total):
+    r, h, w = masks.shape
+    check(load().cm2_rle_count(ptr(masks), r, h, w, ptr(col_count), ptr(col_offset), ptr(total), stream()), "cm2_rle_count")
+    _count(2)
+
+
+def rle_write(masks, col_offset, total, mask_offset, positions, runs):
+    r, h, w = masks.shape
+    check(load().cm2_rle_write(ptr(masks), r, h, w, ptr(col_offset), ptr(total), ptr(mask_offset), ptr(positions), ptr(runs), stream()),
+          "cm2_rle_write")
     _count(2)
 
 

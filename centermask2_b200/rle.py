@@ -1,0 +1,99 @@
+"""COCO RLE encoding of pasted masks with the run lengths computed on the device.
+
+Mirrors what ``instances_to_coco_json`` does with pycocotools
+(``/root/reference/centermask2/centermask/evaluation/coco_evaluation.py:362-427``):
+``mask_util.encode(np.array(mask[:, :, None], order="F", dtype="uint8"))[0]`` per mask, then
+``rle["counts"].decode("utf-8")``.  pycocotools' ``rleEncode`` (column-major run lengths, first run counts zeros) runs in
+``libcm2.so`` (``csrc/rle.cu``); only the runs are copied to the host, where ``rleToString`` (maskApi.c: difference
+coding against the run two places back, 5 bits per character + continuation bit, offset 48) is applied with numpy.
+"""
+import numpy as np
+import torch
+
+from . import lib
+
+
+def runs_to_string(cnts):
+    """maskApi.c ``rleToString``: uint32 run lengths -> ASCII ``bytes``."""
+    x = np.asarray(cnts, dtype=np.int64).copy()
+    if x.size > 3:
+        x[3:] -= np.asarray(cnts, dtype=np.int64)[1:-2]
+    chars, valid = [], []
+    alive = np.ones(x.shape, dtype=bool)
+    while alive.any():
+        c = x & 0x1f
+        x = x >> 5                                    # arithmetic shift, as C's >> on a signed long
+        more = np.where((c & 0x10) != 0, x != -1, x != 0)
+        c = np.where(more, c | 0x20, c) + 48
+        chars.append(c.astype(np.uint8))
+        valid.append(alive.copy())
+        alive &= more
+    ch = np.stack(chars, axis=1)
+    va = np.stack(valid, axis=1)
+    return ch[va].tobytes()
+
+
+def encode_runs(masks):
+    """masks: bool / uint8 CUDA tensor [R, H, W] -> list of R uint32 numpy arrays of run lengths (pycocotools ``rleEncode``)."""
+    if masks.dim() != 3:
+        raise ValueError("masks must be [R, H, W]")
+    if not masks.is_cuda:
+        raise RuntimeError("centermask2_b200.rle needs masks on a CUDA device (there is no CPU fallback)")
+    r, h, w = masks.shape
+    if r == 0:
+        return []
+    m8 = masks.contiguous().view(torch.uint8) if masks.dtype == torch.bool else masks.contiguous()
+    dev = m8.device
+    col_count = torch.empty((r, w), dtype=torch.int32, device=dev)
+    col_offset = torch.empty((r, w), dtype=torch.int32, device=dev)
+    total = torch.empty((r,), dtype=torch.int32, device=dev)
+    lib.rle_count(m8, col_count, col_offset, total)
+    total_h = total.cpu()                                          # one small D2H copy sizes the output
+    nruns = total_h.to(torch.int64) + 1
+    offs = torch.zeros((r + 1,), dtype=torch.int64)
+    offs[1:] = torch.cumsum(nruns, 0)
+    n_all = int(offs[-1])
+    mask_offset = offs[:-1].to(dev)
+    positions = torch.empty((n_all,), dtype=torch.int32, device=dev)
+    runs = torch.empty((n_all,), dtype=torch.int32, device=dev)
+    lib.rle_write(m8, col_offset, total, mask_offset, positions, runs)
+    flat = runs.cpu().numpy().view(np.uint32)
+    o = offs.numpy()
+    return [flat[o[i]:o[i + 1]] for i in range(r)]
+
+
+def encode(masks):
+    """pycocotools ``mask.encode`` for a stack of masks: -> list of ``{"size": [h, w], "counts": bytes}``."""
+    h, w = int(masks.shape[1]), int(masks.shape[2])
+    return [{"size": [h, w], "counts": runs_to_string(c)} for c in encode_runs(masks)]
+
+
+def instances_to_coco_json(instances, img_id):
+    """``coco_evaluation.py:362-427`` for the fields this path produces (boxes XYXY -> XYWH, scores, classes, RLE
+    segmentation with utf-8 ``counts``, ``mask_score``)."""
+    n = len(instances)
+    if n == 0:
+        return []
+    boxes = instances.pred_boxes.tensor.detach().float().cpu().clone()
+    boxes[:, 2] -= boxes[:, 0]
+    boxes[:, 3] -= boxes[:, 1]
+    boxes = boxes.tolist()
+    scores = instances.scores.tolist()
+    classes = instances.pred_classes.tolist()
+    has_mask = instances.has("pred_masks")
+    has_ms = instances.has("mask_scores")
+    if has_mask:
+        rles = encode(instances.pred_masks)
+        for rle in rles:
+            rle["counts"] = rle["counts"].decode("utf-8")
+        if has_ms:
+            mask_scores = instances.mask_scores.tolist()
+    out = []
+    for k in range(n):
+        res = {"image_id": img_id, "category_id": classes[k], "bbox": boxes[k], "score": scores[k]}
+        if has_mask:
+            res["segmentation"] = rles[k]
+            if has_ms:
+                res["mask_score"] = mask_scores[k]
+        out.append(res)
+    return out

@@ -337,6 +337,20 @@ int cm2_scale_clip_boxes_batch(const float* boxes_in, float* boxes_out, uint8_t*
 int cm2_paste_masks(const float* probs, const float* boxes, const uint8_t* valid, uint8_t* out,
                     int32_t r, int32_t m, int32_t out_h, int32_t out_w, float threshold, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Result encoding: COCO run-length encoding of the pasted masks, i.e. pycocotools' rleEncode as
+ * called per mask by instances_to_coco_json (/root/reference/centermask2/centermask/evaluation/coco_evaluation.py:388-391).
+ * masks: uint8 [r][h][w] (0 / non-zero).  Runs are counted in column-major order and start with a run of zeros.
+ * cm2_rle_count: col_count / col_offset int32 [r][w] scratch; total[m] = number of value changes of mask m, so mask m
+ *   has total[m] + 1 runs.  The caller then builds mask_offset (exclusive scan of total + 1) and sizes the outputs.
+ * cm2_rle_write: positions (scratch) and runs: uint32 [sum(total + 1)]; runs[mask_offset[m] + k] = length of run k.
+ * The LEB128-like string compression (rleToString) is done on the host (centermask2_b200/rle.py).
+ * ------------------------------------------------------------------------------------------- */
+int cm2_rle_count(const uint8_t* masks, int32_t r, int32_t h, int32_t w, int32_t* col_count, int32_t* col_offset,
+                  int32_t* total, void* stream);
+int cm2_rle_write(const uint8_t* masks, int32_t r, int32_t h, int32_t w, const int32_t* col_offset, const int32_t* total,
+                  const int64_t* mask_offset, uint32_t* positions, uint32_t* runs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
