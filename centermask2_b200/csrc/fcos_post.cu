@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <string.h>
+#include <stdlib.h>
 
 namespace cm2 {
 
@@ -118,6 +119,58 @@ __global__ void __launch_bounds__(256) fcos_decode_levels_kernel(const __grid_co
                                 thresh_with_ctr, level, lv.num, cap, cand);
       }
     }
+  }
+}
+
+// Flat-tile variant (every level's image is one dense run of h * w * ncls floats): the batch is cut into tiles of
+// DECODE_TILE float4 (32 KB); a CTA takes one tile and every thread has its DECODE_U 16-byte loads in flight before the
+// first compare -- 7 104 full CTAs for the 800x1344 pyramid at batch 32 instead of 24 960 mostly idle row CTAs.
+constexpr int DECODE_U = 8;
+constexpr int DECODE_TILE = 256 * DECODE_U;
+struct DecodeTiles {
+  DecodeLevels lv;
+  int tile_prefix[FCOS_MAX_LEVELS + 1];                 // tiles per image, prefix over levels
+};
+
+__global__ void __launch_bounds__(256) fcos_decode_tiles_kernel(const __grid_constant__ DecodeTiles dt, float thresh, float logit_floor,
+                                                                int thresh_with_ctr, int cap, cm2_cand_buffers cand) {
+  const DecodeLevels& lv = dt.lv;
+  // grid (n, tiles): the image index varies fastest, so the CTAs in flight append to the counters of many
+  // (image, level) segments instead of queueing on a handful of addresses
+  const int img = blockIdx.x, tile = blockIdx.y;
+  int level = 0;
+#pragma unroll
+  for (int l = 1; l < FCOS_MAX_LEVELS; ++l)
+    if (l < lv.num && tile >= dt.tile_prefix[l]) level = l;
+  const View<const float>& logits = lv.logits[level];
+  const int ncls = logits.c;
+  const int n4 = (logits.h * logits.w * ncls) >> 2;
+  const float* img_base = logits.p + img * logits.sn;
+  const float4* base = reinterpret_cast<const float4*>(img_base);
+  const int i0 = (tile - dt.tile_prefix[level]) * DECODE_TILE + threadIdx.x;
+  float4 v[DECODE_U];
+#pragma unroll
+  for (int u = 0; u < DECODE_U; ++u)
+    if (i0 + u * 256 < n4) v[u] = __ldg(base + i0 + u * 256);
+    else v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  // one bit per logit that reaches the floor; the (rare) candidates are then handled by ONE copy of the emit code in a
+  // loop over the set bits -- unrolling the emit path DECODE_U x 4 times made the kernel instruction-fetch bound
+  uint32_t hits = 0u;
+#pragma unroll
+  for (int u = 0; u < DECODE_U; ++u) {
+    hits |= (v[u].x >= logit_floor ? 1u : 0u) << (4 * u);
+    hits |= (v[u].y >= logit_floor ? 2u : 0u) << (4 * u);
+    hits |= (v[u].z >= logit_floor ? 4u : 0u) << (4 * u);
+    hits |= (v[u].w >= logit_floor ? 8u : 0u) << (4 * u);
+  }
+  while (hits) {
+    const int bit = __ffs(hits) - 1;
+    hits &= hits - 1u;
+    const int e = (i0 + (bit >> 2) * 256) * 4 + (bit & 3);
+    const int pos = e / ncls, c = e - pos * ncls;
+    const int py_ = pos / logits.w, px_ = pos - py_ * logits.w;
+    fcos_emit_candidate(lv.regctr[level], img, py_, px_, c, ncls, __ldg(img_base + e), lv.stride[level], lv.reg_scale[level], thresh,
+                        thresh_with_ctr, level, lv.num, cap, cand);
   }
 }
 
@@ -419,6 +472,25 @@ extern "C" int cm2_fcos_decode_levels(const cm2_act* logits, const cm2_act* regc
   }
   CM2_CHECK_ARG(lv.row_prefix[num_levels] <= 65535, "fcos_decode_levels: too many rows");
   const float logit_floor = (thresh > 0.f && thresh < 1.f) ? (float)(log((double)thresh / (1.0 - (double)thresh)) - 1e-3) : -INFINITY;
+  const int variant = getenv("CM2_DECODE_VARIANT") ? atoi(getenv("CM2_DECODE_VARIANT")) : 1;
+  bool dense = variant == 1;
+  for (int l = 0; l < num_levels; ++l) dense = dense && logits[l].sh == (int64_t)logits[l].w * logits[l].c;
+  int tiles_total = 0;
+  for (int l = 0; l < num_levels; ++l) tiles_total += ceil_div(logits[l].h * logits[l].w * logits[l].c / 4, DECODE_TILE);
+  dense = dense && tiles_total <= 65535;
+  if (dense) {
+    DecodeTiles dt;
+    dt.lv = lv;
+    dt.tile_prefix[0] = 0;
+    for (int l = 0; l < FCOS_MAX_LEVELS; ++l) {
+      const int n4 = l < num_levels ? logits[l].h * logits[l].w * logits[l].c / 4 : 0;
+      dt.tile_prefix[l + 1] = dt.tile_prefix[l] + ceil_div(n4, DECODE_TILE);
+    }
+    dim3 grid(logits[0].n, dt.tile_prefix[num_levels]);
+    fcos_decode_tiles_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dt, thresh, logit_floor, thresh_with_ctr, cap, *cand);
+    CM2_CHECK_LAUNCH("fcos_decode_tiles");
+    return CM2_OK;
+  }
   dim3 grid(std::max(1, std::min(4, ceil_div(max_n4, 256 * 4))), lv.row_prefix[num_levels], logits[0].n);
   fcos_decode_levels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(lv, thresh, logit_floor, thresh_with_ctr, cap, *cand);
   CM2_CHECK_LAUNCH("fcos_decode_levels");

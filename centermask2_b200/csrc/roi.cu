@@ -2,6 +2,8 @@
 // class-gathered mask predictor + sigmoid, MaskIoU input/score glue, box rescale and mask paste-back.
 // All bandwidth-bound: coalesced over channels (NHWC) / over x (paste), 8 channels per thread.
 #include "common.cuh"
+#include <algorithm>
+#include <stdlib.h>
 
 namespace cm2 {
 
@@ -97,6 +99,179 @@ __global__ void roialign_fpn_kernel(const RoiAlignParams<T> p) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] /= count;
     }
+    Vec8<T>::store(p.out.at(slot, ph, pw) + cv * 8, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ROIAlign, one CTA per ROI slot, MERGED TAPS.  The average over the adaptive sampling grid is separable:
+//   out[ph][pw] = 1/count * sum_Y sum_X Wy[ph][Y] * Wx[pw][X] * f[Y][X],
+// where Wy[ph][Y] collects the bilinear row weights of the bin's grid_h samples (hy on y_low, ly on y_high; samples
+// outside [-1, H] dropped, coordinates clamped -- torchvision's rules) and Wx likewise.  A bin therefore reads
+// (grid_h + 1) x (grid_w + 1) feature vectors instead of 4 x grid_h x grid_w, every one of them a contiguous 16 bytes
+// per lane / 512 bytes per warp (NHWC).  The two weight tables (res x ROI_MAXT each) are built once per CTA in shared
+// memory; a box whose grid does not fit the tables falls back to the sample loop.  Sums are reordered with respect to
+// torchvision (fp32 rounding only).
+// ---------------------------------------------------------------------------------------------
+// 8 channels as loaded (the conversion happens when the value is used, so several loads can be in flight cheaply)
+__device__ __forceinline__ void ffma2_roi(float& d0, float& d1, float a0, float a1, float b) {
+  asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %4};\nmov.b64 rc, {%0, %1};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0, %1}, rd;\n}"
+      : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1), "f"(b));
+}
+template <typename T> struct Raw8;
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = __ldg(reinterpret_cast<const float4*>(p));
+    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void fma(float w, float (&acc)[8]) const {
+    ffma2_roi(acc[0], acc[1], a.x, a.y, w); ffma2_roi(acc[2], acc[3], a.z, a.w, w);
+    ffma2_roi(acc[4], acc[5], b.x, b.y, w); ffma2_roi(acc[6], acc[7], b.z, b.w, w);
+  }
+};
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 q;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { q = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void fma(float w, float (&acc)[8]) const {
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      ffma2_roi(acc[2 * k], acc[2 * k + 1], __uint_as_float(u[k] << 16), __uint_as_float(u[k] & 0xffff0000u), w);
+  }
+};
+
+constexpr int ROI_MAXT = 32;
+constexpr int ROI_MAX_RES = 32;
+
+template <typename T>
+__device__ __forceinline__ void roialign_sample_loop(const View<const T>& f, int img, int cv, int ph, int pw, float roi_start_h,
+                                                     float roi_start_w, float bin_h, float bin_w, int grid_h, int grid_w,
+                                                     float (&acc)[8]) {
+  const int height = f.h, width = f.w;
+  for (int iy = 0; iy < grid_h; ++iy) {
+    float y = roi_start_h + ph * bin_h + ((float)iy + 0.5f) * bin_h / (float)grid_h;
+    for (int ix = 0; ix < grid_w; ++ix) {
+      float x = roi_start_w + pw * bin_w + ((float)ix + 0.5f) * bin_w / (float)grid_w;
+      if (y < -1.0f || y > (float)height || x < -1.0f || x > (float)width) continue;
+      float yy = y <= 0.f ? 0.f : y, xx = x <= 0.f ? 0.f : x;
+      int y_low = (int)yy, x_low = (int)xx, y_high, x_high;
+      if (y_low >= height - 1) { y_high = y_low = height - 1; yy = (float)y_low; } else y_high = y_low + 1;
+      if (x_low >= width - 1) { x_high = x_low = width - 1; xx = (float)x_low; } else x_high = x_low + 1;
+      float ly = yy - (float)y_low, lx = xx - (float)x_low, hy = 1.f - ly, hx = 1.f - lx;
+      float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+      // rare path (boxes wider than 14 * 30 feature pixels): one tap at a time keeps the register footprint of the
+      // kernel that of the merged-tap loop
+      const float wt[4] = {w1, w2, w3, w4};
+      const int ty[4] = {y_low, y_low, y_high, y_high}, tx[4] = {x_low, x_high, x_low, x_high};
+#pragma unroll 1
+      for (int t = 0; t < 4; ++t) {
+        Raw8<T> rv;
+        rv.load(f.at(img, ty[t], tx[t]) + cv * 8);
+        rv.fma(wt[t], acc);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 3) roialign_roi_kernel(const RoiAlignParams<T> p) {
+  __shared__ float s_w[2][ROI_MAX_RES][ROI_MAXT];       // [axis][bin][tap] merged weights (axis 0 = y)
+  __shared__ int s_start[2][ROI_MAX_RES], s_num[2][ROI_MAX_RES];
+  const int slot = blockIdx.x;
+  const int img = slot / p.r_cap, r = slot - img * p.r_cap;
+  const int res = p.res, c8 = p.out.c >> 3, bins = res * res;
+  const int items = bins * c8;
+  if (r >= p.det_count[img]) {                          // empty slot: zeros
+    const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+      const int bin = i / c8, cv = i - bin * c8;
+      const int ph = bin / res, pw = bin - ph * res;
+      Vec8<T>::store(p.out.at(slot, ph, pw) + cv * 8, z);
+    }
+    return;
+  }
+  const float4 bx = reinterpret_cast<const float4*>(p.boxes)[slot];
+  int lvl = assign_level(bx.x, bx.y, bx.z, bx.w, p.image_area[img], p.crit, p.min_level, p.max_level);
+  if (lvl >= p.num_levels) lvl = p.num_levels - 1;
+  if (p.level_out && threadIdx.x == 0) p.level_out[slot] = lvl;
+  View<const T> f = p.feat[0];
+  float scale = p.scale[0];
+#pragma unroll
+  for (int l = 1; l < ROI_MAX_LEVELS; ++l)
+    if (l == lvl) { f = p.feat[l]; scale = p.scale[l]; }
+  const float roi_start_w = bx.x * scale - 0.5f, roi_start_h = bx.y * scale - 0.5f;
+  const float roi_end_w = bx.z * scale - 0.5f, roi_end_h = bx.w * scale - 0.5f;
+  const float roi_width = roi_end_w - roi_start_w, roi_height = roi_end_h - roi_start_h;
+  const float bin_h = roi_height / (float)res, bin_w = roi_width / (float)res;
+  const int grid_h = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(roi_height / (float)res);
+  const int grid_w = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(roi_width / (float)res);
+  const float count = fmaxf((float)(grid_h * grid_w), 1.f);
+  const bool merged = grid_h + 2 <= ROI_MAXT && grid_w + 2 <= ROI_MAXT;      // CTA-uniform
+  if (merged) {
+    for (int i = threadIdx.x; i < 2 * res * ROI_MAXT; i += blockDim.x) {
+      const int axis = i / (res * ROI_MAXT), rem = i - axis * res * ROI_MAXT;
+      s_w[axis][rem / ROI_MAXT][rem % ROI_MAXT] = 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * res) {
+      const int axis = threadIdx.x / res, pb = threadIdx.x - axis * res;
+      const float start = axis ? roi_start_w : roi_start_h, bin = axis ? bin_w : bin_h;
+      const int grid = axis ? grid_w : grid_h, extent = axis ? f.w : f.h;
+      int s0 = -1, num = 0;
+      for (int i = 0; i < grid; ++i) {
+        const float v = start + pb * bin + ((float)i + 0.5f) * bin / (float)grid;
+        if (v < -1.0f || v > (float)extent) continue;
+        float vv = v <= 0.f ? 0.f : v;
+        int low = (int)vv, high;
+        if (low >= extent - 1) { high = low = extent - 1; vv = (float)low; } else high = low + 1;
+        const float l = vv - (float)low, h = 1.f - l;
+        if (s0 < 0) s0 = low;
+        s_w[axis][pb][low - s0] += h;
+        s_w[axis][pb][high - s0] += l;
+        num = high - s0 + 1;
+      }
+      s_start[axis][pb] = s0 < 0 ? 0 : s0;
+      s_num[axis][pb] = num;
+    }
+    __syncthreads();
+  }
+  // exact division of small indices by the run-time constants c8 / res: q = umulhi(i, ceil(2^32 / d)) for i * d < 2^32
+  const uint32_t magic_c8 = (uint32_t)((0x100000000ull + c8 - 1) / (uint32_t)c8);
+  const uint32_t magic_res = (uint32_t)((0x100000000ull + res - 1) / (uint32_t)res);
+  const float inv_count = 1.0f / count;
+  const int sw = (int)f.sw;
+  constexpr int RY = 1;             // tap rows in flight together (register budget)
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int bin = c8 == 32 ? (i >> 5) : (c8 == 1 ? i : (int)__umulhi((uint32_t)i, magic_c8)), cv = i - bin * c8;
+    const int ph = res == 1 ? bin : (int)__umulhi((uint32_t)bin, magic_res), pw = bin - ph * res;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (merged) {
+      const int ny = s_num[0][ph], nx = s_num[1][pw];
+      const float* wy = s_w[0][ph];
+      const float* wx = s_w[1][pw];
+      const T* base = f.at(img, s_start[0][ph], s_start[1][pw]) + cv * 8;
+      for (int jy = 0; jy < ny; jy += RY) {
+        for (int jx0 = 0; jx0 < nx; jx0 += 4) {
+          Raw8<T> rv[RY][4];
+#pragma unroll
+          for (int a = 0; a < RY; ++a)
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (jy + a < ny && jx0 + u < nx) rv[a][u].load(base + (size_t)(jy + a) * f.sh + (jx0 + u) * sw);
+#pragma unroll
+          for (int a = 0; a < RY; ++a)
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (jy + a < ny && jx0 + u < nx) rv[a][u].fma(wy[jy + a] * wx[jx0 + u], acc);
+        }
+      }
+    } else {
+      roialign_sample_loop<T>(f, img, cv, ph, pw, roi_start_h, roi_start_w, bin_h, bin_w, grid_h, grid_w, acc);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] *= inv_count;
     Vec8<T>::store(p.out.at(slot, ph, pw) + cv * 8, acc);
   }
 }
@@ -489,6 +664,155 @@ __global__ void __launch_bounds__(256) paste_window_kernel(const float* __restri
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused paste (out_h * out_w % 16 == 0, 16-byte aligned buffer): every byte of the [r, out_h, out_w] buffer is written
+// exactly once with 16-byte stores, no memset.  grid (slabs, r): a CTA owns a contiguous run of 16-byte chunks of one
+// ROI plane (about 48 image rows).
+//   phase Z  chunks that do not touch the dilated box window are stored as zeros (a slab that misses the window rows
+//            does nothing else);
+//   phase C  the window part of the slab is evaluated with FIXED COLUMNS per lane: a warp owns a strip of 32 columns,
+//            the x interpolation (tap column + two weights) lives in registers for the whole strip, the y
+//            interpolation comes from a per-row table and the four taps of a pixel are ONE 16-byte shared-memory load
+//            from a pre-gathered table M4[yl][xl] = (m[yl][xl], m[yl][xl+1], m[yl+1][xl], m[yl+1][xl+1]) with a zero
+//            border of two cells (grid_sample's zero padding without bounds tests).  A ballot per (row, strip) packs
+//            the 32 decisions into one word of a bit tile in shared memory;
+//   phase W  the chunks that touch the window gather their 16 bits from the bit tile (funnel shift over two words,
+//            rows of an 800x1333 plane are not aligned to anything), expand them to 16 bytes and store.
+// The arithmetic (operand order included) is that of paste_window_words_kernel, i.e. ATen's grid_sampler_2d.
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) PasteRow { float wy0, wy1; int base, pad; };
+
+__device__ __forceinline__ uint32_t spread4(uint32_t nib) {          // bits 0..3 -> bytes 0..3 (0 / 1)
+  return (nib * 0x00204081u) & 0x01010101u;
+}
+
+__global__ void __launch_bounds__(256) paste_fused_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
+                                                          const uint8_t* __restrict__ valid, uint8_t* __restrict__ out,
+                                                          int m, int out_h, int out_w, float threshold, int rows_cap,
+                                                          int pitch) {
+  extern __shared__ uint4 s_dyn4[];
+  const int r = blockIdx.y, tid = threadIdx.x;
+  const int nchunks = (out_h * out_w) >> 4;
+  const int cA = (int)((long long)nchunks * blockIdx.x / gridDim.x);
+  const int cB = (int)((long long)nchunks * (blockIdx.x + 1) / gridDim.x);
+  if (cA >= cB) return;
+  uint4* __restrict__ oplane = reinterpret_cast<uint4*>(out + (size_t)r * out_h * out_w);
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  int xa = 0, xb = 0, ya = 0, yb = 0;
+  float4 b = make_float4(0.f, 0.f, 1.f, 1.f);
+  if (valid[r] != 0) {
+    b = reinterpret_cast<const float4*>(boxes)[r];
+    xa = max((int)floorf(b.x) - 1, 0); ya = max((int)floorf(b.y) - 1, 0);
+    xb = min((int)ceilf(b.z) + 1, out_w); yb = min((int)ceilf(b.w) + 1, out_h);
+    if (xa >= xb || ya >= yb) xa = xb = ya = yb = 0;
+  }
+  const int yA = (cA * 16) / out_w, yB = (cB * 16 - 1) / out_w;       // image rows this slab touches
+  const int r0 = max(ya, yA), r1 = min(yb, yB + 1);                   // window rows inside the slab: [r0, r1)
+  if (r0 >= r1) {                                                     // common: nothing but zeros
+    for (int c = cA + tid; c < cB; c += 256) oplane[c] = zero4;
+    return;
+  }
+  // The slab is walked by image rows: row y owns the chunks that START in it, [ceil(y W / 16), ceil((y + 1) W / 16)),
+  // clipped to the slab; only the last of them can reach into row y + 1.  A warp takes a row at a time, its lanes
+  // consecutive chunks (512 contiguous bytes per store instruction).  `window` selects the rows whose chunks can touch
+  // the window (the row itself or the next one is a window row); the other rows are plain zeros.
+  const int warp = tid >> 5, lane = tid & 31;
+  const int nstr = (xb - xa + 31) >> 5;                               // 32-column strips; words 1 .. nstr of a tile row
+  const uint32_t* s_bits_c = nullptr;
+  auto row_pass = [&](bool window) {
+    for (int y = yA + warp; y <= yB; y += 8) {
+      const bool in_y = y >= r0 && y < r1, in_next = y + 1 >= r0 && y + 1 < r1;
+      if ((in_y || in_next) != window) continue;
+      const int row0 = y * out_w;
+      const int cs = max((row0 + 15) >> 4, cA), ce = min((row0 + out_w + 15) >> 4, cB);
+      if (!window) {
+        for (int c = cs + lane; c < ce; c += 32) oplane[c] = zero4;
+        continue;
+      }
+      const uint32_t* trow = s_bits_c + (y - r0) * pitch;             // only dereferenced when the row is a window row
+      for (int c = cs + lane; c < ce; c += 32) {
+        const int x = c * 16 - row0, xe = x + 15;
+        uint32_t bits = 0u;
+        if (in_y && xe >= xa && x < xb) {                             // x - xa + 32 lies in [17, 32 nstr + 32)
+          const int rel = x - xa + 32;
+          bits = __funnelshift_r(trow[rel >> 5], trow[(rel >> 5) + 1], rel & 31) & 0xffffu;
+        }
+        if (in_next && xe >= out_w && xa <= xe - out_w) {             // the chunk's tail lies in columns 0 .. of row y + 1
+          const int n1 = out_w - x, rel = 32 - xa;                    // xa <= 14 here
+          const uint32_t nb = __funnelshift_r(trow[pitch + (rel >> 5)], trow[pitch + (rel >> 5) + 1], rel & 31);
+          bits = (bits & ((1u << n1) - 1u)) | ((nb << n1) & 0xffffu);
+        }
+        oplane[c] = bits ? make_uint4(spread4(bits & 15u), spread4((bits >> 4) & 15u), spread4((bits >> 8) & 15u), spread4(bits >> 12))
+                         : zero4;
+      }
+    }
+  };
+  // ---- phase Z
+  row_pass(false);
+  // ---- tables
+  const int mq = m + 3;
+  float4* s_m4 = reinterpret_cast<float4*>(s_dyn4);
+  PasteRow* s_row = reinterpret_cast<PasteRow*>(s_dyn4 + mq * mq);
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_dyn4 + mq * mq + rows_cap);
+  const float* pm = probs + (size_t)r * m * m;
+  for (int i = tid; i < mq * mq; i += 256) {
+    const int yl = i / mq - 2, xl = i - (yl + 2) * mq - 2;
+    auto P = [&](int yy, int xx) -> float { return (yy >= 0 && yy < m && xx >= 0 && xx < m) ? __ldg(pm + yy * m + xx) : 0.f; };
+    s_m4[i] = make_float4(P(yl, xl), P(yl, xl + 1), P(yl + 1, xl), P(yl + 1, xl + 1));
+  }
+  const float bw = b.z - b.x, bh = b.w - b.y, fm = (float)m;
+  const int nrows = r1 - r0;
+  for (int i = tid; i < nrows; i += 256) {
+    const int y = r0 + i;
+    const float gy = ((float)y + 0.5f - b.y) / bh * 2.f - 1.f;
+    const float iy = ((gy + 1.f) * fm - 1.f) * 0.5f;
+    const float fy = floorf(iy);
+    PasteRow pr;
+    pr.wy1 = iy - fy; pr.wy0 = (fy + 1.f) - iy;                      // ATen: (iy_se - iy), (iy - iy_nw)
+    const int yl = (int)fminf(fmaxf(fy, -2.f), fm);
+    pr.base = (yl + 2) * mq * 16; pr.pad = 0;
+    s_row[i] = pr;
+  }
+  for (int i = tid; i < nrows * pitch; i += 256) s_bits[i] = 0u;
+  __syncthreads();
+  // ---- phase C
+  {
+    // work items = strips x row groups, at least ~24 of them so that the eight warps finish together
+    int groups = (24 + nstr - 1) / nstr;
+    groups = max(1, min(groups, nrows >> 2));
+    const int rows_per_group = (nrows + groups - 1) / groups;
+    for (int item = warp; item < nstr * groups; item += 8) {
+      const int g = item / nstr, j = item - g * nstr;
+      const int x = xa + 32 * j + lane;
+      const float gx = ((float)x + 0.5f - b.x) / bw * 2.f - 1.f;
+      const float ix = ((gx + 1.f) * fm - 1.f) * 0.5f;
+      const float fx = floorf(ix);
+      const float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
+      const int xl = (int)fminf(fmaxf(fx, -2.f), fm);
+      const char* tap0 = reinterpret_cast<const char*>(s_m4) + (xl + 2) * 16;
+      const bool in_x = x < xb;
+      const int i_end = min((g + 1) * rows_per_group, nrows);
+      for (int i = g * rows_per_group; i < i_end; ++i) {
+        const PasteRow pr = s_row[i];
+        const float4 t = *reinterpret_cast<const float4*>(tap0 + pr.base);
+        // same accumulation order as ATen's grid_sampler_2d (nw, ne, sw, se); border cells contribute exact zeros
+        float v = 0.f;
+        v += t.x * (wx0 * pr.wy0);
+        v += t.y * (wx1 * pr.wy0);
+        v += t.z * (wx0 * pr.wy1);
+        v += t.w * (wx1 * pr.wy1);
+        const uint32_t bits = __ballot_sync(0xffffffffu, in_x && v >= threshold);
+        if (lane == 0) s_bits[i * pitch + j + 1] = bits;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase W
+  s_bits_c = s_bits;
+  row_pass(true);
+}
+
 int grid_for(int64_t work, int block);
 
 }  // namespace cm2
@@ -514,6 +838,13 @@ static int roialign_launch(const cm2_act* feats, const int32_t* feat_stride, int
   p.out = make_view<T>(*out);
   p.level_out = level_out;
   int64_t total = (int64_t)n * r_cap * out->h * out->w * (out->c / 8);
+  const int variant = getenv("CM2_ROIALIGN_VARIANT") ? atoi(getenv("CM2_ROIALIGN_VARIANT")) : 1;
+  if (variant == 1 && p.res <= ROI_MAX_RES) {
+    const int items = p.res * p.res * (out->c / 8);
+    const int threads = std::min(256, std::max(64, (items + 31) / 32 * 32));
+    roialign_roi_kernel<T><<<n * r_cap, threads, 0, s>>>(p);
+    return 0;
+  }
   roialign_fpn_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(p);
   return 0;
 }
@@ -654,6 +985,26 @@ extern "C" int cm2_paste_masks(const float* probs, const float* boxes, const uin
   if (r == 0) return CM2_OK;
   CM2_CHECK_ARG(r <= 65535, "paste_masks: too many ROIs in one call (%d)", r);
   cudaStream_t s = (cudaStream_t)stream;
+  const int variant = getenv("CM2_PASTE_VARIANT") ? atoi(getenv("CM2_PASTE_VARIANT")) : 1;
+  const long long plane = (long long)out_h * out_w;
+  if (variant == 1 && plane % 16 == 0 && plane >= 16 && plane < (1ll << 27) && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    // slabs of about 48 image rows; shared memory: M4 table, row table, bit tile
+    const int nchunks = (int)(plane >> 4);
+    int slabs = std::max(1, std::min(ceil_div(out_h, 48), nchunks));
+    const int rows_cap = (ceil_div(nchunks, slabs) * 16) / out_w + 3;
+    const int pitch = ceil_div(out_w, 32) + 4;
+    const size_t smem = ((size_t)(m + 3) * (m + 3) + rows_cap) * 16 + (size_t)rows_cap * pitch * 4;
+    if (smem <= 200 * 1024) {
+      static size_t attr_smem = 0;
+      if (smem > attr_smem) {
+        cudaFuncSetAttribute(paste_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_smem = smem;
+      }
+      paste_fused_kernel<<<dim3(slabs, r), 256, smem, s>>>(probs, boxes, valid, out, m, out_h, out_w, threshold, rows_cap, pitch);
+      CM2_CHECK_LAUNCH("paste_masks_fused");
+      return CM2_OK;
+    }
+  }
   if (cudaMemsetAsync(out, 0, (size_t)r * out_h * out_w, s) != cudaSuccess) {
     set_error("paste_masks: cudaMemsetAsync failed");
     return CM2_ERR_CUDA;

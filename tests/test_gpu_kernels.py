@@ -18,6 +18,15 @@ from oracle import restate                             # noqa: E402
 DEV = "cuda"
 
 
+@pytest.fixture
+def kernel_variant(monkeypatch):
+    """Select the older implementation of a kernel family (CM2_<FAMILY>_VARIANT=0); the default (1) is the current one.
+    The library reads the variable on every call."""
+    def choose(family, variant):
+        monkeypatch.setenv("CM2_{}_VARIANT".format(family), str(variant))
+    return choose
+
+
 def halo(t_nchw, dtype=torch.float32):
     n, c, h, w = t_nchw.shape
     buf = torch.zeros((n, h + 2, w + 2, c), dtype=dtype, device=DEV)
@@ -158,7 +167,9 @@ def _random_boxes(g, n, w, h):
     return torch.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1)
 
 
-def test_roialign_fpn_matches_torchvision_and_reference_level_rule():
+@pytest.mark.parametrize("variant", [1, 0])                  # 1: CTA per ROI, merged taps; 0: thread per (bin, 8 channels)
+def test_roialign_fpn_matches_torchvision_and_reference_level_rule(variant, kernel_variant):
+    kernel_variant("ROIALIGN", variant)
     g = torch.Generator().manual_seed(7)
     n, r_cap, c = 2, 24, 32
     H, W = 96, 128
@@ -194,8 +205,10 @@ def test_roialign_fpn_matches_torchvision_and_reference_level_rule():
     assert got[r_cap + counts[1]:].abs().max() == 0                  # invalid slots are zeroed
 
 
+@pytest.mark.parametrize("variant", [1, 0])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_roialign_large_rois_separable_path(dtype):
+def test_roialign_large_rois_separable_path(dtype, variant, kernel_variant):
+    kernel_variant("ROIALIGN", variant)
     """Adaptive sampling grids of 2..20 samples per bin side: the separable (row / column weight) evaluation, boxes that
     stick out of the image, and bins wider than the register span (sample-loop fallback) against torchvision."""
     import torchvision
@@ -269,7 +282,8 @@ def test_spatial_attention_mask_predict_maskiou_glue():
     assert torch.allclose(ms.cpu(), sc * iou[torch.arange(r), cls], atol=1e-6)
 
 
-@pytest.mark.parametrize("out_h,out_w", [(96, 128), (75, 101), (76, 101), (40, 67)])      # word path (aligned / rows straddling words), byte path
+# fused path (plane % 16 == 0: aligned rows / odd width with chunks straddling rows), word path, byte path
+@pytest.mark.parametrize("out_h,out_w", [(96, 128), (80, 101), (75, 101), (76, 101), (40, 67)])
 def test_paste_masks_and_box_rescale(out_h, out_w):
     g = torch.Generator().manual_seed(9)
     r = 12
@@ -296,6 +310,39 @@ def test_paste_masks_and_box_rescale(out_h, out_w):
     assert masks.cpu()[~keep].sum() == 0
 
 
+@pytest.mark.parametrize("out_h,out_w", [(96, 128), (80, 101), (208, 333), (800, 1333)])
+def test_paste_fused_equals_memset_window_path(out_h, out_w, kernel_variant):
+    """The fused single-pass kernel (variant 1) writes every byte once and must equal the memset + window kernel
+    (variant 0) bit for bit: boxes touching every image edge, full-image, sub-pixel, one-strip and invalid boxes;
+    the output buffer is pre-filled with garbage."""
+    g = torch.Generator().manual_seed(out_h * 7 + out_w)
+    r = 24
+    probs = torch.rand(r, 28, 28, generator=g)
+    W, H = float(out_w), float(out_h)
+    boxes = _random_boxes(g, r, out_w, out_h)
+    boxes[0] = torch.tensor([0.0, 0.0, W, H])
+    boxes[1] = torch.tensor([0.0, H * 0.3, W * 0.2, H * 0.6])            # touches the left edge
+    boxes[2] = torch.tensor([W * 0.7, H * 0.1, W, H * 0.5])              # touches the right edge
+    boxes[3] = torch.tensor([0.0, 0.0, W, 3.5])                          # top rows, full width
+    boxes[4] = torch.tensor([0.0, H - 2.25, W, H])                       # bottom rows, full width
+    boxes[5] = torch.tensor([W * 0.5, H * 0.5, W * 0.5 + 0.4, H * 0.5 + 0.3])   # sub-pixel
+    boxes[6] = torch.tensor([3.0, 2.0, 9.5, H - 1.0])                    # narrow and tall (one strip)
+    boxes[7] = torch.tensor([W - 1.5, 0.0, W, H])                        # last column
+    boxes[8] = torch.tensor([0.0, 0.0, 1.0, H])                          # first column
+    valid = torch.ones(r, dtype=torch.uint8)
+    valid[9] = 0
+    outs = []
+    for variant in (1, 0):
+        kernel_variant("PASTE", variant)
+        masks = torch.full((r, out_h, out_w), 0xAB, dtype=torch.uint8, device=DEV)
+        lib.paste_masks(probs.to(DEV), boxes.to(DEV), valid.to(DEV), masks, r, 28, out_h, out_w, 0.5)
+        torch.cuda.synchronize()
+        outs.append(masks.cpu())
+    assert outs[0].max() <= 1
+    assert torch.equal(outs[0], outs[1]), (outs[0] != outs[1]).sum().item()
+    assert outs[0][9].sum() == 0 and outs[0][0].sum() > 0
+
+
 def _fcos_post_case(g, n, sizes, ncls, target, h0, w0):
     """Random head outputs with ~target candidates per (image, level)."""
     strides = [8, 16, 32, 64, 128][:len(sizes)]
@@ -311,8 +358,10 @@ def _fcos_post_case(g, n, sizes, ncls, target, h0, w0):
     return logits, regs, ctrs, strides
 
 
+@pytest.mark.parametrize("variant", [1, 0])                  # 1: flat 32 KB tiles; 0: one CTA per image row
 @pytest.mark.parametrize("target,post", [(150, 50), (1500, 100)])
-def test_fcos_postprocess_matches_oracle(target, post):
+def test_fcos_postprocess_matches_oracle(target, post, variant, kernel_variant):
+    kernel_variant("DECODE", variant)
     from centermask2_b200.config import get_cfg
     from centermask2_b200.engine import Engine
     g = torch.Generator().manual_seed(10 + target)

@@ -41,16 +41,32 @@ def norm_isf(p):
 
 
 def timed(fn, reps=10, warm=3):
+    """Device time per call: `reps` calls captured into one CUDA graph (what the engine replays in production), the
+    graph replayed 3 times between two events.  Host-side launch overhead (ctypes argument marshalling costs more than
+    some of these kernels run) is thereby kept out of the number."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    if os.environ.get("CM2_MICRO_EAGER") == "1":
+        graph, replays = None, 1
+    else:
+        graph, replays = torch.cuda.CUDAGraph(), 3
+        with torch.cuda.graph(graph):
+            for _ in range(reps):
+                fn()
+        graph.replay()
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps):
-        fn()
+    for _ in range(replays):
+        if graph is None:
+            for _ in range(reps):
+                fn()
+        else:
+            graph.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
+    return e0.elapsed_time(e1) / (reps * replays)
 
 
 def main():
@@ -59,6 +75,7 @@ def main():
     ap.add_argument("--cand", type=int, default=1000)
     ap.add_argument("--rois", type=int, default=100)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--old", action="store_true", help="also time the previous implementation of each kernel (CM2_*_VARIANT=0)")
     args = ap.parse_args()
     n, R = args.batch, args.rois
     dev = "cuda"
@@ -105,6 +122,10 @@ def main():
                                cap, cbuf)
     ms = timed(decode)
     report("fcos_decode (5 levels)", ms, n * 22400 * 85 * 4, "{:.0f} candidates / level / image".format(cand))
+    if args.old:
+        os.environ["CM2_DECODE_VARIANT"] = "0"
+        report("fcos_decode (5 levels) [v0: CTA per image row]", timed(decode), n * 22400 * 85 * 4)
+        os.environ["CM2_DECODE_VARIANT"] = "1"
 
     # ---- per-level top-k + class-aware NMS + post top-k (A12-A14): latency-bound
     ms_all = timed(lambda: eng.run_fcos_post(head))
@@ -126,9 +147,15 @@ def main():
     img_area = torch.full((n,), float(H * W), device=dev)
     roi = eng.fmap("mroi", n * R, 14, 14, c)
     lvl = torch.zeros((n * R,), dtype=torch.int32, device=dev)
-    ms = timed(lambda: lib.roialign_fpn([f.view for f in feats], [8, 16, 32], boxes, counts, n, R, img_area, 0, 0, roi.view, lvl))
+    def roialign():
+        lib.roialign_fpn([f.view for f in feats], [8, 16, 32], boxes, counts, n, R, img_area, 0, 0, roi.view, lvl)
+    ms = timed(roialign)
     hist = torch.bincount(lvl.long(), minlength=3).tolist()
     report("roialign_fpn (+ level assignment)", ms, n * (R * c * 196 * 2 + c * 22050 * 2), "ROIs per level {}".format(hist))
+    if args.old:
+        os.environ["CM2_ROIALIGN_VARIANT"] = "0"
+        report("roialign_fpn [v0: thread per (bin, 8 channels), sample loop]", timed(roialign), n * (R * c * 196 * 2 + c * 22050 * 2))
+        os.environ["CM2_ROIALIGN_VARIANT"] = "1"
 
     # ---- spatial attention (A18)
     att = eng.fmap("matt", n * R, 14, 14, c)
@@ -150,6 +177,10 @@ def main():
     ms = timed(paste, reps=3, warm=1)
     inbox = float(((bx[..., 2] - bx[..., 0]) * (bx[..., 3] - bx[..., 1])).mean().item()) / (H * 1333)
     report("paste_masks", ms, n * R * H * 1333 + n * R * 784 * 4, "mean box area {:.1%} of the image".format(inbox))
+    if args.old:
+        os.environ["CM2_PASTE_VARIANT"] = "0"
+        report("paste_masks [v0: memset + window kernel]", timed(paste, reps=3, warm=1), n * R * H * 1333 + n * R * 784 * 4)
+        os.environ["CM2_PASTE_VARIANT"] = "1"
     if args.out:
         with open(args.out, "w") as f:
             for r in results:
