@@ -690,12 +690,12 @@ __device__ __forceinline__ uint32_t spread4(uint32_t nib) {          // bits 0..
 __global__ void __launch_bounds__(256) paste_fused_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
                                                           const uint8_t* __restrict__ valid, uint8_t* __restrict__ out,
                                                           int m, int out_h, int out_w, float threshold, int rows_cap,
-                                                          int pitch) {
+                                                          int pitch, int chunks_per_slab) {
   extern __shared__ uint4 s_dyn4[];
   const int r = blockIdx.y, tid = threadIdx.x;
   const int nchunks = (out_h * out_w) >> 4;
-  const int cA = (int)((long long)nchunks * blockIdx.x / gridDim.x);
-  const int cB = (int)((long long)nchunks * (blockIdx.x + 1) / gridDim.x);
+  const int cA = blockIdx.x * chunks_per_slab;
+  const int cB = min(cA + chunks_per_slab, nchunks);
   if (cA >= cB) return;
   uint4* __restrict__ oplane = reinterpret_cast<uint4*>(out + (size_t)r * out_h * out_w);
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(256) paste_fused_kernel(const float* __restric
     xb = min((int)ceilf(b.z) + 1, out_w); yb = min((int)ceilf(b.w) + 1, out_h);
     if (xa >= xb || ya >= yb) xa = xb = ya = yb = 0;
   }
-  const int yA = (cA * 16) / out_w, yB = (cB * 16 - 1) / out_w;       // image rows this slab touches
+  const int yA = (int)((uint32_t)(cA * 16) / (uint32_t)out_w), yB = (int)((uint32_t)(cB * 16 - 1) / (uint32_t)out_w);   // image rows this slab touches
   const int r0 = max(ya, yA), r1 = min(yb, yB + 1);                   // window rows inside the slab: [r0, r1)
   if (r0 >= r1) {                                                     // common: nothing but zeros
     for (int c = cA + tid; c < cB; c += 256) oplane[c] = zero4;
@@ -755,11 +755,25 @@ __global__ void __launch_bounds__(256) paste_fused_kernel(const float* __restric
   float4* s_m4 = reinterpret_cast<float4*>(s_dyn4);
   PasteRow* s_row = reinterpret_cast<PasteRow*>(s_dyn4 + mq * mq);
   uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_dyn4 + mq * mq + rows_cap);
-  const float* pm = probs + (size_t)r * m * m;
-  for (int i = tid; i < mq * mq; i += 256) {
-    const int yl = i / mq - 2, xl = i - (yl + 2) * mq - 2;
-    auto P = [&](int yy, int xx) -> float { return (yy >= 0 && yy < m && xx >= 0 && xx < m) ? __ldg(pm + yy * m + xx) : 0.f; };
-    s_m4[i] = make_float4(P(yl, xl), P(yl, xl + 1), P(yl + 1, xl), P(yl + 1, xl + 1));
+  // the mask with a zero border of two cells goes to shared memory first (it lives in the not yet used bit tile), so
+  // that the gathered table is built without bounds tests
+  {
+    const float* pm = probs + (size_t)r * m * m;
+    float* s_pad = reinterpret_cast<float*>(s_bits);
+    const int mpd = m + 4;
+    for (int i = tid; i < mpd * mpd; i += 256) s_pad[i] = 0.f;
+    __syncthreads();
+    for (int i = tid; i < m * m; i += 256) {
+      const int yy = (int)((uint32_t)i / (uint32_t)m), xx = i - yy * m;
+      s_pad[(yy + 2) * mpd + xx + 2] = __ldg(pm + i);
+    }
+    __syncthreads();
+    for (int i = tid; i < mq * mq; i += 256) {
+      const int yi = (int)((uint32_t)i / (uint32_t)mq), xi = i - yi * mq;        // (yl + 2, xl + 2)
+      const float* q = s_pad + yi * mpd + xi;
+      s_m4[i] = make_float4(q[0], q[1], q[mpd], q[mpd + 1]);
+    }
+    __syncthreads();
   }
   const float bw = b.z - b.x, bh = b.w - b.y, fm = (float)m;
   const int nrows = r1 - r0;
@@ -790,20 +804,25 @@ __global__ void __launch_bounds__(256) paste_fused_kernel(const float* __restric
       const float fx = floorf(ix);
       const float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
       const int xl = (int)fminf(fmaxf(fx, -2.f), fm);
-      const char* tap0 = reinterpret_cast<const char*>(s_m4) + (xl + 2) * 16;
+      const uint32_t tap0 = (uint32_t)__cvta_generic_to_shared(s_m4) + (uint32_t)(xl + 2) * 16u;
       const bool in_x = x < xb;
-      const int i_end = min((g + 1) * rows_per_group, nrows);
-      for (int i = g * rows_per_group; i < i_end; ++i) {
-        const PasteRow pr = s_row[i];
-        const float4 t = *reinterpret_cast<const float4*>(tap0 + pr.base);
+      const int i_begin = g * rows_per_group, i_end = min((g + 1) * rows_per_group, nrows);
+      uint32_t row_addr = (uint32_t)__cvta_generic_to_shared(s_row + i_begin);
+      uint32_t bit_addr = (uint32_t)__cvta_generic_to_shared(s_bits + i_begin * pitch + j + 1);
+      const uint32_t bit_step = (uint32_t)pitch * 4u;
+      for (int i = i_begin; i < i_end; ++i, row_addr += 16u, bit_addr += bit_step) {
+        float wy0, wy1, t0, t1, t2, t3;
+        uint32_t base, pad;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(wy0), "=f"(wy1), "=r"(base), "=r"(pad) : "r"(row_addr) : "memory");
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t0), "=f"(t1), "=f"(t2), "=f"(t3) : "r"(tap0 + base) : "memory");
         // same accumulation order as ATen's grid_sampler_2d (nw, ne, sw, se); border cells contribute exact zeros
         float v = 0.f;
-        v += t.x * (wx0 * pr.wy0);
-        v += t.y * (wx1 * pr.wy0);
-        v += t.z * (wx0 * pr.wy1);
-        v += t.w * (wx1 * pr.wy1);
+        v += t0 * (wx0 * wy0);
+        v += t1 * (wx1 * wy0);
+        v += t2 * (wx0 * wy1);
+        v += t3 * (wx1 * wy1);
         const uint32_t bits = __ballot_sync(0xffffffffu, in_x && v >= threshold);
-        if (lane == 0) s_bits[i * pitch + j + 1] = bits;
+        if (lane == 0) asm volatile("st.shared.b32 [%0], %1;" :: "r"(bit_addr), "r"(bits) : "memory");
       }
     }
   }
@@ -991,16 +1010,20 @@ extern "C" int cm2_paste_masks(const float* probs, const float* boxes, const uin
     // slabs of about 48 image rows; shared memory: M4 table, row table, bit tile
     const int nchunks = (int)(plane >> 4);
     int slabs = std::max(1, std::min(ceil_div(out_h, 48), nchunks));
-    const int rows_cap = (ceil_div(nchunks, slabs) * 16) / out_w + 3;
+    const int chunks_per_slab = ceil_div(nchunks, slabs);
+    slabs = ceil_div(nchunks, chunks_per_slab);
+    const int rows_cap = (chunks_per_slab * 16) / out_w + 3;
     const int pitch = ceil_div(out_w, 32) + 4;
-    const size_t smem = ((size_t)(m + 3) * (m + 3) + rows_cap) * 16 + (size_t)rows_cap * pitch * 4;
+    const size_t tile_bytes = std::max((size_t)rows_cap * pitch * 4, (size_t)(m + 4) * (m + 4) * 4);
+    const size_t smem = ((size_t)(m + 3) * (m + 3) + rows_cap) * 16 + tile_bytes;
     if (smem <= 200 * 1024) {
       static size_t attr_smem = 0;
       if (smem > attr_smem) {
         cudaFuncSetAttribute(paste_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_smem = smem;
       }
-      paste_fused_kernel<<<dim3(slabs, r), 256, smem, s>>>(probs, boxes, valid, out, m, out_h, out_w, threshold, rows_cap, pitch);
+      paste_fused_kernel<<<dim3(slabs, r), 256, smem, s>>>(probs, boxes, valid, out, m, out_h, out_w, threshold, rows_cap, pitch,
+                                                           chunks_per_slab);
       CM2_CHECK_LAUNCH("paste_masks_fused");
       return CM2_OK;
     }
