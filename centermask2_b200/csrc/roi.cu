@@ -241,8 +241,9 @@ __global__ void __launch_bounds__(256, 3) roialign_roi_kernel(const RoiAlignPara
   const uint32_t magic_c8 = (uint32_t)((0x100000000ull + c8 - 1) / (uint32_t)c8);
   const uint32_t magic_res = (uint32_t)((0x100000000ull + res - 1) / (uint32_t)res);
   const float inv_count = 1.0f / count;
-  const int sw = (int)f.sw;
-  constexpr int RY = 1;             // tap rows in flight together (register budget)
+  // 32-bit element offsets inside the image (the host checks sn < 2^31): one IMAD.WIDE per load address
+  const T* img_base = f.p + (size_t)img * f.sn;
+  const int sh32 = (int)f.sh, sw32 = (int)f.sw;
   for (int i = threadIdx.x; i < items; i += blockDim.x) {
     const int bin = c8 == 32 ? (i >> 5) : (c8 == 1 ? i : (int)__umulhi((uint32_t)i, magic_c8)), cv = i - bin * c8;
     const int ph = res == 1 ? bin : (int)__umulhi((uint32_t)bin, magic_res), pw = bin - ph * res;
@@ -251,20 +252,27 @@ __global__ void __launch_bounds__(256, 3) roialign_roi_kernel(const RoiAlignPara
       const int ny = s_num[0][ph], nx = s_num[1][pw];
       const float* wy = s_w[0][ph];
       const float* wx = s_w[1][pw];
-      const T* base = f.at(img, s_start[0][ph], s_start[1][pw]) + cv * 8;
-      for (int jy = 0; jy < ny; jy += RY) {
-        for (int jx0 = 0; jx0 < nx; jx0 += 4) {
-          Raw8<T> rv[RY][4];
-#pragma unroll
-          for (int a = 0; a < RY; ++a)
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (jy + a < ny && jx0 + u < nx) rv[a][u].load(base + (size_t)(jy + a) * f.sh + (jx0 + u) * sw);
-#pragma unroll
-          for (int a = 0; a < RY; ++a)
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (jy + a < ny && jx0 + u < nx) rv[a][u].fma(wy[jy + a] * wx[jx0 + u], acc);
+      int off0 = s_start[0][ph] * sh32 + s_start[1][pw] * sw32 + cv * 8;
+      for (int jy = 0; jy < ny; ++jy, off0 += sh32) {
+        const float wyv = wy[jy];
+        int off = off0, jx = 0;
+        for (; jx + 4 <= nx; jx += 4, off += 4 * sw32) {
+          Raw8<T> r0, r1, r2, r3;
+          r0.load(img_base + off); r1.load(img_base + off + sw32);
+          r2.load(img_base + off + 2 * sw32); r3.load(img_base + off + 3 * sw32);
+          r0.fma(wyv * wx[jx], acc); r1.fma(wyv * wx[jx + 1], acc);
+          r2.fma(wyv * wx[jx + 2], acc); r3.fma(wyv * wx[jx + 3], acc);
+        }
+        if (nx - jx >= 2) {
+          Raw8<T> r0, r1;
+          r0.load(img_base + off); r1.load(img_base + off + sw32);
+          r0.fma(wyv * wx[jx], acc); r1.fma(wyv * wx[jx + 1], acc);
+          jx += 2; off += 2 * sw32;
+        }
+        if (nx - jx >= 1) {
+          Raw8<T> r0;
+          r0.load(img_base + off);
+          r0.fma(wyv * wx[jx], acc);
         }
       }
     } else {
@@ -858,7 +866,9 @@ static int roialign_launch(const cm2_act* feats, const int32_t* feat_stride, int
   p.level_out = level_out;
   int64_t total = (int64_t)n * r_cap * out->h * out->w * (out->c / 8);
   const int variant = getenv("CM2_ROIALIGN_VARIANT") ? atoi(getenv("CM2_ROIALIGN_VARIANT")) : 1;
-  if (variant == 1 && p.res <= ROI_MAX_RES) {
+  bool small = true;
+  for (int l = 0; l < num_levels; ++l) small = small && feats[l].sn < (1ll << 31);
+  if (variant == 1 && p.res <= ROI_MAX_RES && small) {
     const int items = p.res * p.res * (out->c / 8);
     const int threads = std::min(256, std::max(64, (items + 31) / 32 * 32));
     roialign_roi_kernel<T><<<n * r_cap, threads, 0, s>>>(p);
