@@ -427,6 +427,110 @@ __global__ void __launch_bounds__(512) spatial_attention_smem_kernel(View<const 
   }
 }
 
+// Persistent, double-buffered variant: one CTA per SM walks over the ROIs; the [S, S, C] tile of the NEXT ROI is
+// fetched by the copy engine (cp.async.bulk, one contiguous S * C run per tile row, completion on an mbarrier) into the
+// other shared-memory buffer while the current tile is pooled, convolved, scaled and stored -- the load latency that
+// the CTA-per-ROI kernel pays three times per SM residency slot disappears behind the store phase.
+__device__ __forceinline__ void sam_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins > (1u << 26)) { printf("spatial_attention_pipe: mbarrier wait timed out (block %d)\n", blockIdx.x); __trap(); }
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1) spatial_attention_pipe_kernel(View<const __nv_bfloat16> x, View<__nv_bfloat16> out,
+                                                                         const float* __restrict__ w18) {
+  extern __shared__ uint4 s_x[];                        // [2][S*S*c8] tiles, then avg / max / att maps
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  __shared__ float s_w[18];
+  const int S = x.h, C = x.c, c8 = C >> 3, npix = S * S;
+  const int tile_vecs = npix * c8;
+  float* s_avg = reinterpret_cast<float*>(s_x + 2 * tile_vecs);
+  float* s_max = s_avg + npix;
+  float* s_att = s_max + npix;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const uint32_t row_bytes = (uint32_t)S * C * 2;
+  if (threadIdx.x < 18) s_w[threadIdx.x] = w18[threadIdx.x];
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_bar[b])), "r"(1u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int r, int buf) {                    // one thread
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[buf]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic reads of the buffer precede the async writes
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (uint32_t)S) : "memory");
+    const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(s_x + (size_t)buf * tile_vecs);
+    for (int y = 0; y < S; ++y)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"(dst0 + (uint32_t)y * row_bytes), "l"(x.at(r, y, 0)), "r"(row_bytes), "r"(bar) : "memory");
+  };
+  const int nroi = x.n;
+  if (threadIdx.x == 0 && (int)blockIdx.x < nroi) issue(blockIdx.x, 0);
+  int k = 0;
+  for (int r = blockIdx.x; r < nroi; r += gridDim.x, ++k) {
+    const int buf = k & 1;
+    if (threadIdx.x == 0 && r + (int)gridDim.x < nroi) issue(r + gridDim.x, buf ^ 1);
+    sam_mbar_wait((uint32_t)__cvta_generic_to_shared(&s_bar[buf]), (uint32_t)(k >> 1) & 1u);
+    const uint4* tile = s_x + (size_t)buf * tile_vecs;
+    // phase 1: channel mean / max per pixel (warp per pixel)
+    for (int pix = warp; pix < npix; pix += nwarps) {
+      float sum = 0.f, mx = -INFINITY;
+      for (int cv = lane; cv < c8; cv += 32) {
+        const uint4 q = tile[pix * c8 + cv];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
+          sum += lo; sum += hi;
+          mx = fmaxf(mx, fmaxf(lo, hi));
+        }
+      }
+      sum = warp_sum(sum);
+      mx = warp_max(mx);
+      if (lane == 0) { s_avg[pix] = sum / (float)C; s_max[pix] = mx; }
+    }
+    __syncthreads();
+    // phase 2: 3x3 conv over (avg, max) + sigmoid
+    for (int pix = threadIdx.x; pix < npix; pix += blockDim.x) {
+      const int y = pix / S, xx = pix - y * S;
+      float acc = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int iy = y + ky - 1, ix = xx + kx - 1;
+          if (iy >= 0 && iy < S && ix >= 0 && ix < S) {
+            acc = fmaf(s_w[ky * 3 + kx], s_avg[iy * S + ix], acc);
+            acc = fmaf(s_w[9 + ky * 3 + kx], s_max[iy * S + ix], acc);
+          }
+        }
+      s_att[pix] = sigmoid_f32(acc);
+    }
+    __syncthreads();
+    // phase 3: scale and store
+    for (int i = threadIdx.x; i < tile_vecs; i += blockDim.x) {
+      const int pix = i / c8, cv = i - pix * c8;
+      const int y = pix / S, xx = pix - y * S;
+      const uint4 q = tile[i];
+      const float a = s_att[pix];
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(w[j] << 16) * a, __uint_as_float(w[j] & 0xffff0000u) * a);
+        o[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(out.at(r, y, xx) + cv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();                                    // the tile and the maps are free again
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // predictor restricted to the predicted class + sigmoid (sam.py:97, mask_head.py:196-216).
 // warp per output pixel; lanes stride over channels.
@@ -919,6 +1023,24 @@ extern "C" int cm2_spatial_attention(const cm2_act* x, const cm2_act* out, int32
   if (x->n == 0) return CM2_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t tile_bytes = (size_t)x->h * x->w * x->c * 2;
+  const int sam_variant = getenv("CM2_SAM_VARIANT") ? atoi(getenv("CM2_SAM_VARIANT")) : 1;
+  const size_t pipe_smem = 2 * tile_bytes + (size_t)3 * x->h * x->w * sizeof(float);
+  if (sam_variant == 1 && dtype == CM2_BF16 && pipe_smem <= 220 * 1024 && x->sw == x->c && x->n >= 2 * 148 &&
+      ((size_t)x->w * x->c * 2) % 16 == 0) {
+    // persistent double-buffered kernel: worth it once every SM gets at least two ROIs
+    static bool pipe_attr_done = false;
+    if (!pipe_attr_done) {
+      cudaFuncSetAttribute(spatial_attention_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      pipe_attr_done = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    spatial_attention_pipe_kernel<<<std::min(sms, x->n), 1024, pipe_smem, s>>>(make_view<const __nv_bfloat16>(*x),
+                                                                               make_view<__nv_bfloat16>(*out), w18);
+    CM2_CHECK_LAUNCH("spatial_attention_pipe");
+    return CM2_OK;
+  }
   if (dtype == CM2_BF16 && tile_bytes <= 110 * 1024) {     // two CTAs per SM
     static bool attr_done = false;
     if (!attr_done) {

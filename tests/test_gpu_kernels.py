@@ -282,6 +282,29 @@ def test_spatial_attention_mask_predict_maskiou_glue():
     assert torch.allclose(ms.cpu(), sc * iou[torch.arange(r), cls], atol=1e-6)
 
 
+@pytest.mark.parametrize("c", [256, 64])
+def test_spatial_attention_bf16_pipelined_equals_cta_per_roi(c, kernel_variant):
+    """>= 296 ROIs select the persistent double-buffered kernel (bulk copies + mbarriers); it must equal the CTA-per-ROI
+    kernel bit for bit (same reduction order) and torch within bf16 rounding (rtol 1e-2)."""
+    g = torch.Generator().manual_seed(21 + c)
+    r = 333
+    x = torch.randn(r, c, 14, 14, generator=g).to(torch.bfloat16).float()
+    w = torch.randn(1, 2, 3, 3, generator=g) * 0.5
+    att = torch.sigmoid(F.conv2d(torch.cat([x.mean(1, keepdim=True), x.max(1, keepdim=True)[0]], 1), w, None, 1, 1))
+    xin = halo(x, torch.bfloat16)
+    outs = []
+    for variant in (1, 0):
+        kernel_variant("SAM", variant)
+        out = halo(torch.zeros_like(x), torch.bfloat16)
+        lib.spatial_attention(xin.view, out.view, w.reshape(18).to(DEV))
+        torch.cuda.synchronize()
+        outs.append(out.buf.clone())
+    assert torch.equal(outs[0], outs[1])
+    got = outs[0][:, 1:-1, 1:-1].permute(0, 3, 1, 2).float().cpu()
+    assert torch.allclose(got, x * att, rtol=1e-2, atol=1e-2)
+    assert outs[0][:, 0].abs().max() == 0 and outs[0][:, :, 0].abs().max() == 0        # halo untouched
+
+
 # fused path (plane % 16 == 0: aligned rows / odd width with chunks straddling rows), word path, byte path
 @pytest.mark.parametrize("out_h,out_w", [(96, 128), (80, 101), (75, 101), (76, 101), (40, 67)])
 def test_paste_masks_and_box_rescale(out_h, out_w):
