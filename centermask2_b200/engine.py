@@ -151,6 +151,16 @@ class Engine(object):
             self._bufs[key] = t
         return t
 
+    _stage_free = None                                  # event: the staging input buffers have been consumed
+
+    def copy_stream(self):
+        """Side stream for host->device input copies that overlap the previous batch (GeneralizedRCNN.inference_stream)."""
+        st = self._bufs.get(("copy_stream",))
+        if st is None:
+            st = torch.cuda.Stream(device=self.device)
+            self._bufs[("copy_stream",)] = st
+        return st
+
     def pinned(self, name, shape, dtype):
         """Page-locked host staging buffer (async D2H of the small result-size tensors)."""
         key = ("pinned", name, tuple(shape), dtype)

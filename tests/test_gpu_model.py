@@ -79,6 +79,30 @@ def test_postprocessed_match_reference(case):
             assert_masks_match(g["pred_masks"], ref_masks, what="{}[{}]".format(name, i))
 
 
+def test_inference_stream_equals_forward_per_batch(case):
+    """The pipelined API (next batch's host->device copy overlapped on a copy stream) returns exactly what
+    ``forward`` returns batch by batch, in order, for batches with different pixels."""
+    name, gold, cfg, sd, inputs, model = case
+    batches = []
+    for k in range(3):
+        batch = []
+        for b in inputs:
+            img = b["image"].roll(shifts=7 * k, dims=-1).contiguous().pin_memory()
+            batch.append(dict(b, image=img))
+        batches.append(batch)
+    want = []
+    for batch in batches:
+        want.append([fields(o["instances"]) for o in model(batch)])
+    got = [[fields(o["instances"]) for o in out] for out in model.inference_stream(iter(batches))]
+    assert len(got) == len(want) == 3
+    for gb, wb in zip(got, want):
+        assert len(gb) == len(wb)
+        for g, w in zip(gb, wb):
+            assert set(g) == set(w)
+            for k in g:
+                assert torch.equal(g[k], w[k]), k
+
+
 def test_registry_level_modules_compose_like_the_reference(case):
     """backbone -> FCOS.forward -> CenterROIHeads.forward through the public module API (the sequence of
     modified_class.py:27-40), on arbitrary (non-engine) NCHW feature tensors."""

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--graph", type=int, default=0)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--e2e", action="store_true", help="trace GeneralizedRCNN.inference_stream (host images in, records out) instead")
     args = ap.parse_args()
     import centermask2_b200 as cm
     from centermask2_b200.synth import synthetic_state_dict
@@ -37,13 +38,23 @@ def main():
     bench.calibrate_on_gpu(model, cfg, host_inputs)
     dev_images = [b["image"].cuda() for b in host_inputs]
     step = bench.make_device_step(model, cfg, dev_images, (bench.H, bench.W), graph=bool(args.graph))
+    r_cap = cfg.MODEL.FCOS.POST_NMS_TOPK_TEST
+
+    def stream(k):
+        for out in model.inference_stream(host_inputs for _ in range(k)):
+            bench.compact_results(out, r_cap).cpu()
     for _ in range(3):
         step()
+    if args.e2e:
+        stream(4)
     torch.cuda.synchronize()
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-        for _ in range(args.steps):
-            step()
+        if args.e2e:
+            stream(args.steps)
+        else:
+            for _ in range(args.steps):
+                step()
         torch.cuda.synchronize()
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     agg = collections.defaultdict(lambda: [0, 0.0])
