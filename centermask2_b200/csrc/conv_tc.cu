@@ -81,6 +81,7 @@ struct alignas(64) TcParams {
   int epi_sets;             // column sets of epilogue warps per 128-row accumulator (1, 2 or 4)
   int fast_store;           // 1: epilogue transposes through shared memory and writes 64-byte row segments
   int dbg;                  // tuning experiments (CM2_TC_DEBUG): 1 no epilogue stores, 2 no TMA loads, 4 no MMAs, 8 no epilogue body
+  int pair;                 // v2 only: 1 = launched as CTA pairs, cta_group::2 MMAs (see conv_tc2_kernel<.., true>)
   int variant;              // host only: 1 = conv_tc_kernel (128-row tiles), 2 = conv_tc2_kernel
   unsigned smem_bytes;      // host only: dynamic shared memory of the launch
 };
@@ -196,6 +197,55 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
       "}\n"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// ---- cta_group::2 (CTA pair) forms.  Shared-memory addresses of a cluster launch carry the CTA rank in bit 24;
+// clearing it addresses the same offset in the even (leader) CTA of the pair.
+constexpr uint32_t TC_PEER_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA box into THIS CTA's shared memory, transaction bytes credited to the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & TC_PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive on the same barrier of both CTAs of the pair when the MMAs issued so far have completed
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & TC_PEER_MASK) : "memory");
+}
+// D[256 x N] += A[256 x 16] * B[N x 16]^T over the CTA pair: rows 0-127 / A and B[0, N/2) from the leader's shared
+// memory, rows 128-255 / B[N/2, N) from the peer's (same offsets); each CTA's TMEM holds its 128 rows
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool PAIR> __device__ __forceinline__ void tc_mma_x(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (PAIR) tc_mma_bf16_pair(d, a, b, idesc, acc); else tc_mma_bf16(d, a, b, idesc, acc);
+}
+template <bool PAIR> __device__ __forceinline__ void tc_commit_x(uint32_t bar) {
+  if (PAIR) tc_commit_pair(bar); else tc_commit(bar);
+}
+template <bool PAIR> __device__ __forceinline__ void tma_load_2d_x(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  if (PAIR) tma_load_2d_pair(dst, map, bar, c0, c1); else tma_load_2d(dst, map, bar, c0, c1);
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -913,13 +963,23 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_at(uint32_t smem_addr, int d
   return d;
 }
 
-template <int MAXT>
+// PAIR = true: the kernel is launched in clusters of two CTAs (one TPC) and every MMA is a cta_group::2 instruction of
+// M = 256: the pair works on 512 consecutive GEMM rows (256 per CTA, as above), each CTA loads its own A slab and HALF
+// of every weight tile (N/2 rows), and the leader CTA's MMA warp issues for both.  Per MMA a CTA then reads 4 KB of A
+// and N/2 x 32 B of W from its shared memory instead of 4 KB + N x 32 B -- for N = 128 that is 96 instead of 128 bytes
+// per clock, the shared-memory bandwidth that bounds the single-CTA kernel on N <= 128 layers -- and the L2 -> shared
+// weight traffic halves as well.  Barrier protocol: `full` barriers live in the leader (both CTAs' TMA loads credit
+// their bytes there), `empty` / `tmem full` barriers are signalled in both CTAs by multicast commits, the epilogue
+// warps of both CTAs arrive on the leader's `tmem empty` barrier.
+template <int MAXT, bool PAIR>
 __global__ void __launch_bounds__(MAXT, 1) conv_tc2_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_half_bytes = (uint32_t)p.a_box_rows * 128u;
   const uint32_t a_slab_bytes = 2u * a_half_bytes;
-  const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 2;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  constexpr int NCTA = PAIR ? 2 : 1;
+  const uint32_t b_bytes = (uint32_t)(p.bn / NCTA) * TC_BK * 2;      // weight rows held by THIS CTA
   const uint32_t b_base = base + (uint32_t)p.sa_stages * a_slab_bytes;
   const uint32_t bar_base = b_base + (uint32_t)p.sb_stages * b_bytes;
   auto afull_bar = [&](int s) { return bar_base + 8u * s; };
@@ -935,7 +995,11 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc2_kernel(const __grid_constant
   const uint32_t ss_base = epi_base + (uint32_t)n_epi_warps * EPI_WARP_BYTES;         // EPI_SS_BYTES of scale/shift
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // tiles are walked per CTA (256 rows) or per pair (512 rows, 256 per CTA)
+  const int total_tiles = PAIR ? ((p.m_tiles + 1) >> 1) * p.n_tiles : p.m_tiles * p.n_tiles;
+  const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tile_rows = PAIR ? 512 : 256, row_off = rank * 256;
   const int groups_per_tap_row = p.kx_merge ? 3 : 1;          // W tiles consumed per A slab
   const int ngroup_outer = p.kx_merge ? 3 : p.taps;            // ky (merged) or tap
 
@@ -944,15 +1008,20 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc2_kernel(const __grid_constant
     tma_prefetch_desc(&p.b_map);
     for (int s = 0; s < p.sa_stages; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
     for (int s = 0; s < p.sb_stages; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (uint32_t)n_epi_warps); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (uint32_t)(n_epi_warps * NCTA)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
@@ -977,8 +1046,8 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc2_kernel(const __grid_constant
           __syncwarp();
         }
       }
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int m0 = (t / p.n_tiles) * 256, n0 = (t % p.n_tiles) * p.bn;
+      for (int t = tile_first; t < total_tiles; t += tile_step) {
+        const int m0 = (t / p.n_tiles) * tile_rows + row_off, n0 = (t % p.n_tiles) * p.bn;
         for (int g = 0; g < ngroup_outer; ++g) {
           // first row of the slab in the flat source matrix
           const int pitch = p.num_seg ? tc_geom(p, m0).pitch : p.pitch;
@@ -991,11 +1060,11 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc2_kernel(const __grid_constant
               const uint32_t slab = base + (uint32_t)sa * a_slab_bytes;
               if (elect_one_sync()) {
                 if (p.dbg & 2) {
-                  mbar_arrive(afull_bar(sa));
+                  if (rank == 0) mbar_arrive(afull_bar(sa));
                 } else {
-                  mbar_expect_tx(afull_bar(sa), a_slab_bytes);
-                  tma_load_2d(slab, &p.a_map[s], afull_bar(sa), cb * TC_BK, row0);
-                  tma_load_2d(slab + a_half_bytes, &p.a_map[s], afull_bar(sa), cb * TC_BK, row0 + p.a_box_rows);
+                  if (rank == 0) mbar_expect_tx(afull_bar(sa), a_slab_bytes * NCTA);
+                  tma_load_2d_x<PAIR>(slab, &p.a_map[s], afull_bar(sa), cb * TC_BK, row0);
+                  tma_load_2d_x<PAIR>(slab + a_half_bytes, &p.a_map[s], afull_bar(sa), cb * TC_BK, row0 + p.a_box_rows);
                 }
               }
               __syncwarp();
@@ -1005,10 +1074,11 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc2_kernel(const __grid_constant
                 mbar_wait_ctl(p.spin, bempty_bar(sb), pb ^ 1u);
                 if (elect_one_sync()) {
                   if (p.dbg & 2) {
-                    mbar_arrive(bfull_bar(sb));
+                    if (rank == 0) mbar_arrive(bfull_bar(sb));
                   } else {
-                    mbar_expect_tx(bfull_bar(sb), b_bytes);
-                    tma_load_2d(b_base + (uint32_t)sb * b_bytes, &p.b_map, bfull_bar(sb), (tap * p.nblk_total + blk) * TC_BK, n0);
+                    if (rank == 0) mbar_expect_tx(bfull_bar(sb), b_bytes * NCTA);
+                    tma_load_2d_x<PAIR>(b_base + (uint32_t)sb * b_bytes, &p.b_map, bfull_bar(sb), (tap * p.nblk_total + blk) * TC_BK,
+                                        n0 + rank * (p.bn / NCTA));
                   }
                 }
                 __syncwarp();
@@ -1021,11 +1091,11 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc2_kernel(const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    {
+    if (rank == 0) {
       // The issue loop is the critical path of short-N layers (ncu: the producer waits for THIS warp, which never waits
       // itself): every parameter it needs is copied to a local first, descriptors are advanced incrementally, a full
       // 64-channel block takes the branch-free 8-MMA path, and a whole slab is issued under a single elect.
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)((TC_BM * NCTA) >> 4) << 24);
       const int kx_merge = p.kx_merge, b_res = p.b_resident, nblk_total = p.nblk_total, n_acc = p.acc_stages;
       const int n_sa = p.sa_stages, n_sb = p.sb_stages, num_src = p.num_src, spin = p.spin;
       const bool no_mma = (p.dbg & 4) != 0;
@@ -1038,7 +1108,7 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc2_kernel(const __grid_constant
         for (int i = 0; i < n_sb; ++i) mbar_wait_ctl(spin, bfull_bar(i), 0u);
         tc_fence_after();
       }
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = tile_first; t < total_tiles; t += tile_step) {
         mbar_wait_ctl(spin, tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * half_cols);
@@ -1064,22 +1134,22 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc2_kernel(const __grid_constant
                     const uint64_t adesc0 = adesc_slab + (uint64_t)(kx_merge ? 8 * j : 0), adesc1 = adesc0 + adesc_half;
                     if (!no_mma) {
                       if (nk == 4) {
-                        tc_mma_bf16(d0, adesc0, bdesc, idesc, accumulate);
-                        tc_mma_bf16(d0, adesc0 + 2, bdesc + 2, idesc, 1u);
-                        tc_mma_bf16(d0, adesc0 + 4, bdesc + 4, idesc, 1u);
-                        tc_mma_bf16(d0, adesc0 + 6, bdesc + 6, idesc, 1u);
-                        tc_mma_bf16(d1, adesc1, bdesc, idesc, accumulate);
-                        tc_mma_bf16(d1, adesc1 + 2, bdesc + 2, idesc, 1u);
-                        tc_mma_bf16(d1, adesc1 + 4, bdesc + 4, idesc, 1u);
-                        tc_mma_bf16(d1, adesc1 + 6, bdesc + 6, idesc, 1u);
+                        tc_mma_x<PAIR>(d0, adesc0, bdesc, idesc, accumulate);
+                        tc_mma_x<PAIR>(d0, adesc0 + 2, bdesc + 2, idesc, 1u);
+                        tc_mma_x<PAIR>(d0, adesc0 + 4, bdesc + 4, idesc, 1u);
+                        tc_mma_x<PAIR>(d0, adesc0 + 6, bdesc + 6, idesc, 1u);
+                        tc_mma_x<PAIR>(d1, adesc1, bdesc, idesc, accumulate);
+                        tc_mma_x<PAIR>(d1, adesc1 + 2, bdesc + 2, idesc, 1u);
+                        tc_mma_x<PAIR>(d1, adesc1 + 4, bdesc + 4, idesc, 1u);
+                        tc_mma_x<PAIR>(d1, adesc1 + 6, bdesc + 6, idesc, 1u);
                       } else {
-                        for (int k = 0; k < nk; ++k) tc_mma_bf16(d0, adesc0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
-                        for (int k = 0; k < nk; ++k) tc_mma_bf16(d1, adesc1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
+                        for (int k = 0; k < nk; ++k) tc_mma_x<PAIR>(d0, adesc0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
+                        for (int k = 0; k < nk; ++k) tc_mma_x<PAIR>(d1, adesc1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
                       }
                     }
                     accumulate = 1;
                   }
-                  tc_commit(aempty_bar(sa));
+                  tc_commit_x<PAIR>(aempty_bar(sa));
                 }
                 __syncwarp();
                 accumulate = 1;
@@ -1094,21 +1164,21 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc2_kernel(const __grid_constant
                   if (elect_one_sync()) {
                     if (!no_mma) {
                       if (nk == 4) {
-                        tc_mma_bf16(d0, adesc0, bdesc, idesc, accumulate);
-                        tc_mma_bf16(d0, adesc0 + 2, bdesc + 2, idesc, 1u);
-                        tc_mma_bf16(d0, adesc0 + 4, bdesc + 4, idesc, 1u);
-                        tc_mma_bf16(d0, adesc0 + 6, bdesc + 6, idesc, 1u);
-                        tc_mma_bf16(d1, adesc1, bdesc, idesc, accumulate);
-                        tc_mma_bf16(d1, adesc1 + 2, bdesc + 2, idesc, 1u);
-                        tc_mma_bf16(d1, adesc1 + 4, bdesc + 4, idesc, 1u);
-                        tc_mma_bf16(d1, adesc1 + 6, bdesc + 6, idesc, 1u);
+                        tc_mma_x<PAIR>(d0, adesc0, bdesc, idesc, accumulate);
+                        tc_mma_x<PAIR>(d0, adesc0 + 2, bdesc + 2, idesc, 1u);
+                        tc_mma_x<PAIR>(d0, adesc0 + 4, bdesc + 4, idesc, 1u);
+                        tc_mma_x<PAIR>(d0, adesc0 + 6, bdesc + 6, idesc, 1u);
+                        tc_mma_x<PAIR>(d1, adesc1, bdesc, idesc, accumulate);
+                        tc_mma_x<PAIR>(d1, adesc1 + 2, bdesc + 2, idesc, 1u);
+                        tc_mma_x<PAIR>(d1, adesc1 + 4, bdesc + 4, idesc, 1u);
+                        tc_mma_x<PAIR>(d1, adesc1 + 6, bdesc + 6, idesc, 1u);
                       } else {
-                        for (int k = 0; k < nk; ++k) tc_mma_bf16(d0, adesc0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
-                        for (int k = 0; k < nk; ++k) tc_mma_bf16(d1, adesc1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
+                        for (int k = 0; k < nk; ++k) tc_mma_x<PAIR>(d0, adesc0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
+                        for (int k = 0; k < nk; ++k) tc_mma_x<PAIR>(d1, adesc1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
                       }
                     }
-                    tc_commit(bempty_bar(sb));
-                    if (j + 1 == groups_per_tap_row) tc_commit(aempty_bar(sa));
+                    tc_commit_x<PAIR>(bempty_bar(sb));
+                    if (j + 1 == groups_per_tap_row) tc_commit_x<PAIR>(aempty_bar(sa));
                   }
                   __syncwarp();
                   accumulate = 1;
@@ -1119,7 +1189,7 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc2_kernel(const __grid_constant
             }
           }
         }
-        if (elect_one_sync()) tc_commit(tfull_bar(acc));
+        if (elect_one_sync()) tc_commit_x<PAIR>(tfull_bar(acc));
         __syncwarp();
         if (++acc == n_acc) { acc = 0; acc_phase ^= 1u; }
       }
@@ -1132,10 +1202,10 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc2_kernel(const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t parity = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, parity ^= 1u) {
-      const int m0 = (t / p.n_tiles) * 256, n0 = (t % p.n_tiles) * p.bn;
+    for (int t = tile_first; t < total_tiles; t += tile_step, parity ^= 1u) {
+      const int m0 = (t / p.n_tiles) * tile_rows + row_off, n0 = (t % p.n_tiles) * p.bn;
       const uint32_t ss = ss_base + (p.n_tiles == 1 ? 0u : parity * 2048u);
-      if (p.n_tiles > 1 || t == (int)blockIdx.x)
+      if (p.n_tiles > 1 || t == tile_first)
         tc_stage_scale_shift(p, ss, n0, (int)threadIdx.x - 64, 32 * n_epi_warps, m0);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -1149,16 +1219,17 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc2_kernel(const __grid_constant
         tc_epilogue_rows(p, tg, taddr, m0 + half * 128 + q * 32 + lane, n0, ss);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
       if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();    // the peer may still read this CTA's shared memory / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -1385,6 +1456,9 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
       size_t st = (smem_max - tail_v2) / (a_slab + b_bytes);
       p->sa_stages = p->sb_stages = (int)(st > 6 ? 6 : st);
     }
+    // CTA pairs (cta_group::2): streamed weights only, N a multiple of 32 (each CTA holds N/2 rows, N/2 % 16 == 0)
+    static const int env_pair = getenv("CM2_TC_PAIR") ? atoi(getenv("CM2_TC_PAIR")) : 0;
+    p->pair = (env_pair && !p->b_resident && p->bn % 32 == 0 && p->bn >= 32) ? 1 : 0;
     p->smem_bytes = (unsigned)(1024 + p->sa_stages * a_slab + p->sb_stages * b_bytes + tail2);
   } else {
     p->variant = 1;
@@ -1455,7 +1529,7 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     }
   }
   const int64_t ktc = cm2_conv_tc_klen(d->kh, d->kw, d->num_src, p->src_c);
-  if (!encode_2d(&p->b_map, d->weight, (uint64_t)cout_pad, (uint64_t)ktc, (uint32_t)p->bn)) {
+  if (!encode_2d(&p->b_map, d->weight, (uint64_t)cout_pad, (uint64_t)ktc, (uint32_t)(p->pair ? p->bn / 2 : p->bn))) {
     set_error("conv_tc: cuTensorMapEncodeTiled failed for the weights");
     return CM2_ERR_CUDA;
   }
@@ -1472,7 +1546,8 @@ int conv_tc_launch(const cm2_conv_desc* d, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(conv_tc_kernel<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_tc2_kernel<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc2_kernel<320, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc2_kernel<320, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   }
   if (p.stats) {
     long long imgs = d->src[0].n;
@@ -1487,8 +1562,26 @@ int conv_tc_launch(const cm2_conv_desc* d, cudaStream_t stream) {
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sms ? tiles : sms;
-  if (p.variant == 2)
-    conv_tc2_kernel<320><<<grid, 64 + 256 * p.epi_sets, p.smem_bytes, stream>>>(p);
+  if (p.variant == 2 && p.pair) {
+    const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    int clusters = sms / 2;
+    if (pair_tiles < clusters) clusters = pair_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(64 + 256 * p.epi_sets);
+    cfg.dynamicSmemBytes = p.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, conv_tc2_kernel<320, true>, p) != cudaSuccess) {
+      set_error("conv_tc: cluster launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return CM2_ERR_CUDA;
+    }
+  } else if (p.variant == 2)
+    conv_tc2_kernel<320, false><<<grid, 64 + 256 * p.epi_sets, p.smem_bytes, stream>>>(p);
   else
     conv_tc_kernel<320><<<grid, 64 + 128 * p.epi_sets, p.smem_bytes, stream>>>(p);
   CM2_CHECK_LAUNCH("conv_tc");
