@@ -1414,6 +1414,14 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   const int tiles256 = m_tiles256 * (cout_pad / bn2);
   bool use_v2 = !pred && (merge_ok && bn2 <= 128 && tiles256 >= 2 * sms) || (phase && bn2 <= 128 && tiles256 >= sms) ||
                 (p->taps == 1 && k_total <= 128 && tiles256 >= sms);
+  // CTA pairs (cta_group::2 MMAs, conv_tc2_kernel<.., true>): measured on the same tool (profiles/r1b_convbench_pair_b16.txt)
+  // +17 % / +14 % / +10 % on the stride-1 3x3 layers with N = 128 / 160 / 192 (their single-CTA MMAs are bound by
+  // shared-memory operand bandwidth); N = 256 layers and maps with fewer than ~1.5 pair tiles per cluster stay on v1.
+  static const int env_pair = getenv("CM2_TC_PAIR") ? atoi(getenv("CM2_TC_PAIR")) : 1;
+  const int pair_tiles = ((m_tiles256 + 1) / 2) * (cout_pad / bn2);
+  const bool pair_ok = env_pair >= 1 && !pred && merge_ok && bn2 % 32 == 0 && bn2 <= 224 && cout_pad == bn2 &&
+                       2 * pair_tiles >= 3 * (sms / 2);
+  if (pair_ok) use_v2 = true;
   if (env_variant == 1) use_v2 = false;
   if (env_variant >= 2 && !pred) use_v2 = true;
   static const int env_sets1 = getenv("CM2_TC_EPI_SETS_V1") ? atoi(getenv("CM2_TC_EPI_SETS_V1")) : 2;
@@ -1457,8 +1465,9 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
       p->sa_stages = p->sb_stages = (int)(st > 6 ? 6 : st);
     }
     // CTA pairs (cta_group::2): streamed weights only, N a multiple of 32 (each CTA holds N/2 rows, N/2 % 16 == 0)
-    static const int env_pair = getenv("CM2_TC_PAIR") ? atoi(getenv("CM2_TC_PAIR")) : 0;
-    p->pair = (env_pair && !p->b_resident && p->bn % 32 == 0 && p->bn >= 32) ? 1 : 0;
+    // streamed weights only, N a multiple of 32 (each CTA holds N/2 rows, N/2 % 16 == 0); CM2_TC_PAIR=2 forces pairs on
+    // every v2 layer (tests), 0 disables them
+    p->pair = ((pair_ok || env_pair == 2) && !p->b_resident && p->bn % 32 == 0 && p->bn >= 32) ? 1 : 0;
     p->smem_bytes = (unsigned)(1024 + p->sa_stages * a_slab + p->sb_stages * b_bytes + tail2);
   } else {
     p->variant = 1;

@@ -150,6 +150,40 @@ def test_conv_tc_large_multi_wave():
     close(nchw(out.view), ref)
 
 
+@pytest.mark.parametrize("c", [128, 160])
+def test_conv_tc_cta_pair_layers(c):
+    """Stride-1 3x3 layers with N <= 224 and enough tiles run as CTA pairs (cta_group::2 MMAs of M = 256, half a weight
+    tile per CTA).  271 tiles of 256 rows: the last pair has only its leader half inside the matrix."""
+    g = torch.Generator().manual_seed(50 + c)
+    x = rb(torch.randn(4, c, 100, 168, generator=g))
+    wt = rb(torch.randn(c, c, 3, 3, generator=g) / math.sqrt(9 * c))
+    scale = torch.rand(c, generator=g) + 0.5
+    shift = torch.randn(c, generator=g) * 0.1
+    ref = F.relu(F.conv2d(x, wt, None, 1, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    cw = packing.ConvW(wt, [c], 1, 1, scale, shift, True, BF, DEV, True)
+    out = halo(torch.zeros(4, c, 100, 168))
+    out.buf.fill_(3.0)
+    assert lib.conv2d([halo(x).view], cw.w_tc, out.view, c, 3, 1, 1, scale=cw.scale, shift=cw.shift, relu=True,
+                      engine=lib.ENGINE_TC, probe=True), lib.last_error()
+    torch.cuda.synchronize()
+    close(nchw(out.view), ref)
+    b = out.buf.float()
+    assert b[:, 0].abs().max() == 0 and b[:, -1].abs().max() == 0 and b[:, :, 0].abs().max() == 0 and b[:, :, -1].abs().max() == 0
+
+
+def test_conv_tc_every_shape_through_cta_pairs():
+    """The whole halo-convolution shape table forced through the pair kernel (the variant switches are read once per
+    process, hence the child process): CM2_TC_VARIANT=3 puts every layer on the 256-row kernel, CM2_TC_PAIR=2 pairs it."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, CM2_TC_PAIR="2", CM2_TC_VARIANT="3", CM2_TC_B_RESIDENT="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_conv_tc.py", "-m", "gpu", "-q", "-x", "-k",
+                        "conv_tc_halo or multi_wave or cta_pair_layers"], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_unsupported_shapes_are_refused_not_miscomputed():
     x = halo(torch.zeros(1, 64, 8, 8))
     w = torch.zeros((64, 64 * 9), dtype=BF, device=DEV)

@@ -50,12 +50,17 @@ def _fields(inst):
     return {k: (v.tensor if hasattr(v, "tensor") else v).detach().cpu() for k, v in inst.get_fields().items()}
 
 
+MS_REL_GATE = 1e-1         # unnormalised MaskIoU outputs of random-init weights amplify a flipped bf16 bit: 3.6e-2 measured
+
+
 def _same(a, b, what):
     """Same kept detections.  Sources of variation between two evaluations of one image: the order of the fp64 atomics
     behind the GroupNorm / eSE statistics and, when the position in the batch changes, the grouping of an image's rows
     into the fp32 warp partial sums in front of them -- ~1e-7 relative, i.e. an occasional bf16 rounding flip.  So
     detections are matched by (class, location) instead of by rank (near-tied scores may swap), at most 2 of 50 may
-    differ, and matched ones must agree to the north-star tolerances of the fp32 variant."""
+    differ, and matched ones must agree to the north-star tolerances of the fp32 variant -- except the boxes, which get
+    5e-2 px here: one bf16 flip (2^-8 relative) in the last box-tower activation moves a 100 px regression distance by
+    ~1e-2 px, and a handful of flips was measured at 2.6e-2 px (the bound on the fp32 engine stays 1e-2 px, test_gpu_model)."""
     ka = {(int(c), float(l[0]), float(l[1])): i for i, (c, l) in enumerate(zip(a["pred_classes"], a["locations"]))}
     kb = {(int(c), float(l[0]), float(l[1])): i for i, (c, l) in enumerate(zip(b["pred_classes"], b["locations"]))}
     common = sorted(set(ka) & set(kb))
@@ -66,10 +71,13 @@ def _same(a, b, what):
         torch.equal(a["scores"], b["scores"]) and torch.equal(a["pred_masks"], b["pred_masks"])
     print("{}: {} ({} of {} detections in common)".format(what, "bit-identical" if exact else "equal within tolerance",
                                                           len(common), len(ka)))
-    assert (a["pred_boxes"][ia] - b["pred_boxes"][ib]).abs().max().item() <= 1e-2, what
+    assert (a["pred_boxes"][ia] - b["pred_boxes"][ib]).abs().max().item() <= 5e-2, what
     assert (a["scores"][ia] - b["scores"][ib]).abs().max().item() <= 1e-3, what
     ms_a, ms_b = a["mask_scores"][ia], b["mask_scores"][ib]        # unnormalised with random-init weights: relative gate
-    assert ((ms_a - ms_b).abs() <= 1e-2 * ms_b.abs().clamp(min=1.0)).all(), what
+    rel = ((ms_a - ms_b).abs() / ms_b.abs().clamp(min=1.0)).max().item()
+    print("{}: max box diff {:.4f} px, max relative mask_score diff {:.4f}".format(
+        what, (a["pred_boxes"][ia] - b["pred_boxes"][ib]).abs().max().item(), rel))
+    assert rel <= MS_REL_GATE, (what, rel)
     assert mask_iou(a["pred_masks"][ia], b["pred_masks"][ib]).min().item() >= 0.99, what
 
 
