@@ -353,11 +353,19 @@ def main():
         rec = compact_results(out, r_cap)
         return rec.cpu()
 
+    side = torch.cuda.Stream()
+    h_rec = torch.empty((args.batch, r_cap, 8), dtype=torch.float32, pin_memory=True)
+
     def e2e_stream(k):
-        rec = None
-        for out in model.inference_stream(host_inputs for _ in range(k)):
-            rec = compact_results(out, r_cap).cpu()
-        return rec
+        # the record of every step is packed and copied to the host on a side stream that waits for that step only
+        # (on the compute stream the copy would queue behind the steps already enqueued ahead)
+        for out, done in model.inference_stream((host_inputs for _ in range(k)), with_event=True):
+            side.wait_event(done)
+            with torch.cuda.stream(side):
+                rec = compact_results(out, r_cap)
+                h_rec.copy_(rec, non_blocking=True)
+            side.synchronize()
+        return h_rec.clone()
     for _ in range(2):
         e2e_step()
     e2e_stream(3)

@@ -51,14 +51,18 @@ class GeneralizedRCNN(nn.Module):
         return self.inference(batched_inputs)
 
     @torch.no_grad()
-    def inference_stream(self, batches, do_postprocess=True, depth=2):
+    def inference_stream(self, batches, do_postprocess=True, depth=2, with_event=False):
         """Generator over an iterable of ``batched_inputs`` lists: yields what ``inference`` returns for each, in order.
 
         Same results as calling ``forward`` per batch, software-pipelined ``depth`` batches deep: (1) the host->device
         copy of the next batch (pinned host images) runs on a copy stream into a staging buffer while earlier batches
         are computed; (2) the device work of the following ``depth`` batches is enqueued BEFORE the host waits for batch
         ``i`` and cuts its ``Instances`` out, so the GPU does not idle during the host-side assembly and read-back.
-        Every batch is still copied from the host, run and read back; only the order of issue changes."""
+        Every batch is still copied from the host, run and read back; only the order of issue changes.
+
+        ``with_event=True`` yields ``(results, event)``: the CUDA event marks the end of that batch's device work.  A
+        consumer that reads results back should do so on its own stream after ``stream.wait_event(event)`` -- a copy on
+        the compute stream would queue behind the batches already enqueued ahead and drain the pipeline."""
         eng = runtime.engine_for(self.cfg)
         copy_stream = eng.copy_stream()
         it = iter(batches)
@@ -107,7 +111,9 @@ class GeneralizedRCNN(nn.Module):
                 break
         while pending:
             launch_next()                               # keep `depth` batches queued behind the one about to be finished
-            yield self._finish(pending.popleft())
+            ctx = pending.popleft()
+            out = self._finish(ctx)
+            yield (out, ctx["done"]) if with_event else out
 
     @torch.no_grad()
     def inference(self, batched_inputs, detected_instances=None, do_postprocess=True):
@@ -182,7 +188,9 @@ class GeneralizedRCNN(nn.Module):
         masks = None
         if do_postprocess and probs is not None:
             masks = eng.paste_batch(probs, boxes, valid, out_sizes, dtype=torch.bool)
-        return dict(eng=eng, n=n, sizes=sizes, out_sizes=out_sizes, do_postprocess=do_postprocess, r_cap=r_cap, scores=scores,
+        done = torch.cuda.Event()
+        done.record()
+        return dict(done=done, eng=eng, n=n, sizes=sizes, out_sizes=out_sizes, do_postprocess=do_postprocess, r_cap=r_cap, scores=scores,
                     classes=classes, locs=locs, mscores=mscores, boxes=boxes, masks=masks, pm=None if do_postprocess else pm,
                     ready=ready, h_count=h_count, h_cand=h_cand, h_valid=h_valid if do_postprocess else None,
                     cand_cap=det["cand_cap"], have_probs=probs is not None)
