@@ -81,6 +81,7 @@ struct alignas(64) TcParams {
   int epi_sets;             // column sets of epilogue warps per 128-row accumulator (1, 2 or 4)
   int fast_store;           // 1: epilogue transposes through shared memory and writes 64-byte row segments
   int dbg;                  // tuning experiments (CM2_TC_DEBUG): 1 no epilogue stores, 2 no TMA loads, 4 no MMAs, 8 no epilogue body
+  int row_begin;            // v1 only: first GEMM row covered by a tile (leading halo rows trimmed to save a wave of tiles)
   int pair;                 // v2 only: 1 = launched as CTA pairs, cta_group::2 MMAs (see conv_tc2_kernel<.., true>)
   int variant;              // host only: 1 = conv_tc_kernel (128-row tiles), 2 = conv_tc2_kernel
   unsigned smem_bytes;      // host only: dynamic shared memory of the launch
@@ -833,7 +834,7 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc_kernel(const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int m0 = (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.bn;
+        const int m0 = p.row_begin + (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.bn;
         int kb = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int shift = tc_tap_shift(p, tap, p.num_seg ? tc_geom(p, m0).pitch : p.pitch);
@@ -915,7 +916,7 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc_kernel(const __grid_constant_
     uint32_t acc_phase = 0;
     uint32_t parity = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, parity ^= 1u) {
-      const int m0 = (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.bn;
+      const int m0 = p.row_begin + (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.bn;
       // scale / shift of the tile's columns: staged once when there is a single N tile, else per tile (double buffered)
       const uint32_t ss = ss_base + (p.n_tiles == 1 ? 0u : parity * 2048u);
       if (p.n_tiles > 1 || t == (int)blockIdx.x)
@@ -1475,6 +1476,16 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     p->m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
     p->bn = pred ? d->cout / 4 : pick_bn(cout_pad, p->m_tiles, sms);     // fused predictor: one N tile per quadrant
     p->n_tiles = (cout_pad + p->bn - 1) / p->bn;
+    // Wave quantisation: the first pitch + 1 and the last pitch + 1 rows of a halo matrix are halo pixels of the first /
+    // last image.  When leaving them out saves a whole wave of tiles (16 images of 25x42: 149 tiles on 148 SMs -> 148),
+    // the tiles start at the first interior pixel and the launch clears those output rows with two small memsets.
+    static const int env_trim = getenv("CM2_TC_TRIM") ? atoi(getenv("CM2_TC_TRIM")) : 1;
+    if (env_trim && halo && !seg && !phase && !pred && rows > 4 * (long long)(p->pitch + 1)) {
+      const int lead = p->pitch + 1;
+      const int t_trim = (int)((rows - 2 * lead + TC_BM - 1) / TC_BM);
+      const int waves_full = (p->m_tiles * p->n_tiles + sms - 1) / sms, waves_trim = (t_trim * p->n_tiles + sms - 1) / sms;
+      if (waves_trim < waves_full) { p->row_begin = lead; p->m_tiles = t_trim; }
+    }
     p->a_box_rows = TC_BM;
     const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p->bn * TC_BK * 2;
     int stages = (int)((smem_max - tail_v1) / stage_bytes);
@@ -1568,6 +1579,16 @@ int conv_tc_launch(const cm2_conv_desc* d, cudaStream_t stream) {
       set_error("conv_tc: cudaMemsetAsync(stats) failed");
       return CM2_ERR_CUDA;
     }
+  }
+  if (p.row_begin > 0 && p.out_halo && d->out_mode == 0) {
+    // output rows outside the trimmed tile range are halo pixels: keep them zero
+    const size_t eb = p.out_f32 ? 4 : 2, row_bytes = (size_t)d->out.sw * eb;
+    char* obase = reinterpret_cast<char*>(d->out.data) - (size_t)(d->out.sh + d->out.sw) * eb;
+    const long long covered_end = (long long)p.row_begin + (long long)p.m_tiles * TC_BM;
+    bool ok = cudaMemsetAsync(obase, 0, (size_t)p.row_begin * row_bytes, stream) == cudaSuccess;
+    if (ok && covered_end < p.rows)
+      ok = cudaMemsetAsync(obase + (size_t)covered_end * row_bytes, 0, (size_t)(p.rows - covered_end) * row_bytes, stream) == cudaSuccess;
+    if (!ok) { set_error("conv_tc: cudaMemsetAsync(halo rows) failed"); return CM2_ERR_CUDA; }
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sms ? tiles : sms;

@@ -50,6 +50,8 @@ def close(got, ref, out_bf16=True):
     ([256, 160, 160, 160, 160, 160], 512, 1, 10, 12, 2),   # OSA3 aggregation: two N tiles, K tails
     ([1024], 256, 1, 25, 42, 1),         # FPN lateral 5
     ([256, 16], 256, 3, 14, 14, 5),      # MaskIoU fcn1: roi feature + 16-channel padded mask plane
+    ([224], 224, 3, 25, 42, 16),         # 149 row tiles on 148 SMs: leading / trailing halo rows trimmed (148 tiles) + memset
+    ([1024], 256, 1, 25, 42, 16),        # same geometry, 1x1
 ])
 def test_conv_tc_halo(srcs, cout, k, h, w, n):
     g = torch.Generator().manual_seed(sum(srcs) + cout + k)
