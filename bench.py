@@ -178,7 +178,8 @@ def device_step(model, cfg, dev_images, sizes_out):
 
 
 def conv_time_per_step(model, cfg, dev_images, steps, layers=None):
-    """Sum of the device time of every convolution launch in one step (CUDA events around each launch)."""
+    """Sum of the device time of every convolution launch in one step (CUDA events around each launch, the launches of a
+    step enqueued behind a device-side delay so that the events measure kernel time, not host launch latency)."""
     from centermask2_b200 import runtime
     eng = runtime.engine_for(cfg)
     events = []
@@ -212,6 +213,9 @@ def conv_time_per_step(model, cfg, dev_images, steps, layers=None):
     eng.conv_seg = timed_seg
     try:
         for _ in range(steps):
+            # keep the GPU behind the host while the step is enqueued: with an empty queue every (event, launch) pair
+            # would also time the few microseconds of host-side argument marshalling between the two calls
+            torch.cuda._sleep(40_000_000)                # ~20 ms of device-side spinning
             device_step(model, cfg, dev_images, (H, W))
         torch.cuda.synchronize()
     finally:
