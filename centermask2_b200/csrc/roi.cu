@@ -175,6 +175,71 @@ __device__ __forceinline__ void roialign_sample_loop(const View<const T>& f, int
   }
 }
 
+// weight tables of one ROI (all threads of the CTA call this; ends with a barrier)
+__device__ __forceinline__ void roi_build_tables(float (*s_w)[ROI_MAX_RES][ROI_MAXT], int (*s_start)[ROI_MAX_RES],
+                                                 int (*s_num)[ROI_MAX_RES], int res, float roi_start_h, float roi_start_w,
+                                                 float bin_h, float bin_w, int grid_h, int grid_w, int fh, int fw) {
+  for (int i = threadIdx.x; i < 2 * res * ROI_MAXT; i += blockDim.x) {
+    const int axis = i / (res * ROI_MAXT), rem = i - axis * res * ROI_MAXT;
+    s_w[axis][rem / ROI_MAXT][rem % ROI_MAXT] = 0.f;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 2 * res; t += blockDim.x) {
+    const int axis = t / res, pb = t - axis * res;
+    const float start = axis ? roi_start_w : roi_start_h, bin = axis ? bin_w : bin_h;
+    const int grid = axis ? grid_w : grid_h, extent = axis ? fw : fh;
+    int s0 = -1, num = 0;
+    for (int i = 0; i < grid; ++i) {
+      const float v = start + pb * bin + ((float)i + 0.5f) * bin / (float)grid;
+      if (v < -1.0f || v > (float)extent) continue;
+      float vv = v <= 0.f ? 0.f : v;
+      int low = (int)vv, high;
+      if (low >= extent - 1) { high = low = extent - 1; vv = (float)low; } else high = low + 1;
+      const float l = vv - (float)low, h = 1.f - l;
+      if (s0 < 0) s0 = low;
+      s_w[axis][pb][low - s0] += h;
+      s_w[axis][pb][high - s0] += l;
+      num = high - s0 + 1;
+    }
+    s_start[axis][pb] = s0 < 0 ? 0 : s0;
+    s_num[axis][pb] = num;
+  }
+  __syncthreads();
+}
+
+// merged-tap evaluation of one bin for 8 channels (weights and tap ranges from the tables)
+template <typename T>
+__device__ __forceinline__ void roi_bin_merged(const T* __restrict__ img_base, int sh32, int sw32,
+                                               const float (*s_w)[ROI_MAX_RES][ROI_MAXT], const int (*s_start)[ROI_MAX_RES],
+                                               const int (*s_num)[ROI_MAX_RES], int ph, int pw, int cv, float (&acc)[8]) {
+  const int ny = s_num[0][ph], nx = s_num[1][pw];
+  const float* wy = s_w[0][ph];
+  const float* wx = s_w[1][pw];
+  int off0 = s_start[0][ph] * sh32 + s_start[1][pw] * sw32 + cv * 8;
+  for (int jy = 0; jy < ny; ++jy, off0 += sh32) {
+    const float wyv = wy[jy];
+    int off = off0, jx = 0;
+    for (; jx + 4 <= nx; jx += 4, off += 4 * sw32) {
+      Raw8<T> r0, r1, r2, r3;
+      r0.load(img_base + off); r1.load(img_base + off + sw32);
+      r2.load(img_base + off + 2 * sw32); r3.load(img_base + off + 3 * sw32);
+      r0.fma(wyv * wx[jx], acc); r1.fma(wyv * wx[jx + 1], acc);
+      r2.fma(wyv * wx[jx + 2], acc); r3.fma(wyv * wx[jx + 3], acc);
+    }
+    if (nx - jx >= 2) {
+      Raw8<T> r0, r1;
+      r0.load(img_base + off); r1.load(img_base + off + sw32);
+      r0.fma(wyv * wx[jx], acc); r1.fma(wyv * wx[jx + 1], acc);
+      jx += 2; off += 2 * sw32;
+    }
+    if (nx - jx >= 1) {
+      Raw8<T> r0;
+      r0.load(img_base + off);
+      r0.fma(wyv * wx[jx], acc);
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256, 3) roialign_roi_kernel(const RoiAlignParams<T> p) {
   __shared__ float s_w[2][ROI_MAX_RES][ROI_MAXT];       // [axis][bin][tap] merged weights (axis 0 = y)
@@ -209,34 +274,8 @@ __global__ void __launch_bounds__(256, 3) roialign_roi_kernel(const RoiAlignPara
   const int grid_w = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(roi_width / (float)res);
   const float count = fmaxf((float)(grid_h * grid_w), 1.f);
   const bool merged = grid_h + 2 <= ROI_MAXT && grid_w + 2 <= ROI_MAXT;      // CTA-uniform
-  if (merged) {
-    for (int i = threadIdx.x; i < 2 * res * ROI_MAXT; i += blockDim.x) {
-      const int axis = i / (res * ROI_MAXT), rem = i - axis * res * ROI_MAXT;
-      s_w[axis][rem / ROI_MAXT][rem % ROI_MAXT] = 0.f;
-    }
-    __syncthreads();
-    if (threadIdx.x < 2 * res) {
-      const int axis = threadIdx.x / res, pb = threadIdx.x - axis * res;
-      const float start = axis ? roi_start_w : roi_start_h, bin = axis ? bin_w : bin_h;
-      const int grid = axis ? grid_w : grid_h, extent = axis ? f.w : f.h;
-      int s0 = -1, num = 0;
-      for (int i = 0; i < grid; ++i) {
-        const float v = start + pb * bin + ((float)i + 0.5f) * bin / (float)grid;
-        if (v < -1.0f || v > (float)extent) continue;
-        float vv = v <= 0.f ? 0.f : v;
-        int low = (int)vv, high;
-        if (low >= extent - 1) { high = low = extent - 1; vv = (float)low; } else high = low + 1;
-        const float l = vv - (float)low, h = 1.f - l;
-        if (s0 < 0) s0 = low;
-        s_w[axis][pb][low - s0] += h;
-        s_w[axis][pb][high - s0] += l;
-        num = high - s0 + 1;
-      }
-      s_start[axis][pb] = s0 < 0 ? 0 : s0;
-      s_num[axis][pb] = num;
-    }
-    __syncthreads();
-  }
+  if (merged)
+    roi_build_tables(s_w, s_start, s_num, res, roi_start_h, roi_start_w, bin_h, bin_w, grid_h, grid_w, f.h, f.w);
   // exact division of small indices by the run-time constants c8 / res: q = umulhi(i, ceil(2^32 / d)) for i * d < 2^32
   const uint32_t magic_c8 = (uint32_t)((0x100000000ull + c8 - 1) / (uint32_t)c8);
   const uint32_t magic_res = (uint32_t)((0x100000000ull + res - 1) / (uint32_t)res);
@@ -249,38 +288,252 @@ __global__ void __launch_bounds__(256, 3) roialign_roi_kernel(const RoiAlignPara
     const int ph = res == 1 ? bin : (int)__umulhi((uint32_t)bin, magic_res), pw = bin - ph * res;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (merged) {
-      const int ny = s_num[0][ph], nx = s_num[1][pw];
-      const float* wy = s_w[0][ph];
-      const float* wx = s_w[1][pw];
-      int off0 = s_start[0][ph] * sh32 + s_start[1][pw] * sw32 + cv * 8;
-      for (int jy = 0; jy < ny; ++jy, off0 += sh32) {
-        const float wyv = wy[jy];
-        int off = off0, jx = 0;
-        for (; jx + 4 <= nx; jx += 4, off += 4 * sw32) {
-          Raw8<T> r0, r1, r2, r3;
-          r0.load(img_base + off); r1.load(img_base + off + sw32);
-          r2.load(img_base + off + 2 * sw32); r3.load(img_base + off + 3 * sw32);
-          r0.fma(wyv * wx[jx], acc); r1.fma(wyv * wx[jx + 1], acc);
-          r2.fma(wyv * wx[jx + 2], acc); r3.fma(wyv * wx[jx + 3], acc);
-        }
-        if (nx - jx >= 2) {
-          Raw8<T> r0, r1;
-          r0.load(img_base + off); r1.load(img_base + off + sw32);
-          r0.fma(wyv * wx[jx], acc); r1.fma(wyv * wx[jx + 1], acc);
-          jx += 2; off += 2 * sw32;
-        }
-        if (nx - jx >= 1) {
-          Raw8<T> r0;
-          r0.load(img_base + off);
-          r0.fma(wyv * wx[jx], acc);
-        }
-      }
+      roi_bin_merged<T>(img_base, sh32, sw32, s_w, s_start, s_num, ph, pw, cv, acc);
     } else {
       roialign_sample_loop<T>(f, img, cv, ph, pw, roi_start_h, roi_start_w, bin_h, bin_w, grid_h, grid_w, acc);
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] *= inv_count;
     Vec8<T>::store(p.out.at(slot, ph, pw) + cv * 8, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ROIAlign, one CTA per ROI slot, COLUMN WALK (separable evaluation).  ncu of the merged-tap kernel above: 234 M warp
+// instructions for 7.0 M warp-taps (33 per tap: 12 are the bf16 unpack + FMA floor, the rest loop / address / weight
+// overhead), issue-bound at 28 % of the HBM peak.  Here a thread owns (bin column pw, 8 channels) and walks the bin rows
+// ph = 0..res-1 downwards:
+//   out[ph][pw] = 1/count * sum_Y Wy[ph][Y] * v[Y],      v[Y] = sum_X Wx[pw][X] * f[Y][X]      (x pass of ONE feature row)
+// The x weights of the column live in registers for the whole walk (compile-time tap count NX: immediate-offset loads,
+// no weight fetch, no inner loop), and v[Y] is kept for the following bins: with an adaptive sampling grid neighbouring
+// samples are <= 1 pixel apart, so the rows of bin ph + 1 start at most two rows before the last row of bin ph -- the
+// last two x-passed rows are carried in registers and a feature row is loaded and unpacked ONCE per column (h + 2 rows
+// instead of sum_ph ny[ph] ~ h + 21).  The raw vectors of the next row are prefetched while the current one is consumed.
+// Columns with more than ROI_COL_NX taps, tables that do not fit (sample-loop case) fall back to the merged-tap bin
+// evaluation inside the same kernel.  With c = 256 a warp is one bin column (uniform control flow).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void roi_fma8(float (&acc)[8], float w, const float (&v)[8]) {
+  ffma2_roi(acc[0], acc[1], v[0], v[1], w); ffma2_roi(acc[2], acc[3], v[2], v[3], w);
+  ffma2_roi(acc[4], acc[5], v[4], v[5], w); ffma2_roi(acc[6], acc[7], v[6], v[7], w);
+}
+
+// Raw feature vectors of the rows ahead are staged through shared memory with cp.async: every thread copies the 16 (bf16)
+// / 32 (fp32) bytes of ITS OWN channels of tap k of row t + 2 into its private cell [slot = t & 1][k][thread] while rows
+// t and t + 1 are processed, and reads them back with one LDS.128 -- no barrier (a thread only ever reads what it copied
+// itself), a full row of lead time for the loads, and no registers held across the latency (with the prefetch in
+// registers ncu showed 46 % of the warp samples in long-scoreboard stalls: the load of row t + 1 could only be issued
+// after the registers of row t had been unpacked).
+// FAST: pixel stride 256 elements and 448 threads as compile-time constants (immediate offsets everywhere).
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+template <typename T> struct RoiStage;
+template <> struct RoiStage<__nv_bfloat16> {
+  static constexpr int BYTES = 16;
+  static __device__ __forceinline__ void copy(uint32_t saddr, const __nv_bfloat16* g) { cp_async16(saddr, g); }
+  static __device__ __forceinline__ void read(uint32_t saddr, Raw8<__nv_bfloat16>& r) { r.q = lds128(saddr); }
+};
+template <> struct RoiStage<float> {
+  static constexpr int BYTES = 32;
+  static __device__ __forceinline__ void copy(uint32_t saddr, const float* g) { cp_async16(saddr, g); cp_async16(saddr + 16, g + 4); }
+  static __device__ __forceinline__ void read(uint32_t saddr, Raw8<float>& r) {
+    const uint4 a = lds128(saddr), b = lds128(saddr + 16);
+    r.a = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
+    r.b = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w));
+  }
+};
+constexpr int ROI_COL_THREADS = 448;                     // 14 bin columns x 32 lanes (256 channels)
+constexpr int ROI_COL_CELL = 96;                         // staging bytes per thread and slot (6 bf16 taps / 3 fp32 taps)
+
+template <typename T, int NX, bool FAST>
+__device__ __forceinline__ void roi_col_walk(const T* __restrict__ colp, int sh32, int sw_rt, const float* __restrict__ wxs,
+                                             const float (*wys)[ROI_MAXT], const int* __restrict__ ny_s,
+                                             const int* __restrict__ carry_s, int res, int y_first, int y_end,
+                                             T* __restrict__ outp, long long out_sh, uint32_t stage) {
+  constexpr int B = RoiStage<T>::BYTES;
+  const int sw = FAST ? 256 : sw_rt;
+  const uint32_t kstride = (FAST ? ROI_COL_THREADS : blockDim.x) * B;     // [slot][tap][thread] cells
+  const uint32_t cell0 = stage + threadIdx.x * B;
+  float wx[NX];
+#pragma unroll
+  for (int k = 0; k < NX; ++k) wx[k] = wxs[k];
+  float cl[8], cp[8];                                     // x-passed rows y_done (cl) and y_done - 1 (cp)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) cl[k] = cp[k] = 0.f;
+  // rows y_first .. y_end - 1 are consumed in order, each exactly once
+  const T* nextp = colp + (long long)y_first * sh32;      // next row to copy
+  int t_next = y_first, t_cur = y_first;
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    if (t_next < y_end) {
+#pragma unroll
+      for (int k = 0; k < NX; ++k) RoiStage<T>::copy(cell0 + (d * NX + k) * kstride, nextp + k * sw);
+      ++t_next;
+      nextp += sh32;
+    }
+    cp_async_commit();
+  }
+  for (int ph = 0; ph < res; ++ph, outp += out_sh) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int ny = ny_s[ph];
+    const float* wy = wys[ph];                            // already divided by the sample count
+    const int c = carry_s[ph];                            // leading rows of this bin that are x-passed already
+    int j = 0;
+    if (c == 2) {
+      roi_fma8(acc, wy[0], cp);
+      if (ny > 1) roi_fma8(acc, wy[1], cl);
+      j = 2;
+    } else if (c == 1) {
+      roi_fma8(acc, wy[0], cl);
+      j = 1;
+    }
+    for (; j < ny; ++j, ++t_cur) {
+      const uint32_t cell = cell0 + ((t_cur - y_first) & 1) * (NX * kstride);
+      cp_async_wait1();                                   // row t_cur has landed (row t_cur + 1 may be in flight)
+      Raw8<T> raw[NX];
+#pragma unroll
+      for (int k = 0; k < NX; ++k) RoiStage<T>::read(cell + k * kstride, raw[k]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { cp[k] = cl[k]; cl[k] = 0.f; }
+#pragma unroll
+      for (int k = 0; k < NX; ++k) raw[k].fma(wx[k], cl);
+      if (t_next < y_end) {                               // rows below y_end are in bounds by construction
+#pragma unroll
+        for (int k = 0; k < NX; ++k) RoiStage<T>::copy(cell + k * kstride, nextp + k * sw);
+        ++t_next;
+        nextp += sh32;
+      }
+      cp_async_commit();
+      roi_fma8(acc, wy[j], cl);
+    }
+    Vec8<T>::store(outp, acc);
+  }
+}
+
+template <typename T> struct RoiColNx { static constexpr int value = ROI_COL_CELL / RoiStage<T>::BYTES; };
+
+template <typename T, bool FAST>
+__device__ __forceinline__ bool roi_col_dispatch(int nx, const T* __restrict__ colp, int sh32, int sw_rt,
+                                                 const float* __restrict__ wxs, const float (*wys)[ROI_MAXT],
+                                                 const int* __restrict__ ny_s, const int* __restrict__ carry_s, int res,
+                                                 int y_first, int y_end, T* __restrict__ outp, long long out_sh,
+                                                 uint32_t stage) {
+#define CM2_ROI_COL_CASE(NXV)                                                                                        \
+  case NXV:                                                                                                          \
+    if constexpr (NXV <= RoiColNx<T>::value) {                                                                       \
+      roi_col_walk<T, NXV, FAST>(colp, sh32, sw_rt, wxs, wys, ny_s, carry_s, res, y_first, y_end, outp, out_sh, stage); \
+      return true;                                                                                                   \
+    }                                                                                                                \
+    break;
+  switch (nx) {
+    CM2_ROI_COL_CASE(1) CM2_ROI_COL_CASE(2) CM2_ROI_COL_CASE(3) CM2_ROI_COL_CASE(4) CM2_ROI_COL_CASE(5) CM2_ROI_COL_CASE(6)
+    default: break;
+  }
+#undef CM2_ROI_COL_CASE
+  return false;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(448, 2) roialign_col_kernel(const RoiAlignParams<T> p) {
+  __shared__ float s_w[2][ROI_MAX_RES][ROI_MAXT];       // [axis][bin][tap] merged weights (axis 0 = y)
+  __shared__ int s_start[2][ROI_MAX_RES], s_num[2][ROI_MAX_RES];
+  __shared__ int s_carry[ROI_MAX_RES];                  // per bin row: leading feature rows shared with the bins above
+  __shared__ int s_walk[3];                             // first needed feature row, one past the last, walk usable
+  extern __shared__ __align__(16) unsigned char s_stage[];   // [2 slots][ROI_COL_CELL bytes][threads] cp.async staging
+  const int slot = blockIdx.x;
+  const int img = slot / p.r_cap, r = slot - img * p.r_cap;
+  const int res = p.res, c8 = p.out.c >> 3;
+  const int pw = threadIdx.x / c8, cv = threadIdx.x - pw * c8;       // blockDim.x == res * c8
+  T* outp = p.out.at(slot, 0, pw) + cv * 8;
+  if (r >= p.det_count[img]) {                          // empty slot: zeros
+    const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+    for (int ph = 0; ph < res; ++ph, outp += p.out.sh) Vec8<T>::store(outp, z);
+    return;
+  }
+  const float4 bx = reinterpret_cast<const float4*>(p.boxes)[slot];
+  int lvl = assign_level(bx.x, bx.y, bx.z, bx.w, p.image_area[img], p.crit, p.min_level, p.max_level);
+  if (lvl >= p.num_levels) lvl = p.num_levels - 1;
+  if (p.level_out && threadIdx.x == 0) p.level_out[slot] = lvl;
+  View<const T> f = p.feat[0];
+  float scale = p.scale[0];
+#pragma unroll
+  for (int l = 1; l < ROI_MAX_LEVELS; ++l)
+    if (l == lvl) { f = p.feat[l]; scale = p.scale[l]; }
+  const float roi_start_w = bx.x * scale - 0.5f, roi_start_h = bx.y * scale - 0.5f;
+  const float roi_end_w = bx.z * scale - 0.5f, roi_end_h = bx.w * scale - 0.5f;
+  const float roi_width = roi_end_w - roi_start_w, roi_height = roi_end_h - roi_start_h;
+  const float bin_h = roi_height / (float)res, bin_w = roi_width / (float)res;
+  const int grid_h = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(roi_height / (float)res);
+  const int grid_w = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(roi_width / (float)res);
+  const float inv_count = 1.0f / fmaxf((float)(grid_h * grid_w), 1.f);
+  const bool merged = grid_h + 2 <= ROI_MAXT && grid_w + 2 <= ROI_MAXT;      // CTA-uniform
+  const T* img_base = f.p + (size_t)img * f.sn;
+  const int sh32 = (int)f.sh, sw32 = (int)f.sw;
+  if (merged) {
+    roi_build_tables(s_w, s_start, s_num, res, roi_start_h, roi_start_w, bin_h, bin_w, grid_h, grid_w, f.h, f.w);
+    if (threadIdx.x < res) {                             // fold 1 / count into the row weights
+      for (int j = 0; j < s_num[0][threadIdx.x]; ++j) s_w[0][threadIdx.x][j] *= inv_count;
+    }
+    if (threadIdx.x == blockDim.x - 1) {
+      // which leading rows of a bin are already x-passed by the bins above it (cl = row y_done, cp = row y_done - 1)
+      // the walk needs the rows of the bins to follow each other without a gap (always the case with an adaptive grid)
+      int y_first = 0, y_done = -1, valid = 0, ok = 1;
+      for (int ph = 0; ph < res; ++ph) {
+        const int ny = s_num[0][ph], sy = s_start[0][ph];
+        int c = 0;
+        if (ny > 0) {
+          if (valid > 0) {
+            c = y_done - sy + 1;
+            if (c < 0 || c > valid) ok = 0;              // gap, or a row that is not carried any more: no walk
+          } else {
+            y_first = sy;
+          }
+          const int nnew = ny - min(max(c, 0), ny);      // rows this bin x-passes itself
+          if (nnew > 0) {
+            valid = min(valid + nnew, 2);
+            y_done = sy + ny - 1;
+          }
+        }
+        s_carry[ph] = c;
+      }
+      s_walk[0] = y_first;
+      s_walk[1] = y_done + 1;
+      s_walk[2] = ok;
+    }
+    __syncthreads();
+    if (s_walk[2]) {
+      const int nx = s_num[1][pw];
+      const T* colp = img_base + s_start[1][pw] * sw32 + cv * 8;
+      const uint32_t stage = (uint32_t)__cvta_generic_to_shared(s_stage);
+      const bool done = sw32 == 256 && blockDim.x == ROI_COL_THREADS
+          ? roi_col_dispatch<T, true>(nx, colp, sh32, sw32, s_w[1][pw], s_w[0], s_num[0], s_carry, res, s_walk[0], s_walk[1],
+                                      outp, p.out.sh, stage)
+          : roi_col_dispatch<T, false>(nx, colp, sh32, sw32, s_w[1][pw], s_w[0], s_num[0], s_carry, res, s_walk[0], s_walk[1],
+                                       outp, p.out.sh, stage);
+      if (done) return;
+    }
+  }
+  // generic column: merged-tap (or sample-loop) evaluation of each bin
+#pragma unroll 1
+  for (int ph = 0; ph < res; ++ph, outp += p.out.sh) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (merged)
+      roi_bin_merged<T>(img_base, sh32, sw32, s_w, s_start, s_num, ph, pw, cv, acc);   // row weights carry 1 / count
+    else
+      roialign_sample_loop<T>(f, img, cv, ph, pw, roi_start_h, roi_start_w, bin_h, bin_w, grid_h, grid_w, acc);
+    if (!merged) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] *= inv_count;
+    }
+    Vec8<T>::store(outp, acc);
   }
 }
 
@@ -969,10 +1222,20 @@ static int roialign_launch(const cm2_act* feats, const int32_t* feat_stride, int
   p.out = make_view<T>(*out);
   p.level_out = level_out;
   int64_t total = (int64_t)n * r_cap * out->h * out->w * (out->c / 8);
-  const int variant = getenv("CM2_ROIALIGN_VARIANT") ? atoi(getenv("CM2_ROIALIGN_VARIANT")) : 1;
+  const int variant = getenv("CM2_ROIALIGN_VARIANT") ? atoi(getenv("CM2_ROIALIGN_VARIANT")) : 2;
   bool small = true;
   for (int l = 0; l < num_levels; ++l) small = small && feats[l].sn < (1ll << 31);
-  if (variant == 1 && p.res <= ROI_MAX_RES && small) {
+  const int col_threads = p.res * (out->c / 8);
+  if (variant == 2 && p.res <= ROI_MAX_RES && small && col_threads <= ROI_COL_THREADS) {
+    static bool attr_set = false;                        // per instantiation (T)
+    if (!attr_set) {
+      cudaFuncSetAttribute(roialign_col_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ROI_COL_CELL * ROI_COL_THREADS);
+      attr_set = true;
+    }
+    roialign_col_kernel<T><<<n * r_cap, col_threads, 2 * ROI_COL_CELL * col_threads, s>>>(p);
+    return 0;
+  }
+  if (variant >= 1 && p.res <= ROI_MAX_RES && small) {
     const int items = p.res * p.res * (out->c / 8);
     const int threads = std::min(256, std::max(64, (items + 31) / 32 * 32));
     roialign_roi_kernel<T><<<n * r_cap, threads, 0, s>>>(p);

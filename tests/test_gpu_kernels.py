@@ -167,11 +167,14 @@ def _random_boxes(g, n, w, h):
     return torch.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1)
 
 
-@pytest.mark.parametrize("variant", [1, 0])                  # 1: CTA per ROI, merged taps; 0: thread per (bin, 8 channels)
-def test_roialign_fpn_matches_torchvision_and_reference_level_rule(variant, kernel_variant):
+# 2: CTA per ROI, column walk (separable, rows carried in registers); 1: CTA per ROI, merged taps;
+# 0: thread per (bin, 8 channels).  c = 256: a warp is one bin column (the production shape), c = 32: columns share warps
+@pytest.mark.parametrize("c", [32, 256])
+@pytest.mark.parametrize("variant", [2, 1, 0])
+def test_roialign_fpn_matches_torchvision_and_reference_level_rule(variant, c, kernel_variant):
     kernel_variant("ROIALIGN", variant)
     g = torch.Generator().manual_seed(7)
-    n, r_cap, c = 2, 24, 32
+    n, r_cap = 2, 24
     H, W = 96, 128
     feats = [torch.randn(n, c, H // s, W // s, generator=g) for s in (8, 16, 32)]
     counts = [24, 17]
@@ -205,7 +208,7 @@ def test_roialign_fpn_matches_torchvision_and_reference_level_rule(variant, kern
     assert got[r_cap + counts[1]:].abs().max() == 0                  # invalid slots are zeroed
 
 
-@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("variant", [2, 1, 0])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_roialign_large_rois_separable_path(dtype, variant, kernel_variant):
     kernel_variant("ROIALIGN", variant)

@@ -153,9 +153,17 @@ def main():
     hist = torch.bincount(lvl.long(), minlength=3).tolist()
     report("roialign_fpn (+ level assignment)", ms, n * (R * c * 196 * 2 + c * 22050 * 2), "ROIs per level {}".format(hist))
     if args.old:
+        got2 = roi.view.float().clone()
+        os.environ["CM2_ROIALIGN_VARIANT"] = "1"
+        roialign()
+        torch.cuda.synchronize()
+        dev_ = (roi.view.float() - got2).abs().max().item()
+        print("roialign column walk vs merged taps: max |diff| = {:.4g} (bf16 outputs, max |value| {:.3g})".format(
+            dev_, got2.abs().max().item()), file=sys.stderr)
+        report("roialign_fpn [v1: CTA per ROI, merged taps]", timed(roialign), n * (R * c * 196 * 2 + c * 22050 * 2))
         os.environ["CM2_ROIALIGN_VARIANT"] = "0"
         report("roialign_fpn [v0: thread per (bin, 8 channels), sample loop]", timed(roialign), n * (R * c * 196 * 2 + c * 22050 * 2))
-        os.environ["CM2_ROIALIGN_VARIANT"] = "1"
+        del os.environ["CM2_ROIALIGN_VARIANT"]
 
     # ---- spatial attention (A18)
     att = eng.fmap("matt", n * R, 14, 14, c)

@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""ROIAlign-only slice of tools/micro_post.py (same boxes, same features) for tuning sweeps:
+
+    python tools/micro_roi.py [--knobs 0,2,3,10,11] [--variants 2,1]
+
+Prints ms / GB/s over the algorithmic bytes per (variant, CM2_ROI_KNOB) and the deviation of every variant from variant 0.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from micro_post import H, W, LEVELS, timed                          # noqa: E402
+from centermask2_b200 import lib                                    # noqa: E402
+from centermask2_b200.config import get_cfg                        # noqa: E402
+from centermask2_b200.engine import Engine                         # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--rois", type=int, default=100)
+    ap.add_argument("--knobs", default="0")
+    ap.add_argument("--variants", default="2,1")
+    args = ap.parse_args()
+    n, R, dev, c = args.batch, args.rois, "cuda", 256
+    hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    cfg = get_cfg("centermask_V_39_eSE_FPN.yaml", ["MODEL.FCOS.POST_NMS_TOPK_TEST", R, "MODEL.B200.PRECISION", "bf16"])
+    eng = Engine(cfg, "bf16", dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    feats = [eng.fmap("mf{}".format(i), n, h, w, c) for i, (h, w, _) in enumerate(LEVELS[:3])]
+    for f in feats:
+        f.view.copy_(torch.randn(f.view.shape, device=dev, generator=g).to(torch.bfloat16))
+    area = torch.exp(torch.rand((n, R), device=dev, generator=g) * (math.log(0.9 * H * W) - math.log(32.0 * 32.0)) + math.log(32.0 * 32.0))
+    ar = torch.exp((torch.rand((n, R), device=dev, generator=g) - 0.5) * 1.4)
+    bw, bh = torch.sqrt(area * ar).clamp(max=W - 1.0), torch.sqrt(area / ar).clamp(max=H - 1.0)
+    x0 = torch.rand((n, R), device=dev, generator=g) * (W - bw)
+    y0 = torch.rand((n, R), device=dev, generator=g) * (H - bh)
+    boxes = torch.stack([x0, y0, x0 + bw, y0 + bh], dim=2).contiguous()
+    counts = torch.full((n,), R, dtype=torch.int32, device=dev)
+    img_area = torch.full((n,), float(H * W), device=dev)
+    roi = eng.fmap("mroi", n * R, 14, 14, c)
+    lvl = torch.zeros((n * R,), dtype=torch.int32, device=dev)
+
+    def roialign():
+        lib.roialign_fpn([f.view for f in feats], [8, 16, 32], boxes, counts, n, R, img_area, 0, 0, roi.view, lvl)
+    alg = n * (R * c * 196 * 2 + c * 22050 * 2)
+    os.environ["CM2_ROIALIGN_VARIANT"] = "0"
+    roialign()
+    torch.cuda.synchronize()
+    ref = roi.view.float().clone()
+    for v in [int(t) for t in args.variants.split(",")]:
+        os.environ["CM2_ROIALIGN_VARIANT"] = str(v)
+        for k in ([int(t) for t in args.knobs.split(",")] if v == 2 else [0]):
+            os.environ["CM2_ROI_KNOB"] = str(k)
+            roi.view.zero_()
+            ms = timed(roialign)
+            d = (roi.view.float() - ref).abs().max().item()
+            print("variant {} knob {:3d}: {:.4f} ms  {:7.1f} GB/s  {:.3f} of HBM peak   max|diff vs v0| {:.4g}".format(
+                v, k, ms, alg / ms / 1e6, alg / ms / 1e6 / hbm, d))
+
+
+if __name__ == "__main__":
+    main()
