@@ -26,6 +26,7 @@ struct RoiAlignParams {
   int n, r_cap, crit, sampling_ratio, res;
   View<T> out;
   int* level_out;
+  int* order;                     // column kernel: ROI slots in launch order (largest first), [n * r_cap]
 };
 
 __device__ __forceinline__ int assign_level(float x0, float y0, float x1, float y1, float img_area, int crit,
@@ -299,33 +300,33 @@ __global__ void __launch_bounds__(256, 3) roialign_roi_kernel(const RoiAlignPara
 }
 
 // ---------------------------------------------------------------------------------------------
-// ROIAlign, one CTA per ROI slot, COLUMN WALK (separable evaluation).  ncu of the merged-tap kernel above: 234 M warp
-// instructions for 7.0 M warp-taps (33 per tap: 12 are the bf16 unpack + FMA floor, the rest loop / address / weight
-// overhead), issue-bound at 28 % of the HBM peak.  Here a thread owns (bin column pw, 8 channels) and walks the bin rows
-// ph = 0..res-1 downwards:
+// ROIAlign, COLUMN WALK (separable evaluation), one WARP-SIZED CTA per (ROI slot, bin column).
+// ncu of the merged-tap kernel above: 234 M warp instructions for 7.0 M warp-taps (33 per tap: 12 are the bf16 unpack +
+// FMA floor, the rest loop / address / weight overhead), issue-bound at 28 % of the HBM peak.  Here a thread owns
+// (bin column pw, 8 channels) and walks the bin rows ph = 0..res-1 downwards:
 //   out[ph][pw] = 1/count * sum_Y Wy[ph][Y] * v[Y],      v[Y] = sum_X Wx[pw][X] * f[Y][X]      (x pass of ONE feature row)
-// The x weights of the column live in registers for the whole walk (compile-time tap count NX: immediate-offset loads,
-// no weight fetch, no inner loop), and v[Y] is kept for the following bins: with an adaptive sampling grid neighbouring
-// samples are <= 1 pixel apart, so the rows of bin ph + 1 start at most two rows before the last row of bin ph -- the
-// last two x-passed rows are carried in registers and a feature row is loaded and unpacked ONCE per column (h + 2 rows
-// instead of sum_ph ny[ph] ~ h + 21).  The raw vectors of the next row are prefetched while the current one is consumed.
-// Columns with more than ROI_COL_NX taps, tables that do not fit (sample-loop case) fall back to the merged-tap bin
-// evaluation inside the same kernel.  With c = 256 a warp is one bin column (uniform control flow).
+// * The x weights of the column live in registers for the whole walk (compile-time tap count NX: immediate-offset
+//   accesses, no weight fetch, no inner loop), and v[Y] is kept for the following bins: with an adaptive sampling grid
+//   neighbouring samples are <= 1 pixel apart, so the rows of bin ph + 1 start at most two rows before the last row of
+//   bin ph -- the last two x-passed rows are carried in registers and a feature row is loaded and unpacked ONCE per
+//   column (h + 2 rows instead of sum_ph ny[ph] ~ h + 21).
+// * Raw feature vectors of the rows ahead are staged through shared memory with cp.async: every thread copies the 16
+//   (bf16) / 32 (fp32) bytes of ITS OWN channels of tap k of row t + 2 into its private cell [slot = t & 1][k][lane]
+//   while rows t and t + 1 are processed, and reads them back with one LDS.128 -- no barrier (a thread only ever reads
+//   what it copied itself), a full row of lead time for the loads, no registers held across the latency.
+// * Work granularity is one column (44 800 CTAs at cfg 5): with one CTA per ROI the box-size spread left the SMs idle
+//   for 17 % of the kernel (tail) and every warp waited at the table-building barriers; a warp now builds the small
+//   tables it needs itself (lane = bin row for the y weights, shuffles for the carry bookkeeping) and nothing waits.
+// Columns with more than RoiColNx taps run the same walk with a run-time tap loop; ROIs whose rows do not follow each
+// other without a gap (fixed sampling ratios with bins > 2 pixels) or whose tables do not fit use the sample loop.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void roi_fma8(float (&acc)[8], float w, const float (&v)[8]) {
   ffma2_roi(acc[0], acc[1], v[0], v[1], w); ffma2_roi(acc[2], acc[3], v[2], v[3], w);
   ffma2_roi(acc[4], acc[5], v[4], v[5], w); ffma2_roi(acc[6], acc[7], v[6], v[7], w);
 }
-
-// Raw feature vectors of the rows ahead are staged through shared memory with cp.async: every thread copies the 16 (bf16)
-// / 32 (fp32) bytes of ITS OWN channels of tap k of row t + 2 into its private cell [slot = t & 1][k][thread] while rows
-// t and t + 1 are processed, and reads them back with one LDS.128 -- no barrier (a thread only ever reads what it copied
-// itself), a full row of lead time for the loads, and no registers held across the latency (with the prefetch in
-// registers ncu showed 46 % of the warp samples in long-scoreboard stalls: the load of row t + 1 could only be issued
-// after the registers of row t had been unpacked).
-// FAST: pixel stride 256 elements and 448 threads as compile-time constants (immediate offsets everywhere).
+// .cg: the staged lines bypass L1 (a column's taps are read once; with .ca the spill / table traffic lost its L1 hits)
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
@@ -349,41 +350,56 @@ template <> struct RoiStage<float> {
     r.b = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w));
   }
 };
-constexpr int ROI_COL_THREADS = 448;                     // 14 bin columns x 32 lanes (256 channels)
-constexpr int ROI_COL_CELL = 96;                         // staging bytes per thread and slot (6 bf16 taps / 3 fp32 taps)
+constexpr int ROI_COL_CLASSES = 6;                       // cost classes of the largest-first launch order
+constexpr int ROI_WYT = 16;                              // row taps per bin the column kernel keeps (grid_h <= 15)
+constexpr int ROI_COL_CELL = 96;                         // staging bytes per lane and slot (6 bf16 taps / 3 fp32 taps)
+template <typename T> struct RoiColNx { static constexpr int value = ROI_COL_CELL / RoiStage<T>::BYTES; };
 
-template <typename T, int NX, bool FAST>
-__device__ __forceinline__ void roi_col_walk(const T* __restrict__ colp, int sh32, int sw_rt, const float* __restrict__ wxs,
-                                             const float (*wys)[ROI_MAXT], const int* __restrict__ ny_s,
-                                             const int* __restrict__ carry_s, int res, int y_first, int y_end,
-                                             T* __restrict__ outp, long long out_sh, uint32_t stage) {
+// shared-memory layout of the column kernel (one warp): [res][ROI_WYT] y weights, [ROI_MAXT] x weights, [res] rows per
+// bin, [res] carried rows per bin, then 2 staging slots of ROI_COL_CELL bytes per lane
+__host__ __device__ inline int roi_col_tables_bytes(int res) { return (res * ROI_WYT + ROI_MAXT + 2 * res) * 4; }
+__host__ __device__ inline int roi_col_smem_bytes(int res) { return (roi_col_tables_bytes(res) + 15) / 16 * 16 + 2 * ROI_COL_CELL * 32; }
+
+// NX > 0: compile-time tap count, weights in registers, rows staged by cp.async.  NX == 0: run-time tap count (wide
+// columns), weights from shared memory, direct loads.  SW: compile-time pixel stride in elements (0 = run-time).
+template <typename T, int NX, int SW>
+__device__ __forceinline__ void roi_col_walk(const T* __restrict__ colp, int sh32, int sw_rt, int nx_rt,
+                                             const float* __restrict__ wxs, const float* __restrict__ wys,
+                                             const int* __restrict__ ny_s, const int* __restrict__ carry_s, int res,
+                                             int y_first, int y_end, T* __restrict__ outp, long long out_sh,
+                                             uint32_t stage) {
   constexpr int B = RoiStage<T>::BYTES;
-  const int sw = FAST ? 256 : sw_rt;
-  const uint32_t kstride = (FAST ? ROI_COL_THREADS : blockDim.x) * B;     // [slot][tap][thread] cells
-  const uint32_t cell0 = stage + threadIdx.x * B;
-  float wx[NX];
+  constexpr uint32_t kstride = 32 * B;                    // [slot][tap][lane] cells
+  constexpr int NXR = NX > 0 ? NX : 1;
+  const int sw = SW ? SW : sw_rt;
+  const uint32_t cell0 = stage + (threadIdx.x & 31) * B;
+  float wx[NXR];
+  if (NX > 0) {
 #pragma unroll
-  for (int k = 0; k < NX; ++k) wx[k] = wxs[k];
+    for (int k = 0; k < NXR; ++k) wx[k] = wxs[k];
+  }
   float cl[8], cp[8];                                     // x-passed rows y_done (cl) and y_done - 1 (cp)
 #pragma unroll
   for (int k = 0; k < 8; ++k) cl[k] = cp[k] = 0.f;
   // rows y_first .. y_end - 1 are consumed in order, each exactly once
-  const T* nextp = colp + (long long)y_first * sh32;      // next row to copy
+  const T* nextp = colp + (long long)y_first * sh32;      // next row to copy (NX > 0) / to read (NX == 0)
   int t_next = y_first, t_cur = y_first;
+  if (NX > 0) {
 #pragma unroll
-  for (int d = 0; d < 2; ++d) {
-    if (t_next < y_end) {
+    for (int d = 0; d < 2; ++d) {
+      if (t_next < y_end) {
 #pragma unroll
-      for (int k = 0; k < NX; ++k) RoiStage<T>::copy(cell0 + (d * NX + k) * kstride, nextp + k * sw);
-      ++t_next;
-      nextp += sh32;
+        for (int k = 0; k < NXR; ++k) RoiStage<T>::copy(cell0 + (d * NXR + k) * kstride, nextp + k * sw);
+        ++t_next;
+        nextp += sh32;
+      }
+      cp_async_commit();
     }
-    cp_async_commit();
   }
   for (int ph = 0; ph < res; ++ph, outp += out_sh) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const int ny = ny_s[ph];
-    const float* wy = wys[ph];                            // already divided by the sample count
+    const float* wy = wys + ph * ROI_WYT;                 // already divided by the sample count
     const int c = carry_s[ph];                            // leading rows of this bin that are x-passed already
     int j = 0;
     if (c == 2) {
@@ -395,64 +411,144 @@ __device__ __forceinline__ void roi_col_walk(const T* __restrict__ colp, int sh3
       j = 1;
     }
     for (; j < ny; ++j, ++t_cur) {
-      const uint32_t cell = cell0 + ((t_cur - y_first) & 1) * (NX * kstride);
-      cp_async_wait1();                                   // row t_cur has landed (row t_cur + 1 may be in flight)
-      Raw8<T> raw[NX];
-#pragma unroll
-      for (int k = 0; k < NX; ++k) RoiStage<T>::read(cell + k * kstride, raw[k]);
 #pragma unroll
       for (int k = 0; k < 8; ++k) { cp[k] = cl[k]; cl[k] = 0.f; }
+      if (NX > 0) {
+        const uint32_t cell = cell0 + ((t_cur - y_first) & 1) * (NXR * kstride);
+        cp_async_wait1();                                 // row t_cur has landed (row t_cur + 1 may be in flight)
+        Raw8<T> raw[NXR];
 #pragma unroll
-      for (int k = 0; k < NX; ++k) raw[k].fma(wx[k], cl);
-      if (t_next < y_end) {                               // rows below y_end are in bounds by construction
+        for (int k = 0; k < NXR; ++k) RoiStage<T>::read(cell + k * kstride, raw[k]);
 #pragma unroll
-        for (int k = 0; k < NX; ++k) RoiStage<T>::copy(cell + k * kstride, nextp + k * sw);
-        ++t_next;
+        for (int k = 0; k < NXR; ++k) raw[k].fma(wx[k], cl);
+        if (t_next < y_end) {                             // rows below y_end are in bounds by construction
+#pragma unroll
+          for (int k = 0; k < NXR; ++k) RoiStage<T>::copy(cell + k * kstride, nextp + k * sw);
+          ++t_next;
+          nextp += sh32;
+        }
+        cp_async_commit();
+      } else {
+        const T* tp = nextp;
+        int k = 0;
+        for (; k + 2 <= nx_rt; k += 2, tp += 2 * sw) {
+          Raw8<T> r0, r1;
+          r0.load(tp); r1.load(tp + sw);
+          r0.fma(wxs[k], cl); r1.fma(wxs[k + 1], cl);
+        }
+        if (k < nx_rt) {
+          Raw8<T> r0;
+          r0.load(tp);
+          r0.fma(wxs[k], cl);
+        }
         nextp += sh32;
       }
-      cp_async_commit();
       roi_fma8(acc, wy[j], cl);
     }
     Vec8<T>::store(outp, acc);
   }
 }
 
-template <typename T> struct RoiColNx { static constexpr int value = ROI_COL_CELL / RoiStage<T>::BYTES; };
-
-template <typename T, bool FAST>
-__device__ __forceinline__ bool roi_col_dispatch(int nx, const T* __restrict__ colp, int sh32, int sw_rt,
-                                                 const float* __restrict__ wxs, const float (*wys)[ROI_MAXT],
+template <typename T, int SW>
+__device__ __forceinline__ void roi_col_dispatch(int nx, const T* __restrict__ colp, int sh32, int sw_rt,
+                                                 const float* __restrict__ wxs, const float* __restrict__ wys,
                                                  const int* __restrict__ ny_s, const int* __restrict__ carry_s, int res,
                                                  int y_first, int y_end, T* __restrict__ outp, long long out_sh,
                                                  uint32_t stage) {
-#define CM2_ROI_COL_CASE(NXV)                                                                                        \
-  case NXV:                                                                                                          \
-    if constexpr (NXV <= RoiColNx<T>::value) {                                                                       \
-      roi_col_walk<T, NXV, FAST>(colp, sh32, sw_rt, wxs, wys, ny_s, carry_s, res, y_first, y_end, outp, out_sh, stage); \
-      return true;                                                                                                   \
-    }                                                                                                                \
+#define CM2_ROI_COL_CASE(NXV)                                                                                          \
+  case NXV:                                                                                                            \
+    if constexpr (NXV <= RoiColNx<T>::value) {                                                                         \
+      roi_col_walk<T, NXV, SW>(colp, sh32, sw_rt, nx, wxs, wys, ny_s, carry_s, res, y_first, y_end, outp, out_sh, stage); \
+      return;                                                                                                          \
+    }                                                                                                                  \
     break;
   switch (nx) {
     CM2_ROI_COL_CASE(1) CM2_ROI_COL_CASE(2) CM2_ROI_COL_CASE(3) CM2_ROI_COL_CASE(4) CM2_ROI_COL_CASE(5) CM2_ROI_COL_CASE(6)
     default: break;
   }
 #undef CM2_ROI_COL_CASE
-  return false;
+  roi_col_walk<T, 0, SW>(colp, sh32, sw_rt, nx, wxs, wys, ny_s, carry_s, res, y_first, y_end, outp, out_sh, stage);
+}
+
+// Launch order of the column kernel: ROI slots bucketed by decreasing cost of one bin column (~ feature rows x taps per
+// row; octave classes, empty slots last), slots ascending inside a class (STABLE counting sort: the CTAs in flight at
+// any time then belong to few images, whose feature maps stay in L2).  One CTA; warp w owns a contiguous range of slots,
+// ranks inside a 32-slot chunk come from __match_any_sync.  The order only affects scheduling, never a result.
+template <typename T>
+__global__ void __launch_bounds__(1024) roi_order_kernel(const RoiAlignParams<T> p) {
+  constexpr int NC = ROI_COL_CLASSES + 1;
+  __shared__ int s_cnt[32][NC];                         // per warp and class: count, then start position
+  __shared__ int s_base[NC];
+  const int nslots = p.n * p.r_cap, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = ((nslots + 31) / 32 + 31) / 32 * 32;  // slots per warp, a multiple of the chunk size
+  const int lo = warp * per, hi = min(lo + per, nslots);
+  const unsigned full = 0xffffffffu;
+  auto cost_class = [&](int slot) {
+    const int img = slot / p.r_cap, r = slot - img * p.r_cap;
+    if (r >= p.det_count[img]) return ROI_COL_CLASSES;
+    const float4 bx = reinterpret_cast<const float4*>(p.boxes)[slot];
+    int lvl = assign_level(bx.x, bx.y, bx.z, bx.w, p.image_area[img], p.crit, p.min_level, p.max_level);
+    if (lvl >= p.num_levels) lvl = p.num_levels - 1;
+    float scale = p.scale[0];
+#pragma unroll
+    for (int l = 1; l < ROI_MAX_LEVELS; ++l)
+      if (l == lvl) scale = p.scale[l];
+    const float rows = (bx.w - bx.y) * scale + 2.f, taps = (bx.z - bx.x) * scale / (float)p.res + 2.f;
+    const float cost = fmaxf(rows * taps, 1.f);                        // NaN -> 1
+    const int cls = ROI_COL_CLASSES - 1 - ((int)log2f(cost) - 4);      // cost < 32 -> last class, doubling per class
+    return min(max(cls, 0), ROI_COL_CLASSES - 1);
+  };
+  for (int i = threadIdx.x; i < 32 * NC; i += blockDim.x) (&s_cnt[0][0])[i] = 0;
+  __syncthreads();
+  for (int c0 = lo; c0 < hi; c0 += 32) {
+    const int slot = c0 + lane;
+    const int cls = slot < hi ? cost_class(slot) : NC;                 // NC: no slot
+    const unsigned m = __match_any_sync(full, cls);
+    if (cls < NC && lane == __ffs(m) - 1) s_cnt[warp][cls] += __popc(m);
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x < NC) {                               // per class: exclusive prefix over the warps
+    int run = 0;
+    for (int w = 0; w < 32; ++w) { const int c = s_cnt[w][threadIdx.x]; s_cnt[w][threadIdx.x] = run; run += c; }
+    s_base[threadIdx.x] = run;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int k = 0; k < NC; ++k) { const int c = s_base[k]; s_base[k] = run; run += c; }
+  }
+  __syncthreads();
+  for (int c0 = lo; c0 < hi; c0 += 32) {
+    const int slot = c0 + lane;
+    const int cls = slot < hi ? cost_class(slot) : NC;
+    const unsigned m = __match_any_sync(full, cls);
+    if (cls < NC) p.order[s_base[cls] + s_cnt[warp][cls] + __popc(m & ((1u << lane) - 1u))] = slot;
+    __syncwarp();
+    if (cls < NC && lane == __ffs(m) - 1) s_cnt[warp][cls] += __popc(m);
+    __syncwarp();
+  }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(448, 2) roialign_col_kernel(const RoiAlignParams<T> p) {
-  __shared__ float s_w[2][ROI_MAX_RES][ROI_MAXT];       // [axis][bin][tap] merged weights (axis 0 = y)
-  __shared__ int s_start[2][ROI_MAX_RES], s_num[2][ROI_MAX_RES];
-  __shared__ int s_carry[ROI_MAX_RES];                  // per bin row: leading feature rows shared with the bins above
-  __shared__ int s_walk[3];                             // first needed feature row, one past the last, walk usable
-  extern __shared__ __align__(16) unsigned char s_stage[];   // [2 slots][ROI_COL_CELL bytes][threads] cp.async staging
-  const int slot = blockIdx.x;
+__global__ void __launch_bounds__(32, 24) roialign_col_kernel(const RoiAlignParams<T> p) {
+  extern __shared__ __align__(16) unsigned char s_col[];
+  const int res = p.res, c8 = p.out.c >> 3;             // c8 <= 32 lanes walk, all 32 build the tables
+  float* s_wy = reinterpret_cast<float*>(s_col);        // [res][ROI_WYT]
+  float* s_wx = s_wy + res * ROI_WYT;                   // [ROI_MAXT]
+  int* s_ny = reinterpret_cast<int*>(s_wx + ROI_MAXT);  // [res]
+  int* s_carry = s_ny + res;                            // [res]
+  const uint32_t stage = (uint32_t)__cvta_generic_to_shared(s_col) + (roi_col_tables_bytes(res) + 15) / 16 * 16;
+  const int lane = threadIdx.x;
+  // CTAs start in blockIdx order: p.order lists the ROI slots by decreasing column cost (roi_order_kernel), so the long
+  // columns (up to ~90 rows x 6 taps, tens of microseconds for one warp) run first and the short ones fill the tail.
+  // (CTAs of 7 or 14 warps = neighbouring columns sharing taps through L1 were measured too: same time.)
+  const int oi = blockIdx.x / res, pw = blockIdx.x - oi * res;
+  const int slot = p.order[oi];
   const int img = slot / p.r_cap, r = slot - img * p.r_cap;
-  const int res = p.res, c8 = p.out.c >> 3;
-  const int pw = threadIdx.x / c8, cv = threadIdx.x - pw * c8;       // blockDim.x == res * c8
-  T* outp = p.out.at(slot, 0, pw) + cv * 8;
+  T* outp = p.out.at(slot, 0, pw) + lane * 8;
   if (r >= p.det_count[img]) {                          // empty slot: zeros
+    if (lane >= c8) return;
     const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll 1
     for (int ph = 0; ph < res; ++ph, outp += p.out.sh) Vec8<T>::store(outp, z);
@@ -461,7 +557,7 @@ __global__ void __launch_bounds__(448, 2) roialign_col_kernel(const RoiAlignPara
   const float4 bx = reinterpret_cast<const float4*>(p.boxes)[slot];
   int lvl = assign_level(bx.x, bx.y, bx.z, bx.w, p.image_area[img], p.crit, p.min_level, p.max_level);
   if (lvl >= p.num_levels) lvl = p.num_levels - 1;
-  if (p.level_out && threadIdx.x == 0) p.level_out[slot] = lvl;
+  if (p.level_out && lane == 0 && pw == 0) p.level_out[slot] = lvl;
   View<const T> f = p.feat[0];
   float scale = p.scale[0];
 #pragma unroll
@@ -474,65 +570,86 @@ __global__ void __launch_bounds__(448, 2) roialign_col_kernel(const RoiAlignPara
   const int grid_h = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(roi_height / (float)res);
   const int grid_w = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(roi_width / (float)res);
   const float inv_count = 1.0f / fmaxf((float)(grid_h * grid_w), 1.f);
-  const bool merged = grid_h + 2 <= ROI_MAXT && grid_w + 2 <= ROI_MAXT;      // CTA-uniform
   const T* img_base = f.p + (size_t)img * f.sn;
   const int sh32 = (int)f.sh, sw32 = (int)f.sw;
-  if (merged) {
-    roi_build_tables(s_w, s_start, s_num, res, roi_start_h, roi_start_w, bin_h, bin_w, grid_h, grid_w, f.h, f.w);
-    if (threadIdx.x < res) {                             // fold 1 / count into the row weights
-      for (int j = 0; j < s_num[0][threadIdx.x]; ++j) s_w[0][threadIdx.x][j] *= inv_count;
+
+  // ---- tables: lane b < res builds the y weights of bin row b, lane 31 the x weights of this column
+  for (int i = lane; i < res * ROI_WYT + ROI_MAXT; i += 32) s_wy[i] = 0.f;      // s_wx follows s_wy
+  __syncwarp();
+  int t0 = 0, tn = 0;                                   // first feature row / column of "my" bin, rows / columns it spans
+  bool bad = false;
+  {
+    const bool xlane = lane == 31;
+    const bool active = xlane || lane < res;
+    const float start = xlane ? roi_start_w : roi_start_h, bin = xlane ? bin_w : bin_h;
+    const int pb = xlane ? pw : lane, grid = active ? (xlane ? grid_w : grid_h) : 0;
+    const int extent = xlane ? f.w : f.h, cap = xlane ? ROI_MAXT : ROI_WYT;
+    const float wscale = xlane ? 1.f : inv_count;       // 1 / count folded into the y weights
+    float* wrow = xlane ? s_wx : s_wy + lane * ROI_WYT;
+    int s0 = -1;
+    for (int i = 0; i < grid; ++i) {
+      const float v = start + pb * bin + ((float)i + 0.5f) * bin / (float)grid;
+      if (v < -1.0f || v > (float)extent) continue;
+      float vv = v <= 0.f ? 0.f : v;
+      int low = (int)vv, high;
+      if (low >= extent - 1) { high = low = extent - 1; vv = (float)low; } else high = low + 1;
+      const float l = vv - (float)low, h = 1.f - l;
+      if (s0 < 0) s0 = low;
+      if (high - s0 >= cap) { bad = true; break; }
+      wrow[low - s0] += h * wscale;
+      wrow[high - s0] += l * wscale;
+      tn = high - s0 + 1;
     }
-    if (threadIdx.x == blockDim.x - 1) {
-      // which leading rows of a bin are already x-passed by the bins above it (cl = row y_done, cp = row y_done - 1)
-      // the walk needs the rows of the bins to follow each other without a gap (always the case with an adaptive grid)
-      int y_first = 0, y_done = -1, valid = 0, ok = 1;
-      for (int ph = 0; ph < res; ++ph) {
-        const int ny = s_num[0][ph], sy = s_start[0][ph];
-        int c = 0;
-        if (ny > 0) {
-          if (valid > 0) {
-            c = y_done - sy + 1;
-            if (c < 0 || c > valid) ok = 0;              // gap, or a row that is not carried any more: no walk
-          } else {
-            y_first = sy;
-          }
-          const int nnew = ny - min(max(c, 0), ny);      // rows this bin x-passes itself
-          if (nnew > 0) {
-            valid = min(valid + nnew, 2);
-            y_done = sy + ny - 1;
-          }
-        }
-        s_carry[ph] = c;
-      }
-      s_walk[0] = y_first;
-      s_walk[1] = y_done + 1;
-      s_walk[2] = ok;
-    }
-    __syncthreads();
-    if (s_walk[2]) {
-      const int nx = s_num[1][pw];
-      const T* colp = img_base + s_start[1][pw] * sw32 + cv * 8;
-      const uint32_t stage = (uint32_t)__cvta_generic_to_shared(s_stage);
-      const bool done = sw32 == 256 && blockDim.x == ROI_COL_THREADS
-          ? roi_col_dispatch<T, true>(nx, colp, sh32, sw32, s_w[1][pw], s_w[0], s_num[0], s_carry, res, s_walk[0], s_walk[1],
-                                      outp, p.out.sh, stage)
-          : roi_col_dispatch<T, false>(nx, colp, sh32, sw32, s_w[1][pw], s_w[0], s_num[0], s_carry, res, s_walk[0], s_walk[1],
-                                       outp, p.out.sh, stage);
-      if (done) return;
-    }
+    t0 = s0 < 0 ? 0 : s0;
   }
-  // generic column: merged-tap (or sample-loop) evaluation of each bin
+  const unsigned full = 0xffffffffu;
+  const int sx = __shfl_sync(full, t0, 31), nx = __shfl_sync(full, tn, 31);
+  // carry bookkeeping with shuffles: rows of the bins above end at y_done; rows y_done - 1, y_done are in (cp, cl)
+  const bool ybin = lane < res && tn > 0;
+  int pm = ybin ? t0 + tn - 1 : -1;                     // inclusive prefix max of the last row of a bin
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(full, pm, o);
+    if (lane >= o) pm = max(pm, t);
+  }
+  int y_done = __shfl_up_sync(full, pm, 1);
+  if (lane == 0) y_done = -1;
+  int y_first = ybin ? t0 : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) y_first = min(y_first, __shfl_xor_sync(full, y_first, o));
+  int y_end = __shfl_sync(full, pm, 31) + 1;
+  if (y_first == 0x7fffffff) { y_first = 0; y_end = 0; }
+  int c = 0;
+  if (ybin && y_done >= 0) {
+    c = y_done - t0 + 1;
+    if (c < 0 || c > min(2, y_done - y_first + 1)) bad = true;       // gap, or a row that is not carried any more
+  }
+  const bool walk = !__any_sync(full, bad);
+  if (lane < res) { s_ny[lane] = tn; s_carry[lane] = c; }
+  __syncwarp();
+  if (lane >= c8) return;
+
+  if (walk) {
+    if (nx == 0) {                                       // column entirely outside the feature map
+      const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+      for (int ph = 0; ph < res; ++ph, outp += p.out.sh) Vec8<T>::store(outp, z);
+      return;
+    }
+    const T* colp = img_base + sx * sw32 + lane * 8;
+    if (sw32 == 256)
+      roi_col_dispatch<T, 256>(nx, colp, sh32, sw32, s_wx, s_wy, s_ny, s_carry, res, y_first, y_end, outp, p.out.sh, stage);
+    else
+      roi_col_dispatch<T, 0>(nx, colp, sh32, sw32, s_wx, s_wy, s_ny, s_carry, res, y_first, y_end, outp, p.out.sh, stage);
+    return;
+  }
+  // sample loop (torchvision's own order of evaluation) for the bins of this column
 #pragma unroll 1
   for (int ph = 0; ph < res; ++ph, outp += p.out.sh) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (merged)
-      roi_bin_merged<T>(img_base, sh32, sw32, s_w, s_start, s_num, ph, pw, cv, acc);   // row weights carry 1 / count
-    else
-      roialign_sample_loop<T>(f, img, cv, ph, pw, roi_start_h, roi_start_w, bin_h, bin_w, grid_h, grid_w, acc);
-    if (!merged) {
+    roialign_sample_loop<T>(f, img, lane, ph, pw, roi_start_h, roi_start_w, bin_h, bin_w, grid_h, grid_w, acc);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] *= inv_count;
-    }
+    for (int k = 0; k < 8; ++k) acc[k] *= inv_count;
     Vec8<T>::store(outp, acc);
   }
 }
@@ -1206,7 +1323,7 @@ using namespace cm2;
 template <typename T>
 static int roialign_launch(const cm2_act* feats, const int32_t* feat_stride, int num_levels, const float* boxes,
                            const int32_t* det_count, int n, int r_cap, const float* image_area, int crit,
-                           int sampling_ratio, const cm2_act* out, int32_t* level_out, cudaStream_t s) {
+                           int sampling_ratio, const cm2_act* out, int32_t* level_out, void* workspace, cudaStream_t s) {
   RoiAlignParams<T> p;
   for (int l = 0; l < ROI_MAX_LEVELS; ++l) {
     int k = l < num_levels ? l : num_levels - 1;
@@ -1225,14 +1342,10 @@ static int roialign_launch(const cm2_act* feats, const int32_t* feat_stride, int
   const int variant = getenv("CM2_ROIALIGN_VARIANT") ? atoi(getenv("CM2_ROIALIGN_VARIANT")) : 2;
   bool small = true;
   for (int l = 0; l < num_levels; ++l) small = small && feats[l].sn < (1ll << 31);
-  const int col_threads = p.res * (out->c / 8);
-  if (variant == 2 && p.res <= ROI_MAX_RES && small && col_threads <= ROI_COL_THREADS) {
-    static bool attr_set = false;                        // per instantiation (T)
-    if (!attr_set) {
-      cudaFuncSetAttribute(roialign_col_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ROI_COL_CELL * ROI_COL_THREADS);
-      attr_set = true;
-    }
-    roialign_col_kernel<T><<<n * r_cap, col_threads, 2 * ROI_COL_CELL * col_threads, s>>>(p);
+  p.order = reinterpret_cast<int*>(workspace);
+  if (variant == 2 && workspace && p.res < 32 && small && out->c <= 256) {   // lane 31 builds the x table, lanes < res the y table
+    roi_order_kernel<T><<<1, 1024, 0, s>>>(p);
+    roialign_col_kernel<T><<<n * r_cap * p.res, 32, roi_col_smem_bytes(p.res), s>>>(p);
     return 0;
   }
   if (variant >= 1 && p.res <= ROI_MAX_RES && small) {
@@ -1248,7 +1361,7 @@ static int roialign_launch(const cm2_act* feats, const int32_t* feat_stride, int
 extern "C" int cm2_roialign_fpn(const cm2_act* feats, const int32_t* feat_stride, int32_t num_levels, int32_t dtype,
                                 const float* boxes, const int32_t* det_count, int32_t n, int32_t r_cap,
                                 const float* image_area, int32_t crit, int32_t sampling_ratio, const cm2_act* out,
-                                int32_t* level_out, void* stream) {
+                                int32_t* level_out, void* workspace, void* stream) {
   CM2_CHECK_ARG(feats && feat_stride && boxes && det_count && image_area && out && out->data, "roialign: null pointer");
   CM2_CHECK_ARG(num_levels >= 1 && num_levels <= ROI_MAX_LEVELS, "roialign: num_levels %d not in [1,%d]", num_levels,
                 ROI_MAX_LEVELS);
@@ -1268,10 +1381,10 @@ extern "C" int cm2_roialign_fpn(const cm2_act* feats, const int32_t* feat_stride
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == CM2_F32)
     roialign_launch<float>(feats, feat_stride, num_levels, boxes, det_count, n, r_cap, image_area, crit, sampling_ratio,
-                           out, level_out, s);
+                           out, level_out, workspace, s);
   else
     roialign_launch<__nv_bfloat16>(feats, feat_stride, num_levels, boxes, det_count, n, r_cap, image_area, crit,
-                                   sampling_ratio, out, level_out, s);
+                                   sampling_ratio, out, level_out, workspace, s);
   CM2_CHECK_LAUNCH("roialign_fpn");
   return CM2_OK;
 }

@@ -564,7 +564,8 @@ class Engine(object):
         roi = self.fmap("roi_feat", R, res, res, P["in_ch"])
         crit = 0 if mh.ASSIGN_CRITERION == "ratio" else 1
         lib.roialign_fpn([f.view for f in feats], strides, det["boxes"], det["count"], n, r_cap, area, crit,
-                         int(mh.POOLER_SAMPLING_RATIO), roi.view)
+                         int(mh.POOLER_SAMPLING_RATIO), roi.view,
+                         workspace=self.buffer("roi_order", (max(R, 1),), torch.int32, False))
         x = roi
         for k, w in enumerate(P["mask_fcn"]):
             x = self.conv("mask_fcn{}".format(k + 1), [x], w)

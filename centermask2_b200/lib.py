@@ -90,7 +90,7 @@ SYMBOLS = {
     "cm2_fcos_select_workspace": (_L, [_I, _I, _I]),
     "cm2_fcos_select": (_I, [C.POINTER(CandBuffers), _I, _I, _I, C.POINTER(_I), C.POINTER(_I), _I, _I, _F, _I,
                              C.POINTER(DetBuffers), _P, _P]),
-    "cm2_roialign_fpn": (_I, [_AP, C.POINTER(_I), _I, _I, _P, _P, _I, _I, _P, _I, _I, _AP, _P, _P]),
+    "cm2_roialign_fpn": (_I, [_AP, C.POINTER(_I), _I, _I, _P, _P, _I, _I, _P, _I, _I, _AP, _P, _P, _P]),
     "cm2_spatial_attention": (_I, [_AP, _AP, _I, _P, _P]),
     "cm2_mask_predict": (_I, [_AP, _I, _P, _P, _P, _I, _P, _P]),
     "cm2_maskiou_prep": (_I, [_P, _AP, _I, _P]),
@@ -384,14 +384,26 @@ def fcos_select(cand, n, num_levels, cap, level_w, level_stride, ncls, pre_topk,
     _count(2)
 
 
-def roialign_fpn(feats, strides, boxes, det_count, n, r_cap, image_area, crit, sampling_ratio, out, level_out=None):
+_roi_workspace = {}
+
+
+def roialign_fpn(feats, strides, boxes, det_count, n, r_cap, image_area, crit, sampling_ratio, out, level_out=None,
+                 workspace=None):
+    """``workspace``: int32 device tensor of >= n * r_cap elements (the launch order of the column kernel); when omitted
+    one is kept per (device, stream) -- a buffer shared between streams could be overwritten by a concurrent launch."""
     arr = (Act * len(feats))(*[act(f) for f in feats])
     st = (C.c_int32 * len(strides))(*strides)
     o = act(out)
+    if workspace is None:
+        key = (boxes.device, torch.cuda.current_stream().cuda_stream)
+        workspace = _roi_workspace.get(key)
+        if workspace is None or workspace.numel() < n * r_cap:
+            workspace = _roi_workspace[key] = torch.empty((max(n * r_cap, 1024),), dtype=torch.int32, device=boxes.device)
+    assert workspace.dtype == torch.int32 and workspace.numel() >= n * r_cap
     check(load().cm2_roialign_fpn(arr, st, len(feats), dtype_code(feats[0]), ptr(boxes), ptr(det_count), n, r_cap,
-                                  ptr(image_area), crit, sampling_ratio, C.byref(o), ptr(level_out), stream()),
+                                  ptr(image_area), crit, sampling_ratio, C.byref(o), ptr(level_out), ptr(workspace), stream()),
           "cm2_roialign_fpn")
-    _count()
+    _count(2)
 
 
 def spatial_attention(x, out, w18):

@@ -283,11 +283,14 @@ int cm2_fcos_select(const cm2_cand_buffers* cand, int32_t n, int32_t num_levels,
  *   det_count[n] valid ones per image; out is a view [n*r_cap, res, res, c] (invalid slots are
  *   written with zeros).  image_area: device float [n] = h*w of the unpadded image (pooler.py:70-77).
  *   level_out: device int32 [n*r_cap] (may be NULL).
+ *   workspace: device scratch of n*r_cap int32 (contents overwritten: the ROI slots in launch order,
+ *   largest boxes first, for the column-walk kernel); may be NULL, then the slower CTA-per-ROI
+ *   kernel runs.  Results do not depend on it.
  * ------------------------------------------------------------------------------------------- */
 int cm2_roialign_fpn(const cm2_act* feats, const int32_t* feat_stride, int32_t num_levels, int32_t dtype,
                      const float* boxes, const int32_t* det_count, int32_t n, int32_t r_cap,
                      const float* image_area, int32_t crit, int32_t sampling_ratio,
-                     const cm2_act* out, int32_t* level_out, void* stream);
+                     const cm2_act* out, int32_t* level_out, void* workspace, void* stream);
 
 /* SpatialAttention, centermask/sam.py:23-28: x * sigmoid(conv3x3([mean_c x, max_c x])); views
  * [r,s,s,c]; w18 = conv weight [1][2][3][3] flattened (device). */

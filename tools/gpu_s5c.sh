@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python tools/micro_roi.py --knobs ${KNOBS:-0,1,2,3,9,10,11} 2>&1 | tail -12
+timeout 600 python tools/micro_roi.py --variants 2,1 --knobs 0,7,100,107 2>&1 | tail -10

@@ -26,8 +26,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--rois", type=int, default=100)
-    ap.add_argument("--knobs", default="0")
+    ap.add_argument("--knobs", default="0", help="CM2_ROI_KNOB values (tuning experiments; the library ignores it now)")
     ap.add_argument("--variants", default="2,1")
+    ap.add_argument("--sort", action="store_true", help="boxes of the whole batch in descending area order (tail experiment)")
     args = ap.parse_args()
     n, R, dev, c = args.batch, args.rois, "cuda", 256
     hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -43,6 +44,9 @@ def main():
     x0 = torch.rand((n, R), device=dev, generator=g) * (W - bw)
     y0 = torch.rand((n, R), device=dev, generator=g) * (H - bh)
     boxes = torch.stack([x0, y0, x0 + bw, y0 + bh], dim=2).contiguous()
+    if args.sort:       # experiment only: slots of all images in descending area order (the image index of a slot stays)
+        order = torch.argsort((bw * bh).flatten(), descending=True)
+        boxes = boxes.view(-1, 4)[order].view(n, R, 4).contiguous()
     counts = torch.full((n,), R, dtype=torch.int32, device=dev)
     img_area = torch.full((n,), float(H * W), device=dev)
     roi = eng.fmap("mroi", n * R, 14, 14, c)
@@ -55,15 +59,19 @@ def main():
     roialign()
     torch.cuda.synchronize()
     ref = roi.view.float().clone()
-    for v in [int(t) for t in args.variants.split(",")]:
-        os.environ["CM2_ROIALIGN_VARIANT"] = str(v)
-        for k in ([int(t) for t in args.knobs.split(",")] if v == 2 else [0]):
-            os.environ["CM2_ROI_KNOB"] = str(k)
-            roi.view.zero_()
-            ms = timed(roialign)
-            d = (roi.view.float() - ref).abs().max().item()
-            print("variant {} knob {:3d}: {:.4f} ms  {:7.1f} GB/s  {:.3f} of HBM peak   max|diff vs v0| {:.4g}".format(
-                v, k, ms, alg / ms / 1e6, alg / ms / 1e6 / hbm, d))
+    for _ in range(300):                  # bring the clocks up before anything is timed
+        roialign()
+    torch.cuda.synchronize()
+    for rep in range(2):                  # every configuration twice (ABAB) so that drift shows
+        for v in [int(t) for t in args.variants.split(",")]:
+            os.environ["CM2_ROIALIGN_VARIANT"] = str(v)
+            for k in ([int(t) for t in args.knobs.split(",")] if v == 2 else [0]):
+                os.environ["CM2_ROI_KNOB"] = str(k)
+                roi.view.zero_()
+                ms = timed(roialign)
+                d = (roi.view.float() - ref).abs().max().item()
+                print("variant {} knob {:3d}: {:.4f} ms  {:7.1f} GB/s  {:.3f} of HBM peak   max|diff vs v0| {:.4g}".format(
+                    v, k, ms, alg / ms / 1e6, alg / ms / 1e6 / hbm, d))
 
 
 if __name__ == "__main__":
