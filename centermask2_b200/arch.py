@@ -11,25 +11,35 @@ Reference: ``centermask/modeling/backbone/vovnet.py:60-108`` (stage tables), ``:
 """
 from collections import OrderedDict
 
-# (stem widths, 3x3 width per stage, stage output width, 3x3 convs per OSA block, OSA blocks per stage)
+# (stem widths, 3x3 width per stage, stage output width, 3x3 convs per OSA block, OSA blocks per stage, depthwise)
+# vovnet.py:30-108.  Depthwise bodies (vovnet.py:110-130, :284-293): every 3x3 unit except stem_1 is a depthwise 3x3
+# (no norm / ReLU) followed by a pointwise 1x1 -> FrozenBN -> ReLU, and a block whose input width differs from its
+# 3x3 width starts with a 1x1 "reduction" unit.
 VOVNET_BODIES = {
-    "V-19-slim-eSE": ((64, 64, 128), (64, 80, 96, 112), (112, 256, 384, 512), 3, (1, 1, 1, 1)),
-    "V-19-eSE": ((64, 64, 128), (128, 160, 192, 224), (256, 512, 768, 1024), 3, (1, 1, 1, 1)),
-    "V-39-eSE": ((64, 64, 128), (128, 160, 192, 224), (256, 512, 768, 1024), 5, (1, 1, 2, 2)),
-    "V-57-eSE": ((64, 64, 128), (128, 160, 192, 224), (256, 512, 768, 1024), 5, (1, 1, 4, 3)),
-    "V-99-eSE": ((64, 64, 128), (128, 160, 192, 224), (256, 512, 768, 1024), 5, (1, 3, 9, 3)),
+    "V-19-slim-dw-eSE": ((64, 64, 64), (64, 80, 96, 112), (112, 256, 384, 512), 3, (1, 1, 1, 1), True),
+    "V-19-dw-eSE": ((64, 64, 64), (128, 160, 192, 224), (256, 512, 768, 1024), 3, (1, 1, 1, 1), True),
+    "V-19-slim-eSE": ((64, 64, 128), (64, 80, 96, 112), (112, 256, 384, 512), 3, (1, 1, 1, 1), False),
+    "V-19-eSE": ((64, 64, 128), (128, 160, 192, 224), (256, 512, 768, 1024), 3, (1, 1, 1, 1), False),
+    "V-39-eSE": ((64, 64, 128), (128, 160, 192, 224), (256, 512, 768, 1024), 5, (1, 1, 2, 2), False),
+    "V-57-eSE": ((64, 64, 128), (128, 160, 192, 224), (256, 512, 768, 1024), 5, (1, 1, 4, 3), False),
+    "V-99-eSE": ((64, 64, 128), (128, 160, 192, 224), (256, 512, 768, 1024), 5, (1, 3, 9, 3), False),
 }
 
 
 class OSABlock(object):
     """One eSE-OSA block: ``n_conv`` chained 3x3 units, 1x1 aggregation over all of them, eSE gate."""
 
-    def __init__(self, stage, index, in_ch, mid_ch, out_ch, n_conv):
+    def __init__(self, stage, index, in_ch, mid_ch, out_ch, n_conv, dw=False):
         self.stage, self.index = stage, index
         self.name = "OSA{}_{}".format(stage, index)
         self.in_ch, self.mid_ch, self.out_ch, self.n_conv = in_ch, mid_ch, out_ch, n_conv
         self.identity = index > 1          # vovnet.py:363-376: blocks >= 2 add their input
         self.cat_ch = in_ch + n_conv * mid_ch
+        self.dw = dw                       # vovnet.py:284-293: depthwise 3x3 + pointwise 1x1 units
+        self.reduced = dw and in_ch != mid_ch      # vovnet.py:278-283: 1x1 reduction in front of the chain
+
+    def reduction_key(self):
+        return "stage{s}.{n}.conv_reduction.{n}_reduction_0".format(s=self.stage, n=self.name)
 
     def key(self, unit):
         # unit: 0..n_conv-1 for the 3x3 chain, "concat" for the aggregation conv
@@ -44,15 +54,19 @@ class OSABlock(object):
 def vovnet_blocks(body):
     """Stem widths and the flat list of OSA blocks (stage 2..5) of a VoVNetV2 body."""
     if body not in VOVNET_BODIES:
-        raise KeyError("unsupported MODEL.VOVNET.CONV_BODY '{}' (depthwise variants are out of scope)".format(body))
-    stem, mid, out, n_conv, per_stage = VOVNET_BODIES[body]
+        raise KeyError("unsupported MODEL.VOVNET.CONV_BODY '{}'".format(body))
+    stem, mid, out, n_conv, per_stage, dw = VOVNET_BODIES[body]
     blocks = []
     in_ch = stem[2]
     for si in range(4):
         for bi in range(per_stage[si]):
-            blocks.append(OSABlock(si + 2, bi + 1, in_ch if bi == 0 else out[si], mid[si], out[si], n_conv))
+            blocks.append(OSABlock(si + 2, bi + 1, in_ch if bi == 0 else out[si], mid[si], out[si], n_conv, dw))
         in_ch = out[si]
     return stem, blocks
+
+
+def vovnet_is_depthwise(body):
+    return VOVNET_BODIES[body][5]
 
 
 def _conv_bn(spec, prefix, cout, cin, k):
@@ -63,18 +77,39 @@ def _conv_bn(spec, prefix, cout, cin, k):
     spec[prefix + "/norm.running_var"] = ((cout,), "bn_var")
 
 
+def _dw_pw_bn(spec, prefix, cout, cin):
+    # vovnet.py:110-130: Conv2d(cin, cout, 3, groups=cout) needs cin == cout; no norm / ReLU between dw and pw
+    assert cin == cout, (prefix, cin, cout)
+    spec[prefix + "/dw_conv3x3.weight"] = ((cout, 1, 3, 3), "conv_linear")
+    spec[prefix + "/pw_conv1x1.weight"] = ((cout, cin, 1, 1), "conv_relu")
+    spec[prefix + "/pw_norm.weight"] = ((cout,), "bn_weight")
+    spec[prefix + "/pw_norm.bias"] = ((cout,), "bn_bias")
+    spec[prefix + "/pw_norm.running_mean"] = ((cout,), "bn_mean")
+    spec[prefix + "/pw_norm.running_var"] = ((cout,), "bn_var")
+
+
 def backbone_param_spec(cfg):
     """``state_dict`` layout of ``build_fcos_vovnet_fpn_backbone(cfg, ...)`` -> {key: (shape, kind)}."""
     stem, blocks = vovnet_blocks(cfg.MODEL.VOVNET.CONV_BODY)
+    dw = vovnet_is_depthwise(cfg.MODEL.VOVNET.CONV_BODY)
     spec = OrderedDict()
     cin = 3
     for i, c in enumerate(stem):
-        _conv_bn(spec, "bottom_up.stem.stem_{}".format(i + 1), c, cin, 3)
+        if dw and i > 0:                    # vovnet.py:408-411: stem_2 / stem_3 follow the body's conv type
+            _dw_pw_bn(spec, "bottom_up.stem.stem_{}".format(i + 1), c, cin)
+        else:
+            _conv_bn(spec, "bottom_up.stem.stem_{}".format(i + 1), c, cin, 3)
         cin = c
     for b in blocks:
         c = b.in_ch
+        if b.reduced:
+            _conv_bn(spec, "bottom_up." + b.reduction_key(), b.mid_ch, b.in_ch, 1)
+            c = b.mid_ch
         for i in range(b.n_conv):
-            _conv_bn(spec, "bottom_up." + b.key(i), b.mid_ch, c, 3)
+            if b.dw:
+                _dw_pw_bn(spec, "bottom_up." + b.key(i), b.mid_ch, c)
+            else:
+                _conv_bn(spec, "bottom_up." + b.key(i), b.mid_ch, c, 3)
             c = b.mid_ch
         _conv_bn(spec, "bottom_up." + b.key("concat"), b.out_ch, b.cat_ch, 1)
         if b.identity:
@@ -186,11 +221,16 @@ def conv_gflop_per_image(cfg, height, width, rois):
         return (x - 1) // 2 + 1          # 3x3 s2 p1 conv == ceil(x/2); also maxpool3 s2 ceil on even x
 
     stem, blocks = vovnet_blocks(cfg.MODEL.VOVNET.CONV_BODY)
+    dw = vovnet_is_depthwise(cfg.MODEL.VOVNET.CONV_BODY)
+
+    def unit(h, w, cin, cout):            # one 3x3 unit: dense, or depthwise 3x3 + pointwise 1x1
+        return 2.0 * h * w * cin * 9 + conv(h, w, cin, cout, 1) if dw else conv(h, w, cin, cout, 3)
+
     f = 0.0
     h, w = half(height), half(width)
-    f += conv(h, w, 3, stem[0], 3) + conv(h, w, stem[0], stem[1], 3)
+    f += conv(h, w, 3, stem[0], 3) + unit(h, w, stem[0], stem[1])
     h, w = half(h), half(w)
-    f += conv(h, w, stem[1], stem[2], 3)
+    f += unit(h, w, stem[1], stem[2])
     sizes = {}
     stage = 2
     for b in blocks:
@@ -198,8 +238,11 @@ def conv_gflop_per_image(cfg, height, width, rois):
             h, w = -(-(h - 3) // 2) + 1, -(-(w - 3) // 2) + 1
             stage = b.stage
         c = b.in_ch
+        if b.reduced:
+            f += conv(h, w, c, b.mid_ch, 1)
+            c = b.mid_ch
         for _ in range(b.n_conv):
-            f += conv(h, w, c, b.mid_ch, 3)
+            f += unit(h, w, c, b.mid_ch)
             c = b.mid_ch
         f += conv(h, w, b.cat_ch, b.out_ch, 1)
         sizes[b.stage] = (h, w, b.out_ch)

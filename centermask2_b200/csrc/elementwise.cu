@@ -66,6 +66,59 @@ __global__ void maxpool3s2_kernel(View<const T> in, View<T> out) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Depthwise 3x3 convolution, padding 1, stride 1 or 2, no bias (vovnet.py:110-130 "dw_conv3x3": Conv2d(c, c, 3,
+// groups=c); the norm / ReLU follow the pointwise 1x1 that comes next).  HBM-bound: one thread = 8 channels of TWO
+// neighbouring output pixels (the 3x3 windows of a stride-1 pair share 6 of their 12 input vectors), weights
+// [9][c] fp32 read through L1.  fp32 accumulation in tap order (ky, kx), one rounding on store.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int STRIDE>
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(View<const T> in, View<T> out, const float* __restrict__ w) {
+  const int c8 = in.c >> 3, c = in.c;
+  const int wpairs = (out.w + 1) >> 1;
+  const int64_t total = (int64_t)out.n * out.h * wpairs * c8;
+  constexpr int COLS = STRIDE == 1 ? 4 : 5;             // input columns under two neighbouring windows
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % c8);
+    int64_t t = i / c8;
+    const int op = (int)(t % wpairs);
+    t /= wpairs;
+    const int oy = (int)(t % out.h), b = (int)(t / out.h);
+    const int ox = op * 2;
+    float acc0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int y = oy * STRIDE + ky - 1;
+      if (y < 0 || y >= in.h) continue;
+      float wk[3][8];
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * c + cv * 8));
+        const float4 d = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * c + cv * 8) + 1);
+        wk[kx][0] = a.x; wk[kx][1] = a.y; wk[kx][2] = a.z; wk[kx][3] = a.w;
+        wk[kx][4] = d.x; wk[kx][5] = d.y; wk[kx][6] = d.z; wk[kx][7] = d.w;
+      }
+#pragma unroll
+      for (int j = 0; j < COLS; ++j) {
+        const int x = ox * STRIDE + j - 1;
+        if (x < 0 || x >= in.w) continue;
+        float v[8];
+        Vec8<T>::load(in.at(b, y, x) + cv * 8, v);
+        if (j < 3) {                                      // window of output pixel ox: columns 0..2
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc0[k] = fmaf(v[k], wk[j][k], acc0[k]);
+        }
+        if (j >= STRIDE) {                                // window of output pixel ox + 1: columns STRIDE..STRIDE+2
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc1[k] = fmaf(v[k], wk[j - STRIDE][k], acc1[k]);
+        }
+      }
+    }
+    Vec8<T>::store(out.at(b, oy, ox) + cv * 8, acc0);
+    if (ox + 1 < out.w) Vec8<T>::store(out.at(b, oy, ox + 1) + cv * 8, acc1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // eSE
 // ---------------------------------------------------------------------------------------------
 constexpr int ESE_PIX_PER_CHUNK = 256;
@@ -735,6 +788,27 @@ extern "C" int cm2_maxpool3x3s2_ceil(const cm2_act* in, const cm2_act* out, int3
     maxpool3s2_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(make_view<const __nv_bfloat16>(*in),
                                                                         make_view<__nv_bfloat16>(*out));
   CM2_CHECK_LAUNCH("maxpool3x3s2");
+  return CM2_OK;
+}
+
+extern "C" int cm2_dwconv3x3(const cm2_act* in, const cm2_act* out, int32_t dtype, const float* w, int32_t stride,
+                             void* stream) {
+  CM2_CHECK_ARG(in && out && in->data && out->data && w, "dwconv3x3: null pointer");
+  CM2_CHECK_DTYPE(dtype, "dwconv3x3");
+  CM2_CHECK_ARG(stride == 1 || stride == 2, "dwconv3x3: stride %d", stride);
+  CM2_CHECK_ARG(in->n == out->n && in->c == out->c && out->h == (in->h - 1) / stride + 1 && out->w == (in->w - 1) / stride + 1,
+                "dwconv3x3: in [%d,%d,%d,%d] / out [%d,%d,%d,%d] do not match stride %d", in->n, in->h, in->w, in->c, out->n,
+                out->h, out->w, out->c, stride);
+  CM2_CHECK_ARG(vec8_ok(*in, elem_bytes(dtype)) && vec8_ok(*out, elem_bytes(dtype)) && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+                "dwconv3x3: channels / strides must be multiples of 8, weights 16-byte aligned");
+  const int64_t total = (int64_t)out->n * out->h * ((out->w + 1) / 2) * (out->c / 8);
+  if (total == 0) return CM2_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+#define CM2_DW(T, S) dwconv3x3_kernel<T, S><<<grid_for(total, 256), 256, 0, s>>>(make_view<const T>(*in), make_view<T>(*out), w)
+  if (dtype == CM2_F32) { if (stride == 1) CM2_DW(float, 1); else CM2_DW(float, 2); }
+  else { if (stride == 1) CM2_DW(__nv_bfloat16, 1); else CM2_DW(__nv_bfloat16, 2); }
+#undef CM2_DW
+  CM2_CHECK_LAUNCH("dwconv3x3");
   return CM2_OK;
 }
 

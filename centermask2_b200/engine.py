@@ -16,7 +16,7 @@ import os
 import torch
 
 from . import lib, packing
-from .arch import vovnet_blocks
+from .arch import vovnet_is_depthwise, vovnet_blocks
 
 
 class FMap(object):
@@ -217,6 +217,12 @@ class Engine(object):
         lib.conv2d(views, w.w_simt, out.view, w.cout, w.k, w.stride, w.pad, engine=lib.ENGINE_SIMT, **kw)
         return out
 
+    def dw_unit(self, name, x, w9c, pw, stride):
+        """Depthwise 3x3 (stride 1 / 2, no activation) -> pointwise 1x1 + FrozenBN + ReLU, vovnet.py:110-130."""
+        mid = self.fmap(name + "_dw", x.n, (x.h - 1) // stride + 1, (x.w - 1) // stride + 1, x.c)
+        lib.dwconv3x3(x.view, mid.view, w9c, stride)
+        return self.conv(name, [mid], pw)
+
     def segmap(self, name, shapes, c, dtype=None):
         dt = dtype or self.dtype
         return SegMap(shapes, c, dt, self.device, alloc=lambda shape: self.buffer(name, shape, dt))
@@ -238,10 +244,15 @@ class Engine(object):
         """``sd`` keys relative to the backbone module (``bottom_up.*``, ``fpn_*``, ``top_block.*``)."""
         cfg, dt, dev, tc = self.cfg, self.dtype, self.device, self.tc
         stem, blocks = vovnet_blocks(cfg.MODEL.VOVNET.CONV_BODY)
-        P = {"stem": [], "blocks": []}
+        P = {"stem": [], "blocks": [], "reduction": {}}
+        dw = vovnet_is_depthwise(cfg.MODEL.VOVNET.CONV_BODY)
         cin = 3
         for i, (c, s) in enumerate(zip(stem, (2, 1, 2))):
-            P["stem"].append(packing.conv_bn_relu(sd, prefix + "bottom_up.stem.stem_{}".format(i + 1), [cin], s, 1, dt, dev, tc))
+            k = prefix + "bottom_up.stem.stem_{}".format(i + 1)
+            if dw and i > 0:                                   # vovnet.py:408-411: (depthwise weights, pointwise unit, stride)
+                P["stem"].append(packing.dw_pw_bn_relu(sd, k, c, dt, dev, tc) + (s,))
+            else:
+                P["stem"].append(packing.conv_bn_relu(sd, k, [cin], s, 1, dt, dev, tc))
             cin = c
         if tc:
             # stem_1 as a 1x1 conv over the fused normalise+im2col input (cm2_preprocess_im2col): K = 27 -> 32
@@ -255,8 +266,14 @@ class Engine(object):
         for b in blocks:
             convs = []
             c = b.in_ch
+            if b.reduced:                                      # vovnet.py:278-283
+                P["reduction"][b.name] = packing.conv_bn_relu(sd, prefix + "bottom_up." + b.reduction_key(), [c], 1, 0, dt, dev, tc)
+                c = b.mid_ch
             for i in range(b.n_conv):
-                convs.append(packing.conv_bn_relu(sd, prefix + "bottom_up." + b.key(i), [c], 1, 1, dt, dev, tc))
+                if b.dw:
+                    convs.append(packing.dw_pw_bn_relu(sd, prefix + "bottom_up." + b.key(i), c, dt, dev, tc))
+                else:
+                    convs.append(packing.conv_bn_relu(sd, prefix + "bottom_up." + b.key(i), [c], 1, 1, dt, dev, tc))
                 c = b.mid_ch
             cat = packing.conv_bn_relu(sd, prefix + "bottom_up." + b.key("concat"), [b.in_ch] + [b.mid_ch] * b.n_conv, 1, 0, dt, dev, tc)
             ek = prefix + "bottom_up." + b.ese_key()
@@ -288,17 +305,22 @@ class Engine(object):
     def run_backbone(self, x, P):
         """x: FMap [N, Hp, Wp, 3] (normalised, padded to /32).  Returns {"p3": FMap, ...}."""
         cfg = self.cfg
-        if self.tc:
-            # tensor-core path: stem_1 = 1x1 over the im2col'd input, stem_2 writes phase planes, stem_3 (stride 2) reads them
-            if x.c == 32:
-                x = self.conv("stem1", [x], P["stem1_im2col"])
-            else:
-                x = self.conv("stem1", [x], P["stem"][0])
+        dw_body = isinstance(P["stem"][1], tuple)
+        if self.tc and x.c == 32:
+            x = self.conv("stem1", [x], P["stem1_im2col"])      # stem_1 = 1x1 over the im2col'd input
+        else:
+            x = self.conv("stem1", [x], P["stem"][0])
+        if dw_body:
+            for i in (1, 2):
+                w9c, pw, stride = P["stem"][i]
+                x = self.dw_unit("stem{}".format(i + 1), x, w9c, pw, stride)
+        elif self.tc:
+            # tensor-core path: stem_2 writes phase planes, stem_3 (stride 2) reads them
             x = self.conv("stem2", [x], P["stem"][1], out_mode=2)
             x = self.conv("stem3", [x], P["stem"][2])
         else:
-            for i, w in enumerate(P["stem"]):
-                x = self.conv("stem{}".format(i + 1), [x], w)
+            for i in (1, 2):
+                x = self.conv("stem{}".format(i + 1), [x], P["stem"][i])
         stage = 2
         stage_out = {}
         blocks = P["blocks"]
@@ -318,8 +340,13 @@ class Engine(object):
             identity = x
             feats = [x]
             y = x
+            if b.reduced:
+                y = self.conv(b.name + "_reduction", [y], P["reduction"][b.name])
             for i, w in enumerate(convs):
-                y = self.conv("{}_{}".format(b.name, i), [y], w)
+                if b.dw:
+                    y = self.dw_unit("{}_{}".format(b.name, i), y, w[0], w[1], 1)
+                else:
+                    y = self.conv("{}_{}".format(b.name, i), [y], w)
                 feats.append(y)
             n, c = x.n, cat.cout
             gate = self.buffer(b.name + "_gate", (n, c), torch.float32, zero=False)

@@ -73,6 +73,7 @@ SYMBOLS = {
     "cm2_rle_write": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "cm2_phase_split": (_I, [_AP, _AP, _I, _I, _P]),
     "cm2_maxpool3x3s2_ceil": (_I, [_AP, _AP, _I, _P]),
+    "cm2_dwconv3x3": (_I, [_AP, _AP, _I, _P, _I, _P]),
     "cm2_ese_pool_chunks": (_I, [_I]),
     "cm2_ese_pool": (_I, [_AP, _I, _P, _P, _P]),
     "cm2_ese_gate": (_I, [_P, _F, _P, _P, _P, _I, _I, _P]),
@@ -276,6 +277,12 @@ def phase_split(x, out_plane0, relu=False):
 def maxpool3x3s2_ceil(x, out):
     a, b = act(x), act(out)
     check(load().cm2_maxpool3x3s2_ceil(C.byref(a), C.byref(b), dtype_code(x), stream()), "cm2_maxpool3x3s2_ceil")
+    _count()
+
+
+def dwconv3x3(x, out, w9c, stride):
+    a, b = act(x), act(out)
+    check(load().cm2_dwconv3x3(C.byref(a), C.byref(b), dtype_code(x), ptr(w9c), stride, stream()), "cm2_dwconv3x3")
     _count()
 
 

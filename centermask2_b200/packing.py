@@ -57,6 +57,18 @@ def conv_bn_relu(sd, prefix, src_c, stride, pad, dtype, device, tc):
     return ConvW(sd[prefix + "/conv.weight"], src_c, stride, pad, scale, shift, True, dtype, device, tc)
 
 
+def dw_pw_bn_relu(sd, prefix, c, dtype, device, tc):
+    """Depthwise unit, vovnet.py:110-130: (depthwise 3x3 weights as fp32 [9][c] for cm2_dwconv3x3, pointwise 1x1 ->
+    FrozenBN -> ReLU as a ConvW).  The depthwise weights stay fp32 in every precision (c * 9 values)."""
+    wd = sd[prefix + "/dw_conv3x3.weight"].detach().to(torch.float32)          # [c, 1, 3, 3]
+    assert tuple(wd.shape) == (c, 1, 3, 3), (prefix, tuple(wd.shape))
+    w9c = wd.reshape(c, 9).t().contiguous().to(device=device)
+    scale, shift = fold_frozen_bn(sd[prefix + "/pw_norm.weight"], sd[prefix + "/pw_norm.bias"],
+                                  sd[prefix + "/pw_norm.running_mean"], sd[prefix + "/pw_norm.running_var"])
+    pw = ConvW(sd[prefix + "/pw_conv1x1.weight"], [c], 1, 0, scale, shift, True, dtype, device, tc)
+    return w9c, pw
+
+
 def conv_bias(sd, prefix, src_c, stride, pad, relu, dtype, device, tc):
     """conv with bias (no norm), optional ReLU."""
     return ConvW(sd[prefix + ".weight"], src_c, stride, pad, None, sd[prefix + ".bias"], relu, dtype, device, tc)

@@ -171,6 +171,12 @@ int cm2_preprocess_im2col_batch(const void* const* imgs, const int32_t* hs, cons
                                 int32_t hp, int32_t wp, const float* mean3, const float* std3, const cm2_act* out,
                                 int32_t out_index0, void* stream);
 
+/* Depthwise 3x3 convolution, padding 1, stride 1 or 2, no bias: the "dw_conv3x3" half of the depthwise bodies'
+ * units (vovnet.py:110-130, Conv2d(c, c, 3, groups=c)); the pointwise 1x1 + FrozenBN + ReLU that follows is a
+ * cm2_conv_nhwc call.  w: device fp32 [9][c] (tap-major: w[(ky*3+kx)*c + ch] = weight[ch][0][ky][kx]).
+ * out extent = ((h-1)/stride+1, (w-1)/stride+1). */
+int cm2_dwconv3x3(const cm2_act* in, const cm2_act* out, int32_t dtype, const float* w, int32_t stride, void* stream);
+
 /* MaxPool2d(3, stride 2, ceil_mode=True), vovnet.py:349-350. */
 int cm2_maxpool3x3s2_ceil(const cm2_act* in, const cm2_act* out, int32_t dtype, void* stream);
 

@@ -10,6 +10,8 @@ CASES = {
     "v19_crowded": (["MODEL.VOVNET.CONV_BODY", "V-19-eSE", "MODEL.FCOS.POST_NMS_TOPK_TEST", 100],
                     [(128, 128)], 15, 25, 3000),
     "v99_one_image": (["MODEL.VOVNET.CONV_BODY", "V-99-eSE"], [(64, 96)], 16, 26, 300),
+    # depthwise body (vovnet.py:30-38, :110-130): dw 3x3 + pw 1x1 units, 1x1 reduction in stages 3-5, stem 64/64/64
+    "v19_slim_dw": (["MODEL.VOVNET.CONV_BODY", "V-19-slim-dw-eSE"], [(96, 128), (72, 100)], 17, 27, 300),
 }
 
 

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY -- generate ``tests/golden/*.pt`` by running the UNMODIFIED reference.
 
-Run in the build container (needs ``/root/reference``):  ``python -m oracle.gen_golden``
+Run in the build container (needs ``/root/reference``):  ``python -m oracle.gen_golden [case ...]``
 
 For each case in ``oracle/cases.py``: build seeded synthetic weights (``centermask2_b200.synth``),
 calibrate ``cls_logits.bias`` so that a useful number of candidates survives the 0.05 threshold,
@@ -61,7 +61,10 @@ def fields_to_dict(inst):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    only = sys.argv[1:]                   # optional case names; default: all
     for name in CASES:
+        if only and name not in only:
+            continue
         cfg, sd, inputs, target = build_case(name)
         bias = calibrate(cfg, sd, inputs, target)
         model = refrun.build_reference_model(cfg, sd)

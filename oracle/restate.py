@@ -21,7 +21,7 @@ import torch
 import torch.nn.functional as F
 import torchvision
 
-from centermask2_b200.arch import vovnet_blocks          # static layer tables only (no compute)
+from centermask2_b200.arch import vovnet_blocks, vovnet_is_depthwise          # static layer tables only (no compute)
 
 BN_EPS = 1e-5
 
@@ -64,6 +64,16 @@ def _conv_bn_relu(x, sd, prefix, stride, pad):
     return _q(F.relu(x))
 
 
+def _dw_pw_bn_relu(x, sd, prefix, stride):
+    """depthwise 3x3 (groups = channels, no bias / norm / ReLU) -> pointwise 1x1 -> FrozenBN -> ReLU.
+    modeling/backbone/vovnet.py:110-130 ("dw_conv3x3")."""
+    x = _q(F.conv2d(x, sd[prefix + "/dw_conv3x3.weight"], None, stride, 1, 1, x.shape[1]))
+    x = F.conv2d(x, _q(sd[prefix + "/pw_conv1x1.weight"]))
+    x = F.batch_norm(x, sd[prefix + "/pw_norm.running_mean"], sd[prefix + "/pw_norm.running_var"],
+                     sd[prefix + "/pw_norm.weight"], sd[prefix + "/pw_norm.bias"], False, 0.0, BN_EPS)
+    return _q(F.relu(x))
+
+
 def _ese(x, sd, prefix):
     """eSE gate: x * relu6(fc(mean_hw(x)) + 3) / 6.  vovnet.py:238-260."""
     g = F.adaptive_avg_pool2d(x, 1)
@@ -75,9 +85,14 @@ def _ese(x, sd, prefix):
 def vovnet_forward(x, sd, cfg, prefix="backbone.bottom_up.", trace=None):
     """VoVNet.forward (vovnet.py:471-481) with _OSA_stage (:335-376) and _OSA_module.forward (:310-332)."""
     stem, blocks = vovnet_blocks(cfg.MODEL.VOVNET.CONV_BODY)
+    dw = vovnet_is_depthwise(cfg.MODEL.VOVNET.CONV_BODY)            # vovnet.py:408: conv_type of stem_2 / stem_3
     x = _conv_bn_relu(x, sd, prefix + "stem.stem_1", 2, 1)          # vovnet.py:409
-    x = _conv_bn_relu(x, sd, prefix + "stem.stem_2", 1, 1)          # :410
-    x = _conv_bn_relu(x, sd, prefix + "stem.stem_3", 2, 1)          # :411
+    if dw:
+        x = _dw_pw_bn_relu(x, sd, prefix + "stem.stem_2", 1)        # :410
+        x = _dw_pw_bn_relu(x, sd, prefix + "stem.stem_3", 2)        # :411
+    else:
+        x = _conv_bn_relu(x, sd, prefix + "stem.stem_2", 1, 1)      # :410
+        x = _conv_bn_relu(x, sd, prefix + "stem.stem_3", 2, 1)      # :411
     if trace is not None:
         trace["stem"] = x
     outs = {}
@@ -90,8 +105,10 @@ def vovnet_forward(x, sd, cfg, prefix="backbone.bottom_up.", trace=None):
         identity = x
         feats = [x]
         y = x
+        if b.reduced:                                                  # :315-316 (the concat still takes the input x)
+            y = _conv_bn_relu(y, sd, prefix + b.reduction_key(), 1, 0)
         for i in range(b.n_conv):
-            y = _conv_bn_relu(y, sd, prefix + b.key(i), 1, 1)
+            y = _dw_pw_bn_relu(y, sd, prefix + b.key(i), 1) if b.dw else _conv_bn_relu(y, sd, prefix + b.key(i), 1, 1)
             feats.append(y)
         y = torch.cat(feats, dim=1)                                    # :324
         y = _conv_bn_relu(y, sd, prefix + b.key("concat"), 1, 0)        # :325

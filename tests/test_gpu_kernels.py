@@ -161,6 +161,27 @@ def test_preprocess_u8_and_f32():
         assert nchw(out.view)[0].min() == 1                                     # other batch slot untouched
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("stride,h,w,c,n", [(1, 13, 17, 64, 2), (2, 13, 17, 64, 2), (2, 12, 16, 80, 1), (1, 1, 1, 8, 1), (1, 5, 2, 112, 3)])
+def test_dwconv3x3_matches_grouped_conv2d(stride, h, w, c, n, dtype):
+    """Depthwise 3x3 of the dw bodies (vovnet.py:110-130) against F.conv2d(groups=c) on halo and dense views."""
+    g = torch.Generator().manual_seed(31 + stride + h)
+    x = torch.randn(n, c, h, w, generator=g)
+    wt = torch.randn(c, 1, 3, 3, generator=g) * 0.3
+    if dtype == torch.bfloat16:
+        x = x.to(torch.bfloat16).float()
+    ref = F.conv2d(x, wt, None, stride, 1, 1, c)
+    w9c = wt.reshape(c, 9).t().contiguous().to(DEV)
+    out = halo(torch.full_like(ref, 7.0), dtype)
+    lib.dwconv3x3(halo(x, dtype).view, out.view, w9c, stride)
+    torch.cuda.synchronize()
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert torch.allclose(nchw(out.view), ref, rtol=tol, atol=tol)
+    assert out.buf[:, 0].abs().max() == 0 and out.buf[:, :, 0].abs().max() == 0          # halo untouched
+    with pytest.raises(RuntimeError):
+        lib.dwconv3x3(halo(x, dtype).view, out.view, w9c, 3)
+
+
 def _random_boxes(g, n, w, h):
     cx, cy = torch.rand(n, generator=g) * w, torch.rand(n, generator=g) * h
     bw, bh = torch.rand(n, generator=g) * w * 0.5 + 2, torch.rand(n, generator=g) * h * 0.5 + 2
