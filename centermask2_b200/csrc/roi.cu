@@ -495,7 +495,8 @@ __global__ void __launch_bounds__(1024) roi_order_kernel(const RoiAlignParams<T>
       if (l == lvl) scale = p.scale[l];
     const float rows = (bx.w - bx.y) * scale + 2.f, taps = (bx.z - bx.x) * scale / (float)p.res + 2.f;
     const float cost = fmaxf(rows * taps, 1.f);                        // NaN -> 1
-    const int cls = ROI_COL_CLASSES - 1 - ((int)log2f(cost) - 4);      // cost < 32 -> last class, doubling per class
+    // cost < 32 -> last class, doubling per class (2, 3, 4 and 12 classes were measured too: 6 is as good as any)
+    const int cls = ROI_COL_CLASSES - 1 - ((int)log2f(cost) - 4);
     return min(max(cls, 0), ROI_COL_CLASSES - 1);
   };
   for (int i = threadIdx.x; i < 32 * NC; i += blockDim.x) (&s_cnt[0][0])[i] = 0;
@@ -898,6 +899,298 @@ __global__ void __launch_bounds__(1024, 1) spatial_attention_pipe_kernel(View<co
       *reinterpret_cast<uint4*>(out.at(r, y, xx) + cv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
     }
     __syncthreads();                                    // the tile and the maps are free again
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ROIAlign, column walk over a SHARED ROW RING (variant 3, CM2_ROIALIGN_VARIANT=3; NOT the default: it moves a third
+// of the L2 -> SM bytes of variant 2 and runs in the same time, 0.263 vs 0.258 ms at cfg 5 -- with the launch order
+// mixing images both read the feature maps ~2x from DRAM, ~1 GB of DRAM traffic in 0.26 ms).  ncu of the
+// warp-per-column kernel: the L2 -> SM path is the
+// busiest unit (143 M sectors = 4.6 GB at cfg 5, 71 % of the L2 peak) because every column fetches its own copy of the
+// taps it shares with its neighbours and with the bins above.  Here one CTA owns one ROI: a producer warp streams the
+// feature rows of the ROI (one contiguous run of (x_hi - x_lo) pixels per row, NHWC) into a ring of shared-memory slots
+// with cp.async.bulk + mbarriers (full / empty per slot, up to 8 rows ahead), and the 14 column warps run the same walk
+// as roi_col_walk with their taps read from the ring by LDS.128 -- every feature byte crosses L2 -> SM once per ROI.
+// Rows wider than half the ring, pixel strides != c, and irregular ROIs use the direct-load walk / the sample loop.
+// ---------------------------------------------------------------------------------------------
+constexpr int ROI_RING_BYTES = 96 * 1024;
+constexpr int ROI_RING_MAXD = 8;
+constexpr int ROI_RING_COLS = 14;                        // consumer warps (bin columns) per CTA; one more warp produces
+constexpr int ROI_RING_NX = 4;                           // taps per row with the weights in registers (64-register budget)
+
+__device__ __forceinline__ void roi_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// NX > 0: compile-time tap count; NX == 0: run-time count, weights from shared memory.  PB: pixel bytes (0 = run-time).
+template <typename T, int NX, int PB>
+__device__ __forceinline__ void roi_ring_walk(uint32_t ring, uint32_t slot_bytes, int depth, uint32_t bars, uint32_t col_off,
+                                              uint32_t pb_rt, int nx_rt, bool active, const float* __restrict__ wxs,
+                                              const float* __restrict__ wys, const int* __restrict__ ny_s,
+                                              const int* __restrict__ carry_s, int res, T* __restrict__ outp,
+                                              long long out_sh) {
+  constexpr int NXR = NX > 0 ? NX : 1;
+  const uint32_t pb = PB ? PB : pb_rt;
+  const int lane = threadIdx.x & 31;
+  float wx[NXR];
+  if (NX > 0) {
+#pragma unroll
+    for (int k = 0; k < NXR; ++k) wx[k] = wxs[k];
+  }
+  float cl[8], cp[8];                                     // x-passed rows y_done (cl) and y_done - 1 (cp)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) cl[k] = cp[k] = 0.f;
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int ph = 0; ph < res; ++ph, outp += out_sh) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int ny = ny_s[ph];
+    const float* wy = wys + ph * ROI_WYT;                 // already divided by the sample count
+    const int c = carry_s[ph];                            // leading rows of this bin that are x-passed already
+    int j = 0;
+    if (c == 2) {
+      roi_fma8(acc, wy[0], cp);
+      if (ny > 1) roi_fma8(acc, wy[1], cl);
+      j = 2;
+    } else if (c == 1) {
+      roi_fma8(acc, wy[0], cl);
+      j = 1;
+    }
+    for (; j < ny; ++j) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { cp[k] = cl[k]; cl[k] = 0.f; }
+      sam_mbar_wait(bars + slot * 8, phase);              // the row has landed in the slot
+      const uint32_t base = ring + slot * slot_bytes + col_off;
+      if (active) {
+        if (NX > 0) {
+          Raw8<T> raw[NXR];
+#pragma unroll
+          for (int k = 0; k < NXR; ++k) RoiStage<T>::read(base + k * pb, raw[k]);
+#pragma unroll
+          for (int k = 0; k < NXR; ++k) raw[k].fma(wx[k], cl);
+        } else {
+          uint32_t a = base;
+          for (int k = 0; k < nx_rt; ++k, a += pb) {
+            Raw8<T> r0;
+            RoiStage<T>::read(a, r0);
+            r0.fma(wxs[k], cl);
+          }
+        }
+      }
+      __syncwarp();                                       // every lane has its values in registers
+      if (lane == 0) roi_mbar_arrive(bars + (ROI_RING_MAXD + slot) * 8);
+      if (++slot == depth) { slot = 0; phase ^= 1u; }
+      roi_fma8(acc, wy[j], cl);
+    }
+    if (active) Vec8<T>::store(outp, acc);
+  }
+}
+
+template <typename T, int PB>
+__device__ __forceinline__ void roi_ring_dispatch(int nx, uint32_t ring, uint32_t slot_bytes, int depth, uint32_t bars,
+                                                  uint32_t col_off, uint32_t pb_rt, bool active, const float* __restrict__ wxs,
+                                                  const float* __restrict__ wys, const int* __restrict__ ny_s,
+                                                  const int* __restrict__ carry_s, int res, T* __restrict__ outp,
+                                                  long long out_sh) {
+  constexpr int NXMAX = sizeof(T) == 2 ? ROI_RING_NX : 2;
+#define CM2_ROI_RING_CASE(NXV)                                                                                          \
+  case NXV:                                                                                                             \
+    if constexpr (NXV <= NXMAX) {                                                                                       \
+      roi_ring_walk<T, NXV, PB>(ring, slot_bytes, depth, bars, col_off, pb_rt, nx, active, wxs, wys, ny_s, carry_s, res, \
+                                outp, out_sh);                                                                          \
+      return;                                                                                                           \
+    }                                                                                                                   \
+    break;
+  switch (nx) {
+    CM2_ROI_RING_CASE(1) CM2_ROI_RING_CASE(2) CM2_ROI_RING_CASE(3) CM2_ROI_RING_CASE(4)
+    default: break;
+  }
+#undef CM2_ROI_RING_CASE
+  roi_ring_walk<T, 0, PB>(ring, slot_bytes, depth, bars, col_off, pb_rt, nx, active, wxs, wys, ny_s, carry_s, res, outp, out_sh);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32 * (ROI_RING_COLS + 1), 2) roialign_ring_kernel(const RoiAlignParams<T> p) {
+  extern __shared__ __align__(128) unsigned char s_ring[];
+  __shared__ __align__(8) unsigned long long s_bar[2 * ROI_RING_MAXD];       // full[0..7], empty[8..15]
+  __shared__ float s_wy[ROI_MAX_RES * ROI_WYT];
+  __shared__ float s_wx[ROI_RING_COLS][ROI_MAXT];
+  __shared__ int s_ny[ROI_MAX_RES], s_carry[ROI_MAX_RES], s_sx[ROI_RING_COLS], s_nx[ROI_RING_COLS];
+  __shared__ int s_info[3];                             // first needed feature row, one past the last, walk usable
+  const int res = p.res, c8 = p.out.c >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int groups = (res + ROI_RING_COLS - 1) / ROI_RING_COLS;
+  const int oi = blockIdx.x / groups, pw0 = (blockIdx.x - oi * groups) * ROI_RING_COLS;
+  const int ncons = min(ROI_RING_COLS, res - pw0);      // column warps of this CTA
+  const int pw = pw0 + warp;
+  const bool consumer = warp < ncons, active = lane < c8;
+  const int slot = p.order[oi];
+  const int img = slot / p.r_cap, r = slot - img * p.r_cap;
+  T* outp = p.out.at(slot, 0, consumer ? pw : 0) + lane * 8;
+  if (r >= p.det_count[img]) {                          // empty slot: zeros (CTA-uniform)
+    if (!consumer || !active) return;
+    const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+    for (int ph = 0; ph < res; ++ph, outp += p.out.sh) Vec8<T>::store(outp, z);
+    return;
+  }
+  const float4 bx = reinterpret_cast<const float4*>(p.boxes)[slot];
+  int lvl = assign_level(bx.x, bx.y, bx.z, bx.w, p.image_area[img], p.crit, p.min_level, p.max_level);
+  if (lvl >= p.num_levels) lvl = p.num_levels - 1;
+  if (p.level_out && threadIdx.x == 0 && pw0 == 0) p.level_out[slot] = lvl;
+  View<const T> f = p.feat[0];
+  float scale = p.scale[0];
+#pragma unroll
+  for (int l = 1; l < ROI_MAX_LEVELS; ++l)
+    if (l == lvl) { f = p.feat[l]; scale = p.scale[l]; }
+  const float roi_start_w = bx.x * scale - 0.5f, roi_start_h = bx.y * scale - 0.5f;
+  const float roi_end_w = bx.z * scale - 0.5f, roi_end_h = bx.w * scale - 0.5f;
+  const float roi_width = roi_end_w - roi_start_w, roi_height = roi_end_h - roi_start_h;
+  const float bin_h = roi_height / (float)res, bin_w = roi_width / (float)res;
+  const int grid_h = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(roi_height / (float)res);
+  const int grid_w = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(roi_width / (float)res);
+  const float inv_count = 1.0f / fmaxf((float)(grid_h * grid_w), 1.f);
+  const T* img_base = f.p + (size_t)img * f.sn;
+  const int sh32 = (int)f.sh, sw32 = (int)f.sw;
+  const unsigned full = 0xffffffffu;
+
+  // ---- tables: warp 0 builds the y weights (lane = bin row) and the carry bookkeeping, lane 31 of every column warp
+  //      the x weights of its column
+  if (warp == 0)
+    for (int i = lane; i < res * ROI_WYT; i += 32) s_wy[i] = 0.f;
+  if (consumer) s_wx[warp][lane] = 0.f;                 // ROI_MAXT == 32
+  __syncwarp();
+  if (consumer) {
+    int t0 = 0, tn = 0;                                 // first feature row / column of "my" bin, rows / columns it spans
+    bool bad = false;
+    const bool xlane = lane == 31;
+    const bool build = xlane || (warp == 0 && lane < res);
+    const float start = xlane ? roi_start_w : roi_start_h, bin = xlane ? bin_w : bin_h;
+    const int pb = xlane ? pw : lane, grid = build ? (xlane ? grid_w : grid_h) : 0;
+    const int extent = xlane ? f.w : f.h, cap = xlane ? ROI_MAXT : ROI_WYT;
+    const float wscale = xlane ? 1.f : inv_count;       // 1 / count folded into the y weights
+    float* wrow = xlane ? s_wx[warp] : s_wy + lane * ROI_WYT;
+    int s0 = -1;
+    for (int i = 0; i < grid; ++i) {
+      const float v = start + pb * bin + ((float)i + 0.5f) * bin / (float)grid;
+      if (v < -1.0f || v > (float)extent) continue;
+      float vv = v <= 0.f ? 0.f : v;
+      int low = (int)vv, high;
+      if (low >= extent - 1) { high = low = extent - 1; vv = (float)low; } else high = low + 1;
+      const float l = vv - (float)low, h = 1.f - l;
+      if (s0 < 0) s0 = low;
+      if (high - s0 >= cap) { bad = true; break; }
+      wrow[low - s0] += h * wscale;
+      wrow[high - s0] += l * wscale;
+      tn = high - s0 + 1;
+    }
+    t0 = s0 < 0 ? 0 : s0;
+    if (xlane) { s_sx[warp] = t0; s_nx[warp] = bad ? -1 : tn; }
+    if (warp == 0) {
+      // carry bookkeeping with shuffles: rows of the bins above end at y_done; rows y_done - 1, y_done are in (cp, cl)
+      if (xlane) { bad = false; tn = 0; }
+      const bool ybin = lane < res && tn > 0;
+      int pm = ybin ? t0 + tn - 1 : -1;                 // inclusive prefix max of the last row of a bin
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(full, pm, o);
+        if (lane >= o) pm = max(pm, t);
+      }
+      int y_done = __shfl_up_sync(full, pm, 1);
+      if (lane == 0) y_done = -1;
+      int y_first = ybin ? t0 : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) y_first = min(y_first, __shfl_xor_sync(full, y_first, o));
+      int y_end = __shfl_sync(full, pm, 31) + 1;
+      if (y_first == 0x7fffffff) { y_first = 0; y_end = 0; }
+      int c = 0;
+      if (ybin && y_done >= 0) {
+        c = y_done - t0 + 1;
+        if (c < 0 || c > min(2, y_done - y_first + 1)) bad = true;     // gap, or a row that is not carried any more
+      }
+      const bool walk = !__any_sync(full, bad);
+      if (lane < res) { s_ny[lane] = tn; s_carry[lane] = c; }
+      if (lane == 0) { s_info[0] = y_first; s_info[1] = y_end; s_info[2] = walk ? 1 : 0; }
+    }
+  }
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < ROI_RING_MAXD; ++b) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_bar[b])), "r"(1u) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_bar[ROI_RING_MAXD + b])),
+                   "r"((uint32_t)ncons) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int y_first = s_info[0], y_end = s_info[1];
+  int x_lo = 0x7fffffff, x_hi = 0;
+  bool xbad = false;
+  for (int w = 0; w < ncons; ++w) {
+    const int n = s_nx[w], x0 = s_sx[w];
+    if (n < 0) xbad = true;
+    if (n > 0) { x_lo = min(x_lo, x0); x_hi = max(x_hi, x0 + n); }
+  }
+  const int nrows = y_end - y_first;
+  const uint32_t pix_bytes = (uint32_t)f.c * sizeof(T);
+  const bool walk = s_info[2] != 0 && !xbad;
+  const bool none = nrows <= 0 || x_hi <= x_lo;         // nothing inside the feature map: zeros
+  const uint32_t row_bytes = none ? 0u : (uint32_t)(x_hi - x_lo) * pix_bytes;
+  const uint32_t slot_bytes = (row_bytes + 127u) & ~127u;
+  const bool ring_ok = walk && !none && sw32 == f.c && 2u * slot_bytes <= (uint32_t)ROI_RING_BYTES;
+  if (walk && (none || ring_ok)) {
+    const int depth = none ? 1 : min(ROI_RING_MAXD, (int)((uint32_t)ROI_RING_BYTES / slot_bytes));
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_ring), bars = (uint32_t)__cvta_generic_to_shared(s_bar);
+    if (warp == ROI_RING_COLS) {                        // producer
+      if (lane == 0 && !none) {
+        const T* src = img_base + (long long)y_first * sh32 + (long long)x_lo * sw32;
+        int sl = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < nrows; ++t, src += sh32) {
+          if (t >= depth) sam_mbar_wait(bars + (ROI_RING_MAXD + sl) * 8, phase ^ 1u);      // consumers released the slot
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bars + sl * 8), "r"(row_bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       :: "r"(ring + sl * slot_bytes), "l"(src), "r"(row_bytes), "r"(bars + sl * 8) : "memory");
+          if (++sl == depth) { sl = 0; phase ^= 1u; }
+        }
+      }
+      return;
+    }
+    if (!consumer) return;
+    const int nx = none ? 0 : s_nx[warp];
+    const uint32_t col_off = none ? 0u : (uint32_t)(s_sx[warp] - x_lo) * pix_bytes + lane * RoiStage<T>::BYTES;
+    if (none) {
+      if (!active) return;
+      const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+      for (int ph = 0; ph < res; ++ph, outp += p.out.sh) Vec8<T>::store(outp, z);
+      return;
+    }
+    // a column outside the feature map (nx == 0) still consumes every row: the run-time walk with zero taps
+    if (pix_bytes == 512)
+      roi_ring_dispatch<T, 512>(nx, ring, slot_bytes, depth, bars, nx > 0 ? col_off : 0u, pix_bytes, active, s_wx[warp], s_wy, s_ny,
+                                s_carry, res, outp, p.out.sh);
+    else
+      roi_ring_dispatch<T, 0>(nx, ring, slot_bytes, depth, bars, nx > 0 ? col_off : 0u, pix_bytes, active, s_wx[warp], s_wy, s_ny,
+                              s_carry, res, outp, p.out.sh);
+    return;
+  }
+  if (!consumer || !active) return;
+  if (walk) {                                           // rows too wide for the ring / pitched pixels: direct-load walk
+    const int nx = s_nx[warp];
+    const T* colp = img_base + s_sx[warp] * sw32 + lane * 8;
+    roi_col_walk<T, 0, 0>(colp, sh32, sw32, nx, s_wx[warp], s_wy, s_ny, s_carry, res, y_first, y_end, outp, p.out.sh, 0u);
+    return;
+  }
+  // sample loop (torchvision's own order of evaluation) for the bins of this column
+#pragma unroll 1
+  for (int ph = 0; ph < res; ++ph, outp += p.out.sh) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    roialign_sample_loop<T>(f, img, lane, ph, pw, roi_start_h, roi_start_w, bin_h, bin_w, grid_h, grid_w, acc);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] *= inv_count;
+    Vec8<T>::store(outp, acc);
   }
 }
 
@@ -1343,6 +1636,16 @@ static int roialign_launch(const cm2_act* feats, const int32_t* feat_stride, int
   bool small = true;
   for (int l = 0; l < num_levels; ++l) small = small && feats[l].sn < (1ll << 31);
   p.order = reinterpret_cast<int*>(workspace);
+  if (variant == 3 && workspace && p.res < 32 && small && out->c <= 256) {
+    static bool attr_set = false;                        // per instantiation (T)
+    if (!attr_set) {
+      cudaFuncSetAttribute(roialign_ring_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ROI_RING_BYTES);
+      attr_set = true;
+    }
+    roi_order_kernel<T><<<1, 1024, 0, s>>>(p);
+    roialign_ring_kernel<T><<<n * r_cap * ((p.res + ROI_RING_COLS - 1) / ROI_RING_COLS), 32 * (ROI_RING_COLS + 1), ROI_RING_BYTES, s>>>(p);
+    return 0;
+  }
   if (variant == 2 && workspace && p.res < 32 && small && out->c <= 256) {   // lane 31 builds the x table, lanes < res the y table
     roi_order_kernel<T><<<1, 1024, 0, s>>>(p);
     roialign_col_kernel<T><<<n * r_cap * p.res, 32, roi_col_smem_bytes(p.res), s>>>(p);

@@ -191,7 +191,7 @@ def _random_boxes(g, n, w, h):
 # 2: CTA per ROI, column walk (separable, rows carried in registers); 1: CTA per ROI, merged taps;
 # 0: thread per (bin, 8 channels).  c = 256: a warp is one bin column (the production shape), c = 32: columns share warps
 @pytest.mark.parametrize("c", [32, 256])
-@pytest.mark.parametrize("variant", [2, 1, 0])
+@pytest.mark.parametrize("variant", [3, 2, 1, 0])
 def test_roialign_fpn_matches_torchvision_and_reference_level_rule(variant, c, kernel_variant):
     kernel_variant("ROIALIGN", variant)
     g = torch.Generator().manual_seed(7)
@@ -229,7 +229,7 @@ def test_roialign_fpn_matches_torchvision_and_reference_level_rule(variant, c, k
     assert got[r_cap + counts[1]:].abs().max() == 0                  # invalid slots are zeroed
 
 
-@pytest.mark.parametrize("variant", [2, 1, 0])
+@pytest.mark.parametrize("variant", [3, 2, 1, 0])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_roialign_large_rois_separable_path(dtype, variant, kernel_variant):
     kernel_variant("ROIALIGN", variant)

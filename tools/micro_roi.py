@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """ROIAlign-only slice of tools/micro_post.py (same boxes, same features) for tuning sweeps:
 
-    python tools/micro_roi.py [--knobs 0,2,3,10,11] [--variants 2,1]
+    python tools/micro_roi.py [--variants 3,2,1] [--sort]
 
-Prints ms / GB/s over the algorithmic bytes per (variant, CM2_ROI_KNOB) and the deviation of every variant from variant 0.
+Prints ms / GB/s over the algorithmic bytes per CM2_ROIALIGN_VARIANT (every variant twice, ABAB, after a clock warm-up) and
+the deviation of every variant from variant 0.
 """
 import argparse
 import json
@@ -26,7 +27,6 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--rois", type=int, default=100)
-    ap.add_argument("--knobs", default="0", help="CM2_ROI_KNOB values (tuning experiments; the library ignores it now)")
     ap.add_argument("--variants", default="2,1")
     ap.add_argument("--sort", action="store_true", help="boxes of the whole batch in descending area order (tail experiment)")
     args = ap.parse_args()
@@ -65,12 +65,11 @@ def main():
     for rep in range(2):                  # every configuration twice (ABAB) so that drift shows
         for v in [int(t) for t in args.variants.split(",")]:
             os.environ["CM2_ROIALIGN_VARIANT"] = str(v)
-            for k in ([int(t) for t in args.knobs.split(",")] if v == 2 else [0]):
-                os.environ["CM2_ROI_KNOB"] = str(k)
+            for k in [""]:
                 roi.view.zero_()
                 ms = timed(roialign)
                 d = (roi.view.float() - ref).abs().max().item()
-                print("variant {} knob {:3d}: {:.4f} ms  {:7.1f} GB/s  {:.3f} of HBM peak   max|diff vs v0| {:.4g}".format(
+                print("variant {}{}: {:.4f} ms  {:7.1f} GB/s  {:.3f} of HBM peak   max|diff vs v0| {:.4g}".format(
                     v, k, ms, alg / ms / 1e6, alg / ms / 1e6 / hbm, d))
 
 
