@@ -410,7 +410,7 @@ def roialign_fpn(feats, strides, boxes, det_count, n, r_cap, image_area, crit, s
     check(load().cm2_roialign_fpn(arr, st, len(feats), dtype_code(feats[0]), ptr(boxes), ptr(det_count), n, r_cap,
                                   ptr(image_area), crit, sampling_ratio, C.byref(o), ptr(level_out), ptr(workspace), stream()),
           "cm2_roialign_fpn")
-    _count(2)
+    _count(2 if int(os.environ.get("CM2_ROIALIGN_VARIANT", "2")) >= 2 else 1)       # order kernel + ROIAlign kernel
 
 
 def spatial_attention(x, out, w18):
