@@ -287,33 +287,77 @@ __device__ __forceinline__ bool iou_gt(const float4& a, float area_a, const floa
   return ovr > thr;
 }
 
-// grid (n); 1024 threads sort, warp 0 runs the greedy sweep with early exit at post_topk survivors.
+// grid (n); 1024 threads order the candidates of all levels, warp 0 runs the greedy sweep with early exit at post_topk
+// survivors.  MERGE: the per-level lists arrive sorted (fcos_select_level_kernel), so the global order is a multi-way
+// merge: rank = own rank + the number of larger keys in every other level (binary searches), written straight to its
+// place -- ncu of the bitonic version (8192 keys, 91 stages) showed the sort as ~90 % of the kernel's 570 k warp
+// instructions per image.  Same total order (keys are distinct), hence identical results.
+constexpr int NMS_MAX_LEVELS = 8;
+template <bool MERGE>
 __global__ void fcos_nms_image_kernel(SelectWs ws, int num_levels, int pre_topk, int sort_n, const int* level_w,
                                       const int* level_stride, int ncls, float nms_thresh, int post_topk,
                                       cm2_det_buffers det) {
-  extern __shared__ unsigned long long keys[];
+  extern __shared__ unsigned long long keys_all[];      // MERGE: [2][levels * pre_topk], else [sort_n]
   __shared__ float4 kept_box[256];
   __shared__ float kept_area[256];
   __shared__ int kept_cls[256];
   __shared__ int kept_idx[256];
+  __shared__ int s_off[NMS_MAX_LEVELS + 1];
   const int img = blockIdx.x;
   const int total_slots = num_levels * pre_topk;
-  for (int i = threadIdx.x; i < sort_n; i += blockDim.x) {
-    unsigned long long k = 0ull;
-    if (i < total_slots) {
-      int level = i / pre_topk, r = i - level * pre_topk;
-      if (r < ws.kept[img * num_levels + level]) {
-        size_t o = (size_t)(img * num_levels + level) * pre_topk + r;
-        float sc = sqrtf(ws.score[o]);                       // fcos_outputs.py:460
-        // secondary key: earlier (level, rank) first -- deterministic because segments are sorted
-        k = ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned)(0xffffffffu - (unsigned)i);
-        if (k == 0ull) k = 1ull;
-      }
+  unsigned long long* keys = keys_all;
+  auto make_key = [&](int level, int r) {
+    const size_t o = (size_t)(img * num_levels + level) * pre_topk + r;
+    const float sc = sqrtf(ws.score[o]);                   // fcos_outputs.py:460
+    // secondary key: earlier (level, rank) first -- deterministic because segments are sorted
+    unsigned long long k = ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned)(0xffffffffu - (unsigned)(level * pre_topk + r));
+    return k == 0ull ? 1ull : k;
+  };
+  if (MERGE) {
+    if (threadIdx.x == 0) {
+      int run = 0;
+      for (int l = 0; l < num_levels; ++l) { s_off[l] = run; run += ws.kept[img * num_levels + l]; }
+      s_off[num_levels] = run;
     }
-    keys[i] = k;
+    __syncthreads();
+    unsigned long long* lists = keys_all + total_slots;   // level-sorted keys, packed back to back
+    for (int i = threadIdx.x; i < total_slots; i += blockDim.x) {
+      const int level = i / pre_topk, r = i - level * pre_topk;
+      if (r < s_off[level + 1] - s_off[level]) lists[s_off[level] + r] = make_key(level, r);
+      keys[i] = 0ull;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < total_slots; i += blockDim.x) {
+      const int level = i / pre_topk, r = i - level * pre_topk;
+      if (r >= s_off[level + 1] - s_off[level]) continue;
+      const unsigned long long k = lists[s_off[level] + r];
+      int rank = r;
+      for (int l = 0; l < num_levels; ++l) {
+        if (l == level) continue;
+        int lo = s_off[l], hi = s_off[l + 1];              // descending list: count the keys > k
+        const int base = lo;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (lists[mid] > k) lo = mid + 1; else hi = mid;
+        }
+        rank += lo - base;
+      }
+      keys[rank] = k;
+    }
+    __syncthreads();
+  } else {
+    for (int i = threadIdx.x; i < sort_n; i += blockDim.x) {
+      unsigned long long k = 0ull;
+      if (i < total_slots) {
+        int level = i / pre_topk, r = i - level * pre_topk;
+        if (r < ws.kept[img * num_levels + level]) k = make_key(level, r);
+      }
+      keys[i] = k;
+    }
+    __syncthreads();
+    bitonic_sort_desc(keys, sort_n);
   }
-  __syncthreads();
-  bitonic_sort_desc(keys, sort_n);
+  sort_n = MERGE ? total_slots : sort_n;
 
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
@@ -520,14 +564,20 @@ extern "C" int cm2_fcos_select(const cm2_cand_buffers* cand, int32_t n, int32_t 
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(fcos_select_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
-    cudaFuncSetAttribute(fcos_nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    cudaFuncSetAttribute(fcos_nms_image_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    cudaFuncSetAttribute(fcos_nms_image_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
     attr_done = true;
   }
   dim3 g1(num_levels, n);
   fcos_select_level_kernel<<<g1, 1024, (size_t)sort_a * 8, s>>>(*cand, num_levels, cap, pre_topk, sort_a, ws);
   CM2_CHECK_LAUNCH("fcos_select_level");
-  fcos_nms_image_kernel<<<n, 1024, (size_t)sort_b * 8, s>>>(ws, num_levels, pre_topk, sort_b, level_w, level_stride, ncls,
-                                                          nms_thresh, post_topk, *det);
+  const int nms_variant = getenv("CM2_NMS_VARIANT") ? atoi(getenv("CM2_NMS_VARIANT")) : 1;
+  if (nms_variant == 1 && num_levels <= NMS_MAX_LEVELS && 2 * num_levels * pre_topk <= 16384)
+    fcos_nms_image_kernel<true><<<n, 1024, (size_t)2 * num_levels * pre_topk * 8, s>>>(ws, num_levels, pre_topk, sort_b, level_w,
+                                                                                     level_stride, ncls, nms_thresh, post_topk, *det);
+  else
+    fcos_nms_image_kernel<false><<<n, 1024, (size_t)sort_b * 8, s>>>(ws, num_levels, pre_topk, sort_b, level_w, level_stride, ncls,
+                                                                   nms_thresh, post_topk, *det);
   CM2_CHECK_LAUNCH("fcos_nms_image");
   return CM2_OK;
 }

@@ -405,10 +405,12 @@ def _fcos_post_case(g, n, sizes, ncls, target, h0, w0):
     return logits, regs, ctrs, strides
 
 
+@pytest.mark.parametrize("nms_variant", [1, 0])              # 1: multi-way merge of the sorted levels; 0: bitonic sort
 @pytest.mark.parametrize("variant", [1, 0])                  # 1: flat 32 KB tiles; 0: one CTA per image row
 @pytest.mark.parametrize("target,post", [(150, 50), (1500, 100)])
-def test_fcos_postprocess_matches_oracle(target, post, variant, kernel_variant):
+def test_fcos_postprocess_matches_oracle(target, post, variant, nms_variant, kernel_variant):
     kernel_variant("DECODE", variant)
+    kernel_variant("NMS", nms_variant)
     from centermask2_b200.config import get_cfg
     from centermask2_b200.engine import Engine
     g = torch.Generator().manual_seed(10 + target)
@@ -433,3 +435,10 @@ def test_fcos_postprocess_matches_oracle(target, post, variant, kernel_variant):
         assert torch.equal(det["locations"][i, :k].cpu(), ref[i]["locations"])
         assert torch.allclose(det["boxes"][i, :k].cpu(), ref[i]["pred_boxes"], atol=1e-4)
         assert torch.allclose(det["scores"][i, :k].cpu(), ref[i]["scores"], atol=1e-6)
+    if nms_variant == 1:                                          # both orderings keep exactly the same detections
+        first = {k: det[k].clone() for k in ("boxes", "scores", "classes", "locations", "count")}
+        kernel_variant("NMS", 0)
+        det0 = eng.run_fcos_post(head)
+        torch.cuda.synchronize()
+        for k, v in first.items():
+            assert torch.equal(v, det0[k]), k
