@@ -195,6 +195,16 @@ def roi_heads_param_spec(cfg, in_channels):
         spec["maskiou_head.maskiou_fc2.bias"] = ((1024,), "bias")
         spec["maskiou_head.maskiou.weight"] = ((cfg.MODEL.ROI_HEADS.NUM_CLASSES, 1024), "maskiou_out")
         spec["maskiou_head.maskiou.bias"] = ((cfg.MODEL.ROI_HEADS.NUM_CLASSES,), "maskiou_bias")
+    if cfg.MODEL.KEYPOINT_ON:
+        # KRCNNConvDeconvUpsampleHead, keypoint_head.py:168-215
+        kh = cfg.MODEL.ROI_KEYPOINT_HEAD
+        c = in_channels
+        for k, dim in enumerate(kh.CONV_DIMS, 1):
+            spec["keypoint_head.conv_fcn{}.weight".format(k)] = ((dim, c, 3, 3), "conv_relu")
+            spec["keypoint_head.conv_fcn{}.bias".format(k)] = ((dim,), "bias")
+            c = dim
+        spec["keypoint_head.score_lowres.weight"] = ((c, kh.NUM_KEYPOINTS, 4, 4), "kp_deconv")
+        spec["keypoint_head.score_lowres.bias"] = ((kh.NUM_KEYPOINTS,), "bias")
     return spec
 
 

@@ -154,7 +154,11 @@ def _d2_defaults():
                 "POOLER_RESOLUTION": 14,
                 "POOLER_SAMPLING_RATIO": 0,
                 "POOLER_TYPE": "ROIAlignV2",
+                "CONV_DIMS": (512,) * 8,
                 "NUM_KEYPOINTS": 17,
+                "MIN_KEYPOINTS_PER_IMAGE": 1,
+                "NORMALIZE_LOSS_BY_VISIBLE_KEYPOINTS": True,
+                "LOSS_WEIGHT": 1.0,
             },
         },
         "INPUT": {"MIN_SIZE_TEST": 800, "MAX_SIZE_TEST": 1333, "FORMAT": "BGR",

@@ -41,6 +41,9 @@ def _draw(kind, shape, g, key):
         return normal(math.sqrt(1.0 / fan_in))
     if kind == "deconv":          # (Cin, Cout, 2, 2), stride 2: one tap per output pixel
         return normal(math.sqrt(2.0 / shape[0]))
+    if kind == "kp_deconv":       # (Cin, K, 4, 4), stride 2, pad 1: four taps per output pixel.  The synthetic FPN
+        # features are O(70), so the gain is small: logits of O(2-3) spread keep the scores exp(l - max) / sum in fp32 range
+        return normal(0.02 * math.sqrt(4.0 / shape[0]))
     if kind == "bn_weight":
         return uniform(0.5, 1.5)
     if kind == "bn_var":

@@ -12,6 +12,11 @@ CASES = {
     "v99_one_image": (["MODEL.VOVNET.CONV_BODY", "V-99-eSE"], [(64, 96)], 16, 26, 300),
     # depthwise body (vovnet.py:30-38, :110-130): dw 3x3 + pw 1x1 units, 1x1 reduction in stages 3-5, stem 64/64/64
     "v19_slim_dw": (["MODEL.VOVNET.CONV_BODY", "V-19-slim-dw-eSE"], [(96, 128), (72, 100)], 17, 27, 300),
+    # keypoint branch (center_heads.py:358-383,520-553; keypoint_head.py:95-222): narrow tower to keep the case small
+    "v19_keypoints": (["MODEL.VOVNET.CONV_BODY", "V-19-eSE", "MODEL.KEYPOINT_ON", True,
+                       "MODEL.ROI_KEYPOINT_HEAD.IN_FEATURES", ["p3", "p4", "p5"],
+                       "MODEL.ROI_KEYPOINT_HEAD.CONV_DIMS", (128, 128, 64), "MODEL.FCOS.POST_NMS_TOPK_TEST", 20],
+                      [(96, 128), (80, 120)], 18, 28, 300),
 }
 
 

@@ -15,4 +15,7 @@ def detector_postprocess(results, output_height, output_width, mask_threshold=0.
         roi_masks = ROIMasks(results.pred_masks[:, 0, :, :])
         results.pred_masks = roi_masks.to_bitmasks(
             results.pred_boxes, output_height, output_width, mask_threshold).tensor
+    if results.has("pred_keypoints"):
+        results.pred_keypoints[:, :, 0] *= scale_x
+        results.pred_keypoints[:, :, 1] *= scale_y
     return results

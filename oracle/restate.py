@@ -278,19 +278,21 @@ def assign_levels_by_area(boxes, min_level, max_level, canonical_box_size=224, c
     return lv.to(torch.int64) - min_level
 
 
-def roi_pool(features, dets, cfg):
+def roi_pool(features, dets, cfg, head="mask"):
     """ROIPooler.forward eager branch (centermask/pooler.py:320-366); ROIAlign [d2] = torchvision
-    roi_align(output 14, scale 1/stride, sampling_ratio 0, aligned=True)."""
-    names = list(cfg.MODEL.ROI_HEADS.IN_FEATURES)
-    res = cfg.MODEL.ROI_MASK_HEAD.POOLER_RESOLUTION
-    ratio = cfg.MODEL.ROI_MASK_HEAD.POOLER_SAMPLING_RATIO
+    roi_align(output 14, scale 1/stride, sampling_ratio 0, aligned=True).  ``head``: "mask" (center_heads.py:334-356)
+    or "keypoint" (center_heads.py:358-379, its own IN_FEATURES / resolution / criterion)."""
+    hc = cfg.MODEL.ROI_MASK_HEAD if head == "mask" else cfg.MODEL.ROI_KEYPOINT_HEAD
+    names = list(cfg.MODEL.ROI_HEADS.IN_FEATURES if head == "mask" else hc.IN_FEATURES)
+    res = hc.POOLER_RESOLUTION
+    ratio = hc.POOLER_SAMPLING_RATIO
     strides = [2 ** int(n[-1]) for n in names]
     min_l, max_l = int(math.log2(strides[0])), int(math.log2(strides[-1]))
     rois, lvls = [], []
     for i, d in enumerate(dets):
         b = d["pred_boxes"]
         rois.append(torch.cat([torch.full((b.shape[0], 1), float(i)), b], dim=1))
-        if cfg.MODEL.ROI_MASK_HEAD.ASSIGN_CRITERION == "ratio":
+        if hc.ASSIGN_CRITERION == "ratio":
             lvls.append(assign_levels_by_ratio(b, d["image_size"][0] * d["image_size"][1], min_l, max_l))
         else:
             lvls.append(assign_levels_by_area(b, min_l, max_l))
@@ -330,6 +332,58 @@ def maskiou_head_forward(roi_feat, mask, sd, cfg, prefix="roi_heads.maskiou_head
     x = _q(F.relu(F.linear(x, _q(sd[prefix + "maskiou_fc1.weight"]), sd[prefix + "maskiou_fc1.bias"])))
     x = _q(F.relu(F.linear(x, _q(sd[prefix + "maskiou_fc2.weight"]), sd[prefix + "maskiou_fc2.bias"])))
     return F.linear(x, _q(sd[prefix + "maskiou.weight"]), sd[prefix + "maskiou.bias"])
+
+
+def keypoint_head_forward(x, sd, cfg, prefix="roi_heads.keypoint_head."):
+    """KRCNNConvDeconvUpsampleHead.layers (centermask/keypoint_head.py:217-222): conv3x3 + ReLU per CONV_DIMS entry,
+    ConvTranspose2d(k 4, s 2, p 1) to K maps, bilinear x2 (align_corners=False) -> [R, K, 4 * res, 4 * res] logits."""
+    for k in range(len(cfg.MODEL.ROI_KEYPOINT_HEAD.CONV_DIMS)):
+        p = prefix + "conv_fcn{}".format(k + 1)
+        x = _q(F.relu(F.conv2d(x, _q(sd[p + ".weight"]), sd[p + ".bias"], 1, 1)))
+    x = F.conv_transpose2d(x, _q(sd[prefix + "score_lowres.weight"]), sd[prefix + "score_lowres.bias"], stride=2, padding=1)
+    return F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+
+
+def heatmaps_to_keypoints(maps, boxes):
+    """heatmaps_to_keypoints [d2-memory] (detectron2 v0.5 structures/keypoints.py; called at keypoint_head.py:113).
+    maps [R, K, S, S] logits, boxes [R, 4] -> [R, K, 4] = (x, y, logit, score).  Per ROI: bicubic resize
+    (align_corners=False, A = -0.75, torch's upsample_bicubic2d) to (ceil(h), ceil(w)) with h, w clamped to >= 1;
+    first arg-max pixel per map; x = (x_int + 0.5) * w / ceil(w) + x0 (same for y); logit = resized map there;
+    score = exp(logit - max) / sum_{S x S}(exp(map - max)) = 1 / sum_{S x S}(exp(map - max))."""
+    r, k = maps.shape[:2]
+    out = maps.new_zeros((r, k, 4))
+    for i in range(r):
+        x0, y0, x1, y1 = [boxes[i, j] for j in range(4)]
+        w = (x1 - x0).clamp(min=1)
+        h = (y1 - y0).clamp(min=1)
+        wc, hc = w.ceil(), h.ceil()
+        big = F.interpolate(maps[i:i + 1], size=(int(hc), int(wc)), mode="bicubic", align_corners=False)[0]
+        flat = big.reshape(k, -1)
+        mx, pos = flat.max(dim=1)
+        pos = flat.argmax(dim=1)
+        xi = pos % int(wc)
+        yi = (pos - xi) // int(wc)
+        pool = (maps[i] - mx.view(k, 1, 1)).exp().sum(dim=(1, 2))
+        out[i, :, 0] = (xi.float() + 0.5) * (w / wc) + x0
+        out[i, :, 1] = (yi.float() + 0.5) * (h / hc) + y0
+        out[i, :, 2] = mx
+        out[i, :, 3] = (mx - mx).exp() / pool
+    return out
+
+
+def keypoints_forward(features, dets, sd, cfg, trace=None):
+    """CenterROIHeads._forward_keypoint inference branch (center_heads.py:551-553) + keypoint_rcnn_inference
+    (keypoint_head.py:95-120): adds pred_keypoints [R, K, 3] = (x, y, score)."""
+    roi_feat, _ = roi_pool(features, dets, cfg, head="keypoint")
+    logits = keypoint_head_forward(roi_feat, sd, cfg)
+    boxes = torch.cat([d["pred_boxes"] for d in dets])
+    res = heatmaps_to_keypoints(logits, boxes)
+    if trace is not None:
+        trace.update(kp_roi_feat=roi_feat, kp_logits=logits, kp_full=res)
+    counts = [d["pred_classes"].shape[0] for d in dets]
+    for d, kp in zip(dets, res[:, :, [0, 1, 3]].split(counts, dim=0)):
+        d["pred_keypoints"] = kp
+    return dets
 
 
 def roi_heads_forward(features, dets, sd, cfg, trace=None):
@@ -424,6 +478,11 @@ def detector_postprocess(det, out_h, out_w, mask_threshold=0.5):
     for k in ("scores", "pred_classes", "locations", "mask_scores"):
         if k in det:
             out[k] = det[k][keep]
+    if "pred_keypoints" in det:                          # detector_postprocess [d2]: x *= scale_x, y *= scale_y
+        kp = det["pred_keypoints"][keep].clone()
+        kp[:, :, 0] *= sx
+        kp[:, :, 1] *= sy
+        out["pred_keypoints"] = kp
     if "pred_masks" in det:
         out["pred_masks"] = paste_masks(det["pred_masks"][keep][:, 0], out["pred_boxes"], out_h, out_w, mask_threshold)
     return out
@@ -442,6 +501,8 @@ def run_model(batched_inputs, sd, cfg, postprocess=True, pre_topk=True, trace=No
         dets = fcos_postprocess(logits, regs, ctrs, sizes, cfg, pre_topk=pre_topk)
         if cfg.MODEL.MASK_ON:
             dets = roi_heads_forward(feats, dets, sd, cfg, trace=trace)
+        if cfg.MODEL.KEYPOINT_ON:                       # center_heads.py:441-442: masks first, then keypoints
+            dets = keypoints_forward(feats, dets, sd, cfg, trace=trace)
         if not postprocess:
             return dets
         return [detector_postprocess(d, b.get("height", s[0]), b.get("width", s[1]))

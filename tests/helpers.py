@@ -88,3 +88,20 @@ def assert_masks_match(got, ref, what=""):
     area = (a | b).sum(1)
     ok = (iou >= MASK_IOU_MIN) | ((area < 100) & (diff <= 1))
     assert bool(ok.all()), "{}: mask IoU {} (diff px {}, area {})".format(what, iou[~ok].tolist(), diff[~ok].tolist(), area[~ok].tolist())
+
+
+def assert_keypoints_match(got, ref, what="", xy_tol=1e-2, score_rtol=2e-3, max_moved_frac=0.0):
+    """pred_keypoints [R, K, 3] = (x, y, score).  The location is an arg-max over a bicubic-resized map: where two
+    pixels of the resized map are within float rounding of each other the arg-max may legitimately move, so at most
+    ``max_moved_frac`` of the keypoints may differ in location -- and those must still carry the same score (the score
+    is 1 / sum(exp(map - max)), a function of the maximum VALUE only)."""
+    got, ref = got.cpu().float(), ref.float()
+    assert got.shape == ref.shape, "{}: {} vs {}".format(what, tuple(got.shape), tuple(ref.shape))
+    if ref.numel() == 0:
+        return
+    moved = ((got[..., :2] - ref[..., :2]).abs() > xy_tol).any(dim=-1)
+    frac = moved.float().mean().item()
+    assert frac <= max_moved_frac, "{}: {:.2%} of the keypoints moved (max diff {} px)".format(
+        what, frac, (got[..., :2] - ref[..., :2]).abs().max().item())
+    ds = ((got[..., 2] - ref[..., 2]).abs() / ref[..., 2].abs().clamp(min=1e-6)).max().item()
+    assert ds <= score_rtol, "{}: keypoint score relative diff {}".format(what, ds)

@@ -6,7 +6,7 @@ import torch
 from oracle import restate
 from oracle.cases import CASES
 from tests.helpers import (load_golden, build_case, weights_checksum, unpack_masks, mask_iou,
-                           assert_detections_match, MASK_IOU_MIN)
+                           assert_detections_match, assert_keypoints_match, MASK_IOU_MIN)
 
 
 @pytest.fixture(scope="module", params=sorted(CASES))
@@ -41,6 +41,8 @@ def test_raw_detections(case):
     name, gold, cfg, sd, inputs, raw, trace = case
     for i, (g, r) in enumerate(zip(raw, gold["raw"])):
         assert_detections_match(g, r, what="{}[{}]".format(name, i))
+        if "pred_keypoints" in r:                      # keypoint_head.py:95-120 (x, y, score) per keypoint
+            assert_keypoints_match(g["pred_keypoints"], r["pred_keypoints"], what="{}[{}]".format(name, i), score_rtol=1e-4)
         if len(r["scores"]):
             assert torch.allclose(g["pred_masks"], r["pred_masks"], atol=1e-4)
             assert "mask_scores" in g
@@ -54,6 +56,8 @@ def test_postprocessed(case):
     post = [restate.detector_postprocess(d, b["height"], b["width"]) for d, b in zip(raw, inputs)]
     for i, (g, r) in enumerate(zip(post, gold["post"])):
         assert_detections_match(g, r, what="{}[{}] post".format(name, i))
+        if "pred_keypoints" in r:
+            assert_keypoints_match(g["pred_keypoints"], r["pred_keypoints"], what="{}[{}] post".format(name, i), score_rtol=1e-4)
         if len(r["scores"]):
             ref_masks = unpack_masks(r)
             assert g["pred_masks"].shape == ref_masks.shape
