@@ -1,0 +1,133 @@
+// Keypoint decode: the tail of KRCNNConvDeconvUpsampleHead.layers (bilinear x2, keypoint_head.py:221) fused with
+// keypoint_rcnn_inference -> detectron2 heatmaps_to_keypoints [d2] (keypoint_head.py:95-120).
+//
+// One CTA per (keypoint, ROI slot).  The 2res x 2res low-resolution logits of that keypoint are gathered into shared
+// memory, expanded x2 (bilinear) into a 4res x 4res map that also stays in shared memory, and the bicubic resize to
+// the ROI's own ceil(h) x ceil(w) pixels is evaluated on the fly -- the resized maps (up to image size per ROI and
+// keypoint) are never stored.  What leaves the SM is 16 bytes per (ROI, keypoint).
+//
+// Bound: fp32 issue (~60 FMA-pipe instructions + 16 shared loads per resized pixel), not HBM: algorithmic bytes are
+// 4 * (2res)^2 in + 16 out per CTA.
+#include "common.cuh"
+#include "kp_math.cuh"
+
+namespace cm2 {
+
+constexpr int KP_THREADS = 256;
+
+__global__ void __launch_bounds__(KP_THREADS)
+keypoints_decode_kernel(const float* __restrict__ lowres, const float* __restrict__ boxes, const int32_t* __restrict__ count,
+                        int r_cap, int res, int k, float* __restrict__ out) {
+  extern __shared__ float kp_smem[];
+  const int s_low = 2 * res, s_hi = 4 * res;
+  float* low = kp_smem;                       // [s_low][s_low]
+  float* hi = kp_smem + s_low * s_low;        // [s_hi][s_hi]
+  __shared__ float red_v[KP_THREADS / 32];
+  __shared__ long long red_p[KP_THREADS / 32];
+  __shared__ float s_max;
+
+  const int kp = blockIdx.x, slot = blockIdx.y;
+  const int img = slot / r_cap;
+  float* o = out + ((size_t)slot * k + kp) * 4;
+  if (slot - img * r_cap >= count[img]) {     // empty ROI slot: defined output, no work
+    if (threadIdx.x < 4) o[threadIdx.x] = 0.f;
+    return;
+  }
+  for (int i = threadIdx.x; i < s_low * s_low; i += KP_THREADS) {
+    const int y = i / s_low, x = i - y * s_low;
+    low[i] = __ldg(lowres + kp_lowres_offset(slot, y, x, kp, res, k));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < s_hi * s_hi; i += KP_THREADS) {
+    const int y = i / s_hi, x = i - y * s_hi;
+    hi[i] = kp_bilinear_at(low, s_low, y, x);
+  }
+  __syncthreads();
+
+  const float4 b = __ldg(reinterpret_cast<const float4*>(boxes) + slot);
+  const KpRoi roi = kp_roi(b.x, b.y, b.z, b.w);
+  const float scale_y = (float)s_hi / (float)roi.hc, scale_x = (float)s_hi / (float)roi.wc;
+  const long long total = (long long)roi.hc * roi.wc;
+
+  // arg-max of the resized map; first index wins among equal values (torch.argmax on CPU)
+  float best = -INFINITY;
+  long long best_p = 0x7fffffffffffffffLL;
+  if (total <= 0x7fffffffLL) {
+    const unsigned wc = (unsigned)roi.wc;
+    for (unsigned p = threadIdx.x; p < (unsigned)total; p += KP_THREADS) {
+      const unsigned oy = p / wc, ox = p - oy * wc;
+      const KpCubic cy = kp_cubic_taps(scale_y, (int)oy, s_hi);
+      const KpCubic cx = kp_cubic_taps(scale_x, (int)ox, s_hi);
+      const float v = kp_bicubic_at(hi, s_hi, cy, cx);
+      if (v > best) { best = v; best_p = p; }
+    }
+  } else {
+    for (long long p = threadIdx.x; p < total; p += KP_THREADS) {
+      const long long oy = p / roi.wc;
+      const int ox = (int)(p - oy * roi.wc);
+      const KpCubic cy = kp_cubic_taps(scale_y, (int)oy, s_hi);
+      const KpCubic cx = kp_cubic_taps(scale_x, ox, s_hi);
+      const float v = kp_bicubic_at(hi, s_hi, cy, cx);
+      if (v > best) { best = v; best_p = p; }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const float v2 = __shfl_xor_sync(0xffffffffu, best, d);
+    const long long p2 = __shfl_xor_sync(0xffffffffu, best_p, d);
+    if (v2 > best || (v2 == best && p2 < best_p)) { best = v2; best_p = p2; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red_v[warp] = best; red_p[warp] = best_p; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < KP_THREADS / 32; ++w)
+      if (red_v[w] > best || (red_v[w] == best && red_p[w] < best_p)) { best = red_v[w]; best_p = red_p[w]; }
+    red_p[0] = best_p;
+    s_max = best;
+  }
+  __syncthreads();
+  const float mx = s_max;
+  best_p = red_p[0];
+
+  // score = exp(logit - max) / sum over the pool-resolution map of exp(map - max), logit == max
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < s_hi * s_hi; i += KP_THREADS) acc += expf(hi[i] - mx);
+  acc = warp_sum(acc);
+  __syncthreads();                             // red_v is reused
+  if (lane == 0) red_v[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float pool = 0.f;
+    for (int w = 0; w < KP_THREADS / 32; ++w) pool += red_v[w];
+    if (best_p == 0x7fffffffffffffffLL) best_p = 0;          // all-NaN map: torch would also return some index
+    const long long y_int = best_p / roi.wc;
+    const int x_int = (int)(best_p - y_int * roi.wc);
+    // separate multiply and add, as the reference's tensor expressions do (no contraction)
+    o[0] = __fadd_rn(__fmul_rn((float)x_int + 0.5f, __fdiv_rn(roi.w, (float)roi.wc)), roi.x0);
+    o[1] = __fadd_rn(__fmul_rn((float)y_int + 0.5f, __fdiv_rn(roi.h, (float)roi.hc)), roi.y0);
+    o[2] = mx;
+    o[3] = __fdiv_rn(1.0f, pool);
+  }
+}
+
+}  // namespace cm2
+
+using namespace cm2;
+
+extern "C" int cm2_keypoints_decode(const float* lowres, const float* boxes, const int32_t* det_count, int32_t n,
+                                    int32_t r_cap, int32_t res, int32_t num_keypoints, float* out, void* stream) {
+  CM2_CHECK_ARG(lowres && boxes && det_count && out, "keypoints_decode: null pointer");
+  CM2_CHECK_ARG(n >= 0 && r_cap > 0 && num_keypoints > 0, "keypoints_decode: bad extents n=%d r_cap=%d k=%d", n, r_cap,
+                num_keypoints);
+  CM2_CHECK_ARG((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "keypoints_decode: boxes must be 16-byte aligned");
+  CM2_CHECK_ARG(res > 0 && res <= 24, "keypoints_decode: pooler resolution %d not in [1, 24]", res);
+  CM2_CHECK_ARG((long long)n * r_cap <= 65535, "keypoints_decode: %lld ROI slots exceed the grid limit", (long long)n * r_cap);
+  if (n == 0) return CM2_OK;
+  const size_t smem = (size_t)20 * res * res * sizeof(float);           // (2res)^2 + (4res)^2 floats
+  dim3 grid(num_keypoints, n * r_cap);
+  keypoints_decode_kernel<<<grid, KP_THREADS, smem, (cudaStream_t)stream>>>(lowres, boxes, det_count, r_cap, res,
+                                                                           num_keypoints, out);
+  CM2_CHECK_LAUNCH("keypoints_decode");
+  return CM2_OK;
+}

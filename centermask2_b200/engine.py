@@ -542,6 +542,18 @@ class Engine(object):
     def pack_roi_heads(self, sd, prefix=""):
         cfg, dt, dev, tc = self.cfg, self.dtype, self.device, self.tc
         P = {}
+        if cfg.MODEL.KEYPOINT_ON:
+            # KRCNNConvDeconvUpsampleHead, keypoint_head.py:168-215
+            kh = cfg.MODEL.ROI_KEYPOINT_HEAD
+            c = sd[prefix + "keypoint_head.conv_fcn1.weight"].shape[1] if len(kh.CONV_DIMS) else sd[prefix + "keypoint_head.score_lowres.weight"].shape[0]
+            P["kp_in_ch"] = c
+            P["kp_fcn"] = []
+            for k, dim in enumerate(kh.CONV_DIMS, 1):
+                P["kp_fcn"].append(packing.conv_bias(sd, prefix + "keypoint_head.conv_fcn{}".format(k), [c], 1, 1, True, dt, dev, tc))
+                c = dim
+            P["kp_deconv"] = packing.deconv4x4s2(sd, prefix + "keypoint_head.score_lowres", dt, dev, tc)
+        if not cfg.MODEL.MASK_ON:
+            return P
         mh = cfg.MODEL.ROI_MASK_HEAD
         c = sd[prefix + "mask_head.mask_fcn1.weight"].shape[1] if mh.NUM_CONV > 0 else sd[prefix + "mask_head.deconv.weight"].shape[0]
         P["in_ch"] = c
@@ -628,6 +640,30 @@ class Engine(object):
             mask_scores = self.buffer("mask_scores", (R,), torch.float32, False)
             lib.maskiou_score(y.buf, R, y.c, classes, det["scores"].reshape(-1), mask_scores)
         return probs, mask_scores
+
+    def run_keypoint_head(self, feats, strides, det, image_sizes, P):
+        """center_heads.py:551-553 + keypoint_head.py:95-120 on fixed-size ROI slots.  feats: list of FMap
+        (ROI_KEYPOINT_HEAD.IN_FEATURES).  Returns f32 [N, R, K, 4] = (x, y, logit, score); pred_keypoints = [..., (0, 1, 3)]."""
+        cfg = self.cfg
+        kh = cfg.MODEL.ROI_KEYPOINT_HEAD
+        n, r_cap = det["boxes"].shape[0], det["boxes"].shape[1]
+        R = n * r_cap
+        res, nk = kh.POOLER_RESOLUTION, kh.NUM_KEYPOINTS
+        key = ("img_area", tuple(image_sizes))
+        if key not in self._bufs:
+            self._bufs[key] = torch.tensor([float(h * w) for h, w in image_sizes], dtype=torch.float32, device=self.device)
+        roi = self.fmap("kp_roi_feat", R, res, res, P["kp_in_ch"])
+        lib.roialign_fpn([f.view for f in feats], strides, det["boxes"], det["count"], n, r_cap, self._bufs[key],
+                         0 if kh.ASSIGN_CRITERION == "ratio" else 1, int(kh.POOLER_SAMPLING_RATIO), roi.view,
+                         workspace=self.buffer("kp_roi_order", (max(R, 1),), torch.int32, False))
+        x = roi
+        for k, w in enumerate(P["kp_fcn"]):
+            x = self.conv("kp_fcn{}".format(k + 1), [x], w)
+        # score_lowres as a 3x3 conv to 4 * K phase columns, fp32 out (logits are not rounded to bf16)
+        low = self.conv("kp_score_lowres", [x], P["kp_deconv"], out_dtype=torch.float32, out_halo=0)
+        out = self.buffer("kp_out", (n, r_cap, nk, 4), torch.float32, False)
+        lib.keypoints_decode(low.buf, det["boxes"], det["count"], n, r_cap, res, nk, out)
+        return out
 
     # =============================================================================================
     # input / output side

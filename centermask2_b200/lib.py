@@ -96,6 +96,7 @@ SYMBOLS = {
     "cm2_mask_predict": (_I, [_AP, _I, _P, _P, _P, _I, _P, _P]),
     "cm2_maskiou_prep": (_I, [_P, _AP, _I, _P]),
     "cm2_maskiou_score": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
+    "cm2_keypoints_decode": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "cm2_scale_clip_boxes": (_I, [_P, _P, _P, _I, _F, _F, _F, _F, _P]),
     "cm2_scale_clip_boxes_batch": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "cm2_paste_masks": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
@@ -435,6 +436,15 @@ def maskiou_prep(probs, out):
 def maskiou_score(iou, r, ncls, classes, scores, mask_scores):
     check(load().cm2_maskiou_score(ptr(iou), dtype_code(iou), r, ncls, ptr(classes), ptr(scores), ptr(mask_scores),
                                    stream()), "cm2_maskiou_score")
+    _count()
+
+
+def keypoints_decode(lowres, boxes, det_count, n, r_cap, res, num_keypoints, out):
+    """lowres f32 [n*r_cap, res, res, 4*k] (phase layout), boxes f32 [n, r_cap, 4] -> out f32 [n*r_cap, k, 4]."""
+    assert lowres.dtype == torch.float32 and lowres.is_contiguous() and lowres.numel() == n * r_cap * res * res * 4 * num_keypoints
+    assert boxes.dtype == torch.float32 and boxes.is_contiguous() and out.dtype == torch.float32 and out.is_contiguous()
+    check(load().cm2_keypoints_decode(ptr(lowres), ptr(boxes), ptr(det_count), n, r_cap, res, num_keypoints, ptr(out),
+                                      stream()), "cm2_keypoints_decode")
     _count()
 
 

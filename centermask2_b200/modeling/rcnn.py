@@ -158,18 +158,27 @@ class GeneralizedRCNN(nn.Module):
             x, _ = eng.preprocess(images, self.backbone.size_divisibility)
             feats = self.backbone.forward_fmap(x)
             det = fcos.detect([feats[f] for f in fcos.in_features])
-            probs = mask_scores = boxes = valid = None
+            probs = mask_scores = boxes = valid = kps = None
             if roi.mask_on:
                 probs, mask_scores = roi.run([feats[f] for f in roi.in_features], det, sizes)
+            if roi.keypoint_on:                                        # center_heads.py:441-442: after the masks
+                kps = roi.run_keypoints([feats[f] for f in roi.kp_in_features], det, sizes)
             if do_postprocess:
                 boxes, valid = eng.rescale_boxes(det["boxes"], sizes, out_sizes)
-            return det, probs, mask_scores, boxes, valid
+            return det, probs, mask_scores, boxes, valid, kps
 
-        det, probs, mask_scores, boxes, valid = eng.graphed(("inference", sig, tuple(out_sizes), bool(do_postprocess)), plan)
+        det, probs, mask_scores, boxes, valid, kps = eng.graphed(("inference", sig, tuple(out_sizes), bool(do_postprocess)), plan)
         r_cap = det["boxes"].shape[1]
         # one snapshot of the small per-detection tensors (the engine reuses its buffers on the next call)
         scores, classes, locs = det["scores"].clone(), det["classes"].clone(), det["locations"].clone()
         mscores = mask_scores.reshape(n, r_cap).clone() if mask_scores is not None else None
+        keypoints = None
+        if kps is not None:
+            keypoints = torch.cat([kps[..., :2], kps[..., 3:4]], dim=-1)   # keypoint_head.py:116 (x, y, score); a copy
+            if do_postprocess:                                          # detector_postprocess [d2]: x *= scale_x, y *= scale_y
+                pp = eng._bufs[("pp_params", tuple(sizes), tuple(out_sizes))]
+                keypoints[..., 0] *= pp[:, 0].view(n, 1, 1)
+                keypoints[..., 1] *= pp[:, 1].view(n, 1, 1)
         h_count = eng.pinned("h_count{}".format(slot), (n,), torch.int32)
         h_cand = eng.pinned("h_cand{}".format(slot), tuple(det["cand_count"].shape), torch.int32)
         h_count.copy_(det["count"], non_blocking=True)
@@ -193,7 +202,7 @@ class GeneralizedRCNN(nn.Module):
         return dict(done=done, eng=eng, n=n, sizes=sizes, out_sizes=out_sizes, do_postprocess=do_postprocess, r_cap=r_cap, scores=scores,
                     classes=classes, locs=locs, mscores=mscores, boxes=boxes, masks=masks, pm=None if do_postprocess else pm,
                     ready=ready, h_count=h_count, h_cand=h_cand, h_valid=h_valid if do_postprocess else None,
-                    cand_cap=det["cand_cap"], have_probs=probs is not None)
+                    cand_cap=det["cand_cap"], have_probs=probs is not None, keypoints=keypoints)
 
     def _finish(self, ctx):
         """Wait for the small result-size tensors of a launched batch and cut the per-image ``Instances`` out."""
@@ -224,6 +233,8 @@ class GeneralizedRCNN(nn.Module):
                 inst.pred_masks = masks[i][sel] if do_postprocess else pm[i * r_cap:(i + 1) * r_cap][sel]
                 if mscores is not None and total > 0:                    # center_heads.py:511-517
                     inst.mask_scores = mscores[i, sel]
+            if ctx["keypoints"] is not None:
+                inst.pred_keypoints = ctx["keypoints"][i, sel]
             out.append({"instances": inst} if do_postprocess else inst)
         return out
 
@@ -255,6 +266,11 @@ class GeneralizedRCNN(nn.Module):
             if k in ("pred_boxes", "pred_masks"):
                 continue
             out.set(k, v[keep])
+        if out.has("pred_keypoints"):                                   # [d2]: x *= scale_x, y *= scale_y
+            kp = out.pred_keypoints.clone()
+            kp[:, :, 0] *= output_width / results.image_size[1]
+            kp[:, :, 1] *= output_height / results.image_size[0]
+            out.pred_keypoints = kp
         if masks is not None:
             out.pred_masks = masks[keep].bool()
         elif results.has("pred_masks"):

@@ -1,8 +1,9 @@
-"""``CenterROIHeads`` with the SAG-Mask head and the MaskIoU head on libcm2.
+"""``CenterROIHeads`` with the SAG-Mask head, the MaskIoU head and the keypoint head on libcm2.
 
 Replaces ``centermask/modeling/centermask/center_heads.py:295-553`` (inference branches),
 ``pooler.py:192-366`` (ROIPooler eager path), ``sam.py:12-97`` (SpatialAttention(MaskHead)),
-``mask_head.py:174-216`` (mask_rcnn_inference) and ``maskiou_head.py:50-120``.
+``mask_head.py:174-216`` (mask_rcnn_inference), ``maskiou_head.py:50-120`` and, when ``MODEL.KEYPOINT_ON``,
+``keypoint_head.py:95-222`` (KRCNNConvDeconvUpsampleHead + keypoint_rcnn_inference -> heatmaps_to_keypoints [d2]).
 """
 import torch
 
@@ -16,6 +17,7 @@ from .params import PackedModule, attach_params
 # the names are kept so that cfg.MODEL.ROI_MASK_HEAD.NAME / ROI_MASKIOU_HEAD.NAME resolve.
 ROI_MASK_HEAD_REGISTRY = Registry("ROI_MASK_HEAD")
 ROI_MASKIOU_HEAD_REGISTRY = Registry("ROI_MASKIOU_HEAD")
+ROI_KEYPOINT_HEAD_REGISTRY = Registry("ROI_KEYPOINT_HEAD")                       # keypoint_head.py:13
 
 
 @ROI_MASK_HEAD_REGISTRY.register()
@@ -29,6 +31,12 @@ class MaskIoUHead(object):
     """Marker for ``cfg.MODEL.ROI_MASKIOU_HEAD.NAME`` (maskiou_head.py:63)."""
 
 
+@ROI_KEYPOINT_HEAD_REGISTRY.register()
+class KRCNNConvDeconvUpsampleHead(object):
+    """Marker for ``cfg.MODEL.ROI_KEYPOINT_HEAD.NAME`` (keypoint_head.py:168); parameters live under
+    ``CenterROIHeads.keypoint_head.*``."""
+
+
 @ROI_HEADS_REGISTRY.register()
 class CenterROIHeads(PackedModule):
     def __init__(self, cfg, input_shape):
@@ -37,14 +45,18 @@ class CenterROIHeads(PackedModule):
         self.in_features = list(cfg.MODEL.ROI_HEADS.IN_FEATURES)                 # center_heads.py:121
         self.mask_on = bool(cfg.MODEL.MASK_ON)
         self.maskiou_on = bool(cfg.MODEL.MASKIOU_ON)
-        if cfg.MODEL.KEYPOINT_ON:
-            raise NotImplementedError("KEYPOINT_ON is out of scope (false in every reference config)")
+        self.keypoint_on = bool(cfg.MODEL.KEYPOINT_ON)                           # center_heads.py:360
         ROI_MASK_HEAD_REGISTRY.get(cfg.MODEL.ROI_MASK_HEAD.NAME)
         if self.maskiou_on:
             ROI_MASKIOU_HEAD_REGISTRY.get(cfg.MODEL.ROI_MASKIOU_HEAD.NAME)
         chans = {input_shape[f].channels for f in self.in_features}
         assert len(chans) == 1, chans                                            # center_heads.py:327
         self.strides = [input_shape[f].stride for f in self.in_features]
+        if self.keypoint_on:
+            ROI_KEYPOINT_HEAD_REGISTRY.get(cfg.MODEL.ROI_KEYPOINT_HEAD.NAME)
+            self.kp_in_features = list(cfg.MODEL.ROI_KEYPOINT_HEAD.IN_FEATURES)  # center_heads.py:363
+            self.kp_strides = [input_shape[f].stride for f in self.kp_in_features]
+            assert input_shape[self.kp_in_features[0]].channels == chans.copy().pop()
         attach_params(self, roi_heads_param_spec(cfg, chans.pop()))
 
     def _pack(self):
@@ -59,6 +71,11 @@ class CenterROIHeads(PackedModule):
         eng, P = self._pack()
         return eng.run_roi_heads(feats, self.strides, det, image_sizes, P)
 
+    def run_keypoints(self, feats, det, image_sizes):
+        """Device-only: feats list of FMaps (kp_in_features), det fixed-size buffers -> f32 [N, R, K, 4] (x, y, logit, score)."""
+        eng, P = self._pack()
+        return eng.run_keypoint_head(feats, self.kp_strides, det, image_sizes, P)
+
     def forward(self, images, features, proposals, targets=None):
         """center_heads.py:384-411 (inference): returns ``(list[Instances], {})``."""
         assert targets is None and not self.training, "inference only"
@@ -68,20 +85,27 @@ class CenterROIHeads(PackedModule):
         """center_heads.py:413-444: adds ``pred_masks`` [R,1,28,28] and, when the batch has at least one
         detection, ``mask_scores`` [R] to the *same* Instances objects and returns them."""
         assert instances[0].has("pred_boxes") and instances[0].has("pred_classes")
-        if not self.mask_on:
+        if not self.mask_on and not self.keypoint_on:
             return instances
         eng, _ = self._pack()
-        feats = [as_fmap(features[f], eng.dtype, eng.device) for f in self.in_features]
         det = _det_from_instances(instances, eng)
         sizes = [tuple(i.image_size) for i in instances]
-        probs, mask_scores = self.run(feats, det, sizes)
         r_cap = det["boxes"].shape[1]
         total = sum(len(i) for i in instances)
-        for k, inst in enumerate(instances):
-            m = len(inst)
-            inst.pred_masks = probs[k * r_cap:k * r_cap + m].clone()              # mask_head.py:215-216
-            if self.maskiou_on and total > 0:                                     # center_heads.py:511-517
-                inst.mask_scores = mask_scores[k * r_cap:k * r_cap + m].clone()   # maskiou_head.py:59-60
+        if self.mask_on:
+            feats = [as_fmap(features[f], eng.dtype, eng.device) for f in self.in_features]
+            probs, mask_scores = self.run(feats, det, sizes)
+            for k, inst in enumerate(instances):
+                m = len(inst)
+                inst.pred_masks = probs[k * r_cap:k * r_cap + m].clone()              # mask_head.py:215-216
+                if self.maskiou_on and total > 0:                                     # center_heads.py:511-517
+                    inst.mask_scores = mask_scores[k * r_cap:k * r_cap + m].clone()   # maskiou_head.py:59-60
+        if self.keypoint_on:                                                          # center_heads.py:442
+            feats = [as_fmap(features[f], eng.dtype, eng.device) for f in self.kp_in_features]
+            kp = self.run_keypoints(feats, det, sizes)
+            for k, inst in enumerate(instances):
+                m = kp[k, :len(inst)]
+                inst.pred_keypoints = torch.cat([m[..., :2], m[..., 3:4]], dim=-1)    # keypoint_head.py:116 (x, y, score)
         return instances
 
 

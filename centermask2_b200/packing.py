@@ -84,6 +84,26 @@ def deconv2x2(sd, prefix, dtype, device, tc):
     return ConvW(w4, [cin], 1, 0, None, bias, True, dtype, device, tc)
 
 
+def deconv4x4s2(sd, prefix, dtype, device, tc):
+    """ConvTranspose2d(k=4, s=2, p=1) + bias, no activation (keypoint_head.py:205-208, :220) as a 3x3 / pad-1
+    convolution to 4*cout columns: column j = (a*2 + b)*cout + co holds output pixel (2i + a, 2j + b).  Each phase
+    uses a 2x2 subset of the 3x3 taps (the other five are zero): row phase a = 0 reads input rows i-1 (ky 3) and
+    i (ky 1), a = 1 reads rows i (ky 2) and i+1 (ky 0); columns alike."""
+    w = sd[prefix + ".weight"].detach().to(torch.float32)          # [cin, cout, 4, 4]
+    cin, cout = w.shape[0], w.shape[1]
+    assert tuple(w.shape[2:]) == (4, 4), tuple(w.shape)
+    taps = {0: ((0, 3), (1, 1)), 1: ((1, 2), (2, 0))}              # phase -> ((tap index u+1, kernel index), ...)
+    w3 = torch.zeros((4 * cout, cin, 3, 3), dtype=torch.float32)
+    for a in (0, 1):
+        for b in (0, 1):
+            blk = w3[(a * 2 + b) * cout:(a * 2 + b + 1) * cout]
+            for u, ky in taps[a]:
+                for v, kx in taps[b]:
+                    blk[:, :, u, v] = w[:, :, ky, kx].t()
+    bias = sd[prefix + ".bias"].detach().to(torch.float32).repeat(4)
+    return ConvW(w3, [cin], 1, 1, None, bias, False, dtype, device, tc)
+
+
 def linear(sd, prefix, relu, dtype, device, tc, chw=None):
     """nn.Linear as a 1x1 convolution over a [r, 1, 1, k] view.  ``chw`` = (c, h, w) re-orders the
     input features from the reference's flatten(C, H, W) order (maskiou_head.py:115) to NHWC."""

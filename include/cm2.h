@@ -318,6 +318,19 @@ int cm2_maskiou_prep(const float* probs, const cm2_act* out, int32_t dtype, void
 int cm2_maskiou_score(const void* iou, int32_t dtype, int32_t r, int32_t ncls, const int64_t* classes,
                       const float* scores, float* mask_scores, void* stream);
 
+/* Keypoint branch: the tail of KRCNNConvDeconvUpsampleHead.layers -- interpolate(x, 2, "bilinear",
+ * align_corners=False), keypoint_head.py:221 -- fused with keypoint_rcnn_inference (keypoint_head.py:95-120) ->
+ * detectron2 heatmaps_to_keypoints [d2]: per ROI and keypoint, the 4res x 4res logit map is resized (bicubic,
+ * align_corners=False) to ceil(h) x ceil(w) pixels of the box (h, w clamped to >= 1), and the first arg-max pixel gives
+ * out[slot][kp] = (x, y, logit, score): x = (x_int + 0.5) * w / ceil(w) + x0 (same for y), score = 1 / sum over the
+ * 4res x 4res map of exp(map - max).  pred_keypoints of the reference = columns (0, 1, 3).
+ *   lowres: f32 dense [n*r_cap][res][res][4][k] = the ConvTranspose2d(k 4, s 2, p 1) output (keypoint_head.py:205-208)
+ *           in phase layout: value at (y, x) of the 2res x 2res map sits at [y / 2][x / 2][(y & 1) * 2 + (x & 1)].
+ *   boxes : f32 [n][r_cap][4] (16-byte aligned), det_count int32 [n]; slots beyond det_count are written with zeros.
+ *   out   : f32 [n*r_cap][k][4].  res <= 24. */
+int cm2_keypoints_decode(const float* lowres, const float* boxes, const int32_t* det_count, int32_t n, int32_t r_cap,
+                         int32_t res, int32_t num_keypoints, float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Input side, upstream of preprocess: detectron2's ResizeShortestEdge / ResizeTransform for
  * uint8 HWC images (/root/reference/deploy_utils.py:60-73), i.e. PIL.Image.resize(BILINEAR): Pillow's two-pass

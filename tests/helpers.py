@@ -105,3 +105,17 @@ def assert_keypoints_match(got, ref, what="", xy_tol=1e-2, score_rtol=2e-3, max_
         what, frac, (got[..., :2] - ref[..., :2]).abs().max().item())
     ds = ((got[..., 2] - ref[..., 2]).abs() / ref[..., 2].abs().clamp(min=1e-6)).max().item()
     assert ds <= score_rtol, "{}: keypoint score relative diff {}".format(what, ds)
+
+
+def pack_lowres(low):
+    """[R, K, 2res, 2res] -> the conv engine's phase layout [R, res, res, 4, K] (kp_lowres_offset)."""
+    r, k, s, _ = low.shape
+    res = s // 2
+    return low.reshape(r, k, res, 2, res, 2).permute(0, 2, 4, 3, 5, 1).reshape(r, res, res, 4, k).contiguous()
+
+
+def keypoint_boxes(g, r, extent=200.0):
+    """Boxes of assorted sizes, including sub-pixel ones (clamped to 1 px by heatmaps_to_keypoints) and off-image ones."""
+    xy = torch.rand(r, 2, generator=g) * extent - 20.0
+    wh = torch.exp(torch.rand(r, 2, generator=g) * 6.0 - 1.0)          # 0.37 .. 150 px
+    return torch.cat([xy, xy + wh], dim=1).float()

@@ -1,0 +1,59 @@
+"""CPU: the arithmetic of the keypoint decode kernel (csrc/kp_math.cuh, shared by the kernel and this host harness)
+against the oracle (torch CPU interpolate + the heatmaps_to_keypoints restatement).  The harness is test
+infrastructure; the GPU tests (test_gpu_kernels.py) check the kernel itself."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from centermask2_b200 import packing
+from oracle import restate
+from tests.helpers import pack_lowres, keypoint_boxes
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def host_lib(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("kp_host") / "kp_host.so")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++",
+                    os.path.join(HERE, "host", "kp_host.cpp"), "-o", so], check=True)
+    lib = ctypes.CDLL(so)
+    lib.kp_host_decode.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 2
+    return lib
+
+
+@pytest.mark.parametrize("res,k,r", [(14, 17, 12), (7, 3, 9)])
+def test_host_harness_matches_oracle(host_lib, res, k, r):
+    g = torch.Generator().manual_seed(100 + res)
+    low = torch.randn(r, k, 2 * res, 2 * res, generator=g) * 2.5
+    boxes = keypoint_boxes(g, r)
+    packed = pack_lowres(low)
+    out = torch.zeros(r, k, 4)
+    hi = torch.zeros(r, k, 4 * res, 4 * res)
+    host_lib.kp_host_decode(packed.data_ptr(), boxes.data_ptr(), r, res, k, out.data_ptr(), hi.data_ptr())
+    ref_hi = F.interpolate(low, scale_factor=2, mode="bilinear", align_corners=False)
+    assert torch.allclose(hi, ref_hi, rtol=0, atol=1e-6)
+    ref = restate.heatmaps_to_keypoints(ref_hi, boxes)
+    moved = ((out[..., :2] - ref[..., :2]).abs() > 1e-3).any(-1)
+    assert moved.float().mean().item() <= 0.01, moved.nonzero()
+    assert torch.allclose(out[..., 2], ref[..., 2], rtol=1e-5, atol=1e-5)
+    assert torch.allclose(out[..., 3], ref[..., 3], rtol=1e-4)
+
+
+def test_deconv4x4s2_as_phase_conv_equals_conv_transpose2d():
+    """packing.deconv4x4s2: ConvTranspose2d(k 4, s 2, p 1) (keypoint_head.py:205-208) rewritten as a 3x3 convolution to
+    4 * K phase columns; the phase layout is the one kp_lowres_offset reads."""
+    g = torch.Generator().manual_seed(3)
+    cin, k, r, res = 8, 3, 2, 5
+    sd = {"d.weight": torch.randn(cin, k, 4, 4, generator=g), "d.bias": torch.randn(k, generator=g)}
+    w = packing.deconv4x4s2(sd, "d", torch.float32, "cpu", False)
+    x = torch.randn(r, cin, res, res, generator=g)
+    ref = F.conv_transpose2d(x, sd["d.weight"], sd["d.bias"], stride=2, padding=1)
+    w3 = w.w_simt.reshape(3, 3, cin, 4 * k).permute(3, 2, 0, 1)
+    y = F.conv2d(x, w3, w.shift, 1, 1).permute(0, 2, 3, 1).reshape(r, res, res, 4, k)       # the engine's NHWC output
+    assert torch.allclose(y, pack_lowres(ref), atol=1e-5)
+    assert not w.relu and w.k == 3 and w.pad == 1 and w.cout == 4 * k
