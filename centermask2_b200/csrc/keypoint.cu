@@ -6,18 +6,24 @@
 // the ROI's own ceil(h) x ceil(w) pixels is evaluated on the fly -- the resized maps (up to image size per ROI and
 // keypoint) are never stored.  What leaves the SM is 16 bytes per (ROI, keypoint).
 //
-// Bound: fp32 issue (~60 FMA-pipe instructions + 16 shared loads per resized pixel), not HBM: algorithmic bytes are
-// 4 * (2res)^2 in + 16 out per CTA.
+// Bound: fp32 issue, not HBM (algorithmic bytes are 4 * (2res)^2 in + 16 out per CTA).  WALK (default): the resized
+// pixels are split into (column, row segment) items; a thread computes the x taps of its column once, keeps the x pass
+// of the four source rows under the current resized row in registers, and spends the four y FMAs + a compare per
+// pixel, with the y taps of every row in a shared table (kp_column_walk in kp_math.cuh).  The flat variant
+// (CM2_KP_VARIANT=0) evaluates all 16 taps and both coefficient sets per pixel (~100 instructions); both build the same
+// expression tree per pixel, so their results are bit-identical.
 #include "common.cuh"
 #include "kp_math.cuh"
+#include <stdlib.h>
 
 namespace cm2 {
 
 constexpr int KP_THREADS = 256;
 
+template <bool WALK>
 __global__ void __launch_bounds__(KP_THREADS)
 keypoints_decode_kernel(const float* __restrict__ lowres, const float* __restrict__ boxes, const int32_t* __restrict__ count,
-                        int r_cap, int res, int k, float* __restrict__ out) {
+                        int r_cap, int res, int k, int tab_rows, float* __restrict__ out) {
   extern __shared__ float kp_smem[];
   const int s_low = 2 * res, s_hi = 4 * res;
   float* low = kp_smem;                       // [s_low][s_low]
@@ -52,7 +58,17 @@ keypoints_decode_kernel(const float* __restrict__ lowres, const float* __restric
   // arg-max of the resized map; first index wins among equal values (torch.argmax on CPU)
   float best = -INFINITY;
   long long best_p = 0x7fffffffffffffffLL;
-  if (total <= 0x7fffffffLL) {
+  if (WALK) {
+    KpRowTaps* tab = reinterpret_cast<KpRowTaps*>(hi + s_hi * s_hi);     // [tab_rows]
+    const bool use_tab = roi.hc <= tab_rows;
+    if (use_tab) {
+      for (int oy = threadIdx.x; oy < roi.hc; oy += KP_THREADS) tab[oy] = kp_row_taps(scale_y, oy, s_hi);
+      __syncthreads();
+    }
+    const KpBest b = kp_column_walk(hi, s_hi, roi.hc, roi.wc, scale_y, scale_x, use_tab ? tab : nullptr, threadIdx.x, KP_THREADS);
+    best = b.v;
+    best_p = b.p;
+  } else if (total <= 0x7fffffffLL) {
     const unsigned wc = (unsigned)roi.wc;
     for (unsigned p = threadIdx.x; p < (unsigned)total; p += KP_THREADS) {
       const unsigned oy = p / wc, ox = p - oy * wc;
@@ -124,10 +140,20 @@ extern "C" int cm2_keypoints_decode(const float* lowres, const float* boxes, con
   CM2_CHECK_ARG(res > 0 && res <= 24, "keypoints_decode: pooler resolution %d not in [1, 24]", res);
   CM2_CHECK_ARG((long long)n * r_cap <= 65535, "keypoints_decode: %lld ROI slots exceed the grid limit", (long long)n * r_cap);
   if (n == 0) return CM2_OK;
-  const size_t smem = (size_t)20 * res * res * sizeof(float);           // (2res)^2 + (4res)^2 floats
+  const size_t maps = (size_t)20 * res * res * sizeof(float);           // (2res)^2 + (4res)^2 floats
   dim3 grid(num_keypoints, n * r_cap);
-  keypoints_decode_kernel<<<grid, KP_THREADS, smem, (cudaStream_t)stream>>>(lowres, boxes, det_count, r_cap, res,
-                                                                           num_keypoints, out);
+  const int variant = getenv("CM2_KP_VARIANT") ? atoi(getenv("CM2_KP_VARIANT")) : 1;
+  if (variant == 1) {
+    // the y-tap table takes what is left of the default 48 KB (static shared memory: ~112 bytes); taller ROIs compute
+    // their y taps on the fly
+    int tab_rows = (int)((48 * 1024 - 256 - maps) / sizeof(KpRowTaps));
+    tab_rows = tab_rows > 1024 ? 1024 : tab_rows;           // 20 KB: six CTAs per SM at res 14
+    keypoints_decode_kernel<true><<<grid, KP_THREADS, maps + (size_t)tab_rows * sizeof(KpRowTaps), (cudaStream_t)stream>>>(
+        lowres, boxes, det_count, r_cap, res, num_keypoints, tab_rows, out);
+  } else {
+    keypoints_decode_kernel<false><<<grid, KP_THREADS, maps, (cudaStream_t)stream>>>(lowres, boxes, det_count, r_cap, res,
+                                                                                    num_keypoints, 0, out);
+  }
   CM2_CHECK_LAUNCH("keypoints_decode");
   return CM2_OK;
 }

@@ -52,6 +52,7 @@ KP_HD float kp_bilinear_at(const float* low, int in_size, int oy, int ox) {
 struct KpCubic {
   int idx[4];      // clamped source indices
   float w[4];      // cubic convolution coefficients
+  int base;        // guarded floor of the source coordinate: idx[j] = clamp(base - 1 + j)
 };
 
 // bicubic, align_corners=False, scale = in / out (float): taps of output index o.
@@ -64,6 +65,7 @@ KP_HD KpCubic kp_cubic_taps(float scale, int o, int in_size) {
   float t = real - (float)i;
   t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
   KpCubic c;
+  c.base = i;
   float x = t + 1.f;
   c.w[0] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
   x = t;
@@ -93,6 +95,102 @@ KP_HD float kp_bicubic_at(const float* hi, int in_size, const KpCubic& cy, const
     out = a == 0 ? t * cy.w[0] : fmaf(t, cy.w[a], out);
   }
   return out;
+}
+
+// x pass of one source row: the inner sum of kp_bicubic_at.
+KP_HD float kp_row_interp(const float* hi, int in_size, int row, const KpCubic& cx) {
+  row = row < 0 ? 0 : (row > in_size - 1 ? in_size - 1 : row);
+  const float* r = hi + row * in_size;
+  float t = r[cx.idx[0]] * cx.w[0];
+  t = fmaf(r[cx.idx[1]], cx.w[1], t);
+  t = fmaf(r[cx.idx[2]], cx.w[2], t);
+  return fmaf(r[cx.idx[3]], cx.w[3], t);
+}
+
+// y taps of one resized row as the column walk keeps them (a table in shared memory, or computed on the fly)
+struct KpRowTaps {
+  float w0, w1, w2, w3;
+  int base;
+};
+KP_HD KpRowTaps kp_row_taps(float scale, int o, int in_size) {
+  const KpCubic c = kp_cubic_taps(scale, o, in_size);
+  KpRowTaps r;
+  r.w0 = c.w[0]; r.w1 = c.w[1]; r.w2 = c.w[2]; r.w3 = c.w[3];
+  r.base = c.base;
+  return r;
+}
+
+struct KpBest {
+  float v;
+  long long p;     // flat index oy * wc + ox; the smaller index wins among equal values (torch.argmax on CPU)
+};
+KP_HD void kp_best_merge(KpBest& a, float v, long long p) {
+  if (v > a.v || (v == a.v && p < a.p)) { a.v = v; a.p = p; }
+}
+
+// Split of the hc x wc resized pixels of one (ROI, keypoint) into work items (column, row segment): about four
+// items per thread for balance, segments of at least KP_MIN_SEG rows so that the window restarts stay cheap.
+constexpr int KP_MIN_SEG = 8;
+struct KpSplit {
+  int seg_len, nseg;
+  long long items;
+};
+KP_HD KpSplit kp_split(int hc, int wc, int nthreads) {
+  long long want = (4LL * nthreads + wc - 1) / wc;
+  const long long cap = (hc + KP_MIN_SEG - 1) / KP_MIN_SEG;
+  want = want < 1 ? 1 : (want > cap ? cap : want);
+  KpSplit s;
+  s.seg_len = (int)((hc + want - 1) / want);
+  s.nseg = (hc + s.seg_len - 1) / s.seg_len;
+  s.items = (long long)s.nseg * wc;
+  return s;
+}
+
+// The column walk of thread `tid`: for each of its (column, segment) items the x taps are computed once, the x pass of
+// the four source rows under the current resized row is kept in registers and advanced when the source row changes
+// (once per hc / in_size rows), and a resized pixel costs the four y FMAs.  Same expression tree per pixel as
+// kp_bicubic_at, hence bit-identical values.  `tab` (may be null): y taps of every resized row.
+KP_HD KpBest kp_column_walk(const float* hi, int in_size, int hc, int wc, float scale_y, float scale_x,
+                            const KpRowTaps* tab, int tid, int nthreads) {
+  KpBest best;
+  best.v = -INFINITY;
+  best.p = 0x7fffffffffffffffLL;
+  const KpSplit sp = kp_split(hc, wc, nthreads);
+  for (long long item = tid; item < sp.items; item += nthreads) {
+    const int seg = (int)(item / wc);
+    const int ox = (int)(item - (long long)seg * wc);
+    const int row0 = seg * sp.seg_len;
+    const int row1 = row0 + sp.seg_len < hc ? row0 + sp.seg_len : hc;
+    const KpCubic cx = kp_cubic_taps(scale_x, ox, in_size);
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    int base = 0;
+    float col_v = -INFINITY;
+    int col_y = row0;
+    for (int oy = row0; oy < row1; ++oy) {
+      const KpRowTaps ty = tab ? tab[oy] : kp_row_taps(scale_y, oy, in_size);
+      int shift = ty.base - base;
+      if (oy == row0 || shift >= 4) {
+        t0 = kp_row_interp(hi, in_size, ty.base - 1, cx);
+        t1 = kp_row_interp(hi, in_size, ty.base, cx);
+        t2 = kp_row_interp(hi, in_size, ty.base + 1, cx);
+        t3 = kp_row_interp(hi, in_size, ty.base + 2, cx);
+      } else {
+        for (; shift > 0; --shift) {           // the source coordinate is monotonic in oy: shift >= 0
+          ++base;
+          t0 = t1; t1 = t2; t2 = t3;
+          t3 = kp_row_interp(hi, in_size, base + 2, cx);
+        }
+      }
+      base = ty.base;
+      float v = t0 * ty.w0;
+      v = fmaf(t1, ty.w1, v);
+      v = fmaf(t2, ty.w2, v);
+      v = fmaf(t3, ty.w3, v);
+      if (v > col_v) { col_v = v; col_y = oy; }
+    }
+    kp_best_merge(best, col_v, (long long)col_y * wc + ox);
+  }
+  return best;
 }
 
 // ROI geometry of heatmaps_to_keypoints [d2]: widths / heights clamped to >= 1, resized map = ceil of them.

@@ -5,7 +5,10 @@
 #include <vector>
 #include "../../centermask2_b200/csrc/kp_math.cuh"
 
-extern "C" void kp_host_decode(const float* lowres, const float* boxes, int r, int res, int k, float* out, float* hi_out) {
+// walk_threads > 0: evaluate through kp_column_walk with that many threads (the kernel uses 256) and a y-tap table of
+// tab_rows rows; 0: the flat per-pixel loop.
+extern "C" void kp_host_decode(const float* lowres, const float* boxes, int r, int res, int k, float* out, float* hi_out,
+                               int walk_threads, int tab_rows) {
   using namespace cm2;
   const int s_low = 2 * res, s_hi = 4 * res;
   std::vector<float> low(s_low * s_low), hi(s_hi * s_hi);
@@ -22,12 +25,29 @@ extern "C" void kp_host_decode(const float* lowres, const float* boxes, int r, i
       const float sy = (float)s_hi / (float)g.hc, sx = (float)s_hi / (float)g.wc;
       float best = -INFINITY;
       long long best_p = 0;
-      for (int oy = 0; oy < g.hc; ++oy) {
-        const KpCubic cy = kp_cubic_taps(sy, oy, s_hi);
-        for (int ox = 0; ox < g.wc; ++ox) {
-          const KpCubic cx = kp_cubic_taps(sx, ox, s_hi);
-          const float v = kp_bicubic_at(hi.data(), s_hi, cy, cx);
-          if (v > best) { best = v; best_p = (long long)oy * g.wc + ox; }
+      if (walk_threads > 0) {
+        // the kernel's default decomposition: every thread's column walk, merged like the block reduction
+        std::vector<KpRowTaps> tab;
+        const bool use_tab = g.hc <= tab_rows;
+        if (use_tab)
+          for (int oy = 0; oy < g.hc; ++oy) tab.push_back(kp_row_taps(sy, oy, s_hi));
+        KpBest b;
+        b.v = -INFINITY;
+        b.p = 0x7fffffffffffffffLL;
+        for (int tid = 0; tid < walk_threads; ++tid) {
+          const KpBest t = kp_column_walk(hi.data(), s_hi, g.hc, g.wc, sy, sx, use_tab ? tab.data() : nullptr, tid, walk_threads);
+          kp_best_merge(b, t.v, t.p);
+        }
+        best = b.v;
+        best_p = b.p;
+      } else {
+        for (int oy = 0; oy < g.hc; ++oy) {
+          const KpCubic cy = kp_cubic_taps(sy, oy, s_hi);
+          for (int ox = 0; ox < g.wc; ++ox) {
+            const KpCubic cx = kp_cubic_taps(sx, ox, s_hi);
+            const float v = kp_bicubic_at(hi.data(), s_hi, cy, cx);
+            if (v > best) { best = v; best_p = (long long)oy * g.wc + ox; }
+          }
         }
       }
       float pool = 0.f;

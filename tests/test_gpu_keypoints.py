@@ -19,8 +19,10 @@ from tests.helpers import pack_lowres, keypoint_boxes, load_golden, build_case  
 DEV = "cuda"
 
 
+@pytest.mark.parametrize("variant", [1, 0])          # 1: column walk (default); 0: flat per-pixel loop
 @pytest.mark.parametrize("res,k,n,r_cap,counts", [(14, 17, 2, 8, (8, 5)), (7, 3, 3, 4, (4, 0, 1)), (14, 17, 1, 3, (3,))])
-def test_keypoints_decode_matches_oracle(res, k, n, r_cap, counts):
+def test_keypoints_decode_matches_oracle(res, k, n, r_cap, counts, variant, monkeypatch):
+    monkeypatch.setenv("CM2_KP_VARIANT", str(variant))
     g = torch.Generator().manual_seed(7 * res + n)
     r = n * r_cap
     low = torch.randn(r, k, 2 * res, 2 * res, generator=g) * 2.5
@@ -44,6 +46,13 @@ def test_keypoints_decode_matches_oracle(res, k, n, r_cap, counts):
     assert torch.allclose(got[..., 2], ref[..., 2], rtol=1e-5, atol=1e-4)
     assert torch.allclose(got[..., 3], ref[..., 3], rtol=2e-3)
     assert torch.equal(got[~moved][..., :2], ref[~moved][..., :2])                          # same pixel -> same fp32 expression
+    if variant == 1:                                  # both work splits evaluate the same expression tree per pixel
+        monkeypatch.setenv("CM2_KP_VARIANT", "0")
+        flat = torch.full_like(out, float("nan"))
+        lib.keypoints_decode(pack_lowres(low).to(DEV), boxes.view(n, r_cap, 4).to(DEV),
+                             torch.tensor(counts, dtype=torch.int32, device=DEV), n, r_cap, res, k, flat)
+        torch.cuda.synchronize()
+        assert torch.equal(out, flat)
 
 
 def test_keypoints_decode_rejects_bad_arguments():

@@ -22,7 +22,7 @@ def host_lib(tmp_path_factory):
     subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++",
                     os.path.join(HERE, "host", "kp_host.cpp"), "-o", so], check=True)
     lib = ctypes.CDLL(so)
-    lib.kp_host_decode.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 2
+    lib.kp_host_decode.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 2 + [ctypes.c_int] * 2
     return lib
 
 
@@ -34,7 +34,7 @@ def test_host_harness_matches_oracle(host_lib, res, k, r):
     packed = pack_lowres(low)
     out = torch.zeros(r, k, 4)
     hi = torch.zeros(r, k, 4 * res, 4 * res)
-    host_lib.kp_host_decode(packed.data_ptr(), boxes.data_ptr(), r, res, k, out.data_ptr(), hi.data_ptr())
+    host_lib.kp_host_decode(packed.data_ptr(), boxes.data_ptr(), r, res, k, out.data_ptr(), hi.data_ptr(), 0, 0)
     ref_hi = F.interpolate(low, scale_factor=2, mode="bilinear", align_corners=False)
     assert torch.allclose(hi, ref_hi, rtol=0, atol=1e-6)
     ref = restate.heatmaps_to_keypoints(ref_hi, boxes)
@@ -57,3 +57,28 @@ def test_deconv4x4s2_as_phase_conv_equals_conv_transpose2d():
     y = F.conv2d(x, w3, w.shift, 1, 1).permute(0, 2, 3, 1).reshape(r, res, res, 4, k)       # the engine's NHWC output
     assert torch.allclose(y, pack_lowres(ref), atol=1e-5)
     assert not w.relu and w.k == 3 and w.pad == 1 and w.cout == 4 * k
+
+
+@pytest.mark.parametrize("threads,tab_rows", [(256, 1024), (256, 40), (32, 1024)])
+def test_column_walk_decomposition_is_bit_identical_to_the_flat_loop(host_lib, threads, tab_rows):
+    """kp_column_walk (the kernel's default work split: (column, row segment) items, x pass carried in registers down the
+    column, y taps from a table or -- for ROIs taller than the table -- on the fly) against the flat per-pixel loop:
+    same expression tree per pixel, first-index tie-break, so every output must be bit-identical."""
+    g = torch.Generator().manual_seed(11)
+    res, k = 14, 2
+    boxes = torch.cat([keypoint_boxes(g, 10), torch.tensor([
+        [0.0, 0.0, 640.0, 3.0],          # wide strip: wc >= threads, one short segment
+        [5.0, 5.0, 6.0, 505.0],          # tall strip: one column, many segments
+        [-3.5, 2.25, 500.5, 402.0],      # large: several items per thread
+        [1.0, 1.0, 30.0, 1300.0],        # taller than any table: y taps on the fly
+        [10.2, 11.7, 10.5, 11.9],        # sub-pixel: one resized pixel
+        [0.0, 0.0, 20.0, 20.0],          # downscale: the source row advances by more than one per resized row
+        [0.0, 0.0, 9.0, 300.0]])])
+    r = boxes.shape[0]
+    low = torch.randn(r, k, 2 * res, 2 * res, generator=g) * 2.5
+    low[1] = low[1].round()                 # plateaus / exact ties for the first-index rule
+    packed = pack_lowres(low)
+    flat, walk = torch.zeros(r, k, 4), torch.zeros(r, k, 4)
+    host_lib.kp_host_decode(packed.data_ptr(), boxes.data_ptr(), r, res, k, flat.data_ptr(), None, 0, 0)
+    host_lib.kp_host_decode(packed.data_ptr(), boxes.data_ptr(), r, res, k, walk.data_ptr(), None, threads, tab_rows)
+    assert torch.equal(flat, walk), (flat - walk).abs().amax(dim=(1, 2))
