@@ -24,7 +24,7 @@ template <bool WALK>
 __global__ void __launch_bounds__(KP_THREADS)
 keypoints_decode_kernel(const float* __restrict__ lowres, const float* __restrict__ boxes, const int32_t* __restrict__ count,
                         int r_cap, int res, int k, int tab_rows, float* __restrict__ out) {
-  extern __shared__ float kp_smem[];
+  extern __shared__ __align__(16) float kp_smem[];
   const int s_low = 2 * res, s_hi = 4 * res;
   float* low = kp_smem;                       // [s_low][s_low]
   float* hi = kp_smem + s_low * s_low;        // [s_hi][s_hi]
@@ -59,13 +59,19 @@ keypoints_decode_kernel(const float* __restrict__ lowres, const float* __restric
   float best = -INFINITY;
   long long best_p = 0x7fffffffffffffffLL;
   if (WALK) {
-    KpRowTaps* tab = reinterpret_cast<KpRowTaps*>(hi + s_hi * s_hi);     // [tab_rows]
+    KpW4* wtab = reinterpret_cast<KpW4*>(hi + s_hi * s_hi);               // [tab_rows]; 20 res^2 floats precede: 16-byte aligned
+    int* btab = reinterpret_cast<int*>(wtab + tab_rows);                  // [tab_rows]
     const bool use_tab = roi.hc <= tab_rows;
     if (use_tab) {
-      for (int oy = threadIdx.x; oy < roi.hc; oy += KP_THREADS) tab[oy] = kp_row_taps(scale_y, oy, s_hi);
+      for (int oy = threadIdx.x; oy < roi.hc; oy += KP_THREADS) {
+        const KpRowTaps t = kp_row_taps(scale_y, oy, s_hi);
+        wtab[oy] = t.w;
+        btab[oy] = t.base;
+      }
       __syncthreads();
     }
-    const KpBest b = kp_column_walk(hi, s_hi, roi.hc, roi.wc, scale_y, scale_x, use_tab ? tab : nullptr, threadIdx.x, KP_THREADS);
+    const KpBest b = kp_column_walk(hi, s_hi, roi.hc, roi.wc, scale_y, scale_x, use_tab ? wtab : nullptr, btab, threadIdx.x,
+                                    KP_THREADS);
     best = b.v;
     best_p = b.p;
   } else if (total <= 0x7fffffffLL) {
@@ -146,9 +152,9 @@ extern "C" int cm2_keypoints_decode(const float* lowres, const float* boxes, con
   if (variant == 1) {
     // the y-tap table takes what is left of the default 48 KB (static shared memory: ~112 bytes); taller ROIs compute
     // their y taps on the fly
-    int tab_rows = (int)((48 * 1024 - 256 - maps) / sizeof(KpRowTaps));
+    int tab_rows = (int)((48 * 1024 - 256 - maps) / 20);               // 16 bytes of weights + the source row base
     tab_rows = tab_rows > 1024 ? 1024 : tab_rows;           // 20 KB: six CTAs per SM at res 14
-    keypoints_decode_kernel<true><<<grid, KP_THREADS, maps + (size_t)tab_rows * sizeof(KpRowTaps), (cudaStream_t)stream>>>(
+    keypoints_decode_kernel<true><<<grid, KP_THREADS, maps + (size_t)tab_rows * 20, (cudaStream_t)stream>>>(
         lowres, boxes, det_count, r_cap, res, num_keypoints, tab_rows, out);
   } else {
     keypoints_decode_kernel<false><<<grid, KP_THREADS, maps, (cudaStream_t)stream>>>(lowres, boxes, det_count, r_cap, res,

@@ -108,14 +108,17 @@ KP_HD float kp_row_interp(const float* hi, int in_size, int row, const KpCubic& 
 }
 
 // y taps of one resized row as the column walk keeps them (a table in shared memory, or computed on the fly)
-struct KpRowTaps {
+struct alignas(16) KpW4 {
   float w0, w1, w2, w3;
+};
+struct KpRowTaps {
+  KpW4 w;
   int base;
 };
 KP_HD KpRowTaps kp_row_taps(float scale, int o, int in_size) {
   const KpCubic c = kp_cubic_taps(scale, o, in_size);
   KpRowTaps r;
-  r.w0 = c.w[0]; r.w1 = c.w[1]; r.w2 = c.w[2]; r.w3 = c.w[3];
+  r.w.w0 = c.w[0]; r.w.w1 = c.w[1]; r.w.w2 = c.w[2]; r.w.w3 = c.w[3];
   r.base = c.base;
   return r;
 }
@@ -149,9 +152,10 @@ KP_HD KpSplit kp_split(int hc, int wc, int nthreads) {
 // The column walk of thread `tid`: for each of its (column, segment) items the x taps are computed once, the x pass of
 // the four source rows under the current resized row is kept in registers and advanced when the source row changes
 // (once per hc / in_size rows), and a resized pixel costs the four y FMAs.  Same expression tree per pixel as
-// kp_bicubic_at, hence bit-identical values.  `tab` (may be null): y taps of every resized row.
+// kp_bicubic_at, hence bit-identical values.  `wtab` / `btab` (may be null): y taps of every resized row (weights as
+// one 16-byte load, source row base).
 KP_HD KpBest kp_column_walk(const float* hi, int in_size, int hc, int wc, float scale_y, float scale_x,
-                            const KpRowTaps* tab, int tid, int nthreads) {
+                            const KpW4* wtab, const int* btab, int tid, int nthreads) {
   KpBest best;
   best.v = -INFINITY;
   best.p = 0x7fffffffffffffffLL;
@@ -167,7 +171,13 @@ KP_HD KpBest kp_column_walk(const float* hi, int in_size, int hc, int wc, float 
     float col_v = -INFINITY;
     int col_y = row0;
     for (int oy = row0; oy < row1; ++oy) {
-      const KpRowTaps ty = tab ? tab[oy] : kp_row_taps(scale_y, oy, in_size);
+      KpRowTaps ty;
+      if (wtab) {
+        ty.w = wtab[oy];
+        ty.base = btab[oy];
+      } else {
+        ty = kp_row_taps(scale_y, oy, in_size);
+      }
       int shift = ty.base - base;
       if (oy == row0 || shift >= 4) {
         t0 = kp_row_interp(hi, in_size, ty.base - 1, cx);
@@ -182,10 +192,10 @@ KP_HD KpBest kp_column_walk(const float* hi, int in_size, int hc, int wc, float 
         }
       }
       base = ty.base;
-      float v = t0 * ty.w0;
-      v = fmaf(t1, ty.w1, v);
-      v = fmaf(t2, ty.w2, v);
-      v = fmaf(t3, ty.w3, v);
+      float v = t0 * ty.w.w0;
+      v = fmaf(t1, ty.w.w1, v);
+      v = fmaf(t2, ty.w.w2, v);
+      v = fmaf(t3, ty.w.w3, v);
       if (v > col_v) { col_v = v; col_y = oy; }
     }
     kp_best_merge(best, col_v, (long long)col_y * wc + ox);

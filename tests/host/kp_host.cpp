@@ -27,15 +27,20 @@ extern "C" void kp_host_decode(const float* lowres, const float* boxes, int r, i
       long long best_p = 0;
       if (walk_threads > 0) {
         // the kernel's default decomposition: every thread's column walk, merged like the block reduction
-        std::vector<KpRowTaps> tab;
+        std::vector<KpW4> wtab;
+        std::vector<int> btab;
         const bool use_tab = g.hc <= tab_rows;
         if (use_tab)
-          for (int oy = 0; oy < g.hc; ++oy) tab.push_back(kp_row_taps(sy, oy, s_hi));
+          for (int oy = 0; oy < g.hc; ++oy) {
+            const KpRowTaps t = kp_row_taps(sy, oy, s_hi);
+            wtab.push_back(t.w);
+            btab.push_back(t.base);
+          }
         KpBest b;
         b.v = -INFINITY;
         b.p = 0x7fffffffffffffffLL;
         for (int tid = 0; tid < walk_threads; ++tid) {
-          const KpBest t = kp_column_walk(hi.data(), s_hi, g.hc, g.wc, sy, sx, use_tab ? tab.data() : nullptr, tid, walk_threads);
+          const KpBest t = kp_column_walk(hi.data(), s_hi, g.hc, g.wc, sy, sx, use_tab ? wtab.data() : nullptr, btab.data(), tid, walk_threads);
           kp_best_merge(b, t.v, t.p);
         }
         best = b.v;
