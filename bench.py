@@ -49,11 +49,11 @@ class ClockSampler(object):
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=20):
         self.index, self.rows, self.proc, self.windows = index, [], None, []
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", str(int(period_ms))],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -262,6 +262,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("CM2_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-ms", type=int, default=int(os.environ.get("CM2_CLOCK_MS", "20")),
+                    help="nvidia-smi sampling period for the clocks line (the sampler runs during the timed regions)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying its CUDA graph")
     ap.add_argument("--profile-step", action="store_true",
                     help="warm up, then run exactly one eager step between cudaProfilerStart/Stop and exit (for "
@@ -295,7 +297,7 @@ def main():
     from centermask2_b200.arch import conv_gflop_per_image
     from centermask2_b200.synth import synthetic_state_dict
 
-    clk = ClockSampler(local)
+    clk = ClockSampler(local, args.clock_ms)
     cfg = make_cfg(args.precision)
     model = cm.build_model(cfg)
     model.load_state_dict(synthetic_state_dict(cfg, seed=WEIGHT_SEED))

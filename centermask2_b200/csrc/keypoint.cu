@@ -20,8 +20,31 @@ namespace cm2 {
 
 constexpr int KP_THREADS = 256;
 
+// Shared-space twin of KpMemPtr (kp_math.cuh): 32-bit shared addresses and ld.shared, so that the inner loop of the
+// column walk does not rebuild generic addresses (ncu: ~10 of ~45 instructions per resized pixel were that).
+struct KpMemShared {
+  uint32_t hi, wtab, btab;
+  __device__ __forceinline__ float hi_at(int elem) const {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(hi + 4u * (uint32_t)elem));
+    return v;
+  }
+  __device__ __forceinline__ KpW4 w_at(int oy) const {
+    KpW4 w;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(w.w0), "=f"(w.w1), "=f"(w.w2), "=f"(w.w3)
+                 : "r"(wtab + 16u * (uint32_t)oy));
+    return w;
+  }
+  __device__ __forceinline__ int base_at(int oy) const {
+    int b;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(b) : "r"(btab + 4u * (uint32_t)oy));
+    return b;
+  }
+};
+
 template <bool WALK>
-__global__ void __launch_bounds__(KP_THREADS)
+__global__ void __launch_bounds__(KP_THREADS, 4)
 keypoints_decode_kernel(const float* __restrict__ lowres, const float* __restrict__ boxes, const int32_t* __restrict__ count,
                         int r_cap, int res, int k, int tab_rows, float* __restrict__ out) {
   extern __shared__ __align__(16) float kp_smem[];
@@ -58,20 +81,20 @@ keypoints_decode_kernel(const float* __restrict__ lowres, const float* __restric
   // arg-max of the resized map; first index wins among equal values (torch.argmax on CPU)
   float best = -INFINITY;
   long long best_p = 0x7fffffffffffffffLL;
-  if (WALK) {
+  if (WALK && roi.hc <= tab_rows) {      // taller ROIs (> 1024 px at res 14) take the flat loop below
     KpW4* wtab = reinterpret_cast<KpW4*>(hi + s_hi * s_hi);               // [tab_rows]; 20 res^2 floats precede: 16-byte aligned
     int* btab = reinterpret_cast<int*>(wtab + tab_rows);                  // [tab_rows]
-    const bool use_tab = roi.hc <= tab_rows;
-    if (use_tab) {
-      for (int oy = threadIdx.x; oy < roi.hc; oy += KP_THREADS) {
-        const KpRowTaps t = kp_row_taps(scale_y, oy, s_hi);
-        wtab[oy] = t.w;
-        btab[oy] = t.base;
-      }
-      __syncthreads();
+    for (int oy = threadIdx.x; oy < roi.hc; oy += KP_THREADS) {
+      const KpRowTaps t = kp_row_taps(scale_y, oy, s_hi);
+      wtab[oy] = t.w;
+      btab[oy] = t.base;
     }
-    const KpBest b = kp_column_walk(hi, s_hi, roi.hc, roi.wc, scale_y, scale_x, use_tab ? wtab : nullptr, btab, threadIdx.x,
-                                    KP_THREADS);
+    __syncthreads();
+    KpMemShared m;
+    m.hi = (uint32_t)__cvta_generic_to_shared(hi);
+    m.wtab = (uint32_t)__cvta_generic_to_shared(wtab);
+    m.btab = (uint32_t)__cvta_generic_to_shared(btab);
+    const KpBest b = kp_column_walk(m, s_hi, roi.hc, roi.wc, scale_x, (int)threadIdx.x, KP_THREADS);
     best = b.v;
     best_p = b.p;
   } else if (total <= 0x7fffffffLL) {

@@ -97,16 +97,6 @@ KP_HD float kp_bicubic_at(const float* hi, int in_size, const KpCubic& cy, const
   return out;
 }
 
-// x pass of one source row: the inner sum of kp_bicubic_at.
-KP_HD float kp_row_interp(const float* hi, int in_size, int row, const KpCubic& cx) {
-  row = row < 0 ? 0 : (row > in_size - 1 ? in_size - 1 : row);
-  const float* r = hi + row * in_size;
-  float t = r[cx.idx[0]] * cx.w[0];
-  t = fmaf(r[cx.idx[1]], cx.w[1], t);
-  t = fmaf(r[cx.idx[2]], cx.w[2], t);
-  return fmaf(r[cx.idx[3]], cx.w[3], t);
-}
-
 // y taps of one resized row as the column walk keeps them (a table in shared memory, or computed on the fly)
 struct alignas(16) KpW4 {
   float w0, w1, w2, w3;
@@ -121,6 +111,29 @@ KP_HD KpRowTaps kp_row_taps(float scale, int o, int in_size) {
   r.w.w0 = c.w[0]; r.w.w1 = c.w[1]; r.w.w2 = c.w[2]; r.w.w3 = c.w[3];
   r.base = c.base;
   return r;
+}
+
+// How the column walk reads the 4res x 4res map and the y-tap table.  This one goes through ordinary pointers (host
+// harness, generic addressing); keypoint.cu has the shared-space twin (32-bit addresses, ld.shared) with the same
+// three members, because generic addressing of dynamic shared memory re-derives the window base inside the loop.
+struct KpMemPtr {
+  const float* hi;
+  const KpW4* wtab;
+  const int* btab;
+  KP_HD float hi_at(int elem) const { return hi[elem]; }
+  KP_HD KpW4 w_at(int oy) const { return wtab[oy]; }
+  KP_HD int base_at(int oy) const { return btab[oy]; }
+};
+
+// x pass of one source row: the inner sum of kp_bicubic_at.
+template <typename Mem>
+KP_HD float kp_row_interp(const Mem& m, int in_size, int row, const KpCubic& cx) {
+  row = row < 0 ? 0 : (row > in_size - 1 ? in_size - 1 : row);
+  const int o = row * in_size;
+  float t = m.hi_at(o + cx.idx[0]) * cx.w[0];
+  t = fmaf(m.hi_at(o + cx.idx[1]), cx.w[1], t);
+  t = fmaf(m.hi_at(o + cx.idx[2]), cx.w[2], t);
+  return fmaf(m.hi_at(o + cx.idx[3]), cx.w[3], t);
 }
 
 struct KpBest {
@@ -151,11 +164,11 @@ KP_HD KpSplit kp_split(int hc, int wc, int nthreads) {
 
 // The column walk of thread `tid`: for each of its (column, segment) items the x taps are computed once, the x pass of
 // the four source rows under the current resized row is kept in registers and advanced when the source row changes
-// (once per hc / in_size rows), and a resized pixel costs the four y FMAs.  Same expression tree per pixel as
-// kp_bicubic_at, hence bit-identical values.  `wtab` / `btab` (may be null): y taps of every resized row (weights as
-// one 16-byte load, source row base).
-KP_HD KpBest kp_column_walk(const float* hi, int in_size, int hc, int wc, float scale_y, float scale_x,
-                            const KpW4* wtab, const int* btab, int tid, int nthreads) {
+// (once per hc / in_size rows), and a resized pixel costs the four y FMAs + a compare.  Same expression tree per pixel
+// as kp_bicubic_at, hence bit-identical values.  The y taps of every resized row come from the table behind `m`
+// (weights as one 16-byte load + the source row base); ROIs taller than the table take the flat per-pixel loop.
+template <typename Mem>
+KP_HD KpBest kp_column_walk(const Mem& m, int in_size, int hc, int wc, float scale_x, int tid, int nthreads) {
   KpBest best;
   best.v = -INFINITY;
   best.p = 0x7fffffffffffffffLL;
@@ -166,37 +179,41 @@ KP_HD KpBest kp_column_walk(const float* hi, int in_size, int hc, int wc, float 
     const int row0 = seg * sp.seg_len;
     const int row1 = row0 + sp.seg_len < hc ? row0 + sp.seg_len : hc;
     const KpCubic cx = kp_cubic_taps(scale_x, ox, in_size);
-    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-    int base = 0;
+    KpRowTaps ty;
+    ty.w = m.w_at(row0);
+    ty.base = m.base_at(row0);
+    int base = ty.base;
+    float t0 = kp_row_interp(m, in_size, base - 1, cx);
+    float t1 = kp_row_interp(m, in_size, base, cx);
+    float t2 = kp_row_interp(m, in_size, base + 1, cx);
+    float t3 = kp_row_interp(m, in_size, base + 2, cx);
     float col_v = -INFINITY;
     int col_y = row0;
-    for (int oy = row0; oy < row1; ++oy) {
-      KpRowTaps ty;
-      if (wtab) {
-        ty.w = wtab[oy];
-        ty.base = btab[oy];
-      } else {
-        ty = kp_row_taps(scale_y, oy, in_size);
-      }
-      int shift = ty.base - base;
-      if (oy == row0 || shift >= 4) {
-        t0 = kp_row_interp(hi, in_size, ty.base - 1, cx);
-        t1 = kp_row_interp(hi, in_size, ty.base, cx);
-        t2 = kp_row_interp(hi, in_size, ty.base + 1, cx);
-        t3 = kp_row_interp(hi, in_size, ty.base + 2, cx);
-      } else {
-        for (; shift > 0; --shift) {           // the source coordinate is monotonic in oy: shift >= 0
-          ++base;
-          t0 = t1; t1 = t2; t2 = t3;
-          t3 = kp_row_interp(hi, in_size, base + 2, cx);
-        }
-      }
-      base = ty.base;
+    for (int oy = row0;;) {
       float v = t0 * ty.w.w0;
       v = fmaf(t1, ty.w.w1, v);
       v = fmaf(t2, ty.w.w2, v);
       v = fmaf(t3, ty.w.w3, v);
       if (v > col_v) { col_v = v; col_y = oy; }
+      if (++oy >= row1) break;
+      ty.w = m.w_at(oy);
+      ty.base = m.base_at(oy);
+      int shift = ty.base - base;              // the source coordinate is monotonic in oy: shift >= 0
+      if (shift != 0) {
+        if (shift >= 4) {
+          base = ty.base;
+          t0 = kp_row_interp(m, in_size, base - 1, cx);
+          t1 = kp_row_interp(m, in_size, base, cx);
+          t2 = kp_row_interp(m, in_size, base + 1, cx);
+          t3 = kp_row_interp(m, in_size, base + 2, cx);
+        } else {
+          do {
+            ++base;
+            t0 = t1; t1 = t2; t2 = t3;
+            t3 = kp_row_interp(m, in_size, base + 2, cx);
+          } while (--shift);
+        }
+      }
     }
     kp_best_merge(best, col_v, (long long)col_y * wc + ox);
   }

@@ -5,8 +5,8 @@
 #include <vector>
 #include "../../centermask2_b200/csrc/kp_math.cuh"
 
-// walk_threads > 0: evaluate through kp_column_walk with that many threads (the kernel uses 256) and a y-tap table of
-// tab_rows rows; 0: the flat per-pixel loop.
+// walk_threads > 0: evaluate through kp_column_walk with that many threads (the kernel uses 256) when the ROI fits the
+// y-tap table of tab_rows rows, as the kernel does; otherwise, and with walk_threads == 0: the flat per-pixel loop.
 extern "C" void kp_host_decode(const float* lowres, const float* boxes, int r, int res, int k, float* out, float* hi_out,
                                int walk_threads, int tab_rows) {
   using namespace cm2;
@@ -25,22 +25,24 @@ extern "C" void kp_host_decode(const float* lowres, const float* boxes, int r, i
       const float sy = (float)s_hi / (float)g.hc, sx = (float)s_hi / (float)g.wc;
       float best = -INFINITY;
       long long best_p = 0;
-      if (walk_threads > 0) {
+      if (walk_threads > 0 && g.hc <= tab_rows) {
         // the kernel's default decomposition: every thread's column walk, merged like the block reduction
         std::vector<KpW4> wtab;
         std::vector<int> btab;
-        const bool use_tab = g.hc <= tab_rows;
-        if (use_tab)
-          for (int oy = 0; oy < g.hc; ++oy) {
-            const KpRowTaps t = kp_row_taps(sy, oy, s_hi);
-            wtab.push_back(t.w);
-            btab.push_back(t.base);
-          }
+        for (int oy = 0; oy < g.hc; ++oy) {
+          const KpRowTaps t = kp_row_taps(sy, oy, s_hi);
+          wtab.push_back(t.w);
+          btab.push_back(t.base);
+        }
+        KpMemPtr m;
+        m.hi = hi.data();
+        m.wtab = wtab.data();
+        m.btab = btab.data();
         KpBest b;
         b.v = -INFINITY;
         b.p = 0x7fffffffffffffffLL;
         for (int tid = 0; tid < walk_threads; ++tid) {
-          const KpBest t = kp_column_walk(hi.data(), s_hi, g.hc, g.wc, sy, sx, use_tab ? wtab.data() : nullptr, btab.data(), tid, walk_threads);
+          const KpBest t = kp_column_walk(m, s_hi, g.hc, g.wc, sx, tid, walk_threads);
           kp_best_merge(b, t.v, t.p);
         }
         best = b.v;

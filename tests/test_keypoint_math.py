@@ -62,7 +62,7 @@ def test_deconv4x4s2_as_phase_conv_equals_conv_transpose2d():
 @pytest.mark.parametrize("threads,tab_rows", [(256, 1024), (256, 40), (32, 1024)])
 def test_column_walk_decomposition_is_bit_identical_to_the_flat_loop(host_lib, threads, tab_rows):
     """kp_column_walk (the kernel's default work split: (column, row segment) items, x pass carried in registers down the
-    column, y taps from a table or -- for ROIs taller than the table -- on the fly) against the flat per-pixel loop:
+    column, y taps from a table; ROIs taller than the table fall back to the flat loop) against the flat per-pixel loop:
     same expression tree per pixel, first-index tie-break, so every output must be bit-identical."""
     g = torch.Generator().manual_seed(11)
     res, k = 14, 2
@@ -70,7 +70,7 @@ def test_column_walk_decomposition_is_bit_identical_to_the_flat_loop(host_lib, t
         [0.0, 0.0, 640.0, 3.0],          # wide strip: wc >= threads, one short segment
         [5.0, 5.0, 6.0, 505.0],          # tall strip: one column, many segments
         [-3.5, 2.25, 500.5, 402.0],      # large: several items per thread
-        [1.0, 1.0, 30.0, 1300.0],        # taller than any table: y taps on the fly
+        [1.0, 1.0, 30.0, 1300.0],        # taller than any table: flat-loop fallback
         [10.2, 11.7, 10.5, 11.9],        # sub-pixel: one resized pixel
         [0.0, 0.0, 20.0, 20.0],          # downscale: the source row advances by more than one per resized row
         [0.0, 0.0, 9.0, 300.0]])])
