@@ -62,15 +62,17 @@ keypoints_decode_kernel(const float* __restrict__ lowres, const float* __restric
     if (threadIdx.x < 4) o[threadIdx.x] = 0.f;
     return;
   }
-  for (int i = threadIdx.x; i < s_low * s_low; i += KP_THREADS) {
-    const int y = i / s_low, x = i - y * s_low;
-    low[i] = __ldg(lowres + kp_lowres_offset(slot, y, x, kp, res, k));
-  }
+  // gather + bilinear x2, rows over warps and columns over lanes (no divisions by run-time extents)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* src = lowres + (size_t)slot * (res * res * 4) * k + kp;       // this ROI's [res][res][4][k] block
+  for (int cy = warp; cy < res; cy += KP_THREADS / 32)
+    for (int t = lane; t < res * 4; t += 32) {                               // t = (cell column, phase)
+      const int cx = t >> 2, ph = t & 3;
+      low[(2 * cy + (ph >> 1)) * s_low + 2 * cx + (ph & 1)] = __ldg(src + (size_t)(cy * res * 4 + t) * k);
+    }
   __syncthreads();
-  for (int i = threadIdx.x; i < s_hi * s_hi; i += KP_THREADS) {
-    const int y = i / s_hi, x = i - y * s_hi;
-    hi[i] = kp_bilinear_at(low, s_low, y, x);
-  }
+  for (int y = warp; y < s_hi; y += KP_THREADS / 32)
+    for (int x = lane; x < s_hi; x += 32) hi[y * s_hi + x] = kp_bilinear2_at(low, s_low, y, x);
   __syncthreads();
 
   const float4 b = __ldg(reinterpret_cast<const float4*>(boxes) + slot);
@@ -81,7 +83,7 @@ keypoints_decode_kernel(const float* __restrict__ lowres, const float* __restric
   // arg-max of the resized map; first index wins among equal values (torch.argmax on CPU)
   float best = -INFINITY;
   long long best_p = 0x7fffffffffffffffLL;
-  if (WALK && roi.hc <= tab_rows) {      // taller ROIs (> 1024 px at res 14) take the flat loop below
+  if (WALK && kp_walk_applies(roi.hc, roi.wc, tab_rows)) {      // taller ROIs (> 1024 px at res 14) take the flat loop below
     KpW4* wtab = reinterpret_cast<KpW4*>(hi + s_hi * s_hi);               // [tab_rows]; 20 res^2 floats precede: 16-byte aligned
     int* btab = reinterpret_cast<int*>(wtab + tab_rows);                  // [tab_rows]
     for (int oy = threadIdx.x; oy < roi.hc; oy += KP_THREADS) {
@@ -122,7 +124,6 @@ keypoints_decode_kernel(const float* __restrict__ lowres, const float* __restric
     const long long p2 = __shfl_xor_sync(0xffffffffu, best_p, d);
     if (v2 > best || (v2 == best && p2 < best_p)) { best = v2; best_p = p2; }
   }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) { red_v[warp] = best; red_p[warp] = best_p; }
   __syncthreads();
   if (threadIdx.x == 0) {

@@ -49,6 +49,34 @@ KP_HD float kp_bilinear_at(const float* low, int in_size, int oy, int ox) {
   return fmaf(t1, ly, out);
 }
 
+// The same taps without float index arithmetic: for scale 1/2 the source coordinate of o = 2i is i - 1/4 (clamped to 0
+// for o = 0) and of o = 2i + 1 is i + 1/4, so the weights are the exact constants 3/4, 1/4 (or 0) and both
+// formulations give bit-identical results (checked exhaustively per size in tests/test_keypoint_math.py).
+KP_HD void kp_bilinear2_src(int o, int in_size, int& i0, int& i1, float& l1) {
+  const int i = o >> 1;
+  if (o & 1) {
+    i0 = i;
+    l1 = 0.25f;
+  } else {
+    i0 = i > 0 ? i - 1 : 0;
+    l1 = i > 0 ? 0.75f : 0.f;
+  }
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+}
+KP_HD float kp_bilinear2_at(const float* low, int in_size, int oy, int ox) {
+  int y0, y1, x0, x1;
+  float ly, lx;
+  kp_bilinear2_src(oy, in_size, y0, y1, ly);
+  kp_bilinear2_src(ox, in_size, x0, x1, lx);
+  const float wy0 = 1.f - ly, wx0 = 1.f - lx;
+  float t0 = low[y0 * in_size + x0] * wx0;
+  t0 = fmaf(low[y0 * in_size + x1], lx, t0);
+  float t1 = low[y1 * in_size + x0] * wx0;
+  t1 = fmaf(low[y1 * in_size + x1], lx, t1);
+  float out = t0 * wy0;
+  return fmaf(t1, ly, out);
+}
+
 struct KpCubic {
   int idx[4];      // clamped source indices
   float w[4];      // cubic convolution coefficients
@@ -162,6 +190,12 @@ KP_HD KpSplit kp_split(int hc, int wc, int nthreads) {
   return s;
 }
 
+// Which ROIs take the column walk: those whose rows fit the y-tap table and whose item count fits 31 bits (wc up to
+// 2^20 with at most tab_rows / KP_MIN_SEG segments); the others take the flat per-pixel loop.
+KP_HD bool kp_walk_applies(int hc, int wc, int tab_rows) {
+  return hc <= tab_rows && tab_rows <= 2048 && wc <= (1 << 20);
+}
+
 // The column walk of thread `tid`: for each of its (column, segment) items the x taps are computed once, the x pass of
 // the four source rows under the current resized row is kept in registers and advanced when the source row changes
 // (once per hc / in_size rows), and a resized pixel costs the four y FMAs + a compare.  Same expression tree per pixel
@@ -173,9 +207,12 @@ KP_HD KpBest kp_column_walk(const Mem& m, int in_size, int hc, int wc, float sca
   best.v = -INFINITY;
   best.p = 0x7fffffffffffffffLL;
   const KpSplit sp = kp_split(hc, wc, nthreads);
-  for (long long item = tid; item < sp.items; item += nthreads) {
-    const int seg = (int)(item / wc);
-    const int ox = (int)(item - (long long)seg * wc);
+  // precondition (kp_walk_applies): the item count fits 31 bits, so the item -> (segment, column) split is one
+  // 32-bit division per item (the 64-bit one was ~190 instructions per item in the first version)
+  const unsigned items = (unsigned)sp.items, uwc = (unsigned)wc;
+  for (unsigned item = (unsigned)tid; item < items; item += (unsigned)nthreads) {
+    const int seg = (int)(item / uwc);
+    const int ox = (int)(item - (unsigned)seg * uwc);
     const int row0 = seg * sp.seg_len;
     const int row1 = row0 + sp.seg_len < hc ? row0 + sp.seg_len : hc;
     const KpCubic cx = kp_cubic_taps(scale_x, ox, in_size);

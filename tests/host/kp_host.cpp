@@ -17,7 +17,7 @@ extern "C" void kp_host_decode(const float* lowres, const float* boxes, int r, i
       for (int y = 0; y < s_low; ++y)
         for (int x = 0; x < s_low; ++x) low[y * s_low + x] = lowres[kp_lowres_offset(roi, y, x, kp, res, k)];
       for (int y = 0; y < s_hi; ++y)
-        for (int x = 0; x < s_hi; ++x) hi[y * s_hi + x] = kp_bilinear_at(low.data(), s_low, y, x);
+        for (int x = 0; x < s_hi; ++x) hi[y * s_hi + x] = kp_bilinear2_at(low.data(), s_low, y, x);
       if (hi_out)
         for (int i = 0; i < s_hi * s_hi; ++i) hi_out[((size_t)roi * k + kp) * s_hi * s_hi + i] = hi[i];
       const float* b = boxes + 4 * roi;
@@ -25,7 +25,7 @@ extern "C" void kp_host_decode(const float* lowres, const float* boxes, int r, i
       const float sy = (float)s_hi / (float)g.hc, sx = (float)s_hi / (float)g.wc;
       float best = -INFINITY;
       long long best_p = 0;
-      if (walk_threads > 0 && g.hc <= tab_rows) {
+      if (walk_threads > 0 && kp_walk_applies(g.hc, g.wc, tab_rows)) {
         // the kernel's default decomposition: every thread's column walk, merged like the block reduction
         std::vector<KpW4> wtab;
         std::vector<int> btab;
@@ -69,4 +69,16 @@ extern "C" void kp_host_decode(const float* lowres, const float* boxes, int r, i
       o[2] = best;
       o[3] = 1.0f / pool;
     }
+}
+
+// number of pixels of the x2 map where the constant-weight formulation differs (bitwise) from the float-index one
+extern "C" int kp_host_bilinear_mismatches(const float* low, int in_size) {
+  using namespace cm2;
+  int bad = 0;
+  for (int y = 0; y < 2 * in_size; ++y)
+    for (int x = 0; x < 2 * in_size; ++x) {
+      const float a = kp_bilinear_at(low, in_size, y, x), b = kp_bilinear2_at(low, in_size, y, x);
+      if (!(a == b)) ++bad;
+    }
+  return bad;
 }

@@ -82,3 +82,13 @@ def test_column_walk_decomposition_is_bit_identical_to_the_flat_loop(host_lib, t
     host_lib.kp_host_decode(packed.data_ptr(), boxes.data_ptr(), r, res, k, flat.data_ptr(), None, 0, 0)
     host_lib.kp_host_decode(packed.data_ptr(), boxes.data_ptr(), r, res, k, walk.data_ptr(), None, threads, tab_rows)
     assert torch.equal(flat, walk), (flat - walk).abs().amax(dim=(1, 2))
+
+
+@pytest.mark.parametrize("size", [2, 3, 14, 28, 48])
+def test_bilinear_x2_constant_weights_equal_float_index_formulation(host_lib, size):
+    """kp_bilinear2_at (weights 1/4, 3/4, 0 from the parity of the output index: what the kernel runs) against
+    kp_bilinear_at (ATen's float source-index arithmetic): bit-identical on every pixel."""
+    g = torch.Generator().manual_seed(size)
+    low = (torch.randn(size, size, generator=g) * 3.0).contiguous()
+    host_lib.kp_host_bilinear_mismatches.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    assert host_lib.kp_host_bilinear_mismatches(low.data_ptr(), size) == 0
