@@ -70,7 +70,9 @@ def encode(masks):
 
 def instances_to_coco_json(instances, img_id):
     """``coco_evaluation.py:362-427`` for the fields this path produces (boxes XYXY -> XYWH, scores, classes, RLE
-    segmentation with utf-8 ``counts``, ``mask_score``)."""
+    segmentation with utf-8 ``counts``, ``mask_score``, and -- with the keypoint branch -- ``keypoints`` as the flat
+    [x, y, score] * K list with x, y shifted by -0.5 to COCO's pixel-index convention, ``:418-425``; the reference
+    shifts ``instances.pred_keypoints`` in place, this function leaves the caller's tensor untouched)."""
     n = len(instances)
     if n == 0:
         return []
@@ -88,6 +90,11 @@ def instances_to_coco_json(instances, img_id):
             rle["counts"] = rle["counts"].decode("utf-8")
         if has_ms:
             mask_scores = instances.mask_scores.tolist()
+    has_kp = instances.has("pred_keypoints")
+    if has_kp:
+        kp = instances.pred_keypoints.detach().float().cpu().clone()
+        kp[:, :, :2] -= 0.5
+        kp = kp.reshape(n, -1).tolist()
     out = []
     for k in range(n):
         res = {"image_id": img_id, "category_id": classes[k], "bbox": boxes[k], "score": scores[k]}
@@ -95,5 +102,7 @@ def instances_to_coco_json(instances, img_id):
             res["segmentation"] = rles[k]
             if has_ms:
                 res["mask_score"] = mask_scores[k]
+        if has_kp:
+            res["keypoints"] = kp[k]
         out.append(res)
     return out

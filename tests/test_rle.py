@@ -87,3 +87,19 @@ def test_gpu_instances_to_coco_json():
     assert out[0]["mask_score"] == 0.5 and isinstance(out[0]["segmentation"]["counts"], str)
     back = oracle_rle.rle_decode(oracle_rle.rle_from_string(out[0]["segmentation"]["counts"]), 20, 30)
     assert np.array_equal(back, m[0].numpy().astype(np.uint8))
+
+
+def test_instances_to_coco_json_keypoints():
+    """coco_evaluation.py:418-425: flat [x, y, score] * K with x, y shifted by -0.5 (no masks -> no device work)."""
+    from centermask2_b200.modeling.compat import Boxes, Instances
+    inst = Instances((20, 30))
+    inst.pred_boxes = Boxes(torch.tensor([[2.0, 3.0, 12.0, 9.0], [0.0, 0.0, 4.0, 4.0]]))
+    inst.scores = torch.tensor([0.9, 0.8])
+    inst.pred_classes = torch.tensor([0, 0])
+    kp = torch.tensor([[[3.5, 4.5, 0.7], [10.0, 8.25, 0.1]], [[1.5, 2.5, 0.3], [0.5, 0.5, 0.2]]])
+    inst.pred_keypoints = kp.clone()
+    out = rle.instances_to_coco_json(inst, 7)
+    assert out[0]["keypoints"] == pytest.approx([3.0, 4.0, 0.7, 9.5, 7.75, 0.1])
+    assert out[1]["keypoints"] == pytest.approx([1.0, 2.0, 0.3, 0.0, 0.0, 0.2])
+    assert torch.equal(inst.pred_keypoints, kp)                   # the caller's tensor is not shifted
+    assert "segmentation" not in out[0]
