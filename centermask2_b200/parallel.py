@@ -19,7 +19,10 @@ def shard_range(n_items, rank, world):
 
 def pack_records(instances_list, r_cap, device=None):
     """list[Instances] -> float32 [len, r_cap, RECORD_FIELDS] (zero padded; field 7 = number of detections).
-    A handful of batched ops for the whole list (one cat per field, one scatter), not a loop of small kernels."""
+
+    This runs on the host once per step in the end-to-end loop, so it is written for few framework calls: one padded
+    batch per field (``pad_sequence`` walks the list in C++) and one strided assignment each -- about a dozen ops for
+    the whole list instead of several per image."""
     n = len(instances_list)
     if n == 0:
         return torch.zeros((0, r_cap, RECORD_FIELDS), dtype=torch.float32, device=device)
@@ -27,23 +30,25 @@ def pack_records(instances_list, r_cap, device=None):
     counts = [min(len(inst), r_cap) for inst in instances_list]
     rec = torch.zeros((n, r_cap, RECORD_FIELDS), dtype=torch.float32, device=dev)
     rec[:, :, 7] = torch.tensor(counts, dtype=torch.float32).to(dev, non_blocking=True).view(n, 1)
-    total = sum(counts)
-    if total:
-        rows = torch.cat([torch.arange(k, dtype=torch.int64) + i * r_cap for i, k in enumerate(counts) if k]).to(dev, non_blocking=True)
-        live = [(inst, k) for inst, k in zip(instances_list, counts) if k]
-        vals = torch.zeros((total, 7), dtype=torch.float32, device=dev)
-        vals[:, :4] = torch.cat([inst.pred_boxes.tensor[:k] for inst, k in live]).to(dev)
-        vals[:, 4] = torch.cat([inst.scores[:k] for inst, k in live]).to(dev)
-        vals[:, 5] = torch.cat([inst.pred_classes[:k] for inst, k in live]).to(dev, torch.float32)
-        if all(inst.has("mask_scores") for inst, _ in live):
-            vals[:, 6] = torch.cat([inst.mask_scores[:k] for inst, k in live]).to(dev)
-        else:
-            off = 0
-            for inst, k in live:
-                if inst.has("mask_scores"):
-                    vals[off:off + k, 6] = inst.mask_scores[:k].to(dev)
-                off += k
-        rec.view(n * r_cap, RECORD_FIELDS)[rows, :7] = vals
+    m = max(counts)
+    if m:
+        def padded(tensors):
+            return torch.nn.utils.rnn.pad_sequence(tensors, batch_first=True).to(dev)      # [n, m, ...], zero filled
+
+        rec[:, :m, :4] = padded([inst.pred_boxes.tensor[:k] for inst, k in zip(instances_list, counts)])
+        rec[:, :m, 4] = padded([inst.scores[:k] for inst, k in zip(instances_list, counts)])
+        rec[:, :m, 5] = padded([inst.pred_classes[:k] for inst, k in zip(instances_list, counts)]).to(torch.float32)
+        empty = None
+        ms = []
+        for inst, k in zip(instances_list, counts):
+            if inst.has("mask_scores"):
+                ms.append(inst.mask_scores[:k])
+            else:                                   # center_heads.py:511-513: no field on a batch without detections
+                if empty is None:
+                    empty = instances_list[0].scores.new_zeros((0,))
+                ms.append(empty.to(inst.scores.device))
+        ms = padded(ms)                             # [n, longest present]; shorter than m when fields are missing
+        rec[:, :ms.shape[1], 6] = ms
     return rec
 
 
