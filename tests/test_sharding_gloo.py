@@ -77,3 +77,30 @@ def test_gather_records_world2_gloo():
 def test_gather_is_identity_without_process_group():
     local = torch.arange(2 * 3 * parallel.RECORD_FIELDS, dtype=torch.float32).reshape(2, 3, -1)
     assert parallel.gather_records(local, 2) is local
+
+
+def test_pack_records_layout_against_a_plain_loop():
+    """Record layout (x0, y0, x1, y1, score, class, mask_score, count), zero padding, truncation at r_cap, images without
+    detections and without a mask_scores field (center_heads.py:511-513), written out field by field."""
+    r_cap = 6
+    insts = [_fake_instances(i, 9) for i in range(7)]                 # up to 9 detections: some are truncated at r_cap
+    empty = Instances((64, 64))
+    empty.pred_boxes = Boxes(torch.zeros((0, 4)))
+    empty.scores = torch.zeros((0,))
+    empty.pred_classes = torch.zeros((0,), dtype=torch.int64)
+    insts.insert(2, empty)
+    no_ms = _fake_instances(50, 5)
+    no_ms.remove("mask_scores") if no_ms.has("mask_scores") else None
+    insts.append(no_ms)
+    got = parallel.pack_records(insts, r_cap, device="cpu")
+    want = torch.zeros((len(insts), r_cap, parallel.RECORD_FIELDS))
+    for i, inst in enumerate(insts):
+        k = min(len(inst), r_cap)
+        want[i, :, 7] = k
+        want[i, :k, :4] = inst.pred_boxes.tensor[:k]
+        want[i, :k, 4] = inst.scores[:k]
+        want[i, :k, 5] = inst.pred_classes[:k].float()
+        if inst.has("mask_scores"):
+            want[i, :k, 6] = inst.mask_scores[:k]
+    assert torch.equal(got, want)
+    assert parallel.pack_records([empty, empty], r_cap, device="cpu").abs().sum().item() == 0
