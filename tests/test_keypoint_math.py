@@ -92,3 +92,35 @@ def test_bilinear_x2_constant_weights_equal_float_index_formulation(host_lib, si
     low = (torch.randn(size, size, generator=g) * 3.0).contiguous()
     host_lib.kp_host_bilinear_mismatches.argtypes = [ctypes.c_void_p, ctypes.c_int]
     assert host_lib.kp_host_bilinear_mismatches(low.data_ptr(), size) == 0
+
+
+def test_keypoint_decode_properties(host_lib):
+    """Size-independent properties of heatmaps_to_keypoints that hold for any map: (1) translating the box translates
+    the keypoints and leaves logit / score untouched (the resized map depends on the box size only); (2) every keypoint
+    lies inside its (>= 1 px) box; (3) adding a constant to a map adds it to the logit and leaves location and score
+    untouched up to rounding (softmax shift invariance)."""
+    g = torch.Generator().manual_seed(21)
+    res, k, r = 14, 5, 8
+    low = torch.randn(r, k, 2 * res, 2 * res, generator=g) * 2.0
+    boxes = keypoint_boxes(g, r)
+
+    def run(lo, bx):
+        out = torch.zeros(r, k, 4)
+        packed, bx = pack_lowres(lo), bx.contiguous()                      # keep the buffers alive across the C call
+        host_lib.kp_host_decode(packed.data_ptr(), bx.data_ptr(), r, res, k, out.data_ptr(), None, 256, 1024)
+        return out
+
+    base = run(low, boxes)
+    shift = torch.tensor([64.0, -32.0, 64.0, -32.0])                       # exactly representable offsets
+    moved = run(low, boxes + shift)
+    assert torch.allclose(moved[..., 0], base[..., 0] + 64.0, atol=1e-4) and torch.allclose(moved[..., 1], base[..., 1] - 32.0, atol=1e-4)
+    assert torch.equal(moved[..., 2:], base[..., 2:])
+    w = (boxes[:, 2] - boxes[:, 0]).clamp(min=1).view(r, 1)
+    h = (boxes[:, 3] - boxes[:, 1]).clamp(min=1).view(r, 1)
+    assert bool(((base[..., 0] >= boxes[:, 0:1]) & (base[..., 0] <= boxes[:, 0:1] + w)).all())
+    assert bool(((base[..., 1] >= boxes[:, 1:2]) & (base[..., 1] <= boxes[:, 1:2] + h)).all())
+    lifted = run(low + 1.5, boxes)
+    same = ((lifted[..., :2] - base[..., :2]).abs() < 1e-3).all(-1)
+    assert same.float().mean().item() >= 0.95                              # rounding may move a near-tie
+    assert torch.allclose(lifted[..., 2][same], base[..., 2][same] + 1.5, atol=1e-4)
+    assert torch.allclose(lifted[..., 3][same], base[..., 3][same], rtol=1e-4)
