@@ -73,3 +73,15 @@ def test_struct_layout_matches_header():
     assert vals == [C.sizeof(lib.Act), C.sizeof(lib.ConvDesc), lib.ConvDesc.weight.offset, lib.ConvDesc.out.offset,
                     lib.ConvDesc.stats.offset, lib.ConvDesc.src_phase.offset, lib.ConvDesc.seg.offset, C.sizeof(lib.Seg),
                     lib.ConvDesc.stats_mode.offset]
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No fallback path: without the built libcm2.so every product entry raises (nothing silently runs on torch / CPU)."""
+    import pytest as _pytest
+    from centermask2_b200 import lib as cmlib
+    monkeypatch.setattr(cmlib, "_lib", None)
+    monkeypatch.setattr(cmlib, "LIB_PATH", str(tmp_path / "libcm2.so"))
+    with _pytest.raises(RuntimeError, match="no fallback"):
+        cmlib.load()
+    with _pytest.raises(RuntimeError, match="no fallback"):
+        cmlib.last_error()                          # every wrapper goes through load()
