@@ -168,7 +168,7 @@ def make_device_step(model, cfg, dev_images, sizes_out, graph=True):
         return det, mask_scores
 
     if graph and eng.use_graphs:
-        return lambda: eng.graphed(("bench_step", n, tuple(sizes_out)), plan)
+        return lambda: eng.graphed(("bench_step", model.graph_tokens(), n, tuple(sizes_out)), plan, keep=model.packed_refs())
     return plan
 
 

@@ -9,6 +9,7 @@ stripping a ``module.`` prefix (DataParallel / DDP) and ignoring the meta-arch's
 (derived from the cfg here).  After loading, the packed device copies (``packing.py``) are rebuilt lazily on the next
 forward.
 """
+import logging
 import pickle
 from collections import OrderedDict, namedtuple
 
@@ -17,6 +18,7 @@ import torch
 
 IncompatibleKeys = namedtuple("IncompatibleKeys", ["missing_keys", "unexpected_keys", "incorrect_shapes"])
 _IGNORED = ("pixel_mean", "pixel_std")
+_LOG = logging.getLogger("centermask2_b200.checkpoint")
 
 
 def read_checkpoint(path):
@@ -64,14 +66,29 @@ def load_checkpoint(model, path_or_obj, strict=False):
         if k in own and tuple(own[k].shape) != tuple(sd[k].shape):
             bad_shape.append((k, tuple(sd[k].shape), tuple(own[k].shape)))
             sd.pop(k)
+    matched = [k for k in sd if k in own]
+    if own and not matched:
+        # wrong file / wrong prefix: loading "successfully" would leave every weight at its random initial value
+        raise RuntimeError("checkpoint has no key in common with the model (first checkpoint keys: {}; first model keys: {})".format(
+            list(sd)[:3], list(own)[:3]))
     res = model.load_state_dict(sd, strict=False)
-    inc = IncompatibleKeys(list(res.missing_keys), list(res.unexpected_keys), bad_shape)
+    missing = [k for k in res.missing_keys if k not in _IGNORED]
+    inc = IncompatibleKeys(missing, list(res.unexpected_keys), bad_shape)
     if strict and (inc.missing_keys or inc.unexpected_keys or inc.incorrect_shapes):
         raise RuntimeError("checkpoint does not match the model: missing {}, unexpected {}, shape mismatches {}".format(
             inc.missing_keys[:5], inc.unexpected_keys[:5], inc.incorrect_shapes[:5]))
+    # detectron2's Checkpointer logs these; silence here would hide a checkpoint whose names do not match
+    if inc.missing_keys:
+        _LOG.warning("%d model keys are missing from the checkpoint and keep their initial values: %s%s", len(inc.missing_keys),
+                     inc.missing_keys[:8], " ..." if len(inc.missing_keys) > 8 else "")
+    if inc.unexpected_keys:
+        _LOG.warning("%d checkpoint keys are not used by the model: %s%s", len(inc.unexpected_keys), inc.unexpected_keys[:8],
+                     " ..." if len(inc.unexpected_keys) > 8 else "")
+    for k, got, want in inc.incorrect_shapes:
+        _LOG.warning("shape mismatch, skipped: %s checkpoint %s vs model %s", k, got, want)
     for m in model.modules():                       # packed device copies are derived state: rebuild on next use
-        if hasattr(m, "_packed"):
-            m._packed = None
+        if hasattr(m, "_invalidate"):
+            m._invalidate()
     return inc
 
 

@@ -12,7 +12,7 @@ import os
 
 import yaml
 
-__all__ = ["CfgNode", "get_cfg", "lite_overrides"]
+__all__ = ["CfgNode", "get_cfg", "lite_overrides", "validate_cfg"]
 
 
 class CfgNode(dict):
@@ -259,3 +259,38 @@ def lite_overrides():
         "INPUT.MIN_SIZE_TEST", 512,
         "INPUT.MAX_SIZE_TEST", 853,
     ]
+
+
+def validate_cfg(cfg, part):
+    """Refuse, at build time, cfg values the reference honours but this path does not implement -- a silently ignored
+    option would give plausible but different results.  ``part``: "backbone", "fcos" or "roi_heads"."""
+    def need(cond, msg):
+        if not cond:
+            raise NotImplementedError("centermask2_b200: " + msg)
+
+    m = cfg.MODEL
+    if part == "backbone":
+        need(m.FPN.FUSE_TYPE == "sum", "MODEL.FPN.FUSE_TYPE={!r} (only 'sum', the reference's setting at vovnet.py:553)".format(m.FPN.FUSE_TYPE))
+        need(m.FPN.NORM in ("", None), "MODEL.FPN.NORM={!r} (only '' -- FPN convs carry a bias, vovnet.py:551)".format(m.FPN.NORM))
+        need(m.VOVNET.NORM == "FrozenBN", "MODEL.VOVNET.NORM={!r} (inference folds FrozenBN; other norms are out of scope)".format(m.VOVNET.NORM))
+        need(0 <= m.FCOS.TOP_LEVELS <= 2, "MODEL.FCOS.TOP_LEVELS={} (0, 1 or 2: vovnet.py:541-546)".format(m.FCOS.TOP_LEVELS))
+    elif part == "fcos":
+        need(0 < m.FCOS.POST_NMS_TOPK_TEST <= 256, "MODEL.FCOS.POST_NMS_TOPK_TEST={} (the NMS kernel keeps at most 256 detections "
+             "per image)".format(m.FCOS.POST_NMS_TOPK_TEST))
+        need(0 < m.FCOS.PRE_NMS_TOPK_TEST and len(m.FCOS.IN_FEATURES) * m.FCOS.PRE_NMS_TOPK_TEST <= 16384,
+             "MODEL.FCOS.PRE_NMS_TOPK_TEST={} x {} levels exceeds the in-CTA merge (16384 candidates per image)".format(
+                 m.FCOS.PRE_NMS_TOPK_TEST, len(m.FCOS.IN_FEATURES)))
+        need(m.FCOS.NORM in ("GN", "", None, "none"), "MODEL.FCOS.NORM={!r} (GN or none)".format(m.FCOS.NORM))
+    elif part == "roi_heads":
+        heads = [("ROI_MASK_HEAD", m.MASK_ON)] + ([("ROI_KEYPOINT_HEAD", True)] if m.KEYPOINT_ON else [])
+        for name, on in heads:
+            if not on:
+                continue
+            h = m[name]
+            need(h.POOLER_TYPE == "ROIAlignV2", "MODEL.{}.POOLER_TYPE={!r} (only ROIAlignV2, i.e. aligned=True: pooler.py:249-255)".format(
+                name, h.POOLER_TYPE))
+            need(h.ASSIGN_CRITERION in ("ratio", "area"), "MODEL.{}.ASSIGN_CRITERION={!r}".format(name, h.ASSIGN_CRITERION))
+        if m.MASK_ON:
+            need(m.ROI_MASK_HEAD.NORM in ("", None), "MODEL.ROI_MASK_HEAD.NORM={!r} (only '': sam.py:59-68 with bias)".format(m.ROI_MASK_HEAD.NORM))
+    else:
+        raise KeyError(part)

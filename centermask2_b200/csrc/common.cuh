@@ -28,6 +28,28 @@ void set_error(const char* fmt, ...);
     }                                                                            \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute (MODEL.DEVICE=cuda:N selects the device per cfg
+// within one process): remember the largest value set on every device, and fail loudly when the driver refuses it.
+constexpr int CM2_MAX_DEVICES = 64;
+#define CM2_ENSURE_DYN_SMEM(kernel, nbytes, name)                                                                  \
+  do {                                                                                                             \
+    static int set__[cm2::CM2_MAX_DEVICES];                                                                        \
+    int dev__ = 0;                                                                                                 \
+    if (cudaGetDevice(&dev__) != cudaSuccess || dev__ < 0 || dev__ >= cm2::CM2_MAX_DEVICES) {                      \
+      cm2::set_error("%s: cudaGetDevice failed", name);                                                            \
+      return CM2_ERR_CUDA;                                                                                         \
+    }                                                                                                              \
+    if (set__[dev__] < (int)(nbytes)) {                                                                            \
+      cudaError_t e__ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(nbytes));  \
+      if (e__ != cudaSuccess) {                                                                                    \
+        cm2::set_error("%s: cudaFuncSetAttribute(%d bytes of dynamic shared memory) failed: %s", name,             \
+                       (int)(nbytes), cudaGetErrorString(e__));                                                    \
+        return CM2_ERR_CUDA;                                                                                       \
+      }                                                                                                            \
+      set__[dev__] = (int)(nbytes);                                                                                \
+    }                                                                                                              \
+  } while (0)
+
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }

@@ -1565,10 +1565,10 @@ int conv_tc_launch(const cm2_conv_desc* d, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(conv_tc_kernel<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_tc2_kernel<320, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_tc2_kernel<320, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   }
+  CM2_ENSURE_DYN_SMEM(conv_tc_kernel<320>, 227 * 1024, "conv_tc");
+  CM2_ENSURE_DYN_SMEM((conv_tc2_kernel<320, false>), 227 * 1024, "conv_tc2");
+  CM2_ENSURE_DYN_SMEM((conv_tc2_kernel<320, true>), 227 * 1024, "conv_tc2 (pair)");
   if (p.stats) {
     long long imgs = d->src[0].n;
     if (d->num_seg > 0) {

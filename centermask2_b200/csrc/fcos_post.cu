@@ -561,13 +561,9 @@ extern "C" int cm2_fcos_select(const cm2_cand_buffers* cand, int32_t n, int32_t 
   if (n == 0) return CM2_OK;
   cudaStream_t s = (cudaStream_t)stream;
   SelectWs ws = carve_ws(workspace, n, num_levels, pre_topk);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(fcos_select_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
-    cudaFuncSetAttribute(fcos_nms_image_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
-    cudaFuncSetAttribute(fcos_nms_image_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
-    attr_done = true;
-  }
+  CM2_ENSURE_DYN_SMEM(fcos_select_level_kernel, 16384 * 8, "fcos_select_level");
+  CM2_ENSURE_DYN_SMEM(fcos_nms_image_kernel<false>, 16384 * 8, "fcos_nms_image");
+  CM2_ENSURE_DYN_SMEM(fcos_nms_image_kernel<true>, 16384 * 8, "fcos_nms_image");
   dim3 g1(num_levels, n);
   fcos_select_level_kernel<<<g1, 1024, (size_t)sort_a * 8, s>>>(*cand, num_levels, cap, pre_topk, sort_a, ws);
   CM2_CHECK_LAUNCH("fcos_select_level");

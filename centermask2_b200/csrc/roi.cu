@@ -1637,11 +1637,7 @@ static int roialign_launch(const cm2_act* feats, const int32_t* feat_stride, int
   for (int l = 0; l < num_levels; ++l) small = small && feats[l].sn < (1ll << 31);
   p.order = reinterpret_cast<int*>(workspace);
   if (variant == 3 && workspace && p.res < 32 && small && out->c <= 256) {
-    static bool attr_set = false;                        // per instantiation (T)
-    if (!attr_set) {
-      cudaFuncSetAttribute(roialign_ring_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ROI_RING_BYTES);
-      attr_set = true;
-    }
+    CM2_ENSURE_DYN_SMEM(roialign_ring_kernel<T>, ROI_RING_BYTES, "roialign_ring");      // per instantiation (T) and device
     roi_order_kernel<T><<<1, 1024, 0, s>>>(p);
     roialign_ring_kernel<T><<<n * r_cap * ((p.res + ROI_RING_COLS - 1) / ROI_RING_COLS), 32 * (ROI_RING_COLS + 1), ROI_RING_BYTES, s>>>(p);
     return 0;
@@ -1682,12 +1678,14 @@ extern "C" int cm2_roialign_fpn(const cm2_act* feats, const int32_t* feat_stride
   }
   if (n * r_cap == 0) return CM2_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  int rc;
   if (dtype == CM2_F32)
-    roialign_launch<float>(feats, feat_stride, num_levels, boxes, det_count, n, r_cap, image_area, crit, sampling_ratio,
-                           out, level_out, workspace, s);
+    rc = roialign_launch<float>(feats, feat_stride, num_levels, boxes, det_count, n, r_cap, image_area, crit, sampling_ratio,
+                                out, level_out, workspace, s);
   else
-    roialign_launch<__nv_bfloat16>(feats, feat_stride, num_levels, boxes, det_count, n, r_cap, image_area, crit,
-                                   sampling_ratio, out, level_out, workspace, s);
+    rc = roialign_launch<__nv_bfloat16>(feats, feat_stride, num_levels, boxes, det_count, n, r_cap, image_area, crit,
+                                        sampling_ratio, out, level_out, workspace, s);
+  if (rc != CM2_OK) return rc;
   CM2_CHECK_LAUNCH("roialign_fpn");
   return CM2_OK;
 }
@@ -1707,11 +1705,7 @@ extern "C" int cm2_spatial_attention(const cm2_act* x, const cm2_act* out, int32
   if (sam_variant == 1 && dtype == CM2_BF16 && pipe_smem <= 220 * 1024 && x->sw == x->c && x->n >= 2 * 148 &&
       ((size_t)x->w * x->c * 2) % 16 == 0) {
     // persistent double-buffered kernel: worth it once every SM gets at least two ROIs
-    static bool pipe_attr_done = false;
-    if (!pipe_attr_done) {
-      cudaFuncSetAttribute(spatial_attention_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-      pipe_attr_done = true;
-    }
+    CM2_ENSURE_DYN_SMEM(spatial_attention_pipe_kernel, 220 * 1024, "spatial_attention_pipe");
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1721,11 +1715,7 @@ extern "C" int cm2_spatial_attention(const cm2_act* x, const cm2_act* out, int32
     return CM2_OK;
   }
   if (dtype == CM2_BF16 && tile_bytes <= 110 * 1024) {     // two CTAs per SM
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaFuncSetAttribute(spatial_attention_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-      attr_done = true;
-    }
+    CM2_ENSURE_DYN_SMEM(spatial_attention_smem_kernel, 110 * 1024, "spatial_attention_smem");
     spatial_attention_smem_kernel<<<x->n, 512, tile_bytes, s>>>(make_view<const __nv_bfloat16>(*x), make_view<__nv_bfloat16>(*out), w18);
     CM2_CHECK_LAUNCH("spatial_attention_smem");
     return CM2_OK;
@@ -1828,11 +1818,7 @@ extern "C" int cm2_paste_masks(const float* probs, const float* boxes, const uin
     const size_t tile_bytes = std::max((size_t)rows_cap * pitch * 4, (size_t)(m + 4) * (m + 4) * 4);
     const size_t smem = ((size_t)(m + 3) * (m + 3) + rows_cap) * 16 + tile_bytes;
     if (smem <= 200 * 1024) {
-      static size_t attr_smem = 0;
-      if (smem > attr_smem) {
-        cudaFuncSetAttribute(paste_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_smem = smem;
-      }
+      CM2_ENSURE_DYN_SMEM(paste_fused_kernel, smem, "paste_masks_fused");
       paste_fused_kernel<<<dim3(slabs, r), 256, smem, s>>>(probs, boxes, valid, out, m, out_h, out_w, threshold, rows_cap, pitch,
                                                            chunks_per_slab);
       CM2_CHECK_LAUNCH("paste_masks_fused");
@@ -1847,12 +1833,8 @@ extern "C" int cm2_paste_masks(const float* probs, const float* boxes, const uin
   const size_t mask_floats = (size_t)(((m + 2) * (m + 2) + 3) & ~3);
   if (((long long)out_h * out_w) % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0 && out_w <= PASTE_MAX_W) {
     const size_t smem = mask_floats * sizeof(float) + (size_t)out_w * sizeof(PasteCol);
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaFuncSetAttribute(paste_window_words_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(((64 + 2) * (64 + 2) + 4) * sizeof(float) + PASTE_MAX_W * sizeof(PasteCol)));
-      attr_done = true;
-    }
+    CM2_ENSURE_DYN_SMEM(paste_window_words_kernel, ((64 + 2) * (64 + 2) + 4) * sizeof(float) + PASTE_MAX_W * sizeof(PasteCol),
+                        "paste_masks_words");
     paste_window_words_kernel<<<grid, 256, smem, s>>>(probs, boxes, valid, out, m, out_h, out_w, threshold);
     CM2_CHECK_LAUNCH("paste_masks_words");
     return CM2_OK;

@@ -10,6 +10,7 @@ Reference call sequence being replaced: ``GeneralizedRCNN.inference`` [d2] as mi
 -> ``FCOS.forward`` (``fcos/fcos.py:61-118``) -> ``CenterROIHeads.forward`` (``center_heads.py:384-444``)
 -> ``detector_postprocess`` [d2].
 """
+import collections
 import math
 import os
 
@@ -137,9 +138,16 @@ class Engine(object):
         self.dtype = torch.float32 if precision == "fp32" else torch.bfloat16
         self.tc = precision == "bf16"
         self.device = torch.device(device)
-        self._bufs = {}
-        self._graphs = {}
+        self._bufs = collections.OrderedDict()              # least recently used first
+        self._buf_bytes = 0
+        self._graphs = collections.OrderedDict()            # key -> (graph, result, launches, kept-alive objects)
+        self._graph_seen = collections.OrderedDict()        # key -> number of eager runs so far
+        self._recording = None                              # buffers touched while a plan is being captured
+        self._det_gen = 0                                   # bumped by every run_fcos_post (see roi_heads._det_from_instances)
         self.use_graphs = os.environ.get("CM2_GRAPH", "1") != "0"
+        self.graph_after = max(1, int(os.environ.get("CM2_GRAPH_AFTER", "1")))      # eager runs of a key before it is captured
+        self.graph_cache = max(1, int(os.environ.get("CM2_GRAPH_CACHE", "16")))     # captured graphs kept (LRU)
+        self.buffer_budget = int(float(os.environ.get("CM2_BUFFER_BUDGET_GB", "96")) * (1 << 30))
         lib.load()
 
     # -- buffers ---------------------------------------------------------------------------------
@@ -149,7 +157,41 @@ class Engine(object):
         if t is None:
             t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
             self._bufs[key] = t
+            self._buf_bytes += t.numel() * t.element_size()
+        else:
+            self._bufs.move_to_end(key)
+        if self._recording is not None:
+            self._recording.append(t)
         return t
+
+    def const(self, key, make):
+        """Small cached device constant (or tuple of them) under a free-form ``key``; built by ``make()`` on first use."""
+        t = self._bufs.get(key)
+        if t is None:
+            t = make()
+            self._bufs[key] = t
+            for x in (t if isinstance(t, tuple) else (t,)):
+                self._buf_bytes += x.numel() * x.element_size()
+        else:
+            self._bufs.move_to_end(key)
+        if self._recording is not None:
+            self._recording.append(t)
+        return t
+
+    def trim(self):
+        """Between steps: when the cached buffers exceed the budget (a data set with many padded shapes keeps one
+        activation set per shape), drop the least recently used ones.  A buffer a captured graph refers to stays alive
+        through that graph's entry, so dropping it here never invalidates a replay."""
+        if self._buf_bytes <= self.buffer_budget:
+            return
+        for key in list(self._bufs.keys()):
+            if self._buf_bytes <= self.buffer_budget // 2:
+                break
+            t = self._bufs[key]
+            if not isinstance(t, torch.Tensor) or t.is_pinned():
+                continue
+            del self._bufs[key]
+            self._buf_bytes -= t.numel() * t.element_size()
 
     _stage_free = None                                  # event: the staging input buffers have been consumed
 
@@ -184,7 +226,19 @@ class Engine(object):
 
     def release(self):
         self._graphs.clear()
+        self._graph_seen.clear()
         self._bufs.clear()
+        self._buf_bytes = 0
+
+    def drop_graphs(self, owner=None):
+        """Forget captured graphs: all of them, or those whose key carries a ``graph_token`` of module ``owner`` (its
+        packed weights -- whose addresses the capture baked in -- are about to be rebuilt)."""
+        def owned(key):
+            return any(isinstance(k, tuple) and any(isinstance(t, tuple) and len(t) == 3 and t[0] == "cm2w" and t[1] == owner
+                                                    for t in k) for k in key)
+        for d in (self._graphs, self._graph_seen):
+            for key in [k for k in d if owner is None or owned(k)]:
+                del d[key]
 
     # -- one convolution -------------------------------------------------------------------------
     def conv(self, name, srcs, w, out_dtype=None, residual=None, res_mode=0, out_mode=0, in_relu=False,
@@ -524,16 +578,16 @@ class Engine(object):
         det = dict(boxes=B("det_boxes", (n, post, 4), torch.float32, False), scores=B("det_scores", (n, post), torch.float32, False),
                    classes=B("det_classes", (n, post), torch.int64, False), locations=B("det_locs", (n, post, 2), torch.float32, False),
                    count=B("det_count", (n,), torch.int32, False))
-        lw_key = ("level_w", tuple(h[0].w for h in head_out))
-        if lw_key not in self._bufs:
-            self._bufs[lw_key] = (torch.tensor([h[0].w for h in head_out], dtype=torch.int32, device=self.device),
-                                  torch.tensor(strides[:L], dtype=torch.int32, device=self.device))
-        level_w, level_s = self._bufs[lw_key]
+        level_w, level_s = self.const(("level_w", tuple(h[0].w for h in head_out), tuple(strides[:L])), lambda: (
+            torch.tensor([h[0].w for h in head_out], dtype=torch.int32, device=self.device),
+            torch.tensor(strides[:L], dtype=torch.int32, device=self.device)))
         wsp = B("select_ws", (lib.fcos_select_workspace(n, L, cap),), torch.uint8, False)
         lib.fcos_select(cand, n, L, cap, level_w, level_s, ncls, min(pre, cap), float(cfg.MODEL.FCOS.NMS_TH), post,
                         lib.det_buffers(det["boxes"], det["scores"], det["classes"], det["locations"], det["count"]), wsp)
         det["cand_count"] = cb["count"]
         det["cand_cap"] = cap
+        self._det_gen += 1
+        det["gen"] = self._det_gen
         return det
 
     # =============================================================================================
@@ -588,6 +642,11 @@ class Engine(object):
             P["iou_out"] = packing.linear(sd, prefix + "maskiou_head.maskiou", False, dt, dev, tc)
         return P
 
+    def image_area(self, image_sizes):
+        """Unpadded image areas (pooler.py:70-77) as a device vector, cached per size list."""
+        return self.const(("img_area", tuple(image_sizes)), lambda: torch.tensor(
+            [float(h * w) for h, w in image_sizes], dtype=torch.float32, device=self.device))
+
     def run_roi_heads(self, feats, strides, det, image_sizes, P):
         """center_heads.py:413-444 on fixed-size ROI slots [N*R].  feats: list of FMap (p3..p5).
         Returns (mask probs f32 [N*R, 1, 2*res, 2*res], mask_scores f32 [N*R] or None)."""
@@ -596,10 +655,7 @@ class Engine(object):
         n, r_cap = det["boxes"].shape[0], det["boxes"].shape[1]
         R = n * r_cap
         res = mh.POOLER_RESOLUTION
-        key = ("img_area", tuple(image_sizes))
-        if key not in self._bufs:
-            self._bufs[key] = torch.tensor([float(h * w) for h, w in image_sizes], dtype=torch.float32, device=self.device)
-        area = self._bufs[key]
+        area = self.image_area(image_sizes)
         roi = self.fmap("roi_feat", R, res, res, P["in_ch"])
         crit = 0 if mh.ASSIGN_CRITERION == "ratio" else 1
         lib.roialign_fpn([f.view for f in feats], strides, det["boxes"], det["count"], n, r_cap, area, crit,
@@ -649,11 +705,8 @@ class Engine(object):
         n, r_cap = det["boxes"].shape[0], det["boxes"].shape[1]
         R = n * r_cap
         res, nk = kh.POOLER_RESOLUTION, kh.NUM_KEYPOINTS
-        key = ("img_area", tuple(image_sizes))
-        if key not in self._bufs:
-            self._bufs[key] = torch.tensor([float(h * w) for h, w in image_sizes], dtype=torch.float32, device=self.device)
         roi = self.fmap("kp_roi_feat", R, res, res, P["kp_in_ch"])
-        lib.roialign_fpn([f.view for f in feats], strides, det["boxes"], det["count"], n, r_cap, self._bufs[key],
+        lib.roialign_fpn([f.view for f in feats], strides, det["boxes"], det["count"], n, r_cap, self.image_area(image_sizes),
                          0 if kh.ASSIGN_CRITERION == "ratio" else 1, int(kh.POOLER_SAMPLING_RATIO), roi.view,
                          workspace=self.buffer("kp_roi_order", (max(R, 1),), torch.int32, False))
         x = roi
@@ -707,14 +760,16 @@ class Engine(object):
         """Box half of detector_postprocess for the whole batch (one launch): det_boxes [n, r_cap, 4] ->
         (boxes' [n, r_cap, 4], valid u8 [n, r_cap]) in engine-owned buffers."""
         n, r_cap = det_boxes.shape[0], det_boxes.shape[1]
-        key = ("pp_params", tuple(sizes), tuple(out_sizes))
-        if key not in self._bufs:
-            self._bufs[key] = torch.tensor([[ow / sz[1], oh / sz[0], float(ow), float(oh)] for (oh, ow), sz in zip(out_sizes, sizes)],
-                                           dtype=torch.float32, device=self.device)
         boxes = self.buffer("pp_boxes", (n, r_cap, 4), torch.float32, False)
         valid = self.buffer("pp_valid", (n, r_cap), torch.uint8, False)
-        lib.scale_clip_boxes_batch(det_boxes, boxes, valid, n, r_cap, self._bufs[key])
+        lib.scale_clip_boxes_batch(det_boxes, boxes, valid, n, r_cap, self.pp_params(sizes, out_sizes))
         return boxes, valid
+
+    def pp_params(self, sizes, out_sizes):
+        """Per image (scale_x, scale_y, out_w, out_h) of detector_postprocess [d2], cached per (sizes, out_sizes)."""
+        return self.const(("pp_params", tuple(sizes), tuple(out_sizes)), lambda: torch.tensor(
+            [[ow / sz[1], oh / sz[0], float(ow), float(oh)] for (oh, ow), sz in zip(out_sizes, sizes)],
+            dtype=torch.float32, device=self.device))
 
     def paste_batch(self, probs, boxes, valid, out_sizes, masks=None, threshold=0.5, dtype=torch.uint8):
         """Mask half of detector_postprocess: probs [n*r_cap, 1, m, m] -> list of [r_cap, oh, ow] 0/1 byte masks
@@ -738,24 +793,46 @@ class Engine(object):
     # =============================================================================================
     # CUDA-graph replay of a launch plan
     # =============================================================================================
-    def graphed(self, key, fn):
-        """Run ``fn`` (a sequence of C-ABI launches on engine-owned buffers, no host sync) through a CUDA graph:
-        the first call with a given ``key`` runs it eagerly once (allocates every buffer), captures it, and every
-        call replays the capture -- the ~170 launches of a step cost one graph launch on the host.  Returns whatever
-        ``fn`` returned at capture time (the same engine-owned buffers every call).  ``CM2_GRAPH=0`` disables."""
+    def graphed(self, key, fn, keep=None):
+        """Run ``fn`` (a sequence of C-ABI launches on engine-owned buffers, no host sync) through a CUDA graph.
+
+        The first ``graph_after`` calls with a given ``key`` run eagerly (they also allocate every buffer and fill the
+        lazily cached constants); the next one captures the plan, and every later call replays the capture -- the ~100
+        launches of a step cost one graph launch on the host.  A key that is seen only once (a data set whose images
+        all differ in shape) therefore never pays for a capture.  Returns whatever ``fn`` returned (the same engine-owned
+        buffers every call).  Captured graphs are kept least-recently-used up to ``graph_cache``; an entry keeps alive
+        every buffer the plan touched plus ``keep`` (the packed weights whose addresses are baked into it), and
+        ``key`` must carry the ``graph_token`` of every module whose weights the plan reads so that re-packed weights
+        can never be replayed (``drop_graphs``).  ``CM2_GRAPH=0`` disables."""
         if not self.use_graphs:
             return fn()
         ent = self._graphs.get(key)
         if ent is None:
-            fn()                                        # warm-up: buffer allocation, lazily cached constants
+            seen = self._graph_seen.get(key, 0)
+            if seen < self.graph_after:
+                self._graph_seen[key] = seen + 1
+                self._graph_seen.move_to_end(key)
+                while len(self._graph_seen) > 64 * self.graph_cache:
+                    self._graph_seen.popitem(last=False)
+                return fn()
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             c0 = lib.launch_count
-            with torch.cuda.graph(g):
-                out = fn()
-            ent = (g, out, lib.launch_count - c0)
+            self._recording = []
+            try:
+                with torch.cuda.graph(g):
+                    out = fn()
+                touched = self._recording
+            finally:
+                self._recording = None
+            ent = (g, out, lib.launch_count - c0, (touched, keep))
             self._graphs[key] = ent
-        g, out, launches = ent
+            self._graph_seen.pop(key, None)
+            while len(self._graphs) > self.graph_cache:
+                self._graphs.popitem(last=False)
+        else:
+            self._graphs.move_to_end(key)
+        g, out, launches = ent[0], ent[1], ent[2]
         g.replay()
         lib._count(launches)
         return out

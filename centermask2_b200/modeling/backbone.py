@@ -4,6 +4,7 @@ Replaces ``centermask/modeling/backbone/vovnet.py:527-555`` (builder), ``:380-48
 ``:263-376`` (OSA), ``fpn.py:17-35`` (LastLevelP6P7) and detectron2's ``FPN`` [d2].
 """
 from .. import runtime
+from ..config import validate_cfg
 from ..arch import backbone_param_spec, vovnet_blocks
 from .compat import BACKBONE_REGISTRY, ShapeSpec
 from .params import PackedModule, attach_params
@@ -18,6 +19,7 @@ class VoVNetFPN(PackedModule):
     def __init__(self, cfg, input_shape=None):
         super().__init__()
         self.cfg = cfg
+        validate_cfg(cfg, "backbone")
         attach_params(self, backbone_param_spec(cfg))
         fc = cfg.MODEL.FPN.OUT_CHANNELS
         self._size_divisibility = 32

@@ -9,6 +9,7 @@ whenever a level has <= PRE_NMS_TOPK_TEST candidates above the threshold.
 import torch
 
 from .. import runtime
+from ..config import validate_cfg
 from ..arch import fcos_param_spec
 from ..engine import as_fmap
 from .compat import PROPOSAL_GENERATOR_REGISTRY, Boxes, Instances
@@ -20,6 +21,7 @@ class FCOS(PackedModule):
     def __init__(self, cfg, input_shape):
         super().__init__()
         self.cfg = cfg
+        validate_cfg(cfg, "fcos")
         self.in_features = list(cfg.MODEL.FCOS.IN_FEATURES)                 # fcos.py:35
         self.fpn_strides = list(cfg.MODEL.FCOS.FPN_STRIDES)
         chans = {input_shape[f].channels for f in self.in_features}

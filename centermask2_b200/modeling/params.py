@@ -50,10 +50,20 @@ class PackedModule(nn.Module):
         self.training = False
         self._packed = None
         self._engine = None
+        self._pack_gen = 0
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
 
     def _invalidate(self):
+        """The parameters changed (``load_state_dict``, ``load_checkpoint``, ``.to()``): drop the packed device copies AND
+        every CUDA graph that was captured with their addresses baked in -- a replay would read freed / stale weights."""
         self._packed = None
+        self._pack_gen += 1
+        if self._engine is not None:
+            self._engine.drop_graphs(id(self))
+
+    def graph_token(self):
+        """Identity of this module's packed weights for CUDA-graph keys: (module, weight generation)."""
+        return ("cm2w", id(self), self._pack_gen)
 
     def _apply(self, fn, *a, **k):
         self._invalidate()

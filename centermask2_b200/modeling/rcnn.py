@@ -142,6 +142,7 @@ class GeneralizedRCNN(nn.Module):
         """Enqueue the whole device side of one batch (inputs -> graph replay -> result snapshots -> paste-back) without
         waiting for it.  ``slot`` selects the set of pinned host buffers, so that two batches can be in flight."""
         eng = runtime.engine_for(self.cfg)
+        eng.trim()
         n = len(batched_inputs)
         sizes = [(int(b["image"].shape[-2]), int(b["image"].shape[-1])) for b in batched_inputs]
         roi = self.roi_heads
@@ -167,7 +168,10 @@ class GeneralizedRCNN(nn.Module):
                 boxes, valid = eng.rescale_boxes(det["boxes"], sizes, out_sizes)
             return det, probs, mask_scores, boxes, valid, kps
 
-        det, probs, mask_scores, boxes, valid, kps = eng.graphed(("inference", sig, tuple(out_sizes), bool(do_postprocess)), plan)
+        # the key names the weights the capture bakes in (module identity + weight generation): a model whose weights were
+        # reloaded, or a second model built from the same cfg, can never replay another capture
+        det, probs, mask_scores, boxes, valid, kps = eng.graphed(
+            ("inference", self.graph_tokens(), sig, tuple(out_sizes), bool(do_postprocess)), plan, keep=self.packed_refs())
         r_cap = det["boxes"].shape[1]
         # one snapshot of the small per-detection tensors (the engine reuses its buffers on the next call)
         scores, classes, locs = det["scores"].clone(), det["classes"].clone(), det["locations"].clone()
@@ -176,7 +180,7 @@ class GeneralizedRCNN(nn.Module):
         if kps is not None:
             keypoints = torch.cat([kps[..., :2], kps[..., 3:4]], dim=-1)   # keypoint_head.py:116 (x, y, score); a copy
             if do_postprocess:                                          # detector_postprocess [d2]: x *= scale_x, y *= scale_y
-                pp = eng._bufs[("pp_params", tuple(sizes), tuple(out_sizes))]
+                pp = eng.pp_params(sizes, out_sizes)
                 keypoints[..., 0] *= pp[:, 0].view(n, 1, 1)
                 keypoints[..., 1] *= pp[:, 1].view(n, 1, 1)
         h_count = eng.pinned("h_count{}".format(slot), (n,), torch.int32)
@@ -203,6 +207,13 @@ class GeneralizedRCNN(nn.Module):
                     classes=classes, locs=locs, mscores=mscores, boxes=boxes, masks=masks, pm=None if do_postprocess else pm,
                     ready=ready, h_count=h_count, h_cand=h_cand, h_valid=h_valid if do_postprocess else None,
                     cand_cap=det["cand_cap"], have_probs=probs is not None, keypoints=keypoints)
+
+    def graph_tokens(self):
+        return tuple(m.graph_token() for m in (self.backbone, self.proposal_generator, self.roi_heads))
+
+    def packed_refs(self):
+        """The packed weight objects of the three plug-ins (packing them if needed): kept alive by a captured graph."""
+        return tuple(m._pack()[1] for m in (self.backbone, self.proposal_generator, self.roi_heads))
 
     def _finish(self, ctx):
         """Wait for the small result-size tensors of a launched batch and cut the per-image ``Instances`` out."""

@@ -8,6 +8,7 @@ Replaces ``centermask/modeling/centermask/center_heads.py:295-553`` (inference b
 import torch
 
 from .. import runtime
+from ..config import validate_cfg
 from ..arch import roi_heads_param_spec
 from ..engine import as_fmap
 from .compat import ROI_HEADS_REGISTRY, Registry
@@ -42,6 +43,7 @@ class CenterROIHeads(PackedModule):
     def __init__(self, cfg, input_shape):
         super().__init__()
         self.cfg = cfg
+        validate_cfg(cfg, "roi_heads")
         self.in_features = list(cfg.MODEL.ROI_HEADS.IN_FEATURES)                 # center_heads.py:121
         self.mask_on = bool(cfg.MODEL.MASK_ON)
         self.maskiou_on = bool(cfg.MODEL.MASKIOU_ON)
@@ -115,7 +117,14 @@ def _det_from_instances(instances, eng):
     tags = [getattr(i, "_cm2_det", None) for i in instances]
     if all(t is not None for t in tags) and all(t[0] is tags[0][0] and t[1] == k for k, t in enumerate(tags)) \
             and tags[0][0]["boxes"].shape[0] == len(instances):
-        return tags[0][0]
+        det = tags[0][0]
+        # The tag only says where the Instances came from.  The engine's detection buffers are shared: another FCOS forward
+        # since then (generation stamp) or a caller that refined pred_boxes / pred_classes in place (content check) means
+        # the buffers no longer describe THESE instances -- then the given boxes are packed instead.
+        if det.get("gen") == eng._det_gen and all(
+                len(i) <= det["boxes"].shape[1] and torch.equal(det["boxes"][k, :len(i)], i.pred_boxes.tensor)
+                and torch.equal(det["classes"][k, :len(i)], i.pred_classes) for k, i in enumerate(instances)):
+            return det
     n = len(instances)
     r_cap = max(1, max(len(i) for i in instances))
     dev = eng.device

@@ -66,3 +66,39 @@ def test_bare_state_dict_invalidates_packed_weights(case):
     inc = checkpoint.load_checkpoint(model, dict(sd), strict=True)
     assert not inc.missing_keys and model.backbone._packed is None
     assert _same(model, sd)
+
+
+def test_unrelated_checkpoint_is_refused_and_mismatches_are_logged(caplog):
+    """A file whose names do not match must not leave random-init weights behind silently (detectron2 logs these)."""
+    import logging
+    import pytest
+    import centermask2_b200 as cm
+    from centermask2_b200.checkpoint import load_checkpoint
+    cfg = cm.get_cfg("centermask_V_39_eSE_FPN.yaml", ["MODEL.VOVNET.CONV_BODY", "V-19-eSE"])
+    model = cm.modeling.FCOS(cfg, {k: cm.modeling.ShapeSpec(channels=256, stride=2 ** int(k[1])) for k in cfg.MODEL.FCOS.IN_FEATURES})
+    with pytest.raises(RuntimeError, match="no key in common"):
+        load_checkpoint(model, {"model": {"some.other.net.weight": torch.zeros(3)}})
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    dropped = sorted(sd)[0]
+    sd.pop(dropped)
+    sd["extra.key"] = torch.zeros(1)
+    with caplog.at_level(logging.WARNING, logger="centermask2_b200.checkpoint"):
+        inc = load_checkpoint(model, {"model": sd})
+    assert inc.missing_keys == [dropped] and inc.unexpected_keys == ["extra.key"]
+    text = caplog.text
+    assert "missing from the checkpoint" in text and "not used by the model" in text
+
+
+def test_unsupported_cfg_values_are_refused_at_build_time():
+    import pytest
+    import centermask2_b200 as cm
+    from centermask2_b200.config import validate_cfg
+    base = ["MODEL.VOVNET.CONV_BODY", "V-19-eSE"]
+    for part in ("backbone", "fcos", "roi_heads"):
+        validate_cfg(cm.get_cfg("centermask_V_39_eSE_FPN.yaml", base), part)
+    for part, opts in (("backbone", ["MODEL.FPN.FUSE_TYPE", "avg"]), ("backbone", ["MODEL.FPN.NORM", "GN"]),
+                       ("backbone", ["MODEL.VOVNET.NORM", "BN"]), ("fcos", ["MODEL.FCOS.POST_NMS_TOPK_TEST", 300]),
+                       ("roi_heads", ["MODEL.ROI_MASK_HEAD.POOLER_TYPE", "ROIAlign"]),
+                       ("roi_heads", ["MODEL.ROI_MASK_HEAD.NORM", "GN"])):
+        with pytest.raises(NotImplementedError):
+            validate_cfg(cm.get_cfg("centermask_V_39_eSE_FPN.yaml", base + opts), part)
