@@ -259,7 +259,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
-    ap.add_argument("--precision", default=os.environ.get("CM2_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("CM2_PRECISION", "bf16"), choices=["bf16", "fp32", "fp32_simt"],
+                    help="bf16: bf16 activations, tcgen05 convolutions; fp32: fp32 activations, split-precision (f16 hi/lo) "
+                         "tcgen05 convolutions with fp32-grade accuracy; fp32_simt: fp32 on CUDA cores")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--clock-ms", type=int, default=int(os.environ.get("CM2_CLOCK_MS", "20")),

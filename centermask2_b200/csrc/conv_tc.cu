@@ -85,6 +85,12 @@ struct alignas(64) TcParams {
   int pair;                 // v2 only: 1 = launched as CTA pairs, cta_group::2 MMAs (see conv_tc2_kernel<.., true>)
   int variant;              // host only: 1 = conv_tc_kernel (128-row tiles), 2 = conv_tc2_kernel
   unsigned smem_bytes;      // host only: dynamic shared memory of the launch
+  uint32_t idesc_ab;        // operand format bits of the instruction descriptor: bf16 (1 << 7 | 1 << 10) or f16 (0)
+  int res_f32;              // the residual tensor is fp32 (split-precision convolutions), else bf16
+  // ---- v3 kernel (split precision): src_c[] holds the LOGICAL channel counts, a source matrix is [rows][hi(c) | lo(c)]
+  int split;                // 1: conv_tc3_kernel
+  int chunk;                // main-accumulator K-blocks between two drains into the fp32 register sums
+  int cout_pad;             // W_lo tiles start cout_pad rows below the W_hi tiles in the weight matrix
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -257,6 +263,14 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile (rows of 128 bytes, 8-row groups 1024 bytes apart):
 //   start address >> 4 | LBO (ignored for swizzled K-major) = 1 | SBO = 1024 >> 4 | version 1 | SWIZZLE_128B
@@ -354,9 +368,13 @@ __device__ __forceinline__ void tc_epilogue_rows(const TcParams& p, const TileGe
     out_off = (long long)((y & 1) * 2 + (x & 1)) * p.out_plane + (long long)img * p.out_sn +
               (long long)(y >> 1) * p.out_sh + (long long)(x >> 1) * p.out_sw;
   const __nv_bfloat16* res_row = nullptr;
-  if (p.res_mode && interior)
-    res_row = p.res + (long long)img * p.res_sn + (long long)(p.res_mode == 2 ? (y >> 1) : y) * p.res_sh +
-              (long long)(p.res_mode == 2 ? (x >> 1) : x) * p.res_sw;
+  const float* res_row_f = nullptr;
+  if (p.res_mode && interior) {
+    const long long roff = (long long)img * p.res_sn + (long long)(p.res_mode == 2 ? (y >> 1) : y) * p.res_sh +
+                           (long long)(p.res_mode == 2 ? (x >> 1) : x) * p.res_sw;
+    if (p.res_f32) res_row_f = reinterpret_cast<const float*>(p.res) + roff;
+    else res_row = p.res + roff;
+  }
 
   for (int c0 = 0; c0 < p.bn; c0 += 16) {
     uint32_t raw[16];
@@ -373,6 +391,11 @@ __device__ __forceinline__ void tc_epilogue_rows(const TcParams& p, const TileGe
       v[4 * j4 + 1] = fmaf(__uint_as_float(raw[4 * j4 + 1]), sc.y, sh.y);
       v[4 * j4 + 2] = fmaf(__uint_as_float(raw[4 * j4 + 2]), sc.z, sh.z);
       v[4 * j4 + 3] = fmaf(__uint_as_float(raw[4 * j4 + 3]), sc.w, sh.w);
+    }
+    if (res_row_f) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (co0 + j < p.cout) v[j] += __ldg(res_row_f + co0 + j);
     }
     if (res_row) {
       if (p.out_vec) {
@@ -554,6 +577,7 @@ __device__ __forceinline__ int tc_fast_div(int n, int d, double rcp) {          
 template <bool F32, bool RES, int STATS, bool DECONV>
 __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const TileGeom& g, uint32_t taddr, int m, int n0,
                                                         uint32_t stage_smem, int lane, uint32_t ss_smem, int cset, int ncset) {
+  constexpr int esize_res = F32 ? 4 : 2;             // the residual has the output's element type
   const int mr = m - g.row0;
   bool in_range = mr >= 0 && mr < g.rows, interior = false;
   int img = 0, y = 0, x = 0;
@@ -580,10 +604,12 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
   else
     out_off = (long long)((y & 1) * 2 + (x & 1)) * p.out_plane + (long long)img * p.out_sn +
               (long long)(y >> 1) * p.out_sh + (long long)(x >> 1) * p.out_sw;
-  const __nv_bfloat16* res_row = nullptr;
+  // residual row: bf16, or fp32 when the output is fp32 (split-precision convolutions)
+  const char* res_row = nullptr;
   if (RES && interior)
-    res_row = p.res + (long long)img * p.res_sn + (long long)(p.res_mode == 2 ? (y >> 1) : y) * p.res_sh +
-              (long long)(p.res_mode == 2 ? (x >> 1) : x) * p.res_sw;
+    res_row = reinterpret_cast<const char*>(p.res) +
+              ((long long)img * p.res_sn + (long long)(p.res_mode == 2 ? (y >> 1) : y) * p.res_sh +
+               (long long)(p.res_mode == 2 ? (x >> 1) : x) * p.res_sw) * esize_res;
   const unsigned store_mask = __ballot_sync(0xffffffffu, do_store);      // rows of this warp that get written
   const unsigned int_mask = __ballot_sync(0xffffffffu, interior);
   const bool all_int = int_mask == 0xffffffffu;
@@ -612,9 +638,12 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
     const bool has_res = RES && res_row != nullptr && co0 < p.cout;
     if (RES && has_res) {                                     // issue the residual loads before waiting on TMEM
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (8 * j < cpp && co0 + 8 * j < p.cout) rres[j] = __ldg(reinterpret_cast<const uint4*>(res_row + co0 + 8 * j));
+      for (int j = 0; j < 4; ++j) {                             // 16 bytes each: 8 bf16 or 4 fp32 channels
+        constexpr int per = F32 ? 4 : 8;
+        if (per * j < cpp && co0 + per * j < p.cout)
+          rres[j] = __ldg(reinterpret_cast<const uint4*>(res_row + (size_t)(co0 + per * j) * esize_res));
         else rres[j] = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
     {
       uint32_t raw[16];
@@ -646,8 +675,11 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
     if (RES && has_res) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (8 * j < cpp) {
-          const uint32_t w[4] = {rres[j].x, rres[j].y, rres[j].z, rres[j].w};
+        const uint32_t w[4] = {rres[j].x, rres[j].y, rres[j].z, rres[j].w};
+        if (F32) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[4 * j + i] += __uint_as_float(w[i]);
+        } else if (8 * j < cpp) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             v[8 * j + 2 * i] += __uint_as_float(w[i] << 16);
@@ -693,7 +725,7 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + 16u * j), "r"(w[4 * j]), "r"(w[4 * j + 1]),
                      "r"(w[4 * j + 2]), "r"(w[4 * j + 3]) : "memory");
     }
-    if (STATS) tc_epilogue_stats<STATS>(p, v, stat_rows, interior, img_g, co0, min(p.bn - c0, p.cout - co0), lane);
+    if (STATS) tc_epilogue_stats<STATS>(p, v, stat_rows, interior, img_g, co0, min(cpp, min(p.bn - c0, p.cout - co0)), lane);
     __syncwarp();
     // ---- write back: 4 instructions x (8 rows x 64 bytes)
     long long extra = 0;
@@ -771,7 +803,8 @@ __device__ __forceinline__ void tc_epilogue_deconv_predict(const TcParams& p, co
   }
 }
 
-// kind: 0 plain bf16, 1 bf16 + channel sums, 2 bf16 + GroupNorm sums, 3 bf16 + residual, 4 f32, 5 bf16 deconv scatter
+// kind: 0 plain bf16, 1 bf16 + channel sums, 2 bf16 + GroupNorm sums, 3 bf16 + residual, 4 f32, 5 bf16 deconv scatter,
+//       6 fused deconv + predictor, 7 f32 + channel sums, 8 f32 + GroupNorm sums, 9 f32 + f32 residual, 10 f32 deconv scatter
 __device__ __forceinline__ void tc_epilogue_dispatch(const TcParams& p, const TileGeom& g, uint32_t taddr, int m, int n0,
                                                      uint32_t stage_smem, int lane, uint32_t ss_smem, int cset, int ncset) {
   if (p.epi_kind == 6) {
@@ -784,6 +817,10 @@ __device__ __forceinline__ void tc_epilogue_dispatch(const TcParams& p, const Ti
     case 2: tc_epilogue_rows_staged<false, false, 2, false>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
     case 3: tc_epilogue_rows_staged<false, true, 0, false>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
     case 4: tc_epilogue_rows_staged<true, false, 0, false>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
+    case 7: tc_epilogue_rows_staged<true, false, 1, false>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
+    case 8: tc_epilogue_rows_staged<true, false, 2, false>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
+    case 9: tc_epilogue_rows_staged<true, true, 0, false>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
+    case 10: tc_epilogue_rows_staged<true, false, 0, true>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
     default: tc_epilogue_rows_staged<false, false, 0, true>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
   }
 }
@@ -862,8 +899,8 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc_kernel(const __grid_constant_
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = bn, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      // instruction descriptor: D=f32, A=B=bf16 (or f16: p.idesc_ab), both K-major, N = bn, M = 128
+      const uint32_t idesc = (1u << 4) | p.idesc_ab | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       const int taps = p.taps, num_src = p.num_src, n_stages = p.stages, spin = p.spin;
@@ -1096,7 +1133,7 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc2_kernel(const __grid_constant
       // The issue loop is the critical path of short-N layers (ncu: the producer waits for THIS warp, which never waits
       // itself): every parameter it needs is copied to a local first, descriptors are advanced incrementally, a full
       // 64-channel block takes the branch-free 8-MMA path, and a whole slab is issued under a single elect.
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)((TC_BM * NCTA) >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | p.idesc_ab | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)((TC_BM * NCTA) >> 4) << 24);
       const int kx_merge = p.kx_merge, b_res = p.b_resident, nblk_total = p.nblk_total, n_acc = p.acc_stages;
       const int n_sa = p.sa_stages, n_sb = p.sb_stages, num_src = p.num_src, spin = p.spin;
       const bool no_mma = (p.dbg & 4) != 0;
@@ -1234,6 +1271,249 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc2_kernel(const __grid_constant
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// v3: split-precision convolution (include/cm2.h "Split precision"): fp32-grade results from f16 tensor-core MMAs.
+//
+//   x = x_hi + x_lo, W = W_hi + W_lo (f16 pairs, 22 significant bits each):  x*W ~= x_hi*W_hi + x_lo*W_hi + x_hi*W_lo
+//
+// Measured on B200 (tests/test_gpu_conv_split.py): tcgen05.mma adds into its fp32 TMEM accumulator with truncation -- a
+// same-sign sum of 2304 terms accumulated in ONE accumulator came out 1.3e-5 low (3e-8 per MMA), ten times the error of
+// the CUDA-core fp32 engine and systematic.  So (Ootomo & Yokota's scheme, re-cut for TMEM):
+//   * the dominant x_hi*W_hi products go to a MAIN accumulator that is drained every `chunk` K-blocks (<= 4 * chunk
+//     accumulations) into fp32 registers of the epilogue warps, where the partial sums are added with round-to-nearest;
+//     two main accumulators alternate so that the drain of one overlaps the MMAs into the other;
+//   * the two cross terms are 2^-11 of the main term, so is their truncation error: they accumulate over the whole
+//     K loop in a CROSS accumulator that is added once per tile (two of them alternate between tiles).
+// One pipeline stage holds A_hi, A_lo (two boxes of the source's [hi | lo] matrix), W_hi and W_lo of one K-block: x_hi
+// and W_hi are loaded once and used by two MMA groups.  128-row tiles, N <= 128: 4 x 128 TMEM columns.
+// At the end of a tile the fp32 sums are written back to the cross accumulator's columns (tcgen05.st) and the ordinary
+// epilogue (scale / shift / residual / statistics / stores) runs on them unchanged.
+// Warps: 0 = TMA producer, 1 = TMEM alloc + MMA issue, 2..9 = epilogue (lane quarter q = warp & 3, column set = (warp - 2) >> 2).
+// ------------------------------------------------------------------------------------------------
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) conv_tc3_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 2;
+  const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;          // A_hi, A_lo, W_hi, W_lo
+  const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  const uint32_t tb = bar_base + 8u * (2 * p.stages);
+  auto mfull_bar = [&](int a) { return tb + 8u * a; };
+  auto mempty_bar = [&](int a) { return tb + 8u * (2 + a); };
+  auto xfull_bar = [&](int a) { return tb + 8u * (4 + a); };
+  auto xempty_bar = [&](int a) { return tb + 8u * (6 + a); };
+  const uint32_t tmem_slot = tb + 8u * 8;
+  constexpr int n_epi_warps = 8;
+  const uint32_t epi_base = (tmem_slot + 16u + 15u) & ~15u;
+  const uint32_t ss_base = epi_base + (uint32_t)n_epi_warps * EPI_WARP_BYTES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int nkb = p.taps * p.nblk_total;                  // K-blocks per tile
+  const int nchunks = (nkb + p.chunk - 1) / p.chunk;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&p.a_map[s]);
+    tma_prefetch_desc(&p.b_map);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(mfull_bar(a), 1); mbar_init(mempty_bar(a), (uint32_t)n_epi_warps);
+      mbar_init(xfull_bar(a), 1); mbar_init(xempty_bar(a), (uint32_t)n_epi_warps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m0 = p.row_begin + (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.bn;
+      int kb = 0;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        const int shift = tc_tap_shift(p, tap, p.num_seg ? tc_geom(p, m0).pitch : p.pitch);
+        for (int s = 0; s < p.num_src; ++s) {
+          const int c = p.src_c[s];
+          const int nblk = (c + TC_BK - 1) / TC_BK;
+          for (int cb = 0; cb < nblk; ++cb, ++kb) {
+            mbar_wait_ctl(p.spin, empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+            if (elect_one_sync()) {
+              mbar_expect_tx(full_bar(stage), stage_bytes);
+              tma_load_2d(sa, &p.a_map[s], full_bar(stage), cb * TC_BK, m0 + shift);                       // x_hi
+              tma_load_2d(sa + TC_A_BYTES, &p.a_map[s], full_bar(stage), c + cb * TC_BK, m0 + shift);      // x_lo
+              tma_load_2d(sa + 2u * TC_A_BYTES, &p.b_map, full_bar(stage), kb * TC_BK, n0);                // W_hi
+              tma_load_2d(sa + 2u * TC_A_BYTES + b_bytes, &p.b_map, full_bar(stage), kb * TC_BK, p.cout_pad + n0);   // W_lo
+            }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    const uint32_t idesc = (1u << 4) | p.idesc_ab | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const int taps = p.taps, num_src = p.num_src, n_stages = p.stages, spin = p.spin, chunk = p.chunk;
+    const uint64_t desc_step = (uint64_t)(stage_bytes >> 4);
+    const uint64_t ahi_base = umma_desc_sw128(base), alo_base = umma_desc_sw128(base + TC_A_BYTES);
+    const uint64_t whi_base = umma_desc_sw128(base + 2u * TC_A_BYTES), wlo_base = umma_desc_sw128(base + 2u * TC_A_BYTES + b_bytes);
+    int stage = 0, mbuf = 0, xbuf = 0;
+    uint32_t phase = 0, mphase = 0, xphase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      mbar_wait_ctl(spin, xempty_bar(xbuf), xphase ^ 1u);
+      tc_fence_after();
+      const uint32_t dx = tmem_base + 256u + (uint32_t)(xbuf * 128);
+      uint32_t acc_m = 0, acc_x = 0;
+      int in_chunk = 0, kb = 0;
+      for (int tap = 0; tap < taps; ++tap) {
+        for (int s = 0; s < num_src; ++s) {
+          const int c = p.src_c[s];
+          const int nblk = (c + TC_BK - 1) / TC_BK;
+          for (int cb = 0; cb < nblk; ++cb, ++kb) {
+            const int nk = (min(TC_BK, c - cb * TC_BK) + 15) >> 4;
+            if (in_chunk == 0) {                              // a fresh main accumulator
+              mbar_wait_ctl(spin, mempty_bar(mbuf), mphase ^ 1u);
+              tc_fence_after();
+              acc_m = 0;
+            }
+            const uint32_t dm = tmem_base + (uint32_t)(mbuf * 128);
+            mbar_wait_ctl(spin, full_bar(stage), phase);
+            tc_fence_after();
+            const uint64_t off = (uint64_t)stage * desc_step;
+            const uint64_t ahi = ahi_base + off, alo = alo_base + off, whi = whi_base + off, wlo = wlo_base + off;
+            const bool close_chunk = (in_chunk + 1 == chunk) || (kb + 1 == nkb);
+            if (elect_one_sync()) {
+              if (nk == 4) {                                  // full 64-channel block: branch-free issue
+                tc_mma_bf16(dm, ahi, whi, idesc, acc_m);
+                tc_mma_bf16(dm, ahi + 2, whi + 2, idesc, 1u);
+                tc_mma_bf16(dm, ahi + 4, whi + 4, idesc, 1u);
+                tc_mma_bf16(dm, ahi + 6, whi + 6, idesc, 1u);
+                tc_mma_bf16(dx, alo, whi, idesc, acc_x);
+                tc_mma_bf16(dx, alo + 2, whi + 2, idesc, 1u);
+                tc_mma_bf16(dx, alo + 4, whi + 4, idesc, 1u);
+                tc_mma_bf16(dx, alo + 6, whi + 6, idesc, 1u);
+                tc_mma_bf16(dx, ahi, wlo, idesc, 1u);
+                tc_mma_bf16(dx, ahi + 2, wlo + 2, idesc, 1u);
+                tc_mma_bf16(dx, ahi + 4, wlo + 4, idesc, 1u);
+                tc_mma_bf16(dx, ahi + 6, wlo + 6, idesc, 1u);
+              } else {
+                for (int k = 0; k < nk; ++k) tc_mma_bf16(dm, ahi + (uint64_t)(2 * k), whi + (uint64_t)(2 * k), idesc, acc_m | (uint32_t)k);
+                for (int k = 0; k < nk; ++k) tc_mma_bf16(dx, alo + (uint64_t)(2 * k), whi + (uint64_t)(2 * k), idesc, acc_x | (uint32_t)k);
+                for (int k = 0; k < nk; ++k) tc_mma_bf16(dx, ahi + (uint64_t)(2 * k), wlo + (uint64_t)(2 * k), idesc, 1u);
+              }
+              tc_commit(empty_bar(stage));
+              if (close_chunk) tc_commit(mfull_bar(mbuf));
+            }
+            __syncwarp();
+            acc_m = 1; acc_x = 1;
+            if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+            if (close_chunk) {
+              in_chunk = 0;
+              if (++mbuf == 2) { mbuf = 0; mphase ^= 1u; }
+            } else {
+              ++in_chunk;
+            }
+          }
+        }
+      }
+      if (elect_one_sync()) tc_commit(xfull_bar(xbuf));
+      __syncwarp();
+      if (++xbuf == 2) { xbuf = 0; xphase ^= 1u; }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int q = warp & 3, cset = (warp - 2) >> 2;
+    int mbuf = 0, xbuf = 0;
+    uint32_t mphase = 0, xphase = 0, parity = 0;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, parity ^= 1u) {
+      const int m0 = p.row_begin + (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.bn;
+      const uint32_t ss = ss_base + (p.n_tiles == 1 ? 0u : parity * 2048u);
+      if (p.n_tiles > 1 || t == (int)blockIdx.x)
+        tc_stage_scale_shift(p, ss, n0, (int)threadIdx.x - 64, 32 * n_epi_warps, m0);
+      // this warp sums the 16-column groups g = cset, cset + 2, ... of its 32 rows -- the same groups its staged epilogue
+      // pass handles for an fp32 output, so it later reads back only what it wrote itself
+      float run[4][16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) run[j][i] = 0.f;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        mbar_wait(mfull_bar(mbuf), mphase);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + (uint32_t)(mbuf * 128) + lane_off;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c0 = 16 * (cset + 2 * j);
+          if (c0 < p.bn) {                                  // warp-uniform
+            uint32_t raw[16];
+            __syncwarp();
+            tc_ld16(ta + (uint32_t)c0, raw);
+            tc_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) run[j][i] += __uint_as_float(raw[i]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(mempty_bar(mbuf));
+        if (++mbuf == 2) { mbuf = 0; mphase ^= 1u; }
+      }
+      mbar_wait(xfull_bar(xbuf), xphase);
+      tc_fence_after();
+      const uint32_t tx = tmem_base + 256u + (uint32_t)(xbuf * 128) + lane_off;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c0 = 16 * (cset + 2 * j);
+        if (c0 < p.bn) {
+          uint32_t raw[16];
+          __syncwarp();
+          tc_ld16(tx + (uint32_t)c0, raw);
+          tc_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) run[j][i] += __uint_as_float(raw[i]);
+          tc_st16(tx + (uint32_t)c0, run[j]);
+        }
+      }
+      tc_st_wait();
+      const TileGeom g = tc_geom(p, m0);
+      if (p.fast_store) {
+        tc_epilogue_dispatch(p, g, tx, m0 + q * 32 + lane, n0, epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES, lane, ss, cset, 2);
+      } else {
+        // the row-per-thread epilogue reads all columns from the cset-0 warps: make the other set's sums visible first
+        tc_fence_before();
+        asm volatile("bar.sync 2, %0;" ::"r"(32 * n_epi_warps) : "memory");
+        tc_fence_after();
+        if (cset == 0) tc_epilogue_rows(p, g, tx, m0 + q * 32 + lane, n0, ss);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(xempty_bar(xbuf));
+      if (++xbuf == 2) { xbuf = 0; xphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1257,25 +1537,27 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 matrix [rows][cols] (cols contiguous, row pitch = cols) ; box = [box_rows][64 cols], 128B swizzle
-static bool encode_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// 16-bit matrix [rows][cols] (cols contiguous, row pitch `pitch` >= cols elements: a channel slice of a wider tensor
+// is a matrix too); box = [box_rows][64 cols], 128B swizzle; columns beyond `cols` read as zero
+static bool encode_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows, bool f16) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
+  cuuint64_t strides[1] = {pitch * 2};
   cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
-static bool is_halo_view(const cm2_act& a) {
-  return a.sw == a.c && a.sh == (long long)(a.w + 2) * a.sw && a.sn == (long long)(a.h + 2) * a.sh;
+// sources may be channel slices (sw > c); outputs / residuals are whole tensors (sw == c)
+static bool is_halo_view(const cm2_act& a, bool slice_ok = false) {
+  return (slice_ok ? a.sw >= a.c : a.sw == a.c) && a.sh == (long long)(a.w + 2) * a.sw && a.sn == (long long)(a.h + 2) * a.sh;
 }
-static bool is_dense_view(const cm2_act& a) {
-  return a.sw == a.c && a.sh == (long long)a.w * a.sw && a.sn == (long long)a.h * a.sh;
+static bool is_dense_view(const cm2_act& a, bool slice_ok = false) {
+  return (slice_ok ? a.sw >= a.c : a.sw == a.c) && a.sh == (long long)a.w * a.sw && a.sn == (long long)a.h * a.sh;
 }
 
 static int device_is_sm100() {
@@ -1307,7 +1589,10 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   const cm2_act& s0 = d->src[0];
   if (!device_is_sm100()) { set_error("conv_tc: device is not sm_100"); return CM2_ERR_UNSUPPORTED; }
 #define TC_REQUIRE(cond, ...) do { if (!(cond)) { set_error(__VA_ARGS__); return CM2_ERR_UNSUPPORTED; } } while (0)
-  TC_REQUIRE(d->dtype == CM2_BF16 && (d->out_dtype == CM2_BF16 || d->out_dtype == CM2_F32), "conv_tc: needs bf16 sources");
+  const bool f16 = d->dtype == CM2_F16;
+  TC_REQUIRE((d->dtype == CM2_BF16 && (d->out_dtype == CM2_BF16 || d->out_dtype == CM2_F32)) || (f16 && d->out_dtype == CM2_F32),
+             "conv_tc: needs bf16 sources (bf16 / f32 output) or f16 sources (f32 output)");
+  TC_REQUIRE(!(f16 && d->out_mode == 3), "conv_tc: the fused deconv + predictor epilogue is bf16 only");
   const bool phase = d->src_phase != 0;
   if (phase)
     TC_REQUIRE(d->stride == 2 && d->kh == 3 && d->kw == 3 && d->pad == 1, "conv_tc: phase-split sources need a 3x3/s2/p1 conv");
@@ -1321,16 +1606,26 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   if (seg)
     TC_REQUIRE(d->num_seg <= CM2_MAX_SEG && !phase && d->out_mode == 0 && !d->residual.data,
                "conv_tc: segmented tensors need stride 1, out_mode 0, no residual");
-  const bool halo = seg || is_halo_view(s0);
-  TC_REQUIRE(halo || (d->kh == 1 && is_dense_view(s0)), "conv_tc: source 0 is neither a halo-1 view nor (for 1x1) dense");
+  const bool halo = seg || is_halo_view(s0, true);
+  TC_REQUIRE(halo || (d->kh == 1 && is_dense_view(s0, true)), "conv_tc: source 0 is neither a halo-1 view nor (for 1x1) dense");
   for (int i = 0; i < d->num_src; ++i) {
     const cm2_act& s = d->src[i];
-    TC_REQUIRE(s.c % 16 == 0 && (reinterpret_cast<uintptr_t>(s.data) & 15) == 0, "conv_tc: source %d channels %d / alignment", i, s.c);
-    if (!seg) TC_REQUIRE(halo ? is_halo_view(s) : is_dense_view(s), "conv_tc: source %d geometry differs from source 0", i);
+    TC_REQUIRE(s.c % 16 == 0 && (reinterpret_cast<uintptr_t>(s.data) & 15) == 0 && s.sw % 8 == 0 && s.sw >= s.c,
+               "conv_tc: source %d channels %d / pitch %lld / alignment", i, s.c, (long long)s.sw);
+    if (!seg) TC_REQUIRE(halo ? is_halo_view(s, true) : is_dense_view(s, true), "conv_tc: source %d geometry differs from source 0", i);
   }
   memset(p, 0, sizeof(*p));
+  p->idesc_ab = f16 ? 0u : ((1u << 7) | (1u << 10));
   p->num_src = d->num_src;
   for (int i = 0; i < d->num_src; ++i) p->src_c[i] = d->src[i].c;
+  if (f16) {
+    // split precision: a source is the [hi | lo] tensor of 2c channels; the K loop runs over the c logical channels
+    for (int i = 0; i < d->num_src; ++i) {
+      TC_REQUIRE(d->src[i].c % 32 == 0, "conv_tc: split-precision source %d needs 2c %% 32 == 0 (got %d)", i, d->src[i].c);
+      p->src_c[i] = d->src[i].c / 2;
+    }
+    p->split = 1;
+  }
   p->taps = d->kh * d->kw;
   p->halo = halo ? 1 : 0;
   p->phase = phase ? 1 : 0;
@@ -1393,7 +1688,8 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
                "conv_tc: fused deconv + predictor writes probabilities [n, 2h, 2w, 1]");
   }
   p->nblk_total = 0;
-  for (int i = 0; i < d->num_src; ++i) p->nblk_total += (d->src[i].c + TC_BK - 1) / TC_BK;
+  for (int i = 0; i < d->num_src; ++i) p->nblk_total += (p->src_c[i] + TC_BK - 1) / TC_BK;
+  p->cout_pad = cout_pad;
   // ---- kernel variant: 256-row tiles (v2) whenever that still fills the machine, else 128-row tiles (v1)
   static const int env_variant = getenv("CM2_TC_VARIANT") ? atoi(getenv("CM2_TC_VARIANT")) : 0;
   static const int env_desc = getenv("CM2_TC_DESC_MODE") ? atoi(getenv("CM2_TC_DESC_MODE")) : 0;
@@ -1425,6 +1721,7 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   if (pair_ok) use_v2 = true;
   if (env_variant == 1) use_v2 = false;
   if (env_variant >= 2 && !pred) use_v2 = true;
+  if (f16) use_v2 = false;
   static const int env_sets1 = getenv("CM2_TC_EPI_SETS_V1") ? atoi(getenv("CM2_TC_EPI_SETS_V1")) : 2;
   static const int env_sets2 = getenv("CM2_TC_EPI_SETS_V2") ? atoi(getenv("CM2_TC_EPI_SETS_V2")) : 1;
   // 16 epilogue warps (576 threads, <= 96 registers per thread) were measured 3-20 % slower on every layer
@@ -1471,10 +1768,19 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     p->pair = ((pair_ok || env_pair == 2) && !p->b_resident && p->bn % 32 == 0 && p->bn >= 32) ? 1 : 0;
     p->smem_bytes = (unsigned)(1024 + p->sa_stages * a_slab + p->sb_stages * b_bytes + tail2);
   } else {
-    p->variant = 1;
-    p->epi_sets = sets1;
+    p->variant = f16 ? 3 : 1;
+    p->epi_sets = f16 ? 2 : sets1;
     p->m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
     p->bn = pred ? d->cout / 4 : pick_bn(cout_pad, p->m_tiles, sms);     // fused predictor: one N tile per quadrant
+    if (f16) {
+      // four accumulators (2 main + 2 cross) share the 512 TMEM columns: N <= 128
+      while (p->bn > 128 || cout_pad % p->bn) p->bn -= 16;
+      // K-blocks (4 accumulations each) of the main term between two drains.  Measured on the full-size workload
+      // (profiles/r2_split_chunk_sweep.txt): chunk 1 / 2 / 4 / 6 -> box error 0.0026 / 0.0051 / 0.0058 / 0.0078 px against
+      // the fp32 oracle (the truncation bias grows with the chain length), 316 / 340 / 357 / 354 img/s
+      static const int env_chunk = getenv("CM2_TC_CHUNK") ? atoi(getenv("CM2_TC_CHUNK")) : 2;
+      p->chunk = env_chunk < 1 ? 1 : env_chunk;
+    }
     p->n_tiles = (cout_pad + p->bn - 1) / p->bn;
     // Wave quantisation: the first pitch + 1 and the last pitch + 1 rows of a halo matrix are halo pixels of the first /
     // last image.  When leaving them out saves a whole wave of tiles (16 images of 25x42: 149 tiles on 148 SMs -> 148),
@@ -1487,10 +1793,12 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
       if (waves_trim < waves_full) { p->row_begin = lead; p->m_tiles = t_trim; }
     }
     p->a_box_rows = TC_BM;
-    const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p->bn * TC_BK * 2;
-    int stages = (int)((smem_max - tail_v1) / stage_bytes);
+    const uint32_t stage_bytes = (f16 ? 2u : 1u) * (TC_A_BYTES + (uint32_t)p->bn * TC_BK * 2);
+    const size_t tail = f16 ? (size_t)(8 * (2 * 8 + 8) + 48 + 8 * EPI_WARP_BYTES + EPI_SS_BYTES) : tail_v1;
+    int stages = (int)((smem_max - tail) / stage_bytes);
     p->stages = stages > 8 ? 8 : stages;
-    p->smem_bytes = (unsigned)(1024 + (size_t)p->stages * stage_bytes + tail_v1);
+    TC_REQUIRE(p->stages >= 2, "conv_tc: tile does not fit in shared memory");
+    p->smem_bytes = (unsigned)(1024 + (size_t)p->stages * stage_bytes + tail);
   }
   p->scale = d->scale; p->shift = d->shift; p->relu = d->relu;
   p->out = d->out.data;
@@ -1514,27 +1822,30 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     p->res = reinterpret_cast<const __nv_bfloat16*>(d->residual.data);
     p->res_sn = d->residual.sn; p->res_sh = d->residual.sh; p->res_sw = d->residual.sw;
     p->res_mode = d->res_mode;
+    p->res_f32 = f16 ? 1 : 0;                          // the residual has dtype `dtype`; f32 for split-precision convolutions
     if (p->out_vec && !(d->residual.sn % 8 == 0 && d->residual.sh % 8 == 0 && d->residual.sw % 8 == 0 &&
                         (reinterpret_cast<uintptr_t>(d->residual.data) & 15) == 0))
       p->out_vec = 0;
   }
   static const int env_store = getenv("CM2_TC_FAST_STORE") ? atoi(getenv("CM2_TC_FAST_STORE")) : 1;
   p->fast_store = (env_store && p->out_vec && (d->out_mode != 1 || (d->cout / 4) % 32 == 0)) ? 1 : 0;
-  p->epi_kind = p->out_f32 ? 4 : (p->res_mode ? 3 : (d->out_mode == 1 ? 5 : 0));
+  // the staged epilogue adds a residual of the OUTPUT's element type: bf16 + bf16 residual, or f32 + f32 residual
+  if (p->res_mode && (p->out_f32 != 0) != (p->res_f32 != 0)) p->fast_store = 0;
+  if (p->out_f32) p->epi_kind = p->res_mode ? 9 : (d->out_mode == 1 ? 10 : 4);
+  else p->epi_kind = p->res_mode ? 3 : (d->out_mode == 1 ? 5 : 0);
   if (pred) {
     p->fast_store = 1;                                 // dispatcher path; nothing is staged
     p->epi_kind = 6;
     p->pred_w = d->pred_w; p->pred_b = d->pred_b; p->pred_cls = reinterpret_cast<const long long*>(d->pred_cls);
     p->pred_ncls = d->pred_ncls;
   }
-  if (p->fast_store) TC_REQUIRE(!(p->out_f32 && (p->res_mode || d->out_mode == 1)) && !(p->res_mode && d->out_mode == 1),
-                                "conv_tc: unsupported epilogue combination (f32 / residual / deconv)");
+  if (p->fast_store) TC_REQUIRE(!(p->res_mode && d->out_mode == 1), "conv_tc: unsupported epilogue combination (residual + deconv)");
   if (d->stats) {
-    TC_REQUIRE(p->fast_store && !p->res_mode && !p->out_f32 && d->out_mode == 0 && d->cout % 8 == 0,
-               "conv_tc: fused statistics need a bf16 out_mode-0 output without residual, cout %% 8 == 0");
+    TC_REQUIRE(p->fast_store && !p->res_mode && d->out_mode == 0 && d->cout % 8 == 0,
+               "conv_tc: fused statistics need an out_mode-0 output without residual, cout %% 8 == 0");
     p->stats = reinterpret_cast<double*>(d->stats);
     p->stats_mode = d->stats_mode;
-    p->epi_kind = d->stats_mode;
+    p->epi_kind = p->out_f32 ? 6 + d->stats_mode : d->stats_mode;
     p->stats_stride = d->stats_mode == 1 ? d->cout : (d->cout / 8) * 2;
   }
 #undef TC_REQUIRE
@@ -1543,13 +1854,16 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     // base of the flat matrix = address of padded pixel (0,0) of image 0
     const char* basep = reinterpret_cast<const char*>(d->src[i].data);
     if (halo && !seg) basep -= (size_t)(d->src[i].sh + d->src[i].sw) * 2;
-    if (!encode_2d(&p->a_map[i], basep, (uint64_t)rows * (phase ? 4 : 1), (uint64_t)d->src[i].c, (uint32_t)p->a_box_rows)) {
+    if (!encode_2d(&p->a_map[i], basep, (uint64_t)rows * (phase ? 4 : 1), (uint64_t)d->src[i].c, (uint64_t)d->src[i].sw,
+                   (uint32_t)p->a_box_rows, f16)) {
       set_error("conv_tc: cuTensorMapEncodeTiled failed for source %d", i);
       return CM2_ERR_CUDA;
     }
   }
   const int64_t ktc = cm2_conv_tc_klen(d->kh, d->kw, d->num_src, p->src_c);
-  if (!encode_2d(&p->b_map, d->weight, (uint64_t)cout_pad, (uint64_t)ktc, (uint32_t)(p->pair ? p->bn / 2 : p->bn))) {
+  // split precision: rows [0, cout_pad) hold W_hi, rows [cout_pad, 2 cout_pad) W_lo
+  if (!encode_2d(&p->b_map, d->weight, (uint64_t)cout_pad * (f16 ? 2 : 1), (uint64_t)ktc, (uint64_t)ktc,
+                 (uint32_t)(p->pair ? p->bn / 2 : p->bn), f16)) {
     set_error("conv_tc: cuTensorMapEncodeTiled failed for the weights");
     return CM2_ERR_CUDA;
   }
@@ -1569,6 +1883,7 @@ int conv_tc_launch(const cm2_conv_desc* d, cudaStream_t stream) {
   CM2_ENSURE_DYN_SMEM(conv_tc_kernel<320>, 227 * 1024, "conv_tc");
   CM2_ENSURE_DYN_SMEM((conv_tc2_kernel<320, false>), 227 * 1024, "conv_tc2");
   CM2_ENSURE_DYN_SMEM((conv_tc2_kernel<320, true>), 227 * 1024, "conv_tc2 (pair)");
+  CM2_ENSURE_DYN_SMEM(conv_tc3_kernel<320>, 227 * 1024, "conv_tc3");
   if (p.stats) {
     long long imgs = d->src[0].n;
     if (d->num_seg > 0) {
@@ -1612,6 +1927,8 @@ int conv_tc_launch(const cm2_conv_desc* d, cudaStream_t stream) {
     }
   } else if (p.variant == 2)
     conv_tc2_kernel<320, false><<<grid, 64 + 256 * p.epi_sets, p.smem_bytes, stream>>>(p);
+  else if (p.variant == 3)
+    conv_tc3_kernel<320><<<grid, 320, p.smem_bytes, stream>>>(p);
   else
     conv_tc_kernel<320><<<grid, 64 + 128 * p.epi_sets, p.smem_bytes, stream>>>(p);
   CM2_CHECK_LAUNCH("conv_tc");

@@ -2,6 +2,7 @@
 // All are coalesced over the channel dimension (innermost) and vectorised 8 channels/thread.
 // Reductions are deterministic (fixed two-stage trees, no atomics).
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include <algorithm>
 #include <string.h>
 
@@ -649,6 +650,34 @@ static bool gn_make_segs(int32_t num_seg, const cm2_seg* seg, int c, GnSegs* g) 
   return true;
 }
 
+// Split-precision operand preparation (cm2.h: cm2_split_f16x2): one thread = 8 channels of one pixel; reads 32 bytes,
+// writes the 16-byte hi piece to [pixel][ch] and the 16-byte lo piece to [pixel][c + ch].  hi = half(x) (round to nearest
+// even), lo = half(x - float(hi)): x - hi is exact in fp32 (Sterbenz / the difference has at most 13 significant bits left
+// of x's 24), so hi + lo carries 22 significant bits of x; below 2^-14 the lo part is a half subnormal with 2^-24
+// absolute resolution.
+__global__ void __launch_bounds__(256) split_f16x2_kernel(const float* __restrict__ x, __half* __restrict__ out, long long total8,
+                                                           int c8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / c8;
+    const int ch = (int)(i - pix * c8) * 8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + i * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(x + i * 8) + 1);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+      hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    __half* o = out + pix * (2ll * c8 * 8) + ch;
+    *reinterpret_cast<uint4*>(o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(o + c8 * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
 int grid_for(int64_t work, int block) {
   int64_t g = ceil_div64(work, block);
   int64_t cap = 148 * 16;
@@ -941,6 +970,18 @@ extern "C" int cm2_groupnorm_relu_seg(void* x, int32_t dtype, int32_t c, int32_t
     gn_seg_apply_kernel<__nv_bfloat16><<<grid_for(total8, 256), 256, 0, s>>>((__nv_bfloat16*)x, c, groups, g, stats, gamma,
                                                                           beta, relu);
   CM2_CHECK_LAUNCH("gn_seg_apply");
+  return CM2_OK;
+}
+
+extern "C" int cm2_split_f16x2(const float* x, void* out, int64_t pixels, int32_t c, void* stream) {
+  CM2_CHECK_ARG(x && out, "split_f16x2: null pointer");
+  CM2_CHECK_ARG(pixels >= 0 && c > 0 && c % 8 == 0, "split_f16x2: c=%d must be a positive multiple of 8", c);
+  CM2_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "split_f16x2: pointers must be 16-byte aligned");
+  const long long total8 = (long long)pixels * (c / 8);
+  if (total8 == 0) return CM2_OK;
+  split_f16x2_kernel<<<grid_for(total8, 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__half*>(out), total8, c / 8);
+  CM2_CHECK_LAUNCH("split_f16x2");
   return CM2_OK;
 }
 

@@ -132,11 +132,15 @@ class Engine(object):
     """Buffer cache + layer launchers for one (cfg, precision, device)."""
 
     def __init__(self, cfg, precision="fp32", device="cuda"):
-        assert precision in ("fp32", "bf16"), precision
+        assert precision in ("fp32", "fp32_simt", "bf16"), precision
         self.cfg = cfg
         self.precision = precision
-        self.dtype = torch.float32 if precision == "fp32" else torch.bfloat16
-        self.tc = precision == "bf16"
+        self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        # tcgen05 convolutions: bf16 operands ("bf16"), or fp32 activations whose convolutions run on split f16 hi/lo
+        # operands ("fp32": three MMAs per product term, fp32-grade accuracy); "fp32_simt" keeps everything on CUDA cores
+        self.tc = precision in ("bf16", "fp32")
+        self.split = precision == "fp32"
+        self._split_cache = {}
         self.device = torch.device(device)
         self._bufs = collections.OrderedDict()              # least recently used first
         self._buf_bytes = 0
@@ -262,13 +266,43 @@ class Engine(object):
         views = [s.view for s in srcs]
         for v, c in zip(views, w.src_c):
             assert v.shape[3] == c, (name, v.shape, w.src_c)
-        kw = dict(scale=w.scale, shift=w.shift, relu=w.relu, in_relu=in_relu, src_phase=src_phase,
+        kw = dict(shift=w.shift, relu=w.relu, in_relu=in_relu, src_phase=src_phase,
                   residual=None if residual is None else residual.view, res_mode=res_mode, out_mode=out_mode)
-        if self.tc and w.w_tc is not None and lib.conv2d(views, w.w_tc, out.view, w.cout, w.k, w.stride, w.pad,
-                                                          engine=lib.ENGINE_TC, stats=stats, stats_mode=stats_mode, probe=True, pred=pred, **kw):
-            return out
+        if self.tc and w.w_tc is not None:
+            tc_views = views
+            if w.split:
+                # split precision: fp32 activations -> [hi | lo] f16 tensors (cm2_split_f16x2), one per source
+                if in_relu or any(s.c % 16 for s in srcs) or out.view.dtype != torch.float32:
+                    tc_views = None
+                else:
+                    tc_views = [self.split_of(s).view for s in srcs]
+            if tc_views is not None and lib.conv2d(tc_views, w.w_tc, out.view, w.cout, w.k, w.stride, w.pad, scale=w.scale_tc,
+                                                   engine=lib.ENGINE_TC, stats=stats, stats_mode=stats_mode, probe=True, pred=pred, **kw):
+                return out
         assert stats is None and pred is None, "fused epilogues require the tensor-core engine: " + lib.last_error()
-        lib.conv2d(views, w.w_simt, out.view, w.cout, w.k, w.stride, w.pad, engine=lib.ENGINE_SIMT, **kw)
+        lib.conv2d(views, w.w_simt, out.view, w.cout, w.k, w.stride, w.pad, scale=w.scale, engine=lib.ENGINE_SIMT, **kw)
+        return out
+
+    # -- split-precision operands ------------------------------------------------------------------
+    def begin_pass(self):
+        """Start of a run_* call: split tensors made from here on are valid until the next call (their sources are
+        engine buffers that the following pass overwrites)."""
+        self._split_cache = {}
+
+    def split_of(self, x):
+        """[hi | lo] f16 companion of an fp32 FMap / PhaseMap / flat segmented buffer (``cm2_split_f16x2``), made once per
+        pass however many convolutions read ``x``.  The companion lives in an engine buffer named after the source's
+        address, so a CUDA-graph capture sees the same addresses every step."""
+        buf = x if isinstance(x, torch.Tensor) else x.buf
+        key = (buf.data_ptr(), tuple(buf.shape))
+        hit = self._split_cache.get(key)
+        if hit is not None:
+            return hit
+        assert buf.dtype == torch.float32 and buf.is_contiguous(), (buf.dtype, buf.stride())
+        sp = self.buffer(("split",) + key, tuple(buf.shape[:-1]) + (2 * buf.shape[-1],), torch.float16, zero=False)
+        lib.split_f16x2(buf, sp)
+        out = sp if isinstance(x, torch.Tensor) else (PhaseMap(sp) if isinstance(x, PhaseMap) else FMap(sp, x.halo))
+        self._split_cache[key] = out
         return out
 
     def dw_unit(self, name, x, w9c, pw, stride):
@@ -287,7 +321,8 @@ class Engine(object):
         cout_pad = (w.cout + 15) // 16 * 16
         assert cout_pad == w.cout, "segmented conv needs cout % 16 == 0"
         out = x.like(w.cout, dt, lambda shape: self.buffer(name, shape, dt))
-        lib.conv2d([x.flat], w.w_tc, out.flat, w.cout, w.k, w.stride, w.pad, scale=w.scale, shift=w.shift, relu=w.relu,
+        srcs = [self.split_of(x.flat)] if w.split else [x.flat]
+        lib.conv2d(srcs, w.w_tc, out.flat, w.cout, w.k, w.stride, w.pad, scale=w.scale_tc, shift=w.shift, relu=w.relu,
                    engine=lib.ENGINE_TC, segs=x.segs, stats=stats, stats_mode=stats_mode)
         return out
 
@@ -308,7 +343,7 @@ class Engine(object):
             else:
                 P["stem"].append(packing.conv_bn_relu(sd, k, [cin], s, 1, dt, dev, tc))
             cin = c
-        if tc:
+        if tc and not self.split:
             # stem_1 as a 1x1 conv over the fused normalise+im2col input (cm2_preprocess_im2col): K = 27 -> 32
             k1 = prefix + "bottom_up.stem.stem_1"
             w1 = sd[k1 + "/conv.weight"].detach().float()
@@ -359,6 +394,7 @@ class Engine(object):
     def run_backbone(self, x, P):
         """x: FMap [N, Hp, Wp, 3] (normalised, padded to /32).  Returns {"p3": FMap, ...}."""
         cfg = self.cfg
+        self.begin_pass()
         dw_body = isinstance(P["stem"][1], tuple)
         if self.tc and x.c == 32:
             x = self.conv("stem1", [x], P["stem1_im2col"])      # stem_1 = 1x1 over the im2col'd input
@@ -508,6 +544,7 @@ class Engine(object):
 
     def run_fcos_head(self, feats, P):
         """feats: list of FMap (p3..p7).  Returns per level (logits f32 FMap [N,H,W,ncls], regctr f32 FMap [N,H,W,5])."""
+        self.begin_pass()
         pyr = getattr(self, "_pyramid", None)
         if self.tc and pyr is not None and len(pyr[1]) == len(feats) and all(a is b for a, b in zip(pyr[1], feats)) \
                 and P["cls"].cout % 16 == 0:
@@ -651,6 +688,7 @@ class Engine(object):
         """center_heads.py:413-444 on fixed-size ROI slots [N*R].  feats: list of FMap (p3..p5).
         Returns (mask probs f32 [N*R, 1, 2*res, 2*res], mask_scores f32 [N*R] or None)."""
         cfg = self.cfg
+        self.begin_pass()
         mh = cfg.MODEL.ROI_MASK_HEAD
         n, r_cap = det["boxes"].shape[0], det["boxes"].shape[1]
         R = n * r_cap
@@ -670,7 +708,7 @@ class Engine(object):
         ncls = P["pred_w"].shape[0]
         classes = det["classes"].reshape(-1)
         dw = P["deconv"]
-        if self.tc and dw.w_tc is not None and ((res + 2) * (res + 2)) % 128 == 0 and (dw.cout // 4) % 32 == 0 and dw.cout // 4 <= 256:
+        if self.tc and not self.split and dw.w_tc is not None and ((res + 2) * (res + 2)) % 128 == 0 and (dw.cout // 4) % 32 == 0 and dw.cout // 4 <= 256:
             # deconv + ReLU + class-gathered predictor + sigmoid in one launch (the [R, 28, 28, C] tensor is never stored)
             self.conv("mask_deconv_predict", [att], dw, out_mode=3, out=FMap(probs.view(R, 2 * res, 2 * res, 1), 0),
                       pred=(P["pred_w"], P["pred_b"], classes, ncls))
@@ -701,6 +739,7 @@ class Engine(object):
         """center_heads.py:551-553 + keypoint_head.py:95-120 on fixed-size ROI slots.  feats: list of FMap
         (ROI_KEYPOINT_HEAD.IN_FEATURES).  Returns f32 [N, R, K, 4] = (x, y, logit, score); pred_keypoints = [..., (0, 1, 3)]."""
         cfg = self.cfg
+        self.begin_pass()
         kh = cfg.MODEL.ROI_KEYPOINT_HEAD
         n, r_cap = det["boxes"].shape[0], det["boxes"].shape[1]
         R = n * r_cap
@@ -730,7 +769,7 @@ class Engine(object):
         wp = max(s[1] for s in sizes)
         hp = (hp + size_divisibility - 1) // size_divisibility * size_divisibility
         wp = (wp + size_divisibility - 1) // size_divisibility * size_divisibility
-        if self.tc and fused_stem and len(cfg.MODEL.PIXEL_MEAN) == 3:
+        if self.tc and not self.split and fused_stem and len(cfg.MODEL.PIXEL_MEAN) == 3:
             # normalise + pad + im2col of stem_1 in one pass (the TC engine then runs stem_1 as a 1x1 conv)
             x = self.fmap("input_im2col", len(images), hp // 2, wp // 2, 32)
             if len({im.dtype for im in images}) == 1:

@@ -11,11 +11,11 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcm2.so")
 
-F32, BF16, U8 = 0, 1, 2
+F32, BF16, U8, F16 = 0, 1, 2, 3
 ENGINE_SIMT, ENGINE_TC = 0, 1
 MAX_SRC = 8
 
-_DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.uint8: U8}
+_DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.uint8: U8, torch.float16: F16}
 
 
 class Act(C.Structure):
@@ -62,6 +62,7 @@ SYMBOLS = {
     "cm2_last_error": (C.c_char_p, []),
     "cm2_device_info": (_I, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cm2_conv2d": (_I, [C.POINTER(ConvDesc), _P]),
+    "cm2_split_f16x2": (_I, [_P, _P, _L, _I, _P]),
     "cm2_conv_tc_klen": (_L, [_I, _I, _I, C.POINTER(_I)]),
     "cm2_conv_tc_supported": (_I, [C.POINTER(ConvDesc)]),
     "cm2_preprocess_image": (_I, [_P, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _AP, _I, _I, _P]),
@@ -151,9 +152,11 @@ def act(t):
 
 
 def flat_act(t):
-    """``cm2_act`` of a flat [rows, c] buffer (segmented tensors: only data and c are read)."""
-    assert t.dim() == 2 and t.stride(1) == 1 and t.stride(0) == t.shape[1], (t.shape, t.stride())
-    return Act(t.data_ptr(), 1, 1, t.shape[0], t.shape[1], t.shape[0] * t.shape[1], t.shape[0] * t.shape[1], t.shape[1])
+    """``cm2_act`` of a flat [rows, c] buffer or a channel slice of one (segmented tensors: data, c and the row pitch
+    ``sw`` are read)."""
+    assert t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1], (t.shape, t.stride())
+    pitch = t.stride(0)
+    return Act(t.data_ptr(), 1, 1, t.shape[0], t.shape[1], t.shape[0] * pitch, t.shape[0] * pitch, pitch)
 
 
 def seg_array(segs):
@@ -211,6 +214,15 @@ def conv2d(srcs, weight, out, cout, k, stride, pad, scale=None, shift=None, relu
     check(load().cm2_conv2d(C.byref(d), stream()), "cm2_conv2d")
     _count()
     return True
+
+
+def split_f16x2(x, out):
+    """fp32 buffer [..., c] (contiguous, halo included) -> f16 [..., 2c] = [hi | lo] for the split-precision TC convolution."""
+    assert x.dtype == torch.float32 and out.dtype == torch.float16 and x.is_contiguous() and out.is_contiguous()
+    c = x.shape[-1]
+    assert out.shape[-1] == 2 * c and out.numel() == 2 * x.numel(), (tuple(x.shape), tuple(out.shape))
+    check(load().cm2_split_f16x2(ptr(x), ptr(out), x.numel() // c, c, stream()), "cm2_split_f16x2")
+    _count()
 
 
 def conv_tc_klen(k, src_c):

@@ -14,9 +14,16 @@ class ConvW(object):
     """Packed weights of one convolution / linear layer.
 
     ``w_simt``: [kh*kw*cin_total, cout] in the activation dtype (CM2_ENGINE_SIMT layout).
-    ``w_tc``  : [cout_pad16, k_tc] bf16, K-major with every source's channels padded to 64
-                (CM2_ENGINE_TC layout) -- only built for bf16 models.
-    ``scale`` / ``shift``: fp32 [cout] epilogue vectors (folded FrozenBN, or bias)."""
+    ``w_tc``  : [cout_pad16, k_tc], K-major with every source's channels padded to 64 (CM2_ENGINE_TC layout):
+                bf16 for bf16 models; for fp32 models (``dtype`` float32 with ``build_tc``) the *split-precision*
+                f16 layout described below.
+    ``scale`` / ``shift``: fp32 [cout] epilogue vectors (folded FrozenBN, or bias); ``scale_tc`` is what the TC launch
+                uses (differs from ``scale`` only in the split layout).
+
+    Split-precision layout (include/cm2.h, "Split precision"): ``w_tc`` = f16 [2 * cout_pad16, k_tc], rows
+    [0, cout_pad) = W_hi = half(s * W), rows [cout_pad, 2 cout_pad) = W_lo = half(s * W - W_hi), s a per-output-channel
+    power of two that lifts the largest |W| of the channel to [256, 512) -- far from the half subnormals, far from
+    overflow -- and is undone exactly by ``scale_tc = scale / s``."""
 
     def __init__(self, weight, src_c, stride, pad, scale, shift, relu, dtype, device, build_tc):
         cout, cin, kh, kw = weight.shape
@@ -25,22 +32,37 @@ class ConvW(object):
         w = weight.detach().to(torch.float32)
         self.w_simt = w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous().to(device=device, dtype=dtype)
         self.w_tc = None
-        if build_tc:
-            cout_pad = (cout + 15) // 16 * 16
-            parts = []
-            off = 0
-            for c in src_c:
-                cp = (c + 63) // 64 * 64
-                blk = torch.zeros((cout_pad, kh * kw, cp), dtype=torch.float32)
-                blk[:cout, :, :c] = w[:, off:off + c].permute(0, 2, 3, 1).reshape(cout, kh * kw, c)
-                parts.append(blk)
-                off += c
-            # k = (tap, source, channel): concatenate sources inside each tap
-            wt = torch.cat(parts, dim=2).reshape(cout_pad, -1)
-            assert wt.shape[1] == lib.conv_tc_klen(kh, src_c)
-            self.w_tc = wt.contiguous().to(device=device, dtype=torch.bfloat16)
+        self.split = bool(build_tc and dtype == torch.float32)
         self.scale = None if scale is None else scale.detach().to(device=device, dtype=torch.float32).contiguous()
         self.shift = None if shift is None else shift.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.scale_tc = self.scale
+        if build_tc:
+            cout_pad = (cout + 15) // 16 * 16
+
+            def pack(wf):
+                # k = (tap, source, channel padded to 64): concatenate the sources inside each tap
+                parts, off = [], 0
+                for c in src_c:
+                    cp = (c + 63) // 64 * 64
+                    blk = torch.zeros((cout_pad, kh * kw, cp), dtype=torch.float32)
+                    blk[:cout, :, :c] = wf[:, off:off + c].permute(0, 2, 3, 1).reshape(cout, kh * kw, c)
+                    parts.append(blk)
+                    off += c
+                wt = torch.cat(parts, dim=2).reshape(cout_pad, -1)
+                assert wt.shape[1] == lib.conv_tc_klen(kh, src_c)
+                return wt
+
+            if self.split:
+                amax = w.abs().amax(dim=(1, 2, 3)).clamp(min=1e-30)
+                pre = torch.exp2(torch.floor(torch.log2(256.0 / amax))).clamp(max=2.0 ** 40)   # power of two: exact rescale
+                ws = w * pre.view(-1, 1, 1, 1)
+                hi = ws.to(torch.float16).to(torch.float32)
+                lo = (ws - hi).to(torch.float16).to(torch.float32)
+                base = torch.ones(cout) if scale is None else scale.detach().to(torch.float32).cpu()
+                self.scale_tc = (base / pre).to(device=device, dtype=torch.float32).contiguous()
+                self.w_tc = torch.cat([pack(hi), pack(lo)], dim=0).contiguous().to(device=device, dtype=torch.float16)
+            else:
+                self.w_tc = pack(w).contiguous().to(device=device, dtype=torch.bfloat16)
 
 
 def fold_frozen_bn(weight, bias, mean, var, eps=BN_EPS):

@@ -8,13 +8,16 @@ import os
 
 import torch
 
+# "bf16": bf16 activations + tcgen05 convolutions (the benchmarked engine); "fp32": fp32 activations, convolutions on the
+# tensor cores with fp16 hi/lo split operands (fp32-grade accuracy); "fp32_simt": fp32 activations, CUDA-core convolutions
+PRECISIONS = ("fp32", "fp32_simt", "bf16")
 _precision = os.environ.get("CM2_PRECISION", "fp32")
 _engines = {}
 
 
 def set_precision(p):
     global _precision
-    assert p in ("fp32", "bf16")
+    assert p in PRECISIONS, p
     _precision = p
 
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CM2_VERSION 103
+#define CM2_VERSION 200
 
 #define CM2_OK 0
 #define CM2_ERR_BAD_SHAPE (-1)
@@ -41,9 +41,10 @@ extern "C" {
 #define CM2_F32 0
 #define CM2_BF16 1
 #define CM2_U8 2
+#define CM2_F16 3 /* IEEE half: operand type of the split-precision tensor-core convolution (see cm2_split_f16x2) */
 
 #define CM2_ENGINE_SIMT 0 /* fp32-accumulate CUDA-core implicit GEMM; any shape; f32 or bf16 I/O   */
-#define CM2_ENGINE_TC 1   /* tcgen05/TMEM implicit GEMM with TMA-staged tiles; bf16 in             */
+#define CM2_ENGINE_TC 1   /* tcgen05/TMEM implicit GEMM with TMA-staged tiles; bf16 or f16 in      */
 
 #define CM2_MAX_SRC 8
 #define CM2_MAX_SEG 8
@@ -82,18 +83,32 @@ int cm2_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *
  * Weight layouts (built once by the caller; see centermask2_b200/packing.py):
  *   SIMT : [kh*kw*cin_total][cout]          row k = (ky*kw + kx)*cin_total + c,  dtype = `dtype`
- *   TC   : [cout_pad][k_tc] bf16, K-major; k = (tap, source, channel padded to 64 per source);
+ *   TC   : [cout_pad][k_tc] bf16 (f16 [2*cout_pad][k_tc] for split precision, see below), K-major;
+ *          k = (tap, source, channel padded to 64 per source);
  *          k_tc = kh*kw * sum_s roundup(src_c[s], 64)  (cm2_conv_tc_klen); cout_pad =
  *          roundup(cout, 16); padding entries are zero.
  *
- * TC engine constraints (cm2_conv_tc_supported): bf16 sources, stride 1, kernel 1x1 (pad 0) or 3x3
- * (pad 1); all sources and the output are interior views of one-pixel-halo buffers of identical
- * geometry (sw == c, sh == (w+2)*sw, sn == (h+2)*sh), or, for 1x1 only, fully dense views
- * (sh == w*sw, sn == h*sh).  With halo buffers the engine also (re)writes the halo of the output
- * with zeros, so a chain of convolutions keeps the invariant "halo == 0".
+ * TC engine constraints (cm2_conv_tc_supported): bf16 or f16 sources, stride 1, kernel 1x1 (pad 0) or
+ * 3x3 (pad 1); all sources and the output are interior views of one-pixel-halo buffers of identical
+ * geometry (sh == (w+2)*sw, sn == (h+2)*sh; a source may be a channel slice, sw >= c), or, for 1x1
+ * only, fully dense views (sh == w*sw, sn == h*sh).  With halo buffers the engine also (re)writes the
+ * halo of the output with zeros, so a chain of convolutions keeps the invariant "halo == 0".
+ *
+ * Split precision (dtype CM2_F16; the fp32-accuracy variant of the tensor-core path): the caller keeps
+ * activations in fp32 and converts a convolution's inputs with cm2_split_f16x2 into [.., 2c] half tensors
+ * (channels [0, c) = hi = half(x), [c, 2c) = lo = half(x - hi)); src[i] is that split tensor (src[i].c = 2c,
+ * 2c % 32 == 0).  The weights are f16 [2*cout_pad][k_tc] in the TC layout over the c LOGICAL channels of every
+ * source: rows [0, cout_pad) = W_hi = half(s*W), rows [cout_pad, 2*cout_pad) = W_lo = half(s*W - W_hi), with a
+ * per-output-channel power-of-two pre-scale s (undone through `scale`) that keeps W_lo out of the half
+ * subnormals.  The kernel accumulates x_hi*W_hi + x_lo*W_hi + x_hi*W_lo -- 22 significant bits per operand, the
+ * dropped x_lo*W_lo term is 2^-22 relative -- and, because tcgen05.mma adds into its accumulator with
+ * truncation, sums the dominant x_hi*W_hi term in short chunks that are added in fp32 registers with
+ * round-to-nearest (csrc/conv_tc.cu, conv_tc3_kernel).  Output and residual are CM2_F32; out_mode 3 is not
+ * available.
  * ------------------------------------------------------------------------------------------- */
 typedef struct cm2_conv_desc {
-  int32_t dtype;     /* CM2_F32 | CM2_BF16: sources, weights, residual                            */
+  int32_t dtype;     /* CM2_F32 | CM2_BF16: sources, weights, residual; CM2_F16 (TC engine): f16 sources
+                        and weights, f32 residual                                                 */
   int32_t out_dtype; /* CM2_F32 | CM2_BF16: output                                                */
   int32_t engine;    /* CM2_ENGINE_*                                                              */
   int32_t num_src;
@@ -118,8 +133,8 @@ typedef struct cm2_conv_desc {
                             sigmoid(pred_w[cls_n] . relu(deconv)[n, y, x, :] + pred_b[cls_n]); the deconv
                             output is rounded to bf16 in registers and never stored                       */
   cm2_act out;
-  /* optional fused statistics of the stored (post-activation, bf16-rounded) interior outputs, fp64, zeroed by
-   * the call and accumulated by the epilogue (see stats_mode below).  NULL: off.  TC engine only, bf16 output,
+  /* optional fused statistics of the stored (post-activation; bf16-rounded for a bf16 output) interior outputs,
+   * fp64, zeroed by the call and accumulated by the epilogue (see stats_mode below).  NULL: off.  TC engine only,
    * out_mode 0, no residual.  Image index runs over all images of all segments for segmented tensors. */
   void* stats;
   /* 1: every source is stored as four stride-2 *phase planes* (see cm2_phase_split): src[i] is the
@@ -142,6 +157,11 @@ typedef struct cm2_conv_desc {
 } cm2_conv_desc;
 
 int cm2_conv2d(const cm2_conv_desc* d, void* stream);
+/* Split an fp32 tensor for the split-precision convolution: x is a flat array of `pixels` rows of `c` channels
+ * (any NHWC buffer, halo included: zeros stay zeros); out is f16 [pixels][2c] with out[p][ch] = half(x[p][ch]) and
+ * out[p][c + ch] = half(x[p][ch] - float(out[p][ch])).  c % 8 == 0, both pointers 16-byte aligned.  |x| must be
+ * below the half range (65504); larger magnitudes saturate to +-inf and are reported by nobody. */
+int cm2_split_f16x2(const float* x, void* out, int64_t pixels, int32_t c, void* stream);
 /* K extent of the TC weight layout for this source list. */
 int64_t cm2_conv_tc_klen(int32_t kh, int32_t kw, int32_t num_src, const int32_t* src_c);
 /* 1 if the TC engine accepts this descriptor, 0 otherwise (message via cm2_last_error). */

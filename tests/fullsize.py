@@ -71,12 +71,45 @@ def margins(raw, tr, thresh=0.05):
     return {"min_prob_distance_to_threshold": gap, "min_score_gap_between_kept": sgap}
 
 
-def compare(got_raw, got_post, ref_raw, ref_post):
-    """Per-field deviations over the detections both sides kept, plus the set / order agreement."""
+def roialign_margin_px(boxes, image_size, feat_hw, res=14):
+    """Distance, in image pixels, of every ROI's closest ROIAlign sample to a DISCONTINUITY of the reference operator.
+
+    torchvision's roi_align (the op behind detectron2's ROIAlign, pooler.py:249-255) drops a sample whose coordinate is
+    below -1 or above the feature extent and clamps it to the border otherwise: a sample that crosses x = -1 jumps from
+    f[.., 0] to 0.  A box that differs by less than the box tolerance can therefore change the pooled feature by O(1)
+    when a sample sits that close to the jump -- downstream fields of such a ROI (mask, mask score) are ill-posed at the
+    stated box tolerance, exactly like a score within rounding of the threshold (SURVEY 8d margin check).
+    ``feat_hw``: {level index: (h, w)} of the pooled levels (strides 8, 16, 32)."""
+    from oracle import restate
+    if boxes.numel() == 0:
+        return boxes.new_zeros((0,))
+    lv = restate.assign_levels_by_ratio(boxes, image_size[0] * image_size[1], 3, 5)
+    out = []
+    for b, l in zip(boxes.double(), lv.tolist()):
+        stride = 8 << l
+        fh, fw = feat_hw[l]
+        best = float("inf")
+        for lo, hi, extent in ((b[0], b[2], fw), (b[1], b[3], fh)):
+            start = lo.item() / stride - 0.5
+            size = (hi.item() - lo.item()) / stride
+            grid = max(1, int(-(-size // res)))
+            bin_ = size / res
+            idx = torch.arange(res * grid, dtype=torch.float64)
+            pos = start + (idx // grid) * bin_ + ((idx % grid) + 0.5) * bin_ / grid
+            d = torch.minimum((pos + 1.0).abs(), (pos - extent).abs()).min().item() * stride
+            best = min(best, d)
+        out.append(best)
+    return torch.tensor(out)
+
+
+def compare(got_raw, got_post, ref_raw, ref_post, feat_hw=None, box_tol=1e-2):
+    """Per-field deviations over the detections both sides kept, plus the set / order agreement.  ROIs whose ROIAlign
+    sampling sits within ``box_tol`` of a discontinuity of the reference operator (``roialign_margin_px``) are counted
+    in ``roialign_ill_posed`` and left out of the mask / mask-score statistics."""
     from tests.helpers import mask_iou
     rep = {"images": len(ref_raw), "kept_ref": [], "kept_got": [], "common": [], "same_order": True, "box_px": 0.0,
            "score": 0.0, "mask_score_rel": 0.0, "mask_prob": 0.0, "post_box_px": 0.0, "mask_iou_min": 1.0,
-           "mask_iou_below_0p99": 0, "masks_compared": 0}
+           "mask_iou_below_0p99": 0, "masks_compared": 0, "roialign_ill_posed": 0, "roialign_margin_px_min": None}
     ious = []
     for g, gp, r, rp in zip(got_raw, got_post, ref_raw, ref_post):
         kg, kr = _keys(g), _keys(r)
@@ -92,6 +125,17 @@ def compare(got_raw, got_post, ref_raw, ref_post):
         ir = torch.tensor([i for i, k in enumerate(kr) if k in pos_g])
         rep["box_px"] = max(rep["box_px"], (g["pred_boxes"][ig] - r["pred_boxes"][ir]).abs().max().item())
         rep["score"] = max(rep["score"], (g["scores"][ig] - r["scores"][ir]).abs().max().item())
+        well = torch.ones(len(kr), dtype=torch.bool)
+        if feat_hw is not None:
+            margin = roialign_margin_px(r["pred_boxes"], r["image_size"], feat_hw)
+            well = margin >= box_tol
+            rep["roialign_ill_posed"] += int((~well).sum())
+            m = margin.min().item()
+            rep["roialign_margin_px_min"] = m if rep["roialign_margin_px_min"] is None else min(m, rep["roialign_margin_px_min"])
+            sel = well[ir]
+            ig, ir = ig[sel], ir[sel]
+            if len(ir) == 0:
+                continue
         if "mask_scores" in r:
             ms_r = r["mask_scores"][ir]
             rel = ((g["mask_scores"][ig] - ms_r).abs() / ms_r.abs().clamp(min=1.0)).max().item()
@@ -101,10 +145,11 @@ def compare(got_raw, got_post, ref_raw, ref_post):
         # match again by key
         kgp, krp = _keys(gp), _keys(rp)
         pos_gp = {k: i for i, k in enumerate(kgp)}
-        cp = [k for k in krp if k in pos_gp]
+        bad = {k for k, ok in zip(kr, well.tolist()) if not ok}
+        cp = [k for k in krp if k in pos_gp and k not in bad]
         if cp:
             jg = torch.tensor([pos_gp[k] for k in cp])
-            jr = torch.tensor([i for i, k in enumerate(krp) if k in pos_gp])
+            jr = torch.tensor([i for i, k in enumerate(krp) if k in pos_gp and k not in bad])
             rep["post_box_px"] = max(rep["post_box_px"], (gp["pred_boxes"][jg] - rp["pred_boxes"][jr]).abs().max().item())
             a, b = gp["pred_masks"][jg], rp["pred_masks"][jr]
             iou = mask_iou(a, b)
@@ -146,14 +191,15 @@ def deviation_report(precision):
     bf16 = precision == "bf16"
     ref_raw, ref_post, tr = oracle_outputs(bf16)
     got_raw, got_post = device_outputs(precision)
-    rep = compare(got_raw, got_post, ref_raw, ref_post)
+    feat_hw = {l: tuple(tr["features"]["p{}".format(3 + l)].shape[-2:]) for l in range(3)}
+    rep = compare(got_raw, got_post, ref_raw, ref_post, feat_hw)
     rep["precision"] = precision
     rep["oracle"] = "restate.bf16_sim()" if bf16 else "restate (fp32)"
     rep["margins"] = margins(ref_raw, tr)
     if bf16:
         # for the record: the bf16 engine against the PURE fp32 oracle (what a user switching precision sees)
         f_raw, f_post, _ = oracle_outputs(False)
-        raw32 = compare(got_raw, got_post, f_raw, f_post)
+        raw32 = compare(got_raw, got_post, f_raw, f_post, feat_hw)
         rep["vs_fp32_oracle"] = {k: raw32[k] for k in ("overlap", "box_px", "score", "mask_score_rel", "mask_iou_min",
                                                         "mask_iou_median", "mask_iou_below_0p99", "masks_compared")
                                  if k in raw32}

@@ -23,15 +23,20 @@ def fields(inst):
     return out
 
 
-@pytest.fixture(scope="module", params=sorted(CASES))
+# both fp32 engines: "fp32" = tensor cores on split f16 hi/lo operands, "fp32_simt" = CUDA cores
+@pytest.fixture(scope="module", params=[(c, p) for p in ("fp32", "fp32_simt") for c in sorted(CASES)],
+                ids=lambda cp: "{}-{}".format(*cp))
 def case(request):
+    name, precision = request.param
     runtime.reset()
-    runtime.set_precision("fp32")
-    gold = load_golden(request.param)
-    cfg, sd, inputs = build_case(request.param, gold)
+    runtime.set_precision(precision)
+    gold = load_golden(name)
+    cfg, sd, inputs = build_case(name, gold)
     model = cm.build_model(cfg)
     model.load_state_dict(sd, strict=True)
-    return request.param, gold, cfg, sd, inputs, model
+    yield name, gold, cfg, sd, inputs, model
+    runtime.reset()
+    runtime.set_precision("fp32")
 
 
 def test_backbone_and_head_tensors_match_reference(case):
@@ -126,7 +131,12 @@ def test_registry_level_modules_compose_like_the_reference(case):
         fa, fb = fields(a), fields(b)
         assert set(fa) == set(fb)
         for k in fa:
-            assert torch.allclose(fa[k].float(), fb[k].float(), atol=1e-5), k
+            # ``inference`` runs the FCOS towers as one segmented launch over all levels, the module-level call one launch
+            # per level: other tile shapes, another accumulation order (~1e-6 relative per layer, amplified by the layers
+            # behind it); mask probabilities and mask scores see the whole ROI stage on top
+            big = fb[k].float().abs().max().item() if fb[k].numel() else 0.0
+            tol = 2e-4 * max(1.0, big) if k in ("pred_masks", "mask_scores") else 1e-5
+            assert torch.allclose(fa[k].float(), fb[k].float(), atol=tol), k
 
 
 def test_layerwise_against_oracle_trace():
