@@ -278,7 +278,9 @@ def conv_gflop_per_image(cfg, height, width, rois):
         for _ in range(cfg.MODEL.ROI_MASK_HEAD.NUM_CONV):
             per += conv(r, r, c, d, 3)
             c = d
-        per += 2.0 * r * r * c * d * 4 + conv(2 * r, 2 * r, d, cfg.MODEL.ROI_HEADS.NUM_CLASSES, 1)
+        # the deconv, then the predictor for the ONE class of the ROI: mask_rcnn_inference (mask_head.py:196-216) reads a
+        # single class plane, the engine computes only that one (class-gathered predictor) -- skipped work is not credited
+        per += 2.0 * r * r * c * d * 4 + conv(2 * r, 2 * r, d, 1, 1)
         if cfg.MODEL.MASKIOU_ON:
             di = cfg.MODEL.ROI_MASKIOU_HEAD.CONV_DIM
             nc = cfg.MODEL.ROI_MASKIOU_HEAD.NUM_CONV

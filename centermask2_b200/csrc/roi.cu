@@ -1270,9 +1270,15 @@ __global__ void scale_clip_boxes_kernel(const float* __restrict__ in, float* __r
 
 // Batched variant: params[img] = (sx, sy, out_w, out_h) in device memory, r_cap slots per image.
 __global__ void scale_clip_boxes_batch_kernel(const float* __restrict__ in, float* __restrict__ out, uint8_t* __restrict__ valid,
-                                              int total, int r_cap, const float* __restrict__ params) {
+                                              int total, int r_cap, const float* __restrict__ params,
+                                              const int* __restrict__ det_count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
+  if (det_count && i % r_cap >= det_count[i / r_cap]) {       // empty slot: no box, no mask
+    reinterpret_cast<float4*>(out)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    valid[i] = 0;
+    return;
+  }
   const float4 q = __ldg(reinterpret_cast<const float4*>(params) + i / r_cap);
   float4 b = reinterpret_cast<const float4*>(in)[i];
   b.x = fminf(fmaxf(b.x * q.x, 0.f), q.z);
@@ -1281,6 +1287,28 @@ __global__ void scale_clip_boxes_batch_kernel(const float* __restrict__ in, floa
   b.w = fminf(fmaxf(b.w * q.y, 0.f), q.w);
   reinterpret_cast<float4*>(out)[i] = b;
   valid[i] = ((b.z - b.x) > 0.f && (b.w - b.y) > 0.f) ? 1 : 0;
+}
+
+// Fixed-size result record of every detection slot (centermask2_b200/parallel.py: RECORD_FIELDS = 11):
+// box[4], score, class, mask score, location[2], valid, detections of the image.  One thread per slot.
+__global__ void pack_records_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, const long long* __restrict__ classes,
+                                    const float* __restrict__ mask_scores, const float* __restrict__ locations,
+                                    const uint8_t* __restrict__ valid, const int* __restrict__ count, int total, int r_cap,
+                                    float* __restrict__ rec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int img = i / r_cap, k = i - img * r_cap, n = count[img];
+  float* o = rec + (size_t)i * 11;
+  const bool live = k < n;
+  const float4 b = live ? reinterpret_cast<const float4*>(boxes)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w;
+  o[4] = live ? scores[i] : 0.f;
+  o[5] = live ? (float)classes[i] : 0.f;
+  o[6] = live && mask_scores ? mask_scores[i] : 0.f;
+  o[7] = live && locations ? locations[2 * i] : 0.f;
+  o[8] = live && locations ? locations[2 * i + 1] : 0.f;
+  o[9] = live && (!valid || valid[i]) ? 1.f : 0.f;
+  o[10] = (float)n;
 }
 
 // Mask paste-back in two steps: (1) the whole [r, out_h, out_w] buffer is cleared with one memset at store bandwidth
@@ -1788,13 +1816,25 @@ extern "C" int cm2_scale_clip_boxes(const float* boxes_in, float* boxes_out, uin
 }
 
 extern "C" int cm2_scale_clip_boxes_batch(const float* boxes_in, float* boxes_out, uint8_t* valid, int32_t n, int32_t r_cap,
-                                          const float* params, void* stream) {
+                                          const float* params, const int32_t* det_count, void* stream) {
   CM2_CHECK_ARG(boxes_in && boxes_out && valid && params, "scale_clip_boxes_batch: null pointer");
   CM2_CHECK_ARG(n >= 0 && r_cap > 0, "scale_clip_boxes_batch: bad extents n=%d r_cap=%d", n, r_cap);
   if (n == 0) return CM2_OK;
   scale_clip_boxes_batch_kernel<<<ceil_div(n * r_cap, 128), 128, 0, (cudaStream_t)stream>>>(boxes_in, boxes_out, valid, n * r_cap,
-                                                                                           r_cap, params);
+                                                                                           r_cap, params, det_count);
   CM2_CHECK_LAUNCH("scale_clip_boxes_batch");
+  return CM2_OK;
+}
+
+extern "C" int cm2_pack_records(const float* boxes, const float* scores, const int64_t* classes, const float* mask_scores,
+                                const float* locations, const uint8_t* valid, const int32_t* det_count, int32_t n, int32_t r_cap,
+                                float* records, void* stream) {
+  CM2_CHECK_ARG(boxes && scores && classes && det_count && records, "pack_records: null pointer");
+  CM2_CHECK_ARG(n >= 0 && r_cap > 0 && (reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "pack_records: bad extents n=%d r_cap=%d", n, r_cap);
+  if (n == 0) return CM2_OK;
+  pack_records_kernel<<<ceil_div(n * r_cap, 128), 128, 0, (cudaStream_t)stream>>>(
+      boxes, scores, reinterpret_cast<const long long*>(classes), mask_scores, locations, valid, det_count, n * r_cap, r_cap, records);
+  CM2_CHECK_LAUNCH("pack_records");
   return CM2_OK;
 }
 

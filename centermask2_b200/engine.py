@@ -207,6 +207,15 @@ class Engine(object):
             self._bufs[("copy_stream",)] = st
         return st
 
+    def side_stream(self, name):
+        """A named extra stream (result read-back of the pipelined entry points)."""
+        key = ("stream", name)
+        st = self._bufs.get(key)
+        if st is None:
+            st = torch.cuda.Stream(device=self.device)
+            self._bufs[key] = st
+        return st
+
     def pinned(self, name, shape, dtype):
         """Page-locked host staging buffer (async D2H of the small result-size tensors)."""
         key = ("pinned", name, tuple(shape), dtype)
@@ -795,13 +804,14 @@ class Engine(object):
         lib.paste_masks(probs, b2, valid, masks, r, m, out_h, out_w, threshold)
         return b2, valid, masks
 
-    def rescale_boxes(self, det_boxes, sizes, out_sizes):
+    def rescale_boxes(self, det_boxes, sizes, out_sizes, det_count=None):
         """Box half of detector_postprocess for the whole batch (one launch): det_boxes [n, r_cap, 4] ->
-        (boxes' [n, r_cap, 4], valid u8 [n, r_cap]) in engine-owned buffers."""
+        (boxes' [n, r_cap, 4], valid u8 [n, r_cap]) in engine-owned buffers.  With ``det_count`` the slots that hold no
+        detection come out invalid (no mask is pasted into them)."""
         n, r_cap = det_boxes.shape[0], det_boxes.shape[1]
         boxes = self.buffer("pp_boxes", (n, r_cap, 4), torch.float32, False)
         valid = self.buffer("pp_valid", (n, r_cap), torch.uint8, False)
-        lib.scale_clip_boxes_batch(det_boxes, boxes, valid, n, r_cap, self.pp_params(sizes, out_sizes))
+        lib.scale_clip_boxes_batch(det_boxes, boxes, valid, n, r_cap, self.pp_params(sizes, out_sizes), det_count)
         return boxes, valid
 
     def pp_params(self, sizes, out_sizes):

@@ -72,6 +72,7 @@ SYMBOLS = {
     "cm2_resize_pil_u8": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _I, _P]),
     "cm2_rle_count": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "cm2_rle_write": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "cm2_rle_encode": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
     "cm2_phase_split": (_I, [_AP, _AP, _I, _I, _P]),
     "cm2_maxpool3x3s2_ceil": (_I, [_AP, _AP, _I, _P]),
     "cm2_dwconv3x3": (_I, [_AP, _AP, _I, _P, _I, _P]),
@@ -99,8 +100,9 @@ SYMBOLS = {
     "cm2_maskiou_score": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "cm2_keypoints_decode": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "cm2_scale_clip_boxes": (_I, [_P, _P, _P, _I, _F, _F, _F, _F, _P]),
-    "cm2_scale_clip_boxes_batch": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "cm2_scale_clip_boxes_batch": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "cm2_paste_masks": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
+    "cm2_pack_records": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
 }
 
 _lib = None
@@ -279,6 +281,16 @@ def rle_write(masks, col_offset, total, mask_offset, positions, runs):
     check(load().cm2_rle_write(ptr(masks), r, h, w, ptr(col_offset), ptr(total), ptr(mask_offset), ptr(positions), ptr(runs), stream()),
           "cm2_rle_write")
     _count(2)
+
+
+def rle_encode(masks, col_count, col_offset, total, mask_offset, positions, runs, boxes=None, valid=None):
+    """Count + device-side offsets + write in one call (no host sync); ``runs.numel()`` is the capacity.  ``boxes`` /
+    ``valid``: what the masks were pasted with -- only the box windows are scanned then."""
+    r, h, w = masks.shape
+    assert mask_offset.dtype == torch.int64 and mask_offset.numel() >= r + 1 and positions.numel() >= runs.numel()
+    check(load().cm2_rle_encode(ptr(masks), r, h, w, ptr(col_count), ptr(col_offset), ptr(total), ptr(mask_offset), ptr(positions),
+                                ptr(runs), runs.numel(), ptr(boxes), ptr(valid), stream()), "cm2_rle_encode")
+    _count(5)
 
 
 def phase_split(x, out_plane0, relu=False):
@@ -466,8 +478,8 @@ def scale_clip_boxes(boxes_in, boxes_out, valid, r, sx, sy, out_w, out_h):
     _count()
 
 
-def scale_clip_boxes_batch(boxes_in, boxes_out, valid, n, r_cap, params):
-    check(load().cm2_scale_clip_boxes_batch(ptr(boxes_in), ptr(boxes_out), ptr(valid), n, r_cap, ptr(params), stream()),
+def scale_clip_boxes_batch(boxes_in, boxes_out, valid, n, r_cap, params, det_count=None):
+    check(load().cm2_scale_clip_boxes_batch(ptr(boxes_in), ptr(boxes_out), ptr(valid), n, r_cap, ptr(params), ptr(det_count), stream()),
           "cm2_scale_clip_boxes_batch")
     _count()
 
@@ -475,4 +487,13 @@ def scale_clip_boxes_batch(boxes_in, boxes_out, valid, n, r_cap, params):
 def paste_masks(probs, boxes, valid, out, r, m, out_h, out_w, threshold):
     check(load().cm2_paste_masks(ptr(probs), ptr(boxes), ptr(valid), ptr(out), r, m, out_h, out_w, threshold, stream()),
           "cm2_paste_masks")
+    _count()
+
+
+def pack_records(boxes, scores, classes, mask_scores, locations, valid, det_count, records):
+    n, r_cap = boxes.shape[0], boxes.shape[1]
+    assert records.dtype == torch.float32 and records.is_contiguous() and tuple(records.shape) == (n, r_cap, 11)
+    assert classes.dtype == torch.int64 and det_count.dtype == torch.int32
+    check(load().cm2_pack_records(ptr(boxes), ptr(scores), ptr(classes), ptr(mask_scores), ptr(locations), ptr(valid), ptr(det_count),
+                                  n, r_cap, ptr(records), stream()), "cm2_pack_records")
     _count()

@@ -64,32 +64,8 @@ class GeneralizedRCNN(nn.Module):
         consumer that reads results back should do so on its own stream after ``stream.wait_event(event)`` -- a copy on
         the compute stream would queue behind the batches already enqueued ahead and drain the pipeline."""
         eng = runtime.engine_for(self.cfg)
-        copy_stream = eng.copy_stream()
         it = iter(batches)
-
-        def stage(batch):
-            # H2D on the copy stream, after the previous consumer of the staging buffers has read them
-            if batch is None:
-                return None
-            if eng._stage_free is not None:
-                copy_stream.wait_event(eng._stage_free)
-            with torch.cuda.stream(copy_stream):
-                bufs = [eng.buffer("stage_image{}".format(i), tuple(b["image"].shape), b["image"].dtype, zero=False)
-                        for i, b in enumerate(batch)]
-                for dst, b in zip(bufs, batch):
-                    dst.copy_(b["image"], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            return batch, bufs, ev
-
-        def consume(staged):
-            _, bufs, ev = staged
-            torch.cuda.current_stream().wait_event(ev)
-            images = [eng.buffer("input_image{}".format(i), tuple(t.shape), t.dtype, zero=False) for i, t in enumerate(bufs)]
-            for dst, src in zip(images, bufs):
-                dst.copy_(src, non_blocking=True)                       # device-to-device, ~0.03 ms for 51 MB
-            eng._stage_free = torch.cuda.Event()
-            eng._stage_free.record()
+        stage, consume = self._stager(eng)
 
         pending = collections.deque()
         state = {"staged": None, "launched": 0}
@@ -114,6 +90,163 @@ class GeneralizedRCNN(nn.Module):
             ctx = pending.popleft()
             out = self._finish(ctx)
             yield (out, ctx["done"]) if with_event else out
+
+    @staticmethod
+    def _stager(eng):
+        """(stage, consume) of the pipelined entry points: ``stage(batch)`` issues the host->device copies of a batch of
+        pinned host images on the copy stream into staging buffers; ``consume(staged)`` makes the compute stream wait for
+        them and moves the pixels into the input buffers the launch plan reads (device to device, ~0.03 ms for 51 MB)."""
+        copy_stream = eng.copy_stream()
+
+        def stage(batch):
+            if batch is None:
+                return None
+            if eng._stage_free is not None:                  # the previous consumer of the staging buffers has read them
+                copy_stream.wait_event(eng._stage_free)
+            with torch.cuda.stream(copy_stream):
+                bufs = [eng.buffer("stage_image{}".format(i), tuple(b["image"].shape), b["image"].dtype, zero=False)
+                        for i, b in enumerate(batch)]
+                for dst, b in zip(bufs, batch):
+                    dst.copy_(b["image"], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return batch, bufs, ev
+
+        def consume(staged):
+            _, bufs, ev = staged
+            torch.cuda.current_stream().wait_event(ev)
+            images = [eng.buffer("input_image{}".format(i), tuple(t.shape), t.dtype, zero=False) for i, t in enumerate(bufs)]
+            for dst, src in zip(images, bufs):
+                dst.copy_(src, non_blocking=True)
+            eng._stage_free = torch.cuda.Event()
+            eng._stage_free.record()
+
+        return stage, consume
+
+    @torch.no_grad()
+    def inference_records(self, batches, depth=2, rle_capacity=1 << 22):
+        """Pipelined inference that hands the WHOLE result of every batch to the host: generator over an iterable of
+        ``batched_inputs`` lists (pinned host images), yielding one ``parallel.BatchResult`` per batch, in order.
+
+        What the reference returns per image is ``Instances`` with boxes, scores, classes, locations, mask scores and
+        full-resolution bool masks (1 MB per mask at 800x1333); what leaves the device here is the fixed-size detection
+        record of every slot (``parallel.RECORD_FIELDS``: post-processed box, score, class, mask score, location, validity)
+        and the masks as COCO run lengths (``csrc/rle.cu``: pycocotools' column-major ``rleEncode``, the form
+        ``instances_to_coco_json`` -- coco_evaluation.py:362-427 -- turns them into anyway), computed on the device right
+        after the paste-back.  Per batch: H2D of the images (copy stream, overlapping the previous batch), one graph
+        replay, paste-back, RLE, then two small D2H copies on a read-back stream (records + run offsets, then exactly the
+        runs that were produced).  ``depth`` batches are enqueued ahead of the one being read back, so the device never
+        waits for the host.  ``rle_capacity``: initial run capacity of the device / pinned run buffers (they grow when a
+        batch needs more: that batch is re-encoded, nothing is lost)."""
+        from .. import lib, parallel
+        eng = runtime.engine_for(self.cfg)
+        it = iter(batches)
+        stage, consume = self._stager(eng)
+        back = eng.side_stream("readback")
+        fcos, roi = self.proposal_generator, self.roi_heads
+        state = {"staged": stage(next(it, None)), "launched": 0, "cap": int(rle_capacity)}
+        pending = collections.deque()
+
+        def encode(ctx):
+            """paste-back + RLE of a launched batch into its slot's buffers (compute stream), then the first read-back."""
+            n, r_cap, slot, (oh, ow) = ctx["n"], ctx["r_cap"], ctx["slot"], ctx["out_size"]
+            cap = state["cap"]
+            R = n * r_cap
+            B = eng.buffer
+            masks = B("rec_masks{}".format(slot), (R, oh, ow), torch.uint8, False)
+            lib.paste_masks(ctx["probs"], ctx["boxes"], ctx["valid"], masks, R, ctx["probs"].shape[-1], oh, ow, 0.5)
+            cc = B("rle_col_count", (R, ow), torch.int32, False)
+            co = B("rle_col_offset", (R, ow), torch.int32, False)
+            tot = B("rle_total", (R,), torch.int32, False)
+            moff = B("rle_mask_offset{}".format(slot), (R + 1,), torch.int64, False)
+            pos = B("rle_positions", (cap,), torch.int32, False)
+            runs = B("rle_runs{}".format(slot), (cap,), torch.int32, False)
+            lib.rle_encode(masks, cc, co, tot, moff, pos, runs, ctx["boxes"], ctx["valid"])
+            # the next batch's replay overwrites the plan's record buffer: snapshot it for the read-back stream
+            rec = B("records_slot{}".format(slot), tuple(ctx["rec"].shape), torch.float32, False)
+            rec.copy_(ctx["rec"], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            back.wait_event(ev)
+            with torch.cuda.stream(back):
+                ctx["h_rec"].copy_(rec, non_blocking=True)
+                ctx["h_off"] = eng.pinned("h_rle_off{}".format(slot), (R + 1,), torch.int64)
+                ctx["h_off"].copy_(moff, non_blocking=True)
+                ctx["ready"] = torch.cuda.Event()
+                ctx["ready"].record(back)
+            ctx.update(masks=masks, runs=runs, cap=cap)
+
+        def launch_next():
+            if state["staged"] is None:
+                return False
+            consume(state["staged"])
+            batch = state["staged"][0]
+            state["staged"] = stage(next(it, None))
+            slot = state["launched"] % (depth + 1)
+            state["launched"] += 1
+            n = len(batch)
+            sizes = [(int(b["image"].shape[-2]), int(b["image"].shape[-1])) for b in batch]
+            out_sizes = [(int(b.get("height", sz[0])), int(b.get("width", sz[1]))) for b, sz in zip(batch, sizes)]
+            if len(set(out_sizes)) != 1:
+                raise ValueError("inference_records needs one output size per batch (got {})".format(sorted(set(out_sizes))))
+            sig = tuple((tuple(b["image"].shape), b["image"].dtype) for b in batch)
+            images = [eng.buffer("input_image{}".format(i), shp, dt, zero=False) for i, (shp, dt) in enumerate(sig)]
+
+            def plan():
+                x, _ = eng.preprocess(images, self.backbone.size_divisibility)
+                feats = self.backbone.forward_fmap(x)
+                det = fcos.detect([feats[f] for f in fcos.in_features])
+                probs, mask_scores = roi.run([feats[f] for f in roi.in_features], det, sizes)
+                boxes, valid = eng.rescale_boxes(det["boxes"], sizes, out_sizes, det["count"])
+                rec = eng.buffer("records", (n, det["boxes"].shape[1], parallel.RECORD_FIELDS), torch.float32, False)
+                parallel.pack_slots(rec, boxes, det["scores"], det["classes"], mask_scores, det["locations"], valid, det["count"])
+                return det, probs, boxes, valid, rec
+
+            eng.trim()
+            det, probs, boxes, valid, rec = eng.graphed(("records", self.graph_tokens(), sig, tuple(out_sizes)), plan,
+                                                        keep=self.packed_refs())
+            r_cap = det["boxes"].shape[1]
+            ctx = dict(n=n, r_cap=r_cap, slot=slot, out_size=out_sizes[0], probs=probs, boxes=boxes, valid=valid, rec=rec,
+                       h_rec=eng.pinned("h_records{}".format(slot), (n, r_cap, parallel.RECORD_FIELDS), torch.float32),
+                       cand=det["cand_count"], cand_cap=det["cand_cap"],
+                       h_cand=eng.pinned("h_rcand{}".format(slot), tuple(det["cand_count"].shape), torch.int32))
+            ctx["h_cand"].copy_(det["cand_count"], non_blocking=True)
+            encode(ctx)
+            pending.append(ctx)
+            return True
+
+        if not roi.mask_on:
+            raise NotImplementedError("inference_records needs MODEL.MASK_ON")
+        for _ in range(depth):
+            if not launch_next():
+                break
+        while pending:
+            launch_next()
+            ctx = pending.popleft()
+            ctx["ready"].synchronize()
+            if bool((ctx["h_cand"] > ctx["cand_cap"]).any()):
+                raise RuntimeError("FCOS candidate buffer overflow (> {} candidates above threshold in one level)".format(ctx["cand_cap"]))
+            R = ctx["n"] * ctx["r_cap"]
+            n_runs = int(ctx["h_off"][R])
+            while n_runs > ctx["cap"]:
+                # the run buffers were too small for this batch: grow them (for every later batch too) and encode again --
+                # the pasted masks of the slot are still there
+                state["cap"] = max(2 * state["cap"], n_runs + (n_runs >> 2))
+                moff = eng.buffer("rle_mask_offset{}".format(ctx["slot"]), (R + 1,), torch.int64, False)
+                pos = eng.buffer("rle_positions", (state["cap"],), torch.int32, False)
+                runs = eng.buffer("rle_runs{}".format(ctx["slot"]), (state["cap"],), torch.int32, False)
+                lib.rle_encode(ctx["masks"], eng.buffer("rle_col_count", (R, ctx["out_size"][1]), torch.int32, False),
+                               eng.buffer("rle_col_offset", (R, ctx["out_size"][1]), torch.int32, False),
+                               eng.buffer("rle_total", (R,), torch.int32, False), moff, pos, runs)       # (whole-mask scan)
+                torch.cuda.current_stream().synchronize()
+                ctx.update(runs=runs, cap=state["cap"])
+                ctx["h_off"].copy_(moff)
+                n_runs = int(ctx["h_off"][R])
+            h_runs = eng.pinned("h_rle_runs{}".format(ctx["slot"]), (max(ctx["cap"], 1),), torch.int32)
+            with torch.cuda.stream(back):
+                h_runs[:n_runs].copy_(ctx["runs"][:n_runs], non_blocking=True)
+            back.synchronize()
+            yield parallel.BatchResult(ctx["h_rec"], ctx["h_off"], h_runs[:n_runs], ctx["out_size"])
 
     @torch.no_grad()
     def inference(self, batched_inputs, detected_instances=None, do_postprocess=True):
@@ -165,7 +298,7 @@ class GeneralizedRCNN(nn.Module):
             if roi.keypoint_on:                                        # center_heads.py:441-442: after the masks
                 kps = roi.run_keypoints([feats[f] for f in roi.kp_in_features], det, sizes)
             if do_postprocess:
-                boxes, valid = eng.rescale_boxes(det["boxes"], sizes, out_sizes)
+                boxes, valid = eng.rescale_boxes(det["boxes"], sizes, out_sizes, det["count"])
             return det, probs, mask_scores, boxes, valid, kps
 
         # the key names the weights the capture bakes in (module identity + weight generation): a model whose weights were

@@ -373,11 +373,19 @@ int cm2_resize_pil_u8(const uint8_t* src, uint8_t* tmp, uint8_t* dst, int32_t h,
  * ------------------------------------------------------------------------------------------- */
 int cm2_scale_clip_boxes(const float* boxes_in, float* boxes_out, uint8_t* valid, int32_t r, float sx,
                          float sy, float out_w, float out_h, void* stream);
-/* Whole batch in one launch: boxes [n][r_cap][4]; params [n][4] = (sx, sy, out_w, out_h) in DEVICE memory. */
+/* Whole batch in one launch: boxes [n][r_cap][4]; params [n][4] = (sx, sy, out_w, out_h) in DEVICE memory.  det_count
+ * (device int32 [n], may be NULL): slots >= det_count[image] hold no detection: box 0, valid 0 (so no mask is pasted). */
 int cm2_scale_clip_boxes_batch(const float* boxes_in, float* boxes_out, uint8_t* valid, int32_t n, int32_t r_cap,
-                               const float* params, void* stream);
+                               const float* params, const int32_t* det_count, void* stream);
 int cm2_paste_masks(const float* probs, const float* boxes, const uint8_t* valid, uint8_t* out,
                     int32_t r, int32_t m, int32_t out_h, int32_t out_w, float threshold, void* stream);
+/* Result record of every detection slot for the host / the final gather: records float32
+ * [n][r_cap][11] = (x0, y0, x1, y1, score, class, mask score, location x, location y, valid, detections of the image);
+ * fields 0..9 of slots >= det_count[image] are zero.  boxes [n][r_cap][4] (16-byte aligned), scores / mask_scores (may be
+ * NULL) [n][r_cap], classes int64 [n][r_cap], locations (may be NULL) [n][r_cap][2], valid (may be NULL) uint8 [n][r_cap]. */
+int cm2_pack_records(const float* boxes, const float* scores, const int64_t* classes, const float* mask_scores,
+                     const float* locations, const uint8_t* valid, const int32_t* det_count, int32_t n, int32_t r_cap,
+                     float* records, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Result encoding: COCO run-length encoding of the pasted masks, i.e. pycocotools' rleEncode as
@@ -392,6 +400,15 @@ int cm2_rle_count(const uint8_t* masks, int32_t r, int32_t h, int32_t w, int32_t
                   int32_t* total, void* stream);
 int cm2_rle_write(const uint8_t* masks, int32_t r, int32_t h, int32_t w, const int32_t* col_offset, const int32_t* total,
                   const int64_t* mask_offset, uint32_t* positions, uint32_t* runs, void* stream);
+/* Both steps in one call with the offsets made on the device (no host round trip between them; for pipelined callers):
+ * mask_offset int64 [r + 1] = exclusive scan of (total + 1), mask_offset[r] = number of runs of all masks.  positions / runs
+ * have room for `capacity` entries; a mask whose runs would end beyond it is skipped, which the caller detects as
+ * mask_offset[r] > capacity after the fact (and retries with larger buffers).
+ * boxes / valid (may be NULL): the boxes [r][4] (16-byte aligned) and validity flags the masks were pasted with
+ * (cm2_paste_masks): a pasted mask is zero outside the dilated window of its box, so only that window is scanned. */
+int cm2_rle_encode(const uint8_t* masks, int32_t r, int32_t h, int32_t w, int32_t* col_count, int32_t* col_offset,
+                   int32_t* total, int64_t* mask_offset, uint32_t* positions, uint32_t* runs, int64_t capacity,
+                   const float* boxes, const uint8_t* valid, void* stream);
 
 #ifdef __cplusplus
 }

@@ -284,3 +284,41 @@ def test_reloaded_weights_and_second_model_never_replay_a_stale_graph():
         assert _same_fields(_detections(model, inputs), want_b)
     assert len(eng._graphs) == 2
     runtime.reset()
+
+
+def test_inference_records_hand_the_whole_result_to_the_host(case):
+    """``inference_records``: detection records + masks as COCO run lengths on the host == what ``forward`` returns as
+    ``Instances`` (boxes, scores, classes, locations, mask scores, pasted bool masks), batch after batch."""
+    import numpy as np
+    from centermask2_b200 import parallel
+    name, gold, cfg, sd, inputs, model = case
+    oh, ow = 100, 140                                                        # one output size per batch
+    batch = [dict(b, image=b["image"].contiguous().pin_memory(), height=oh, width=ow) for b in inputs]
+    want = [fields(o["instances"]) for o in model(batch)]
+    results = [r.clone() for r in model.inference_records(iter([batch, batch, batch]), rle_capacity=64)]   # tiny capacity: grows
+    assert len(results) == 3
+    for res in results:
+        assert tuple(res.size) == (oh, ow) and res.records.shape[0] == len(batch)
+        r_cap = res.records.shape[1]
+        assert res.rle_offsets.numel() == len(batch) * r_cap + 1 and int(res.rle_offsets[-1]) == res.rle_runs.numel()
+        for i, w in enumerate(want):
+            rec = res.records[i]
+            k = int(rec[0, parallel.F_COUNT])
+            assert (rec[k:, :parallel.F_COUNT] == 0).all()
+            keep = [j for j in range(k) if rec[j, parallel.F_VALID] == 1]
+            assert len(keep) == len(w["scores"])
+            if not keep:
+                continue
+            sel = torch.tensor(keep)
+            assert torch.equal(rec[sel, 0:4], w["pred_boxes"]) and torch.equal(rec[sel, parallel.F_SCORE], w["scores"])
+            assert torch.equal(rec[sel, parallel.F_CLASS].long(), w["pred_classes"])
+            assert torch.equal(rec[sel, parallel.F_LOC:parallel.F_LOC + 2], w["locations"])
+            if "mask_scores" in w:
+                assert torch.equal(rec[sel, parallel.F_MASK_SCORE], w["mask_scores"])
+            for n_, j in enumerate(keep):
+                runs = res.runs(i, j)
+                assert int(runs.astype(np.int64).sum()) == oh * ow
+                assert np.array_equal(res.mask(i, j), w["pred_masks"][n_].numpy()), (i, j)
+            for j in range(r_cap):
+                if j not in keep:                                            # empty / dropped slots: one run of zeros
+                    assert res.runs(i, j).tolist() == [oh * ow]
