@@ -161,50 +161,75 @@ def fcos_param_spec(cfg, in_channels):
     return spec
 
 
+def mask_head_param_spec(cfg, in_channels):
+    """``state_dict`` layout of ``SpatialAttentionMaskHead`` (sam.py:41-90), keys relative to the head."""
+    spec = OrderedDict()
+    dim = cfg.MODEL.ROI_MASK_HEAD.CONV_DIM
+    n_conv = cfg.MODEL.ROI_MASK_HEAD.NUM_CONV
+    if cfg.MODEL.ROI_MASK_HEAD.NORM:
+        raise NotImplementedError("ROI_MASK_HEAD.NORM != '' is not configured by the reference")
+    c = in_channels
+    for k in range(n_conv):
+        spec["mask_fcn{}.weight".format(k + 1)] = ((dim, c, 3, 3), "conv_relu")
+        spec["mask_fcn{}.bias".format(k + 1)] = ((dim,), "bias")
+        c = dim
+    spec["spatialAtt.conv.weight"] = ((1, 2, 3, 3), "sam")
+    spec["deconv.weight"] = ((c, dim, 2, 2), "deconv")
+    spec["deconv.bias"] = ((dim,), "bias")
+    ncls = 1 if cfg.MODEL.ROI_MASK_HEAD.CLS_AGNOSTIC_MASK else cfg.MODEL.ROI_HEADS.NUM_CLASSES
+    spec["predictor.weight"] = ((ncls, dim, 1, 1), "predictor")
+    spec["predictor.bias"] = ((ncls,), "zero")
+    return spec
+
+
+def maskiou_head_param_spec(cfg, in_channels, resolution):
+    """``state_dict`` layout of ``MaskIoUHead`` (maskiou_head.py:64-105); ``in_channels`` = channels of the pooled ROI
+    feature (the head concatenates one mask channel, :71), ``resolution`` = width of its input (:72 halves it)."""
+    spec = OrderedDict()
+    dim = cfg.MODEL.ROI_MASKIOU_HEAD.CONV_DIM
+    n_conv = cfg.MODEL.ROI_MASKIOU_HEAD.NUM_CONV
+    res = resolution // 2
+    c = in_channels + 1
+    for k in range(n_conv):
+        spec["maskiou_fcn{}.weight".format(k + 1)] = ((dim, c, 3, 3), "conv_relu")
+        spec["maskiou_fcn{}.bias".format(k + 1)] = ((dim,), "bias")
+        c = dim
+    spec["maskiou_fc1.weight"] = ((1024, dim * res * res), "fc_relu")
+    spec["maskiou_fc1.bias"] = ((1024,), "bias")
+    spec["maskiou_fc2.weight"] = ((1024, 1024), "fc_relu")
+    spec["maskiou_fc2.bias"] = ((1024,), "bias")
+    spec["maskiou.weight"] = ((cfg.MODEL.ROI_HEADS.NUM_CLASSES, 1024), "maskiou_out")
+    spec["maskiou.bias"] = ((cfg.MODEL.ROI_HEADS.NUM_CLASSES,), "maskiou_bias")
+    return spec
+
+
+def keypoint_head_param_spec(cfg, in_channels):
+    """KRCNNConvDeconvUpsampleHead, keypoint_head.py:168-215."""
+    spec = OrderedDict()
+    kh = cfg.MODEL.ROI_KEYPOINT_HEAD
+    c = in_channels
+    for k, dim in enumerate(kh.CONV_DIMS, 1):
+        spec["conv_fcn{}.weight".format(k)] = ((dim, c, 3, 3), "conv_relu")
+        spec["conv_fcn{}.bias".format(k)] = ((dim,), "bias")
+        c = dim
+    spec["score_lowres.weight"] = ((c, kh.NUM_KEYPOINTS, 4, 4), "kp_deconv")
+    spec["score_lowres.bias"] = ((kh.NUM_KEYPOINTS,), "bias")
+    return spec
+
+
 def roi_heads_param_spec(cfg, in_channels):
-    """``state_dict`` layout of ``CenterROIHeads`` (SAG-Mask head + MaskIoU head)."""
+    """``state_dict`` layout of ``CenterROIHeads``: its heads under ``mask_head.`` / ``maskiou_head.`` / ``keypoint_head.``
+    (center_heads.py:337-383)."""
     spec = OrderedDict()
     if cfg.MODEL.MASK_ON:
-        dim = cfg.MODEL.ROI_MASK_HEAD.CONV_DIM
-        n_conv = cfg.MODEL.ROI_MASK_HEAD.NUM_CONV
-        if cfg.MODEL.ROI_MASK_HEAD.NORM:
-            raise NotImplementedError("ROI_MASK_HEAD.NORM != '' is not configured by the reference")
-        c = in_channels
-        for k in range(n_conv):
-            spec["mask_head.mask_fcn{}.weight".format(k + 1)] = ((dim, c, 3, 3), "conv_relu")
-            spec["mask_head.mask_fcn{}.bias".format(k + 1)] = ((dim,), "bias")
-            c = dim
-        spec["mask_head.spatialAtt.conv.weight"] = ((1, 2, 3, 3), "sam")
-        spec["mask_head.deconv.weight"] = ((c, dim, 2, 2), "deconv")
-        spec["mask_head.deconv.bias"] = ((dim,), "bias")
-        ncls = 1 if cfg.MODEL.ROI_MASK_HEAD.CLS_AGNOSTIC_MASK else cfg.MODEL.ROI_HEADS.NUM_CLASSES
-        spec["mask_head.predictor.weight"] = ((ncls, dim, 1, 1), "predictor")
-        spec["mask_head.predictor.bias"] = ((ncls,), "zero")
+        for k, v in mask_head_param_spec(cfg, in_channels).items():
+            spec["mask_head." + k] = v
     if cfg.MODEL.MASKIOU_ON:
-        dim = cfg.MODEL.ROI_MASKIOU_HEAD.CONV_DIM
-        n_conv = cfg.MODEL.ROI_MASKIOU_HEAD.NUM_CONV
-        res = cfg.MODEL.ROI_MASK_HEAD.POOLER_RESOLUTION // 2
-        c = cfg.MODEL.ROI_MASK_HEAD.CONV_DIM + 1
-        for k in range(n_conv):
-            spec["maskiou_head.maskiou_fcn{}.weight".format(k + 1)] = ((dim, c, 3, 3), "conv_relu")
-            spec["maskiou_head.maskiou_fcn{}.bias".format(k + 1)] = ((dim,), "bias")
-            c = dim
-        spec["maskiou_head.maskiou_fc1.weight"] = ((1024, dim * res * res), "fc_relu")
-        spec["maskiou_head.maskiou_fc1.bias"] = ((1024,), "bias")
-        spec["maskiou_head.maskiou_fc2.weight"] = ((1024, 1024), "fc_relu")
-        spec["maskiou_head.maskiou_fc2.bias"] = ((1024,), "bias")
-        spec["maskiou_head.maskiou.weight"] = ((cfg.MODEL.ROI_HEADS.NUM_CLASSES, 1024), "maskiou_out")
-        spec["maskiou_head.maskiou.bias"] = ((cfg.MODEL.ROI_HEADS.NUM_CLASSES,), "maskiou_bias")
+        for k, v in maskiou_head_param_spec(cfg, in_channels, cfg.MODEL.ROI_MASK_HEAD.POOLER_RESOLUTION).items():
+            spec["maskiou_head." + k] = v
     if cfg.MODEL.KEYPOINT_ON:
-        # KRCNNConvDeconvUpsampleHead, keypoint_head.py:168-215
-        kh = cfg.MODEL.ROI_KEYPOINT_HEAD
-        c = in_channels
-        for k, dim in enumerate(kh.CONV_DIMS, 1):
-            spec["keypoint_head.conv_fcn{}.weight".format(k)] = ((dim, c, 3, 3), "conv_relu")
-            spec["keypoint_head.conv_fcn{}.bias".format(k)] = ((dim,), "bias")
-            c = dim
-        spec["keypoint_head.score_lowres.weight"] = ((c, kh.NUM_KEYPOINTS, 4, 4), "kp_deconv")
-        spec["keypoint_head.score_lowres.bias"] = ((kh.NUM_KEYPOINTS,), "bias")
+        for k, v in keypoint_head_param_spec(cfg, in_channels).items():
+            spec["keypoint_head." + k] = v
     return spec
 
 

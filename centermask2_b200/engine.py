@@ -654,39 +654,86 @@ class Engine(object):
             P["kp_deconv"] = packing.deconv4x4s2(sd, prefix + "keypoint_head.score_lowres", dt, dev, tc)
         if not cfg.MODEL.MASK_ON:
             return P
+        P.update(self.pack_mask_head(sd, prefix + "mask_head."))
+        if cfg.MODEL.MASKIOU_ON:
+            P.update(self.pack_maskiou_head(sd, prefix + "maskiou_head.", P["in_ch"], cfg.MODEL.ROI_MASK_HEAD.POOLER_RESOLUTION))
+        return P
+
+    def pack_mask_head(self, sd, prefix=""):
+        """SpatialAttentionMaskHead (sam.py:41-90); keys ``prefix + mask_fcn{k}.*`` ..."""
+        cfg, dt, dev, tc = self.cfg, self.dtype, self.device, self.tc
         mh = cfg.MODEL.ROI_MASK_HEAD
-        c = sd[prefix + "mask_head.mask_fcn1.weight"].shape[1] if mh.NUM_CONV > 0 else sd[prefix + "mask_head.deconv.weight"].shape[0]
+        P = {}
+        c = sd[prefix + "mask_fcn1.weight"].shape[1] if mh.NUM_CONV > 0 else sd[prefix + "deconv.weight"].shape[0]
         P["in_ch"] = c
         P["mask_fcn"] = []
         for k in range(mh.NUM_CONV):
-            P["mask_fcn"].append(packing.conv_bias(sd, prefix + "mask_head.mask_fcn{}".format(k + 1), [c], 1, 1, True, dt, dev, tc))
+            P["mask_fcn"].append(packing.conv_bias(sd, prefix + "mask_fcn{}".format(k + 1), [c], 1, 1, True, dt, dev, tc))
             c = mh.CONV_DIM
-        P["sam_w"] = sd[prefix + "mask_head.spatialAtt.conv.weight"].detach().reshape(18).to(device=dev, dtype=torch.float32).contiguous()
-        P["deconv"] = packing.deconv2x2(sd, prefix + "mask_head.deconv", dt, dev, tc)
-        pw = sd[prefix + "mask_head.predictor.weight"].detach()
+        P["sam_w"] = sd[prefix + "spatialAtt.conv.weight"].detach().reshape(18).to(device=dev, dtype=torch.float32).contiguous()
+        P["deconv"] = packing.deconv2x2(sd, prefix + "deconv", dt, dev, tc)
+        pw = sd[prefix + "predictor.weight"].detach()
         P["pred_w"] = pw.reshape(pw.shape[0], pw.shape[1]).to(device=dev, dtype=torch.float32).contiguous()
-        P["pred_b"] = sd[prefix + "mask_head.predictor.bias"].detach().to(device=dev, dtype=torch.float32).contiguous()
-        if cfg.MODEL.MASKIOU_ON:
-            mi = cfg.MODEL.ROI_MASKIOU_HEAD
-            P["iou_fcn"] = []
-            src = [P["in_ch"], 1]
-            for k in range(mi.NUM_CONV):
-                stride = 2 if k + 1 == mi.NUM_CONV else 1
-                wk = prefix + "maskiou_head.maskiou_fcn{}".format(k + 1)
-                if k == 0:
-                    # input = cat(roi feature, pooled mask) (maskiou_head.py:109-112); the single mask channel
-                    # lives in a 16-channel zero-padded buffer so that the TC engine can read it
-                    w = sd[wk + ".weight"].detach().float()
-                    wpad = torch.zeros((w.shape[0], P["in_ch"] + 16, 3, 3))
-                    wpad[:, :P["in_ch"] + 1] = w
-                    P["iou_fcn"].append(packing.ConvW(wpad, [P["in_ch"], 16], stride, 1, None, sd[wk + ".bias"], True, dt, dev, tc))
-                else:
-                    P["iou_fcn"].append(packing.conv_bias(sd, wk, [mi.CONV_DIM], stride, 1, True, dt, dev, tc))
-            r = mh.POOLER_RESOLUTION // 2
-            P["iou_fc1"] = packing.linear(sd, prefix + "maskiou_head.maskiou_fc1", True, dt, dev, tc, chw=(mi.CONV_DIM, r, r))
-            P["iou_fc2"] = packing.linear(sd, prefix + "maskiou_head.maskiou_fc2", True, dt, dev, tc)
-            P["iou_out"] = packing.linear(sd, prefix + "maskiou_head.maskiou", False, dt, dev, tc)
+        P["pred_b"] = sd[prefix + "predictor.bias"].detach().to(device=dev, dtype=torch.float32).contiguous()
+        P["pred_key"] = prefix + "predictor"
         return P
+
+    def pack_maskiou_head(self, sd, prefix, in_ch, resolution):
+        """MaskIoUHead (maskiou_head.py:64-105); ``in_ch`` = channels of the pooled ROI feature."""
+        cfg, dt, dev, tc = self.cfg, self.dtype, self.device, self.tc
+        mi = cfg.MODEL.ROI_MASKIOU_HEAD
+        P = {"iou_fcn": [], "iou_in_ch": in_ch}
+        for k in range(mi.NUM_CONV):
+            stride = 2 if k + 1 == mi.NUM_CONV else 1
+            wk = prefix + "maskiou_fcn{}".format(k + 1)
+            if k == 0:
+                # input = cat(roi feature, pooled mask) (maskiou_head.py:109-112); the single mask channel
+                # lives in a 16-channel zero-padded buffer so that the TC engine can read it
+                w = sd[wk + ".weight"].detach().float()
+                wpad = torch.zeros((w.shape[0], in_ch + 16, 3, 3))
+                wpad[:, :in_ch + 1] = w
+                P["iou_fcn"].append(packing.ConvW(wpad, [in_ch, 16], stride, 1, None, sd[wk + ".bias"], True, dt, dev, tc))
+            else:
+                P["iou_fcn"].append(packing.conv_bias(sd, wk, [mi.CONV_DIM], stride, 1, True, dt, dev, tc))
+        r = resolution // 2
+        P["iou_fc1"] = packing.linear(sd, prefix + "maskiou_fc1", True, dt, dev, tc, chw=(mi.CONV_DIM, r, r))
+        P["iou_fc2"] = packing.linear(sd, prefix + "maskiou_fc2", True, dt, dev, tc)
+        P["iou_out"] = packing.linear(sd, prefix + "maskiou", False, dt, dev, tc)
+        return P
+
+    # -- the two heads as stand-alone operators (modeling.roi_heads.SpatialAttentionMaskHead / MaskIoUHead) ----------
+    def run_mask_head_logits(self, roi, P, pred_conv):
+        """SpatialAttentionMaskHead.forward (sam.py:92-97): roi FMap [R, res, res, C] -> f32 logits [R, 2res, 2res, ncls] for
+        ALL classes (the fused plan of ``run_roi_heads`` computes only the class of each ROI)."""
+        self.begin_pass()
+        x = roi
+        for k, w in enumerate(P["mask_fcn"]):
+            x = self.conv("sa_mask_fcn{}".format(k + 1), [x], w)
+        att = self.fmap("sa_mask_att", x.n, x.h, x.w, x.c)
+        lib.spatial_attention(x.view, att.view, P["sam_w"])
+        up = self.conv("sa_mask_deconv", [att], P["deconv"], out_mode=1, out_halo=0)
+        return self.conv("sa_mask_logits", [up], pred_conv, out_dtype=torch.float32, out_halo=0)
+
+    def run_maskiou_head(self, roi, probs, P, fresh=True):
+        """MaskIoUHead.forward (maskiou_head.py:107-120): roi FMap [R, res, res, C] + mask f32 [R, 1, 2res, 2res] -> f32 [R, ncls].
+        ``fresh=False``: called inside a pass that already holds the split operands of ``roi`` (run_roi_heads)."""
+        if fresh:
+            self.begin_pass()
+        R, res = roi.n, roi.h
+        pm = self.fmap("iou_mask", R, res, res, 16)
+        lib.maskiou_prep(probs, pm.view)
+        y = None
+        nconv = len(P["iou_fcn"])
+        for k, w in enumerate(P["iou_fcn"]):
+            last = k + 1 == nconv
+            srcs = [roi, pm] if k == 0 else [y]
+            # the last conv is stride 2: on the TC engine its producer stores phase planes
+            to_phase = self.tc and k + 2 == nconv and k > 0
+            y = self.conv("iou_fcn{}".format(k + 1), srcs, w, out_halo=0 if last else 1, out_mode=2 if to_phase else 0)
+        flat = FMap(y.buf.reshape(R, 1, 1, -1), 0)
+        y = self.conv("iou_fc1", [flat], P["iou_fc1"], out_halo=0)
+        y = self.conv("iou_fc2", [y], P["iou_fc2"], out_halo=0)
+        return self.conv("iou_out", [y], P["iou_out"], out_dtype=torch.float32, out_halo=0)
 
     def image_area(self, image_sizes):
         """Unpadded image areas (pooler.py:70-77) as a device vector, cached per size list."""
@@ -726,20 +773,7 @@ class Engine(object):
             lib.mask_predict(up.view, P["pred_w"], P["pred_b"], classes, ncls, probs)
         mask_scores = None
         if cfg.MODEL.MASKIOU_ON:
-            pm = self.fmap("iou_mask", R, res, res, 16)
-            lib.maskiou_prep(probs, pm.view)
-            y = None
-            nconv = len(P["iou_fcn"])
-            for k, w in enumerate(P["iou_fcn"]):
-                last = k + 1 == nconv
-                srcs = [roi, pm] if k == 0 else [y]
-                # the last conv is stride 2: on the TC engine its producer stores phase planes
-                to_phase = self.tc and k + 2 == nconv and k > 0
-                y = self.conv("iou_fcn{}".format(k + 1), srcs, w, out_halo=0 if last else 1, out_mode=2 if to_phase else 0)
-            flat = FMap(y.buf.reshape(R, 1, 1, -1), 0)
-            y = self.conv("iou_fc1", [flat], P["iou_fc1"], out_halo=0)
-            y = self.conv("iou_fc2", [y], P["iou_fc2"], out_halo=0)
-            y = self.conv("iou_out", [y], P["iou_out"], out_dtype=torch.float32, out_halo=0)
+            y = self.run_maskiou_head(roi, probs, P, fresh=False)
             mask_scores = self.buffer("mask_scores", (R,), torch.float32, False)
             lib.maskiou_score(y.buf, R, y.c, classes, det["scores"].reshape(-1), mask_scores)
         return probs, mask_scores

@@ -423,11 +423,13 @@ class GeneralizedRCNN(nn.Module):
 
     # -- the fork's export-friendly variant ------------------------------------------------------
     @torch.no_grad()
-    def forward_tensor(self, img):
+    def forward_tensor(self, img, hw=None):
         """``modified_class.py:27-40``: already normalised + padded ``img[1,3,H,W]`` -> 6-tuple
-        (locations, mask_scores, pred_boxes, pred_classes, pred_masks, scores) of batch element 0."""
+        (locations, mask_scores, pred_boxes, pred_classes, pred_masks, scores) of batch element 0.  ``hw``: the
+        ``image_sizes`` list of the fork's ``FakeImageList`` (modified_class.py:11-24); like there it defaults to
+        1344 x 1344 per image whatever the tensor's extent (the fork feeds its fixed 1344 x 1344 export shape)."""
         features = self.backbone(img)
-        sizes = _Sizes([(img.shape[-2], img.shape[-1])] * img.shape[0])
+        sizes = _Sizes(hw if hw is not None else [(1344, 1344)] * img.shape[0])
         proposals, _ = self.proposal_generator(sizes, features, None)
         results, _ = self.roi_heads(sizes, features, proposals, None)
         r = results[0]

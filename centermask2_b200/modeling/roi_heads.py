@@ -9,9 +9,9 @@ import torch
 
 from .. import runtime
 from ..config import validate_cfg
-from ..arch import roi_heads_param_spec
+from ..arch import keypoint_head_param_spec, mask_head_param_spec, maskiou_head_param_spec
 from ..engine import as_fmap
-from .compat import ROI_HEADS_REGISTRY, Registry
+from .compat import ROI_HEADS_REGISTRY, Registry, ShapeSpec
 from .params import PackedModule, attach_params
 
 # The reference registers its heads in two more registries (mask_head.py:17, maskiou_head.py:10);
@@ -22,14 +22,71 @@ ROI_KEYPOINT_HEAD_REGISTRY = Registry("ROI_KEYPOINT_HEAD")                      
 
 
 @ROI_MASK_HEAD_REGISTRY.register()
-class SpatialAttentionMaskHead(object):
-    """Marker for ``cfg.MODEL.ROI_MASK_HEAD.NAME`` (sam.py:31); its parameters live under
-    ``CenterROIHeads.mask_head.*`` and its compute is part of the fused ROI plan."""
+class SpatialAttentionMaskHead(PackedModule):
+    """``sam.py:31-97``: ``SpatialAttentionMaskHead(cfg, input_shape).forward(x[R, C, res, res]) -> logits[R, num_mask_classes,
+    2res, 2res]`` (all classes, no sigmoid -- what ``mask_rcnn_inference`` consumes, mask_head.py:174-216).  Parameters under
+    the reference's names (``mask_fcn{k}``, ``spatialAtt.conv``, ``deconv``, ``predictor``).  Inside ``CenterROIHeads`` the
+    same parameters feed the fused ROI plan, which evaluates only the class of each ROI."""
+
+    def __init__(self, cfg, input_shape):
+        super().__init__()
+        self.cfg = cfg
+        validate_cfg(cfg, "roi_heads")
+        self.in_channels = input_shape.channels
+        attach_params(self, mask_head_param_spec(cfg, input_shape.channels))
+
+    def _pack(self):
+        from .. import packing
+        eng = runtime.engine_for(self.cfg)
+        if self._packed is None or self._engine is not eng:
+            sd = self.state_dict()
+            P = eng.pack_mask_head(sd)
+            c = sd["predictor.weight"].shape[1]
+            P["pred_conv"] = packing.conv_bias(sd, "predictor", [c], 1, 0, False, eng.dtype, eng.device, eng.tc)
+            self._packed, self._engine = P, eng
+        return eng, self._packed
+
+    def forward(self, x):
+        eng, P = self._pack()
+        out = eng.run_mask_head_logits(as_fmap(x, eng.dtype, eng.device), P, P["pred_conv"])
+        return out.view.permute(0, 3, 1, 2)
 
 
 @ROI_MASKIOU_HEAD_REGISTRY.register()
-class MaskIoUHead(object):
-    """Marker for ``cfg.MODEL.ROI_MASKIOU_HEAD.NAME`` (maskiou_head.py:63)."""
+class MaskIoUHead(PackedModule):
+    """``maskiou_head.py:63-120``: ``MaskIoUHead(cfg, input_shape).forward(x[R, C, res, res], mask[R, 1, 2res, 2res]) ->
+    [R, num_classes]`` (max-pool the mask, concatenate, 4 convs, 3 linear layers); ``input_shape.channels`` / ``.width`` as
+    ``CenterROIHeads`` passes them (center_heads.py:353-356)."""
+
+    def __init__(self, cfg, input_shape):
+        super().__init__()
+        self.cfg = cfg
+        self.in_channels = input_shape.channels
+        self.resolution = input_shape.width
+        attach_params(self, maskiou_head_param_spec(cfg, input_shape.channels, input_shape.width))
+
+    def _pack(self):
+        eng = runtime.engine_for(self.cfg)
+        if self._packed is None or self._engine is not eng:
+            self._packed = eng.pack_maskiou_head(self.state_dict(), "", self.in_channels, self.resolution)
+            self._engine = eng
+        return eng, self._packed
+
+    def forward(self, x, mask):
+        eng, P = self._pack()
+        probs = mask.to(device=eng.device, dtype=torch.float32).contiguous()
+        out = eng.run_maskiou_head(as_fmap(x, eng.dtype, eng.device), probs, P)
+        return out.buf.reshape(out.n, -1)
+
+
+def build_mask_head(cfg, input_shape):
+    """``mask_head.py:284-289``: the head named by ``cfg.MODEL.ROI_MASK_HEAD.NAME``."""
+    return ROI_MASK_HEAD_REGISTRY.get(cfg.MODEL.ROI_MASK_HEAD.NAME)(cfg, input_shape)
+
+
+def build_maskiou_head(cfg, input_shape):
+    """``maskiou_head.py:123-128``: the head named by ``cfg.MODEL.ROI_MASKIOU_HEAD.NAME``."""
+    return ROI_MASKIOU_HEAD_REGISTRY.get(cfg.MODEL.ROI_MASKIOU_HEAD.NAME)(cfg, input_shape)
 
 
 @ROI_KEYPOINT_HEAD_REGISTRY.register()
@@ -48,24 +105,39 @@ class CenterROIHeads(PackedModule):
         self.mask_on = bool(cfg.MODEL.MASK_ON)
         self.maskiou_on = bool(cfg.MODEL.MASKIOU_ON)
         self.keypoint_on = bool(cfg.MODEL.KEYPOINT_ON)                           # center_heads.py:360
-        ROI_MASK_HEAD_REGISTRY.get(cfg.MODEL.ROI_MASK_HEAD.NAME)
-        if self.maskiou_on:
-            ROI_MASKIOU_HEAD_REGISTRY.get(cfg.MODEL.ROI_MASKIOU_HEAD.NAME)
         chans = {input_shape[f].channels for f in self.in_features}
         assert len(chans) == 1, chans                                            # center_heads.py:327
         self.strides = [input_shape[f].stride for f in self.in_features]
+        in_ch = next(iter(chans))
+        res = cfg.MODEL.ROI_MASK_HEAD.POOLER_RESOLUTION
+        # the heads are real sub-modules built through their registries (center_heads.py:337-356); they own the parameters
+        # (``mask_head.*`` / ``maskiou_head.*`` keys) and can be called on their own; the fused ROI plan packs the same tensors
+        if self.mask_on:
+            self.mask_head = build_mask_head(cfg, ShapeSpec(channels=in_ch, width=res, height=res))
+        if self.maskiou_on:
+            self.maskiou_head = build_maskiou_head(cfg, ShapeSpec(channels=in_ch, width=res, height=res))
         if self.keypoint_on:
             ROI_KEYPOINT_HEAD_REGISTRY.get(cfg.MODEL.ROI_KEYPOINT_HEAD.NAME)
             self.kp_in_features = list(cfg.MODEL.ROI_KEYPOINT_HEAD.IN_FEATURES)  # center_heads.py:363
             self.kp_strides = [input_shape[f].stride for f in self.kp_in_features]
-            assert input_shape[self.kp_in_features[0]].channels == chans.copy().pop()
-        attach_params(self, roi_heads_param_spec(cfg, chans.pop()))
+            assert input_shape[self.kp_in_features[0]].channels == in_ch
+            attach_params(self, {"keypoint_head." + k: v for k, v in keypoint_head_param_spec(cfg, in_ch).items()})
+
+    def _head_gens(self):
+        """Weight generations of the head sub-modules: a head whose weights were loaded on its own re-packs the plan too."""
+        return tuple(getattr(self, n)._pack_gen for n in ("mask_head", "maskiou_head") if hasattr(self, n))
+
+    def graph_token(self):
+        return ("cm2w", id(self), (self._pack_gen,) + self._head_gens())
 
     def _pack(self):
         eng = runtime.engine_for(self.cfg)
-        if self._packed is None or self._engine is not eng:
+        gens = self._head_gens()
+        if self._packed is None or self._engine is not eng or self._packed_gens != gens:
+            if self._packed is not None and self._engine is not None:
+                self._engine.drop_graphs(id(self))
             self._packed = eng.pack_roi_heads(self.state_dict())
-            self._engine = eng
+            self._engine, self._packed_gens = eng, gens
         return eng, self._packed
 
     def run(self, feats, det, image_sizes):

@@ -106,3 +106,46 @@ def instances_to_coco_json(instances, img_id):
             res["keypoints"] = kp[k]
         out.append(res)
     return out
+
+
+def results_to_coco_json(result, image_ids):
+    """``coco_evaluation.py:362-427`` for a ``parallel.BatchResult`` (records + run lengths already on the host, as
+    ``GeneralizedRCNN.inference_records`` yields them): one dict per valid detection with ``bbox`` XYWH, ``score``,
+    ``category_id``, ``mask_score`` and the ``segmentation`` RLE with its ``counts`` compressed by ``rleToString`` and
+    decoded to utf-8 -- the same json ``instances_to_coco_json`` builds from ``Instances``, without the masks ever
+    crossing PCIe."""
+    from . import parallel as P
+    rec = result.records
+    h, w = result.size
+    out = []
+    for i, img_id in enumerate(image_ids):
+        k = int(rec[i, 0, P.F_COUNT])
+        for j in range(k):
+            r = rec[i, j]
+            if r[P.F_VALID] != 1:
+                continue
+            x0, y0, x1, y1 = [float(v) for v in r[P.F_BOX:P.F_BOX + 4]]
+            out.append({"image_id": img_id, "category_id": int(r[P.F_CLASS]), "bbox": [x0, y0, x1 - x0, y1 - y0],
+                        "score": float(r[P.F_SCORE]),
+                        "segmentation": {"size": [h, w], "counts": runs_to_string(result.runs(i, j)).decode("utf-8")},
+                        "mask_score": float(r[P.F_MASK_SCORE])})
+    return out
+
+
+def prepare_segm_results(coco_results):
+    """The mask-score-aware half of ``_evaluate_predictions_on_coco`` for ``iou_type == "segm"``
+    (``coco_evaluation.py:551-563``): on a deep copy, drop ``bbox`` (so that COCOeval takes the instance area from the mask)
+    and, when the results carry a ``mask_score`` (MaskIoU head: score * predicted mask IoU, maskiou_head.py:50-60), rank the
+    masks by it instead of by the box score.  What follows in the reference (``coco_gt.loadRes`` + ``COCOeval``) needs
+    pycocotools and the COCO annotations and is out of scope."""
+    import copy
+    results = copy.deepcopy(coco_results)
+    if not results:
+        return results
+    has_mask_scores = "mask_score" in results[0]
+    for c in results:
+        c.pop("bbox", None)
+        if has_mask_scores:
+            c["score"] = c["mask_score"]
+            del c["mask_score"]
+    return results

@@ -16,13 +16,13 @@ import torch
 
 from centermask2_b200.synth import synthetic_state_dict, synthetic_images, calibrate_cls_bias
 from oracle import refrun, restate
-from oracle.cases import CASES, case_cfg
+from oracle.cases import CASES, case_cfg, case_flags
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
 def build_case(name):
-    overrides, sizes, wseed, iseed, target = CASES[name]
+    overrides, sizes, wseed, iseed, target = CASES[name][:5]
     cfg = case_cfg(name)
     sd = synthetic_state_dict(cfg, seed=wseed)
     inputs = []
@@ -49,6 +49,12 @@ def calibrate(cfg, sd, inputs, target):
     b = calibrate_cls_bias(tr["logits"], target)
     sd[key] = torch.full_like(sd[key], b)
     return b
+
+
+def cfg_cpu(cfg):
+    c = cfg.clone()
+    c.MODEL.DEVICE = "cpu"
+    return c
 
 
 def fields_to_dict(inst):
@@ -92,6 +98,23 @@ def main():
             "raw": raw, "post": post,
             "torch": torch.__version__,
         }
+        flags = case_flags(name)
+        if flags.get("lean"):                 # variant cases: the end results pin the behaviour, intermediates are dropped
+            for k in ("features", "logits", "regs", "ctrs"):
+                gold.pop(k)
+        if flags.get("tensor_in"):
+            # modified_class.GeneralizedRCNN.forward (the fork's export-friendly meta-arch): already normalised + padded
+            # tensor in, 6-tuple out, image_sizes fixed by FakeImageList (modified_class.py:11-24)
+            sys.path.insert(0, refrun.REFERENCE_ROOT)
+            import modified_class
+            m2 = modified_class.GeneralizedRCNN(cfg_cpu(cfg))
+            m2.eval()
+            m2.load_state_dict(sd, strict=True)
+            with torch.no_grad(), refrun.quiet():
+                x = model.preprocess_image(inputs).tensor.clone()
+                out = m2(x)
+            gold["tensor_in"] = {"input": x, "outputs": [o.clone() for o in out],
+                                 "names": ["locations", "mask_scores", "pred_boxes", "pred_classes", "pred_masks", "scores"]}
         path = os.path.join(OUT, name + ".pt")
         torch.save(gold, path)
         print("{:16s} bias {:8.3f} cand/level {} dets {} -> {} ({:.0f} KB)".format(

@@ -21,7 +21,7 @@ def load_golden(name):
 
 def build_case(name, gold=None):
     """cfg, state_dict (with the golden's calibrated cls bias) and inputs of a named case."""
-    overrides, sizes, wseed, iseed, target = CASES[name]
+    overrides, sizes, wseed, iseed, target = CASES[name][:5]
     cfg = case_cfg(name)
     sd = synthetic_state_dict(cfg, seed=wseed)
     if gold is None:

@@ -41,6 +41,8 @@ def case(request):
 
 def test_backbone_and_head_tensors_match_reference(case):
     name, gold, cfg, sd, inputs, model = case
+    if "features" not in gold:
+        pytest.skip("lean golden (variant case): end results only")
     images = model.preprocess_image(inputs)
     feats = model.backbone(images.tensor)
     for k, v in gold["features"].items():
@@ -322,3 +324,66 @@ def test_inference_records_hand_the_whole_result_to_the_host(case):
             for j in range(r_cap):
                 if j not in keep:                                            # empty / dropped slots: one run of zeros
                     assert res.runs(i, j).tolist() == [oh * ow]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp32_simt"])
+def test_forward_tensor_matches_the_forks_tuple_out_meta_arch(precision):
+    """``GeneralizedRCNN.forward_tensor`` against the 6-tuple the reference's own ``modified_class.GeneralizedRCNN.forward``
+    (modified_class.py:27-40) returned for the same normalised + padded tensor (golden ``v19_tensor_in``)."""
+    runtime.reset()
+    runtime.set_precision(precision)
+    try:
+        name = "v19_tensor_in"
+        gold = load_golden(name)
+        cfg, sd, inputs = build_case(name, gold)
+        model = cm.build_model(cfg)
+        model.load_state_dict(sd)
+        out = model.forward_tensor(gold["tensor_in"]["input"].cuda())
+        got = dict(zip(gold["tensor_in"]["names"], [o.cpu() for o in out]))
+        want = dict(zip(gold["tensor_in"]["names"], gold["tensor_in"]["outputs"]))
+        assert_detections_match(got, want, what=name)
+        assert (got["pred_masks"] - want["pred_masks"]).abs().max().item() <= 1e-3
+    finally:
+        runtime.reset()
+        runtime.set_precision("fp32")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp32_simt", "bf16"])
+def test_standalone_mask_heads_match_the_reference_modules(precision):
+    """``build_mask_head(cfg, shape).forward(x)`` (sam.py:92-97: logits of ALL classes) and ``build_maskiou_head(cfg,
+    shape).forward(x, mask)`` (maskiou_head.py:107-120) as stand-alone registry objects, against the oracle's restatement
+    of the two reference modules; and the heads hanging off ``CenterROIHeads`` are these very classes."""
+    from centermask2_b200.modeling import ShapeSpec
+    from centermask2_b200.modeling.roi_heads import build_mask_head, build_maskiou_head, SpatialAttentionMaskHead, MaskIoUHead
+    from centermask2_b200.synth import synthetic_state_dict
+    runtime.reset()
+    runtime.set_precision(precision)
+    try:
+        cfg = cm.get_cfg("centermask_V_39_eSE_FPN.yaml", ["MODEL.VOVNET.CONV_BODY", "V-19-eSE"])
+        sd = synthetic_state_dict(cfg, seed=9)
+        shape = ShapeSpec(channels=256, width=14, height=14)
+        mh, ih = build_mask_head(cfg, shape), build_maskiou_head(cfg, shape)
+        assert isinstance(mh, SpatialAttentionMaskHead) and isinstance(ih, MaskIoUHead)
+        mh.load_state_dict({k[len("roi_heads.mask_head."):]: v for k, v in sd.items() if k.startswith("roi_heads.mask_head.")}, strict=True)
+        ih.load_state_dict({k[len("roi_heads.maskiou_head."):]: v for k, v in sd.items() if k.startswith("roi_heads.maskiou_head.")},
+                           strict=True)
+        g = torch.Generator().manual_seed(3)
+        x = torch.relu(torch.randn(37, 256, 14, 14, generator=g))
+        mask = torch.rand(37, 1, 28, 28, generator=g)
+        bf = precision == "bf16"
+        with restate.bf16_sim(bf):
+            ref_logits, _ = restate.mask_head_forward(restate._q(x), sd, cfg)
+            ref_iou = restate.maskiou_head_forward(restate._q(x), mask, sd, cfg)
+        got_logits = mh(x.cuda()).float().cpu()
+        got_iou = ih(x.cuda(), mask.cuda()).float().cpu()
+        assert got_logits.shape == ref_logits.shape == (37, 80, 28, 28) and got_iou.shape == ref_iou.shape == (37, 80)
+        tol = 3e-2 if bf else 1e-4
+        for got, ref, what in ((got_logits, ref_logits, "mask logits"), (got_iou, ref_iou, "maskiou")):
+            err = ((got - ref).abs().max() / ref.abs().max()).item()
+            print("{} [{}]: max err / max |ref| = {:.2e}".format(what, precision, err))
+            assert err <= tol, (what, err)
+        model = cm.build_model(cfg)
+        assert type(model.roi_heads.mask_head) is SpatialAttentionMaskHead and type(model.roi_heads.maskiou_head) is MaskIoUHead
+    finally:
+        runtime.reset()
+        runtime.set_precision("fp32")

@@ -27,6 +27,8 @@ def test_weights_reproduce(case):
 
 def test_head_tensors(case):
     name, gold, cfg, sd, inputs, raw, trace = case
+    if "features" not in gold:
+        pytest.skip("lean golden (variant case): end results only")
     for k, v in gold["features"].items():
         assert torch.allclose(trace["features"][k], v, rtol=1e-4, atol=1e-4), k
     for a, b in zip(trace["logits"], gold["logits"]):
@@ -71,3 +73,42 @@ def test_pre_topk_semantics_only_differ_when_crowded(case):
     if not crowded and max(gold["candidates_per_level"]) <= cfg.MODEL.FCOS.PRE_NMS_TOPK_TEST:
         for a, b in zip(capped, raw):
             assert torch.equal(a["pred_boxes"], b["pred_boxes"])
+
+
+def test_tensor_in_tuple_out_variant_of_the_fork():
+    """modified_class.GeneralizedRCNN.forward (modified_class.py:27-40) restated with the oracle's pieces: normalised +
+    padded tensor in, (locations, mask_scores, pred_boxes, pred_classes, pred_masks, scores) out, image_sizes fixed at
+    1344 x 1344 by FakeImageList (modified_class.py:11-24) -- against the tuple the reference's own class produced."""
+    name = "v19_tensor_in"
+    gold = load_golden(name)
+    cfg, sd, inputs = build_case(name, gold)
+    x = gold["tensor_in"]["input"]
+    with torch.no_grad():
+        feats = restate.fpn_forward(restate.vovnet_forward(x, sd, cfg), sd, cfg)
+        logits, regs, ctrs = restate.fcos_head_forward(feats, sd, cfg)
+        dets = restate.fcos_postprocess(logits, regs, ctrs, [(1344, 1344)] * x.shape[0], cfg, pre_topk=False)
+        dets = restate.roi_heads_forward(feats, dets, sd, cfg)
+    d = dets[0]
+    want = dict(zip(gold["tensor_in"]["names"], gold["tensor_in"]["outputs"]))
+    assert_detections_match(d, want, what=name)
+    assert torch.allclose(d["pred_masks"], want["pred_masks"], atol=1e-4)
+
+
+def test_config_defaults_equal_the_reference_defaults():
+    """centermask/config/defaults.py:9-86 imported unchanged (needs /root/reference: build container only)."""
+    from oracle import refrun
+    if not refrun.available():
+        pytest.skip("reference tree not present")
+    refrun._import_reference()
+    from centermask.config import get_cfg as ref_get_cfg
+    from centermask2_b200.config import get_cfg
+
+    def flat(node, prefix=""):
+        out = {}
+        for k, v in node.items():
+            if isinstance(v, dict):
+                out.update(flat(v, prefix + k + "."))
+            else:
+                out[prefix + k] = list(v) if isinstance(v, (list, tuple)) else v
+        return out
+    assert flat(ref_get_cfg()) == flat(get_cfg())

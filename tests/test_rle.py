@@ -103,3 +103,45 @@ def test_instances_to_coco_json_keypoints():
     assert out[1]["keypoints"] == pytest.approx([1.0, 2.0, 0.3, 0.0, 0.0, 0.2])
     assert torch.equal(inst.pred_keypoints, kp)                   # the caller's tensor is not shifted
     assert "segmentation" not in out[0]
+
+
+def test_batch_result_to_coco_json_and_mask_score_aware_segm_scoring():
+    """BatchResult (records + run lengths on the host) -> the json of coco_evaluation.py:362-427, then the segm branch of
+    _evaluate_predictions_on_coco (:551-563): bbox dropped, score replaced by mask_score.  CPU only."""
+    import numpy as np
+    import torch
+    from centermask2_b200 import parallel as P
+    from centermask2_b200 import rle
+    from oracle import rle as orle
+    h, w, r_cap = 7, 5, 3
+    g = torch.Generator().manual_seed(0)
+    rec = torch.zeros((2, r_cap, P.RECORD_FIELDS))
+    masks, runs, offs = {}, [], [0]
+    counts = [2, 1]
+    for i in range(2):
+        rec[i, :, P.F_COUNT] = counts[i]
+        for j in range(r_cap):
+            live = j < counts[i]
+            m = (torch.rand(h, w, generator=g) > 0.5).numpy() if live else np.zeros((h, w), dtype=bool)
+            masks[(i, j)] = m
+            c = orle.rle_encode(m)
+            runs += c
+            offs.append(offs[-1] + len(c))
+            if live:
+                rec[i, j, :4] = torch.tensor([1.0 + j, 2.0, 4.0 + j, 6.0])
+                rec[i, j, P.F_SCORE], rec[i, j, P.F_CLASS], rec[i, j, P.F_MASK_SCORE], rec[i, j, P.F_VALID] = 0.9 - 0.1 * j, 17 + j, 0.5 + 0.1 * j, 1.0
+    rec[0, 1, P.F_VALID] = 0.0                                        # dropped by detector_postprocess (empty after clipping)
+    res = P.BatchResult(rec, torch.tensor(offs), torch.tensor(runs, dtype=torch.int32), (h, w))
+    js = rle.results_to_coco_json(res, [101, 102])
+    assert [(d["image_id"], d["category_id"]) for d in js] == [(101, 17), (102, 17)]
+    d = js[0]
+    assert d["bbox"] == [1.0, 2.0, 3.0, 4.0] and abs(d["score"] - 0.9) < 1e-6 and abs(d["mask_score"] - 0.5) < 1e-6
+    assert d["segmentation"]["size"] == [h, w]
+    back = orle.rle_decode(orle.rle_from_string(d["segmentation"]["counts"]), h, w)
+    assert np.array_equal(back.astype(bool), masks[(0, 0)]) and np.array_equal(res.mask(0, 0), masks[(0, 0)])
+    segm = rle.prepare_segm_results(js)
+    assert all("bbox" not in c and "mask_score" not in c for c in segm) and abs(segm[0]["score"] - 0.5) < 1e-6
+    assert "bbox" in js[0] and "mask_score" in js[0]                 # the caller's list is untouched (deep copy, :553)
+    no_ms = [{k: v for k, v in c.items() if k != "mask_score"} for c in js]
+    assert abs(rle.prepare_segm_results(no_ms)[0]["score"] - 0.9) < 1e-6
+    assert rle.prepare_segm_results([]) == []
