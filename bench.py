@@ -302,6 +302,7 @@ def instrumented_step(model, cfg, dev_images, sizes_out, steps, layers=None):
             return wrapped
         setattr(lib, fn_name, make())
     eng.conv, eng.conv_seg = timed_conv, timed_seg
+    branches, eng.branch_streams = eng.branch_streams, False      # one kernel at a time: every event pair times its own launch only
     try:
         for _ in range(steps):
             # keep the GPU behind the host while the step is enqueued: with an empty queue every (event, launch) pair
@@ -311,6 +312,7 @@ def instrumented_step(model, cfg, dev_images, sizes_out, steps, layers=None):
         torch.cuda.synchronize()
     finally:
         eng.conv, eng.conv_seg = orig_conv, orig_seg
+        eng.branch_streams = branches
         for fn_name, orig in saved.items():
             setattr(lib, fn_name, orig)
     conv_total = sum(a.elapsed_time(b) for a, b in conv_events)

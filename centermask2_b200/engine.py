@@ -152,6 +152,11 @@ class Engine(object):
         self.graph_after = max(1, int(os.environ.get("CM2_GRAPH_AFTER", "1")))      # eager runs of a key before it is captured
         self.graph_cache = max(1, int(os.environ.get("CM2_GRAPH_CACHE", "16")))     # captured graphs kept (LRU)
         self.buffer_budget = int(float(os.environ.get("CM2_BUFFER_BUDGET_GB", "96")) * (1 << 30))
+        # independent branches of the launch plan (FCOS cls / bbox towers, the P6 / P7 chain) go to a second stream: when
+        # a launch does not fill the 148 SMs (small batches, small maps) the other branch runs beside it
+        # (measured, profiles/r2_small_batch.txt: -3.6 % step time at 2 images per GPU, -2 % on the Lite config, nothing at 16
+        # images where every launch already runs ~20 waves of tiles -- so it is used below BRANCH_MAX_ROWS GEMM rows)
+        self.branch_streams = os.environ.get("CM2_BRANCH_STREAMS", "1") != "0"
         lib.load()
 
     # -- buffers ---------------------------------------------------------------------------------
@@ -215,6 +220,23 @@ class Engine(object):
             st = torch.cuda.Stream(device=self.device)
             self._bufs[key] = st
         return st
+
+    BRANCH_MAX_ROWS = 8 * 148 * 128          # a tower launch of fewer than ~8 waves of 128-row tiles leaves SMs idle at its tail
+
+    def fork(self):
+        """Start a branch: returns a side stream ordered after everything enqueued so far on the current stream (works
+        eagerly and under CUDA-graph capture, where it becomes a parallel branch of the graph)."""
+        side = self.side_stream("branch")
+        ev = torch.cuda.Event()
+        ev.record()
+        side.wait_event(ev)
+        return side
+
+    def join(self, side):
+        """End a branch: the current stream waits for everything enqueued on ``side``."""
+        ev = torch.cuda.Event()
+        ev.record(side)
+        torch.cuda.current_stream().wait_event(ev)
 
     def pinned(self, name, shape, dtype):
         """Page-locked host staging buffer (async D2H of the small result-size tensors)."""
@@ -492,21 +514,34 @@ class Engine(object):
                 shapes.append((shapes[0][0], hh, ww))
             pyramid = self.segmap("pyramid", shapes, cfg.MODEL.FPN.OUT_CHANNELS)
         slot = {nme: i for i, nme in enumerate(names)}
-        for f in reversed(in_feats):
+
+        def top_levels():
+            # LastLevelP6P7 / LastLevelP6, fpn.py:32-35, :50-53 (P7 = conv(relu(P6)))
+            top = res[names[len(in_feats) - 1]]
+            for i, w in enumerate(P["top"]):
+                nme = names[len(in_feats) + i]
+                if self.tc:
+                    src = self.phase_split(nme + "_src_phase", top, relu=(i == 1))
+                    top = self.conv(nme, [src], w, out=pyramid.level(slot[nme]))
+                else:
+                    top = self.conv(nme, [top], w, in_relu=(i == 1))
+                res[nme] = top
+
+        side = None
+        for fi, f in enumerate(reversed(in_feats)):
             lvl, lat, outc = P["fpn"][f]
             prev = self.conv("fpn_inner{}".format(lvl), [stage_out[f]], lat, residual=prev, res_mode=2 if prev is not None else 0)
             nme = "p{}".format(lvl)
             res[nme] = self.conv(nme, [prev], outc, out=pyramid.level(slot[nme]) if pyramid is not None else None)
-        # LastLevelP6P7, fpn.py:32-35 (P7 = conv(relu(P6)))
-        top = res[names[len(in_feats) - 1]]
-        for i, w in enumerate(P["top"]):
-            nme = names[len(in_feats) + i]
-            if self.tc:
-                src = self.phase_split(nme + "_src_phase", top, relu=(i == 1))
-                top = self.conv(nme, [src], w, out=pyramid.level(slot[nme]))
-            else:
-                top = self.conv(nme, [top], w, in_relu=(i == 1))
-            res[nme] = top
+            if fi == 0 and P["top"] and self.tc and self.branch_streams and len(in_feats) > 1 and pyramid.rows <= self.BRANCH_MAX_ROWS:
+                # the extra levels hang off the coarsest output only: their small launches run beside the finer levels
+                side = self.fork()
+                with torch.cuda.stream(side):
+                    top_levels()
+        if side is not None:
+            self.join(side)
+        elif P["top"]:
+            top_levels()
         out = {k: res[k] for k in sorted(res)}
         if pyramid is not None:
             self._pyramid = (pyramid, [out[k] for k in names])
@@ -584,20 +619,32 @@ class Engine(object):
             for i, (conv, gn) in enumerate(units):
                 if gn is not None and conv.cout % 256 == 0:
                     # GroupNorm statistics come out of the conv epilogue (fp64 sums per image and 8-channel chunk)
-                    st = self.buffer("fcos_gnstats_seg", (n_img, conv.cout // 8, 2), torch.float64, zero=False)
+                    st = self.buffer("fcos_gnstats_seg_" + tag, (n_img, conv.cout // 8, 2), torch.float64, zero=False)
                     x = self.conv_seg("fcos_{}{}_seg".format(tag, i), x, conv, stats=st, stats_mode=2)
                     lib.groupnorm_apply_seg(x.flat, x.segs, 32, gn[0], gn[1], 1e-5, True, st)
                     continue
                 x = self.conv_seg("fcos_{}{}_seg".format(tag, i), x, conv)
                 if gn is not None:
-                    wsp = self.buffer("fcos_gnws_seg", (lib.gn_seg_workspace_floats(x.segs, x.c, 32),), torch.float32, zero=False)
+                    wsp = self.buffer("fcos_gnws_seg_" + tag, (lib.gn_seg_workspace_floats(x.segs, x.c, 32),), torch.float32, zero=False)
                     lib.groupnorm_relu_seg(x.flat, x.segs, 32, gn[0], gn[1], 1e-5, True, wsp)
             return x
         x = tower(pyramid, P["towers"]["share"], "share")
-        ct = tower(x, P["towers"]["cls"], "cls")
-        bt = tower(x, P["towers"]["bbox"], "bbox")
-        logits = self.conv_seg("fcos_logits_seg", ct, P["cls"], out_dtype=torch.float32)
-        regctr = self.conv_seg("fcos_regctr_seg", bt, P["regctr"], out_dtype=torch.float32)
+        if self.branch_streams and pyramid.rows <= self.BRANCH_MAX_ROWS:
+            # the classification and the box branch are independent (fcos.py:227-238): two streams
+            if self.split:
+                self.split_of(x.flat)                   # both branches read it: make the operand split before they part
+            side = self.fork()
+            with torch.cuda.stream(side):
+                bt = tower(x, P["towers"]["bbox"], "bbox")
+                regctr = self.conv_seg("fcos_regctr_seg", bt, P["regctr"], out_dtype=torch.float32)
+            ct = tower(x, P["towers"]["cls"], "cls")
+            logits = self.conv_seg("fcos_logits_seg", ct, P["cls"], out_dtype=torch.float32)
+            self.join(side)
+        else:
+            ct = tower(x, P["towers"]["cls"], "cls")
+            bt = tower(x, P["towers"]["bbox"], "bbox")
+            logits = self.conv_seg("fcos_logits_seg", ct, P["cls"], out_dtype=torch.float32)
+            regctr = self.conv_seg("fcos_regctr_seg", bt, P["regctr"], out_dtype=torch.float32)
         return [(logits.level(l), regctr.level(l)) for l in range(len(pyramid.segs))]
 
     def run_fcos_post(self, head_out, cand_cap=None, reg_scale=None):
