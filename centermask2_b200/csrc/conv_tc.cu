@@ -1295,12 +1295,19 @@ template <int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) conv_tc3_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 2;
-  const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;          // A_hi, A_lo, W_hi, W_lo
-  const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
-  const uint32_t tb = bar_base + 8u * (2 * p.stages);
+  // A ring: slots of {x_hi slab, x_lo slab} (a_box_rows rows of 128 B each); W ring: slots of {W_hi, W_lo} (bn rows each).
+  // kx-merge (stride-1 3x3): one slab of 136 rows per (ky, source, k-block) serves the three kx taps -- the MMA A
+  // descriptor starts 0 / 1 / 2 rows into it, as in conv_tc2_kernel -- so x traffic drops 3x; this kernel is bound by
+  // L2 -> shared-memory bytes (64 KB per 12 MMAs unmerged), so that is where its time goes.
+  const uint32_t a_half = (uint32_t)p.a_box_rows * 128u, a_slot = 2u * a_half;
+  const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 2, w_slot = 2u * b_bytes;
+  const uint32_t w_base = base + (uint32_t)p.sa_stages * a_slot;
+  const uint32_t bar_base = w_base + (uint32_t)p.sb_stages * w_slot;
+  auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (p.sa_stages + s); };
+  auto wfull_bar = [&](int s) { return bar_base + 8u * (2 * p.sa_stages + s); };
+  auto wempty_bar = [&](int s) { return bar_base + 8u * (2 * p.sa_stages + p.sb_stages + s); };
+  const uint32_t tb = bar_base + 8u * (2 * p.sa_stages + 2 * p.sb_stages);
   auto mfull_bar = [&](int a) { return tb + 8u * a; };
   auto mempty_bar = [&](int a) { return tb + 8u * (2 + a); };
   auto xfull_bar = [&](int a) { return tb + 8u * (4 + a); };
@@ -1314,11 +1321,14 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc3_kernel(const __grid_constant
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int nkb = p.taps * p.nblk_total;                  // K-blocks per tile
   const int nchunks = (nkb + p.chunk - 1) / p.chunk;
+  const int per_slab = p.kx_merge ? 3 : 1;                // W tiles consumed per A slab
+  const int ngroup_outer = p.kx_merge ? 3 : p.taps;       // ky (merged) or tap
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&p.a_map[s]);
     tma_prefetch_desc(&p.b_map);
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < p.sa_stages; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
+    for (int s = 0; s < p.sb_stages; ++s) { mbar_init(wfull_bar(s), 1); mbar_init(wempty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) {
       mbar_init(mfull_bar(a), 1); mbar_init(mempty_bar(a), (uint32_t)n_epi_warps);
       mbar_init(xfull_bar(a), 1); mbar_init(xempty_bar(a), (uint32_t)n_epi_warps);
@@ -1337,28 +1347,40 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc3_kernel(const __grid_constant
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    int stage = 0;
-    uint32_t phase = 0;
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int m0 = p.row_begin + (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.bn;
-      int kb = 0;
-      for (int tap = 0; tap < p.taps; ++tap) {
-        const int shift = tc_tap_shift(p, tap, p.num_seg ? tc_geom(p, m0).pitch : p.pitch);
+      const int pitch = p.num_seg ? tc_geom(p, m0).pitch : p.pitch;
+      for (int g = 0; g < ngroup_outer; ++g) {
+        const int row0 = m0 + (p.kx_merge ? tc_tap_shift(p, g * 3 + 1, pitch) - 1 : tc_tap_shift(p, g, pitch));
+        int blk = 0;
         for (int s = 0; s < p.num_src; ++s) {
           const int c = p.src_c[s];
           const int nblk = (c + TC_BK - 1) / TC_BK;
-          for (int cb = 0; cb < nblk; ++cb, ++kb) {
-            mbar_wait_ctl(p.spin, empty_bar(stage), phase ^ 1u);
-            const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+          for (int cb = 0; cb < nblk; ++cb, ++blk) {
+            mbar_wait_ctl(p.spin, aempty_bar(sa), pa ^ 1u);
+            const uint32_t slab = base + (uint32_t)sa * a_slot;
             if (elect_one_sync()) {
-              mbar_expect_tx(full_bar(stage), stage_bytes);
-              tma_load_2d(sa, &p.a_map[s], full_bar(stage), cb * TC_BK, m0 + shift);                       // x_hi
-              tma_load_2d(sa + TC_A_BYTES, &p.a_map[s], full_bar(stage), c + cb * TC_BK, m0 + shift);      // x_lo
-              tma_load_2d(sa + 2u * TC_A_BYTES, &p.b_map, full_bar(stage), kb * TC_BK, n0);                // W_hi
-              tma_load_2d(sa + 2u * TC_A_BYTES + b_bytes, &p.b_map, full_bar(stage), kb * TC_BK, p.cout_pad + n0);   // W_lo
+              mbar_expect_tx(afull_bar(sa), a_slot);
+              tma_load_2d(slab, &p.a_map[s], afull_bar(sa), cb * TC_BK, row0);                    // x_hi
+              tma_load_2d(slab + a_half, &p.a_map[s], afull_bar(sa), c + cb * TC_BK, row0);       // x_lo
             }
             __syncwarp();
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            if (++sa == p.sa_stages) { sa = 0; pa ^= 1u; }
+            for (int j = 0; j < per_slab; ++j) {
+              const int tap = p.kx_merge ? g * 3 + j : g;
+              const int kcol = (tap * p.nblk_total + blk) * TC_BK;
+              mbar_wait_ctl(p.spin, wempty_bar(sb), pb ^ 1u);
+              const uint32_t wt = w_base + (uint32_t)sb * w_slot;
+              if (elect_one_sync()) {
+                mbar_expect_tx(wfull_bar(sb), w_slot);
+                tma_load_2d(wt, &p.b_map, wfull_bar(sb), kcol, n0);                               // W_hi
+                tma_load_2d(wt + b_bytes, &p.b_map, wfull_bar(sb), kcol, p.cout_pad + n0);        // W_lo
+              }
+              __syncwarp();
+              if (++sb == p.sb_stages) { sb = 0; pb ^= 1u; }
+            }
           }
         }
       }
@@ -1366,66 +1388,76 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc3_kernel(const __grid_constant
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     const uint32_t idesc = (1u << 4) | p.idesc_ab | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    const int taps = p.taps, num_src = p.num_src, n_stages = p.stages, spin = p.spin, chunk = p.chunk;
-    const uint64_t desc_step = (uint64_t)(stage_bytes >> 4);
-    const uint64_t ahi_base = umma_desc_sw128(base), alo_base = umma_desc_sw128(base + TC_A_BYTES);
-    const uint64_t whi_base = umma_desc_sw128(base + 2u * TC_A_BYTES), wlo_base = umma_desc_sw128(base + 2u * TC_A_BYTES + b_bytes);
-    int stage = 0, mbuf = 0, xbuf = 0;
-    uint32_t phase = 0, mphase = 0, xphase = 0;
+    const int num_src = p.num_src, n_sa = p.sa_stages, n_sb = p.sb_stages, spin = p.spin, chunk = p.chunk, kx_merge = p.kx_merge;
+    const uint64_t a_step = (uint64_t)(a_slot >> 4), w_step = (uint64_t)(w_slot >> 4);
+    const uint64_t ahi_base = umma_desc_sw128(base), alo_base = umma_desc_sw128(base + a_half);
+    const uint64_t whi_base = umma_desc_sw128(w_base), wlo_base = umma_desc_sw128(w_base + b_bytes);
+    int sa = 0, sb = 0, mbuf = 0, xbuf = 0;
+    uint32_t pa = 0, pb = 0, mphase = 0, xphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       mbar_wait_ctl(spin, xempty_bar(xbuf), xphase ^ 1u);
       tc_fence_after();
       const uint32_t dx = tmem_base + 256u + (uint32_t)(xbuf * 128);
       uint32_t acc_m = 0, acc_x = 0;
       int in_chunk = 0, kb = 0;
-      for (int tap = 0; tap < taps; ++tap) {
+      for (int g = 0; g < ngroup_outer; ++g) {
         for (int s = 0; s < num_src; ++s) {
           const int c = p.src_c[s];
           const int nblk = (c + TC_BK - 1) / TC_BK;
-          for (int cb = 0; cb < nblk; ++cb, ++kb) {
+          for (int cb = 0; cb < nblk; ++cb) {
             const int nk = (min(TC_BK, c - cb * TC_BK) + 15) >> 4;
-            if (in_chunk == 0) {                              // a fresh main accumulator
-              mbar_wait_ctl(spin, mempty_bar(mbuf), mphase ^ 1u);
-              tc_fence_after();
-              acc_m = 0;
-            }
-            const uint32_t dm = tmem_base + (uint32_t)(mbuf * 128);
-            mbar_wait_ctl(spin, full_bar(stage), phase);
+            mbar_wait_ctl(spin, afull_bar(sa), pa);
             tc_fence_after();
-            const uint64_t off = (uint64_t)stage * desc_step;
-            const uint64_t ahi = ahi_base + off, alo = alo_base + off, whi = whi_base + off, wlo = wlo_base + off;
-            const bool close_chunk = (in_chunk + 1 == chunk) || (kb + 1 == nkb);
-            if (elect_one_sync()) {
-              if (nk == 4) {                                  // full 64-channel block: branch-free issue
-                tc_mma_bf16(dm, ahi, whi, idesc, acc_m);
-                tc_mma_bf16(dm, ahi + 2, whi + 2, idesc, 1u);
-                tc_mma_bf16(dm, ahi + 4, whi + 4, idesc, 1u);
-                tc_mma_bf16(dm, ahi + 6, whi + 6, idesc, 1u);
-                tc_mma_bf16(dx, alo, whi, idesc, acc_x);
-                tc_mma_bf16(dx, alo + 2, whi + 2, idesc, 1u);
-                tc_mma_bf16(dx, alo + 4, whi + 4, idesc, 1u);
-                tc_mma_bf16(dx, alo + 6, whi + 6, idesc, 1u);
-                tc_mma_bf16(dx, ahi, wlo, idesc, 1u);
-                tc_mma_bf16(dx, ahi + 2, wlo + 2, idesc, 1u);
-                tc_mma_bf16(dx, ahi + 4, wlo + 4, idesc, 1u);
-                tc_mma_bf16(dx, ahi + 6, wlo + 6, idesc, 1u);
-              } else {
-                for (int k = 0; k < nk; ++k) tc_mma_bf16(dm, ahi + (uint64_t)(2 * k), whi + (uint64_t)(2 * k), idesc, acc_m | (uint32_t)k);
-                for (int k = 0; k < nk; ++k) tc_mma_bf16(dx, alo + (uint64_t)(2 * k), whi + (uint64_t)(2 * k), idesc, acc_x | (uint32_t)k);
-                for (int k = 0; k < nk; ++k) tc_mma_bf16(dx, ahi + (uint64_t)(2 * k), wlo + (uint64_t)(2 * k), idesc, 1u);
+            const uint64_t aoff = (uint64_t)sa * a_step;
+            for (int j = 0; j < per_slab; ++j, ++kb) {
+              if (in_chunk == 0) {                            // a fresh main accumulator
+                mbar_wait_ctl(spin, mempty_bar(mbuf), mphase ^ 1u);
+                tc_fence_after();
+                acc_m = 0;
               }
-              tc_commit(empty_bar(stage));
-              if (close_chunk) tc_commit(mfull_bar(mbuf));
+              const uint32_t dm = tmem_base + (uint32_t)(mbuf * 128);
+              mbar_wait_ctl(spin, wfull_bar(sb), pb);
+              tc_fence_after();
+              // tap kx = j reads the slab j rows (128 B = 8 descriptor units each) further down
+              const uint64_t ashift = aoff + (uint64_t)(kx_merge ? 8 * j : 0);
+              const uint64_t ahi = ahi_base + ashift, alo = alo_base + ashift;
+              const uint64_t woff = (uint64_t)sb * w_step;
+              const uint64_t whi = whi_base + woff, wlo = wlo_base + woff;
+              const bool close_chunk = (in_chunk + 1 == chunk) || (kb + 1 == nkb);
+              if (elect_one_sync()) {
+                if (nk == 4) {                                // full 64-channel block: branch-free issue
+                  tc_mma_bf16(dm, ahi, whi, idesc, acc_m);
+                  tc_mma_bf16(dm, ahi + 2, whi + 2, idesc, 1u);
+                  tc_mma_bf16(dm, ahi + 4, whi + 4, idesc, 1u);
+                  tc_mma_bf16(dm, ahi + 6, whi + 6, idesc, 1u);
+                  tc_mma_bf16(dx, alo, whi, idesc, acc_x);
+                  tc_mma_bf16(dx, alo + 2, whi + 2, idesc, 1u);
+                  tc_mma_bf16(dx, alo + 4, whi + 4, idesc, 1u);
+                  tc_mma_bf16(dx, alo + 6, whi + 6, idesc, 1u);
+                  tc_mma_bf16(dx, ahi, wlo, idesc, 1u);
+                  tc_mma_bf16(dx, ahi + 2, wlo + 2, idesc, 1u);
+                  tc_mma_bf16(dx, ahi + 4, wlo + 4, idesc, 1u);
+                  tc_mma_bf16(dx, ahi + 6, wlo + 6, idesc, 1u);
+                } else {
+                  for (int k = 0; k < nk; ++k) tc_mma_bf16(dm, ahi + (uint64_t)(2 * k), whi + (uint64_t)(2 * k), idesc, acc_m | (uint32_t)k);
+                  for (int k = 0; k < nk; ++k) tc_mma_bf16(dx, alo + (uint64_t)(2 * k), whi + (uint64_t)(2 * k), idesc, acc_x | (uint32_t)k);
+                  for (int k = 0; k < nk; ++k) tc_mma_bf16(dx, ahi + (uint64_t)(2 * k), wlo + (uint64_t)(2 * k), idesc, 1u);
+                }
+                tc_commit(wempty_bar(sb));
+                if (j + 1 == per_slab) tc_commit(aempty_bar(sa));
+                if (close_chunk) tc_commit(mfull_bar(mbuf));
+              }
+              __syncwarp();
+              acc_m = 1; acc_x = 1;
+              if (++sb == n_sb) { sb = 0; pb ^= 1u; }
+              if (close_chunk) {
+                in_chunk = 0;
+                if (++mbuf == 2) { mbuf = 0; mphase ^= 1u; }
+              } else {
+                ++in_chunk;
+              }
             }
-            __syncwarp();
-            acc_m = 1; acc_x = 1;
-            if (++stage == n_stages) { stage = 0; phase ^= 1u; }
-            if (close_chunk) {
-              in_chunk = 0;
-              if (++mbuf == 2) { mbuf = 0; mphase ^= 1u; }
-            } else {
-              ++in_chunk;
-            }
+            if (++sa == n_sa) { sa = 0; pa ^= 1u; }
           }
         }
       }
@@ -1793,12 +1825,27 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
       if (waves_trim < waves_full) { p->row_begin = lead; p->m_tiles = t_trim; }
     }
     p->a_box_rows = TC_BM;
-    const uint32_t stage_bytes = (f16 ? 2u : 1u) * (TC_A_BYTES + (uint32_t)p->bn * TC_BK * 2);
-    const size_t tail = f16 ? (size_t)(8 * (2 * 8 + 8) + 48 + 8 * EPI_WARP_BYTES + EPI_SS_BYTES) : tail_v1;
-    int stages = (int)((smem_max - tail) / stage_bytes);
-    p->stages = stages > 8 ? 8 : stages;
-    TC_REQUIRE(p->stages >= 2, "conv_tc: tile does not fit in shared memory");
-    p->smem_bytes = (unsigned)(1024 + (size_t)p->stages * stage_bytes + tail);
+    if (f16) {
+      // separate rings for the {x_hi, x_lo} slabs and the {W_hi, W_lo} tiles.  kx-merge (one 136-row slab per filter row of a
+      // stride-1 3x3) cuts the x traffic 3x but was measured NOT faster (341 vs 350 img/s end to end, profiles/
+      // r2_split_kx_merge.txt): at N = 128 the MMAs themselves read 128 B / clock of shared memory, which is the bound, not
+      // the L2 -> shared-memory fill.  Kept selectable (CM2_TC3_MERGE=1; tests/test_gpu_conv_split.py runs both).
+      const int env_merge = getenv("CM2_TC3_MERGE") ? atoi(getenv("CM2_TC3_MERGE")) : 0;
+      p->kx_merge = (env_merge && p->taps == 9 && !phase) ? 1 : 0;
+      p->a_box_rows = p->kx_merge ? 136 : 128;
+      const size_t a_slot = 2u * (size_t)p->a_box_rows * 128u, w_slot = 2u * (size_t)p->bn * TC_BK * 2;
+      const size_t tail = (size_t)(8 * (2 * 4 + 2 * 8 + 8) + 48 + 8 * EPI_WARP_BYTES + EPI_SS_BYTES);
+      p->sa_stages = p->kx_merge ? 2 : 3;
+      size_t sb = (smem_max - tail - p->sa_stages * a_slot) / w_slot;
+      p->sb_stages = (int)(sb > 8 ? 8 : sb);
+      TC_REQUIRE(p->sb_stages >= 2, "conv_tc: tile does not fit in shared memory");
+      p->smem_bytes = (unsigned)(1024 + p->sa_stages * a_slot + p->sb_stages * w_slot + tail);
+    } else {
+      const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p->bn * TC_BK * 2;
+      int stages = (int)((smem_max - tail_v1) / stage_bytes);
+      p->stages = stages > 8 ? 8 : stages;
+      p->smem_bytes = (unsigned)(1024 + (size_t)p->stages * stage_bytes + tail_v1);
+    }
   }
   p->scale = d->scale; p->shift = d->shift; p->relu = d->relu;
   p->out = d->out.data;

@@ -284,3 +284,27 @@ def test_split_is_made_once_per_pass_and_again_in_the_next(eng):
     c = eng.conv("o3", [x], cw)
     torch.cuda.synchronize()
     assert torch.equal(a.view, b.view) and torch.allclose(c.view, 2.0 * a.view, rtol=1e-5, atol=1e-6)
+
+
+def test_split_conv_kx_merged_slabs_give_the_same_result(eng):
+    """CM2_TC3_MERGE=1: one 136-row {x_hi, x_lo} slab per filter row serves the three kx taps (MMA descriptors start 0 / 1 / 2
+    rows into it); same products, another accumulation order."""
+    import os
+    g = torch.Generator().manual_seed(12)
+    n, c, h, w, cout = 2, 160, 21, 30, 224
+    x = torch.randn(n, c, h, w, generator=g)
+    wt = torch.randn(cout, c, 3, 3, generator=g) / math.sqrt(9 * c)
+    ref = conv_ref([x], wt, None, None, True)
+    cw = packing.ConvW(wt, [c], 1, 1, None, None, True, F32, DEV, True)
+    outs = []
+    for merge in ("0", "1"):
+        os.environ["CM2_TC3_MERGE"] = merge
+        try:
+            eng.begin_pass()
+            o = eng.conv("km" + merge, [halo(x)], cw)
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("CM2_TC3_MERGE", None)
+        check(nchw(o.view), ref, "split 3x3 conv, CM2_TC3_MERGE=" + merge)
+        outs.append(o.view.clone())
+    assert (outs[0] - outs[1]).abs().max().item() <= 2e-6 * ref.abs().max().item()
