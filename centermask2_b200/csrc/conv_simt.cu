@@ -266,12 +266,14 @@ extern "C" int cm2_conv2d(const cm2_conv_desc* d, void* stream) {
   CM2_CHECK_ARG(d->out_mode == 0 || ((d->out_mode == 1 || d->out_mode == 3) && d->cout % 4 == 0) || d->out_mode == 2,
                 "conv2d: bad out_mode");
   CM2_CHECK_ARG(d->weight != nullptr && d->out.data != nullptr, "conv2d: null weight/out");
+  // split-precision output (CM2_F16 out of CM2_F16 sources): [hi | lo] pair, 2 * cout channels
+  const int out_c = (d->dtype == CM2_F16 && d->out_dtype == CM2_F16) ? 2 * d->cout : d->cout;
   if (d->out_mode == 0)
-    CM2_CHECK_ARG(d->out.n == s0.n && d->out.h == ho && d->out.w == wo && d->out.c == d->cout,
+    CM2_CHECK_ARG(d->out.n == s0.n && d->out.h == ho && d->out.w == wo && d->out.c == out_c,
                   "conv2d: out view [%d,%d,%d,%d] != expected [%d,%d,%d,%d]", d->out.n, d->out.h, d->out.w, d->out.c,
                   s0.n, ho, wo, d->cout);
   else if (d->out_mode == 2)
-    CM2_CHECK_ARG(d->out.n == s0.n && d->out.h == (ho + 1) / 2 && d->out.w == (wo + 1) / 2 && d->out.c == d->cout,
+    CM2_CHECK_ARG(d->out.n == s0.n && d->out.h == (ho + 1) / 2 && d->out.w == (wo + 1) / 2 && d->out.c == out_c,
                   "conv2d: phase-split out view [%d,%d,%d,%d] != expected [%d,%d,%d,%d]", d->out.n, d->out.h, d->out.w,
                   d->out.c, s0.n, (ho + 1) / 2, (wo + 1) / 2, d->cout);
   else if (d->out_mode == 3)

@@ -21,6 +21,7 @@
 // Two accumulator stages (2 x 256 TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace cm2 {
@@ -91,6 +92,7 @@ struct alignas(64) TcParams {
   int split;                // 1: conv_tc3_kernel
   int chunk;                // main-accumulator K-blocks between two drains into the fp32 register sums
   int cout_pad;             // W_lo tiles start cout_pad rows below the W_hi tiles in the weight matrix
+  int split_out;            // 1: the output is the [hi | lo] f16 pair of 2 * cout channels (epilogue kind 11)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -574,7 +576,10 @@ __device__ __forceinline__ int tc_fast_div(int n, int d, double rcp) {          
   return q;
 }
 
-template <bool F32, bool RES, int STATS, bool DECONV>
+// SPLIT (fp32 engine): the fp32 result is stored as the [hi | lo] f16 operand pair of the next convolution -- f16 output
+// tensor of 2 * cout channels, hi = half(v) at channel co, lo = half(v - hi) at cout + co (include/cm2.h "Split precision") --
+// so no fp32 copy is written and no separate split pass reads it back.  Two staged store rounds per 32-channel pass.
+template <bool F32, bool RES, int STATS, bool DECONV, bool SPLIT = false>
 __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const TileGeom& g, uint32_t taddr, int m, int n0,
                                                         uint32_t stage_smem, int lane, uint32_t ss_smem, int cset, int ncset) {
   constexpr int esize_res = F32 ? 4 : 2;             // the residual has the output's element type
@@ -700,6 +705,39 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
       for (int j = 0; j < 4; ++j)
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + 16u * j), "f"(v[4 * j]), "f"(v[4 * j + 1]),
                      "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+    } else if (SPLIT) {
+      uint32_t whi[16], wlo[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a0 = fmaxf(v[2 * i], relu_floor), a1 = fmaxf(v[2 * i + 1], relu_floor);
+        const __half2 h = __floats2half2_rn(a0, a1);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+        whi[i] = interior ? *reinterpret_cast<const uint32_t*>(&h) : 0u;
+        wlo[i] = interior ? *reinterpret_cast<const uint32_t*>(&l) : 0u;
+      }
+      const int valid_pieces_s = min(4, (min(p.bn - c0, p.cout - co0) + 7) / 8);
+      const bool piece_ok_s = (lane & 3) < valid_pieces_s;
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {      // hi, then lo
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t* w = part ? wlo : whi;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + 16u * j), "r"(w[4 * j]), "r"(w[4 * j + 1]),
+                       "r"(w[4 * j + 2]), "r"(w[4 * j + 3]) : "memory");
+        }
+        __syncwarp();
+        const long long col_bytes_s = (long long)(co0 + (part ? p.cout : 0)) * 2;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          uint4 val;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                       : "r"(wsm[it]) : "memory");
+          if (wok[it] && piece_ok_s) *reinterpret_cast<uint4*>(wptr[it] + col_bytes_s) = val;
+        }
+        __syncwarp();
+      }
+      continue;
     } else {
       const __nv_bfloat162 floor2 = __floats2bfloat162_rn(relu_floor, relu_floor);
       uint32_t w[16];
@@ -804,7 +842,8 @@ __device__ __forceinline__ void tc_epilogue_deconv_predict(const TcParams& p, co
 }
 
 // kind: 0 plain bf16, 1 bf16 + channel sums, 2 bf16 + GroupNorm sums, 3 bf16 + residual, 4 f32, 5 bf16 deconv scatter,
-//       6 fused deconv + predictor, 7 f32 + channel sums, 8 f32 + GroupNorm sums, 9 f32 + f32 residual, 10 f32 deconv scatter
+//       6 fused deconv + predictor, 7 f32 + channel sums, 8 f32 + GroupNorm sums, 9 f32 + f32 residual, 10 f32 deconv scatter,
+//       11 split f16 [hi | lo] output
 __device__ __forceinline__ void tc_epilogue_dispatch(const TcParams& p, const TileGeom& g, uint32_t taddr, int m, int n0,
                                                      uint32_t stage_smem, int lane, uint32_t ss_smem, int cset, int ncset) {
   if (p.epi_kind == 6) {
@@ -821,6 +860,7 @@ __device__ __forceinline__ void tc_epilogue_dispatch(const TcParams& p, const Ti
     case 8: tc_epilogue_rows_staged<true, false, 2, false>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
     case 9: tc_epilogue_rows_staged<true, true, 0, false>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
     case 10: tc_epilogue_rows_staged<true, false, 0, true>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
+    case 11: tc_epilogue_rows_staged<false, false, 0, false, true>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
     default: tc_epilogue_rows_staged<false, false, 0, true>(p, g, taddr, m, n0, stage_smem, lane, ss_smem, cset, ncset); break;
   }
 }
@@ -1476,8 +1516,11 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc3_kernel(const __grid_constant
       const uint32_t ss = ss_base + (p.n_tiles == 1 ? 0u : parity * 2048u);
       if (p.n_tiles > 1 || t == (int)blockIdx.x)
         tc_stage_scale_shift(p, ss, n0, (int)threadIdx.x - 64, 32 * n_epi_warps, m0);
-      // this warp sums the 16-column groups g = cset, cset + 2, ... of its 32 rows -- the same groups its staged epilogue
-      // pass handles for an fp32 output, so it later reads back only what it wrote itself
+      // this warp sums four 16-column groups of its 32 rows -- the groups its own staged epilogue passes read back (16
+      // columns per pass for an fp32 output: g = cset, cset + 2, ..; 32 per pass for the split f16 output: g = 2 cset,
+      // 2 cset + 1, 2 cset + 4, ..), so it later reads only what it wrote itself
+      const int so = p.split_out;
+      auto group_col = [&](int j) { return 16 * (so ? ((j >> 1) * 4 + cset * 2 + (j & 1)) : (cset + 2 * j)); };
       float run[4][16];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -1489,7 +1532,7 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc3_kernel(const __grid_constant
         const uint32_t ta = tmem_base + (uint32_t)(mbuf * 128) + lane_off;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int c0 = 16 * (cset + 2 * j);
+          const int c0 = group_col(j);
           if (c0 < p.bn) {                                  // warp-uniform
             uint32_t raw[16];
             __syncwarp();
@@ -1509,7 +1552,7 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc3_kernel(const __grid_constant
       const uint32_t tx = tmem_base + 256u + (uint32_t)(xbuf * 128) + lane_off;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int c0 = 16 * (cset + 2 * j);
+        const int c0 = group_col(j);
         if (c0 < p.bn) {
           uint32_t raw[16];
           __syncwarp();
@@ -1622,8 +1665,13 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   if (!device_is_sm100()) { set_error("conv_tc: device is not sm_100"); return CM2_ERR_UNSUPPORTED; }
 #define TC_REQUIRE(cond, ...) do { if (!(cond)) { set_error(__VA_ARGS__); return CM2_ERR_UNSUPPORTED; } } while (0)
   const bool f16 = d->dtype == CM2_F16;
-  TC_REQUIRE((d->dtype == CM2_BF16 && (d->out_dtype == CM2_BF16 || d->out_dtype == CM2_F32)) || (f16 && d->out_dtype == CM2_F32),
-             "conv_tc: needs bf16 sources (bf16 / f32 output) or f16 sources (f32 output)");
+  TC_REQUIRE((d->dtype == CM2_BF16 && (d->out_dtype == CM2_BF16 || d->out_dtype == CM2_F32)) ||
+                 (f16 && (d->out_dtype == CM2_F32 || d->out_dtype == CM2_F16)),
+             "conv_tc: needs bf16 sources (bf16 / f32 output) or f16 split sources (f32 or split f16 output)");
+  const bool split_out = f16 && d->out_dtype == CM2_F16;
+  if (split_out)
+    TC_REQUIRE(!d->residual.data && !d->stats && (d->out_mode == 0 || d->out_mode == 2) && d->cout % 16 == 0,
+               "conv_tc: the split f16 output takes out_mode 0 / 2 without residual or statistics, cout %% 16 == 0");
   TC_REQUIRE(!(f16 && d->out_mode == 3), "conv_tc: the fused deconv + predictor epilogue is bf16 only");
   const bool phase = d->src_phase != 0;
   if (phase)
@@ -1880,6 +1928,11 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   if (p->res_mode && (p->out_f32 != 0) != (p->res_f32 != 0)) p->fast_store = 0;
   if (p->out_f32) p->epi_kind = p->res_mode ? 9 : (d->out_mode == 1 ? 10 : 4);
   else p->epi_kind = p->res_mode ? 3 : (d->out_mode == 1 ? 5 : 0);
+  if (split_out) {
+    TC_REQUIRE(p->fast_store, "conv_tc: the split f16 output needs vectorisable output strides");
+    p->split_out = 1;
+    p->epi_kind = 11;
+  }
   if (pred) {
     p->fast_store = 1;                                 // dispatcher path; nothing is staged
     p->epi_kind = 6;

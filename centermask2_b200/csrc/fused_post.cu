@@ -5,6 +5,7 @@
 //     MaxPool2d(3, 2, ceil_mode=True) that opens the next stage (vovnet.py:349-350) -- the stage output is read once.
 // All HBM-bound: 16-byte channel vectors, 32-bit index arithmetic, a few rows per thread.
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include <string.h>
 #include <algorithm>
 
@@ -211,6 +212,68 @@ __global__ void __launch_bounds__(256) gn_seg_apply_lines_kernel(__nv_bfloat16* 
         o[j] = relu ? pack_bf16x2_relu(v0, v1) : pack_bf16x2(v0, v1);
       }
       base[(size_t)(px + u * pstep) * c8] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// fp32 engine: GroupNorm normalise + ReLU of an fp32 segmented tensor written straight into the [hi | lo] f16 operand form
+// of the next convolution (include/cm2.h "Split precision"): the separate cm2_split_f16x2 pass over the tower tensor
+// disappears.  One CTA per image line; a thread owns 8 channels of a pixel: 32 bytes in, 16 + 16 bytes out.  Only
+// interior pixels are written: the halo of the (zero-initialised) output stays zero.
+__global__ void __launch_bounds__(256) gn_seg_apply_split_lines_kernel(const float* __restrict__ x, __half* __restrict__ out, int c, int cpg,
+                                                                       GnLineSegs g, const double* __restrict__ stats,
+                                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                       float eps, int relu) {
+  const int line = blockIdx.x;
+  int s = 0;
+#pragma unroll
+  for (int j = 1; j < CM2_MAX_SEG; ++j)
+    if (j < g.num && line >= g.line_prefix[j]) s = j;
+  const int l = line - g.line_prefix[s];
+  const int img = l / g.h[s], y = l - img * g.h[s];
+  const int c8 = c >> 3;
+  const int w = g.w[s];
+  for (int cv = threadIdx.x % min(c8, (int)blockDim.x); cv < c8; cv += blockDim.x) {      // c8 <= 256: one pass for c <= 2048
+    float a[8], b[8];
+    {
+      const int gi = g.img0[s] + img;
+      const int chunks_per_group = cpg >> 3;
+      const int grp = (cv * 8) / cpg;
+      const double* q = stats + ((size_t)gi * c8 + (size_t)grp * chunks_per_group) * 2;
+      double sum = 0.0, sq = 0.0;
+      for (int j = 0; j < chunks_per_group; ++j) { sum += q[2 * j]; sq += q[2 * j + 1]; }
+      const double cnt = (double)g.h[s] * (double)w * (double)cpg;
+      const double m = sum / cnt;
+      double var = sq / cnt - m * m;
+      if (var < 0.0) var = 0.0;
+      const float mean = (float)m, rstd = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gm = __ldg(gamma + cv * 8 + j);
+        a[j] = rstd * gm;
+        b[j] = __ldg(beta + cv * 8 + j) - mean * rstd * gm;
+      }
+    }
+    const size_t row_first = (size_t)g.row0[s] + (size_t)img * g.plane[s] + (size_t)(y + 1) * g.pitch[s] + 1;
+    const int pstep = max(1, (int)blockDim.x / c8), p0 = threadIdx.x / c8;
+    for (int px = p0; px < w; px += pstep) {
+      const float4* src = reinterpret_cast<const float4*>(x + (row_first + px) * c + cv * 8);
+      const float4 u0 = __ldg(src), u1 = __ldg(src + 1);
+      float v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float r0 = fmaf(v[2 * j], a[2 * j], b[2 * j]), r1 = fmaf(v[2 * j + 1], a[2 * j + 1], b[2 * j + 1]);
+        if (relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); }
+        const __half2 h = __floats2half2_rn(r0, r1);
+        const float2 hf = __half22float2(h);
+        const __half2 lw = __floats2half2_rn(r0 - hf.x, r1 - hf.y);
+        hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[j] = *reinterpret_cast<const uint32_t*>(&lw);
+      }
+      __half* o = out + (row_first + px) * (size_t)(2 * c) + cv * 8;
+      *reinterpret_cast<uint4*>(o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(o + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
   }
 }
@@ -493,6 +556,35 @@ extern "C" int cm2_groupnorm_apply_seg(void* x, int32_t dtype, int32_t c, int32_
     gn_seg_apply_stats_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((__nv_bfloat16*)x, c, c / groups, g, total_rows, stats, gamma,
                                                                   beta, eps, relu);
   CM2_CHECK_LAUNCH("gn_seg_apply_stats");
+  return CM2_OK;
+}
+
+extern "C" int cm2_groupnorm_apply_seg_split(const float* x, void* out_split, int32_t c, int32_t num_seg, const cm2_seg* seg,
+                                             int32_t groups, const float* gamma, const float* beta, float eps, int32_t relu,
+                                             const double* stats, void* stream) {
+  CM2_CHECK_ARG(x && out_split && seg && gamma && beta && stats, "groupnorm_apply_seg_split: null pointer");
+  CM2_CHECK_ARG(groups > 0 && c % groups == 0 && c % 8 == 0 && (c / groups) % 8 == 0 && c / 8 <= 256 && 256 % (c / 8) == 0 &&
+                (reinterpret_cast<uintptr_t>(x) & 31) == 0 && (reinterpret_cast<uintptr_t>(out_split) & 15) == 0,
+                "groupnorm_apply_seg_split: unsupported c=%d groups=%d", c, groups);
+  CM2_CHECK_ARG(num_seg >= 1 && num_seg <= CM2_MAX_SEG, "groupnorm_apply_seg_split: bad segment count %d", num_seg);
+  GnLineSegs gl;
+  memset(&gl, 0, sizeof(gl));
+  gl.num = num_seg;
+  long long end = 0;
+  int img0 = 0;
+  for (int i = 0; i < num_seg; ++i) {
+    CM2_CHECK_ARG(seg[i].n > 0 && seg[i].h > 0 && seg[i].w > 0 && seg[i].row0 >= end, "groupnorm_apply_seg_split: bad segment %d", i);
+    const long long rows = (long long)seg[i].n * (seg[i].h + 2) * (seg[i].w + 2);
+    CM2_CHECK_ARG(seg[i].row0 + rows < (1ll << 31) - 4096, "groupnorm_apply_seg_split: segment %d out of range", i);
+    gl.row0[i] = (int)seg[i].row0; gl.pitch[i] = seg[i].w + 2; gl.plane[i] = (seg[i].h + 2) * (seg[i].w + 2);
+    gl.h[i] = seg[i].h; gl.w[i] = seg[i].w; gl.img0[i] = img0;
+    gl.line_prefix[i + 1] = gl.line_prefix[i] + seg[i].n * seg[i].h;
+    img0 += seg[i].n;
+    end = seg[i].row0 + rows;
+  }
+  gn_seg_apply_split_lines_kernel<<<gl.line_prefix[num_seg], 256, 0, (cudaStream_t)stream>>>(
+      x, reinterpret_cast<__half*>(out_split), c, c / groups, gl, stats, gamma, beta, eps, relu);
+  CM2_CHECK_LAUNCH("gn_seg_apply_split_lines");
   return CM2_OK;
 }
 

@@ -88,6 +88,28 @@ class PhaseMap(object):
         return self.buf.shape[4]
 
 
+class SplitFMap(FMap):
+    """fp32 engine: a feature map that exists only as the [hi | lo] f16 operand pair of the convolutions that read it
+    (``buf[n, h+2, w+2, 2c]``; include/cm2.h "Split precision"): written by a convolution epilogue or the GroupNorm apply,
+    never materialised in fp32.  ``c`` is the logical channel count."""
+
+    __slots__ = ()
+
+    @property
+    def c(self):
+        return self.buf.shape[3] // 2
+
+
+class SplitPhaseMap(PhaseMap):
+    """The same for a feature map stored as four stride-2 phase planes."""
+
+    __slots__ = ()
+
+    @property
+    def c(self):
+        return self.buf.shape[4] // 2
+
+
 class SegMap(object):
     """Several halo feature maps of different extent stored back to back in one flat ``[rows, c]`` buffer
     (``include/cm2.h``: ``cm2_seg``).  Used for the FPN levels the shared-weight FCOS towers run on, so that one
@@ -109,10 +131,13 @@ class SegMap(object):
         row0, n, h, w = self.segs[i]
         return FMap(self.flat[row0:row0 + n * (h + 2) * (w + 2)].view(n, h + 2, w + 2, self.c), 1)
 
-    def like(self, c, dtype, alloc):
+    is_split = False                                   # True: ``flat`` is the [hi | lo] f16 operand form [rows, 2c]
+
+    def like(self, c, dtype, alloc, split=False):
         out = SegMap.__new__(SegMap)
         out.segs, out.rows, out.c = self.segs, self.rows, c
-        out.flat = alloc((self.rows, c))
+        out.flat = alloc((self.rows, 2 * c if split else c))
+        out.is_split = split
         return out
 
 
@@ -140,6 +165,7 @@ class Engine(object):
         # operands ("fp32": three MMAs per product term, fp32-grade accuracy); "fp32_simt" keeps everything on CUDA cores
         self.tc = precision in ("bf16", "fp32")
         self.split = precision == "fp32"
+        self.split_out_all = os.environ.get("CM2_SPLIT_OUT_ALL") == "1"       # [hi | lo] epilogue store on every eligible layer (tests)
         self._split_cache = {}
         self.device = torch.device(device)
         self._bufs = collections.OrderedDict()              # least recently used first
@@ -277,9 +303,11 @@ class Engine(object):
 
     # -- one convolution -------------------------------------------------------------------------
     def conv(self, name, srcs, w, out_dtype=None, residual=None, res_mode=0, out_mode=0, in_relu=False,
-             out_halo=1, stats=None, stats_mode=0, out=None, pred=None):
+             out_halo=1, stats=None, stats_mode=0, out=None, pred=None, to_conv=False):
         """One convolution.  ``srcs`` are FMaps (virtual concat) or, for a stride-2 conv on the TC engine,
-        PhaseMaps.  ``out_mode`` 1 = deconv scatter, 2 = write the result as a PhaseMap."""
+        PhaseMaps.  ``out_mode`` 1 = deconv scatter, 2 = write the result as a PhaseMap.  ``to_conv=True`` promises that
+        only convolutions read the result: the fp32 engine then stores it directly as their [hi | lo] f16 operands
+        (a ``SplitFMap`` / ``SplitPhaseMap``; no fp32 copy, no split pass); the other engines ignore the hint."""
         x0 = srcs[0]
         src_phase = isinstance(x0, PhaseMap)
         if src_phase:
@@ -287,6 +315,17 @@ class Engine(object):
         else:
             ho = (x0.h + 2 * w.pad - w.k) // w.stride + 1
             wo = (x0.w + 2 * w.pad - w.k) // w.stride + 1
+        # measured per layer (profiles/r2_layers_v39_fp32*.txt): the [hi | lo] store pays where one N tile covers the layer
+        # (cout <= 128: stem_2 -> stem_3, OSA2 3x3 +10 %); with two N tiles per row block (OSA3/4, the ROI heads) the longer
+        # epilogue delays the accumulator drains of the next tile by as much as the saved split pass took
+        split_out = (to_conv and self.split and w.split and out is None and out_mode in (0, 2) and residual is None and stats is None
+                     and w.cout % 16 == 0 and (w.cout <= 128 or self.split_out_all) and not in_relu and out_halo in (0, 1)
+                     and all(s.c % 16 == 0 for s in srcs))
+        if split_out:
+            if out_mode == 0:
+                out = SplitFMap(self.buffer(name, (x0.n, ho + 2 * out_halo, wo + 2 * out_halo, 2 * w.cout), torch.float16), out_halo)
+            else:
+                out = SplitPhaseMap(self.buffer(name, (4, x0.n, (ho + 1) // 2 + 2, (wo + 1) // 2 + 2, 2 * w.cout), torch.float16))
         if out is None:
             if out_mode == 0:
                 out = self.fmap(name, x0.n, ho, wo, w.cout, out_dtype, out_halo)
@@ -294,23 +333,25 @@ class Engine(object):
                 out = self.fmap(name, x0.n, 2 * ho, 2 * wo, w.cout // 4, out_dtype, out_halo)
             else:
                 out = self.phasemap(name, x0.n, ho, wo, w.cout)
+        presplit = [isinstance(s, (SplitFMap, SplitPhaseMap)) for s in srcs]
         views = [s.view for s in srcs]
-        for v, c in zip(views, w.src_c):
-            assert v.shape[3] == c, (name, v.shape, w.src_c)
+        for s_, c in zip(srcs, w.src_c):
+            assert s_.c == c, (name, s_.c, w.src_c)
         kw = dict(shift=w.shift, relu=w.relu, in_relu=in_relu, src_phase=src_phase,
                   residual=None if residual is None else residual.view, res_mode=res_mode, out_mode=out_mode)
         if self.tc and w.w_tc is not None:
             tc_views = views
             if w.split:
                 # split precision: fp32 activations -> [hi | lo] f16 tensors (cm2_split_f16x2), one per source
-                if in_relu or any(s.c % 16 for s in srcs) or out.view.dtype != torch.float32:
+                if in_relu or any(s.c % 16 for s in srcs) or not (split_out or out.view.dtype == torch.float32):
                     tc_views = None
                 else:
-                    tc_views = [self.split_of(s).view for s in srcs]
+                    tc_views = [s.view if pre else self.split_of(s).view for s, pre in zip(srcs, presplit)]
             if tc_views is not None and lib.conv2d(tc_views, w.w_tc, out.view, w.cout, w.k, w.stride, w.pad, scale=w.scale_tc,
                                                    engine=lib.ENGINE_TC, stats=stats, stats_mode=stats_mode, probe=True, pred=pred, **kw):
                 return out
         assert stats is None and pred is None, "fused epilogues require the tensor-core engine: " + lib.last_error()
+        assert not split_out and not any(presplit), "split-precision operands require the tensor-core engine: " + lib.last_error()
         lib.conv2d(views, w.w_simt, out.view, w.cout, w.k, w.stride, w.pad, scale=w.scale, engine=lib.ENGINE_SIMT, **kw)
         return out
 
@@ -352,7 +393,7 @@ class Engine(object):
         cout_pad = (w.cout + 15) // 16 * 16
         assert cout_pad == w.cout, "segmented conv needs cout % 16 == 0"
         out = x.like(w.cout, dt, lambda shape: self.buffer(name, shape, dt))
-        srcs = [self.split_of(x.flat)] if w.split else [x.flat]
+        srcs = [x.flat if getattr(x, "is_split", False) else self.split_of(x.flat)] if w.split else [x.flat]
         lib.conv2d(srcs, w.w_tc, out.flat, w.cout, w.k, w.stride, w.pad, scale=w.scale_tc, shift=w.shift, relu=w.relu,
                    engine=lib.ENGINE_TC, segs=x.segs, stats=stats, stats_mode=stats_mode)
         return out
@@ -437,7 +478,7 @@ class Engine(object):
                 x = self.dw_unit("stem{}".format(i + 1), x, w9c, pw, stride)
         elif self.tc:
             # tensor-core path: stem_2 writes phase planes, stem_3 (stride 2) reads them
-            x = self.conv("stem2", [x], P["stem"][1], out_mode=2)
+            x = self.conv("stem2", [x], P["stem"][1], out_mode=2, to_conv=True)
             x = self.conv("stem3", [x], P["stem"][2])
         else:
             for i in (1, 2):
@@ -467,7 +508,7 @@ class Engine(object):
                 if b.dw:
                     y = self.dw_unit("{}_{}".format(b.name, i), y, w[0], w[1], 1)
                 else:
-                    y = self.conv("{}_{}".format(b.name, i), [y], w)
+                    y = self.conv("{}_{}".format(b.name, i), [y], w, to_conv=True)     # read by the next 3x3 and the aggregation
                 feats.append(y)
             n, c = x.n, cat.cout
             gate = self.buffer(b.name + "_gate", (n, c), torch.float32, zero=False)
@@ -621,7 +662,14 @@ class Engine(object):
                     # GroupNorm statistics come out of the conv epilogue (fp64 sums per image and 8-channel chunk)
                     st = self.buffer("fcos_gnstats_seg_" + tag, (n_img, conv.cout // 8, 2), torch.float64, zero=False)
                     x = self.conv_seg("fcos_{}{}_seg".format(tag, i), x, conv, stats=st, stats_mode=2)
-                    lib.groupnorm_apply_seg(x.flat, x.segs, 32, gn[0], gn[1], 1e-5, True, st)
+                    if self.split and conv.cout // 8 <= 256 and 256 % (conv.cout // 8) == 0:
+                        # every tower output feeds convolutions only: normalise straight into their [hi | lo] operands
+                        nm = "fcos_{}{}_seg_split".format(tag, i)
+                        sp = x.like(conv.cout, torch.float16, lambda shape: self.buffer(nm, shape, torch.float16), split=True)
+                        lib.groupnorm_apply_seg_split(x.flat, sp.flat, x.segs, 32, gn[0], gn[1], 1e-5, True, st)
+                        x = sp
+                    else:
+                        lib.groupnorm_apply_seg(x.flat, x.segs, 32, gn[0], gn[1], 1e-5, True, st)
                     continue
                 x = self.conv_seg("fcos_{}{}_seg".format(tag, i), x, conv)
                 if gn is not None:
@@ -776,10 +824,13 @@ class Engine(object):
             srcs = [roi, pm] if k == 0 else [y]
             # the last conv is stride 2: on the TC engine its producer stores phase planes
             to_phase = self.tc and k + 2 == nconv and k > 0
-            y = self.conv("iou_fcn{}".format(k + 1), srcs, w, out_halo=0 if last else 1, out_mode=2 if to_phase else 0)
+            # the stride-2 conv reads phase planes on the TC engine; when its producer cannot write them (k == 0: the concat
+            # input) it runs on the CUDA-core engine, which needs the fp32 map
+            y = self.conv("iou_fcn{}".format(k + 1), srcs, w, out_halo=0 if last else 1, out_mode=2 if to_phase else 0,
+                          to_conv=not last and (to_phase or k + 2 < nconv))
         flat = FMap(y.buf.reshape(R, 1, 1, -1), 0)
-        y = self.conv("iou_fc1", [flat], P["iou_fc1"], out_halo=0)
-        y = self.conv("iou_fc2", [y], P["iou_fc2"], out_halo=0)
+        y = self.conv("iou_fc1", [flat], P["iou_fc1"], out_halo=0, to_conv=True)
+        y = self.conv("iou_fc2", [y], P["iou_fc2"], out_halo=0, to_conv=True)
         return self.conv("iou_out", [y], P["iou_out"], out_dtype=torch.float32, out_halo=0)
 
     def image_area(self, image_sizes):
@@ -804,7 +855,7 @@ class Engine(object):
                          workspace=self.buffer("roi_order", (max(R, 1),), torch.int32, False))
         x = roi
         for k, w in enumerate(P["mask_fcn"]):
-            x = self.conv("mask_fcn{}".format(k + 1), [x], w)
+            x = self.conv("mask_fcn{}".format(k + 1), [x], w, to_conv=k + 1 < len(P["mask_fcn"]))   # the last one feeds the SAM
         att = self.fmap("mask_att", R, res, res, x.c)
         lib.spatial_attention(x.view, att.view, P["sam_w"])
         probs = self.buffer("mask_probs", (R, 1, 2 * res, 2 * res), torch.float32, False)

@@ -85,6 +85,7 @@ SYMBOLS = {
     "cm2_gn_seg_workspace_floats": (_L, [_I, C.POINTER(Seg), _I, _I]),
     "cm2_groupnorm_relu_seg": (_I, [_P, _I, _I, _I, C.POINTER(Seg), _I, _P, _P, _F, _I, _P, _P]),
     "cm2_groupnorm_apply_seg": (_I, [_P, _I, _I, _I, C.POINTER(Seg), _I, _P, _P, _F, _I, _P, _P]),
+    "cm2_groupnorm_apply_seg_split": (_I, [_P, _P, _I, _I, C.POINTER(Seg), _I, _P, _P, _F, _I, _P, _P]),
     "cm2_ese_gate_f64": (_I, [_P, C.c_double, _P, _P, _P, _I, _I, _P]),
     "cm2_ese_apply_pool": (_I, [_AP, _P, _AP, _AP, _AP, _I, _P]),
     "cm2_relu": (_I, [_AP, _AP, _I, _P]),
@@ -358,6 +359,15 @@ def groupnorm_apply_seg(flat, segs, groups, gamma, beta, eps, relu, stats):
     check(load().cm2_groupnorm_apply_seg(ptr(flat), dtype_code(flat), flat.shape[1], len(segs), seg_array(segs), groups,
                                          ptr(gamma), ptr(beta), eps, int(relu), ptr(stats), stream()),
           "cm2_groupnorm_apply_seg")
+    _count()
+
+
+def groupnorm_apply_seg_split(flat, out_split, segs, groups, gamma, beta, eps, relu, stats):
+    """fp32 segmented tensor -> GroupNorm + ReLU written as the [hi | lo] f16 operand tensor [rows, 2c] of the next conv."""
+    assert flat.dtype == torch.float32 and out_split.dtype == torch.float16 and out_split.shape[1] == 2 * flat.shape[1]
+    check(load().cm2_groupnorm_apply_seg_split(ptr(flat), ptr(out_split), flat.shape[1], len(segs), seg_array(segs), groups,
+                                               ptr(gamma), ptr(beta), eps, int(relu), ptr(stats), stream()),
+          "cm2_groupnorm_apply_seg_split")
     _count()
 
 

@@ -104,7 +104,9 @@ int cm2_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * dropped x_lo*W_lo term is 2^-22 relative -- and, because tcgen05.mma adds into its accumulator with
  * truncation, sums the dominant x_hi*W_hi term in short chunks that are added in fp32 registers with
  * round-to-nearest (csrc/conv_tc.cu, conv_tc3_kernel).  Output and residual are CM2_F32; out_mode 3 is not
- * available.
+ * available.  out_dtype CM2_F16 (out_mode 0 / 2, no residual, no statistics): the result is stored directly as the
+ * [hi | lo] pair of the NEXT convolution -- out.c = 2*cout, hi at channel co, lo at cout + co -- so a chain of
+ * convolutions needs no fp32 copy and no cm2_split_f16x2 pass in between.
  * ------------------------------------------------------------------------------------------- */
 typedef struct cm2_conv_desc {
   int32_t dtype;     /* CM2_F32 | CM2_BF16: sources, weights, residual; CM2_F16 (TC engine): f16 sources
@@ -244,6 +246,12 @@ int cm2_groupnorm_relu_seg(void* x, int32_t dtype, int32_t c, int32_t num_seg, c
 int cm2_groupnorm_apply_seg(void* x, int32_t dtype, int32_t c, int32_t num_seg, const cm2_seg* seg, int32_t groups,
                             const float* gamma, const float* beta, float eps, int32_t relu, const double* stats,
                             void* stream);
+/* fp32 engine: cm2_groupnorm_apply_seg reading the fp32 convolution output `x` and writing normalise + ReLU straight into
+ * the [hi | lo] f16 operand tensor of the next convolution (out_split: f16 [rows][2c], same segment table, zero-initialised
+ * by the caller: only interior pixels are written) -- see "Split precision" above. */
+int cm2_groupnorm_apply_seg_split(const float* x, void* out_split, int32_t c, int32_t num_seg, const cm2_seg* seg,
+                                  int32_t groups, const float* gamma, const float* beta, float eps, int32_t relu,
+                                  const double* stats, void* stream);
 
 /* Elementwise ReLU copy (P7 input when the conv engine cannot apply in_relu). */
 int cm2_relu(const cm2_act* in, const cm2_act* out, int32_t dtype, void* stream);

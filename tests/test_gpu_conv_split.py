@@ -308,3 +308,86 @@ def test_split_conv_kx_merged_slabs_give_the_same_result(eng):
         check(nchw(o.view), ref, "split 3x3 conv, CM2_TC3_MERGE=" + merge)
         outs.append(o.view.clone())
     assert (outs[0] - outs[1]).abs().max().item() <= 2e-6 * ref.abs().max().item()
+
+
+def test_split_output_feeds_the_next_convolution_without_an_fp32_copy(eng):
+    """``to_conv=True``: the epilogue stores the [hi | lo] f16 operand pair of the next convolution directly (epilogue kind
+    11) -- 3x3 chain on halo maps, the stride-2 chain on phase planes, and dense linear layers."""
+    from centermask2_b200.engine import SplitFMap, SplitPhaseMap
+    eng.split_out_all = True                                 # the engine itself uses the store for cout <= 128 only (measured)
+    g = torch.Generator().manual_seed(21)
+    n, c, h, w = 2, 160, 19, 26
+    x = torch.randn(n, c, h, w, generator=g)
+    w1 = torch.randn(c, c, 3, 3, generator=g) / math.sqrt(9 * c)
+    w2 = torch.randn(224, 2 * c, 1, 1, generator=g) / math.sqrt(2 * c)
+    sc, sh = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    c1 = packing.ConvW(w1, [c], 1, 1, sc, sh, True, F32, DEV, True)
+    c2 = packing.ConvW(w2, [c, c], 1, 0, None, None, False, F32, DEV, True)
+    mid = conv_ref([x], w1, sc, sh, True)
+    ref = conv_ref([x, mid.float()], w2, None, None, False)
+    eng.begin_pass()
+    xin = halo(x)
+    c0 = lib.launch_count
+    y = eng.conv("so1", [xin], c1, to_conv=True)
+    assert isinstance(y, SplitFMap) and y.buf.dtype == torch.float16 and y.c == c and y.buf.shape[3] == 2 * c
+    out = eng.conv("so2", [xin, y], c2)                     # virtual concat of an fp32 map and a split map
+    torch.cuda.synchronize()
+    assert lib.launch_count - c0 == 3                        # one split (x), two convolutions: none for y
+    hi, lo = y.view[..., :c].float(), y.view[..., c:].float()
+    check((hi + lo).permute(0, 3, 1, 2).double().cpu(), mid, "split output hi + lo", tol=1e-6)
+    b = y.buf.float()
+    assert b[:, 0].abs().max() == 0 and b[:, -1].abs().max() == 0 and b[:, :, 0].abs().max() == 0 and b[:, :, -1].abs().max() == 0
+    check(nchw(out.view), ref, "conv over [fp32 map, split map]", tol=3e-6)
+    # stride-2 chain: split phase planes
+    w3 = torch.randn(128, c, 3, 3, generator=g) / math.sqrt(9 * c)
+    c3 = packing.ConvW(w3, [c], 2, 1, None, None, False, F32, DEV, True)
+    ref3 = conv_ref([mid.float()], w3, None, None, False, stride=2, pad=1)
+    eng.begin_pass()
+    pm = eng.conv("so3", [xin], c1, out_mode=2, to_conv=True)
+    assert isinstance(pm, SplitPhaseMap)
+    o3 = eng.conv("so4", [pm], c3, out_halo=0)
+    torch.cuda.synchronize()
+    check(nchw(o3.view), ref3, "stride-2 conv on split phase planes", tol=3e-6)
+    # dense rows (linear layers)
+    r, k1, k2 = 70, 512, 256
+    xl = torch.randn(r, k1, generator=g)
+    wl1, wl2 = torch.randn(k2, k1, generator=g) / math.sqrt(k1), torch.randn(80, k2, generator=g) / math.sqrt(k2)
+    bl1 = torch.randn(k2, generator=g) * 0.1
+    l1 = packing.linear({"l.weight": wl1, "l.bias": bl1}, "l", True, F32, DEV, True)
+    l2 = packing.linear({"l.weight": wl2, "l.bias": torch.zeros(80)}, "l", False, F32, DEV, True)
+    refl = F.linear(F.relu(F.linear(xl.double(), wl1.double(), bl1.double())), wl2.double())
+    eng.begin_pass()
+    a = eng.conv("sl1", [FMap(xl.to(DEV).reshape(r, 1, 1, k1).contiguous(), 0)], l1, out_halo=0, to_conv=True)
+    assert isinstance(a, SplitFMap) and a.halo == 0
+    o = eng.conv("sl2", [a], l2, out_halo=0)
+    torch.cuda.synchronize()
+    check(o.view.reshape(r, 80).double().cpu(), refl, "linear chain through a split map", tol=3e-6)
+
+
+def test_groupnorm_apply_writes_split_operands(eng):
+    """cm2_groupnorm_apply_seg_split: normalise + ReLU of the fp32 tower tensor straight into [hi | lo] f16 (== the in-place
+    fp32 apply followed by cm2_split_f16x2, bit for bit)."""
+    g = torch.Generator().manual_seed(6)
+    shapes = [(2, 13, 21), (2, 7, 11), (2, 4, 6)]
+    c = 256
+    seg = SegMap(shapes, c, F32, DEV)
+    for i, (n, h, w) in enumerate(shapes):
+        seg.level(i).view.copy_(torch.randn(n, h, w, c, generator=g).to(DEV))
+    wt = torch.randn(c, c, 3, 3, generator=g) / 48
+    bias = torch.randn(c, generator=g) * 0.1
+    gamma, beta = (torch.rand(c, generator=g) + 0.5).to(DEV), (torch.randn(c, generator=g) * 0.1).to(DEV)
+    cw = packing.ConvW(wt, [c], 1, 1, None, bias, False, F32, DEV, True)
+    st = torch.zeros((6, c // 8, 2), dtype=torch.float64, device=DEV)
+    eng.begin_pass()
+    out = eng.conv_seg("gs", seg, cw, stats=st, stats_mode=2)
+    sp = torch.zeros((out.rows, 2 * c), dtype=torch.float16, device=DEV)
+    lib.groupnorm_apply_seg_split(out.flat, sp, out.segs, 32, gamma, beta, 1e-5, True, st)
+    lib.groupnorm_apply_seg(out.flat, out.segs, 32, gamma, beta, 1e-5, True, st)          # in place, fp32
+    want = torch.empty_like(sp)
+    lib.split_f16x2(out.flat, want)
+    torch.cuda.synchronize()
+    # the two apply kernels evaluate v * a + b with the same coefficients; the fused one rounds once more nowhere
+    diff = (sp.float() - want.float()).abs().max().item()
+    assert diff <= 1e-3 * out.flat.abs().max().item(), diff
+    tot = (sp[:, :c].float() + sp[:, c:].float() - out.flat).abs().max().item()
+    assert tot <= 2e-6 * out.flat.abs().max().item(), tot
