@@ -88,6 +88,21 @@ class PhaseMap(object):
         return self.buf.shape[4]
 
 
+class RawInput(object):
+    """The un-normalised input batch on its way to the fused stem (``cm2_stem1_fused_batch``: normalise + pad + stem_1 in
+    one pass): planar ``[3, h, w]`` device images of one dtype and the padded extent.  Never materialised as a tensor."""
+
+    __slots__ = ("images", "hp", "wp")
+
+    def __init__(self, images, hp, wp):
+        self.images, self.hp, self.wp = images, hp, wp
+
+    n = property(lambda self: len(self.images))
+    h = property(lambda self: self.hp)
+    w = property(lambda self: self.wp)
+    c = 3
+
+
 class SplitFMap(FMap):
     """fp32 engine: a feature map that exists only as the [hi | lo] f16 operand pair of the convolutions that read it
     (``buf[n, h+2, w+2, 2c]``; include/cm2.h "Split precision"): written by a convolution epilogue or the GroupNorm apply,
@@ -165,6 +180,7 @@ class Engine(object):
         # operands ("fp32": three MMAs per product term, fp32-grade accuracy); "fp32_simt" keeps everything on CUDA cores
         self.tc = precision in ("bf16", "fp32")
         self.split = precision == "fp32"
+        self.stem_variant = int(os.environ.get("CM2_STEM_VARIANT", "1"))      # 1: fused stem_1 (csrc/stem.cu); 0: im2col pass + K = 32 GEMM
         self.split_out_all = os.environ.get("CM2_SPLIT_OUT_ALL") == "1"       # [hi | lo] epilogue store on every eligible layer (tests)
         self._split_cache = {}
         self.device = torch.device(device)
@@ -424,6 +440,11 @@ class Engine(object):
             sc, sh = packing.fold_frozen_bn(sd[k1 + "/norm.weight"], sd[k1 + "/norm.bias"], sd[k1 + "/norm.running_mean"],
                                             sd[k1 + "/norm.running_var"])
             P["stem1_im2col"] = packing.ConvW(w32, [32], 1, 0, sc, sh, True, dt, dev, tc)
+            if w1.shape[0] == 64:
+                # fused stem (csrc/stem.cu): K order ky * 10 + kx * 3 + c, the filter rows padded from 9 to 10 values
+                w30 = torch.zeros((64, 32))
+                w30[:, :30] = torch.nn.functional.pad(w1.permute(0, 2, 3, 1).reshape(64, 3, 9), (0, 1)).reshape(64, 30)
+                P["stem1_fused"] = (w30.to(device=dev, dtype=torch.bfloat16).contiguous(), P["stem1_im2col"].scale, P["stem1_im2col"].shift)
         for b in blocks:
             convs = []
             c = b.in_ch
@@ -468,7 +489,9 @@ class Engine(object):
         cfg = self.cfg
         self.begin_pass()
         dw_body = isinstance(P["stem"][1], tuple)
-        if self.tc and x.c == 32:
+        if isinstance(x, RawInput):
+            x = self.stem1_fused("stem1", x, P)
+        elif self.tc and x.c == 32:
             x = self.conv("stem1", [x], P["stem1_im2col"])      # stem_1 = 1x1 over the im2col'd input
         else:
             x = self.conv("stem1", [x], P["stem"][0])
@@ -911,18 +934,35 @@ class Engine(object):
         hp = (hp + size_divisibility - 1) // size_divisibility * size_divisibility
         wp = (wp + size_divisibility - 1) // size_divisibility * size_divisibility
         if self.tc and not self.split and fused_stem and len(cfg.MODEL.PIXEL_MEAN) == 3:
-            # normalise + pad + im2col of stem_1 in one pass (the TC engine then runs stem_1 as a 1x1 conv)
-            x = self.fmap("input_im2col", len(images), hp // 2, wp // 2, 32)
-            if len({im.dtype for im in images}) == 1:
-                lib.preprocess_im2col_batch([im.contiguous() for im in images], cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD, hp, wp, x.view)
-            else:
-                for i, im in enumerate(images):
-                    lib.preprocess_im2col(im.contiguous(), cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD, hp, wp, x.view, i)
-            return x, sizes
+            if self.stem_variant >= 1 and len({im.dtype for im in images}) == 1 and images[0].dtype in (torch.uint8, torch.float32):
+                # normalise + pad + stem_1 in ONE pass (run_backbone -> stem1_fused): nothing to do here
+                return RawInput([im.contiguous() for im in images], hp, wp), sizes
+            return self._im2col(images, hp, wp), sizes
         x = self.fmap("input", len(images), hp, wp, 3)
         for i, im in enumerate(images):
             lib.preprocess_image(im.contiguous(), cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD, x.view, i)
         return x, sizes
+
+    def _im2col(self, images, hp, wp):
+        """normalise + pad + im2col of stem_1 in one pass (the TC engine then runs stem_1 as a 1x1 conv, K = 32)."""
+        cfg = self.cfg
+        x = self.fmap("input_im2col", len(images), hp // 2, wp // 2, 32)
+        if len({im.dtype for im in images}) == 1:
+            lib.preprocess_im2col_batch([im.contiguous() for im in images], cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD, hp, wp, x.view)
+        else:
+            for i, im in enumerate(images):
+                lib.preprocess_im2col(im.contiguous(), cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD, hp, wp, x.view, i)
+        return x
+
+    def stem1_fused(self, name, raw, P):
+        """stem_1 straight from the raw images (csrc/stem.cu); falls back to im2col + 1x1 GEMM when the packed fused weights
+        do not exist (stem_1 with other than 64 output channels)."""
+        if "stem1_fused" not in P:
+            return self.conv(name, [self._im2col(raw.images, raw.hp, raw.wp)], P["stem1_im2col"])
+        w30, scale, shift = P["stem1_fused"]
+        out = self.fmap(name, raw.n, raw.hp // 2, raw.wp // 2, 64)
+        lib.stem1_fused_batch(raw.images, self.cfg.MODEL.PIXEL_MEAN, self.cfg.MODEL.PIXEL_STD, raw.hp, raw.wp, w30, scale, shift, True, out.view)
+        return out
 
     def paste(self, probs, boxes, out_h, out_w, image_size, threshold=0.5):
         """detector_postprocess [d2] for the slots of one image: returns (boxes', valid u8, masks u8 [R,H,W])."""

@@ -193,6 +193,17 @@ int cm2_preprocess_im2col_batch(const void* const* imgs, const int32_t* hs, cons
                                 int32_t hp, int32_t wp, const float* mean3, const float* std3, const cm2_act* out,
                                 int32_t out_index0, void* stream);
 
+/* stem_1 fused with the input side (csrc/stem.cu): normalise + zero-pad + Conv2d(3, 64, 3, stride 2, pad 1) + per-channel
+ * scale / shift (folded FrozenBN) + optional ReLU in one pass over the raw planar images (deploy_utils.py:76-98,
+ * vovnet.py:205-236, :392-400); replaces cm2_preprocess_im2col_batch + the K = 32 GEMM.  imgs / hs / ws as above (CM2_U8 or
+ * CM2_F32).  w30: device bf16 [64][32], K-major, k = ky*10 + kx*3 + c (weights of k = 9, 19, 29, 30, 31 must be zero).
+ * out: bf16 view [>= out_index0 + n, hp/2, wp/2, 64]; only interior pixels are written (the halo of a halo buffer is left
+ * untouched).  scale / shift: device fp32 [64] or NULL. */
+int cm2_stem1_fused_batch(const void* const* imgs, const int32_t* hs, const int32_t* ws, int32_t n, int32_t in_dtype,
+                          int32_t hp, int32_t wp, const float* mean3, const float* std3, const void* w30,
+                          const float* scale, const float* shift, int32_t relu, const cm2_act* out, int32_t out_index0,
+                          void* stream);
+
 /* Depthwise 3x3 convolution, padding 1, stride 1 or 2, no bias: the "dw_conv3x3" half of the depthwise bodies'
  * units (vovnet.py:110-130, Conv2d(c, c, 3, groups=c)); the pointwise 1x1 + FrozenBN + ReLU that follows is a
  * cm2_conv_nhwc call.  w: device fp32 [9][c] (tap-major: w[(ky*3+kx)*c + ch] = weight[ch][0][ky][kx]).

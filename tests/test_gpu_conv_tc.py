@@ -272,6 +272,47 @@ def test_fused_preprocess_im2col_stem1():
 
 
 @pytest.mark.parametrize("std", [[1.0, 1.0, 1.0], [57.375, 57.12, 58.395]])
+def test_stem1_fused_matches_conv_and_the_im2col_path(std):
+    """cm2_stem1_fused_batch (normalise + pad + 3x3 / s2 conv + FrozenBN + ReLU in one pass, csrc/stem.cu) against
+    F.conv2d on the bf16-rounded normalised input (vovnet.py:409) and against the two-pass path it replaces (im2col +
+    K = 32 GEMM on the tcgen05 engine): images of different extents (tile edges: 300 columns = 2 full tiles + 44, odd
+    widths, an image smaller than the padded extent), uint8 and float inputs, halo left untouched."""
+    g = torch.Generator().manual_seed(14)
+    hp, wp = 96, 608
+    mean = [103.53, 116.28, 123.675]
+    extents = ((45, 61), (96, 608), (33, 599), (90, 257))
+    imgs = [(torch.rand(3, h, w, generator=g) * 255).floor().to(torch.uint8) for h, w in extents]
+    w1 = rb(torch.randn(64, 3, 3, 3, generator=g) / 5)
+    sc, sh = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.2
+    xn = torch.zeros(len(imgs), 3, hp, wp)
+    for i, (im, (h, w)) in enumerate(zip(imgs, extents)):
+        xn[i, :, :h, :w] = rb((im.float() - torch.tensor(mean).view(3, 1, 1)) / torch.tensor(std).view(3, 1, 1))
+    ref = torch.relu(F.conv2d(xn, w1, None, 2, 1) * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
+    w30 = torch.zeros(64, 32)
+    w30[:, :30] = F.pad(w1.permute(0, 2, 3, 1).reshape(64, 3, 9), (0, 1)).reshape(64, 30)
+    w30 = w30.to(DEV, torch.bfloat16).contiguous()
+    w32 = torch.zeros(64, 32, 1, 1)
+    w32[:, :27, 0, 0] = w1.permute(0, 2, 3, 1).reshape(64, 27)
+    cw = packing.ConvW(w32, [32], 1, 0, sc, sh, True, BF, DEV, True)
+    cols = halo(torch.zeros(len(imgs) + 1, 32, hp // 2, wp // 2))
+    lib.preprocess_im2col_batch([im.to(DEV) for im in imgs], mean, std, hp, wp, cols.view, 1)
+    two = halo(torch.zeros(len(imgs) + 1, 64, hp // 2, wp // 2))
+    assert lib.conv2d([cols.view], cw.w_tc, two.view, 64, 1, 1, 0, scale=cw.scale_tc, shift=cw.shift, relu=True, engine=lib.ENGINE_TC, probe=True)
+    for conv_in in ([im.to(DEV) for im in imgs], [im.float().to(DEV) for im in imgs]):
+        out = halo(torch.zeros(len(imgs) + 1, 64, hp // 2, wp // 2))
+        lib.stem1_fused_batch(conv_in, mean, std, hp, wp, w30, cw.scale, cw.shift, True, out.view, 1)
+        torch.cuda.synchronize()
+        close(nchw(out.view)[1:], ref)
+        assert nchw(out.view)[0].abs().max() == 0
+        b = out.buf.float()
+        assert b[:, 0].abs().max() == 0 and b[:, -1].abs().max() == 0 and b[:, :, 0].abs().max() == 0 and b[:, :, -1].abs().max() == 0
+        # same products, same fp32 accumulation up to the order of the sum: at most one bf16 ulp apart
+        d = (out.view[1:].float() - two.view[1:].float()).abs()          # (slot 0 of the two-pass output is relu(shift): zero columns)
+        assert (d <= two.view[1:].float().abs() / 64 + 1e-3).all(), d.max().item()
+        assert (d > 0).float().mean().item() < 0.05
+
+
+@pytest.mark.parametrize("std", [[1.0, 1.0, 1.0], [57.375, 57.12, 58.395]])
 def test_preprocess_im2col_batch_equals_per_image(std):
     """One launch for the whole batch (images of different extents) == the per-image entry point, bit for bit."""
     g = torch.Generator().manual_seed(13)
