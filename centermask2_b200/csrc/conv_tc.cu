@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <algorithm>
 
 namespace cm2 {
 
@@ -93,6 +94,11 @@ struct alignas(64) TcParams {
   int chunk;                // main-accumulator K-blocks between two drains into the fp32 register sums
   int cout_pad;             // W_lo tiles start cout_pad rows below the W_hi tiles in the weight matrix
   int split_out;            // 1: the output is the [hi | lo] f16 pair of 2 * cout channels (epilogue kind 11)
+  // ---- split-K (v1 kernel): tile t = (k-slice, m tile, n tile); slice ks accumulates K-blocks [ks * kb_per_split, ..) and stores
+  // its fp32 partial sums split_stride elements behind the previous slice's (cm2_conv_desc.splitk; splitk_finish_kernel adds them)
+  int ksplit;               // 0 / 1: off
+  int kb_per_split;
+  long long split_stride;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -281,9 +287,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 
 // Geometry of the map a tile belongs to (segments start at multiples of 256 rows, so a tile never straddles two).
-struct TileGeom { int row0, rows, pitch, plane, h, w, img0; double rcp_plane, rcp_pitch; };
+struct TileGeom { int row0, rows, pitch, plane, h, w, img0; double rcp_plane, rcp_pitch; long long out_extra; };
 __device__ __forceinline__ TileGeom tc_geom(const TcParams& p, int m0) {
   TileGeom g;
+  g.out_extra = 0;
   if (p.num_seg == 0) {
     g.row0 = 0; g.rows = p.rows; g.pitch = p.pitch; g.plane = p.plane; g.h = p.h; g.w = p.w; g.img0 = 0;
     g.rcp_plane = p.rcp_plane; g.rcp_pitch = p.rcp_pitch;
@@ -605,7 +612,7 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
   else if (DECONV)
     out_off = (long long)img * p.out_sn + (long long)(2 * y) * p.out_sh + (long long)(2 * x) * p.out_sw;
   else if (p.out_mode == 0)
-    out_off = (long long)img * p.out_sn + (long long)y * p.out_sh + (long long)x * p.out_sw;
+    out_off = (long long)img * p.out_sn + (long long)y * p.out_sh + (long long)x * p.out_sw + g.out_extra;
   else
     out_off = (long long)((y & 1) * 2 + (x & 1)) * p.out_plane + (long long)img * p.out_sn +
               (long long)(y >> 1) * p.out_sh + (long long)(x >> 1) * p.out_sw;
@@ -886,7 +893,9 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc_kernel(const __grid_constant_
   const uint32_t ss_base = epi_base + (uint32_t)n_epi_warps * EPI_WARP_BYTES;         // EPI_SS_BYTES of scale/shift
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int mn_tiles = p.m_tiles * p.n_tiles;
+  const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+  const int total_tiles = mn_tiles * ksplit;        // split-K: slice-major, so the slices of one output tile run side by side
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&p.a_map[s]);
@@ -911,13 +920,16 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc_kernel(const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int m0 = p.row_begin + (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.bn;
+        const int ks = t / mn_tiles, tt = t - ks * mn_tiles;
+        const int m0 = p.row_begin + (tt / p.n_tiles) * TC_BM, n0 = (tt % p.n_tiles) * p.bn;
+        const int kb_lo = ksplit > 1 ? ks * p.kb_per_split : 0, kb_hi = ksplit > 1 ? kb_lo + p.kb_per_split : 0x7fffffff;
         int kb = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int shift = tc_tap_shift(p, tap, p.num_seg ? tc_geom(p, m0).pitch : p.pitch);
           for (int s = 0; s < p.num_src; ++s) {
             const int nblk = (p.src_c[s] + TC_BK - 1) / TC_BK;
             for (int cb = 0; cb < nblk; ++cb, ++kb) {
+              if (kb < kb_lo || kb >= kb_hi) continue;               // another K slice's block
               mbar_wait_ctl(p.spin, empty_bar(stage), phase ^ 1u);
               const uint32_t sa = base + (uint32_t)stage * stage_bytes;
               if (elect_one_sync()) {
@@ -952,11 +964,15 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc_kernel(const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_ACC_COLS);
         uint32_t accumulate = 0;
+        const int ks = t / mn_tiles;
+        const int kb_lo = ksplit > 1 ? ks * p.kb_per_split : 0, kb_hi = ksplit > 1 ? kb_lo + p.kb_per_split : 0x7fffffff;
+        int kb = 0;
         for (int tap = 0; tap < taps; ++tap) {
           for (int s = 0; s < num_src; ++s) {
             const int c = p.src_c[s];
             const int nblk = (c + TC_BK - 1) / TC_BK;
-            for (int cb = 0; cb < nblk; ++cb) {
+            for (int cb = 0; cb < nblk; ++cb, ++kb) {
+              if (kb < kb_lo || kb >= kb_hi) continue;
               const int nk = (min(TC_BK, c - cb * TC_BK) + 15) >> 4;        // 16-channel MMAs in this block
               mbar_wait_ctl(spin, full_bar(stage), phase);
               tc_fence_after();
@@ -993,7 +1009,8 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc_kernel(const __grid_constant_
     uint32_t acc_phase = 0;
     uint32_t parity = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, parity ^= 1u) {
-      const int m0 = p.row_begin + (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.bn;
+      const int ks = t / mn_tiles, tt = t - ks * mn_tiles;
+      const int m0 = p.row_begin + (tt / p.n_tiles) * TC_BM, n0 = (tt % p.n_tiles) * p.bn;
       // scale / shift of the tile's columns: staged once when there is a single N tile, else per tile (double buffered)
       const uint32_t ss = ss_base + (p.n_tiles == 1 ? 0u : parity * 2048u);
       if (p.n_tiles > 1 || t == (int)blockIdx.x)
@@ -1001,7 +1018,8 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc_kernel(const __grid_constant_
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * TC_ACC_COLS) + ((uint32_t)(q * 32) << 16);
-      const TileGeom g = tc_geom(p, m0);
+      TileGeom g = tc_geom(p, m0);
+      g.out_extra = (long long)ks * p.split_stride;
       const int cset = (warp - 2) >> 2;
       if (p.dbg & 8) {
       } else if (p.fast_store)
@@ -1627,6 +1645,39 @@ static bool encode_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t
   return r == CUDA_SUCCESS;
 }
 
+// Split-K finish: out[n, y, x, c] = act(scale[c] * sum_s part[s][n, y, x, c] + shift[c]) over the interior pixels of the output
+// view; the partial buffers have the output's strides (fp32).  Fixed summation order: results do not depend on scheduling.
+template <typename OutT>
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ part, long long split_stride, int ksplit,
+                                                            View<OutT> out, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, int relu) {
+  const int c8 = out.c >> 3;
+  const long long total = (long long)out.n * out.h * out.w * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % c8);
+    long long t = i / c8;
+    const int x = (int)(t % out.w); t /= out.w;
+    const int y = (int)(t % out.h);
+    const int b = (int)(t / out.h);
+    const long long off = (long long)b * out.sn + (long long)y * out.sh + (long long)x * out.sw + cv * 8;
+    float acc[8];
+    Vec8<float>::load(part + off, acc);
+    for (int s = 1; s < ksplit; ++s) {
+      float v[8];
+      Vec8<float>::load(part + (long long)s * split_stride + off, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float sc = scale ? __ldg(scale + cv * 8 + k) : 1.f, sh = shift ? __ldg(shift + cv * 8 + k) : 0.f;
+      acc[k] = fmaf(acc[k], sc, sh);
+      if (relu) acc[k] = fmaxf(acc[k], 0.f);
+    }
+    Vec8<OutT>::store(out.p + off, acc);
+  }
+}
+
 // sources may be channel slices (sw > c); outputs / residuals are whole tensors (sw == c)
 static bool is_halo_view(const cm2_act& a, bool slice_ok = false) {
   return (slice_ok ? a.sw >= a.c : a.sw == a.c) && a.sh == (long long)(a.w + 2) * a.sw && a.sn == (long long)(a.h + 2) * a.sh;
@@ -1647,6 +1698,8 @@ static int device_is_sm100() {
   }
   return cached;
 }
+
+static thread_local bool g_plan_splitk = false;         // set by conv_tc_launch_splitk around its tc_plan call
 
 static int pick_bn(int cout_pad, int m_tiles, int sms) {
   int bn = cout_pad;
@@ -1801,7 +1854,7 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   if (pair_ok) use_v2 = true;
   if (env_variant == 1) use_v2 = false;
   if (env_variant >= 2 && !pred) use_v2 = true;
-  if (f16) use_v2 = false;
+  if (f16 || g_plan_splitk) use_v2 = false;
   static const int env_sets1 = getenv("CM2_TC_EPI_SETS_V1") ? atoi(getenv("CM2_TC_EPI_SETS_V1")) : 2;
   static const int env_sets2 = getenv("CM2_TC_EPI_SETS_V2") ? atoi(getenv("CM2_TC_EPI_SETS_V2")) : 1;
   // 16 epilogue warps (576 threads, <= 96 registers per thread) were measured 3-20 % slower on every layer
@@ -1851,7 +1904,8 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     p->variant = f16 ? 3 : 1;
     p->epi_sets = f16 ? 2 : sets1;
     p->m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
-    p->bn = pred ? d->cout / 4 : pick_bn(cout_pad, p->m_tiles, sms);     // fused predictor: one N tile per quadrant
+    p->bn = pred ? d->cout / 4 : pick_bn(cout_pad, p->m_tiles, g_plan_splitk ? 1 : sms);   // fused predictor: one N tile per quadrant;
+                                                                                           // split-K: widest tile (K slices fill the SMs)
     if (f16) {
       // four accumulators (2 main + 2 cross) share the 512 TMEM columns: N <= 128
       while (p->bn > 128 || cout_pad % p->bn) p->bn -= 16;
@@ -1901,7 +1955,7 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   p->out_f32 = d->out_dtype == CM2_F32;
   p->out_mode = d->out_mode;
   p->out_plane = (long long)d->out.n * d->out.sn;
-  p->out_halo = (halo && d->out_mode == 0 && is_halo_view(d->out) && d->out.h == s0.h && d->out.w == s0.w) ? 1 : 0;
+  p->out_halo = (halo && d->out_mode == 0 && is_halo_view(d->out) && d->out.h == s0.h && d->out.w == s0.w && !g_plan_splitk) ? 1 : 0;
   const int oc = d->out_mode == 1 ? d->cout / 4 : d->cout;
   const int oeb = p->out_f32 ? 4 : 2;
   p->out_vec = (oc % 16 == 0 && d->out.sn % 8 == 0 && d->out.sh % 8 == 0 && d->out.sw % 8 == 0 &&
@@ -1970,16 +2024,75 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   return CM2_OK;
 }
 
-int conv_tc_launch(const cm2_conv_desc* d, cudaStream_t stream) {
-  TcParams p;
-  int rc = tc_plan(d, &p, true);
+// Split-K launch (cm2_conv_desc.splitk >= 2): the K loop of every output tile is cut into `splitk` slices that run as separate
+// tiles of the 128-row kernel (small-M layers: the MaskIoU linear layers, P6 / P7, whole stages at small batch -- a handful of
+// output tiles cannot fill 148 SMs, their K loops can); fp32 partial sums go to the workspace, splitk_finish_kernel reduces them
+// in a fixed order and applies scale / shift / ReLU.  Returns CM2_ERR_UNSUPPORTED (nothing launched) when the layer does not qualify.
+static int splitk_plan(const cm2_conv_desc* d, TcParams* pp, bool maps) {
+#define SK_REQUIRE(cond, ...) do { if (!(cond)) { set_error(__VA_ARGS__); return CM2_ERR_UNSUPPORTED; } } while (0)
+  SK_REQUIRE(d->dtype == CM2_BF16 && (d->out_dtype == CM2_BF16 || d->out_dtype == CM2_F32) && d->out_mode == 0 && !d->residual.data &&
+             !d->stats && d->num_seg == 0 && d->cout % 8 == 0, "conv_tc: split-K takes plain bf16 convolutions (out_mode 0, no residual / statistics / segments)");
+  SK_REQUIRE(d->splitk_ws && (reinterpret_cast<uintptr_t>(d->splitk_ws) & 31) == 0, "conv_tc: split-K workspace missing or misaligned");
+  const long long split_stride = (long long)d->out.n * d->out.sn;
+  SK_REQUIRE(d->out.sn % 8 == 0 && d->out.sh % 8 == 0 && d->out.sw % 8 == 0 && d->out.c == d->cout,
+             "conv_tc: split-K needs 8-element aligned output strides");
+  cm2_conv_desc d2 = *d;
+  d2.splitk = 0;
+  d2.out.data = d->splitk_ws;
+  d2.out_dtype = CM2_F32;
+  d2.scale = nullptr; d2.shift = nullptr; d2.relu = 0;
+  TcParams& p = *pp;
+  g_plan_splitk = true;                                  // tc_plan: 128-row kernel, widest N tile, no halo stores
+  int rc = tc_plan(&d2, &p, maps);
+  g_plan_splitk = false;
   if (rc != CM2_OK) return rc;
+  SK_REQUIRE(p.variant == 1 && p.fast_store && !p.out_halo, "conv_tc: split-K plan fell off the staged 128-row path");
+  int ksplit = d->splitk;
+  const int kb_total = p.taps * p.nblk_total;
+  if (ksplit > kb_total) ksplit = kb_total;
+  const int per = (kb_total + ksplit - 1) / ksplit;
+  ksplit = (kb_total + per - 1) / per;                   // no empty slice
+  SK_REQUIRE(ksplit >= 2, "conv_tc: split-K with fewer than two slices");
+  SK_REQUIRE((long long)ksplit * split_stride * 4 <= d->splitk_ws_bytes, "conv_tc: split-K workspace too small (%lld bytes needed)",
+             (long long)ksplit * split_stride * 4);
+  p.ksplit = ksplit; p.kb_per_split = per; p.split_stride = split_stride;
+#undef SK_REQUIRE
+  return CM2_OK;
+}
+
+static int conv_tc_launch_splitk(const cm2_conv_desc* d, cudaStream_t stream, int sms) {
+  TcParams p;
+  int rc = splitk_plan(d, &p, true);
+  if (rc != CM2_OK) return rc;
+  const int ksplit = p.ksplit;
+  const long long split_stride = p.split_stride;
+  CM2_ENSURE_DYN_SMEM(conv_tc_kernel<320>, 227 * 1024, "conv_tc");
+  const int tiles = p.m_tiles * p.n_tiles * ksplit;
+  conv_tc_kernel<320><<<tiles < sms ? tiles : sms, 64 + 128 * p.epi_sets, p.smem_bytes, stream>>>(p);
+  CM2_CHECK_LAUNCH("conv_tc (split-K)");
+  const long long vecs = (long long)d->out.n * d->out.h * d->out.w * (d->cout / 8);
+  const int blocks = (int)std::min<long long>((vecs + 255) / 256, 148 * 8);
+  const float* part = reinterpret_cast<const float*>(d->splitk_ws);
+  if (d->out_dtype == CM2_F32)
+    splitk_finish_kernel<float><<<blocks, 256, 0, stream>>>(part, split_stride, ksplit, make_view<float>(d->out), d->scale, d->shift, d->relu);
+  else
+    splitk_finish_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(part, split_stride, ksplit, make_view<__nv_bfloat16>(d->out), d->scale,
+                                                                   d->shift, d->relu);
+  CM2_CHECK_LAUNCH("splitk_finish");
+  return CM2_OK;
+}
+
+int conv_tc_launch(const cm2_conv_desc* d, cudaStream_t stream) {
   static int sms = 0;
   if (!sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  if (d->splitk >= 2) return conv_tc_launch_splitk(d, stream, sms);
+  TcParams p;
+  int rc = tc_plan(d, &p, true);
+  if (rc != CM2_OK) return rc;
   CM2_ENSURE_DYN_SMEM(conv_tc_kernel<320>, 227 * 1024, "conv_tc");
   CM2_ENSURE_DYN_SMEM((conv_tc2_kernel<320, false>), 227 * 1024, "conv_tc2");
   CM2_ENSURE_DYN_SMEM((conv_tc2_kernel<320, true>), 227 * 1024, "conv_tc2 (pair)");
@@ -2046,5 +2159,6 @@ extern "C" int64_t cm2_conv_tc_klen(int32_t kh, int32_t kw, int32_t num_src, con
 extern "C" int cm2_conv_tc_supported(const cm2_conv_desc* d) {
   if (!d || d->num_src < 1 || d->num_src > CM2_MAX_SRC) return 0;
   cm2::TcParams p;
+  if (d->splitk >= 2) return cm2::splitk_plan(d, &p, false) == CM2_OK ? 1 : 0;
   return cm2::tc_plan(d, &p, false) == CM2_OK ? 1 : 0;
 }

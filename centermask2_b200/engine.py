@@ -181,6 +181,7 @@ class Engine(object):
         self.tc = precision in ("bf16", "fp32")
         self.split = precision == "fp32"
         self.stem_variant = int(os.environ.get("CM2_STEM_VARIANT", "1"))      # 1: fused stem_1 (csrc/stem.cu); 0: im2col pass + K = 32 GEMM
+        self.splitk_on = os.environ.get("CM2_SPLITK", "1") != "0"               # split-K for small-M layers (cm2_conv_desc.splitk)
         self.split_out_all = os.environ.get("CM2_SPLIT_OUT_ALL") == "1"       # [hi | lo] epilogue store on every eligible layer (tests)
         self._split_cache = {}
         self.device = torch.device(device)
@@ -363,13 +364,38 @@ class Engine(object):
                     tc_views = None
                 else:
                     tc_views = [s.view if pre else self.split_of(s).view for s, pre in zip(srcs, presplit)]
-            if tc_views is not None and lib.conv2d(tc_views, w.w_tc, out.view, w.cout, w.k, w.stride, w.pad, scale=w.scale_tc,
-                                                   engine=lib.ENGINE_TC, stats=stats, stats_mode=stats_mode, probe=True, pred=pred, **kw):
-                return out
+            if tc_views is not None:
+                ks = 0
+                if (self.splitk_on and not w.split and out_mode == 0 and residual is None and stats is None and pred is None and not in_relu
+                        and w.cout % 8 == 0):
+                    ks = self._splitk_slices(x0, ho, wo, w, src_phase)
+                if ks >= 2:
+                    # few output tiles, long K loop: K slices as separate tiles + a fixed-order reduction (cm2_conv_desc.splitk)
+                    ob = out.buf
+                    ws = self.buffer(name + "_splitk", (ks, ob.shape[0] * ob.stride(0)), torch.float32, zero=False)
+                    if lib.conv2d(tc_views, w.w_tc, out.view, w.cout, w.k, w.stride, w.pad, scale=w.scale_tc, engine=lib.ENGINE_TC, probe=True,
+                                  splitk=ks, splitk_ws=ws, **kw):
+                        lib._count()                                  # the reduction kernel
+                        return out
+                if lib.conv2d(tc_views, w.w_tc, out.view, w.cout, w.k, w.stride, w.pad, scale=w.scale_tc,
+                              engine=lib.ENGINE_TC, stats=stats, stats_mode=stats_mode, probe=True, pred=pred, **kw):
+                    return out
         assert stats is None and pred is None, "fused epilogues require the tensor-core engine: " + lib.last_error()
         assert not split_out and not any(presplit), "split-precision operands require the tensor-core engine: " + lib.last_error()
         lib.conv2d(views, w.w_simt, out.view, w.cout, w.k, w.stride, w.pad, scale=w.scale, engine=lib.ENGINE_SIMT, **kw)
         return out
+
+    @staticmethod
+    def _splitk_slices(x0, ho, wo, w, src_phase, sms=148):
+        """K slices for a layer whose output tiles (128 GEMM rows x up to 256 channels) fill at most half of the SMs: as many
+        as fit on the SMs, at least 4 K-blocks (of 64 channels) each.  0: leave the layer alone."""
+        halo = getattr(x0, "halo", 1)
+        rows = x0.n * ((ho + 2) * (wo + 2) if (src_phase or halo) else ho * wo)
+        tiles = -(-rows // 128) * -(-((w.cout + 15) // 16 * 16) // 256)
+        kb = w.k * w.k * sum(-(-c // 64) for c in w.src_c)
+        if 2 * tiles > sms or kb < 32:
+            return 0
+        return min(sms // tiles, kb // 4, 16)
 
     # -- split-precision operands ------------------------------------------------------------------
     def begin_pass(self):

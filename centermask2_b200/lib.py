@@ -41,7 +41,8 @@ class ConvDesc(C.Structure):
                 ("residual", Act), ("res_mode", C.c_int32), ("out_mode", C.c_int32),
                 ("out", Act), ("stats", C.c_void_p), ("src_phase", C.c_int32), ("num_seg", C.c_int32),
                 ("seg", Seg * MAX_SEG), ("stats_mode", C.c_int32), ("pred_ncls", C.c_int32),
-                ("pred_w", C.c_void_p), ("pred_b", C.c_void_p), ("pred_cls", C.c_void_p)]
+                ("pred_w", C.c_void_p), ("pred_b", C.c_void_p), ("pred_cls", C.c_void_p),
+                ("splitk", C.c_int32), ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64)]
 
 
 class CandBuffers(C.Structure):
@@ -182,7 +183,7 @@ def _count(k=1):
 # ------------------------------------------------------------------------------------------------
 def conv2d(srcs, weight, out, cout, k, stride, pad, scale=None, shift=None, relu=False, in_relu=False,
            residual=None, res_mode=0, out_mode=0, engine=ENGINE_SIMT, stats=None, stats_mode=0, probe=False, src_phase=False,
-           segs=None, pred=None):
+           segs=None, pred=None, splitk=0, splitk_ws=None):
     """Enqueue one convolution.  ``pred`` = (pred_w, pred_b, classes, ncls) for out_mode 3.  With ``probe=True`` (TC engine) the descriptor is first checked with
     ``cm2_conv_tc_supported``; returns False without launching if the engine does not take it."""
     d = ConvDesc()
@@ -214,6 +215,8 @@ def conv2d(srcs, weight, out, cout, k, stride, pad, scale=None, shift=None, relu
     d.src_phase = int(src_phase)
     if pred is not None:
         d.pred_w, d.pred_b, d.pred_cls, d.pred_ncls = pred[0].data_ptr(), pred[1].data_ptr(), pred[2].data_ptr(), int(pred[3])
+    if splitk >= 2:
+        d.splitk, d.splitk_ws, d.splitk_ws_bytes = int(splitk), splitk_ws.data_ptr(), splitk_ws.numel() * splitk_ws.element_size()
     if probe and not load().cm2_conv_tc_supported(C.byref(d)):
         return False
     check(load().cm2_conv2d(C.byref(d), stream()), "cm2_conv2d")

@@ -156,6 +156,14 @@ typedef struct cm2_conv_desc {
   const float* pred_w;      /* out_mode 3: device [pred_ncls][cout/4]                                    */
   const float* pred_b;      /* out_mode 3: device [pred_ncls]                                            */
   const int64_t* pred_cls;  /* out_mode 3: device [n] class per image (ROI); clamped to [0, pred_ncls)   */
+  /* Split-K (TC engine, bf16, out_mode 0, no residual / statistics / segments, cout % 16 == 0).  splitk >= 2: the K loop of
+   * every output tile is cut into (at most) `splitk` slices that run as separate tiles -- for layers whose few output tiles
+   * cannot fill the SMs (MaskIoU linear layers, P6 / P7, late stages at small batch).  fp32 partial sums go to `splitk_ws`
+   * (device, 32-byte aligned, >= splitk * out.n * out.sn * 4 bytes) and are reduced in a fixed order by a second kernel that
+   * applies scale / shift / ReLU: the result does not depend on scheduling.  0 / 1: off. */
+  int32_t splitk;
+  void* splitk_ws;
+  int64_t splitk_ws_bytes;
 } cm2_conv_desc;
 
 int cm2_conv2d(const cm2_conv_desc* d, void* stream);

@@ -223,6 +223,75 @@ def test_conv_tc_stride2_on_phase_planes(cin, cout, h, w, n):
     close(nchw(out), ref)
 
 
+@pytest.mark.parametrize("kind", ["linear", "linear_f32", "conv3x3", "conv1x1_multi", "phase_s2"])
+def test_conv_tc_split_k_matches_the_unsplit_convolution(kind):
+    """cm2_conv_desc.splitk: K slices as separate tiles + fixed-order fp32 reduction (MaskIoU linear layers, P6 / P7, late
+    stages at small batch) == F.conv2d, == the unsplit launch up to fp32 summation order, halo untouched, repeatable bit for bit."""
+    g = torch.Generator().manual_seed(31)
+    relu, out_f32, src_phase, stride = True, False, False, 1
+    if kind.startswith("linear"):
+        r, k, cout = 70, 2112, 144 if kind == "linear_f32" else 528            # K not a multiple of the slice, three N tiles of 176
+        out_f32 = kind == "linear_f32"
+        relu = not out_f32
+        x = rb(torch.randn(r, k, 1, 1, generator=g))
+        wt = rb(torch.randn(cout, k, 1, 1, generator=g) / math.sqrt(k))
+        srcs, views, ksz = [k], [x.reshape(r, k).to(DEV, BF).reshape(r, 1, 1, k)], 1
+        out = torch.zeros((r, 1, 1, cout), dtype=torch.float32 if out_f32 else BF, device=DEV)
+        outs = [out, torch.zeros_like(out)]
+        oview = lambda o: o
+    elif kind == "conv3x3":
+        n, c, h, w, cout = 2, 224, 13, 21, 224
+        x = rb(torch.randn(n, c, h, w, generator=g))
+        wt = rb(torch.randn(cout, c, 3, 3, generator=g) / math.sqrt(9 * c))
+        srcs, views, ksz = [c], [halo(x).view], 3
+        outs = [halo(torch.zeros(n, cout, h, w)), halo(torch.zeros(n, cout, h, w))]
+        oview = lambda o: o.view
+    elif kind == "conv1x1_multi":
+        n, h, w, cout = 1, 9, 14, 256
+        srcs = [256, 160, 160]
+        xs = [rb(torch.randn(n, c, h, w, generator=g)) for c in srcs]
+        x = torch.cat(xs, dim=1)
+        wt = rb(torch.randn(cout, sum(srcs), 1, 1, generator=g) / math.sqrt(sum(srcs)))
+        views, ksz = [halo(t).view for t in xs], 1
+        outs = [halo(torch.zeros(n, cout, h, w)), halo(torch.zeros(n, cout, h, w))]
+        oview = lambda o: o.view
+    else:
+        n, c, h, w, cout = 3, 256, 13, 21, 256
+        src_phase, stride = True, 2
+        x = rb(torch.randn(n, c, h, w, generator=g))
+        wt = rb(torch.randn(cout, c, 3, 3, generator=g) / math.sqrt(9 * c))
+        ho, wo = (h + 1) // 2, (w + 1) // 2
+        planes = torch.zeros((4, n, ho + 2, wo + 2, c), dtype=BF, device=DEV)
+        lib.phase_split(halo(x).view, planes[0, :, 1:-1, 1:-1, :], relu=False)
+        srcs, views, ksz = [c], [planes[0, :, 1:-1, 1:-1, :]], 3
+        outs = [halo(torch.zeros(n, cout, ho, wo)), halo(torch.zeros(n, cout, ho, wo))]
+        oview = lambda o: o.view
+    sc, sh = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    ref = F.conv2d(x, wt, None, stride, ksz // 2) * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
+    if relu:
+        ref = torch.relu(ref)
+    cw = packing.ConvW(wt, srcs, stride, ksz // 2, sc, sh, relu, BF, DEV, True)
+    ob = outs[0] if isinstance(outs[0], torch.Tensor) else outs[0].buf
+    ws = torch.full((6, ob.shape[0] * ob.stride(0)), float("nan"), dtype=torch.float32, device=DEV)
+    kw = dict(scale=cw.scale_tc, shift=cw.shift, relu=relu, engine=lib.ENGINE_TC, probe=True, src_phase=src_phase)
+    assert lib.conv2d(views, cw.w_tc, oview(outs[0]), cout, ksz, stride, ksz // 2, splitk=5, splitk_ws=ws, **kw), lib.last_error()
+    assert lib.conv2d(views, cw.w_tc, oview(outs[1]), cout, ksz, stride, ksz // 2, **kw), lib.last_error()
+    torch.cuda.synchronize()
+    got, plain = nchw(oview(outs[0])), nchw(oview(outs[1]))
+    close(got, ref, out_bf16=not out_f32)
+    d = (got - plain).abs()
+    assert (d <= plain.abs() / 64 + 1e-3).all() if not out_f32 else (d <= 1e-5 * plain.abs() + 1e-5).all(), d.max().item()
+    if not isinstance(outs[0], torch.Tensor):
+        b = outs[0].buf.float()
+        assert b[:, 0].abs().max() == 0 and b[:, -1].abs().max() == 0 and b[:, :, 0].abs().max() == 0 and b[:, :, -1].abs().max() == 0
+    first = oview(outs[0]).clone()
+    assert lib.conv2d(views, cw.w_tc, oview(outs[0]), cout, ksz, stride, ksz // 2, splitk=5, splitk_ws=ws, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(first, oview(outs[0]))
+    # a workspace that is too small is refused, nothing is launched
+    assert not lib.conv2d(views, cw.w_tc, oview(outs[0]), cout, ksz, stride, ksz // 2, splitk=5, splitk_ws=ws[:1, :64], **kw)
+
+
 def test_conv_tc_phase_split_store_feeds_stride2_conv():
     """stem_2 -> stem_3 chain: out_mode 2 (phase-split store) then a stride-2 conv on the planes."""
     g = torch.Generator().manual_seed(11)
