@@ -104,6 +104,11 @@ struct alignas(64) TcParams {
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (the conv launches carry cudaLaunchAttributeProgrammaticStreamSerialization): a kernel may be
+// scheduled while its predecessor in the stream is still draining; griddepcontrol.wait returns once the predecessor has
+// completed and its writes are visible, so every global access of the convolution kernels sits behind it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -913,6 +918,10 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc_kernel(const __grid_constant_
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  // programmatic dependent launch: the setup above overlapped the previous kernel's tail; let the next kernel start its own
+  // setup, then wait until everything this one reads (and overwrites) is final
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -1121,6 +1130,10 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc2_kernel(const __grid_constant
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  // programmatic dependent launch: the setup above overlapped the previous kernel's tail; let the next kernel start its own
+  // setup, then wait until everything this one reads (and overwrites) is final
+  pdl_launch_dependents();
+  pdl_wait();
   const int half_cols = p.acc_stages == 2 ? 128 : 256;        // TMEM columns per 128-row accumulator
 
   if (warp == 0) {
@@ -1402,6 +1415,10 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc3_kernel(const __grid_constant
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  // programmatic dependent launch: the setup above overlapped the previous kernel's tail; let the next kernel start its own
+  // setup, then wait until everything this one reads (and overwrites) is final
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -2028,6 +2045,27 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
 // tiles of the 128-row kernel (small-M layers: the MaskIoU linear layers, P6 / P7, whole stages at small batch -- a handful of
 // output tiles cannot fill 148 SMs, their K loops can); fp32 partial sums go to the workspace, splitk_finish_kernel reduces them
 // in a fixed order and applies scale / shift / ReLU.  Returns CM2_ERR_UNSUPPORTED (nothing launched) when the layer does not qualify.
+static bool tc_pdl_enabled() {
+  static const int on = getenv("CM2_PDL") ? atoi(getenv("CM2_PDL")) : 1;
+  return on != 0;
+}
+// Launch with the programmatic-stream-serialisation attribute (CM2_PDL=0: plain launch; the kernels' griddepcontrol
+// instructions are no-ops then).
+template <typename K>
+static void tc_launch_pdl(K kernel, int grid, int block, unsigned smem, cudaStream_t stream, const TcParams& p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tc_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 static int splitk_plan(const cm2_conv_desc* d, TcParams* pp, bool maps) {
 #define SK_REQUIRE(cond, ...) do { if (!(cond)) { set_error(__VA_ARGS__); return CM2_ERR_UNSUPPORTED; } } while (0)
   SK_REQUIRE(d->dtype == CM2_BF16 && (d->out_dtype == CM2_BF16 || d->out_dtype == CM2_F32) && d->out_mode == 0 && !d->residual.data &&
@@ -2068,7 +2106,7 @@ static int conv_tc_launch_splitk(const cm2_conv_desc* d, cudaStream_t stream, in
   const long long split_stride = p.split_stride;
   CM2_ENSURE_DYN_SMEM(conv_tc_kernel<320>, 227 * 1024, "conv_tc");
   const int tiles = p.m_tiles * p.n_tiles * ksplit;
-  conv_tc_kernel<320><<<tiles < sms ? tiles : sms, 64 + 128 * p.epi_sets, p.smem_bytes, stream>>>(p);
+  tc_launch_pdl(conv_tc_kernel<320>, tiles < sms ? tiles : sms, 64 + 128 * p.epi_sets, p.smem_bytes, stream, p);
   CM2_CHECK_LAUNCH("conv_tc (split-K)");
   const long long vecs = (long long)d->out.n * d->out.h * d->out.w * (d->cout / 8);
   const int blocks = (int)std::min<long long>((vecs + 255) / 256, 148 * 8);
@@ -2129,21 +2167,23 @@ int conv_tc_launch(const cm2_conv_desc* d, cudaStream_t stream) {
     cfg.blockDim = dim3(64 + 256 * p.epi_sets);
     cfg.dynamicSmemBytes = p.smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = tc_pdl_enabled() ? 2 : 1;
     if (cudaLaunchKernelEx(&cfg, conv_tc2_kernel<320, true>, p) != cudaSuccess) {
       set_error("conv_tc: cluster launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       return CM2_ERR_CUDA;
     }
   } else if (p.variant == 2)
-    conv_tc2_kernel<320, false><<<grid, 64 + 256 * p.epi_sets, p.smem_bytes, stream>>>(p);
+    tc_launch_pdl(conv_tc2_kernel<320, false>, grid, 64 + 256 * p.epi_sets, p.smem_bytes, stream, p);
   else if (p.variant == 3)
-    conv_tc3_kernel<320><<<grid, 320, p.smem_bytes, stream>>>(p);
+    tc_launch_pdl(conv_tc3_kernel<320>, grid, 320, p.smem_bytes, stream, p);
   else
-    conv_tc_kernel<320><<<grid, 64 + 128 * p.epi_sets, p.smem_bytes, stream>>>(p);
+    tc_launch_pdl(conv_tc_kernel<320>, grid, 64 + 128 * p.epi_sets, p.smem_bytes, stream, p);
   CM2_CHECK_LAUNCH("conv_tc");
   return CM2_OK;
 }
