@@ -1,5 +1,6 @@
 // libcm2: version / error plumbing.
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace cm2 {
@@ -9,6 +10,10 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+bool pdl_enabled() {
+  static const int on = getenv("CM2_PDL") ? atoi(getenv("CM2_PDL")) : 1;
+  return on != 0;
 }
 }  // namespace cm2
 

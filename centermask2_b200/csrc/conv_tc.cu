@@ -104,11 +104,6 @@ struct alignas(64) TcParams {
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------------
-// Programmatic dependent launch (the conv launches carry cudaLaunchAttributeProgrammaticStreamSerialization): a kernel may be
-// scheduled while its predecessor in the stream is still draining; griddepcontrol.wait returns once the predecessor has
-// completed and its writes are visible, so every global access of the convolution kernels sits behind it.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -2045,10 +2040,7 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
 // tiles of the 128-row kernel (small-M layers: the MaskIoU linear layers, P6 / P7, whole stages at small batch -- a handful of
 // output tiles cannot fill 148 SMs, their K loops can); fp32 partial sums go to the workspace, splitk_finish_kernel reduces them
 // in a fixed order and applies scale / shift / ReLU.  Returns CM2_ERR_UNSUPPORTED (nothing launched) when the layer does not qualify.
-static bool tc_pdl_enabled() {
-  static const int on = getenv("CM2_PDL") ? atoi(getenv("CM2_PDL")) : 1;
-  return on != 0;
-}
+static bool tc_pdl_enabled() { return pdl_enabled(); }
 // Launch with the programmatic-stream-serialisation attribute (CM2_PDL=0: plain launch; the kernels' griddepcontrol
 // instructions are no-ops then).
 template <typename K>

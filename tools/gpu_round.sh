@@ -11,3 +11,5 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r
 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
   --log-file gpurun_out/r2_ncu_step_b16.csv python bench.py --profile-step > gpurun_out/r2_ncu_step.log 2>&1; echo "[ncu-step] exit $?"
 python tools/ncu_step_summary.py gpurun_out/r2_ncu_step_b16.csv --out gpurun_out/r2_ncu_step_b16_summary.txt 2>&1 | tail -3
+# programmatic dependent launch on / off, same box
+for k in 0 1; do CM2_PDL=$k timeout 600 python bench.py --no-cpu-baseline 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('CM2_PDL=$k', d['ms_per_step'], 'ms/step', d['value'], 'img/s')"; done | tee gpurun_out/r2_pdl_ab.txt

@@ -57,7 +57,7 @@ def main():
         gbs = (a[2] + a[3]) / (a[1] * 1e-6) / 1e9 if a[1] else 0.0
         out.append("{:44s} {:6d} {:10.3f} {:6.1f}% {:10.1f} {:10.1f} {:9.0f}".format(k[:44], a[0], a[1] / 1e3, 100 * a[1] / tot,
                                                                                a[2] / 1e6, a[3] / 1e6, gbs))
-        if "conv_tc" in k or "conv_simt" in k:
+        if "conv_tc" in k or "conv_simt" in k or "stem1_fused" in k or "splitk_finish" in k:      # every launch bench.py times as a convolution
             conv_bytes += a[2] + a[3]
     txt = "\n".join(out)
     print(txt)
