@@ -1843,7 +1843,12 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   static const int env_spin = getenv("CM2_TC_SPIN") ? atoi(getenv("CM2_TC_SPIN")) : 0;
   p->spin = env_spin;
   const int m_tiles256 = (int)((rows + 255) / 256);
-  const int bn2 = pick_bn(cout_pad, m_tiles256, sms);
+  int bn2 = pick_bn(cout_pad, m_tiles256, sms);
+  // N = 16 (mod 32) layers (FCOS logits, 80 classes): one N tile padded to the next multiple of 32 makes the layer eligible for
+  // CTA pairs; the weight rows beyond cout_pad are TMA out-of-bounds zero fill, the epilogue stores co < cout only
+  static const int env_padn = getenv("CM2_TC_PAD_N") ? atoi(getenv("CM2_TC_PAD_N")) : 1;   // measured: logits 0.189 -> 0.164 ms
+  const bool padded_n = env_padn && bn2 == cout_pad && cout_pad % 32 == 16 && cout_pad >= 48 && cout_pad <= 208 && p->taps == 9 && !phase && !pred;
+  if (padded_n) bn2 += 16;
   // Measured (tools/conv_bench.py, B200, batch 16; profiles/r1_convbench_variants_b16.txt): 256-row tiles win
   //   * with the kx-merged slab while both accumulators stay double-buffered (bn <= 128) and the problem has at least
   //     two waves of tiles (small maps, e.g. OSA5 25x42, are faster on 128-row tiles);
@@ -1853,15 +1858,15 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   const bool merge_ok = p->taps == 9 && !phase;
   int k_total = 0;
   for (int i = 0; i < d->num_src; ++i) k_total += d->src[i].c;
-  const int tiles256 = m_tiles256 * (cout_pad / bn2);
+  const int tiles256 = m_tiles256 * ((cout_pad + bn2 - 1) / bn2);
   bool use_v2 = !pred && (merge_ok && bn2 <= 128 && tiles256 >= 2 * sms) || (phase && bn2 <= 128 && tiles256 >= sms) ||
                 (p->taps == 1 && k_total <= 128 && tiles256 >= sms);
   // CTA pairs (cta_group::2 MMAs, conv_tc2_kernel<.., true>): measured on the same tool (profiles/r1b_convbench_pair_b16.txt)
   // +17 % / +14 % / +10 % on the stride-1 3x3 layers with N = 128 / 160 / 192 (their single-CTA MMAs are bound by
   // shared-memory operand bandwidth); N = 256 layers and maps with fewer than ~1.5 pair tiles per cluster stay on v1.
   static const int env_pair = getenv("CM2_TC_PAIR") ? atoi(getenv("CM2_TC_PAIR")) : 1;
-  const int pair_tiles = ((m_tiles256 + 1) / 2) * (cout_pad / bn2);
-  const bool pair_ok = env_pair >= 1 && !pred && merge_ok && bn2 % 32 == 0 && bn2 <= 224 && cout_pad == bn2 &&
+  const int pair_tiles = ((m_tiles256 + 1) / 2) * ((cout_pad + bn2 - 1) / bn2);
+  const bool pair_ok = env_pair >= 1 && !pred && merge_ok && bn2 % 32 == 0 && bn2 <= 224 && (cout_pad == bn2 || padded_n) &&
                        2 * pair_tiles >= 3 * (sms / 2);
   if (pair_ok) use_v2 = true;
   if (env_variant == 1) use_v2 = false;
