@@ -13,6 +13,7 @@
 // Arithmetic identical to the two-pass path: (float(u8) - mean) / std rounded to bf16, fp32 accumulation, fma(acc, scale,
 // shift), ReLU, round to bf16.
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include <string.h>
 #include <algorithm>
 
@@ -31,21 +32,44 @@ struct StemBatch {
   int h[CM2_MAX_BATCH_PTRS], w[CM2_MAX_BATCH_PTRS];
 };
 
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+template <bool F16>
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (F16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <typename InT, bool UNIT_STD>
-__global__ void __launch_bounds__(ST_THREADS, 3) stem1_fused_kernel(StemBatch bt, int ho, int wo, float m0, float m1, float m2, float r0,
-                                                                 float r1, float r2, const __nv_bfloat16* __restrict__ w30,
-                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
-                                                                 int relu, View<__nv_bfloat16> out, int b0) {
-  __shared__ __align__(16) __nv_bfloat16 tile[ST_IR * ST_PITCH];
-  __shared__ __align__(16) unsigned char ostage[(ST_THREADS / 32) * 16 * ST_OPITCH];
-  __shared__ __align__(8) float s_sc[64], s_sh[64];
-  __shared__ __align__(16) uint2 s_b[8 * 2 * 32];
+// shared-memory carve-up (dynamic): NT tiles of 16-bit elements, the per-warp output staging, scale / shift, NT sets of B fragments
+constexpr int ST_TILE_BYTES = ST_IR * ST_PITCH * 2;
+constexpr int ST_OST_BYTES = (ST_THREADS / 32) * 16 * ST_OPITCH;
+constexpr int ST_B_BYTES = 8 * 2 * 32 * 8;
+__host__ __device__ constexpr int stem_smem_bytes(bool split) {
+  return (split ? 2 : 1) * (ST_TILE_BYTES + ST_B_BYTES) + ST_OST_BYTES + 2 * 64 * 4;
+}
+static_assert(ST_TILE_BYTES % 16 == 0 && ST_OST_BYTES % 16 == 0, "16-byte aligned regions");
+
+// SPLIT = false: bf16 engine (one bf16 tile, bf16 weights w30 [64][32], bf16 output of 64 channels).
+// SPLIT = true : fp32 engine (include/cm2.h "Split precision"): the normalised fp32 value is kept as an f16 pair hi = half(v),
+//   lo = half(v - hi) in two tiles, the weights come as W_hi / W_lo (w30 [2][64][32], pre-scaled per output channel by a power of
+//   two that `scale` undoes), acc = x_hi W_hi + x_lo W_hi + x_hi W_lo in fp32, and the result is stored as the [hi | lo] f16 operand
+//   pair of stem_2 (128 channels per pixel: hi at co, lo at 64 + co) -- no fp32 copy, no split pass.
+template <typename InT, bool UNIT_STD, bool SPLIT>
+__global__ void __launch_bounds__(ST_THREADS, SPLIT ? 2 : 3) stem1_fused_kernel(StemBatch bt, int ho, int wo, float m0, float m1, float m2,
+                                                                            float r0, float r1, float r2, const uint16_t* __restrict__ w30,
+                                                                            const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                            int relu, View<uint16_t> out, int b0) {
+  constexpr int NT = SPLIT ? 2 : 1;
+  extern __shared__ __align__(16) unsigned char st_smem[];
+  uint16_t* tile = reinterpret_cast<uint16_t*>(st_smem);                               // [NT][ST_IR * ST_PITCH]
+  unsigned char* ostage = st_smem + NT * ST_TILE_BYTES;
+  float* s_sc = reinterpret_cast<float*>(ostage + ST_OST_BYTES);
+  float* s_sh = s_sc + 64;
+  uint2* s_b = reinterpret_cast<uint2*>(s_sh + 64);                                    // [NT][8 * 2 * 32]
   const int b = blockIdx.z, oy0 = blockIdx.y * ST_TR, ox0 = blockIdx.x * ST_TC;
   const InT* __restrict__ img = reinterpret_cast<const InT*>(bt.img[b]);
   const int h = bt.h[b], w = bt.w[b];
@@ -70,38 +94,47 @@ __global__ void __launch_bounds__(ST_THREADS, 3) stem1_fused_kernel(StemBatch bt
   const bool tail_on = threadIdx.x < 2 * 3 * ST_IR;
   const bool tail_in = tail_on && tiy >= 0 && tiy < h && tix >= 0 && tix < w;
   if (tail_in) tail = __ldg(img + tc_ * plane + (size_t)tiy * w + tix);
-  auto normalise = [&](InT raw, int c, bool inside) {
+  auto put = [&](int idx, InT raw, int c, bool inside) {
     float val = 0.f;                                     // padding (conv pad and the /32 image pad) is zero AFTER normalisation
     if (inside) {
       val = (float)raw - (c == 0 ? m0 : (c == 1 ? m1 : m2));
       if (!UNIT_STD) val = val / (c == 0 ? r0 : (c == 1 ? r1 : r2));
     }
-    return __float2bfloat16_rn(val);
+    if (SPLIT) {
+      const __half hi = __float2half_rn(val);
+      const __half lo = __float2half_rn(val - __half2float(hi));
+      tile[idx] = __half_as_ushort(hi);
+      tile[ST_IR * ST_PITCH + idx] = __half_as_ushort(lo);
+    } else {
+      tile[idx] = __bfloat16_as_ushort(__float2bfloat16_rn(val));
+    }
   };
 #pragma unroll
   for (int cr = 0; cr < 3 * ST_IR; ++cr) {
     const int c = cr / ST_IR, r = cr - c * ST_IR;
     const int iy = 2 * oy0 - 1 + r;
-    tile[r * ST_PITCH + (int)threadIdx.x * 3 + c] = normalise(stage[cr], c, x_ok && iy >= 0 && iy < h);
+    put(r * ST_PITCH + (int)threadIdx.x * 3 + c, stage[cr], c, x_ok && iy >= 0 && iy < h);
   }
-  if (tail_on) tile[tr_ * ST_PITCH + tt * 3 + tc_] = normalise(tail, tc_, tail_in);
+  if (tail_on) put(tr_ * ST_PITCH + tt * 3 + tc_, tail, tc_, tail_in);
   if (threadIdx.x < ST_IR) {                             // the two spare elements of every row (read by the last pixel's k = 9)
-    tile[threadIdx.x * ST_PITCH + ST_IC * 3] = __float2bfloat16_rn(0.f);
-    tile[threadIdx.x * ST_PITCH + ST_IC * 3 + 1] = __float2bfloat16_rn(0.f);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      tile[t * ST_IR * ST_PITCH + threadIdx.x * ST_PITCH + ST_IC * 3] = 0;
+      tile[t * ST_IR * ST_PITCH + threadIdx.x * ST_PITCH + ST_IC * 3 + 1] = 0;
+    }
   }
-  // ---- per-lane constants: B fragments (all 64 output channels x K = 32), scale / shift of the lane's channels, A offsets
+  // ---- per-lane constants: scale / shift, B fragments, A offsets
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, q = lane & 3;
   if (threadIdx.x < 64) {
     s_sc[threadIdx.x] = scale ? __ldg(scale + threadIdx.x) : 1.f;
     s_sh[threadIdx.x] = shift ? __ldg(shift + threadIdx.x) : 0.f;
   }
-  // B fragments [j][s][lane] as uint2 = {(k = 16 s + 2 q, + 1), (k = 16 s + 2 q + 8, + 9)} of output channel 8 j + g: a warp reads
-  // 256 contiguous bytes per (j, s)
-#pragma unroll
-  for (int i = threadIdx.x; i < 8 * 2 * 32; i += ST_THREADS) {
-    const int l = i & 31, s2 = (i >> 5) & 1, j = i >> 6;
-    const uint32_t* wr = reinterpret_cast<const uint32_t*>(w30 + (8 * j + (l >> 2)) * 32);
+  // B fragments [set][j][s][lane] as uint2 = {(k = 16 s + 2 q, + 1), (k = 16 s + 2 q + 8, + 9)} of output channel 8 j + g: a warp
+  // reads 256 contiguous bytes per (j, s)
+  for (int i = threadIdx.x; i < NT * 8 * 2 * 32; i += ST_THREADS) {
+    const int l = i & 31, s2 = (i >> 5) & 1, j = (i >> 6) & 7, set = i >> 9;
+    const uint32_t* wr = reinterpret_cast<const uint32_t*>(w30 + set * 64 * 32 + (8 * j + (l >> 2)) * 32);
     s_b[i] = make_uint2(__ldg(wr + 8 * s2 + (l & 3)), __ldg(wr + 8 * s2 + (l & 3) + 4));
   }
   int aoff[4];                                           // element offsets of the operand pairs p = q, q + 4, q + 8, q + 12
@@ -120,47 +153,114 @@ __global__ void __launch_bounds__(ST_THREADS, 3) stem1_fused_kernel(StemBatch bt
     const int r = gi / (ST_TC / 16), cg = gi - r * (ST_TC / 16);
     const int oy = oy0 + r, oxg = ox0 + cg * 16;
     if (oy >= ho || oxg >= wo) continue;                 // warp-uniform
-    const __nv_bfloat16* arow = tile + (2 * r) * ST_PITCH + (cg * 16 + g) * 6;
-    uint32_t a[2][4];
+    uint32_t a[NT][2][4];
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      a[s][0] = *reinterpret_cast<const uint32_t*>(arow + aoff[2 * s]);            // row g,     k = 16 s + 2 q
-      a[s][1] = *reinterpret_cast<const uint32_t*>(arow + 48 + aoff[2 * s]);       // row g + 8 (8 pixels = 48 elements on)
-      a[s][2] = *reinterpret_cast<const uint32_t*>(arow + aoff[2 * s + 1]);        // row g,     k = 16 s + 2 q + 8
-      a[s][3] = *reinterpret_cast<const uint32_t*>(arow + 48 + aoff[2 * s + 1]);   // row g + 8
+    for (int t = 0; t < NT; ++t) {
+      const uint16_t* arow = tile + t * ST_IR * ST_PITCH + (2 * r) * ST_PITCH + (cg * 16 + g) * 6;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        a[t][s][0] = *reinterpret_cast<const uint32_t*>(arow + aoff[2 * s]);            // row g,     k = 16 s + 2 q
+        a[t][s][1] = *reinterpret_cast<const uint32_t*>(arow + 48 + aoff[2 * s]);       // row g + 8 (8 pixels = 48 elements on)
+        a[t][s][2] = *reinterpret_cast<const uint32_t*>(arow + aoff[2 * s + 1]);        // row g,     k = 16 s + 2 q + 8
+        a[t][s][3] = *reinterpret_cast<const uint32_t*>(arow + 48 + aoff[2 * s + 1]);   // row g + 8
+      }
     }
     float acc[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
       const uint2 b0 = s_b[(2 * j) * 32 + lane], b1 = s_b[(2 * j + 1) * 32 + lane];
-      mma_bf16_16816(acc[j], a[0], b0.x, b0.y);
-      mma_bf16_16816(acc[j], a[1], b1.x, b1.y);
+      if (SPLIT) {
+        // cross terms first (2^-11 of the main term), then the main term: x_lo W_hi + x_hi W_lo + x_hi W_hi
+        const uint2 l0 = s_b[512 + (2 * j) * 32 + lane], l1 = s_b[512 + (2 * j + 1) * 32 + lane];
+        mma_16816<true>(acc[j], a[NT - 1][0], b0.x, b0.y);
+        mma_16816<true>(acc[j], a[NT - 1][1], b1.x, b1.y);
+        mma_16816<true>(acc[j], a[0][0], l0.x, l0.y);
+        mma_16816<true>(acc[j], a[0][1], l1.x, l1.y);
+      }
+      mma_16816<SPLIT>(acc[j], a[0][0], b0.x, b0.y);
+      mma_16816<SPLIT>(acc[j], a[0][1], b1.x, b1.y);
     }
-    // epilogue: scale / shift / ReLU / bf16, staged so that the warp writes its 16 pixels x 128 bytes as 16-byte pieces
-    __syncwarp();
+    // epilogue: scale / shift / ReLU, staged so that the warp writes 16 pixels x 128 bytes as 16-byte pieces (two rounds for the
+    // [hi | lo] pair)
+    uint16_t* orow = out.at(b0 + b, oy, oxg);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float2 sc = *reinterpret_cast<const float2*>(s_sc + 8 * j + 2 * q), sh = *reinterpret_cast<const float2*>(s_sh + 8 * j + 2 * q);
-      const float v0 = fmaxf(fmaf(acc[j][0], sc.x, sh.x), floor_v), v1 = fmaxf(fmaf(acc[j][1], sc.y, sh.y), floor_v);
-      const float v2 = fmaxf(fmaf(acc[j][2], sc.x, sh.x), floor_v), v3 = fmaxf(fmaf(acc[j][3], sc.y, sh.y), floor_v);
-      const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(ost + (uint32_t)g * ST_OPITCH + 16u * j + 4u * q),
-                   "r"(*reinterpret_cast<const uint32_t*>(&lo)) : "memory");
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(ost + (uint32_t)(g + 8) * ST_OPITCH + 16u * j + 4u * q),
-                   "r"(*reinterpret_cast<const uint32_t*>(&hi)) : "memory");
-    }
-    __syncwarp();
-    __nv_bfloat16* orow = out.at(b0 + b, oy, oxg);
+    for (int round = 0; round < NT; ++round) {
+      __syncwarp();
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int px = it * 4 + (lane >> 3), chunk = lane & 7;
-      uint4 v;
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                   : "r"(ost + (uint32_t)px * ST_OPITCH + 16u * chunk) : "memory");
-      if (oxg + px < wo) *reinterpret_cast<uint4*>(orow + (long long)px * out.sw + chunk * 8) = v;
+      for (int j = 0; j < 8; ++j) {
+        const float2 sc = *reinterpret_cast<const float2*>(s_sc + 8 * j + 2 * q), sh = *reinterpret_cast<const float2*>(s_sh + 8 * j + 2 * q);
+        const float v0 = fmaxf(fmaf(acc[j][0], sc.x, sh.x), floor_v), v1 = fmaxf(fmaf(acc[j][1], sc.y, sh.y), floor_v);
+        const float v2 = fmaxf(fmaf(acc[j][2], sc.x, sh.x), floor_v), v3 = fmaxf(fmaf(acc[j][3], sc.y, sh.y), floor_v);
+        uint32_t w01, w23;
+        if (SPLIT) {
+          const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+          if (round == 0) {
+            w01 = *reinterpret_cast<const uint32_t*>(&h01); w23 = *reinterpret_cast<const uint32_t*>(&h23);
+          } else {
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y), l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
+            w01 = *reinterpret_cast<const uint32_t*>(&l01); w23 = *reinterpret_cast<const uint32_t*>(&l23);
+          }
+        } else {
+          const __nv_bfloat162 p01 = __floats2bfloat162_rn(v0, v1), p23 = __floats2bfloat162_rn(v2, v3);
+          w01 = *reinterpret_cast<const uint32_t*>(&p01); w23 = *reinterpret_cast<const uint32_t*>(&p23);
+        }
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(ost + (uint32_t)g * ST_OPITCH + 16u * j + 4u * q), "r"(w01) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(ost + (uint32_t)(g + 8) * ST_OPITCH + 16u * j + 4u * q), "r"(w23) : "memory");
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int px = it * 4 + (lane >> 3), chunk = lane & 7;
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "r"(ost + (uint32_t)px * ST_OPITCH + 16u * chunk) : "memory");
+        if (oxg + px < wo) *reinterpret_cast<uint4*>(orow + (long long)px * out.sw + round * 64 + chunk * 8) = v;
+      }
     }
   }
+}
+
+template <bool SPLIT>
+static int stem_launch(const void* const* imgs, const int32_t* hs, const int32_t* ws, int32_t n, int32_t in_dtype, int32_t hp, int32_t wp,
+                       const float* mean3, const float* std3, const void* w30, const float* scale, const float* shift, int32_t relu,
+                       const cm2_act* out, int32_t out_index0, void* stream, const char* who) {
+  CM2_CHECK_ARG(imgs && hs && ws && out && out->data && mean3 && std3 && w30, "%s: null pointer", who);
+  CM2_CHECK_ARG(n >= 0 && hp > 0 && wp > 0 && hp % 2 == 0 && wp % 2 == 0, "%s: bad extents", who);
+  constexpr int OC = SPLIT ? 128 : 64;
+  CM2_CHECK_ARG(out->h == hp / 2 && out->w == wp / 2 && out->c == OC && out_index0 >= 0 && out_index0 + n <= out->n &&
+                vec8_ok(*out, 2), "%s: out view [%d,%d,%d,%d] != [>=%d,%d,%d,%d]", who, out->n, out->h, out->w,
+                out->c, out_index0 + n, hp / 2, wp / 2, OC);
+  CM2_CHECK_ARG(in_dtype == CM2_F32 || in_dtype == CM2_U8, "%s: unsupported input dtype %d", who, in_dtype);
+  CM2_CHECK_ARG((reinterpret_cast<uintptr_t>(w30) & 3) == 0, "%s: weights not 4-byte aligned", who);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool unit = std3[0] == 1.f && std3[1] == 1.f && std3[2] == 1.f;
+  const uint16_t* wq = reinterpret_cast<const uint16_t*>(w30);
+  constexpr int smem = stem_smem_bytes(SPLIT);
+  CM2_ENSURE_DYN_SMEM((stem1_fused_kernel<float, true, SPLIT>), smem, who);
+  CM2_ENSURE_DYN_SMEM((stem1_fused_kernel<float, false, SPLIT>), smem, who);
+  CM2_ENSURE_DYN_SMEM((stem1_fused_kernel<uint8_t, true, SPLIT>), smem, who);
+  CM2_ENSURE_DYN_SMEM((stem1_fused_kernel<uint8_t, false, SPLIT>), smem, who);
+  for (int i0 = 0; i0 < n; i0 += CM2_MAX_BATCH_PTRS) {
+    const int nb = std::min(n - i0, (int)CM2_MAX_BATCH_PTRS);
+    StemBatch bt;
+    memset(&bt, 0, sizeof(bt));
+    for (int i = 0; i < nb; ++i) {
+      CM2_CHECK_ARG(imgs[i0 + i] && hs[i0 + i] > 0 && ws[i0 + i] > 0 && hs[i0 + i] <= hp && ws[i0 + i] <= wp,
+                    "%s: image %d is %dx%d, padded extent %dx%d", who, i0 + i, hs[i0 + i], ws[i0 + i], hp, wp);
+      bt.img[i] = imgs[i0 + i]; bt.h[i] = hs[i0 + i]; bt.w[i] = ws[i0 + i];
+    }
+    dim3 grid(ceil_div(out->w, ST_TC), ceil_div(out->h, ST_TR), nb);
+    View<uint16_t> ov = make_view<uint16_t>(*out);
+#define CM2_STEM(T, U) stem1_fused_kernel<T, U, SPLIT><<<grid, ST_THREADS, smem, s>>>(bt, out->h, out->w, mean3[0], mean3[1], mean3[2], std3[0], \
+                                                                                      std3[1], std3[2], wq, scale, shift, relu, ov, out_index0 + i0)
+    if (in_dtype == CM2_F32) { if (unit) CM2_STEM(float, true); else CM2_STEM(float, false); }
+    else { if (unit) CM2_STEM(uint8_t, true); else CM2_STEM(uint8_t, false); }
+#undef CM2_STEM
+    CM2_CHECK_LAUNCH(who);
+  }
+  return CM2_OK;
 }
 
 }  // namespace cm2
@@ -169,34 +269,14 @@ extern "C" int cm2_stem1_fused_batch(const void* const* imgs, const int32_t* hs,
                                      int32_t hp, int32_t wp, const float* mean3, const float* std3, const void* w30,
                                      const float* scale, const float* shift, int32_t relu, const cm2_act* out,
                                      int32_t out_index0, void* stream) {
-  using namespace cm2;
-  CM2_CHECK_ARG(imgs && hs && ws && out && out->data && mean3 && std3 && w30, "stem1_fused_batch: null pointer");
-  CM2_CHECK_ARG(n >= 0 && hp > 0 && wp > 0 && hp % 2 == 0 && wp % 2 == 0, "stem1_fused_batch: bad extents");
-  CM2_CHECK_ARG(out->h == hp / 2 && out->w == wp / 2 && out->c == 64 && out_index0 >= 0 && out_index0 + n <= out->n &&
-                vec8_ok(*out, 2), "stem1_fused_batch: out view [%d,%d,%d,%d] != [>=%d,%d,%d,64]", out->n, out->h, out->w,
-                out->c, out_index0 + n, hp / 2, wp / 2);
-  CM2_CHECK_ARG(in_dtype == CM2_F32 || in_dtype == CM2_U8, "stem1_fused_batch: unsupported input dtype %d", in_dtype);
-  CM2_CHECK_ARG((reinterpret_cast<uintptr_t>(w30) & 3) == 0, "stem1_fused_batch: weights not 4-byte aligned");
-  cudaStream_t s = (cudaStream_t)stream;
-  const bool unit = std3[0] == 1.f && std3[1] == 1.f && std3[2] == 1.f;
-  const __nv_bfloat16* wq = reinterpret_cast<const __nv_bfloat16*>(w30);
-  for (int i0 = 0; i0 < n; i0 += CM2_MAX_BATCH_PTRS) {
-    const int nb = std::min(n - i0, (int)CM2_MAX_BATCH_PTRS);
-    StemBatch bt;
-    memset(&bt, 0, sizeof(bt));
-    for (int i = 0; i < nb; ++i) {
-      CM2_CHECK_ARG(imgs[i0 + i] && hs[i0 + i] > 0 && ws[i0 + i] > 0 && hs[i0 + i] <= hp && ws[i0 + i] <= wp,
-                    "stem1_fused_batch: image %d is %dx%d, padded extent %dx%d", i0 + i, hs[i0 + i], ws[i0 + i], hp, wp);
-      bt.img[i] = imgs[i0 + i]; bt.h[i] = hs[i0 + i]; bt.w[i] = ws[i0 + i];
-    }
-    dim3 grid(ceil_div(out->w, ST_TC), ceil_div(out->h, ST_TR), nb);
-    View<__nv_bfloat16> ov = make_view<__nv_bfloat16>(*out);
-#define CM2_STEM(T, U) stem1_fused_kernel<T, U><<<grid, ST_THREADS, 0, s>>>(bt, out->h, out->w, mean3[0], mean3[1], mean3[2], std3[0], \
-                                                                             std3[1], std3[2], wq, scale, shift, relu, ov, out_index0 + i0)
-    if (in_dtype == CM2_F32) { if (unit) CM2_STEM(float, true); else CM2_STEM(float, false); }
-    else { if (unit) CM2_STEM(uint8_t, true); else CM2_STEM(uint8_t, false); }
-#undef CM2_STEM
-    CM2_CHECK_LAUNCH("stem1_fused");
-  }
-  return CM2_OK;
+  return cm2::stem_launch<false>(imgs, hs, ws, n, in_dtype, hp, wp, mean3, std3, w30, scale, shift, relu, out, out_index0, stream,
+                                 "stem1_fused_batch");
+}
+
+extern "C" int cm2_stem1_fused_split_batch(const void* const* imgs, const int32_t* hs, const int32_t* ws, int32_t n, int32_t in_dtype,
+                                           int32_t hp, int32_t wp, const float* mean3, const float* std3, const void* w30_hi_lo,
+                                           const float* scale, const float* shift, int32_t relu, const cm2_act* out_split,
+                                           int32_t out_index0, void* stream) {
+  return cm2::stem_launch<true>(imgs, hs, ws, n, in_dtype, hp, wp, mean3, std3, w30_hi_lo, scale, shift, relu, out_split, out_index0,
+                                stream, "stem1_fused_split_batch");
 }

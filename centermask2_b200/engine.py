@@ -457,6 +457,20 @@ class Engine(object):
             else:
                 P["stem"].append(packing.conv_bn_relu(sd, k, [cin], s, 1, dt, dev, tc))
             cin = c
+        if tc and self.split and sd[prefix + "bottom_up.stem.stem_1/conv.weight"].shape[0] == 64:
+            # fp32 engine: fused stem on f16 hi / lo fragments (csrc/stem.cu, SPLIT): weights pre-scaled per output channel by a
+            # power of two (far from the half subnormals), undone exactly by the epilogue scale -- as packing.ConvW does
+            k1 = prefix + "bottom_up.stem.stem_1"
+            w1 = sd[k1 + "/conv.weight"].detach().float()
+            sc, sh = packing.fold_frozen_bn(sd[k1 + "/norm.weight"], sd[k1 + "/norm.bias"], sd[k1 + "/norm.running_mean"],
+                                            sd[k1 + "/norm.running_var"])
+            w30 = torch.zeros((64, 32))
+            w30[:, :30] = torch.nn.functional.pad(w1.permute(0, 2, 3, 1).reshape(64, 3, 9), (0, 1)).reshape(64, 30)
+            pre = torch.exp2(torch.floor(torch.log2(256.0 / w30.abs().amax(dim=1).clamp(min=1e-30)))).clamp(max=2.0 ** 40)
+            ws = w30 * pre.view(-1, 1)
+            hi = ws.to(torch.float16)
+            lo = (ws - hi.float()).to(torch.float16)
+            P["stem1_fused"] = (torch.stack([hi, lo]).to(dev).contiguous(), (sc.float() / pre).to(dev).contiguous(), sh.float().to(dev).contiguous())
         if tc and not self.split:
             # stem_1 as a 1x1 conv over the fused normalise+im2col input (cm2_preprocess_im2col): K = 27 -> 32
             k1 = prefix + "bottom_up.stem.stem_1"
@@ -959,11 +973,12 @@ class Engine(object):
         wp = max(s[1] for s in sizes)
         hp = (hp + size_divisibility - 1) // size_divisibility * size_divisibility
         wp = (wp + size_divisibility - 1) // size_divisibility * size_divisibility
-        if self.tc and not self.split and fused_stem and len(cfg.MODEL.PIXEL_MEAN) == 3:
+        if self.tc and fused_stem and len(cfg.MODEL.PIXEL_MEAN) == 3:
             if self.stem_variant >= 1 and len({im.dtype for im in images}) == 1 and images[0].dtype in (torch.uint8, torch.float32):
                 # normalise + pad + stem_1 in ONE pass (run_backbone -> stem1_fused): nothing to do here
                 return RawInput([im.contiguous() for im in images], hp, wp), sizes
-            return self._im2col(images, hp, wp), sizes
+            if not self.split:
+                return self._im2col(images, hp, wp), sizes
         x = self.fmap("input", len(images), hp, wp, 3)
         for i, im in enumerate(images):
             lib.preprocess_image(im.contiguous(), cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD, x.view, i)
@@ -983,10 +998,19 @@ class Engine(object):
     def stem1_fused(self, name, raw, P):
         """stem_1 straight from the raw images (csrc/stem.cu); falls back to im2col + 1x1 GEMM when the packed fused weights
         do not exist (stem_1 with other than 64 output channels)."""
-        if "stem1_fused" not in P:
+        if "stem1_fused" not in P or (self.split and isinstance(P["stem"][1], tuple)):
+            if self.split:                                    # fp32 engine, stem_1 with other than 64 channels or a depthwise stem_2
+                                                              # (reads fp32, not the [hi | lo] pair): the unfused path
+                x = self.fmap("input", raw.n, raw.hp, raw.wp, 3)
+                for i, im in enumerate(raw.images):
+                    lib.preprocess_image(im, self.cfg.MODEL.PIXEL_MEAN, self.cfg.MODEL.PIXEL_STD, x.view, i)
+                return self.conv(name, [x], P["stem"][0])
             return self.conv(name, [self._im2col(raw.images, raw.hp, raw.wp)], P["stem1_im2col"])
         w30, scale, shift = P["stem1_fused"]
-        out = self.fmap(name, raw.n, raw.hp // 2, raw.wp // 2, 64)
+        if self.split:
+            out = SplitFMap(self.buffer(name, (raw.n, raw.hp // 2 + 2, raw.wp // 2 + 2, 128), torch.float16), 1)
+        else:
+            out = self.fmap(name, raw.n, raw.hp // 2, raw.wp // 2, 64)
         lib.stem1_fused_batch(raw.images, self.cfg.MODEL.PIXEL_MEAN, self.cfg.MODEL.PIXEL_STD, raw.hp, raw.wp, w30, scale, shift, True, out.view)
         return out
 

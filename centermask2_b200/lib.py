@@ -70,6 +70,8 @@ SYMBOLS = {
     "cm2_preprocess_im2col": (_I, [_P, _I, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _AP, _I, _P]),
     "cm2_stem1_fused_batch": (_I, [C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _P, _P, _P, _I,
                                     _AP, _I, _P]),
+    "cm2_stem1_fused_split_batch": (_I, [C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _P, _P, _P,
+                                          _I, _AP, _I, _P]),
     "cm2_preprocess_im2col_batch": (_I, [C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _AP,
                                          _I, _P]),
     "cm2_resize_pil_u8": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _I, _P]),
@@ -273,15 +275,20 @@ def preprocess_im2col_batch(imgs, mean, std, hp, wp, out, index0=0):
 def stem1_fused_batch(imgs, mean, std, hp, wp, w30, scale, shift, relu, out, index0=0):
     """normalise + pad + stem_1 (3x3 / s2, 3 -> 64) + scale / shift + ReLU of all images in one pass (csrc/stem.cu)."""
     n = len(imgs)
-    assert w30.dtype == torch.bfloat16 and tuple(w30.shape) == (64, 32) and w30.is_contiguous() and out.dtype == torch.bfloat16
+    split = w30.dtype == torch.float16
+    if split:        # fp32 engine: W_hi / W_lo, output = the [hi | lo] f16 operand pair of stem_2
+        assert tuple(w30.shape) == (2, 64, 32) and w30.is_contiguous() and out.dtype == torch.float16 and out.shape[3] == 128
+    else:
+        assert w30.dtype == torch.bfloat16 and tuple(w30.shape) == (64, 32) and w30.is_contiguous() and out.dtype == torch.bfloat16
     ptrs = (_P * n)(*[im.data_ptr() for im in imgs])
     hs = (_I * n)(*[im.shape[1] for im in imgs])
     ws = (_I * n)(*[im.shape[2] for im in imgs])
     m = (C.c_float * 3)(*mean)
     s = (C.c_float * 3)(*std)
     a = act(out)
-    check(load().cm2_stem1_fused_batch(ptrs, hs, ws, n, dtype_code(imgs[0]), hp, wp, m, s, ptr(w30), ptr(scale), ptr(shift), int(relu),
-                                       C.byref(a), index0, stream()), "cm2_stem1_fused_batch")
+    fn = load().cm2_stem1_fused_split_batch if split else load().cm2_stem1_fused_batch
+    check(fn(ptrs, hs, ws, n, dtype_code(imgs[0]), hp, wp, m, s, ptr(w30), ptr(scale), ptr(shift), int(relu), C.byref(a), index0, stream()),
+          "cm2_stem1_fused_split_batch" if split else "cm2_stem1_fused_batch")
     _count((n + 31) // 32)
 
 

@@ -212,6 +212,15 @@ int cm2_stem1_fused_batch(const void* const* imgs, const int32_t* hs, const int3
                           const float* scale, const float* shift, int32_t relu, const cm2_act* out, int32_t out_index0,
                           void* stream);
 
+/* The same for the fp32 engine ("Split precision" above): the normalised fp32 input is split into an f16 pair inside the kernel,
+ * w30_hi_lo is device f16 [2][64][32] = W_hi, W_lo of s * W (s a per-channel power of two; scale = folded BN scale / s), and the
+ * result is written as the [hi | lo] f16 operand pair of stem_2: out_split is an f16 view [>= out_index0 + n, hp/2, wp/2, 128]
+ * (hi at channel co, lo at 64 + co). */
+int cm2_stem1_fused_split_batch(const void* const* imgs, const int32_t* hs, const int32_t* ws, int32_t n, int32_t in_dtype,
+                                int32_t hp, int32_t wp, const float* mean3, const float* std3, const void* w30_hi_lo,
+                                const float* scale, const float* shift, int32_t relu, const cm2_act* out_split,
+                                int32_t out_index0, void* stream);
+
 /* Depthwise 3x3 convolution, padding 1, stride 1 or 2, no bias: the "dw_conv3x3" half of the depthwise bodies'
  * units (vovnet.py:110-130, Conv2d(c, c, 3, groups=c)); the pointwise 1x1 + FrozenBN + ReLU that follows is a
  * cm2_conv_nhwc call.  w: device fp32 [9][c] (tap-major: w[(ky*3+kx)*c + ch] = weight[ch][0][ky][kx]).

@@ -382,6 +382,45 @@ def test_stem1_fused_matches_conv_and_the_im2col_path(std):
 
 
 @pytest.mark.parametrize("std", [[1.0, 1.0, 1.0], [57.375, 57.12, 58.395]])
+def test_stem1_fused_split_precision_matches_fp32_conv(std):
+    """cm2_stem1_fused_split_batch (fp32 engine): f16 hi / lo fragments of the normalised input and of the weights, result
+    stored as the [hi | lo] operand pair of stem_2 -- hi + lo against F.conv2d in float64 on the exact fp32 inputs."""
+    g = torch.Generator().manual_seed(15)
+    hp, wp = 96, 608
+    mean = [103.53, 116.28, 123.675]
+    extents = ((45, 61), (96, 608), (33, 599))
+    imgs = [(torch.rand(3, h, w, generator=g) * 255).floor().to(torch.uint8) for h, w in extents]
+    w1 = torch.randn(64, 3, 3, 3, generator=g) / 5
+    w1[5] *= 1e-3                                             # a channel with tiny weights: the per-channel pre-scale matters
+    sc, sh = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.2
+    xn = torch.zeros(len(imgs), 3, hp, wp, dtype=torch.float64)
+    for i, (im, (h, w)) in enumerate(zip(imgs, extents)):
+        v = im.float() - torch.tensor(mean).view(3, 1, 1)
+        if std[0] != 1.0:
+            v = v / torch.tensor(std).view(3, 1, 1)
+        xn[i, :, :h, :w] = v.double()
+    ref = torch.relu(F.conv2d(xn, w1.double(), None, 2, 1) * sc.double().view(1, -1, 1, 1) + sh.double().view(1, -1, 1, 1))
+    w30 = torch.zeros(64, 32)
+    w30[:, :30] = F.pad(w1.permute(0, 2, 3, 1).reshape(64, 3, 9), (0, 1)).reshape(64, 30)
+    pre = torch.exp2(torch.floor(torch.log2(256.0 / w30.abs().amax(dim=1))))
+    ws = w30 * pre.view(-1, 1)
+    hi = ws.to(torch.float16)
+    lo = (ws - hi.float()).to(torch.float16)
+    whl = torch.stack([hi, lo]).to(DEV).contiguous()
+    scale_tc = (sc / pre).to(DEV).contiguous()
+    for conv_in in ([im.to(DEV) for im in imgs], [im.float().to(DEV) for im in imgs]):
+        buf = torch.zeros((len(imgs) + 1, hp // 2 + 2, wp // 2 + 2, 128), dtype=torch.float16, device=DEV)
+        lib.stem1_fused_batch(conv_in, mean, std, hp, wp, whl, scale_tc, sh.to(DEV), True, buf[:, 1:-1, 1:-1, :], 1)
+        torch.cuda.synchronize()
+        got = (buf[:, 1:-1, 1:-1, :64].double() + buf[:, 1:-1, 1:-1, 64:].double()).permute(0, 3, 1, 2).cpu()
+        err = (got[1:] - ref).abs().max().item()
+        assert err <= 3e-6 * ref.abs().max().item(), (err, ref.abs().max().item())
+        assert got[0].abs().max() == 0
+        b = buf.float()
+        assert b[:, 0].abs().max() == 0 and b[:, -1].abs().max() == 0 and b[:, :, 0].abs().max() == 0 and b[:, :, -1].abs().max() == 0
+
+
+@pytest.mark.parametrize("std", [[1.0, 1.0, 1.0], [57.375, 57.12, 58.395]])
 def test_preprocess_im2col_batch_equals_per_image(std):
     """One launch for the whole batch (images of different extents) == the per-image entry point, bit for bit."""
     g = torch.Generator().manual_seed(13)

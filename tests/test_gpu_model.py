@@ -135,9 +135,10 @@ def test_registry_level_modules_compose_like_the_reference(case):
         for k in fa:
             # ``inference`` runs the FCOS towers as one segmented launch over all levels, the module-level call one launch
             # per level: other tile shapes, another accumulation order (~1e-6 relative per layer, amplified by the layers
-            # behind it); mask probabilities and mask scores see the whole ROI stage on top
+            # behind it); mask probabilities and mask scores see the whole ROI stage on top.  The module-level backbone also takes
+            # the NORMALISED tensor (stem_1 as an ordinary convolution), ``inference`` the raw images (fused stem, csrc/stem.cu)
             big = fb[k].float().abs().max().item() if fb[k].numel() else 0.0
-            tol = 2e-4 * max(1.0, big) if k in ("pred_masks", "mask_scores") else 1e-5
+            tol = 1e-3 * max(1.0, big) if k in ("pred_masks", "mask_scores") else 5e-6 * max(10.0, big)   # 1e-3: the north-star probability tolerance
             assert torch.allclose(fa[k].float(), fb[k].float(), atol=tol), k
 
 
@@ -152,8 +153,9 @@ def test_layerwise_against_oracle_trace():
     model = cm.build_model(cfg)
     model.load_state_dict(sd)
     eng = runtime.engine_for(cfg)
-    x, sizes = eng.preprocess([b["image"].cuda() for b in inputs])
+    x, sizes = eng.preprocess([b["image"].cuda() for b in inputs], fused_stem=False)
     assert torch.allclose(x.view.permute(0, 3, 1, 2).cpu(), tr["image"], atol=1e-4)
+    x, sizes = eng.preprocess([b["image"].cuda() for b in inputs])         # the product path: raw images -> fused stem
     feats = model.backbone.forward_fmap(x)
     fcos = model.proposal_generator
     eng2, P = fcos._pack()
