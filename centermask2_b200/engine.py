@@ -886,9 +886,9 @@ class Engine(object):
             last = k + 1 == nconv
             srcs = [roi, pm] if k == 0 else [y]
             # the last conv is stride 2: on the TC engine its producer stores phase planes
-            to_phase = self.tc and k + 2 == nconv and k > 0
-            # the stride-2 conv reads phase planes on the TC engine; when its producer cannot write them (k == 0: the concat
-            # input) it runs on the CUDA-core engine, which needs the fp32 map
+            # (also when the producer is the first conv over the [roi, mask] concat: NUM_CONV 2 of the Lite recipe -- its
+            # stride-2 conv used to fall back to the CUDA-core engine, 0.40 of the 2.0 ms Lite step)
+            to_phase = self.tc and k + 2 == nconv
             y = self.conv("iou_fcn{}".format(k + 1), srcs, w, out_halo=0 if last else 1, out_mode=2 if to_phase else 0,
                           to_conv=not last and (to_phase or k + 2 < nconv))
         flat = FMap(y.buf.reshape(R, 1, 1, -1), 0)
