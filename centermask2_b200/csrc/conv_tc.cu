@@ -630,6 +630,8 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
   constexpr int esize = F32 ? 4 : 2;
   constexpr int cpp = F32 ? 16 : 32;                 // channels per pass = 64 bytes per row
   const float relu_floor = p.relu ? 0.f : -INFINITY;
+  uint64_t keep_policy = 0;
+  if (STATS) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
   const uint32_t my_row = stage_smem + (uint32_t)lane * EPI_PITCH;
   // write-back role of this lane: rows it*8 + lane/4, 16-byte piece lane%4 -- row addresses are fixed for the tile
   char* wptr[4];
@@ -791,7 +793,16 @@ __device__ __forceinline__ void tc_epilogue_rows_staged(const TcParams& p, const
       uint4 val;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
                    : "r"(wsm[it]) : "memory");
-      if (wok[it] && piece_ok) *reinterpret_cast<uint4*>(wptr[it] + col_bytes) = val;
+      if (wok[it] && piece_ok) {
+        if (STATS) {
+          // outputs whose statistics are taken here are read next by a bandwidth-bound pass (GroupNorm apply / eSE apply) that
+          // walks the tensor back to front: ask the L2 to keep these lines (evict_last) rather than the operand tiles streaming by
+          asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(wptr[it] + col_bytes), "r"(val.x), "r"(val.y),
+                       "r"(val.z), "r"(val.w), "l"(keep_policy) : "memory");
+        } else {
+          *reinterpret_cast<uint4*>(wptr[it] + col_bytes) = val;
+        }
+      }
     }
   }
   __syncwarp();

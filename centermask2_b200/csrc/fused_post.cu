@@ -162,7 +162,10 @@ struct GnLineSegs {
 __global__ void __launch_bounds__(256) gn_seg_apply_lines_kernel(__nv_bfloat16* __restrict__ x, int c, int cpg, GnLineSegs g,
                                                                  const double* __restrict__ stats, const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, float eps, int relu) {
-  const int line = blockIdx.x;
+  // CTAs walk the tensor BACKWARDS: the convolution that produced it wrote it front to back, so its tail is what the 126 MB L2
+  // still holds; read back to front, that part never comes from DRAM, and the front -- written last here -- is in L2 when the
+  // next convolution starts reading front to back (measured: see DESIGN.md section 3, round 2)
+  const int line = (int)(gridDim.x - 1 - blockIdx.x);
   int s = 0;
 #pragma unroll
   for (int j = 1; j < CM2_MAX_SEG; ++j)
@@ -224,7 +227,10 @@ __global__ void __launch_bounds__(256) gn_seg_apply_split_lines_kernel(const flo
                                                                        GnLineSegs g, const double* __restrict__ stats,
                                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                        float eps, int relu) {
-  const int line = blockIdx.x;
+  // CTAs walk the tensor BACKWARDS: the convolution that produced it wrote it front to back, so its tail is what the 126 MB L2
+  // still holds; read back to front, that part never comes from DRAM, and the front -- written last here -- is in L2 when the
+  // next convolution starts reading front to back (measured: see DESIGN.md section 3, round 2)
+  const int line = (int)(gridDim.x - 1 - blockIdx.x);
   int s = 0;
 #pragma unroll
   for (int j = 1; j < CM2_MAX_SEG; ++j)
@@ -392,7 +398,7 @@ template <bool IDN, bool FULL>
 __global__ void __launch_bounds__(256) ese_apply_pool_lines_kernel(View<const __nv_bfloat16> x, const float* __restrict__ gate,
                                                                    View<const __nv_bfloat16> idn, View<__nv_bfloat16> full,
                                                                    View<__nv_bfloat16> pool) {
-  const int b = blockIdx.y, oy = blockIdx.x;
+  const int b = (int)(gridDim.y - 1 - blockIdx.y), oy = (int)(gridDim.x - 1 - blockIdx.x);     // back to front (L2, see gn_seg_apply_lines_kernel)
   const int c8 = x.c >> 3;
   const int cv = threadIdx.x % c8, o0 = threadIdx.x / c8, ostep = blockDim.x / c8;
   float gt[8];
@@ -476,7 +482,8 @@ __global__ void __launch_bounds__(256) ese_apply_flat_kernel(const T* __restrict
                                                              const T* __restrict__ idn, T* __restrict__ out, int c, int plane,
                                                              long long total8) {
   const unsigned c8 = (unsigned)c >> 3;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total8; i += gridDim.x * blockDim.x) {
+  for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < (unsigned)total8; j += gridDim.x * blockDim.x) {
+    const unsigned i = (unsigned)total8 - 1u - j;                      // back to front (L2, see gn_seg_apply_lines_kernel)
     const int cv = (int)(i % c8);
     const unsigned row = i / c8;
     const int b = (int)(row / (unsigned)plane);
