@@ -1705,6 +1705,17 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
 static bool is_halo_view(const cm2_act& a, bool slice_ok = false) {
   return (slice_ok ? a.sw >= a.c : a.sw == a.c) && a.sh == (long long)(a.w + 2) * a.sw && a.sn == (long long)(a.h + 2) * a.sh;
 }
+// Halo kinds of an interior view: 1 = every image carries its own one-pixel zero frame ([n, h+2, w+2, c] buffer); 2 = SHARED
+// halo: line pitch w + 1 and image pitch (h + 1)(w + 1) pixels -- the zero pixel right of a line is the zero pixel left of the
+// next line, the zero line under an image the zero line above the next image (the buffer ends with one more zero line + pixel;
+// reads past it are TMA out-of-bounds zero fill).  A 3x3 tap is the same flat row shift (ky - 1) * pitch + (kx - 1) in both; for
+// the 14x14 ROI maps the shared form has 225 GEMM rows per ROI instead of 256 (196 of them interior).
+static int halo_kind(const cm2_act& a, bool slice_ok = false) {
+  if (!(slice_ok ? a.sw >= a.c : a.sw == a.c)) return 0;
+  if (a.sh == (long long)(a.w + 2) * a.sw && a.sn == (long long)(a.h + 2) * a.sh) return 1;
+  if (a.sh == (long long)(a.w + 1) * a.sw && a.sn == (long long)(a.h + 1) * a.sh) return 2;
+  return 0;
+}
 static bool is_dense_view(const cm2_act& a, bool slice_ok = false) {
   return (slice_ok ? a.sw >= a.c : a.sw == a.c) && a.sh == (long long)a.w * a.sw && a.sn == (long long)a.h * a.sh;
 }
@@ -1762,13 +1773,15 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   if (seg)
     TC_REQUIRE(d->num_seg <= CM2_MAX_SEG && !phase && d->out_mode == 0 && !d->residual.data,
                "conv_tc: segmented tensors need stride 1, out_mode 0, no residual");
-  const bool halo = seg || is_halo_view(s0, true);
+  const int hk = seg ? 1 : halo_kind(s0, true);
+  const bool halo = hk != 0;
   TC_REQUIRE(halo || (d->kh == 1 && is_dense_view(s0, true)), "conv_tc: source 0 is neither a halo-1 view nor (for 1x1) dense");
+  TC_REQUIRE(hk != 2 || (!phase && d->out_mode != 3 && !f16), "conv_tc: shared-halo views take bf16 stride-1 convolutions without the fused predictor");
   for (int i = 0; i < d->num_src; ++i) {
     const cm2_act& s = d->src[i];
     TC_REQUIRE(s.c % 16 == 0 && (reinterpret_cast<uintptr_t>(s.data) & 15) == 0 && s.sw % 8 == 0 && s.sw >= s.c,
                "conv_tc: source %d channels %d / pitch %lld / alignment", i, s.c, (long long)s.sw);
-    if (!seg) TC_REQUIRE(halo ? is_halo_view(s, true) : is_dense_view(s, true), "conv_tc: source %d geometry differs from source 0", i);
+    if (!seg) TC_REQUIRE(halo ? halo_kind(s, true) == hk : is_dense_view(s, true), "conv_tc: source %d geometry differs from source 0", i);
   }
   memset(p, 0, sizeof(*p));
   p->idesc_ab = f16 ? 0u : ((1u << 7) | (1u << 10));
@@ -1786,8 +1799,8 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   p->halo = halo ? 1 : 0;
   p->phase = phase ? 1 : 0;
   p->h = s0.h; p->w = s0.w;
-  p->pitch = halo ? s0.w + 2 : 0;
-  p->plane = halo ? (s0.h + 2) * (s0.w + 2) : s0.h * s0.w;
+  p->pitch = halo ? s0.w + (hk == 2 ? 1 : 2) : 0;
+  p->plane = halo ? (s0.h + (hk == 2 ? 1 : 2)) * p->pitch : s0.h * s0.w;
   long long rows = (long long)s0.n * p->plane;
   if (seg) {
     p->num_seg = d->num_seg;
@@ -1952,7 +1965,8 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     static const int env_trim = getenv("CM2_TC_TRIM") ? atoi(getenv("CM2_TC_TRIM")) : 1;
     if (env_trim && halo && !seg && !phase && !pred && rows > 4 * (long long)(p->pitch + 1)) {
       const int lead = p->pitch + 1;
-      const int t_trim = (int)((rows - 2 * lead + TC_BM - 1) / TC_BM);
+      // (shared-halo views end with an interior pixel: only the leading rows can be left out)
+      const int t_trim = (int)((rows - (hk == 2 ? 1 : 2) * lead + TC_BM - 1) / TC_BM);
       const int waves_full = (p->m_tiles * p->n_tiles + sms - 1) / sms, waves_trim = (t_trim * p->n_tiles + sms - 1) / sms;
       if (waves_trim < waves_full) { p->row_begin = lead; p->m_tiles = t_trim; }
     }
@@ -1985,7 +1999,7 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   p->out_f32 = d->out_dtype == CM2_F32;
   p->out_mode = d->out_mode;
   p->out_plane = (long long)d->out.n * d->out.sn;
-  p->out_halo = (halo && d->out_mode == 0 && is_halo_view(d->out) && d->out.h == s0.h && d->out.w == s0.w && !g_plan_splitk) ? 1 : 0;
+  p->out_halo = (halo && d->out_mode == 0 && halo_kind(d->out) == hk && d->out.h == s0.h && d->out.w == s0.w && !g_plan_splitk) ? 1 : 0;
   const int oc = d->out_mode == 1 ? d->cout / 4 : d->cout;
   const int oeb = p->out_f32 ? 4 : 2;
   p->out_vec = (oc % 16 == 0 && d->out.sn % 8 == 0 && d->out.sh % 8 == 0 && d->out.sw % 8 == 0 &&

@@ -88,6 +88,34 @@ class PhaseMap(object):
         return self.buf.shape[4]
 
 
+class SharedHaloFMap(FMap):
+    """A feature map whose images SHARE their zero frame (csrc/conv_tc.cu ``halo_kind`` 2): flat ``[rows, c]`` buffer, line pitch
+    ``w + 1`` and image pitch ``(h + 1)(w + 1)`` pixels -- the zero pixel right of a line is the zero pixel left of the next, the
+    zero line under an image the zero line above the next.  For the 14x14 ROI maps a 3x3 convolution then runs over 225 GEMM rows
+    per ROI instead of 256.  Only convolutions write it (interior + zeros on the shared frame) and view-based kernels read it."""
+
+    __slots__ = ("_shape",)
+
+    def __init__(self, flat, n, h, w):
+        assert flat.dim() == 2 and flat.is_contiguous() and flat.shape[0] >= SharedHaloFMap.rows(n, h, w)
+        self.buf, self.halo, self._shape = flat, 1, (n, h, w)
+
+    @staticmethod
+    def rows(n, h, w):
+        return n * (h + 1) * (w + 1) + (w + 1) + 1
+
+    @property
+    def view(self):
+        n, h, w = self._shape
+        c = self.buf.shape[1]
+        return torch.as_strided(self.buf, (n, h, w, c), ((h + 1) * (w + 1) * c, (w + 1) * c, c, 1), self.buf.storage_offset() + (w + 2) * c)
+
+    n = property(lambda self: self._shape[0])
+    h = property(lambda self: self._shape[1])
+    w = property(lambda self: self._shape[2])
+    c = property(lambda self: self.buf.shape[1])
+
+
 class RawInput(object):
     """The un-normalised input batch on its way to the fused stem (``cm2_stem1_fused_batch``: normalise + pad + stem_1 in
     one pass): planar ``[3, h, w]`` device images of one dtype and the padded extent.  Never materialised as a tensor."""
@@ -181,6 +209,7 @@ class Engine(object):
         self.tc = precision in ("bf16", "fp32")
         self.split = precision == "fp32"
         self.stem_variant = int(os.environ.get("CM2_STEM_VARIANT", "1"))      # 1: fused stem_1 (csrc/stem.cu); 0: im2col pass + K = 32 GEMM
+        self.shared_halo_roi = precision == "bf16" and os.environ.get("CM2_SHARED_HALO_ROI", "1") != "0"
         self.splitk_on = os.environ.get("CM2_SPLITK", "1") != "0"               # split-K for small-M layers (cm2_conv_desc.splitk)
         self.split_out_all = os.environ.get("CM2_SPLIT_OUT_ALL") == "1"       # [hi | lo] epilogue store on every eligible layer (tests)
         self._split_cache = {}
@@ -293,6 +322,9 @@ class Engine(object):
     def fmap(self, name, n, h, w, c, dtype=None, halo=1):
         return FMap(self.buffer(name, (n, h + 2 * halo, w + 2 * halo, c), dtype or self.dtype), halo)
 
+    def shared_halo_fmap(self, name, n, h, w, c, dtype=None):
+        return SharedHaloFMap(self.buffer(name, (SharedHaloFMap.rows(n, h, w), c), dtype or self.dtype), n, h, w)
+
     def phasemap(self, name, n, h, w, c):
         """Phase planes for a full-resolution [n, h, w, c] map."""
         return PhaseMap(self.buffer(name, (4, n, (h + 1) // 2 + 2, (w + 1) // 2 + 2, c), self.dtype))
@@ -344,7 +376,9 @@ class Engine(object):
             else:
                 out = SplitPhaseMap(self.buffer(name, (4, x0.n, (ho + 1) // 2 + 2, (wo + 1) // 2 + 2, 2 * w.cout), torch.float16))
         if out is None:
-            if out_mode == 0:
+            if out_mode == 0 and out_halo == 1 and isinstance(x0, SharedHaloFMap) and w.stride == 1 and out_dtype in (None, self.dtype):
+                out = self.shared_halo_fmap(name, x0.n, ho, wo, w.cout)      # a chain of convolutions keeps the shared-halo layout
+            elif out_mode == 0:
                 out = self.fmap(name, x0.n, ho, wo, w.cout, out_dtype, out_halo)
             elif out_mode == 1:
                 out = self.fmap(name, x0.n, 2 * ho, 2 * wo, w.cout // 4, out_dtype, out_halo)
@@ -878,7 +912,10 @@ class Engine(object):
         if fresh:
             self.begin_pass()
         R, res = roi.n, roi.h
-        pm = self.fmap("iou_mask", R, res, res, 16)
+        if isinstance(roi, SharedHaloFMap):
+            pm = self.shared_halo_fmap("iou_mask_sh", R, res, res, 16)
+        else:
+            pm = self.fmap("iou_mask", R, res, res, 16)
         lib.maskiou_prep(probs, pm.view)
         y = None
         nconv = len(P["iou_fcn"])
@@ -911,7 +948,13 @@ class Engine(object):
         R = n * r_cap
         res = mh.POOLER_RESOLUTION
         area = self.image_area(image_sizes)
-        roi = self.fmap("roi_feat", R, res, res, P["in_ch"])
+        # bf16 engine: ROI maps with a shared zero frame -- 225 instead of 256 GEMM rows per 14x14 ROI in the seven 3x3 convolutions
+        # of the mask / MaskIoU heads (the spatial attention output keeps its own frame: the fused deconv + predictor epilogue
+        # wants one ROI per pair of 128-row tiles)
+        if self.shared_halo_roi:
+            roi = self.shared_halo_fmap("roi_feat_sh", R, res, res, P["in_ch"])
+        else:
+            roi = self.fmap("roi_feat", R, res, res, P["in_ch"])
         crit = 0 if mh.ASSIGN_CRITERION == "ratio" else 1
         lib.roialign_fpn([f.view for f in feats], strides, det["boxes"], det["count"], n, r_cap, area, crit,
                          int(mh.POOLER_SAMPLING_RATIO), roi.view,

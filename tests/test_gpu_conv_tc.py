@@ -292,6 +292,57 @@ def test_conv_tc_split_k_matches_the_unsplit_convolution(kind):
     assert not lib.conv2d(views, cw.w_tc, oview(outs[0]), cout, ksz, stride, ksz // 2, splitk=5, splitk_ws=ws[:1, :64], **kw)
 
 
+def test_conv_tc_on_shared_halo_maps():
+    """ROI maps whose images share their zero frame (engine.SharedHaloFMap, csrc/conv_tc.cu halo_kind 2: 225 GEMM rows per
+    14x14 ROI instead of 256): a chain of 3x3 convolutions, a two-source convolution (the MaskIoU head's [roi, mask] concat),
+    the phase-plane store for a following stride-2 convolution -- all against F.conv2d; the shared frame stays zero."""
+    from centermask2_b200.engine import Engine, SharedHaloFMap
+    eng = Engine(None, "bf16", DEV)
+    eng.use_graphs = False
+    try:
+        g = torch.Generator().manual_seed(41)
+        r, c, res = 37, 256, 14                                       # 37 ROIs: 8325 rows = 65.04 tiles (a ragged last tile)
+        x = rb(torch.randn(r, c, res, res, generator=g))
+        m = rb(torch.randn(r, 16, res, res, generator=g))
+        w1 = rb(torch.randn(c, c, 3, 3, generator=g) / 48)
+        w2 = rb(torch.randn(c, c + 16, 3, 3, generator=g) / 49)
+        w3 = rb(torch.randn(c, c, 3, 3, generator=g) / 48)
+        b1 = torch.randn(c, generator=g) * 0.1
+        y1 = rb(torch.relu(F.conv2d(x, w1, b1, 1, 1)))
+        y2 = rb(torch.relu(F.conv2d(torch.cat([y1, m], 1), w2, None, 1, 1)))
+        ref3 = torch.relu(F.conv2d(y2, w3, None, 2, 1))
+        c1 = packing.ConvW(w1, [c], 1, 1, None, b1, True, BF, DEV, True)
+        c2 = packing.ConvW(w2, [c, 16], 1, 1, None, None, True, BF, DEV, True)
+        c3 = packing.ConvW(w3, [c], 2, 1, None, None, True, BF, DEV, True)
+        xin = eng.shared_halo_fmap("t_x", r, res, res, c)
+        min_ = eng.shared_halo_fmap("t_m", r, res, res, 16)
+        xin.view.copy_(x.permute(0, 2, 3, 1).to(DEV, BF))
+        min_.view.copy_(m.permute(0, 2, 3, 1).to(DEV, BF))
+        eng.begin_pass()
+        o1 = eng.conv("t_1", [xin], c1)
+        assert isinstance(o1, SharedHaloFMap) and o1.buf.shape[0] == r * 225 + 16
+        o2 = eng.conv("t_2", [o1, min_], c2)
+        assert isinstance(o2, SharedHaloFMap)
+        pm = eng.conv("t_2p", [o1, min_], c2, out_mode=2)             # the same layer, stored as phase planes
+        o3 = eng.conv("t_3", [pm], c3, out_halo=0)
+        torch.cuda.synchronize()
+        close(nchw(o1.view), y1)
+        close(nchw(o2.view), y2)
+        close(nchw(o3.view), ref3)
+        for o in (o1, o2):                                            # everything outside the interior view is still zero
+            total = o.buf.float().abs().sum().item()
+            inner = o.view.float().abs().sum().item()
+            assert abs(total - inner) <= 1e-6 * max(1.0, inner), (total, inner)
+        # and the same convolution on an ordinary halo map gives the same numbers (same tiles of K, other row order)
+        std = halo(x)
+        o1s = eng.conv("t_1s", [std], c1)
+        torch.cuda.synchronize()
+        assert not isinstance(o1s, SharedHaloFMap)
+        assert torch.equal(o1s.view, o1.view)
+    finally:
+        eng.release()
+
+
 def test_conv_tc_phase_split_store_feeds_stride2_conv():
     """stem_2 -> stem_3 chain: out_mode 2 (phase-split store) then a stride-2 conv on the planes."""
     g = torch.Generator().manual_seed(11)
