@@ -293,7 +293,12 @@ def instrumented_step(model, cfg, dev_images, sizes_out, steps, layers=None):
     def im2col_bytes(imgs, mean, std, hp, wp, out, *a, **k):
         return sum(_numel_bytes(im) for im in imgs) + len(imgs) * (hp // 2) * (wp // 2) * 32 * out.element_size()
 
-    families = {"groupnorm_apply_seg": ("groupnorm apply (+ReLU)", seg_bytes), "ese_apply_pool": ("eSE apply (+ max-pool)", ese_bytes),
+    def seg_split_bytes(flat, out_split, segs, *a, **k):
+        px = sum(n * h * w for _, n, h, w in segs)
+        return px * (flat.shape[1] * flat.element_size() + out_split.shape[1] * out_split.element_size())     # fp32 in, [hi | lo] f16 out
+
+    families = {"groupnorm_apply_seg": ("groupnorm apply (+ReLU)", seg_bytes), "groupnorm_apply_seg_split": ("groupnorm apply (+ReLU)", seg_split_bytes),
+                "ese_apply_pool": ("eSE apply (+ max-pool)", ese_bytes),
                 "roialign_fpn": ("ROIAlign (+ level assignment)", roi_bytes), "paste_masks": ("mask paste-back", paste_bytes),
                 "spatial_attention": ("spatial attention", lambda x, out, w: 2 * _numel_bytes(x)),
                 "fcos_decode_levels": ("FCOS decode + threshold", decode_bytes),

@@ -96,6 +96,9 @@ struct alignas(64) TcParams {
   int split_out;            // 1: the output is the [hi | lo] f16 pair of 2 * cout channels (epilogue kind 11)
   // ---- split-K (v1 kernel): tile t = (k-slice, m tile, n tile); slice ks accumulates K-blocks [ks * kb_per_split, ..) and stores
   // its fp32 partial sums split_stride elements behind the previous slice's (cm2_conv_desc.splitk; splitk_finish_kernel adds them)
+  // trimmed tile range (row_begin > 0): the halo rows of the output outside it are zeroed by the first / last CTA's epilogue warps
+  char* trim_base;          // address of flat output row 0; nullptr: nothing to zero
+  long long trim_lo_bytes, trim_hi_off, trim_hi_bytes;
   int ksplit;               // 0 / 1: off
   int kb_per_split;
   long long split_stride;
@@ -1020,6 +1023,15 @@ __global__ void __launch_bounds__(MAXT, 1) conv_tc_kernel(const __grid_constant_
   } else {
     // ===================================== epilogue =========================================
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    if (p.trim_base && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+      // output rows outside the trimmed tile range are halo pixels: keep them zero (was two memset nodes per launch)
+      const long long t0 = ((long long)threadIdx.x - 64) * 16, step = 32ll * n_epi_warps * 16;
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      if (blockIdx.x == 0)
+        for (long long i = t0; i < p.trim_lo_bytes; i += step) *reinterpret_cast<uint4*>(p.trim_base + i) = z;
+      if (blockIdx.x == gridDim.x - 1)
+        for (long long i = t0; i < p.trim_hi_bytes; i += step) *reinterpret_cast<uint4*>(p.trim_base + p.trim_hi_off + i) = z;
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t parity = 0;
@@ -2175,10 +2187,17 @@ int conv_tc_launch(const cm2_conv_desc* d, cudaStream_t stream) {
     const size_t eb = p.out_f32 ? 4 : 2, row_bytes = (size_t)d->out.sw * eb;
     char* obase = reinterpret_cast<char*>(d->out.data) - (size_t)(d->out.sh + d->out.sw) * eb;
     const long long covered_end = (long long)p.row_begin + (long long)p.m_tiles * TC_BM;
-    bool ok = cudaMemsetAsync(obase, 0, (size_t)p.row_begin * row_bytes, stream) == cudaSuccess;
-    if (ok && covered_end < p.rows)
-      ok = cudaMemsetAsync(obase + (size_t)covered_end * row_bytes, 0, (size_t)(p.rows - covered_end) * row_bytes, stream) == cudaSuccess;
-    if (!ok) { set_error("conv_tc: cudaMemsetAsync(halo rows) failed"); return CM2_ERR_CUDA; }
+    if (p.variant == 1 && row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(obase) & 15) == 0) {
+      p.trim_base = obase;                              // zeroed inside the kernel
+      p.trim_lo_bytes = (long long)p.row_begin * (long long)row_bytes;
+      p.trim_hi_off = covered_end * (long long)row_bytes;
+      p.trim_hi_bytes = covered_end < p.rows ? (long long)(p.rows - covered_end) * (long long)row_bytes : 0;
+    } else {
+      bool ok = cudaMemsetAsync(obase, 0, (size_t)p.row_begin * row_bytes, stream) == cudaSuccess;
+      if (ok && covered_end < p.rows)
+        ok = cudaMemsetAsync(obase + (size_t)covered_end * row_bytes, 0, (size_t)(p.rows - covered_end) * row_bytes, stream) == cudaSuccess;
+      if (!ok) { set_error("conv_tc: cudaMemsetAsync(halo rows) failed"); return CM2_ERR_CUDA; }
+    }
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sms ? tiles : sms;
