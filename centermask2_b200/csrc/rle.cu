@@ -19,6 +19,7 @@ namespace cm2 {
 // boxes cover ~10 % of an image on average, which is what the scan then reads.  The window is widened by one more pixel on
 // every side; an invalid slot has an empty window.
 struct RleWindow { int xa, xb, ya, yb; };
+constexpr int RLE_ROWS = 8;                                // rows fetched per step of a column walk
 __device__ __forceinline__ RleWindow rle_window(const float* __restrict__ boxes, const uint8_t* __restrict__ valid, int m, int h, int w) {
   RleWindow q;
   if (!boxes) { q.xa = 0; q.xb = w; q.ya = 0; q.yb = h; return q; }
@@ -47,8 +48,23 @@ __global__ void __launch_bounds__(256) rle_count_kernel(const uint8_t* __restric
     const uint8_t* p = masks + (size_t)m * h * w;
     uint8_t prev = rle_prev(p, q, x, h, w);
     const int ye = min(q.yb + 1, h);                       // one row past the window: the closing transition of the column
-    for (int y = q.ya; y < ye; ++y) {
-      const uint8_t v = p[(size_t)y * w + x] != 0;
+    // the walk is a chain of dependent compares but independent loads: eight rows are fetched before the first compare, so that
+    // a tall window costs one L2 round trip per eight rows instead of one per row (the kernel is bound by its tallest columns)
+    int y = q.ya;
+    const uint8_t* col = p + (size_t)y * w + x;
+    for (; y + RLE_ROWS <= ye; y += RLE_ROWS, col += (size_t)RLE_ROWS * w) {
+      uint8_t v[RLE_ROWS];
+#pragma unroll
+      for (int i = 0; i < RLE_ROWS; ++i) v[i] = col[(size_t)i * w];
+#pragma unroll
+      for (int i = 0; i < RLE_ROWS; ++i) {
+        const uint8_t b = v[i] != 0;
+        cnt += b != prev;
+        prev = b;
+      }
+    }
+    for (; y < ye; ++y, col += w) {
+      const uint8_t v = *col != 0;
       cnt += v != prev;
       prev = v;
     }
@@ -158,9 +174,22 @@ __global__ void __launch_bounds__(256) rle_write_kernel(const uint8_t* __restric
   uint8_t prev = rle_prev(p, q, x, h, w);
   const int ye = min(q.yb + 1, h);
   int k = 0;
-  for (int y = q.ya; y < ye; ++y) {
-    const uint8_t v = p[(size_t)y * w + x] != 0;
-    if (v != prev) out[k++] = (unsigned)(x * h + y);      // column-major position of the transition
+  int y = q.ya;
+  const uint8_t* col = p + (size_t)y * w + x;
+  for (; y + RLE_ROWS <= ye; y += RLE_ROWS, col += (size_t)RLE_ROWS * w) {
+    uint8_t v[RLE_ROWS];
+#pragma unroll
+    for (int i = 0; i < RLE_ROWS; ++i) v[i] = col[(size_t)i * w];
+#pragma unroll
+    for (int i = 0; i < RLE_ROWS; ++i) {
+      const uint8_t b = v[i] != 0;
+      if (b != prev) out[k++] = (unsigned)(x * h + y + i);      // column-major position of the transition
+      prev = b;
+    }
+  }
+  for (; y < ye; ++y, col += w) {
+    const uint8_t v = *col != 0;
+    if (v != prev) out[k++] = (unsigned)(x * h + y);
     prev = v;
   }
 }

@@ -245,6 +245,15 @@ class Engine(object):
             self._recording.append(t)
         return t
 
+    def image_buffers(self, prefix, sig):
+        """Engine-owned buffers for a batch of input images (``sig``: one (shape, dtype) per image).  Images of one shape and
+        dtype live back to back in ONE buffer, so that a staging -> input move is a single device-to-device copy instead of
+        one per image.  Returns (list of per-image tensors, the whole batch tensor or None)."""
+        if len(sig) > 1 and len(set(sig)) == 1:
+            whole = self.buffer(prefix + "_all", (len(sig),) + tuple(sig[0][0]), sig[0][1], zero=False)
+            return [whole[i] for i in range(len(sig))], whole
+        return [self.buffer("{}{}".format(prefix, i), tuple(shp), dt, zero=False) for i, (shp, dt) in enumerate(sig)], None
+
     def const(self, key, make):
         """Small cached device constant (or tuple of them) under a free-form ``key``; built by ``make()`` on first use."""
         t = self._bufs.get(key)

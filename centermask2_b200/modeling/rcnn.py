@@ -104,20 +104,23 @@ class GeneralizedRCNN(nn.Module):
             if eng._stage_free is not None:                  # the previous consumer of the staging buffers has read them
                 copy_stream.wait_event(eng._stage_free)
             with torch.cuda.stream(copy_stream):
-                bufs = [eng.buffer("stage_image{}".format(i), tuple(b["image"].shape), b["image"].dtype, zero=False)
-                        for i, b in enumerate(batch)]
+                sig = tuple((tuple(b["image"].shape), b["image"].dtype) for b in batch)
+                bufs, whole = eng.image_buffers("stage_image", sig)
                 for dst, b in zip(bufs, batch):
                     dst.copy_(b["image"], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
-            return batch, bufs, ev
+            return batch, bufs, ev, whole, sig
 
         def consume(staged):
-            _, bufs, ev = staged
+            _, bufs, ev, whole, sig = staged
             torch.cuda.current_stream().wait_event(ev)
-            images = [eng.buffer("input_image{}".format(i), tuple(t.shape), t.dtype, zero=False) for i, t in enumerate(bufs)]
-            for dst, src in zip(images, bufs):
-                dst.copy_(src, non_blocking=True)
+            images, whole_in = eng.image_buffers("input_image", sig)
+            if whole is not None and whole_in is not None:
+                whole_in.copy_(whole, non_blocking=True)                # one copy for the batch (images of one shape)
+            else:
+                for dst, src in zip(images, bufs):
+                    dst.copy_(src, non_blocking=True)
             eng._stage_free = torch.cuda.Event()
             eng._stage_free.record()
 
@@ -190,7 +193,7 @@ class GeneralizedRCNN(nn.Module):
             if len(set(out_sizes)) != 1:
                 raise ValueError("inference_records needs one output size per batch (got {})".format(sorted(set(out_sizes))))
             sig = tuple((tuple(b["image"].shape), b["image"].dtype) for b in batch)
-            images = [eng.buffer("input_image{}".format(i), shp, dt, zero=False) for i, (shp, dt) in enumerate(sig)]
+            images, _ = eng.image_buffers("input_image", sig)
 
             def plan():
                 x, _ = eng.preprocess(images, self.backbone.size_divisibility)
@@ -282,7 +285,7 @@ class GeneralizedRCNN(nn.Module):
         out_sizes = [(int(b.get("height", sz[0])), int(b.get("width", sz[1]))) for b, sz in zip(batched_inputs, sizes)]
         # inputs land in engine-owned buffers (static addresses: the launch plan below is replayed as a CUDA graph)
         sig = tuple((tuple(b["image"].shape), b["image"].dtype) for b in batched_inputs)
-        images = [eng.buffer("input_image{}".format(i), shp, dt, zero=False) for i, (shp, dt) in enumerate(sig)]
+        images, _ = eng.image_buffers("input_image", sig)
         if not inputs_resident:                                         # inference_stream has put them there already
             for dst, b in zip(images, batched_inputs):
                 dst.copy_(b["image"], non_blocking=True)
