@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--graph", type=int, default=0)
     ap.add_argument("--out", default=None)
     ap.add_argument("--e2e", action="store_true", help="trace GeneralizedRCNN.inference_stream (host images in, records out) instead")
+    ap.add_argument("--records", action="store_true", help="with --e2e: trace GeneralizedRCNN.inference_records (bench.py's e2e loop)")
+    ap.add_argument("--gaps", type=float, default=0.0, help="also list device idle gaps longer than this many microseconds")
     args = ap.parse_args()
     import centermask2_b200 as cm
     from centermask2_b200.synth import synthetic_state_dict
@@ -43,6 +45,10 @@ def main():
     side = torch.cuda.Stream()
 
     def stream(k):
+        if args.records:
+            for res in model.inference_records((host_inputs for _ in range(k))):
+                pass
+            return
         for out, done in model.inference_stream((host_inputs for _ in range(k)), with_event=True):
             side.wait_event(done)
             with torch.cuda.stream(side):
@@ -70,16 +76,19 @@ def main():
         dur = e.time_range.end - e.time_range.start
         agg[nme][0] += 1
         agg[nme][1] += dur
-        ivals.append((e.time_range.start, e.time_range.end))
+        ivals.append((e.time_range.start, e.time_range.end, nme))
     ivals.sort()
-    busy, cur_s, cur_e = 0.0, None, None
-    for s, e in ivals:
+    busy, cur_s, cur_e, last_name, gaps = 0.0, None, None, None, []
+    for s, e, nme in ivals:
         if cur_e is None or s > cur_e:
             if cur_e is not None:
                 busy += cur_e - cur_s
-            cur_s, cur_e = s, e
+                if args.gaps and s - cur_e > args.gaps:
+                    gaps.append((s - cur_e, last_name, nme))
+            cur_s, cur_e, last_name = s, e, nme
         else:
-            cur_e = max(cur_e, e)
+            if e > cur_e:
+                cur_e, last_name = e, nme
     if cur_e is not None:
         busy += cur_e - cur_s
     wall = ivals[-1][1] - ivals[0][0] if ivals else 0.0
@@ -90,6 +99,14 @@ def main():
     tot = sum(v for _, v in agg.values())
     for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append("{:58s} {:7.1f} {:9.4f} {:6.1f}%".format(k[:58], n / args.steps, v / 1e3 / args.steps, 100.0 * v / tot))
+    if args.gaps:
+        lines.append("# idle gaps > {} us: {} gaps, {:.3f} ms/step".format(args.gaps, len(gaps), sum(g for g, _, _ in gaps) / 1e3 / args.steps))
+        agg_g = collections.defaultdict(lambda: [0, 0.0])
+        for g, a, b in gaps:
+            agg_g[(a[:40], b[:40])][0] += 1
+            agg_g[(a[:40], b[:40])][1] += g
+        for (a, b), (n, v) in sorted(agg_g.items(), key=lambda kv: -kv[1][1])[:15]:
+            lines.append("#   {:6.1f} us x {:3d}  after {}  before {}".format(v / n, n, a, b))
     txt = "\n".join(lines)
     print(txt)
     if args.out:
