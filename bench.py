@@ -530,7 +530,7 @@ def main():
 
     for _ in range(2):
         e2e_forward()
-    e2e_records(4)
+    e2e_records(8)                                # every slot of the pipeline: one eager pass + its graph capture
     soak(step)
     barrier()
     with clk.window():

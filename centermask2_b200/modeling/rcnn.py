@@ -144,56 +144,51 @@ class GeneralizedRCNN(nn.Module):
         from .. import lib, parallel
         eng = runtime.engine_for(self.cfg)
         it = iter(batches)
-        stage, consume = self._stager(eng)
+        copy_stream = eng.copy_stream()
         back = eng.side_stream("readback")
         fcos, roi = self.proposal_generator, self.roi_heads
-        state = {"staged": stage(next(it, None)), "launched": 0, "cap": int(rle_capacity)}
+        nslots = depth + 1
+        state = {"staged": None, "launched": 0, "cap": int(rle_capacity)}
         pending = collections.deque()
+        slot_free = eng.__dict__.setdefault("_records_slot_free", {})      # slot -> event: that slot's step has read its inputs
 
-        def encode(ctx):
-            """paste-back + RLE of a launched batch into its slot's buffers (compute stream), then the first read-back."""
-            n, r_cap, slot, (oh, ow) = ctx["n"], ctx["r_cap"], ctx["slot"], ctx["out_size"]
-            cap = state["cap"]
-            R = n * r_cap
-            B = eng.buffer
-            masks = B("rec_masks{}".format(slot), (R, oh, ow), torch.uint8, False)
-            lib.paste_masks(ctx["probs"], ctx["boxes"], ctx["valid"], masks, R, ctx["probs"].shape[-1], oh, ow, 0.5)
-            cc = B("rle_col_count", (R, ow), torch.int32, False)
-            co = B("rle_col_offset", (R, ow), torch.int32, False)
-            tot = B("rle_total", (R,), torch.int32, False)
-            moff = B("rle_mask_offset{}".format(slot), (R + 1,), torch.int64, False)
-            pos = B("rle_positions", (cap,), torch.int32, False)
-            runs = B("rle_runs{}".format(slot), (cap,), torch.int32, False)
-            lib.rle_encode(masks, cc, co, tot, moff, pos, runs, ctx["boxes"], ctx["valid"])
-            # the next batch's replay overwrites the plan's record buffer: snapshot it for the read-back stream
-            rec = B("records_slot{}".format(slot), tuple(ctx["rec"].shape), torch.float32, False)
-            rec.copy_(ctx["rec"], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-            back.wait_event(ev)
-            with torch.cuda.stream(back):
-                ctx["h_rec"].copy_(rec, non_blocking=True)
-                ctx["h_off"] = eng.pinned("h_rle_off{}".format(slot), (R + 1,), torch.int64)
-                ctx["h_off"].copy_(moff, non_blocking=True)
-                ctx["ready"] = torch.cuda.Event()
-                ctx["ready"].record(back)
-            ctx.update(masks=masks, runs=runs, cap=cap)
+        # A batch lives in one of ``depth + 1`` SLOTS: its own input buffers (the H2D target), mask / run / record buffers.
+        # The WHOLE step of a slot -- fused stem straight from the slot's input buffers ... paste-back, RLE, record packing --
+        # is one CUDA graph, so the compute stream sees [wait for the H2D event][graph][event] per batch and nothing else
+        # (profiles/r2_trace_e2e_records_b16.txt: with eager staging copies / paste / RLE launches between the graphs the
+        # device idled 0.2-0.4 ms per step at those hand-offs).
+        def stage(batch, slot):
+            if batch is None:
+                return None
+            sig = tuple((tuple(b["image"].shape), b["image"].dtype) for b in batch)
+            if slot in slot_free:                            # the step that last used this slot has finished with the inputs
+                copy_stream.wait_event(slot_free[slot])
+            with torch.cuda.stream(copy_stream):
+                bufs, _ = eng.image_buffers("records_in{}_".format(slot), sig)
+                for dst, b in zip(bufs, batch):
+                    dst.copy_(b["image"], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return batch, bufs, ev, sig, slot
 
         def launch_next():
             if state["staged"] is None:
                 return False
-            consume(state["staged"])
-            batch = state["staged"][0]
-            state["staged"] = stage(next(it, None))
-            slot = state["launched"] % (depth + 1)
+            batch, images, ev, sig, slot = state["staged"]
+            # the H2D copy of this batch was issued a whole step ago: waiting for it on the HOST returns at once in steady state
+            # and keeps the compute stream free of cross-stream waits (a wait in front of a graph launch exposed ~0.1 ms of
+            # launch latency per step)
+            ev.synchronize()
             state["launched"] += 1
+            state["staged"] = stage(next(it, None), (slot + 1) % nslots)
             n = len(batch)
             sizes = [(int(b["image"].shape[-2]), int(b["image"].shape[-1])) for b in batch]
             out_sizes = [(int(b.get("height", sz[0])), int(b.get("width", sz[1]))) for b, sz in zip(batch, sizes)]
             if len(set(out_sizes)) != 1:
                 raise ValueError("inference_records needs one output size per batch (got {})".format(sorted(set(out_sizes))))
-            sig = tuple((tuple(b["image"].shape), b["image"].dtype) for b in batch)
-            images, _ = eng.image_buffers("input_image", sig)
+            oh, ow = out_sizes[0]
+            cap = state["cap"]
+            B = eng.buffer
 
             def plan():
                 x, _ = eng.preprocess(images, self.backbone.size_divisibility)
@@ -201,25 +196,46 @@ class GeneralizedRCNN(nn.Module):
                 det = fcos.detect([feats[f] for f in fcos.in_features])
                 probs, mask_scores = roi.run([feats[f] for f in roi.in_features], det, sizes)
                 boxes, valid = eng.rescale_boxes(det["boxes"], sizes, out_sizes, det["count"])
-                rec = eng.buffer("records", (n, det["boxes"].shape[1], parallel.RECORD_FIELDS), torch.float32, False)
+                r_cap = det["boxes"].shape[1]
+                R = n * r_cap
+                rec = B("records_slot{}".format(slot), (n, r_cap, parallel.RECORD_FIELDS), torch.float32, False)
                 parallel.pack_slots(rec, boxes, det["scores"], det["classes"], mask_scores, det["locations"], valid, det["count"])
-                return det, probs, boxes, valid, rec
+                cand = B("records_cand{}".format(slot), tuple(det["cand_count"].shape), det["cand_count"].dtype, False)
+                cand.copy_(det["cand_count"], non_blocking=True)
+                masks = B("rec_masks{}".format(slot), (R, oh, ow), torch.uint8, False)
+                lib.paste_masks(probs, boxes, valid, masks, R, probs.shape[-1], oh, ow, 0.5)
+                moff = B("rle_mask_offset{}".format(slot), (R + 1,), torch.int64, False)
+                runs = B("rle_runs{}".format(slot), (cap,), torch.int32, False)
+                lib.rle_encode(masks, B("rle_col_count", (R, ow), torch.int32, False), B("rle_col_offset", (R, ow), torch.int32, False),
+                               B("rle_total", (R,), torch.int32, False), moff, B("rle_positions", (cap,), torch.int32, False), runs,
+                               boxes, valid)
+                return det, rec, cand, masks, moff, runs
 
             eng.trim()
-            det, probs, boxes, valid, rec = eng.graphed(("records", self.graph_tokens(), sig, tuple(out_sizes)), plan,
-                                                        keep=self.packed_refs())
+            det, rec, cand, masks, moff, runs = eng.graphed(("records", self.graph_tokens(), sig, (oh, ow), slot, cap), plan,
+                                                            keep=self.packed_refs())
+            done = torch.cuda.Event()
+            done.record()
+            slot_free[slot] = done
             r_cap = det["boxes"].shape[1]
-            ctx = dict(n=n, r_cap=r_cap, slot=slot, out_size=out_sizes[0], probs=probs, boxes=boxes, valid=valid, rec=rec,
+            R = n * r_cap
+            ctx = dict(n=n, r_cap=r_cap, slot=slot, out_size=(oh, ow), masks=masks, runs=runs, cap=cap, cand_cap=det["cand_cap"],
                        h_rec=eng.pinned("h_records{}".format(slot), (n, r_cap, parallel.RECORD_FIELDS), torch.float32),
-                       cand=det["cand_count"], cand_cap=det["cand_cap"],
-                       h_cand=eng.pinned("h_rcand{}".format(slot), tuple(det["cand_count"].shape), torch.int32))
-            ctx["h_cand"].copy_(det["cand_count"], non_blocking=True)
-            encode(ctx)
+                       h_cand=eng.pinned("h_rcand{}".format(slot), tuple(cand.shape), torch.int32),
+                       h_off=eng.pinned("h_rle_off{}".format(slot), (R + 1,), torch.int64))
+            back.wait_event(done)
+            with torch.cuda.stream(back):
+                ctx["h_rec"].copy_(rec, non_blocking=True)
+                ctx["h_off"].copy_(moff, non_blocking=True)
+                ctx["h_cand"].copy_(cand, non_blocking=True)
+                ctx["ready"] = torch.cuda.Event()
+                ctx["ready"].record(back)
             pending.append(ctx)
             return True
 
         if not roi.mask_on:
             raise NotImplementedError("inference_records needs MODEL.MASK_ON")
+        state["staged"] = stage(next(it, None), 0)
         for _ in range(depth):
             if not launch_next():
                 break

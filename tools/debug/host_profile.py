@@ -26,7 +26,7 @@ def main():
     def run(k):
         for res in model.inference_records((host_inputs for _ in range(k))):
             pass
-    run(5)
+    run(8)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     run(steps)

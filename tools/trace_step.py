@@ -57,7 +57,7 @@ def main():
     for _ in range(3):
         step()
     if args.e2e:
-        stream(4)
+        stream(8)
     torch.cuda.synchronize()
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
