@@ -1820,10 +1820,13 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
     for (int i = 0; i < d->num_seg; ++i) {
       const cm2_seg& g = d->seg[i];
       TC_REQUIRE(g.row0 % 256 == 0 && g.row0 >= rows && g.n > 0 && g.h > 0 && g.w > 0, "conv_tc: segment %d badly placed", i);
-      const long long srows = (long long)g.n * (g.h + 2) * (g.w + 2);
+      // g.halo: 0 = every image with its own zero frame, 1 = shared frame (line pitch w + 1, image pitch (h + 1)(w + 1); see halo_kind)
+      TC_REQUIRE(g.halo == 0 || (g.halo == 1 && !f16), "conv_tc: segment %d: halo kind %d not supported here", i, g.halo);
+      const int fr = g.halo == 1 ? 1 : 2;
+      const long long srows = (long long)g.n * (g.h + fr) * (g.w + fr);
       TC_REQUIRE(g.row0 + srows < (1ll << 31) - 4096, "conv_tc: segment %d out of range", i);
-      p->seg_row0[i] = (int)g.row0; p->seg_rows[i] = (int)srows; p->seg_pitch[i] = g.w + 2;
-      p->seg_plane[i] = (g.h + 2) * (g.w + 2); p->seg_h[i] = g.h; p->seg_w[i] = g.w;
+      p->seg_row0[i] = (int)g.row0; p->seg_rows[i] = (int)srows; p->seg_pitch[i] = g.w + fr;
+      p->seg_plane[i] = (g.h + fr) * (g.w + fr); p->seg_h[i] = g.h; p->seg_w[i] = g.w;
       p->seg_img0[i] = i ? p->seg_img0[i - 1] + d->seg[i - 1].n : 0;
       rows = g.row0 + srows;
     }

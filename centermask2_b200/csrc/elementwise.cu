@@ -640,7 +640,7 @@ static bool gn_make_segs(int32_t num_seg, const cm2_seg* seg, int c, GnSegs* g) 
   g->num = num_seg;
   g->chunk_prefix[0] = 0; g->img_prefix[0] = 0; g->vec_prefix[0] = 0;
   for (int i = 0; i < num_seg; ++i) {
-    if (seg[i].n <= 0 || seg[i].h <= 0 || seg[i].w <= 0) return false;
+    if (seg[i].n <= 0 || seg[i].h <= 0 || seg[i].w <= 0 || seg[i].halo != 0) return false;    // (own-frame segments only)
     g->row0[i] = seg[i].row0; g->n[i] = seg[i].n; g->h[i] = seg[i].h; g->w[i] = seg[i].w;
     int cpi = ceil_div(seg[i].h * seg[i].w, GN_PIX_PER_CHUNK);
     g->chunk_prefix[i + 1] = g->chunk_prefix[i] + cpi * seg[i].n;

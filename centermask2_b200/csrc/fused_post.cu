@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include <cuda_fp16.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 
 namespace cm2 {
@@ -532,9 +533,12 @@ extern "C" int cm2_groupnorm_apply_seg(void* x, int32_t dtype, int32_t c, int32_
   int img0 = 0;
   for (int i = 0; i < num_seg; ++i) {
     CM2_CHECK_ARG(seg[i].n > 0 && seg[i].h > 0 && seg[i].w > 0 && seg[i].row0 >= end, "groupnorm_apply_seg: bad segment %d", i);
-    const long long rows = (long long)seg[i].n * (seg[i].h + 2) * (seg[i].w + 2);
+    CM2_CHECK_ARG(seg[i].halo == 0 || (seg[i].halo == 1 && dtype == CM2_BF16 && 256 % (c / 8) == 0),
+                  "groupnorm_apply_seg: segment %d: halo kind %d not supported here", i, seg[i].halo);
+    const int fr = seg[i].halo == 1 ? 1 : 2;                      // shared zero frame: line pitch w + 1, image pitch (h + 1)(w + 1)
+    const long long rows = (long long)seg[i].n * (seg[i].h + fr) * (seg[i].w + fr);
     CM2_CHECK_ARG(seg[i].row0 + rows < (1ll << 31) - 4096, "groupnorm_apply_seg: segment %d out of range", i);
-    g.row0[i] = (int)seg[i].row0; g.rows[i] = (int)rows; g.pitch[i] = seg[i].w + 2; g.plane[i] = (seg[i].h + 2) * (seg[i].w + 2);
+    g.row0[i] = (int)seg[i].row0; g.rows[i] = (int)rows; g.pitch[i] = seg[i].w + fr; g.plane[i] = (seg[i].h + fr) * (seg[i].w + fr);
     g.h[i] = seg[i].h; g.w[i] = seg[i].w; g.img0[i] = img0;
     img0 += seg[i].n;
     end = seg[i].row0 + rows;
@@ -549,7 +553,11 @@ extern "C" int cm2_groupnorm_apply_seg(void* x, int32_t dtype, int32_t c, int32_
       gl.img0[i] = g.img0[i];
       gl.line_prefix[i + 1] = gl.line_prefix[i] + seg[i].n * seg[i].h;
     }
-    gn_seg_apply_lines_kernel<<<gl.line_prefix[num_seg], 256, 0, s>>>((__nv_bfloat16*)x, c, c / groups, gl, stats, gamma, beta, eps, relu);
+    // CTAs of 128 threads (58 registers each: 7.4 K) fit beside a resident convolution CTA (320 threads x 168 registers = 53.8 K of
+    // the SM's 64 K, no shared memory needed here): the pass of one FCOS tower then runs UNDER the other tower's convolution
+    // (Engine.run_fcos_head puts the towers on two streams); alone it reaches the same occupancy with twice the CTAs per SM
+    static const int apply_threads = getenv("CM2_GN_APPLY_THREADS") ? atoi(getenv("CM2_GN_APPLY_THREADS")) : 128;
+    gn_seg_apply_lines_kernel<<<gl.line_prefix[num_seg], apply_threads, 0, s>>>((__nv_bfloat16*)x, c, c / groups, gl, stats, gamma, beta, eps, relu);
     CM2_CHECK_LAUNCH("gn_seg_apply_lines");
     return CM2_OK;
   }
@@ -581,6 +589,7 @@ extern "C" int cm2_groupnorm_apply_seg_split(const float* x, void* out_split, in
   int img0 = 0;
   for (int i = 0; i < num_seg; ++i) {
     CM2_CHECK_ARG(seg[i].n > 0 && seg[i].h > 0 && seg[i].w > 0 && seg[i].row0 >= end, "groupnorm_apply_seg_split: bad segment %d", i);
+    CM2_CHECK_ARG(seg[i].halo == 0, "groupnorm_apply_seg_split: shared-halo segments are not supported");
     const long long rows = (long long)seg[i].n * (seg[i].h + 2) * (seg[i].w + 2);
     CM2_CHECK_ARG(seg[i].row0 + rows < (1ll << 31) - 4096, "groupnorm_apply_seg_split: segment %d out of range", i);
     gl.row0[i] = (int)seg[i].row0; gl.pitch[i] = seg[i].w + 2; gl.plane[i] = (seg[i].h + 2) * (seg[i].w + 2);

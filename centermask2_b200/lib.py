@@ -29,7 +29,7 @@ MAX_SEG = 8
 
 class Seg(C.Structure):
     """cm2_seg: one map of a segmented halo tensor."""
-    _fields_ = [("row0", C.c_int64), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("row0", C.c_int64), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("halo", C.c_int32)]
 
 
 class ConvDesc(C.Structure):
@@ -168,7 +168,9 @@ def flat_act(t):
 
 
 def seg_array(segs):
-    return (Seg * len(segs))(*[Seg(r, n, h, w, 0) for r, n, h, w in segs])
+    """segs: (row0, n, h, w) per segment; ``segs.halo`` (engine.SegList) = 1 for segments whose images share their zero frame."""
+    halo = int(getattr(segs, "halo", 0))
+    return (Seg * len(segs))(*[Seg(r, n, h, w, halo) for r, n, h, w in segs])
 
 
 def ptr(t):
@@ -197,7 +199,7 @@ def conv2d(srcs, weight, out, cout, k, stride, pad, scale=None, shift=None, relu
         # segmented halo tensors: srcs / out are flat [rows, c] buffers sharing the segment table
         d.num_seg = len(segs)
         for i, (row0, n, h, w) in enumerate(segs):
-            d.seg[i] = Seg(row0, n, h, w, 0)
+            d.seg[i] = Seg(row0, n, h, w, int(getattr(segs, "halo", 0)))
         for i, s in enumerate(srcs):
             d.src[i] = flat_act(s)
     else:

@@ -563,13 +563,16 @@ def test_conv_tc_channel_sums(srcs, cout, k, h, w, n, variant):
     assert torch.allclose(sums, ref, rtol=1e-5, atol=1e-3), (sums - ref).abs().max()
 
 
-def test_conv_tc_seg_groupnorm_fused():
-    """stats_mode 2 + cm2_groupnorm_apply_seg == conv -> GroupNorm(32) -> ReLU per level (fcos.py:176-186)."""
+@pytest.mark.parametrize("shared_halo", [False, True])
+def test_conv_tc_seg_groupnorm_fused(shared_halo):
+    """stats_mode 2 + cm2_groupnorm_apply_seg == conv -> GroupNorm(32) -> ReLU per level (fcos.py:176-186); also on segments
+    whose images share their zero frame (cm2_seg.halo 1, the layout the bf16 engine uses for the FCOS levels)."""
     from centermask2_b200.engine import SegMap
     g = torch.Generator().manual_seed(5)
     shapes = [(2, 13, 21), (2, 7, 11), (2, 4, 6), (2, 2, 3)]
     c = 256
-    seg = SegMap(shapes, c, BF, DEV)
+    seg = SegMap(shapes, c, BF, DEV, shared_halo=shared_halo)
+    assert seg.segs.halo == int(shared_halo)
     xs = []
     for i, (n, h, w) in enumerate(shapes):
         x = rb(torch.randn(n, c, h, w, generator=g))
@@ -601,8 +604,13 @@ def test_conv_tc_seg_groupnorm_fused():
         ref = F.relu(F.group_norm(convs[i].float().permute(0, 3, 1, 2), 32, gamma.to(DEV), beta.to(DEV), 1e-5))
         got = out.level(i).view.permute(0, 3, 1, 2).float()
         close(got.cpu(), ref.cpu())
-        b = out.level(i).buf.float()
-        assert b[:, 0].abs().max() == 0 and b[:, -1].abs().max() == 0 and b[:, :, 0].abs().max() == 0 and b[:, :, -1].abs().max() == 0
+        lv = out.level(i)
+        if shared_halo:                                                       # nothing but interior pixels is non-zero
+            total, inner = lv.buf.float().abs().sum().item(), lv.view.float().abs().sum().item()
+            assert abs(total - inner) <= 1e-6 * max(1.0, inner), (total, inner)
+        else:
+            b = lv.buf.float()
+            assert b[:, 0].abs().max() == 0 and b[:, -1].abs().max() == 0 and b[:, :, 0].abs().max() == 0 and b[:, :, -1].abs().max() == 0
 
 
 @pytest.mark.parametrize("h,w,c,identity,full", [(20, 33, 256, False, False), (25, 42, 512, True, True), (7, 8, 64, False, True),
