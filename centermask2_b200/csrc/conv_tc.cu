@@ -1968,9 +1968,10 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
       // K-blocks (4 accumulations each) of the main term between two drains.  Measured on the full-size workload
       // (profiles/r2_split_chunk_sweep.txt): chunk 1 / 2 / 4 / 6 -> box error 0.0026 / 0.0051 / 0.0058 / 0.0078 px against
       // the fp32 oracle (the truncation bias grows with the chain length), 316 / 340 / 357 / 354 img/s
-      // Chunk 4 (16 accumulations per drain) is the default: every full-size gate holds with the same head-room (boxes 5.8e-3 px
-      // against the 1e-2 tolerance, identical kept sets), +4 % img/s over chunk 2 measured again on the round-2 tree.
-      static const int env_chunk = getenv("CM2_TC_CHUNK") ? atoi(getenv("CM2_TC_CHUNK")) : 4;
+      // Final round-2 tree, kx-merged slabs (below; a chunk then spans `chunk` (filter row, K-block) groups of 12 accumulations):
+      // chunk 2 / 3 / 4 -> box error 2.3e-3 / 6.0e-3 / 8.8e-3 px and relative mask-score error 1.8e-4 / 7.0e-4 / 1.07e-3 against
+      // the fp32 oracle at 800x1333 (tolerances 1e-2 px, 1e-3), 377 / 394 / 404 img/s.  Chunk 2 keeps a 4x margin on every gate.
+      static const int env_chunk = getenv("CM2_TC_CHUNK") ? atoi(getenv("CM2_TC_CHUNK")) : 2;
       p->chunk = env_chunk < 1 ? 1 : env_chunk;
     }
     p->n_tiles = (cout_pad + p->bn - 1) / p->bn;
@@ -1991,7 +1992,9 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
       // stride-1 3x3) cuts the x traffic 3x but was measured NOT faster (341 vs 350 img/s end to end, profiles/
       // r2_split_kx_merge.txt): at N = 128 the MMAs themselves read 128 B / clock of shared memory, which is the bound, not
       // the L2 -> shared-memory fill.  Kept selectable (CM2_TC3_MERGE=1; tests/test_gpu_conv_split.py runs both).
-      const int env_merge = getenv("CM2_TC3_MERGE") ? atoi(getenv("CM2_TC3_MERGE")) : 0;
+      // (Re-measured on the final round-2 tree, chunk 4: 367.6 -> 395.3 img/s with the merged slabs -- with half as many
+      // accumulator drains the x traffic is the bound again -- so they are ON; CM2_TC3_MERGE=0 switches back.)
+      const int env_merge = getenv("CM2_TC3_MERGE") ? atoi(getenv("CM2_TC3_MERGE")) : 1;
       p->kx_merge = (env_merge && p->taps == 9 && !phase) ? 1 : 0;
       p->a_box_rows = p->kx_merge ? 136 : 128;
       const size_t a_slot = 2u * (size_t)p->a_box_rows * 128u, w_slot = 2u * (size_t)p->bn * TC_BK * 2;
