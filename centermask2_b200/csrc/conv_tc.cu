@@ -1788,7 +1788,7 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
   const int hk = seg ? 1 : halo_kind(s0, true);
   const bool halo = hk != 0;
   TC_REQUIRE(halo || (d->kh == 1 && is_dense_view(s0, true)), "conv_tc: source 0 is neither a halo-1 view nor (for 1x1) dense");
-  TC_REQUIRE(hk != 2 || (!phase && d->out_mode != 3 && !f16), "conv_tc: shared-halo views take bf16 stride-1 convolutions without the fused predictor");
+  TC_REQUIRE(hk != 2 || (!phase && d->out_mode != 3), "conv_tc: shared-halo views take stride-1 convolutions without the fused predictor");
   for (int i = 0; i < d->num_src; ++i) {
     const cm2_act& s = d->src[i];
     TC_REQUIRE(s.c % 16 == 0 && (reinterpret_cast<uintptr_t>(s.data) & 15) == 0 && s.sw % 8 == 0 && s.sw >= s.c,
@@ -1821,7 +1821,7 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
       const cm2_seg& g = d->seg[i];
       TC_REQUIRE(g.row0 % 256 == 0 && g.row0 >= rows && g.n > 0 && g.h > 0 && g.w > 0, "conv_tc: segment %d badly placed", i);
       // g.halo: 0 = every image with its own zero frame, 1 = shared frame (line pitch w + 1, image pitch (h + 1)(w + 1); see halo_kind)
-      TC_REQUIRE(g.halo == 0 || (g.halo == 1 && !f16), "conv_tc: segment %d: halo kind %d not supported here", i, g.halo);
+      TC_REQUIRE(g.halo == 0 || g.halo == 1, "conv_tc: segment %d: halo kind %d not supported", i, g.halo);
       const int fr = g.halo == 1 ? 1 : 2;
       const long long srows = (long long)g.n * (g.h + fr) * (g.w + fr);
       TC_REQUIRE(g.row0 + srows < (1ll << 31) - 4096, "conv_tc: segment %d out of range", i);

@@ -589,10 +589,11 @@ extern "C" int cm2_groupnorm_apply_seg_split(const float* x, void* out_split, in
   int img0 = 0;
   for (int i = 0; i < num_seg; ++i) {
     CM2_CHECK_ARG(seg[i].n > 0 && seg[i].h > 0 && seg[i].w > 0 && seg[i].row0 >= end, "groupnorm_apply_seg_split: bad segment %d", i);
-    CM2_CHECK_ARG(seg[i].halo == 0, "groupnorm_apply_seg_split: shared-halo segments are not supported");
-    const long long rows = (long long)seg[i].n * (seg[i].h + 2) * (seg[i].w + 2);
+    CM2_CHECK_ARG(seg[i].halo == 0 || seg[i].halo == 1, "groupnorm_apply_seg_split: segment %d: halo kind %d not supported", i, seg[i].halo);
+    const int fr = seg[i].halo == 1 ? 1 : 2;
+    const long long rows = (long long)seg[i].n * (seg[i].h + fr) * (seg[i].w + fr);
     CM2_CHECK_ARG(seg[i].row0 + rows < (1ll << 31) - 4096, "groupnorm_apply_seg_split: segment %d out of range", i);
-    gl.row0[i] = (int)seg[i].row0; gl.pitch[i] = seg[i].w + 2; gl.plane[i] = (seg[i].h + 2) * (seg[i].w + 2);
+    gl.row0[i] = (int)seg[i].row0; gl.pitch[i] = seg[i].w + fr; gl.plane[i] = (seg[i].h + fr) * (seg[i].w + fr);
     gl.h[i] = seg[i].h; gl.w[i] = seg[i].w; gl.img0[i] = img0;
     gl.line_prefix[i + 1] = gl.line_prefix[i] + seg[i].n * seg[i].h;
     img0 += seg[i].n;

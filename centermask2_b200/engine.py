@@ -220,9 +220,9 @@ class Engine(object):
         self.tc = precision in ("bf16", "fp32")
         self.split = precision == "fp32"
         self.stem_variant = int(os.environ.get("CM2_STEM_VARIANT", "1"))      # 1: fused stem_1 (csrc/stem.cu); 0: im2col pass + K = 32 GEMM
-        self.shared_halo_roi = precision == "bf16" and os.environ.get("CM2_SHARED_HALO_ROI", "1") != "0"
+        self.shared_halo_roi = self.tc and os.environ.get("CM2_SHARED_HALO_ROI", "1") != "0"
         self.tower_overlap = int(os.environ.get("CM2_TOWER_OVERLAP", "0")) if precision == "bf16" else 0
-        self.shared_halo_seg = precision == "bf16" and os.environ.get("CM2_SHARED_HALO_SEG", "1") != "0"
+        self.shared_halo_seg = self.tc and os.environ.get("CM2_SHARED_HALO_SEG", "1") != "0"
         self.splitk_on = os.environ.get("CM2_SPLITK", "1") != "0"               # split-K for small-M layers (cm2_conv_desc.splitk)
         self.split_out_all = os.environ.get("CM2_SPLIT_OUT_ALL") == "1"       # [hi | lo] epilogue store on every eligible layer (tests)
         self._split_cache = {}
@@ -471,7 +471,12 @@ class Engine(object):
         assert buf.dtype == torch.float32 and buf.is_contiguous(), (buf.dtype, buf.stride())
         sp = self.buffer(("split",) + key, tuple(buf.shape[:-1]) + (2 * buf.shape[-1],), torch.float16, zero=False)
         lib.split_f16x2(buf, sp)
-        out = sp if isinstance(x, torch.Tensor) else (PhaseMap(sp) if isinstance(x, PhaseMap) else FMap(sp, x.halo))
+        if isinstance(x, torch.Tensor):
+            out = sp
+        elif isinstance(x, SharedHaloFMap):
+            out = SharedHaloFMap(sp, x.n, x.h, x.w)
+        else:
+            out = PhaseMap(sp) if isinstance(x, PhaseMap) else FMap(sp, x.halo)
         self._split_cache[key] = out
         return out
 
@@ -485,7 +490,7 @@ class Engine(object):
         dt = dtype or self.dtype
         # bf16 engine, tower width a multiple of 256 (GroupNorm statistics from the conv epilogue + cm2_groupnorm_apply_seg): the
         # levels share their zero frames
-        shared = self.shared_halo_seg and dt == torch.bfloat16 and c % 256 == 0
+        shared = self.shared_halo_seg and dt == self.dtype and c % 256 == 0 and 256 % (c // 8) == 0
         return SegMap(shapes, c, dt, self.device, alloc=lambda shape: self.buffer(name + ("_sh" if shared else ""), shape, dt),
                       shared_halo=shared)
 

@@ -60,7 +60,7 @@ typedef struct cm2_act {
  * shared-weight FCOS towers run on, fcos.py:227-238) stored back to back in one flat [rows, c] buffer.
  * Segment s occupies rows [row0, row0 + n*(h+2)*(w+2)) as a halo-1 block [n, h+2, w+2, c]; row0 must be a
  * multiple of 256; rows between segments are padding (ignored on input, untouched on output).
- * halo == 1 (bf16 tensor-core convolution and cm2_groupnorm_apply_seg only): the images of the segment SHARE their zero
+ * halo == 1 (tensor-core convolutions, cm2_groupnorm_apply_seg on bf16, cm2_groupnorm_apply_seg_split): the images of the segment SHARE their zero
  * frame -- line pitch w + 1, image pitch (h + 1)(w + 1) rows, n*(h+1)*(w+1) rows plus one trailing zero line + pixel
  * (w + 2 rows) that the caller keeps zero: 2.4 % instead of 9.7 % frame rows on the five FCOS levels at 800x1344. */
 typedef struct cm2_seg {
