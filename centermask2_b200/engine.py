@@ -232,6 +232,7 @@ class Engine(object):
         self._graphs = collections.OrderedDict()            # key -> (graph, result, launches, kept-alive objects)
         self._graph_seen = collections.OrderedDict()        # key -> number of eager runs so far
         self._recording = None                              # buffers touched while a plan is being captured
+        self.records_slot_free = {}                         # GeneralizedRCNN.inference_records: pipeline slot -> "inputs consumed" event
         self._det_gen = 0                                   # bumped by every run_fcos_post (see roi_heads._det_from_instances)
         self.use_graphs = os.environ.get("CM2_GRAPH", "1") != "0"
         self.graph_after = max(1, int(os.environ.get("CM2_GRAPH_AFTER", "1")))      # eager runs of a key before it is captured
@@ -361,6 +362,7 @@ class Engine(object):
         self._graph_seen.clear()
         self._bufs.clear()
         self._buf_bytes = 0
+        self.records_slot_free.clear()
 
     def drop_graphs(self, owner=None):
         """Forget captured graphs: all of them, or those whose key carries a ``graph_token`` of module ``owner`` (its

@@ -150,7 +150,7 @@ class GeneralizedRCNN(nn.Module):
         nslots = depth + 1
         state = {"staged": None, "launched": 0, "cap": int(rle_capacity)}
         pending = collections.deque()
-        slot_free = eng.__dict__.setdefault("_records_slot_free", {})      # slot -> event: that slot's step has read its inputs
+        slot_free = eng.records_slot_free                 # slot -> event: the step that last used the slot has finished
 
         # A batch lives in one of ``depth + 1`` SLOTS: its own input buffers (the H2D target), mask / run / record buffers.
         # The WHOLE step of a slot -- fused stem straight from the slot's input buffers ... paste-back, RLE, record packing --
