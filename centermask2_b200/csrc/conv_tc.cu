@@ -1968,7 +1968,7 @@ static int tc_plan(const cm2_conv_desc* d, TcParams* p, bool maps) {
       // K-blocks (4 accumulations each) of the main term between two drains.  Measured on the full-size workload
       // (profiles/r2_split_chunk_sweep.txt): chunk 1 / 2 / 4 / 6 -> box error 0.0026 / 0.0051 / 0.0058 / 0.0078 px against
       // the fp32 oracle (the truncation bias grows with the chain length), 316 / 340 / 357 / 354 img/s
-      // Final round-2 tree, kx-merged slabs (below; a chunk then spans `chunk` (filter row, K-block) groups of 12 accumulations).
+      // Final round-2 tree, kx-merged slabs (below).  A chunk = `chunk` weight tiles = 4 * chunk accumulations into the main accumulator.
       // Box error against the fp32 oracle at 800x1333 (tolerance 1e-2 px), three weight / image samples (profiles/
       // r2_parity_seeds.json):   chunk 1: 2.4e-3 / 4.3e-3 / 6.0e-3 px     chunk 2: 2.3e-3 / 5.4e-3 / 1.57e-2 px (the unmerged
       // chunk 2 of the first version: 1.65e-2 on the third sample; the CUDA-core fp32 engine: 3.5e-3 / 6.1e-3 / 4.0e-3).
