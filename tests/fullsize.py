@@ -15,9 +15,11 @@ import torch
 
 H, W = 800, 1333
 N_IMAGES = 2
-# CM2_FULLSIZE_SEEDS="weights,images": another sample of the same workload (tools/parity_report.py uses it to check that the
-# measured deviations are not a property of one pair of images; the tests always run the default)
-WEIGHT_SEED, IMAGE_SEED = (int(v) for v in os.environ.get("CM2_FULLSIZE_SEEDS", "101,202").split(","))
+# (weight seed, image seed) of the draw.  CM2_FULLSIZE_SEEDS="weights,images" changes the default for tools/parity_report.py;
+# every function below also takes ``seeds`` explicitly (tests/test_gpu_fullsize.py checks a second draw: the measured deviations
+# must not be a property of one set of random-init weights).
+DEFAULT_SEEDS = tuple(int(v) for v in os.environ.get("CM2_FULLSIZE_SEEDS", "101,202").split(","))
+WEIGHT_SEED, IMAGE_SEED = DEFAULT_SEEDS
 CAND_TARGET = 800
 BIAS_KEY = "proposal_generator.fcos_head.cls_logits.bias"
 
@@ -27,15 +29,15 @@ def _fields(inst):
 
 
 @functools.lru_cache(maxsize=None)
-def workload():
+def workload(seeds=DEFAULT_SEEDS):
     """cfg-independent pieces: state_dict with the calibrated cls bias (picked from the fp32 oracle's own logits, so the
     workload does not depend on any device result) and the uint8 inputs."""
     from centermask2_b200.config import get_cfg
     from centermask2_b200.synth import synthetic_images, synthetic_state_dict, calibrate_cls_bias
     from oracle import restate
     cfg = get_cfg("centermask_V_39_eSE_FPN.yaml")
-    sd = synthetic_state_dict(cfg, seed=WEIGHT_SEED)
-    imgs = synthetic_images(N_IMAGES, H, W, seed=IMAGE_SEED)
+    sd = synthetic_state_dict(cfg, seed=seeds[0])
+    imgs = synthetic_images(N_IMAGES, H, W, seed=seeds[1])
     for b in imgs:
         b["image"] = b["image"].to(torch.uint8)           # what a data loader hands over
     sd[BIAS_KEY] = torch.zeros_like(sd[BIAS_KEY])
@@ -50,11 +52,11 @@ def _float_inputs(imgs):
 
 
 @functools.lru_cache(maxsize=None)
-def oracle_outputs(bf16):
+def oracle_outputs(bf16, seeds=DEFAULT_SEEDS):
     """(raw, post, trace) of the oracle; ``bf16`` selects the bf16-rounding restatement."""
     from centermask2_b200.config import get_cfg
     from oracle import restate
-    sd, imgs = workload()
+    sd, imgs = workload(seeds)
     cfg = get_cfg("centermask_V_39_eSE_FPN.yaml")
     tr = {}
     with restate.bf16_sim(bool(bf16)):
@@ -172,12 +174,12 @@ def compare(got_raw, got_post, ref_raw, ref_post, feat_hw=None, box_tol=1e-2):
     return rep
 
 
-def device_outputs(precision):
+def device_outputs(precision, seeds=DEFAULT_SEEDS):
     """(raw, post) of the registered B200 model at ``precision`` (fields on the CPU)."""
     import centermask2_b200 as cm
     from centermask2_b200 import runtime
     from centermask2_b200.config import get_cfg
-    sd, imgs = workload()
+    sd, imgs = workload(seeds)
     runtime.reset()
     try:
         cfg = get_cfg("centermask_V_39_eSE_FPN.yaml", ["MODEL.B200.PRECISION", precision])
@@ -191,18 +193,19 @@ def device_outputs(precision):
     return raw, post
 
 
-def deviation_report(precision):
+def deviation_report(precision, seeds=DEFAULT_SEEDS):
     bf16 = precision == "bf16"
-    ref_raw, ref_post, tr = oracle_outputs(bf16)
-    got_raw, got_post = device_outputs(precision)
+    ref_raw, ref_post, tr = oracle_outputs(bf16, seeds)
+    got_raw, got_post = device_outputs(precision, seeds)
     feat_hw = {l: tuple(tr["features"]["p{}".format(3 + l)].shape[-2:]) for l in range(3)}
     rep = compare(got_raw, got_post, ref_raw, ref_post, feat_hw)
     rep["precision"] = precision
+    rep["seeds"] = list(seeds)
     rep["oracle"] = "restate.bf16_sim()" if bf16 else "restate (fp32)"
     rep["margins"] = margins(ref_raw, tr)
     if bf16:
         # for the record: the bf16 engine against the PURE fp32 oracle (what a user switching precision sees)
-        f_raw, f_post, _ = oracle_outputs(False)
+        f_raw, f_post, _ = oracle_outputs(False, seeds)
         raw32 = compare(got_raw, got_post, f_raw, f_post, feat_hw)
         rep["vs_fp32_oracle"] = {k: raw32[k] for k in ("overlap", "box_px", "score", "mask_score_rel", "mask_iou_min",
                                                         "mask_iou_median", "mask_iou_below_0p99", "masks_compared")

@@ -35,6 +35,21 @@ def test_fp32_engines_meet_the_north_star_tolerances_at_800x1333(precision):
     assert rep["mask_iou_failures"] == 0 and rep["masks_compared"] == sum(rep["kept_ref"]) - rep["roialign_ill_posed"], rep
 
 
+def test_fp32_engine_holds_the_tolerances_on_a_second_draw_of_the_weights():
+    """The deviations above must not be a property of one set of random-init weights: the tensor-core fp32 engine on another
+    draw (weight seed 31, image seed 32).  This is the draw on which an accumulator chunk of 2 weight tiles (the setting of
+    the first version of the split kernel) misses the box tolerance -- 1.57e-2 px -- while chunk 1, the default, measures
+    6.0e-3 px (profiles/r2_parity_seeds.json; the CUDA-core fp32 engine: 4.0e-3).  The 28x28 mask-probability gate is left to
+    the default draw: on this one the plain-fp32 CUDA-core engine itself sits at 0.9e-3 of the 1e-3 limit."""
+    rep = fullsize.deviation_report("fp32", seeds=(31, 32))
+    print("full-size parity [fp32, weights 31 / images 32]: {}".format(json.dumps(rep)))
+    assert rep["kept_got"] == rep["kept_ref"] and rep["overlap"] == 1.0 and rep["same_order"], rep
+    assert min(rep["kept_ref"]) > 0
+    assert rep["box_px"] <= BOX_TOL_PX and rep["post_box_px"] <= BOX_TOL_PX, rep
+    assert rep["score"] <= SCORE_TOL and rep["mask_score_rel"] <= SCORE_TOL, rep
+    assert rep["mask_iou_failures"] == 0, rep
+
+
 # bf16 engine vs the bf16-rounding oracle.  Measured on B200 (profiles/r2_parity_fullsize.json): 94 of the oracle's 100
 # kept detections kept; over those: boxes <= 3.3 px, scores <= 1.2e-2, mask_scores <= 0.35 relative, 28x28 mask
 # probabilities <= 6e-5, pasted-mask IoU: median 1.0, minimum 0.973, 12 of 94 below 0.99.  The two sides differ by
