@@ -553,9 +553,9 @@ extern "C" int cm2_groupnorm_apply_seg(void* x, int32_t dtype, int32_t c, int32_
       gl.img0[i] = g.img0[i];
       gl.line_prefix[i + 1] = gl.line_prefix[i] + seg[i].n * seg[i].h;
     }
-    // CTAs of 128 threads (58 registers each: 7.4 K) fit beside a resident convolution CTA (320 threads x 168 registers = 53.8 K of
-    // the SM's 64 K, no shared memory needed here): the pass of one FCOS tower then runs UNDER the other tower's convolution
-    // (Engine.run_fcos_head puts the towers on two streams); alone it reaches the same occupancy with twice the CTAs per SM
+    // 128-thread CTAs: measured 0.48 against 0.50 ms per step for 256 (more CTAs in flight per SM).  (They would also fit beside
+    // a resident convolution CTA -- 58 registers x 128 against the 11.7 K the convolution leaves free -- but running the pass under
+    // the other tower's convolution was measured slower: Engine.tower_overlap, off.)
     static const int apply_threads = getenv("CM2_GN_APPLY_THREADS") ? atoi(getenv("CM2_GN_APPLY_THREADS")) : 128;
     gn_seg_apply_lines_kernel<<<gl.line_prefix[num_seg], apply_threads, 0, s>>>((__nv_bfloat16*)x, c, c / groups, gl, stats, gamma, beta, eps, relu);
     CM2_CHECK_LAUNCH("gn_seg_apply_lines");
@@ -646,7 +646,8 @@ extern "C" int cm2_ese_apply_pool(const cm2_act* x, const float* gate, const cm2
     CM2_CHECK_ARG(total < (1ll << 32) - (1ll << 24), "ese_apply_pool: too many elements for 32-bit indexing");
     const int c8 = x->c / 8;
     if (dtype == CM2_BF16 && c8 <= 256 && x->n <= 65535) {
-      const int threads = c8 * std::max(1, 256 / c8);
+      static const int max_threads = getenv("CM2_ESE_APPLY_THREADS") ? atoi(getenv("CM2_ESE_APPLY_THREADS")) : 256;
+      const int threads = c8 * std::max(1, max_threads / c8);
       dim3 grid(po.h, x->n);
       View<const __nv_bfloat16> vx = make_view<const __nv_bfloat16>(*x), vi = make_view<const __nv_bfloat16>(idn);
       View<__nv_bfloat16> vf = make_view<__nv_bfloat16>(fu), vp = make_view<__nv_bfloat16>(po);
