@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace cm2 {
 
@@ -1195,6 +1196,422 @@ __global__ void __launch_bounds__(32 * (ROI_RING_COLS + 1), 2) roialign_ring_ker
 }
 
 // ---------------------------------------------------------------------------------------------
+// ROIAlign with the X PASS ON THE TENSOR CORES (variant 4, CM2_ROIALIGN_VARIANT=4; bf16 maps, res <= 16, c % 32 == 0).
+// ncu of the column walk (variant 2): ~140 M warp instructions at cfg 5, two thirds of them the bf16 unpack + FMA of the
+// x pass.  The x pass of one feature row of an ROI is a small GEMM,
+//   T[pw, ch] = sum_X Wx[pw, X] * f[Y, X, ch]          (M = 16 padded bin columns, K = the ROI's pixel columns, N = channels),
+// so it runs on the warp-level tensor-core path here (mma.sync.m16n8k16, bf16 x bf16 -> fp32); the SIMT pipes keep the y pass
+// (out[ph] += Wy[ph][Y] * T on the accumulator fragments, with the same carried-row bookkeeping as roi_col_walk) and the
+// stores.  The fp32 x weights are split into bf16 hi + lo (two MMAs into the same accumulator; the feature values are bf16
+// already, so every product is exact in fp32 and the result differs from the SIMT walk by summation order only;
+// SPLIT = false keeps hi alone: 2^-9 relative weight error, measured as an alternative, not used).
+// One CTA per ROI (c / 32 warps), launched largest-first like the column kernel.  The tables (y weights / carry counts by
+// warp 0, dense x weights [16][K] by the last warp) are built once per ROI; after that the warps never meet again: warp w
+// owns channels [32 w, 32 w + 32) and stages ITS OWN 64-byte slice of every pixel of a row through a private ring of
+// STAGES slots (cp.async 16 B, zero-filled past the last tap column; 80-byte pixel pitch = conflict-free ldmatrix.trans),
+// so the loop needs cp.async.wait_group + __syncwarp only.  A ring item is (feature row, chunk of <= 32 pixel columns);
+// the MMA accumulators run over the chunks of a row.  ROIs whose tap range exceeds ROI_MMA_KMAX columns or whose rows do not
+// follow each other without a gap use the sample loop.  Non-finite feature values spread over the bin columns of their
+// row chunk (0 * inf in the dense weight matrix) -- the SIMT variants confine them to the bins that tap them.
+// ---------------------------------------------------------------------------------------------
+constexpr int ROI_MMA_M = 16;                            // bin columns of the weight operand (res <= 16)
+constexpr int ROI_MMA_KC = 32;                           // pixel columns per ring item (two k tiles)
+constexpr int ROI_MMA_KMAX = 128;                        // widest tap range (pixel columns) the tensor-core walk handles
+constexpr int ROI_MMA_APITCH = ROI_MMA_KMAX + 8;         // bf16 per weight row: 272 B, 8 rows hit 8 different bank groups
+constexpr int ROI_MMA_PIX = 80;                          // bytes per staged pixel of one warp: 64 B of channels + 16 B pad
+constexpr int ROI_MMA_SLOT = ROI_MMA_KC * ROI_MMA_PIX;   // bytes per ring slot of one warp
+
+inline int roi_mma_smem_bytes(int c, int stages) {
+  return std::max((c / 32) * stages * ROI_MMA_SLOT, ROI_MMA_M * ROI_MMA_KMAX * 4);     // the fp32 x table aliases the rings
+}
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t saddr, const void* g, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(src_bytes) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_n() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldsm_x4(uint32_t saddr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t saddr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr) : "memory");
+}
+// d += a (16 x 16, row) * b (16 x 8, col), fp32 accumulation
+__device__ __forceinline__ void mma_bf16_m16n8k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// d = a * b (the accumulator registers need no zeroing before the first k tile of a row)
+__device__ __forceinline__ void mma_bf16_m16n8k16_zero(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%10, %10, %10, %10};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+__device__ __forceinline__ void roi_fma16(float (&acc)[4][4], float w, const float (&v)[4][4]) {
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    ffma2_roi(acc[nt][0], acc[nt][1], v[nt][0], v[nt][1], w);
+    ffma2_roi(acc[nt][2], acc[nt][3], v[nt][2], v[nt][3], w);
+  }
+}
+
+// SW: compile-time pixel stride of the feature maps in elements (0 = run-time); MINB: CTAs per SM the register budget allows
+template <int STAGES, bool SPLIT, int SW, int MINB>
+__global__ void __launch_bounds__(256, MINB) roialign_mma_kernel(const RoiAlignParams<__nv_bfloat16> p) {
+  using T = __nv_bfloat16;
+  extern __shared__ __align__(128) unsigned char s_mma[];
+  __shared__ __align__(16) T s_a[2][ROI_MMA_M][ROI_MMA_APITCH];              // x weights, bf16 hi / lo, [bin column][pixel column]
+  __shared__ float s_wy[ROI_MMA_M * ROI_WYT];
+  __shared__ int s_ny[ROI_MMA_M], s_carry[ROI_MMA_M];
+  __shared__ int s_info[6];                             // y_first, y_end, rows walkable, first tap column, tap columns, x bad
+  const int res = p.res, c8 = p.out.c >> 3;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int slot = p.order[blockIdx.x];
+  const int img = slot / p.r_cap, r = slot - img * p.r_cap;
+  auto fill_zero = [&]() {
+    const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = tid; i < res * res * c8; i += blockDim.x) {
+      const int bin = i / c8, cv = i - bin * c8;
+      const int ph = bin / res, pw = bin - ph * res;
+      Vec8<T>::store(p.out.at(slot, ph, pw) + cv * 8, z);
+    }
+  };
+  if (r >= p.det_count[img]) {                          // empty slot: zeros (CTA-uniform)
+    fill_zero();
+    return;
+  }
+  const float4 bx = reinterpret_cast<const float4*>(p.boxes)[slot];
+  int lvl = assign_level(bx.x, bx.y, bx.z, bx.w, p.image_area[img], p.crit, p.min_level, p.max_level);
+  if (lvl >= p.num_levels) lvl = p.num_levels - 1;
+  if (p.level_out && tid == 0) p.level_out[slot] = lvl;
+  View<const T> f = p.feat[0];
+  float scale = p.scale[0];
+#pragma unroll
+  for (int l = 1; l < ROI_MAX_LEVELS; ++l)
+    if (l == lvl) { f = p.feat[l]; scale = p.scale[l]; }
+  const float roi_start_w = bx.x * scale - 0.5f, roi_start_h = bx.y * scale - 0.5f;
+  const float roi_end_w = bx.z * scale - 0.5f, roi_end_h = bx.w * scale - 0.5f;
+  const float roi_width = roi_end_w - roi_start_w, roi_height = roi_end_h - roi_start_h;
+  const float bin_h = roi_height / (float)res, bin_w = roi_width / (float)res;
+  const int grid_h = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(roi_height / (float)res);
+  const int grid_w = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(roi_width / (float)res);
+  const float inv_count = 1.0f / fmaxf((float)(grid_h * grid_w), 1.f);
+  const T* img_base = f.p + (size_t)img * f.sn;
+  const unsigned full = 0xffffffffu;
+
+  // ---- tables
+  float* s_wxf = reinterpret_cast<float*>(s_mma);       // [ROI_MMA_M][ROI_MMA_KMAX] fp32 x weights (the rings come later)
+  for (int i = tid; i < ROI_MMA_M * ROI_MMA_KMAX; i += blockDim.x) s_wxf[i] = 0.f;
+  for (int i = tid; i < ROI_MMA_M * ROI_WYT; i += blockDim.x) s_wy[i] = 0.f;
+  __syncthreads();
+  if (warp == 0) {                                      // y weights (lane = bin row) and the carry bookkeeping of the walk
+    int t0 = 0, tn = 0;
+    bool bad = false;
+    if (lane < res) {
+      float* wrow = s_wy + lane * ROI_WYT;
+      int s0 = -1;
+      for (int i = 0; i < grid_h; ++i) {
+        const float v = roi_start_h + lane * bin_h + ((float)i + 0.5f) * bin_h / (float)grid_h;
+        if (v < -1.0f || v > (float)f.h) continue;
+        float vv = v <= 0.f ? 0.f : v;
+        int low = (int)vv, high;
+        if (low >= f.h - 1) { high = low = f.h - 1; vv = (float)low; } else high = low + 1;
+        const float l = vv - (float)low, h = 1.f - l;
+        if (s0 < 0) s0 = low;
+        if (high - s0 >= ROI_WYT) { bad = true; break; }
+        wrow[low - s0] += h * inv_count;                // 1 / count folded into the y weights
+        wrow[high - s0] += l * inv_count;
+        tn = high - s0 + 1;
+      }
+      t0 = s0 < 0 ? 0 : s0;
+    }
+    // rows of the bins above end at y_done; rows y_done - 1, y_done are carried in (cp, cl)
+    const bool ybin = lane < res && tn > 0;
+    int pm = ybin ? t0 + tn - 1 : -1;                   // inclusive prefix max of the last row of a bin
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(full, pm, o);
+      if (lane >= o) pm = max(pm, t);
+    }
+    int y_done = __shfl_up_sync(full, pm, 1);
+    if (lane == 0) y_done = -1;
+    int y_first = ybin ? t0 : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) y_first = min(y_first, __shfl_xor_sync(full, y_first, o));
+    int y_end = __shfl_sync(full, pm, 31) + 1;
+    if (y_first == 0x7fffffff) { y_first = 0; y_end = 0; }
+    int cy = 0;
+    if (ybin && y_done >= 0) {
+      cy = y_done - t0 + 1;
+      if (cy < 0 || cy > min(2, y_done - y_first + 1)) bad = true;      // gap, or a row that is not carried any more
+    }
+    const bool walk_y = !__any_sync(full, bad);
+    if (lane < ROI_MMA_M) { s_ny[lane] = lane < res ? tn : 0; s_carry[lane] = cy; }
+    if (lane == 0) { s_info[0] = y_first; s_info[1] = y_end; s_info[2] = walk_y ? 1 : 0; }
+  }
+  if (warp == nwarps - 1) {                             // x weights: lane = bin column, dense rows over the ROI's tap columns
+    int xlo = 0x7fffffff, xhi = -1;
+    if (lane < res) {
+      for (int i = 0; i < grid_w; ++i) {                // pass 1: the tap range (taps are monotone in i)
+        const float v = roi_start_w + lane * bin_w + ((float)i + 0.5f) * bin_w / (float)grid_w;
+        if (v < -1.0f || v > (float)f.w) continue;
+        const float vv = v <= 0.f ? 0.f : v;
+        int low = (int)vv, high;
+        if (low >= f.w - 1) high = low = f.w - 1; else high = low + 1;
+        xlo = min(xlo, low);
+        xhi = max(xhi, high);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      xlo = min(xlo, __shfl_xor_sync(full, xlo, o));
+      xhi = max(xhi, __shfl_xor_sync(full, xhi, o));
+    }
+    const int kx = xhi >= 0 ? xhi - xlo + 1 : 0;
+    const bool xbad = kx > ROI_MMA_KMAX;
+    if (!xbad && kx > 0 && lane < res) {
+      float* wrow = s_wxf + lane * ROI_MMA_KMAX;
+      for (int i = 0; i < grid_w; ++i) {                // pass 2: the weights
+        const float v = roi_start_w + lane * bin_w + ((float)i + 0.5f) * bin_w / (float)grid_w;
+        if (v < -1.0f || v > (float)f.w) continue;
+        float vv = v <= 0.f ? 0.f : v;
+        int low = (int)vv, high;
+        if (low >= f.w - 1) { high = low = f.w - 1; vv = (float)low; } else high = low + 1;
+        const float l = vv - (float)low, h = 1.f - l;
+        wrow[low - xlo] += h;
+        wrow[high - xlo] += l;
+      }
+    }
+    if (lane == 0) { s_info[3] = kx > 0 ? xlo : 0; s_info[4] = kx; s_info[5] = xbad ? 1 : 0; }
+  }
+  __syncthreads();
+  const int y_first = s_info[0], nrows = s_info[1] - s_info[0], x_first = s_info[3], kx = s_info[4];
+  const bool walk = s_info[2] != 0 && s_info[5] == 0;
+  if (walk && (nrows <= 0 || kx <= 0)) {                // nothing inside the feature map: zeros
+    fill_zero();
+    return;
+  }
+  if (!walk) {                                          // sample loop (torchvision's own order of evaluation), a warp per bin
+#pragma unroll 1
+    for (int bin = warp; bin < res * res; bin += nwarps) {
+      const int ph = bin / res, pw = bin - ph * res;
+#pragma unroll 1
+      for (int cv = lane; cv < c8; cv += 32) {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        roialign_sample_loop<T>(f, img, cv, ph, pw, roi_start_h, roi_start_w, bin_h, bin_w, grid_h, grid_w, acc);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] *= inv_count;
+        Vec8<T>::store(p.out.at(slot, ph, pw) + cv * 8, acc);
+      }
+    }
+    return;
+  }
+  const int nchunk = (kx + ROI_MMA_KC - 1) / ROI_MMA_KC, kpad = nchunk * ROI_MMA_KC;
+  for (int i = tid; i < ROI_MMA_M * kpad; i += blockDim.x) {                  // fp32 -> bf16 hi + lo
+    const int row = i / kpad, k = i - row * kpad;
+    const float w = s_wxf[row * ROI_MMA_KMAX + k];
+    const T hi = __float2bfloat16_rn(w);
+    s_a[0][row][k] = hi;
+    s_a[1][row][k] = __float2bfloat16_rn(w - __bfloat162float(hi));
+  }
+  __syncthreads();                                      // the fp32 table is dead: its memory becomes the rings
+
+  // ---- the walk of this warp's 32 channels
+  const uint32_t wring = (uint32_t)__cvta_generic_to_shared(s_mma) + warp * (STAGES * ROI_MMA_SLOT);
+  const int mat = lane >> 3, r8 = lane & 7;
+  // ldmatrix row addresses: A (weights) matrices = (rows 0-7 | 8-15) x (k 0-7 | 8-15); B (pixels, transposed on load)
+  // matrices = (pixels 0-7 | 8-15) x (channels 0-7 | 8-15) of a 16-channel pair of n tiles
+  const uint32_t a_hi = (uint32_t)__cvta_generic_to_shared(&s_a[0][0][0]) + ((r8 + (mat & 1) * 8) * ROI_MMA_APITCH + (mat >> 1) * 8) * 2;
+  constexpr uint32_t A_LO = ROI_MMA_M * ROI_MMA_APITCH * 2;
+  const uint32_t b_lane = wring + (r8 + (mat & 1) * 8) * ROI_MMA_PIX + (mat >> 1) * 16;
+  // copy role of a lane: pixel cpx (+ 8, 16, 24) of the chunk, 16-byte quarter cq of the warp's 64 bytes per pixel -- the 8
+  // lanes of a quarter warp write 8 different pixels (80-byte pitch: 8 different bank groups, like the ldmatrix rows).
+  // Element offsets inside an image fit 32 bits (the host checks sn < 2^31).
+  const int cpx = lane & 7, cq = lane >> 3;
+  const int sw32 = SW ? SW : (int)f.sw, sh32 = (int)f.sh;
+  const T* iss_src = img_base + (y_first * sh32 + (x_first + cpx) * sw32 + warp * 32 + cq * 8);   // this lane's pixel of the next item
+  const uint32_t lane_dst = wring + cpx * ROI_MMA_PIX + cq * 16;
+  int iss_left = nrows * nchunk;
+  uint32_t iss_slot = 0, cons_slot = 0;
+  const int g = lane >> 2, t4 = lane & 3;
+  T* outp = p.out.at(slot, 0, 0) + warp * 32 + t4 * 8;
+  const int out_sw = (int)p.out.sw;
+
+  float cl[4][4], cp[4][4];                             // x-passed rows y_done (cl) and y_done - 1 (cp): [n tile][fragment]
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cl[nt][k] = cp[nt][k] = 0.f;
+  // cl (+)= Wx[:, 16 columns] * f[row, 16 columns, 32 channels]; FRESH: the first k tile of a row overwrites cl
+  auto ktile = [&](const uint32_t (&ahi)[4], const uint32_t (&alo)[4], uint32_t baddr, auto fresh) {
+    constexpr bool FRESH = decltype(fresh)::value;
+    uint32_t b0[4], b1[4];
+    ldsm_x4_trans(baddr, b0);
+    ldsm_x4_trans(baddr + 32, b1);
+    if (FRESH) {
+      mma_bf16_m16n8k16_zero(cl[0], ahi, b0[0], b0[1]);
+      mma_bf16_m16n8k16_zero(cl[1], ahi, b0[2], b0[3]);
+      mma_bf16_m16n8k16_zero(cl[2], ahi, b1[0], b1[1]);
+      mma_bf16_m16n8k16_zero(cl[3], ahi, b1[2], b1[3]);
+    } else {
+      mma_bf16_m16n8k16(cl[0], ahi, b0[0], b0[1]);
+      mma_bf16_m16n8k16(cl[1], ahi, b0[2], b0[3]);
+      mma_bf16_m16n8k16(cl[2], ahi, b1[0], b1[1]);
+      mma_bf16_m16n8k16(cl[3], ahi, b1[2], b1[3]);
+    }
+    if (SPLIT) {
+      mma_bf16_m16n8k16(cl[0], alo, b0[0], b0[1]);
+      mma_bf16_m16n8k16(cl[1], alo, b0[2], b0[3]);
+      mma_bf16_m16n8k16(cl[2], alo, b1[0], b1[1]);
+      mma_bf16_m16n8k16(cl[3], alo, b1[2], b1[3]);
+    }
+  };
+  auto ktile_smem = [&](uint32_t aaddr, uint32_t baddr, auto fresh) {       // weights fetched per k tile
+    uint32_t ahi[4], alo[4] = {0u, 0u, 0u, 0u};
+    ldsm_x4(aaddr, ahi);
+    if (SPLIT) ldsm_x4(aaddr + A_LO, alo);
+    ktile(ahi, alo, baddr, fresh);
+  };
+  // 4 x 4 transpose of one 32-bit word per (lane of a quad, n tile): afterwards lane t4 holds the 8 consecutive channels
+  // 8 t4 .. 8 t4 + 7 of a bin column as four bf16 pairs -> one 16-byte store per lane instead of four 4-byte stores
+  auto quad_transpose = [&](uint32_t (&v)[4]) {
+    const bool b1 = (t4 & 2) != 0, b0 = (t4 & 1) != 0;
+    uint32_t x = b1 ? v[0] : v[2], y = b1 ? v[1] : v[3];
+    x = __shfl_xor_sync(full, x, 2);
+    y = __shfl_xor_sync(full, y, 2);
+    if (b1) { v[0] = x; v[1] = y; } else { v[2] = x; v[3] = y; }
+    x = b0 ? v[0] : v[1];
+    y = b0 ? v[2] : v[3];
+    x = __shfl_xor_sync(full, x, 1);
+    y = __shfl_xor_sync(full, y, 1);
+    if (b0) { v[0] = x; v[2] = y; } else { v[1] = x; v[3] = y; }
+  };
+  auto pack2 = [](float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  };
+
+  // SINGLE: the tap range fits one chunk (<= 32 columns, the common case): an item is a whole feature row, the weight
+  // fragments of its one or two k tiles stay in registers for the whole ROI and the copy predicates are ROI constants
+  auto run = [&](auto single) {
+    constexpr bool SINGLE = decltype(single)::value;
+    // ---- SINGLE state
+    const int rem0 = kx - cpx;                          // pixel cpx + 8 i is a tap column iff rem0 > 8 i
+    const bool two = kx > 16;                           // second k tile
+    uint32_t w0hi[4] = {0u, 0u, 0u, 0u}, w0lo[4] = {0u, 0u, 0u, 0u}, w1hi[4] = {0u, 0u, 0u, 0u}, w1lo[4] = {0u, 0u, 0u, 0u};
+    if (SINGLE) {
+      ldsm_x4(a_hi, w0hi);
+      if (SPLIT) ldsm_x4(a_hi + A_LO, w0lo);
+      if (two) {
+        ldsm_x4(a_hi + 32, w1hi);
+        if (SPLIT) ldsm_x4(a_hi + 32 + A_LO, w1lo);
+      }
+    }
+    // ---- chunked state
+    const int row_wrap = sh32 - (nchunk - 1) * ROI_MMA_KC * sw32;    // from the last chunk of a row to the first of the next
+    int iss_rem = rem0;
+    // whole k tiles are written; columns past the last tap are zero-filled (src-size 0: nothing is read)
+    auto issue_next = [&]() {
+      if (iss_left > 0) {
+        const uint32_t dst = lane_dst + iss_slot;
+        if (SINGLE) {
+          cp_async16_zfill(dst, iss_src, rem0 > 0 ? 16u : 0u);
+          cp_async16_zfill(dst + 8 * ROI_MMA_PIX, iss_src + 8 * sw32, rem0 > 8 ? 16u : 0u);
+          if (two) {
+            cp_async16_zfill(dst + 16 * ROI_MMA_PIX, iss_src + 16 * sw32, rem0 > 16 ? 16u : 0u);
+            cp_async16_zfill(dst + 24 * ROI_MMA_PIX, iss_src + 24 * sw32, rem0 > 24 ? 16u : 0u);
+          }
+          iss_src += sh32;
+        } else {
+          cp_async16_zfill(dst, iss_src, iss_rem > 0 ? 16u : 0u);
+          cp_async16_zfill(dst + 8 * ROI_MMA_PIX, iss_src + 8 * sw32, iss_rem > 8 ? 16u : 0u);
+          if (iss_rem + cpx > 16) {
+            cp_async16_zfill(dst + 16 * ROI_MMA_PIX, iss_src + 16 * sw32, iss_rem > 16 ? 16u : 0u);
+            cp_async16_zfill(dst + 24 * ROI_MMA_PIX, iss_src + 24 * sw32, iss_rem > 24 ? 16u : 0u);
+          }
+          iss_rem -= ROI_MMA_KC;
+          if (iss_rem + cpx <= 0) { iss_rem = rem0; iss_src += row_wrap; } else iss_src += ROI_MMA_KC * sw32;
+        }
+        --iss_left;
+        iss_slot += ROI_MMA_SLOT;
+        if (iss_slot == STAGES * ROI_MMA_SLOT) iss_slot = 0;
+      }
+      cp_async_commit();                                // one group per step, empty or not: the wait count stays fixed
+    };
+#pragma unroll 1
+    for (int d = 0; d < STAGES - 1; ++d) issue_next();
+
+#pragma unroll 1
+    for (int ph = 0; ph < res; ++ph, outp += p.out.sh) {
+      float acc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[nt][k] = 0.f;
+      const int ny = s_ny[ph];
+      const float* wy = s_wy + ph * ROI_WYT;
+      const int cy = s_carry[ph];                       // leading rows of this bin that are x-passed already
+      int j = 0;
+      if (cy == 2) {
+        roi_fma16(acc, wy[0], cp);
+        if (ny > 1) roi_fma16(acc, wy[1], cl);
+        j = 2;
+      } else if (cy == 1) {
+        roi_fma16(acc, wy[0], cl);
+        j = 1;
+      }
+#pragma unroll 1
+      for (; j < ny; ++j) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) cp[nt][k] = cl[nt][k];
+        if (SINGLE) {
+          cp_async_wait_n<STAGES - 2>();                // this lane's copies of the row have landed ...
+          __syncwarp();                                 // ... and so have the other lanes'; the slot of the previous row is free
+          issue_next();
+          const uint32_t baddr = b_lane + cons_slot;
+          ktile(w0hi, w0lo, baddr, std::true_type());
+          if (two) ktile(w1hi, w1lo, baddr + 16 * ROI_MMA_PIX, std::false_type());
+          cons_slot += ROI_MMA_SLOT;
+          if (cons_slot == STAGES * ROI_MMA_SLOT) cons_slot = 0;
+        } else {
+          int kb = 0;
+#pragma unroll 1
+          do {                                          // the chunks of one feature row
+            cp_async_wait_n<STAGES - 2>();
+            __syncwarp();
+            issue_next();
+            const uint32_t aaddr = a_hi + kb * 2, baddr = b_lane + cons_slot;
+            if (kb == 0) ktile_smem(aaddr, baddr, std::true_type()); else ktile_smem(aaddr, baddr, std::false_type());
+            if (kx - kb > 16) ktile_smem(aaddr + 32, baddr + 16 * ROI_MMA_PIX, std::false_type());
+            cons_slot += ROI_MMA_SLOT;
+            if (cons_slot == STAGES * ROI_MMA_SLOT) cons_slot = 0;
+            kb += ROI_MMA_KC;
+          } while (kb < kx);
+        }
+        roi_fma16(acc, wy[j], cl);
+      }
+      // fragment rows = bin columns g and g + 8, fragment columns = channels 2 t4, 2 t4 + 1 of each n tile
+      uint32_t v[4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) v[nt] = pack2(acc[nt][0], acc[nt][1]);
+      quad_transpose(v);
+      if (g < res) *reinterpret_cast<uint4*>(outp + g * out_sw) = make_uint4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) v[nt] = pack2(acc[nt][2], acc[nt][3]);
+      quad_transpose(v);
+      if (g + 8 < res) *reinterpret_cast<uint4*>(outp + (g + 8) * out_sw) = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+  };
+  if (nchunk == 1) run(std::true_type()); else run(std::false_type());
+  cp_async_wait_n<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
 // predictor restricted to the predicted class + sigmoid (sam.py:97, mask_head.py:196-216).
 // warp per output pixel; lanes stride over channels.
 // ---------------------------------------------------------------------------------------------
@@ -1670,7 +2087,43 @@ static int roialign_launch(const cm2_act* feats, const int32_t* feat_stride, int
     roialign_ring_kernel<T><<<n * r_cap * ((p.res + ROI_RING_COLS - 1) / ROI_RING_COLS), 32 * (ROI_RING_COLS + 1), ROI_RING_BYTES, s>>>(p);
     return 0;
   }
-  if (variant == 2 && workspace && p.res < 32 && small && out->c <= 256) {   // lane 31 builds the x table, lanes < res the y table
+  if constexpr (sizeof(T) == 2) {
+    if (variant == 4 && workspace && p.res <= ROI_MMA_M && small && out->c % 32 == 0 && out->c <= 256) {
+      const int stages = getenv("CM2_ROIALIGN_STAGES") ? atoi(getenv("CM2_ROIALIGN_STAGES")) : 4;
+      const bool split = !(getenv("CM2_ROIALIGN_SPLIT") && atoi(getenv("CM2_ROIALIGN_SPLIT")) == 0);
+      const int minb = getenv("CM2_ROIALIGN_MINB") ? atoi(getenv("CM2_ROIALIGN_MINB")) : 2;
+      CM2_CHECK_ARG(stages >= 3 && stages <= 4, "roialign: CM2_ROIALIGN_STAGES %d not in [3,4]", stages);
+      CM2_CHECK_ARG(minb >= 2 && minb <= 3, "roialign: CM2_ROIALIGN_MINB %d not in [2,3]", minb);
+      bool sw256 = true;
+      for (int l = 0; l < num_levels; ++l) sw256 = sw256 && feats[l].sw == 256;
+      const int smem = roi_mma_smem_bytes(out->c, stages);
+      roi_order_kernel<T><<<1, 1024, 0, s>>>(p);
+#define CM2_ROI_MMA_LAUNCH(ST, SP, SWV, MB)                                                                   \
+  do {                                                                                                        \
+    CM2_ENSURE_DYN_SMEM((roialign_mma_kernel<ST, SP, SWV, MB>), smem, "roialign_mma");                        \
+    roialign_mma_kernel<ST, SP, SWV, MB><<<n * r_cap, out->c, smem, s>>>(p);                                  \
+  } while (0)
+#define CM2_ROI_MMA_LAUNCH_SW(ST, SP, MB)                                                                     \
+  do {                                                                                                        \
+    if (sw256) CM2_ROI_MMA_LAUNCH(ST, SP, 256, MB); else CM2_ROI_MMA_LAUNCH(ST, SP, 0, MB);                   \
+  } while (0)
+#define CM2_ROI_MMA_LAUNCH_SP(ST, MB)                                                                         \
+  do {                                                                                                        \
+    if (split) CM2_ROI_MMA_LAUNCH_SW(ST, true, MB); else CM2_ROI_MMA_LAUNCH_SW(ST, false, MB);                \
+  } while (0)
+      if (minb == 3) {
+        if (stages == 3) CM2_ROI_MMA_LAUNCH_SP(3, 3); else CM2_ROI_MMA_LAUNCH_SP(4, 3);
+      } else {
+        if (stages == 3) CM2_ROI_MMA_LAUNCH_SP(3, 2); else CM2_ROI_MMA_LAUNCH_SP(4, 2);
+      }
+#undef CM2_ROI_MMA_LAUNCH_SP
+#undef CM2_ROI_MMA_LAUNCH_SW
+#undef CM2_ROI_MMA_LAUNCH
+      return 0;
+    }
+  }
+  // variant 4 on fp32 maps / other shapes: the column walk
+  if ((variant == 2 || variant == 4) && workspace && p.res < 32 && small && out->c <= 256) {   // lane 31 builds the x table, lanes < res the y table
     roi_order_kernel<T><<<1, 1024, 0, s>>>(p);
     roialign_col_kernel<T><<<n * r_cap * p.res, 32, roi_col_smem_bytes(p.res), s>>>(p);
     return 0;

@@ -188,10 +188,11 @@ def _random_boxes(g, n, w, h):
     return torch.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1)
 
 
+# 4: x pass on the tensor cores (bf16 maps only: on the fp32 maps of this test it runs the column walk);
 # 2: CTA per ROI, column walk (separable, rows carried in registers); 1: CTA per ROI, merged taps;
 # 0: thread per (bin, 8 channels).  c = 256: a warp is one bin column (the production shape), c = 32: columns share warps
 @pytest.mark.parametrize("c", [32, 256])
-@pytest.mark.parametrize("variant", [3, 2, 1, 0])
+@pytest.mark.parametrize("variant", [4, 3, 2, 1, 0])
 def test_roialign_fpn_matches_torchvision_and_reference_level_rule(variant, c, kernel_variant):
     kernel_variant("ROIALIGN", variant)
     g = torch.Generator().manual_seed(7)
@@ -229,7 +230,7 @@ def test_roialign_fpn_matches_torchvision_and_reference_level_rule(variant, c, k
     assert got[r_cap + counts[1]:].abs().max() == 0                  # invalid slots are zeroed
 
 
-@pytest.mark.parametrize("variant", [3, 2, 1, 0])
+@pytest.mark.parametrize("variant", [4, 3, 2, 1, 0])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_roialign_large_rois_separable_path(dtype, variant, kernel_variant):
     kernel_variant("ROIALIGN", variant)
@@ -269,6 +270,69 @@ def test_roialign_large_rois_separable_path(dtype, variant, kernel_variant):
             tol = 1e-4 if dtype == torch.float32 else 1e-2
             assert torch.allclose(got[slot], ref, rtol=tol, atol=tol), (i, r, li, (got[slot] - ref).abs().max())
     assert got[r_cap + int(counts[1]):].abs().max() == 0
+
+
+@pytest.mark.parametrize("split", [1, 0])
+@pytest.mark.parametrize("stages,minb", [(3, 3), (4, 2)])
+@pytest.mark.parametrize("c,pitched", [(256, False), (256, True), (64, False), (32, False)])
+def test_roialign_tensor_core_x_pass_against_fp32_sampling(c, pitched, stages, minb, split, kernel_variant, monkeypatch):
+    """Variant 4 (mma.sync x pass, bf16 maps) against torchvision's fp32 sampling of the same bf16 values: boxes from 1 pixel
+    to the whole image (tap ranges of one and of several 32-column chunks, more than ROI_MMA_KMAX = 128 columns -> sample
+    loop), boxes that stick out of the image, empty slots; channel-dense (compile-time stride for c = 256) and pitched maps.
+    split = 1 (bf16 hi + lo x weights) has to agree with the fp32 evaluation to the output rounding (bf16, 2^-9 relative:
+    2e-2 on values up to ~4); split = 0 (hi only) carries a 2^-9 weight error on top."""
+    import torchvision
+    kernel_variant("ROIALIGN", 4)
+    monkeypatch.setenv("CM2_ROIALIGN_STAGES", str(stages))
+    monkeypatch.setenv("CM2_ROIALIGN_MINB", str(minb))
+    monkeypatch.setenv("CM2_ROIALIGN_SPLIT", str(split))
+    g = torch.Generator().manual_seed(23 + c)
+    n, r_cap = 2, 40
+    H, W = 512, 1536
+    strides = (8, 16, 32)                                     # P3 = 64 x 192: tap ranges up to the whole row (> 128 columns)
+    feats = [torch.randn(n, c, H // s, W // s, generator=g).to(torch.bfloat16).float() for s in strides]
+    boxes = torch.zeros(n, r_cap, 4)
+    for i in range(n):
+        area = torch.exp(torch.rand(r_cap, generator=g) * (math.log(0.9 * H * W) - math.log(8.0 * 8.0)) + math.log(8.0 * 8.0))
+        ar = torch.exp((torch.rand(r_cap, generator=g) - 0.5) * 3.0)
+        bw, bh = torch.sqrt(area * ar), torch.sqrt(area / ar)
+        cx, cy = torch.rand(r_cap, generator=g) * W, torch.rand(r_cap, generator=g) * H
+        boxes[i] = torch.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1)     # some stick out of the image
+    boxes[0, 0] = torch.tensor([0.0, 0.0, W, H])                        # whole image
+    boxes[0, 1] = torch.tensor([10.0, 10.0, 10.0, 30.0])                # zero area
+    boxes[0, 2] = torch.tensor([3.0, 40.0, W - 5.0, 70.0])              # P3, 191 tap columns: wider than the walk handles
+    boxes[0, 3] = torch.tensor([100.0, 100.0, 101.0, 101.0])            # one pixel: every bin taps the same two rows / columns
+    boxes[0, 4] = torch.tensor([-400.0, -300.0, -100.0, -50.0])         # entirely outside
+    boxes[1, 0] = torch.tensor([200.0, 8.0, 1190.0, 120.0])             # P3, 125 tap columns = four chunks
+    boxes[1, 1] = torch.tensor([W - 60.0, H - 40.0, W + 500.0, H + 300.0])
+    counts = torch.tensor([r_cap, r_cap - 7], dtype=torch.int32)
+    area = torch.tensor([float(H * W)] * n)
+    out = halo(torch.full((n * r_cap, c, 14, 14), 7.0), torch.bfloat16)
+    lvl = torch.full((n * r_cap,), -1, dtype=torch.int32, device=DEV)
+    fm = [halo(f, torch.bfloat16) for f in feats]
+    if pitched:                                               # channel pitch 2 c: the run-time stride instantiation
+        fm = []
+        for f in feats:
+            buf = torch.zeros((n, f.shape[2] + 2, f.shape[3] + 2, 2 * c), dtype=torch.bfloat16, device=DEV)
+            buf[:, 1:-1, 1:-1, :c] = f.permute(0, 2, 3, 1).to(DEV, torch.bfloat16)
+            fm.append(FMap(buf[..., :c], 1))
+    lib.roialign_fpn([f.view for f in fm], list(strides), boxes.to(DEV), counts.to(DEV), n, r_cap, area.to(DEV), 0, 0, out.view, lvl)
+    torch.cuda.synchronize()
+    got = nchw(out.view)
+    lv = lvl.cpu()
+    worst = 0.0
+    for i in range(n):
+        for r in range(int(counts[i])):
+            slot = i * r_cap + r
+            li = int(lv[slot])
+            roi = torch.cat([torch.tensor([float(i)]), boxes[i, r]])[None]
+            ref = torchvision.ops.roi_align(feats[li], roi, 14, 1.0 / strides[li], 0, True)[0]
+            tol = 1e-2 if split else 3e-2
+            assert torch.allclose(got[slot], ref, rtol=tol, atol=tol), (i, r, li, boxes[i, r], (got[slot] - ref).abs().max())
+            worst = max(worst, float((got[slot] - ref).abs().max()))
+    print("variant 4 c={} split={}: max |diff| against fp32 sampling {:.3g}".format(c, split, worst))
+    assert got[r_cap + int(counts[1]):].abs().max() == 0          # empty slots are zeroed
+    assert out.buf[:, 0].abs().max() == 0 and out.buf[:, :, 0].abs().max() == 0          # halo untouched
 
 
 def test_spatial_attention_mask_predict_maskiou_glue():

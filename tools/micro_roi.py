@@ -29,6 +29,9 @@ def main():
     ap.add_argument("--rois", type=int, default=100)
     ap.add_argument("--variants", default="2,1")
     ap.add_argument("--sort", action="store_true", help="boxes of the whole batch in descending area order (tail experiment)")
+    ap.add_argument("--check-only", action="store_true", help="one launch per variant, deviation only (for compute-sanitizer)")
+    ap.add_argument("--mma-configs", default="", help="variant 4 only: comma list of stages:minb:split settings "
+                    "(CM2_ROIALIGN_STAGES / _MINB / _SPLIT), e.g. 3:3:1,4:2:1,3:3:0")
     args = ap.parse_args()
     n, R, dev, c = args.batch, args.rois, "cuda", 256
     hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -59,18 +62,54 @@ def main():
     roialign()
     torch.cuda.synchronize()
     ref = roi.view.float().clone()
+    if args.check_only:
+        for v in [int(t) for t in args.variants.split(",")]:
+            os.environ["CM2_ROIALIGN_VARIANT"] = str(v)
+            roi.view.zero_()
+            roialign()
+            torch.cuda.synchronize()
+            print("variant {}: max|diff vs v0| {:.4g}".format(v, (roi.view.float() - ref).abs().max().item()), flush=True)
+        return
     for _ in range(300):                  # bring the clocks up before anything is timed
         roialign()
     torch.cuda.synchronize()
+    def diagnose(got):
+        """Where a variant leaves variant 0: worst ROI slot, its box / level, the bins and channels that differ."""
+        diff = (got - ref).abs()
+        per_slot = diff.flatten(1).max(1)[0]
+        bad = (per_slot > 0.1).nonzero().flatten()
+        print("  slots off by > 0.1: {} of {}   (first: {})".format(bad.numel(), per_slot.numel(), bad[:8].tolist()))
+        if bad.numel() == 0:
+            return
+        sl = int(per_slot.argmax())
+        b = boxes.view(-1, 4)[sl].tolist()
+        print("  worst slot {} box {} level {} size at level {:.1f} x {:.1f}".format(
+            sl, [round(t, 1) for t in b], int(lvl[sl]), (b[2] - b[0]) / (8 << int(lvl[sl])), (b[3] - b[1]) / (8 << int(lvl[sl]))))
+        d = diff[sl]                                       # [14, 14, c] view of the slot
+        print("  max diff per bin row   :", [round(t, 2) for t in d.flatten(1).max(1)[0].tolist()])
+        print("  max diff per bin column:", [round(t, 2) for t in d.transpose(0, 1).flatten(1).max(1)[0].tolist()])
+        ch = d.flatten(0, 1).max(0)[0]
+        print("  channels off by > 0.1: {} of {} (first: {})".format(int((ch > 0.1).sum()), ch.numel(), (ch > 0.1).nonzero().flatten()[:16].tolist()))
+        print("  got[0, :, 0:4]", got[sl][0, :4, 0:4].flatten().tolist())
+        print("  ref[0, :, 0:4]", ref[sl][0, :4, 0:4].flatten().tolist())
+
+    mma_cfgs = [t.split(":") for t in args.mma_configs.split(",") if t] or [None]
     for rep in range(2):                  # every configuration twice (ABAB) so that drift shows
         for v in [int(t) for t in args.variants.split(",")]:
             os.environ["CM2_ROIALIGN_VARIANT"] = str(v)
-            for k in [""]:
+            for mc in (mma_cfgs if v == 4 else [None]):
+                k = ""
+                if mc is not None:
+                    os.environ["CM2_ROIALIGN_STAGES"], os.environ["CM2_ROIALIGN_MINB"], os.environ["CM2_ROIALIGN_SPLIT"] = mc
+                    k = " (stages {} minb {} split {})".format(*mc)
                 roi.view.zero_()
                 ms = timed(roialign)
-                d = (roi.view.float() - ref).abs().max().item()
-                print("variant {}{}: {:.4f} ms  {:7.1f} GB/s  {:.3f} of HBM peak   max|diff vs v0| {:.4g}".format(
-                    v, k, ms, alg / ms / 1e6, alg / ms / 1e6 / hbm, d))
+                got = roi.view.float()
+                d = (got - ref).abs().max().item()
+                print("variant {}{}: {:.4f} ms  {:7.1f} GB/s  {:.3f} of HBM peak   max|diff vs v0| {:.4g}  mean|diff| {:.3g}".format(
+                    v, k, ms, alg / ms / 1e6, alg / ms / 1e6 / hbm, d, (got - ref).abs().mean().item()), flush=True)
+                if rep == 0 and d > 0.1:
+                    diagnose(got)
 
 
 if __name__ == "__main__":
