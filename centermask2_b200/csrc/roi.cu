@@ -1213,6 +1213,15 @@ __global__ void __launch_bounds__(32 * (ROI_RING_COLS + 1), 2) roialign_ring_ker
 // the MMA accumulators run over the chunks of a row.  ROIs whose tap range exceeds ROI_MMA_KMAX columns or whose rows do not
 // follow each other without a gap use the sample loop.  Non-finite feature values spread over the bin columns of their
 // row chunk (0 * inf in the dense weight matrix) -- the SIMT variants confine them to the bins that tap them.
+// MEASURED (B200, cfg 5: 32 images x 100 ROIs; profiles/r2_roialign_mma.txt, profiles/r2_ncu_roialign_mma_*.txt): 0.285 ms
+// against 0.259 ms of the column walk, which stays the default -- and is the faster one in every box-size class (sides 32-120
+// px: 0.132 vs 0.120 ms, 256-520 px: 0.61 vs 0.51 ms).  Why: the MMAs do 16 / ~2 times the useful multiply-adds (every bin
+// column against every pixel column of a k tile), the staging adds 24 shared-memory wavefronts per k tile (8 copy + 8
+// features + 8 weights; weights in registers when the tap range is one chunk) = 62 % of the LSU data path, and 48 fp32
+// accumulator / carried-row registers per lane allow 16 warps per SM (the column walk: 24), each issuing an instruction
+// every ~12 clocks (tensor pipe 38 % active, issue slots 49 %, no unit saturated: dependent-latency-bound).  Dropping the lo
+// MMAs (SPLIT = false) buys 5 %, a fourth ring stage 2.5 %, register-resident parity buffers instead of the 16 moves per row
+// and both k tiles' fragments loaded up front (124 registers) were 3 % SLOWER.  Kept as a tested alternative.
 // ---------------------------------------------------------------------------------------------
 constexpr int ROI_MMA_M = 16;                            // bin columns of the weight operand (res <= 16)
 constexpr int ROI_MMA_KC = 32;                           // pixel columns per ring item (two k tiles)
@@ -2091,9 +2100,7 @@ static int roialign_launch(const cm2_act* feats, const int32_t* feat_stride, int
     if (variant == 4 && workspace && p.res <= ROI_MMA_M && small && out->c % 32 == 0 && out->c <= 256) {
       const int stages = getenv("CM2_ROIALIGN_STAGES") ? atoi(getenv("CM2_ROIALIGN_STAGES")) : 4;
       const bool split = !(getenv("CM2_ROIALIGN_SPLIT") && atoi(getenv("CM2_ROIALIGN_SPLIT")) == 0);
-      const int minb = getenv("CM2_ROIALIGN_MINB") ? atoi(getenv("CM2_ROIALIGN_MINB")) : 2;
       CM2_CHECK_ARG(stages >= 3 && stages <= 4, "roialign: CM2_ROIALIGN_STAGES %d not in [3,4]", stages);
-      CM2_CHECK_ARG(minb >= 2 && minb <= 3, "roialign: CM2_ROIALIGN_MINB %d not in [2,3]", minb);
       bool sw256 = true;
       for (int l = 0; l < num_levels; ++l) sw256 = sw256 && feats[l].sw == 256;
       const int smem = roi_mma_smem_bytes(out->c, stages);
@@ -2111,11 +2118,7 @@ static int roialign_launch(const cm2_act* feats, const int32_t* feat_stride, int
   do {                                                                                                        \
     if (split) CM2_ROI_MMA_LAUNCH_SW(ST, true, MB); else CM2_ROI_MMA_LAUNCH_SW(ST, false, MB);                \
   } while (0)
-      if (minb == 3) {
-        if (stages == 3) CM2_ROI_MMA_LAUNCH_SP(3, 3); else CM2_ROI_MMA_LAUNCH_SP(4, 3);
-      } else {
-        if (stages == 3) CM2_ROI_MMA_LAUNCH_SP(3, 2); else CM2_ROI_MMA_LAUNCH_SP(4, 2);
-      }
+      if (stages == 3) CM2_ROI_MMA_LAUNCH_SP(3, 2); else CM2_ROI_MMA_LAUNCH_SP(4, 2);
 #undef CM2_ROI_MMA_LAUNCH_SP
 #undef CM2_ROI_MMA_LAUNCH_SW
 #undef CM2_ROI_MMA_LAUNCH

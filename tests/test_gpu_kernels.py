@@ -273,9 +273,9 @@ def test_roialign_large_rois_separable_path(dtype, variant, kernel_variant):
 
 
 @pytest.mark.parametrize("split", [1, 0])
-@pytest.mark.parametrize("stages,minb", [(3, 3), (4, 2)])
+@pytest.mark.parametrize("stages", [3, 4])
 @pytest.mark.parametrize("c,pitched", [(256, False), (256, True), (64, False), (32, False)])
-def test_roialign_tensor_core_x_pass_against_fp32_sampling(c, pitched, stages, minb, split, kernel_variant, monkeypatch):
+def test_roialign_tensor_core_x_pass_against_fp32_sampling(c, pitched, stages, split, kernel_variant, monkeypatch):
     """Variant 4 (mma.sync x pass, bf16 maps) against torchvision's fp32 sampling of the same bf16 values: boxes from 1 pixel
     to the whole image (tap ranges of one and of several 32-column chunks, more than ROI_MMA_KMAX = 128 columns -> sample
     loop), boxes that stick out of the image, empty slots; channel-dense (compile-time stride for c = 256) and pitched maps.
@@ -284,7 +284,6 @@ def test_roialign_tensor_core_x_pass_against_fp32_sampling(c, pitched, stages, m
     import torchvision
     kernel_variant("ROIALIGN", 4)
     monkeypatch.setenv("CM2_ROIALIGN_STAGES", str(stages))
-    monkeypatch.setenv("CM2_ROIALIGN_MINB", str(minb))
     monkeypatch.setenv("CM2_ROIALIGN_SPLIT", str(split))
     g = torch.Generator().manual_seed(23 + c)
     n, r_cap = 2, 40

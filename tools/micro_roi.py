@@ -29,9 +29,11 @@ def main():
     ap.add_argument("--rois", type=int, default=100)
     ap.add_argument("--variants", default="2,1")
     ap.add_argument("--sort", action="store_true", help="boxes of the whole batch in descending area order (tail experiment)")
+    ap.add_argument("--sides", default="", help="lo,hi: box side range in image pixels (sqrt of the area; default 32 .. "
+                    "sqrt(0.9 H W)) -- which box sizes a variant is good at")
     ap.add_argument("--check-only", action="store_true", help="one launch per variant, deviation only (for compute-sanitizer)")
-    ap.add_argument("--mma-configs", default="", help="variant 4 only: comma list of stages:minb:split settings "
-                    "(CM2_ROIALIGN_STAGES / _MINB / _SPLIT), e.g. 3:3:1,4:2:1,3:3:0")
+    ap.add_argument("--mma-configs", default="", help="variant 4 only: comma list of stages:split settings "
+                    "(CM2_ROIALIGN_STAGES / _SPLIT), e.g. 4:1,3:1,4:0")
     args = ap.parse_args()
     n, R, dev, c = args.batch, args.rois, "cuda", 256
     hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -41,7 +43,10 @@ def main():
     feats = [eng.fmap("mf{}".format(i), n, h, w, c) for i, (h, w, _) in enumerate(LEVELS[:3])]
     for f in feats:
         f.view.copy_(torch.randn(f.view.shape, device=dev, generator=g).to(torch.bfloat16))
-    area = torch.exp(torch.rand((n, R), device=dev, generator=g) * (math.log(0.9 * H * W) - math.log(32.0 * 32.0)) + math.log(32.0 * 32.0))
+    a_lo, a_hi = 32.0 * 32.0, 0.9 * H * W
+    if args.sides:
+        a_lo, a_hi = [float(t) ** 2 for t in args.sides.split(",")]
+    area = torch.exp(torch.rand((n, R), device=dev, generator=g) * (math.log(a_hi) - math.log(a_lo)) + math.log(a_lo))
     ar = torch.exp((torch.rand((n, R), device=dev, generator=g) - 0.5) * 1.4)
     bw, bh = torch.sqrt(area * ar).clamp(max=W - 1.0), torch.sqrt(area / ar).clamp(max=H - 1.0)
     x0 = torch.rand((n, R), device=dev, generator=g) * (W - bw)
@@ -100,8 +105,8 @@ def main():
             for mc in (mma_cfgs if v == 4 else [None]):
                 k = ""
                 if mc is not None:
-                    os.environ["CM2_ROIALIGN_STAGES"], os.environ["CM2_ROIALIGN_MINB"], os.environ["CM2_ROIALIGN_SPLIT"] = mc
-                    k = " (stages {} minb {} split {})".format(*mc)
+                    os.environ["CM2_ROIALIGN_STAGES"], os.environ["CM2_ROIALIGN_SPLIT"] = mc
+                    k = " (stages {} split {})".format(*mc)
                 roi.view.zero_()
                 ms = timed(roialign)
                 got = roi.view.float()
