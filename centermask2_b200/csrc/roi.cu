@@ -1219,7 +1219,7 @@ __global__ void __launch_bounds__(32 * (ROI_RING_COLS + 1), 2) roialign_ring_ker
 // column against every pixel column of a k tile), the staging adds 24 shared-memory wavefronts per k tile (8 copy + 8
 // features + 8 weights; weights in registers when the tap range is one chunk) = 62 % of the LSU data path, and 48 fp32
 // accumulator / carried-row registers per lane allow 16 warps per SM (the column walk: 24), each issuing an instruction
-// every ~12 clocks (tensor pipe 38 % active, issue slots 49 %, no unit saturated: dependent-latency-bound).  Dropping the lo
+// every ~8 clocks (tensor pipe 38 % active, issue slots 49 %, no unit saturated: dependent-latency-bound).  Dropping the lo
 // MMAs (SPLIT = false) buys 5 %, a fourth ring stage 2.5 %, register-resident parity buffers instead of the 16 moves per row
 // and both k tiles' fragments loaded up front (124 registers) were 3 % SLOWER.  Kept as a tested alternative.
 // ---------------------------------------------------------------------------------------------
