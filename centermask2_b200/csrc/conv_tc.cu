@@ -29,7 +29,6 @@ namespace cm2 {
 
 constexpr int TC_BM = 128;          // rows per tile (UMMA M)
 constexpr int TC_BK = 64;           // bf16 channels per K-block = 128 bytes = one swizzle row
-constexpr int TC_MAX_THREADS = 320;   // 2 control warps + 8 epilogue warps
 constexpr int TC_ACC_COLS = 256;    // TMEM columns per accumulator stage
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;
 
@@ -1713,10 +1712,6 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
   }
 }
 
-// sources may be channel slices (sw > c); outputs / residuals are whole tensors (sw == c)
-static bool is_halo_view(const cm2_act& a, bool slice_ok = false) {
-  return (slice_ok ? a.sw >= a.c : a.sw == a.c) && a.sh == (long long)(a.w + 2) * a.sw && a.sn == (long long)(a.h + 2) * a.sh;
-}
 // Halo kinds of an interior view: 1 = every image carries its own one-pixel zero frame ([n, h+2, w+2, c] buffer); 2 = SHARED
 // halo: line pitch w + 1 and image pitch (h + 1)(w + 1) pixels -- the zero pixel right of a line is the zero pixel left of the
 // next line, the zero line under an image the zero line above the next image (the buffer ends with one more zero line + pixel;

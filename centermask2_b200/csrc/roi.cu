@@ -2041,8 +2041,8 @@ __global__ void __launch_bounds__(256) paste_fused_kernel(const float* __restric
       const uint32_t bit_step = (uint32_t)pitch * 4u;
       for (int i = i_begin; i < i_end; ++i, row_addr += 16u, bit_addr += bit_step) {
         float wy0, wy1, t0, t1, t2, t3;
-        uint32_t base, pad;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(wy0), "=f"(wy1), "=r"(base), "=r"(pad) : "r"(row_addr) : "memory");
+        uint32_t base;                                    // the fourth word of a row record is padding
+        asm volatile("{\n.reg .b32 pad;\nld.shared.v4.b32 {%0, %1, %2, pad}, [%3];\n}" : "=f"(wy0), "=f"(wy1), "=r"(base) : "r"(row_addr) : "memory");
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t0), "=f"(t1), "=f"(t2), "=f"(t3) : "r"(tap0 + base) : "memory");
         // same accumulation order as ATen's grid_sampler_2d (nw, ne, sw, se); border cells contribute exact zeros
         float v = 0.f;
