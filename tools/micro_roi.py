@@ -31,6 +31,9 @@ def main():
     ap.add_argument("--sort", action="store_true", help="boxes of the whole batch in descending area order (tail experiment)")
     ap.add_argument("--sides", default="", help="lo,hi: box side range in image pixels (sqrt of the area; default 32 .. "
                     "sqrt(0.9 H W)) -- which box sizes a variant is good at")
+    ap.add_argument("--split", default="", help="experiment: comma list of k -- per image the k largest boxes go to one launch "
+                    "and the other R - k to a second launch on a side stream, both inside the timed graph; every pair of "
+                    "variants (large-box launch | small-box launch) out of 2 and 4 is timed (do the two kernels use different units?)")
     ap.add_argument("--check-only", action="store_true", help="one launch per variant, deviation only (for compute-sanitizer)")
     ap.add_argument("--mma-configs", default="", help="variant 4 only: comma list of stages:split settings "
                     "(CM2_ROIALIGN_STAGES / _SPLIT), e.g. 4:1,3:1,4:0")
@@ -78,6 +81,43 @@ def main():
     for _ in range(300):                  # bring the clocks up before anything is timed
         roialign()
     torch.cuda.synchronize()
+    if args.split:
+        order = torch.argsort((bw * bh), dim=1, descending=True)
+        sorted_boxes = torch.gather(boxes, 1, order[:, :, None].expand(-1, -1, 4)).contiguous()
+        side = torch.cuda.Stream()
+        ev0, ev1 = torch.cuda.Event(), torch.cuda.Event()
+        for k in [int(t) for t in args.split.split(",")]:
+            parts = []
+            for lo, hi, tag in ((0, k, "a"), (k, R, "b")):
+                m = hi - lo
+                parts.append((sorted_boxes[:, lo:hi].contiguous(), torch.full((n,), m, dtype=torch.int32, device=dev), m,
+                              eng.fmap("mroi_{}{}".format(tag, k), n * m, 14, 14, c), torch.zeros((n * m,), dtype=torch.int32, device=dev),
+                              torch.empty((n * m + 1024,), dtype=torch.int32, device=dev)))
+
+            def launch(part, variant):
+                bx, cnt, m, out, lv, ws = part
+                os.environ["CM2_ROIALIGN_VARIANT"] = str(variant)
+                lib.roialign_fpn([f.view for f in feats], [8, 16, 32], bx, cnt, n, m, img_area, 0, 0, out.view, lv, ws)
+
+            for va, vb in ((2, 2), (4, 2), (4, 4), (2, 4)):
+                def both():
+                    main = torch.cuda.current_stream()
+                    ev0.record(main)
+                    side.wait_event(ev0)
+                    launch(parts[0], va)
+                    with torch.cuda.stream(side):
+                        launch(parts[1], vb)
+                        ev1.record(side)
+                    main.wait_event(ev1)
+
+                def serial():
+                    launch(parts[0], va)
+                    launch(parts[1], vb)
+                ms_c, ms_s = timed(both), timed(serial)
+                print("split {:3d} largest | {:3d} others: variants {} | {}: concurrent {:.4f} ms   back to back {:.4f} ms".format(
+                    k, R - k, va, vb, ms_c, ms_s), flush=True)
+        return
+
     def diagnose(got):
         """Where a variant leaves variant 0: worst ROI slot, its box / level, the bins and channels that differ."""
         diff = (got - ref).abs()
